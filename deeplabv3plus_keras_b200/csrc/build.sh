@@ -1,0 +1,19 @@
+#!/usr/bin/env bash
+# Build libdlv3p.so for sm_100a, in-tree (the .so travels to the GPU box with the repo snapshot).
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+OUT="${HERE}/../libdlv3p.so"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xptxas -v
+       -I"${HERE}/../../include")
+mkdir -p "${HERE}/build"
+pids=()
+for f in api dwconv eltwise loss gemm_simt gemm_tcgen05; do
+  "${NVCC}" "${FLAGS[@]}" -c "${HERE}/${f}.cu" -o "${HERE}/build/${f}.o" > "${HERE}/build/${f}.log" 2>&1 &
+  pids+=($!)
+done
+rc=0
+for p in "${pids[@]}"; do wait "$p" || rc=1; done
+if [ $rc -ne 0 ]; then cat "${HERE}"/build/*.log | grep -v "^ptxas info" | head -80; exit 1; fi
+"${NVCC}" -shared -o "${OUT}" "${HERE}"/build/*.o -lcudart
+echo "built ${OUT}"

@@ -1,0 +1,391 @@
+// K1 — atrous depthwise 3x3 convolution, forward / input-gradient / filter-gradient, NHWC, sm_100a.
+//
+// Replaces TF DepthwiseConv2dNative(+BackpropInput/+BackpropFilter) as reached from the depthwise half of
+// tf.keras SeparableConv2D (reference call site ss.py:823-830; keras.applications Xception blockN_sepconvM and
+// MobileNetV2 block_k_depthwise).  For dilation > 1 TF 2.4 wraps the op in SpaceToBatchND/BatchToSpaceND — two
+// extra full-tensor copies; here dilation is just an address stride.
+//
+// HBM-bound: algorithmic bytes per launch = (N*H*W*C + N*Ho*Wo*C)*esz + 9*C*4.  Design: one thread owns one
+// 8-channel vector (16 B of bf16, coalesced over the contiguous NHWC channel axis) and a strip of TW output
+// columns; for dense taps (stride 1, dil_w 1) the strip is a sliding window so each output costs (TW+2)*3/TW
+// vector loads from L1 instead of 9, which keeps the L1 wavefront rate under the HBM rate.
+// The optional prologue (BN scale/shift + ReLU/ReLU6 applied to the loaded value, zero padding afterwards)
+// and epilogue (activation-derivative mask + addend) fuse the neighbouring elementwise layers.
+#include "common.cuh"
+
+namespace dlv3p {
+
+template <typename T, int TW, bool DENSE_W, bool HAS_AFFINE, bool HAS_EPI>
+__global__ void __launch_bounds__(256)
+dw_conv_kernel(const T* __restrict__ in, const float* __restrict__ w, T* __restrict__ out, int N, int Hin, int Win,
+               int C, int Hout, int Wout, int stride, int dil_h, int dil_w, int pad_t, int pad_l, int flip,
+               const float* __restrict__ in_scale, const float* __restrict__ in_shift, int in_act,
+               const T* __restrict__ mask_src, const float* __restrict__ m_scale, const float* __restrict__ m_shift,
+               int m_act, const T* __restrict__ addend, long long total) {
+    const int CV = C >> 3;
+    const int WS = (Wout + TW - 1) / TW;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cv = (int)(idx % CV);
+    long long t = idx / CV;
+    const int ws = (int)(t % WS); t /= WS;
+    const int ho = (int)(t % Hout);
+    const int n = (int)(t / Hout);
+    const int c0 = cv << 3;
+    const int wo0 = ws * TW;
+
+    float sc[8], sh[8];
+    if (HAS_AFFINE) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { sc[k] = __ldg(in_scale + c0 + k); sh[k] = __ldg(in_shift + c0 + k); }
+    }
+
+    float acc[TW][8];
+#pragma unroll
+    for (int o = 0; o < TW; ++o)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[o][k] = 0.f;
+
+    const T* in_n = in + (long long)n * Hin * Win * C + c0;
+    constexpr int NCOL = DENSE_W ? (TW + 2) : (3 * TW);
+
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int hi = ho * stride - pad_t + i * dil_h;
+        if (hi < 0 || hi >= Hin) continue;
+        const T* in_row = in_n + (long long)hi * Win * C;
+        // weights of this filter row (flipped for the stride-1 input gradient)
+        float wr[3][8];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int tap = flip ? ((2 - i) * 3 + (2 - j)) : (i * 3 + j);
+            const float4 a = __ldg(reinterpret_cast<const float4*>(w + tap * C + c0));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(w + tap * C + c0) + 1);
+            wr[j][0] = a.x; wr[j][1] = a.y; wr[j][2] = a.z; wr[j][3] = a.w;
+            wr[j][4] = b.x; wr[j][5] = b.y; wr[j][6] = b.z; wr[j][7] = b.w;
+        }
+        Vec8<T> v[NCOL];
+        bool ok[NCOL];
+#pragma unroll
+        for (int q = 0; q < NCOL; ++q) {
+            int wi;
+            if (DENSE_W) wi = wo0 - pad_l + q;
+            else wi = (wo0 + q / 3) * stride - pad_l + (q % 3) * dil_w;
+            ok[q] = (wi >= 0 && wi < Win);
+            if (ok[q]) v[q].load(in_row + (long long)wi * C); else v[q].zero();
+        }
+#pragma unroll
+        for (int q = 0; q < NCOL; ++q) {
+            float f[8];
+            v[q].to_float(f);
+            if (HAS_AFFINE || in_act != DLV3P_ACT_NONE) {
+                if (ok[q]) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        float u = HAS_AFFINE ? fmaf(f[k], sc[k], sh[k]) : f[k];
+                        f[k] = apply_act(u, in_act);
+                    }
+                }
+            }
+            if (DENSE_W) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int o = q - j;
+                    if (o >= 0 && o < TW) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) acc[o][k] = fmaf(f[k], wr[j][k], acc[o][k]);
+                    }
+                }
+            } else {
+                const int o = q / 3, j = q % 3;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[o][k] = fmaf(f[k], wr[j][k], acc[o][k]);
+            }
+        }
+    }
+
+    const long long obase = (((long long)n * Hout + ho) * Wout) * C + c0;
+#pragma unroll
+    for (int o = 0; o < TW; ++o) {
+        const int wo = wo0 + o;
+        if (wo >= Wout) break;
+        const long long off = obase + (long long)wo * C;
+        if (HAS_EPI) {
+            if (mask_src != nullptr && m_act != DLV3P_ACT_NONE) {
+                Vec8<T> mv; mv.load(mask_src + off);
+                float mf[8]; mv.to_float(mf);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float u = mf[k];
+                    if (m_scale != nullptr) u = fmaf(u, __ldg(m_scale + c0 + k), __ldg(m_shift + c0 + k));
+                    acc[o][k] *= act_mask(u, m_act);
+                }
+            }
+            if (addend != nullptr) {
+                Vec8<T> av; av.load(addend + off);
+                float af[8]; av.to_float(af);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[o][k] += af[k];
+            }
+        }
+        Vec8<T> r; r.from_float(acc[o]);
+        r.store(out + off);
+    }
+}
+
+// input gradient for stride > 1 (MobileNetV2 block_1/3/6 depthwise): gather form, one output pixel per thread
+template <typename T>
+__global__ void __launch_bounds__(256)
+dw_dgrad_strided_kernel(const T* __restrict__ dy, const float* __restrict__ w, T* __restrict__ dx, int N, int H,
+                        int W, int C, int Ho, int Wo, int stride, int dil_h, int dil_w, int pad_t, int pad_l,
+                        const T* __restrict__ mask_src, const float* __restrict__ m_scale,
+                        const float* __restrict__ m_shift, int m_act, const T* __restrict__ addend,
+                        long long total) {
+    const int CV = C >> 3;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cv = (int)(idx % CV);
+    long long t = idx / CV;
+    const int wi = (int)(t % W); t /= W;
+    const int hi = (int)(t % H);
+    const int n = (int)(t / H);
+    const int c0 = cv << 3;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int hn = hi + pad_t - i * dil_h;
+        if (hn < 0 || (hn % stride) != 0) continue;
+        const int ho = hn / stride;
+        if (ho >= Ho) continue;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int wn = wi + pad_l - j * dil_w;
+            if (wn < 0 || (wn % stride) != 0) continue;
+            const int wo = wn / stride;
+            if (wo >= Wo) continue;
+            Vec8<T> v; v.load(dy + (((long long)n * Ho + ho) * Wo + wo) * C + c0);
+            float f[8]; v.to_float(f);
+            const float* wp = w + (i * 3 + j) * C + c0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = fmaf(f[k], __ldg(wp + k), acc[k]);
+        }
+    }
+    const long long off = (((long long)n * H + hi) * W + wi) * C + c0;
+    if (mask_src != nullptr && m_act != DLV3P_ACT_NONE) {
+        Vec8<T> mv; mv.load(mask_src + off);
+        float mf[8]; mv.to_float(mf);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float u = mf[k];
+            if (m_scale != nullptr) u = fmaf(u, __ldg(m_scale + c0 + k), __ldg(m_shift + c0 + k));
+            acc[k] *= act_mask(u, m_act);
+        }
+    }
+    if (addend != nullptr) {
+        Vec8<T> av; av.load(addend + off);
+        float af[8]; av.to_float(af);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += af[k];
+    }
+    Vec8<T> r; r.from_float(acc);
+    r.store(dx + off);
+}
+
+// filter gradient: per-channel 9-tap reduction over all N*Ho*Wo output pixels.
+// block = CVB channel-vectors x (256/CVB) pixel lanes; each thread keeps 9x8 fp32 partials in registers,
+// the block reduces them through shared memory and issues one fp32 atomicAdd per (tap, channel).
+template <typename T, int CVB>
+__global__ void __launch_bounds__(256)
+dw_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, int N, int H, int W,
+                int C, int Ho, int Wo, int stride, int dil_h, int dil_w, int pad_t, int pad_l,
+                const float* __restrict__ in_scale, const float* __restrict__ in_shift, int in_act,
+                long long npix, long long pix_per_block) {
+    constexpr int PL = 256 / CVB;
+    const int CV = C >> 3;
+    const int tx = threadIdx.x % CVB;
+    const int ty = threadIdx.x / CVB;
+    const int cv = blockIdx.x * CVB + tx;
+    const bool active = cv < CV;
+    const int c0 = cv << 3;
+
+    float acc[9][8];
+#pragma unroll
+    for (int a = 0; a < 9; ++a)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[a][k] = 0.f;
+
+    float sc[8], sh[8];
+    const bool affine = (in_scale != nullptr);
+    if (active && affine) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { sc[k] = __ldg(in_scale + c0 + k); sh[k] = __ldg(in_shift + c0 + k); }
+    }
+
+    const long long p_begin = (long long)blockIdx.y * pix_per_block;
+    long long p_end = p_begin + pix_per_block;
+    if (p_end > npix) p_end = npix;
+    if (active) {
+        for (long long p = p_begin + ty; p < p_end; p += PL) {
+            const int wo = (int)(p % Wo);
+            long long t = p / Wo;
+            const int ho = (int)(t % Ho);
+            const int n = (int)(t / Ho);
+            Vec8<T> g; g.load_stream(dy + p * C + c0);
+            float gf[8]; g.to_float(gf);
+            const T* xn = x + (long long)n * H * W * C + c0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int hi = ho * stride - pad_t + i * dil_h;
+                if (hi < 0 || hi >= H) continue;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int wi = wo * stride - pad_l + j * dil_w;
+                    if (wi < 0 || wi >= W) continue;
+                    Vec8<T> v; v.load(xn + ((long long)hi * W + wi) * C);
+                    float f[8]; v.to_float(f);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        float u = affine ? fmaf(f[k], sc[k], sh[k]) : f[k];
+                        u = apply_act(u, in_act);
+                        acc[i * 3 + j][k] = fmaf(u, gf[k], acc[i * 3 + j][k]);
+                    }
+                }
+            }
+        }
+    }
+    __shared__ float red[PL][CVB][8];
+#pragma unroll
+    for (int a = 0; a < 9; ++a) {
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) red[ty][tx][k] = acc[a][k];
+        __syncthreads();
+        // CVB*8 channel sums, 256 threads: thread t sums column (t % (CVB*8)) when t < CVB*8
+        for (int col = threadIdx.x; col < CVB * 8; col += 256) {
+            const int cx = col >> 3, k = col & 7;
+            const int cvv = blockIdx.x * CVB + cx;
+            if (cvv < CV) {
+                float s = 0.f;
+#pragma unroll
+                for (int r = 0; r < PL; ++r) s += red[r][cx][k];
+                atomicAdd(dw + a * C + (cvv << 3) + k, s);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool HAS_AFFINE, bool HAS_EPI>
+static int launch_dw_conv(const T* in, const float* w, T* out, int N, int Hin, int Win, int C, int Hout, int Wout,
+                          int stride, int dil_h, int dil_w, int pad_t, int pad_l, int flip, const float* in_scale,
+                          const float* in_shift, int in_act, const T* mask_src, const float* m_scale,
+                          const float* m_shift, int m_act, const T* addend, cudaStream_t st) {
+    const int CV = C / 8;
+    const bool dense = (stride == 1 && dil_w == 1);
+    if (dense) {
+        constexpr int TW = 4;
+        const long long total = (long long)N * Hout * ((Wout + TW - 1) / TW) * CV;
+        dw_conv_kernel<T, TW, true, HAS_AFFINE, HAS_EPI><<<cdiv(total, 256), 256, 0, st>>>(
+            in, w, out, N, Hin, Win, C, Hout, Wout, stride, dil_h, dil_w, pad_t, pad_l, flip, in_scale, in_shift,
+            in_act, mask_src, m_scale, m_shift, m_act, addend, total);
+    } else {
+        constexpr int TW = 2;
+        const long long total = (long long)N * Hout * ((Wout + TW - 1) / TW) * CV;
+        dw_conv_kernel<T, TW, false, HAS_AFFINE, HAS_EPI><<<cdiv(total, 256), 256, 0, st>>>(
+            in, w, out, N, Hin, Win, C, Hout, Wout, stride, dil_h, dil_w, pad_t, pad_l, flip, in_scale, in_shift,
+            in_act, mask_src, m_scale, m_shift, m_act, addend, total);
+    }
+    return check_launch("dwconv3x3");
+}
+
+static int check_dw_args(const void* a, const void* b, const void* c, int N, int H, int W, int C, int stride,
+                         int dil_h, int dil_w, int Ho, int Wo) {
+    DLV3P_REQUIRE(a && b && c, DLV3P_ERR_SHAPE, "dwconv3x3: null pointer");
+    DLV3P_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && Ho > 0 && Wo > 0, DLV3P_ERR_SHAPE,
+                  "dwconv3x3: non-positive extent N=%d H=%d W=%d C=%d Ho=%d Wo=%d", N, H, W, C, Ho, Wo);
+    DLV3P_REQUIRE(C % 8 == 0, DLV3P_ERR_SHAPE, "dwconv3x3: C=%d must be a multiple of 8", C);
+    DLV3P_REQUIRE(stride >= 1 && stride <= 2 && dil_h >= 1 && dil_w >= 1, DLV3P_ERR_SHAPE,
+                  "dwconv3x3: stride=%d dil=(%d,%d) unsupported", stride, dil_h, dil_w);
+    DLV3P_REQUIRE(aligned16(a) && aligned16(c), DLV3P_ERR_ALIGN, "dwconv3x3: tensors must be 16-byte aligned");
+    DLV3P_REQUIRE(aligned16(b), DLV3P_ERR_ALIGN, "dwconv3x3: filter must be 16-byte aligned");
+    return 0;
+}
+
+}  // namespace dlv3p
+
+using namespace dlv3p;
+
+extern "C" int dlv3p_dwconv3x3_fwd(const void* x, const float* w, void* y, int N, int H, int W, int C, int stride,
+                                   int dil_h, int dil_w, int pad_t, int pad_l, int Ho, int Wo,
+                                   const float* in_scale, const float* in_shift, int in_act, int dtype,
+                                   void* stream) {
+    int rc = check_dw_args(x, w, y, N, H, W, C, stride, dil_h, dil_w, Ho, Wo);
+    if (rc) return rc;
+    DLV3P_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), DLV3P_ERR_SHAPE,
+                  "dwconv3x3_fwd: in_scale and in_shift must both be given or both be NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    DLV3P_DISPATCH_DTYPE(dtype, T, {
+        if (in_scale)
+            return launch_dw_conv<T, true, false>((const T*)x, w, (T*)y, N, H, W, C, Ho, Wo, stride, dil_h, dil_w,
+                                                  pad_t, pad_l, 0, in_scale, in_shift, in_act, nullptr, nullptr,
+                                                  nullptr, 0, nullptr, st);
+        return launch_dw_conv<T, false, false>((const T*)x, w, (T*)y, N, H, W, C, Ho, Wo, stride, dil_h, dil_w,
+                                               pad_t, pad_l, 0, nullptr, nullptr, in_act, nullptr, nullptr,
+                                               nullptr, 0, nullptr, st);
+    });
+    return 0;
+}
+
+extern "C" int dlv3p_dwconv3x3_dgrad(const void* dy, const float* w, void* dx, int N, int H, int W, int C,
+                                     int stride, int dil_h, int dil_w, int pad_t, int pad_l, int Ho, int Wo,
+                                     const void* x_pre, const float* in_scale, const float* in_shift, int in_act,
+                                     const void* addend, int dtype, void* stream) {
+    int rc = check_dw_args(dy, w, dx, N, H, W, C, stride, dil_h, dil_w, Ho, Wo);
+    if (rc) return rc;
+    DLV3P_REQUIRE(in_act == DLV3P_ACT_NONE || x_pre != nullptr, DLV3P_ERR_SHAPE,
+                  "dwconv3x3_dgrad: x_pre required when in_act != NONE");
+    cudaStream_t st = (cudaStream_t)stream;
+    DLV3P_DISPATCH_DTYPE(dtype, T, {
+        if (stride == 1) {
+            // conv-transpose of a stride-1 conv = conv with flipped taps and complementary padding
+            return launch_dw_conv<T, false, true>((const T*)dy, w, (T*)dx, N, Ho, Wo, C, H, W, 1, dil_h, dil_w,
+                                                  2 * dil_h - pad_t, 2 * dil_w - pad_l, 1, nullptr, nullptr,
+                                                  DLV3P_ACT_NONE, (const T*)x_pre, in_scale, in_shift, in_act,
+                                                  (const T*)addend, st);
+        }
+        const long long total = (long long)N * H * W * (C / 8);
+        dw_dgrad_strided_kernel<T><<<cdiv(total, 256), 256, 0, st>>>(
+            (const T*)dy, w, (T*)dx, N, H, W, C, Ho, Wo, stride, dil_h, dil_w, pad_t, pad_l, (const T*)x_pre,
+            in_scale, in_shift, in_act, (const T*)addend, total);
+        return check_launch("dwconv3x3_dgrad");
+    });
+    return 0;
+}
+
+extern "C" int dlv3p_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int C,
+                                     int stride, int dil_h, int dil_w, int pad_t, int pad_l, int Ho, int Wo,
+                                     const float* in_scale, const float* in_shift, int in_act, int dtype,
+                                     void* stream) {
+    int rc = check_dw_args(x, dw, dy, N, H, W, C, stride, dil_h, dil_w, Ho, Wo);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int CV = C / 8;
+    const long long npix = (long long)N * Ho * Wo;
+    DLV3P_DISPATCH_DTYPE(dtype, T, {
+        pick_cvb(CV, [&](auto cvb) {
+            constexpr int CVB = decltype(cvb)::value;
+            constexpr int PL = 256 / CVB;
+            const int gx = cdiv(CV, CVB);
+            long long want = (long long)kNumSMs * 6 / gx; if (want < 1) want = 1;
+            long long ppb = (npix + want - 1) / want; ppb = ((ppb + PL - 1) / PL) * PL; if (ppb < PL) ppb = PL;
+            const int gy = cdiv(npix, ppb);
+            dw_wgrad_kernel<T, CVB><<<dim3(gx, gy), 256, 0, st>>>((const T*)x, (const T*)dy, dw, N, H, W, C, Ho, Wo,
+                                                                  stride, dil_h, dil_w, pad_t, pad_l, in_scale,
+                                                                  in_shift, in_act, npix, ppb);
+        });
+        return check_launch("dwconv3x3_wgrad");
+    });
+    return 0;
+}

@@ -1,0 +1,1077 @@
+// K3 (part 1) — memory-bound kernels around the convolutions: BatchNormalization statistics / apply /
+// backward, activation, add, concat slices, pooling, bilinear resize, im2col, dropout, Adam.
+// Every kernel moves each byte once; algorithmic bytes are listed per entry point in DESIGN.md.
+#include "common.cuh"
+
+namespace dlv3p {
+
+// ------------------------------------------------------------------------------------------------
+// column reductions over a row-major [M,C] matrix (BN statistics and BN backward reductions)
+// block = CVB channel-packs x PL row lanes; fp32 partials; one atomicAdd per (quantity, channel) per block.
+// ------------------------------------------------------------------------------------------------
+template <int CVB>
+__device__ __forceinline__ void block_col_reduce_2x8(float (&q0)[8], float (&q1)[8], float* __restrict__ out0,
+                                                     float* __restrict__ out1, int cv_base, int CV) {
+    constexpr int PL = 256 / CVB;
+    __shared__ float red[2][PL][CVB][8];
+    const int tx = threadIdx.x % CVB, ty = threadIdx.x / CVB;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { red[0][ty][tx][k] = q0[k]; red[1][ty][tx][k] = q1[k]; }
+    __syncthreads();
+    for (int col = threadIdx.x; col < 2 * CVB * 8; col += 256) {
+        const int which = col / (CVB * 8);
+        const int r = col % (CVB * 8);
+        const int cx = r >> 3, k = r & 7;
+        const int cv = cv_base + cx;
+        if (cv < CV) {
+            float s = 0.f;
+#pragma unroll
+            for (int p = 0; p < PL; ++p) s += red[which][p][cx][k];
+            atomicAdd((which ? out1 : out0) + (cv << 3) + k, s);
+        }
+    }
+}
+
+template <typename T, int CVB>
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const T* __restrict__ y, long long ld, long long M, int C, float* __restrict__ sums,
+                long long rows_per_block) {
+    constexpr int PL = 256 / CVB;
+    const int CV = C >> 3;
+    const int tx = threadIdx.x % CVB, ty = threadIdx.x / CVB;
+    const int cv = blockIdx.x * CVB + tx;
+    float s1[8], s2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    long long r1 = r0 + rows_per_block; if (r1 > M) r1 = M;
+    if (cv < CV) {
+        const T* p = y + (cv << 3);
+        long long r = r0 + ty;
+        // two rows in flight per iteration
+        for (; r + PL < r1; r += 2 * PL) {
+            Vec8<T> a, b; a.load_stream(p + r * ld); b.load_stream(p + (r + PL) * ld);
+            float fa[8], fb[8]; a.to_float(fa); b.to_float(fb);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                s1[k] += fa[k] + fb[k];
+                s2[k] = fmaf(fa[k], fa[k], s2[k]); s2[k] = fmaf(fb[k], fb[k], s2[k]);
+            }
+        }
+        for (; r < r1; r += PL) {
+            Vec8<T> a; a.load_stream(p + r * ld);
+            float fa[8]; a.to_float(fa);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { s1[k] += fa[k]; s2[k] = fmaf(fa[k], fa[k], s2[k]); }
+        }
+    }
+    block_col_reduce_2x8<CVB>(s1, s2, sums, sums + C, blockIdx.x * CVB, CV);
+}
+
+template <typename T, int CVB>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const T* __restrict__ dz, long long ld_dz, const T* __restrict__ y, long long ld_y,
+                     const float* __restrict__ scale, const float* __restrict__ shift,
+                     const float* __restrict__ mean, const float* __restrict__ invstd, int act, long long M, int C,
+                     float* __restrict__ red, long long rows_per_block) {
+    constexpr int PL = 256 / CVB;
+    const int CV = C >> 3;
+    const int tx = threadIdx.x % CVB, ty = threadIdx.x / CVB;
+    const int cv = blockIdx.x * CVB + tx;
+    float s1[8], s2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    long long r1 = r0 + rows_per_block; if (r1 > M) r1 = M;
+    if (cv < CV) {
+        const int c0 = cv << 3;
+        float sc[8], sh[8], mu[8], is[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            sc[k] = __ldg(scale + c0 + k); sh[k] = __ldg(shift + c0 + k);
+            mu[k] = __ldg(mean + c0 + k); is[k] = __ldg(invstd + c0 + k);
+        }
+        for (long long r = r0 + ty; r < r1; r += PL) {
+            Vec8<T> a, b; a.load_stream(dz + r * ld_dz + c0); b.load_stream(y + r * ld_y + c0);
+            float g[8], v[8]; a.to_float(g); b.to_float(v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float gg = g[k] * act_mask(fmaf(v[k], sc[k], sh[k]), act);
+                s1[k] += gg;
+                s2[k] = fmaf(gg, (v[k] - mu[k]) * is[k], s2[k]);
+            }
+        }
+    }
+    block_col_reduce_2x8<CVB>(s1, s2, red, red + C, blockIdx.x * CVB, CV);
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ moving_mean,
+                                   float* __restrict__ moving_var, int C, double count, float eps, float momentum,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean,
+                                   float* __restrict__ invstd, int update_moving) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    // the two sums are fp32; finish in fp64 so that E[x^2]-E[x]^2 does not lose more than the sums already did
+    const double m = (double)sums[c] / count;
+    double var = (double)sums[C + c] / count - m * m;
+    if (var < 0.0) var = 0.0;
+    const float is = (float)(1.0 / sqrt(var + (double)eps));
+    const float g = gamma ? gamma[c] : 1.f;
+    const float b = beta ? beta[c] : 0.f;
+    const float s = g * is;
+    scale[c] = s;
+    shift[c] = b - (float)m * s;
+    mean[c] = (float)m;
+    invstd[c] = is;
+    if (update_moving) {
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        moving_mean[c] = momentum * moving_mean[c] + (1.f - momentum) * (float)m;
+        moving_var[c] = momentum * moving_var[c] + (1.f - momentum) * (float)unbiased;
+    }
+}
+
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mm, const float* __restrict__ mv, int C, float eps,
+                               float* __restrict__ scale, float* __restrict__ shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float s = (gamma ? gamma[c] : 1.f) / sqrtf(mv[c] + eps);
+    scale[c] = s;
+    shift[c] = (beta ? beta[c] : 0.f) - mm[c] * s;
+}
+
+// out = act(scale*y+shift) (+addend)
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+affine_act_kernel(const T* __restrict__ y, long long ld_y, const float* __restrict__ scale,
+                  const float* __restrict__ shift, int act, const T* __restrict__ addend, long long ld_a,
+                  T* __restrict__ out, long long ld_o, long long M, int C) {
+    const int CV = C / V;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * CV) return;
+    const int c0 = (int)(idx % CV) * V;
+    const long long r = idx / CV;
+    Pack<T, V> a; a.load(y + r * ld_y + c0);
+    float f[V]; a.to_float(f);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        float u = f[k];
+        if (scale != nullptr) u = fmaf(u, __ldg(scale + c0 + k), __ldg(shift + c0 + k));
+        f[k] = apply_act(u, act);
+    }
+    if (addend != nullptr) {
+        Pack<T, V> b; b.load(addend + r * ld_a + c0);
+        float g[V]; b.to_float(g);
+#pragma unroll
+        for (int k = 0; k < V; ++k) f[k] += g[k];
+    }
+    Pack<T, V> o; o.from_float(f);
+    o.store(out + r * ld_o + c0);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const T* __restrict__ dz, long long ld_dz, const T* __restrict__ y, long long ld_y,
+                    const float* __restrict__ scale, const float* __restrict__ shift,
+                    const float* __restrict__ mean, const float* __restrict__ invstd, int act,
+                    const float* __restrict__ red, long long M, int C, T* __restrict__ dy, long long ld_dy) {
+    const int CV = C >> 3;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * CV) return;
+    const int c0 = (int)(idx % CV) << 3;
+    const long long r = idx / CV;
+    Vec8<T> a, b; a.load_stream(dz + r * ld_dz + c0); b.load_stream(y + r * ld_y + c0);
+    float g[8], v[8]; a.to_float(g); b.to_float(v);
+    const float invM = 1.f / (float)M;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float sc = __ldg(scale + c0 + k);
+        const float gg = g[k] * act_mask(fmaf(v[k], sc, __ldg(shift + c0 + k)), act);
+        if (mean != nullptr) {
+            const float xh = (v[k] - __ldg(mean + c0 + k)) * __ldg(invstd + c0 + k);
+            g[k] = sc * (gg - __ldg(red + c0 + k) * invM - xh * __ldg(red + C + c0 + k) * invM);
+        } else {
+            g[k] = sc * gg;
+        }
+    }
+    Vec8<T> o; o.from_float(g);
+    o.store(dy + r * ld_dy + c0);
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx, int act,
+               const T* __restrict__ addend, long long n) {
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V;
+    if (i >= n) return;
+    Pack<T, V> a, b; a.load(dy + i); b.load(x + i);
+    float g[V], v[V]; a.to_float(g); b.to_float(v);
+#pragma unroll
+    for (int k = 0; k < V; ++k) g[k] *= act_mask(v[k], act);
+    if (addend != nullptr) {
+        Pack<T, V> c; c.load(addend + i);
+        float h[V]; c.to_float(h);
+#pragma unroll
+        for (int k = 0; k < V; ++k) g[k] += h[k];
+    }
+    Pack<T, V> o; o.from_float(g);
+    o.store(dx + i);
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long long n) {
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V;
+    if (i >= n) return;
+    Pack<T, V> pa, pb; pa.load(a + i); pb.load(b + i);
+    float fa[V], fb[V]; pa.to_float(fa); pb.to_float(fb);
+#pragma unroll
+    for (int k = 0; k < V; ++k) fa[k] += fb[k];
+    Pack<T, V> o; o.from_float(fa);
+    o.store(out + i);
+}
+
+// ---- pooling -----------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restrict__ argmax, int N, int H,
+                        int W, int C, int pad_t, int pad_l, int Ho, int Wo, const T* __restrict__ addend,
+                        long long total) {
+    const int CV = C >> 3;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c0 = (int)(idx % CV) << 3;
+    long long t = idx / CV;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    float best[8]; int arg[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { best[k] = -INFINITY; arg[k] = 0; }
+    bool first = true;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int hi = ho * 2 - pad_t + i;
+        if (hi < 0 || hi >= H) continue;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int wi = wo * 2 - pad_l + j;
+            if (wi < 0 || wi >= W) continue;
+            Vec8<T> v; v.load(x + (((long long)n * H + hi) * W + wi) * C + c0);
+            float f[8]; v.to_float(f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (first || f[k] > best[k]) { best[k] = f[k]; arg[k] = i * 3 + j; }
+            }
+            first = false;
+        }
+    }
+    const long long off = (((long long)n * Ho + ho) * Wo + wo) * C + c0;
+    if (argmax != nullptr) {
+        uint2 pk;
+        pk.x = (uint32_t)arg[0] | ((uint32_t)arg[1] << 8) | ((uint32_t)arg[2] << 16) | ((uint32_t)arg[3] << 24);
+        pk.y = (uint32_t)arg[4] | ((uint32_t)arg[5] << 8) | ((uint32_t)arg[6] << 16) | ((uint32_t)arg[7] << 24);
+        *reinterpret_cast<uint2*>(argmax + off) = pk;
+    }
+    if (addend != nullptr) {
+        Vec8<T> a; a.load(addend + off);
+        float g[8]; a.to_float(g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) best[k] += g[k];
+    }
+    Vec8<T> o; o.from_float(best);
+    o.store(y + off);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ argmax, T* __restrict__ dx, int N,
+                        int H, int W, int C, int pad_t, int pad_l, int Ho, int Wo, const T* __restrict__ addend,
+                        long long total) {
+    const int CV = C >> 3;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c0 = (int)(idx % CV) << 3;
+    long long t = idx / CV;
+    const int wi = (int)(t % W); t /= W;
+    const int hi = (int)(t % H);
+    const int n = (int)(t / H);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int hn = hi + pad_t - i;
+        if (hn < 0 || (hn & 1)) continue;
+        const int ho = hn >> 1;
+        if (ho >= Ho) continue;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int wn = wi + pad_l - j;
+            if (wn < 0 || (wn & 1)) continue;
+            const int wo = wn >> 1;
+            if (wo >= Wo) continue;
+            const long long off = (((long long)n * Ho + ho) * Wo + wo) * C + c0;
+            const uint2 pk = __ldg(reinterpret_cast<const uint2*>(argmax + off));
+            Vec8<T> g; g.load(dy + off);
+            float gf[8]; g.to_float(gf);
+            const uint32_t tap = (uint32_t)(i * 3 + j);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t a = ((k < 4 ? pk.x : pk.y) >> (8 * (k & 3))) & 0xffu;
+                if (a == tap) acc[k] += gf[k];
+            }
+        }
+    }
+    const long long off = (((long long)n * H + hi) * W + wi) * C + c0;
+    if (addend != nullptr) {
+        Vec8<T> a; a.load(addend + off);
+        float g[8]; a.to_float(g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += g[k];
+    }
+    Vec8<T> o; o.from_float(acc);
+    o.store(dx + off);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+avgpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int k, int Ho, int Wo,
+                   long long total) {
+    const int CV = C >> 3;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c0 = (int)(idx % CV) << 3;
+    long long t = idx / CV;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    for (int i = 0; i < k; ++i)
+        for (int j = 0; j < k; ++j) {
+            Vec8<T> v; v.load(x + (((long long)n * H + ho * k + i) * W + wo * k + j) * C + c0);
+            float f[8]; v.to_float(f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] += f[q];
+        }
+    const float inv = 1.f / (float)(k * k);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] *= inv;
+    Vec8<T> o; o.from_float(acc);
+    o.store(y + (((long long)n * Ho + ho) * Wo + wo) * C + c0);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+avgpool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int N, int H, int W, int C, int k, int Ho, int Wo,
+                   const T* __restrict__ addend, long long total) {
+    const int CV = C >> 3;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c0 = (int)(idx % CV) << 3;
+    long long t = idx / CV;
+    const int wi = (int)(t % W); t /= W;
+    const int hi = (int)(t % H);
+    const int n = (int)(t / H);
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    const int ho = hi / k, wo = wi / k;
+    if (ho < Ho && wo < Wo) {
+        Vec8<T> v; v.load(dy + (((long long)n * Ho + ho) * Wo + wo) * C + c0);
+        v.to_float(acc);
+        const float inv = 1.f / (float)(k * k);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] *= inv;
+    }
+    const long long off = (((long long)n * H + hi) * W + wi) * C + c0;
+    if (addend != nullptr) {
+        Vec8<T> a; a.load(addend + off);
+        float g[8]; a.to_float(g);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] += g[q];
+    }
+    Vec8<T> o; o.from_float(acc);
+    o.store(dx + off);
+}
+
+// ---- bilinear resize, TF ResizeBilinear(half_pixel_centers=True), integer factors --------------------------
+__device__ __forceinline__ void hp_src(int o, float inv_f, int in_size, int& lo, int& hi, float& lerp) {
+    const float in = ((float)o + 0.5f) * inv_f - 0.5f;
+    const float fl = floorf(in);
+    lo = max((int)fl, 0);
+    hi = min((int)ceilf(in), in_size - 1);
+    lerp = in - fl;
+}
+
+template <typename TI, typename TO, int V>
+__global__ void __launch_bounds__(256)
+bilinear_fwd_kernel(const TI* __restrict__ x, long long ld_x, TO* __restrict__ y, long long ld_y, int N, int H,
+                    int W, int C, int fh, int fw, long long total) {
+    const int CV = C / V;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c0 = (int)(idx % CV) * V;
+    long long t = idx / CV;
+    const int Wo = W * fw, Ho = H * fh;
+    const int xo = (int)(t % Wo); t /= Wo;
+    const int yo = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    int y0, y1, x0, x1; float ly, lx;
+    hp_src(yo, 1.f / (float)fh, H, y0, y1, ly);
+    hp_src(xo, 1.f / (float)fw, W, x0, x1, lx);
+    const long long b = (long long)n * H * W;
+    Pack<TI, V> ptl, ptr, pbl, pbr;
+    ptl.load(x + (b + (long long)y0 * W + x0) * ld_x + c0);
+    ptr.load(x + (b + (long long)y0 * W + x1) * ld_x + c0);
+    pbl.load(x + (b + (long long)y1 * W + x0) * ld_x + c0);
+    pbr.load(x + (b + (long long)y1 * W + x1) * ld_x + c0);
+    float tl[V], tr[V], bl[V], br[V];
+    ptl.to_float(tl); ptr.to_float(tr); pbl.to_float(bl); pbr.to_float(br);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        const float top = tl[k] + (tr[k] - tl[k]) * lx;
+        const float bot = bl[k] + (br[k] - bl[k]) * lx;
+        tl[k] = top + (bot - top) * ly;
+    }
+    Pack<TO, V> o; o.from_float(tl);
+    o.store(y + (((long long)n * Ho + yo) * Wo + xo) * ld_y + c0);
+}
+
+// gather form of the transpose: each input pixel sums the output pixels whose 2x2 footprint contains it
+template <typename TI, typename TO, int V>
+__global__ void __launch_bounds__(256)
+bilinear_bwd_kernel(const TI* __restrict__ dy, long long ld_dy, TO* __restrict__ dx, long long ld_dx, int N, int H,
+                    int W, int C, int fh, int fw, const TO* __restrict__ addend, long long total) {
+    const int CV = C / V;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c0 = (int)(idx % CV) * V;
+    long long t = idx / CV;
+    const int wi = (int)(t % W); t /= W;
+    const int hi = (int)(t % H);
+    const int n = (int)(t / H);
+    const int Wo = W * fw, Ho = H * fh;
+    float acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.f;
+    const int ya = max(0, fh * hi - fh / 2 - 1), yb = min(Ho, fh * hi + (3 * fh) / 2 + 2);
+    const int xa = max(0, fw * wi - fw / 2 - 1), xb = min(Wo, fw * wi + (3 * fw) / 2 + 2);
+    for (int yo = ya; yo < yb; ++yo) {
+        int y0, y1; float ly;
+        hp_src(yo, 1.f / (float)fh, H, y0, y1, ly);
+        float wy = 0.f;
+        if (y0 == hi) wy += 1.f - ly;
+        if (y1 == hi) wy += ly;
+        if (wy == 0.f) continue;
+        for (int xo = xa; xo < xb; ++xo) {
+            int x0, x1; float lx;
+            hp_src(xo, 1.f / (float)fw, W, x0, x1, lx);
+            float wx = 0.f;
+            if (x0 == wi) wx += 1.f - lx;
+            if (x1 == wi) wx += lx;
+            if (wx == 0.f) continue;
+            Pack<TI, V> g; g.load(dy + (((long long)n * Ho + yo) * Wo + xo) * ld_dy + c0);
+            float gf[V]; g.to_float(gf);
+            const float wgt = wy * wx;
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] = fmaf(gf[k], wgt, acc[k]);
+        }
+    }
+    const long long off = (((long long)n * H + hi) * W + wi) * ld_dx + c0;
+    if (addend != nullptr) {
+        Pack<TO, V> a; a.load(addend + off);
+        float g[V]; a.to_float(g);
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] += g[k];
+    }
+    Pack<TO, V> o; o.from_float(acc);
+    o.store(dx + off);
+}
+
+// ---- im2col / col2im / subsample ----------------------------------------------------------------------------
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+im2col3x3_kernel(const T* __restrict__ x, T* __restrict__ col, int N, int H, int W, int C, int stride, int dil,
+                 int pad_t, int pad_l, int Ho, int Wo, long long ld_col, long long total) {
+    const int JV = (int)(ld_col / V);
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int j0 = (int)(idx % JV) * V;
+    long long p = idx / JV;
+    T* dst = col + p * ld_col + j0;
+    float f[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) f[k] = 0.f;
+    Pack<T, V> o; o.from_float(f);
+    if (j0 < 9 * C) {
+        const int tap = j0 / C, c = j0 % C;
+        const int wo = (int)(p % Wo); long long t = p / Wo;
+        const int ho = (int)(t % Ho);
+        const int n = (int)(t / Ho);
+        const int hi = ho * stride - pad_t + (tap / 3) * dil;
+        const int wi = wo * stride - pad_l + (tap % 3) * dil;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) o.load(x + (((long long)n * H + hi) * W + wi) * C + c);
+    }
+    o.store(dst);
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+col2im3x3_kernel(const T* __restrict__ col, T* __restrict__ dx, int N, int H, int W, int C, int stride, int dil,
+                 int pad_t, int pad_l, int Ho, int Wo, long long ld_col, const T* __restrict__ addend,
+                 long long total) {
+    const int CV = C / V;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c0 = (int)(idx % CV) * V;
+    long long t = idx / CV;
+    const int wi = (int)(t % W); t /= W;
+    const int hi = (int)(t % H);
+    const int n = (int)(t / H);
+    float acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int hn = hi + pad_t - i * dil;
+        if (hn < 0 || (hn % stride) != 0) continue;
+        const int ho = hn / stride;
+        if (ho >= Ho) continue;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int wn = wi + pad_l - j * dil;
+            if (wn < 0 || (wn % stride) != 0) continue;
+            const int wo = wn / stride;
+            if (wo >= Wo) continue;
+            Pack<T, V> g; g.load(col + (((long long)n * Ho + ho) * Wo + wo) * ld_col + (i * 3 + j) * C + c0);
+            float gf[V]; g.to_float(gf);
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] += gf[k];
+        }
+    }
+    const long long off = (((long long)n * H + hi) * W + wi) * C + c0;
+    if (addend != nullptr) {
+        Pack<T, V> a; a.load(addend + off);
+        float g[V]; a.to_float(g);
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] += g[k];
+    }
+    Pack<T, V> o; o.from_float(acc);
+    o.store(dx + off);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+subsample_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int stride, int Ho,
+                     int Wo, long long total) {
+    const int CV = C >> 3;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c0 = (int)(idx % CV) << 3;
+    long long t = idx / CV;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    Vec8<T> v; v.load(x + (((long long)n * H + ho * stride) * W + wo * stride) * C + c0);
+    v.store(y + (((long long)n * Ho + ho) * Wo + wo) * C + c0);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+subsample_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int N, int H, int W, int C, int stride, int Ho,
+                     int Wo, const T* __restrict__ addend, long long total) {
+    const int CV = C >> 3;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c0 = (int)(idx % CV) << 3;
+    long long t = idx / CV;
+    const int wi = (int)(t % W); t /= W;
+    const int hi = (int)(t % H);
+    const int n = (int)(t / H);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    if ((hi % stride) == 0 && (wi % stride) == 0 && hi / stride < Ho && wi / stride < Wo) {
+        Vec8<T> v; v.load(dy + (((long long)n * Ho + hi / stride) * Wo + wi / stride) * C + c0);
+        v.to_float(acc);
+    }
+    const long long off = (((long long)n * H + hi) * W + wi) * C + c0;
+    if (addend != nullptr) {
+        Vec8<T> a; a.load(addend + off);
+        float g[8]; a.to_float(g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += g[k];
+    }
+    Vec8<T> o; o.from_float(acc);
+    o.store(dx + off);
+}
+
+__global__ void __launch_bounds__(256)
+weight_prep_kernel(const float* __restrict__ w, int K, int N, __nv_bfloat16* __restrict__ wt, long long ldt,
+                   __nv_bfloat16* __restrict__ wn, long long ldn) {
+    // 32x32 smem tile transpose so both the read of w and the write of wt are coalesced
+    __shared__ float tile[32][33];
+    const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int k = k0 + r, n = n0 + tx;
+        float v = 0.f;
+        if (k < K && n < N) v = w[(long long)k * N + n];
+        tile[r][tx] = v;
+        if (wn != nullptr && k < K && n < N) wn[(long long)k * ldn + n] = __float2bfloat16_rn(v);
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int n = n0 + r, k = k0 + tx;
+        if (n < N && k < K) wt[(long long)n * ldt + k] = __float2bfloat16_rn(tile[tx][r]);
+    }
+}
+
+// ---- dropout / adam / misc ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, float rate, uint64_t seed,
+               const T* __restrict__ addend) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t h = splitmix64(seed * 0xD1342543DE82EF95ull + (uint64_t)i);
+    const float u = (float)(h >> 40) * (1.0f / 16777216.0f);   // [0,1)
+    float v = (u >= rate) ? to_f<T>(x[i]) / (1.f - rate) : 0.f;
+    if (addend != nullptr) v += to_f<T>(addend[i]);
+    y[i] = from_f<T>(v);
+}
+
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            long long n, float lr_t, float b1, float b2, float eps, float gscale, float l2) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float wi = w[i];
+    const float gi = fmaf(g[i], gscale, 2.f * l2 * wi);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    w[i] = wi - lr_t * mi / (sqrtf(vi) + eps);
+}
+
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const float* __restrict__ w, long long n, float* __restrict__ out) {
+    float s = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        s = fmaf(w[i], w[i], s);
+    s = warp_sum(s);
+    __shared__ float part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tsum = 0.f;
+        for (int k = 0; k < 8; ++k) tsum += part[k];
+        atomicAdd(out, tsum);
+    }
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = from_f<TO>(to_f<TI>(x[i]));
+}
+
+static void col_reduce_grid(int CV, int CVB, long long M, int& gx, int& gy, long long& rpb) {
+    gx = cdiv(CV, CVB);
+    const int PL = 256 / CVB;
+    long long want = (long long)kNumSMs * 8 / gx; if (want < 1) want = 1;
+    rpb = (M + want - 1) / want;
+    rpb = ((rpb + 2 * PL - 1) / (2 * PL)) * (2 * PL);
+    if (rpb < 2 * PL) rpb = 2 * PL;
+    gy = cdiv(M, rpb);
+}
+
+static bool vec_ok(int C, std::initializer_list<long long> lds, std::initializer_list<const void*> ptrs) {
+    if (C % 8) return false;
+    for (long long l : lds) if (l % 8) return false;
+    for (const void* p : ptrs) if (p && !aligned16(p)) return false;
+    return true;
+}
+
+}  // namespace dlv3p
+
+using namespace dlv3p;
+
+extern "C" int dlv3p_bn_stats(const void* y, int64_t ld, int64_t M, int C, float* sums, int dtype, void* stream) {
+    DLV3P_REQUIRE(y && sums && M > 0 && C > 0, DLV3P_ERR_SHAPE, "bn_stats: bad arguments");
+    DLV3P_REQUIRE(C % 8 == 0 && ld % 8 == 0 && aligned16(y), DLV3P_ERR_ALIGN,
+                  "bn_stats: C=%d, ld=%lld must be multiples of 8 and y 16-byte aligned", C, (long long)ld);
+    cudaStream_t st = (cudaStream_t)stream;
+    DLV3P_DISPATCH_DTYPE(dtype, T, {
+        pick_cvb(C / 8, [&](auto cvb) {
+            constexpr int CVB = decltype(cvb)::value;
+            int gx, gy; long long rpb;
+            col_reduce_grid(C / 8, CVB, M, gx, gy, rpb);
+            bn_stats_kernel<T, CVB><<<dim3(gx, gy), 256, 0, st>>>((const T*)y, ld, M, C, sums, rpb);
+        });
+        return check_launch("bn_stats");
+    });
+    return 0;
+}
+
+extern "C" int dlv3p_bn_finalize(const float* sums, const float* gamma, const float* beta, float* moving_mean,
+                                 float* moving_var, int C, double count, float eps, float momentum, float* scale,
+                                 float* shift, float* mean, float* invstd, int update_moving, void* stream) {
+    DLV3P_REQUIRE(sums && scale && shift && mean && invstd && C > 0 && count > 0, DLV3P_ERR_SHAPE,
+                  "bn_finalize: bad arguments");
+    DLV3P_REQUIRE(!update_moving || (moving_mean && moving_var), DLV3P_ERR_SHAPE,
+                  "bn_finalize: moving statistics required when update_moving");
+    bn_finalize_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, gamma, beta, moving_mean, moving_var,
+                                                                       C, count, eps, momentum, scale, shift, mean,
+                                                                       invstd, update_moving);
+    return check_launch("bn_finalize");
+}
+
+extern "C" int dlv3p_bn_fold(const float* gamma, const float* beta, const float* moving_mean,
+                             const float* moving_var, int C, float eps, float* scale, float* shift, void* stream) {
+    DLV3P_REQUIRE(moving_mean && moving_var && scale && shift && C > 0, DLV3P_ERR_SHAPE, "bn_fold: bad arguments");
+    bn_fold_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(gamma, beta, moving_mean, moving_var, C, eps,
+                                                                   scale, shift);
+    return check_launch("bn_fold");
+}
+
+extern "C" int dlv3p_affine_act(const void* y, int64_t ld_y, const float* scale, const float* shift, int act,
+                                const void* addend, int64_t ld_addend, void* out, int64_t ld_out, int64_t M, int C,
+                                int dtype, void* stream) {
+    DLV3P_REQUIRE(y && out && M > 0 && C > 0, DLV3P_ERR_SHAPE, "affine_act: bad arguments");
+    DLV3P_REQUIRE((scale == nullptr) == (shift == nullptr), DLV3P_ERR_SHAPE, "affine_act: scale/shift mismatch");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool v8 = vec_ok(C, {ld_y, ld_out, addend ? ld_addend : 0}, {y, out, addend});
+    DLV3P_DISPATCH_DTYPE(dtype, T, {
+        if (v8) {
+            const long long total = M * (C / 8);
+            affine_act_kernel<T, 8><<<cdiv(total, 256), 256, 0, st>>>((const T*)y, ld_y, scale, shift, act,
+                                                                      (const T*)addend, ld_addend, (T*)out, ld_out,
+                                                                      M, C);
+        } else {
+            const long long total = M * C;
+            affine_act_kernel<T, 1><<<cdiv(total, 256), 256, 0, st>>>((const T*)y, ld_y, scale, shift, act,
+                                                                      (const T*)addend, ld_addend, (T*)out, ld_out,
+                                                                      M, C);
+        }
+        return check_launch("affine_act");
+    });
+    return 0;
+}
+
+extern "C" int dlv3p_bn_bwd_reduce(const void* dz, int64_t ld_dz, const void* y, int64_t ld_y, const float* scale,
+                                   const float* shift, const float* mean, const float* invstd, int act, int64_t M,
+                                   int C, float* red, int dtype, void* stream) {
+    DLV3P_REQUIRE(dz && y && scale && shift && mean && invstd && red && M > 0 && C > 0, DLV3P_ERR_SHAPE,
+                  "bn_bwd_reduce: bad arguments");
+    DLV3P_REQUIRE(vec_ok(C, {ld_dz, ld_y}, {dz, y}), DLV3P_ERR_ALIGN, "bn_bwd_reduce: C/ld must be multiples of 8");
+    cudaStream_t st = (cudaStream_t)stream;
+    DLV3P_DISPATCH_DTYPE(dtype, T, {
+        pick_cvb(C / 8, [&](auto cvb) {
+            constexpr int CVB = decltype(cvb)::value;
+            int gx, gy; long long rpb;
+            col_reduce_grid(C / 8, CVB, M, gx, gy, rpb);
+            bn_bwd_reduce_kernel<T, CVB><<<dim3(gx, gy), 256, 0, st>>>((const T*)dz, ld_dz, (const T*)y, ld_y, scale,
+                                                                      shift, mean, invstd, act, M, C, red, rpb);
+        });
+        return check_launch("bn_bwd_reduce");
+    });
+    return 0;
+}
+
+extern "C" int dlv3p_bn_bwd_apply(const void* dz, int64_t ld_dz, const void* y, int64_t ld_y, const float* scale,
+                                  const float* shift, const float* mean, const float* invstd, int act,
+                                  const float* red, int64_t M, int C, void* dy, int64_t ld_dy, int dtype,
+                                  void* stream) {
+    DLV3P_REQUIRE(dz && y && scale && shift && dy && M > 0 && C > 0, DLV3P_ERR_SHAPE, "bn_bwd_apply: bad arguments");
+    DLV3P_REQUIRE(mean == nullptr || (invstd && red), DLV3P_ERR_SHAPE, "bn_bwd_apply: invstd/red required");
+    DLV3P_REQUIRE(vec_ok(C, {ld_dz, ld_y, ld_dy}, {dz, y, dy}), DLV3P_ERR_ALIGN,
+                  "bn_bwd_apply: C/ld must be multiples of 8");
+    cudaStream_t st = (cudaStream_t)stream;
+    DLV3P_DISPATCH_DTYPE(dtype, T, {
+        const long long total = M * (C / 8);
+        bn_bwd_apply_kernel<T><<<cdiv(total, 256), 256, 0, st>>>((const T*)dz, ld_dz, (const T*)y, ld_y, scale, shift,
+                                                                 mean, invstd, act, red, M, C, (T*)dy, ld_dy);
+        return check_launch("bn_bwd_apply");
+    });
+    return 0;
+}
+
+extern "C" int dlv3p_act_bwd(const void* dy, const void* x, void* dx, int act, const void* addend, int64_t n,
+                             int dtype, void* stream) {
+    DLV3P_REQUIRE(dy && x && dx && n > 0, DLV3P_ERR_SHAPE, "act_bwd: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool v8 = (n % 8 == 0) && aligned16(dy) && aligned16(x) && aligned16(dx) && (!addend || aligned16(addend));
+    DLV3P_DISPATCH_DTYPE(dtype, T, {
+        if (v8) act_bwd_kernel<T, 8><<<cdiv(n / 8, 256), 256, 0, st>>>((const T*)dy, (const T*)x, (T*)dx, act,
+                                                                       (const T*)addend, n);
+        else act_bwd_kernel<T, 1><<<cdiv(n, 256), 256, 0, st>>>((const T*)dy, (const T*)x, (T*)dx, act,
+                                                               (const T*)addend, n);
+        return check_launch("act_bwd");
+    });
+    return 0;
+}
+
+extern "C" int dlv3p_add(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream) {
+    DLV3P_REQUIRE(a && b && out && n > 0, DLV3P_ERR_SHAPE, "add: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool v8 = (n % 8 == 0) && aligned16(a) && aligned16(b) && aligned16(out);
+    DLV3P_DISPATCH_DTYPE(dtype, T, {
+        if (v8) add_kernel<T, 8><<<cdiv(n / 8, 256), 256, 0, st>>>((const T*)a, (const T*)b, (T*)out, n);
+        else add_kernel<T, 1><<<cdiv(n, 256), 256, 0, st>>>((const T*)a, (const T*)b, (T*)out, n);
+        return check_launch("add");
+    });
+    return 0;
+}
+
+extern "C" int dlv3p_copy2d(const void* x, int64_t ld_x, void* y, int64_t ld_y, int64_t M, int C,
+                            const void* addend, int64_t ld_addend, int dtype, void* stream) {
+    // a copy is the identity affine without activation
+    return dlv3p_affine_act(x, ld_x, nullptr, nullptr, DLV3P_ACT_NONE, addend, ld_addend, y, ld_y, M, C, dtype,
+                            stream);
+}
+
+extern "C" int dlv3p_maxpool3x3s2_fwd(const void* x, void* y, uint8_t* argmax, int N, int H, int W, int C,
+                                      int pad_t, int pad_l, int Ho, int Wo, const void* addend, int dtype,
+                                      void* stream) {
+    DLV3P_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0, DLV3P_ERR_SHAPE, "maxpool_fwd: bad arguments");
+    DLV3P_REQUIRE(C % 8 == 0 && aligned16(x) && aligned16(y), DLV3P_ERR_ALIGN, "maxpool_fwd: C %% 8 and alignment");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)N * Ho * Wo * (C / 8);
+    DLV3P_DISPATCH_DTYPE(dtype, T, {
+        maxpool3x3s2_fwd_kernel<T><<<cdiv(total, 256), 256, 0, st>>>((const T*)x, (T*)y, argmax, N, H, W, C, pad_t,
+                                                                     pad_l, Ho, Wo, (const T*)addend, total);
+        return check_launch("maxpool_fwd");
+    });
+    return 0;
+}
+
+extern "C" int dlv3p_maxpool3x3s2_bwd(const void* dy, const uint8_t* argmax, void* dx, int N, int H, int W, int C,
+                                      int pad_t, int pad_l, int Ho, int Wo, const void* addend, int dtype,
+                                      void* stream) {
+    DLV3P_REQUIRE(dy && argmax && dx && N > 0, DLV3P_ERR_SHAPE, "maxpool_bwd: bad arguments");
+    DLV3P_REQUIRE(C % 8 == 0 && aligned16(dy) && aligned16(dx), DLV3P_ERR_ALIGN, "maxpool_bwd: C %% 8 and alignment");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)N * H * W * (C / 8);
+    DLV3P_DISPATCH_DTYPE(dtype, T, {
+        maxpool3x3s2_bwd_kernel<T><<<cdiv(total, 256), 256, 0, st>>>((const T*)dy, argmax, (T*)dx, N, H, W, C, pad_t,
+                                                                     pad_l, Ho, Wo, (const T*)addend, total);
+        return check_launch("maxpool_bwd");
+    });
+    return 0;
+}
+
+extern "C" int dlv3p_avgpool_fwd(const void* x, void* y, int N, int H, int W, int C, int k, int Ho, int Wo,
+                                 int dtype, void* stream) {
+    DLV3P_REQUIRE(x && y && N > 0 && k > 0 && Ho == H / k && Wo == W / k && Ho > 0 && Wo > 0, DLV3P_ERR_SHAPE,
+                  "avgpool_fwd: bad arguments (VALID, stride=k)");
+    DLV3P_REQUIRE(C % 8 == 0 && aligned16(x) && aligned16(y), DLV3P_ERR_ALIGN, "avgpool_fwd: C %% 8 and alignment");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)N * Ho * Wo * (C / 8);
+    DLV3P_DISPATCH_DTYPE(dtype, T, {
+        avgpool_fwd_kernel<T><<<cdiv(total, 256), 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C, k, Ho, Wo, total);
+        return check_launch("avgpool_fwd");
+    });
+    return 0;
+}
+
+extern "C" int dlv3p_avgpool_bwd(const void* dy, void* dx, int N, int H, int W, int C, int k, int Ho, int Wo,
+                                 const void* addend, int dtype, void* stream) {
+    DLV3P_REQUIRE(dy && dx && N > 0 && k > 0 && Ho == H / k && Wo == W / k, DLV3P_ERR_SHAPE,
+                  "avgpool_bwd: bad arguments");
+    DLV3P_REQUIRE(C % 8 == 0 && aligned16(dy) && aligned16(dx), DLV3P_ERR_ALIGN, "avgpool_bwd: C %% 8 and alignment");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)N * H * W * (C / 8);
+    DLV3P_DISPATCH_DTYPE(dtype, T, {
+        avgpool_bwd_kernel<T><<<cdiv(total, 256), 256, 0, st>>>((const T*)dy, (T*)dx, N, H, W, C, k, Ho, Wo,
+                                                                (const T*)addend, total);
+        return check_launch("avgpool_bwd");
+    });
+    return 0;
+}
+
+#define DLV3P_DISPATCH_2DTYPE(da, TA, db, TB, ...)                                                          \
+    do {                                                                                                    \
+        if ((da) == DLV3P_F32 && (db) == DLV3P_F32) { using TA = float; using TB = float; __VA_ARGS__; }    \
+        else if ((da) == DLV3P_BF16 && (db) == DLV3P_BF16) { using TA = __nv_bfloat16; using TB = __nv_bfloat16; __VA_ARGS__; } \
+        else if ((da) == DLV3P_BF16 && (db) == DLV3P_F32) { using TA = __nv_bfloat16; using TB = float; __VA_ARGS__; } \
+        else if ((da) == DLV3P_F32 && (db) == DLV3P_BF16) { using TA = float; using TB = __nv_bfloat16; __VA_ARGS__; } \
+        else { ::dlv3p::set_error("unsupported dtype pair %d,%d", (int)(da), (int)(db)); return DLV3P_ERR_DTYPE; } \
+    } while (0)
+
+extern "C" int dlv3p_bilinear_fwd(const void* x, int64_t ld_x, void* y, int64_t ld_y, int N, int H, int W, int C,
+                                  int fh, int fw, int in_dtype, int out_dtype, void* stream) {
+    DLV3P_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0 && fh >= 1 && fw >= 1, DLV3P_ERR_SHAPE,
+                  "bilinear_fwd: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool v8 = vec_ok(C, {ld_x, ld_y}, {x, y});
+    DLV3P_DISPATCH_2DTYPE(in_dtype, TI, out_dtype, TO, {
+        if (v8) {
+            const long long total = (long long)N * H * fh * W * fw * (C / 8);
+            bilinear_fwd_kernel<TI, TO, 8><<<cdiv(total, 256), 256, 0, st>>>((const TI*)x, ld_x, (TO*)y, ld_y, N, H,
+                                                                             W, C, fh, fw, total);
+        } else {
+            const long long total = (long long)N * H * fh * W * fw * C;
+            bilinear_fwd_kernel<TI, TO, 1><<<cdiv(total, 256), 256, 0, st>>>((const TI*)x, ld_x, (TO*)y, ld_y, N, H,
+                                                                             W, C, fh, fw, total);
+        }
+        return check_launch("bilinear_fwd");
+    });
+    return 0;
+}
+
+extern "C" int dlv3p_bilinear_bwd(const void* dy, int64_t ld_dy, void* dx, int64_t ld_dx, int N, int H, int W,
+                                  int C, int fh, int fw, const void* addend, int dy_dtype, int dx_dtype,
+                                  void* stream) {
+    DLV3P_REQUIRE(dy && dx && N > 0 && H > 0 && W > 0 && C > 0 && fh >= 1 && fw >= 1, DLV3P_ERR_SHAPE,
+                  "bilinear_bwd: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool v8 = vec_ok(C, {ld_dy, ld_dx}, {dy, dx, addend});
+    DLV3P_DISPATCH_2DTYPE(dy_dtype, TI, dx_dtype, TO, {
+        if (v8) {
+            const long long total = (long long)N * H * W * (C / 8);
+            bilinear_bwd_kernel<TI, TO, 8><<<cdiv(total, 256), 256, 0, st>>>((const TI*)dy, ld_dy, (TO*)dx, ld_dx, N,
+                                                                             H, W, C, fh, fw, (const TO*)addend,
+                                                                             total);
+        } else {
+            const long long total = (long long)N * H * W * C;
+            bilinear_bwd_kernel<TI, TO, 1><<<cdiv(total, 256), 256, 0, st>>>((const TI*)dy, ld_dy, (TO*)dx, ld_dx, N,
+                                                                             H, W, C, fh, fw, (const TO*)addend,
+                                                                             total);
+        }
+        return check_launch("bilinear_bwd");
+    });
+    return 0;
+}
+
+extern "C" int dlv3p_im2col3x3(const void* x, void* col, int N, int H, int W, int C, int stride, int dil, int pad_t,
+                               int pad_l, int Ho, int Wo, int64_t ld_col, int dtype, void* stream) {
+    DLV3P_REQUIRE(x && col && N > 0 && C > 0 && Ho > 0 && Wo > 0 && ld_col >= 9 * C, DLV3P_ERR_SHAPE,
+                  "im2col3x3: bad arguments (ld_col=%lld, 9C=%d)", (long long)ld_col, 9 * C);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool v8 = vec_ok(C, {ld_col}, {x, col});
+    const long long P = (long long)N * Ho * Wo;
+    DLV3P_DISPATCH_DTYPE(dtype, T, {
+        if (v8) {
+            const long long total = P * (ld_col / 8);
+            im2col3x3_kernel<T, 8><<<cdiv(total, 256), 256, 0, st>>>((const T*)x, (T*)col, N, H, W, C, stride, dil,
+                                                                     pad_t, pad_l, Ho, Wo, ld_col, total);
+        } else {
+            const long long total = P * ld_col;
+            im2col3x3_kernel<T, 1><<<cdiv(total, 256), 256, 0, st>>>((const T*)x, (T*)col, N, H, W, C, stride, dil,
+                                                                     pad_t, pad_l, Ho, Wo, ld_col, total);
+        }
+        return check_launch("im2col3x3");
+    });
+    return 0;
+}
+
+extern "C" int dlv3p_col2im3x3(const void* col, void* dx, int N, int H, int W, int C, int stride, int dil,
+                               int pad_t, int pad_l, int Ho, int Wo, int64_t ld_col, const void* addend, int dtype,
+                               void* stream) {
+    DLV3P_REQUIRE(col && dx && N > 0 && C > 0 && Ho > 0 && Wo > 0 && ld_col >= 9 * C, DLV3P_ERR_SHAPE,
+                  "col2im3x3: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool v8 = vec_ok(C, {ld_col}, {col, dx, addend});
+    DLV3P_DISPATCH_DTYPE(dtype, T, {
+        if (v8) {
+            const long long total = (long long)N * H * W * (C / 8);
+            col2im3x3_kernel<T, 8><<<cdiv(total, 256), 256, 0, st>>>((const T*)col, (T*)dx, N, H, W, C, stride, dil,
+                                                                     pad_t, pad_l, Ho, Wo, ld_col, (const T*)addend,
+                                                                     total);
+        } else {
+            const long long total = (long long)N * H * W * C;
+            col2im3x3_kernel<T, 1><<<cdiv(total, 256), 256, 0, st>>>((const T*)col, (T*)dx, N, H, W, C, stride, dil,
+                                                                     pad_t, pad_l, Ho, Wo, ld_col, (const T*)addend,
+                                                                     total);
+        }
+        return check_launch("col2im3x3");
+    });
+    return 0;
+}
+
+extern "C" int dlv3p_subsample_fwd(const void* x, void* y, int N, int H, int W, int C, int stride, int Ho, int Wo,
+                                   int dtype, void* stream) {
+    DLV3P_REQUIRE(x && y && N > 0 && stride >= 1 && (Ho - 1) * stride < H && (Wo - 1) * stride < W,
+                  DLV3P_ERR_SHAPE, "subsample_fwd: bad arguments");
+    DLV3P_REQUIRE(C % 8 == 0 && aligned16(x) && aligned16(y), DLV3P_ERR_ALIGN, "subsample_fwd: C %% 8 and alignment");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)N * Ho * Wo * (C / 8);
+    DLV3P_DISPATCH_DTYPE(dtype, T, {
+        subsample_fwd_kernel<T><<<cdiv(total, 256), 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C, stride, Ho, Wo,
+                                                                  total);
+        return check_launch("subsample_fwd");
+    });
+    return 0;
+}
+
+extern "C" int dlv3p_subsample_bwd(const void* dy, void* dx, int N, int H, int W, int C, int stride, int Ho, int Wo,
+                                   const void* addend, int dtype, void* stream) {
+    DLV3P_REQUIRE(dy && dx && N > 0 && stride >= 1, DLV3P_ERR_SHAPE, "subsample_bwd: bad arguments");
+    DLV3P_REQUIRE(C % 8 == 0 && aligned16(dy) && aligned16(dx), DLV3P_ERR_ALIGN, "subsample_bwd: C %% 8 and alignment");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)N * H * W * (C / 8);
+    DLV3P_DISPATCH_DTYPE(dtype, T, {
+        subsample_bwd_kernel<T><<<cdiv(total, 256), 256, 0, st>>>((const T*)dy, (T*)dx, N, H, W, C, stride, Ho, Wo,
+                                                                  (const T*)addend, total);
+        return check_launch("subsample_bwd");
+    });
+    return 0;
+}
+
+extern "C" int dlv3p_weight_prep(const float* w, int K, int N, void* wt, int64_t ldt, void* wn, int64_t ldn,
+                                 void* stream) {
+    DLV3P_REQUIRE(w && wt && K > 0 && N > 0 && ldt >= K && (wn == nullptr || ldn >= N), DLV3P_ERR_SHAPE,
+                  "weight_prep: bad arguments");
+    weight_prep_kernel<<<dim3(cdiv(N, 32), cdiv(K, 32)), 256, 0, (cudaStream_t)stream>>>(
+        w, K, N, (__nv_bfloat16*)wt, ldt, (__nv_bfloat16*)wn, ldn);
+    return check_launch("weight_prep");
+}
+
+extern "C" int dlv3p_dropout(const void* x, void* y, int64_t n, float rate, uint64_t seed, const void* addend,
+                             int dtype, void* stream) {
+    DLV3P_REQUIRE(x && y && n > 0 && rate >= 0.f && rate < 1.f, DLV3P_ERR_SHAPE, "dropout: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    DLV3P_DISPATCH_DTYPE(dtype, T, {
+        dropout_kernel<T><<<cdiv(n, 256), 256, 0, st>>>((const T*)x, (T*)y, n, rate, seed, (const T*)addend);
+        return check_launch("dropout");
+    });
+    return 0;
+}
+
+extern "C" int dlv3p_adam(float* w, const float* g, float* m, float* v, int64_t n, float lr_t, float beta1,
+                          float beta2, float eps, float grad_scale, float l2, void* stream) {
+    DLV3P_REQUIRE(w && g && m && v && n > 0, DLV3P_ERR_SHAPE, "adam: bad arguments");
+    adam_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(w, g, m, v, n, lr_t, beta1, beta2, eps, grad_scale,
+                                                                l2);
+    return check_launch("adam");
+}
+
+extern "C" int dlv3p_sumsq(const float* w, int64_t n, float* out, void* stream) {
+    DLV3P_REQUIRE(w && out && n > 0, DLV3P_ERR_SHAPE, "sumsq: bad arguments");
+    int blocks = cdiv(n, 256 * 8); if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+    sumsq_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, n, out);
+    return check_launch("sumsq");
+}
+
+extern "C" int dlv3p_cast(const void* x, int x_dtype, void* y, int y_dtype, int64_t n, void* stream) {
+    DLV3P_REQUIRE(x && y && n > 0, DLV3P_ERR_SHAPE, "cast: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    DLV3P_DISPATCH_2DTYPE(x_dtype, TI, y_dtype, TO, {
+        cast_kernel<TI, TO><<<cdiv(n, 256), 256, 0, st>>>((const TI*)x, (TO*)y, n);
+        return check_launch("cast");
+    });
+    return 0;
+}

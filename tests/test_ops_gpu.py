@@ -1,0 +1,527 @@
+"""Per-kernel parity: every C-ABI entry point against the oracle (oracle/tf_ops.py, fp64 on CPU) on seeded inputs.
+
+Tolerances: fp32 storage -> rtol 1e-4 (fp32 accumulation order); bf16 storage -> the oracle is evaluated on the
+bf16-rounded inputs in fp64 and the result may differ by one bf16 rounding of the output (2^-8 relative) plus fp32
+accumulation noise; tensor-core GEMMs: bf16 products are exact in fp32, so only accumulation order differs.
+"""
+import math
+
+import pytest
+import torch
+
+from oracle import tf_ops as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def ops():
+    from deeplabv3plus_keras_b200 import ops as _ops
+    return _ops
+
+
+def rnd(shape, dtype, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g, dtype=torch.float64) * scale).to(dtype)
+
+
+def tol(dtype):
+    return (2e-2, 2e-2) if dtype == torch.bfloat16 else (2e-4, 2e-4)
+
+
+def check(name, got, want, rtol, atol):
+    got = got.detach().double().cpu()
+    want = want.detach().double().cpu()
+    assert got.shape == want.shape, f"{name}: shape {tuple(got.shape)} vs {tuple(want.shape)}"
+    err = (got - want).abs()
+    bound = atol + rtol * want.abs()
+    bad = err > bound
+    if bad.any():
+        idx = torch.nonzero(bad)[0].tolist()
+        raise AssertionError(
+            f"{name}: {int(bad.sum())}/{bad.numel()} mismatches; max abs err {err.max():.4e} "
+            f"(max |want| {want.abs().max():.4e}); first bad idx {idx}: got {got[tuple(idx)]:.6e} want {want[tuple(idx)]:.6e}")
+
+
+DW_CASES = [
+    # N, H, W, C, stride, dil, padding
+    (2, 17, 19, 64, 1, (1, 1), "same"),
+    (1, 33, 33, 96, 1, (18, 15), "same"),
+    (1, 33, 33, 32, 1, (6, 21), "same"),
+    (2, 32, 32, 256, 1, (12, 12), "same"),
+    (1, 64, 64, 64, 1, (36, 36), "same"),
+    (2, 30, 31, 728, 1, (1, 1), "same"),
+    (1, 65, 65, 144, 2, (1, 1), "mnv2"),
+    (1, 64, 48, 32, 2, (1, 1), "mnv2"),
+    (1, 9, 9, 8, 1, (6, 3), "same"),
+]
+
+
+def dw_pad(H, W, stride, dil, padding):
+    o = ops()
+    if padding == "mnv2":
+        # ZeroPadding2D(correct_pad) + VALID == SAME arithmetic for a 3x3 kernel
+        return o.conv_geometry(H, W, 3, stride, dil, "same")
+    return o.conv_geometry(H, W, 3, stride, dil, padding)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("case", DW_CASES)
+@pytest.mark.parametrize("prologue", [False, True])
+def test_dwconv3x3_fwd_dgrad_wgrad(case, dtype, prologue):
+    o = ops()
+    N, H, W, C, stride, dil, padding = case
+    x = rnd((N, H, W, C), dtype, 1)
+    w = rnd((3, 3, C), torch.float32, 2, 0.3)
+    sc = (rnd((C,), torch.float32, 3, 0.2) + 1.0) if prologue else None
+    sh = rnd((C,), torch.float32, 4, 0.3) if prologue else None
+    act = o.ACT_RELU if prologue else o.ACT_NONE
+    pad = dw_pad(H, W, stride, dil, padding)
+    ho, wo, pt, pl = pad
+
+    xr = x.double().requires_grad_(True)
+    wr = w.double().requires_grad_(True)
+    z = xr
+    if prologue:
+        z = torch.relu(z * sc.double() + sh.double())
+    z.retain_grad()
+    y_ref = O.depthwise_conv2d(z, wr.view(3, 3, C, 1), stride, "same", dil)
+    assert y_ref.shape[1:3] == (ho, wo)
+    gy = rnd(tuple(y_ref.shape), dtype, 5)
+    y_ref.backward(gy.double())
+
+    xd, wd = x.to(DEV), w.to(DEV)
+    scd = sc.to(DEV) if prologue else None
+    shd = sh.to(DEV) if prologue else None
+    y = o.dwconv3x3_fwd(xd, wd, stride, dil, in_scale=scd, in_shift=shd, in_act=act, pad=pad)
+    rt, at = tol(dtype)
+    check("dw fwd", y, y_ref, rt, at * 4)
+
+    # dgrad returns the gradient w.r.t. the activation input z_pre = sc*x+sh (mask applied, no scale factor)
+    gyd = gy.to(DEV)
+    add = rnd((N, H, W, C), dtype, 6)
+    dx = o.dwconv3x3_dgrad(gyd, wd, (N, H, W, C), stride, dil, x_pre=xd if prologue else None, in_scale=scd,
+                           in_shift=shd, in_act=act, addend=add.to(DEV), pad=pad)
+    dz_ref = z.grad
+    if prologue:
+        pre = x.double() * sc.double() + sh.double()
+        dz_ref = dz_ref * (pre > 0).double()
+    check("dw dgrad", dx, dz_ref + add.double(), rt, at * 4)
+
+    dw = torch.zeros((3, 3, C), dtype=torch.float32, device=DEV)
+    o.dwconv3x3_wgrad(xd, gyd, dw, stride, dil, in_scale=scd, in_shift=shd, in_act=act, pad=pad)
+    check("dw wgrad", dw, wr.grad, 2e-3, 2e-3 * math.sqrt(N * ho * wo))
+
+
+GEMM_CASES = [
+    # M, N, K
+    (128, 32, 64),
+    (256, 64, 128),
+    (300, 128, 64),
+    (1000, 256, 256),
+    (517, 728, 728),
+    (2048, 21, 2304),
+    (4096, 256, 1280),
+    (130, 48, 1024),
+    (1024, 1024, 728),
+    (96, 16, 32),
+    (4100, 96, 576),
+]
+
+
+@pytest.mark.parametrize("case", GEMM_CASES)
+def test_gemm_bf16_plain(case):
+    o = ops()
+    M, N, K = case
+    a = rnd((M, K), torch.bfloat16, 11)
+    b = rnd((N, K), torch.bfloat16, 12, 1.0 / math.sqrt(K))
+    ref = a.double() @ b.double().t()
+    for cdt in (torch.float32, torch.bfloat16):
+        out = torch.full((M, N), float("nan"), dtype=cdt, device=DEV)
+        o.gemm_bf16(a.to(DEV), b.to(DEV), M, N, K, out)
+        rt, at = (1e-4, 1e-4) if cdt == torch.float32 else (1e-2, 1e-2)
+        check(f"gemm {case} {cdt}", out, ref, rt, at)
+
+
+@pytest.mark.parametrize("case", [(517, 728, 728), (1000, 256, 256), (2048, 21, 288), (300, 40, 64)])
+def test_gemm_bf16_epilogue(case):
+    o = ops()
+    M, N, K = case
+    a = rnd((M, K), torch.bfloat16, 21)
+    b = rnd((N, K), torch.bfloat16, 22, 1.0 / math.sqrt(K))
+    sc = rnd((N,), torch.float32, 23, 0.2) + 1.0
+    sh = rnd((N,), torch.float32, 24, 0.5)
+    ldc = N + 8
+    add = rnd((M, ldc), torch.bfloat16, 25)
+    acc = a.double() @ b.double().t()
+    ref = torch.relu(acc * sc.double() + sh.double()) + add[:, :N].double()
+    out = torch.zeros((M, ldc), dtype=torch.bfloat16, device=DEV)
+    stats = torch.zeros((2, N), dtype=torch.float32, device=DEV)
+    o.gemm_bf16(a.to(DEV), b.to(DEV), M, N, K, out, ldc=ldc, col_scale=sc.to(DEV), col_shift=sh.to(DEV),
+                act=o.ACT_RELU, addend=add.to(DEV), ld_addend=ldc, col_stats=stats)
+    check("gemm epi", out[:, :N], ref, 1e-2, 2e-2)
+    assert float(out[:, N:].abs().max()) == 0.0, "gemm wrote outside its channel slice"
+    check("gemm stats sum", stats[0], acc.sum(0), 1e-3, 1e-3 * math.sqrt(M))
+    check("gemm stats sumsq", stats[1], (acc * acc).sum(0), 1e-3, 1e-3 * M)
+
+
+def test_gemm_bf16_strided_a():
+    """A is a channel slice of a wider tensor (lda > K), as when a branch reads part of a concat."""
+    o = ops()
+    M, N, K, lda = 700, 256, 256, 1280
+    big = rnd((M, lda), torch.bfloat16, 31)
+    b = rnd((N, K), torch.bfloat16, 32, 1.0 / math.sqrt(K))
+    off = 512
+    ref = big[:, off:off + K].double() @ b.double().t()
+    out = torch.empty((M, N), dtype=torch.float32, device=DEV)
+    bd = big.to(DEV)
+    o.gemm_bf16(bd[:, off:], b.to(DEV), M, N, K, out, lda=lda)
+    check("gemm strided A", out, ref, 1e-4, 1e-4)
+
+
+@pytest.mark.parametrize("case", [(1000, 64, 64), (4096, 128, 256), (5000, 728, 728), (16384, 256, 24),
+                                  (3000, 32, 64), (2000, 1024, 256), (900, 304, 24)])
+def test_gemm_wgrad_bf16(case):
+    o = ops()
+    M, K, N = case
+    ldy = ((N + 7) // 8) * 8
+    x = rnd((M, K), torch.bfloat16, 41)
+    dy = rnd((M, ldy), torch.bfloat16, 42)
+    ref = x.double().t() @ dy[:, :N].double()
+    dw0 = rnd((K, N), torch.float32, 43)
+    dw = dw0.to(DEV).clone()
+    o.gemm_wgrad_bf16(x.to(DEV), dy.to(DEV), dw, M, K, N, ldy=ldy)
+    check(f"wgrad {case}", dw, ref + dw0.double(), 1e-3, 1e-3 * math.sqrt(M))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gemm_simt(dtype):
+    o = ops()
+    M, N, K = 333, 77, 130
+    a = rnd((M, K), dtype, 51)
+    b = rnd((K, N), dtype, 52, 1.0 / math.sqrt(K))
+    ref = a.double() @ b.double()
+    out = torch.empty((M, N), dtype=torch.float32, device=DEV)
+    o.gemm_simt(a.to(DEV), K, 1, b.to(DEV), N, 1, out, N, M, N, K)
+    check("simt nn", out, ref, 1e-4, 1e-4)
+    # transposed operands: C = A^T-view * B^T-view
+    at, bt = a.t().contiguous(), b.t().contiguous()
+    out2 = torch.empty((M, N), dtype=torch.float32, device=DEV)
+    o.gemm_simt(at.to(DEV), 1, M, bt.to(DEV), 1, K, out2, N, M, N, K)
+    check("simt tt", out2, ref, 1e-4, 1e-4)
+    out3 = out2.clone()
+    o.gemm_simt(a.to(DEV), K, 1, b.to(DEV), N, 1, out3, N, M, N, K, accumulate=True)
+    check("simt acc", out3, 2 * ref, 1e-4, 2e-4)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("case", [(2, 13, 11, 3, 2, "valid"), (1, 12, 12, 32, 1, "valid"), (2, 8, 9, 256, 1, "same"),
+                                  (1, 9, 9, 24, 2, "same")])
+def test_im2col_conv(case, dtype):
+    """dense 3x3 conv = im2col + GEMM against tf.nn.conv2d; col2im against autograd."""
+    o = ops()
+    N, H, W, C, stride, padding = case
+    Co = 21
+    x = rnd((N, H, W, C), dtype, 61)
+    w = rnd((3, 3, C, Co), torch.float32, 62, 0.2)
+    ho, wo, pt, pl = o.conv_geometry(H, W, 3, stride, (1, 1), padding)
+    xr = x.double().requires_grad_(True)
+    y_ref = O.conv2d(xr, w.double(), stride, padding)
+    assert tuple(y_ref.shape) == (N, ho, wo, Co)
+    ld = ((9 * C + 7) // 8) * 8
+    col = o.im2col3x3(x.to(DEV), stride, 1, ho, wo, pt, pl, ld)
+    y = torch.empty((N * ho * wo, Co), dtype=torch.float32, device=DEV)
+    wk = torch.zeros((ld, Co), dtype=dtype)
+    wk[:9 * C] = w.reshape(9 * C, Co).to(dtype)
+    o.gemm_simt(col, ld, 1, wk.to(DEV), Co, 1, y, Co, N * ho * wo, Co, ld)
+    y_ref2 = O.conv2d(x.double(), wk[:9 * C].double().reshape(3, 3, C, Co), stride, padding)
+    rt, at = tol(dtype)
+    check("im2col conv", y.view(N, ho, wo, Co), y_ref2, rt, at)
+    if C % 8 == 0:
+        gcol = rnd((N * ho * wo, ld), dtype, 63)
+        gcol[:, 9 * C:] = 0
+        # reference: scatter-add of the column gradient == autograd of im2col
+        xx = x.double().requires_grad_(True)
+        cols = []
+        xp = torch.nn.functional.pad(xx.permute(0, 3, 1, 2), (pl, 2 + stride, pt, 2 + stride))
+        for i in range(3):
+            for j in range(3):
+                cols.append(xp[:, :, i:i + stride * ho:stride, j:j + stride * wo:stride].permute(0, 2, 3, 1))
+        colr = torch.cat(cols, dim=-1).reshape(N * ho * wo, 9 * C)
+        check("im2col", col[:, :9 * C], colr, 0, 0)
+        colr.backward(gcol[:, :9 * C].double())
+        dx = o.col2im3x3(gcol.to(DEV), (N, H, W, C), stride, 1, ho, wo, pt, pl, ld)
+        check("col2im", dx, xx.grad, rt, at * 3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_subsample(dtype):
+    o = ops()
+    x = rnd((2, 9, 10, 64), dtype, 71)
+    y = o.subsample_fwd(x.to(DEV), 2)
+    check("subsample", y, x[:, ::2, ::2], 0, 0)
+    gy = rnd(tuple(y.shape), dtype, 72)
+    add = rnd((2, 9, 10, 64), dtype, 73)
+    dx = o.subsample_bwd(gy.to(DEV), (2, 9, 10, 64), 2, addend=add.to(DEV))
+    ref = add.double().clone()
+    ref[:, ::2, ::2] += gy.double()
+    rt, at = tol(dtype)
+    check("subsample bwd", dx, ref, rt, at)
+
+
+def test_weight_prep():
+    o = ops()
+    K, N = 100, 21
+    w = rnd((K, N), torch.float32, 81)
+    ldt, ldn = 104, 24
+    wt = torch.zeros((N, ldt), dtype=torch.bfloat16, device=DEV)
+    wn = torch.zeros((K, ldn), dtype=torch.bfloat16, device=DEV)
+    o.weight_prep(w.to(DEV), K, N, wt, ldt, wn, ldn)
+    check("wt", wt[:, :K], w.t().to(torch.bfloat16), 0, 0)
+    check("wn", wn[:, :N], w.to(torch.bfloat16), 0, 0)
+    assert float(wt[:, K:].abs().max()) == 0 and float(wn[:, N:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("MC", [(1000, 64), (4097, 728), (300, 24), (20000, 256)])
+def test_batchnorm_train(MC, dtype):
+    o = ops()
+    M, C = MC
+    y = (rnd((M, C), torch.float64, 91) * 1.5 + 0.7).to(dtype)
+    gamma = rnd((C,), torch.float32, 92, 0.2) + 1.0
+    beta = rnd((C,), torch.float32, 93, 0.3)
+    mm = rnd((C,), torch.float32, 94)
+    mv = rnd((C,), torch.float32, 95).abs() + 0.5
+    eps, mom = 1e-3, 0.99
+    yr = y.double().view(1, 1, M, C).requires_grad_(True)
+    z_ref, mm_ref, mv_ref = O.batch_norm(yr, gamma.double(), beta.double(), mm.double(), mv.double(), eps, True, mom)
+    res = rnd((M, C), dtype, 96)
+    out_ref = torch.relu(z_ref.view(M, C)) + res.double()
+    gz = rnd((M, C), dtype, 97)
+    out_ref.backward(gz.double())
+
+    yd = y.to(DEV)
+    sums = torch.zeros((2, C), dtype=torch.float32, device=DEV)
+    o.bn_stats(yd, M, C, sums)
+    scale, shift, mean, invstd = (torch.empty(C, dtype=torch.float32, device=DEV) for _ in range(4))
+    mmd, mvd = mm.to(DEV), mv.to(DEV)
+    o.bn_finalize(sums, gamma.to(DEV), beta.to(DEV), mmd, mvd, C, M, eps, mom, scale, shift, mean, invstd)
+    check("bn mean", mean, y.double().mean(0), 1e-4, 1e-4)
+    check("bn moving mean", mmd, mm_ref, 1e-4, 1e-4)
+    check("bn moving var", mvd, mv_ref, 1e-3, 1e-4)
+    out = torch.empty((M, C), dtype=dtype, device=DEV)
+    o.affine_act(yd, M, C, out, scale, shift, o.ACT_RELU, addend=res.to(DEV))
+    rt, at = tol(dtype)
+    check("bn apply", out, out_ref, rt, at)
+
+    red = torch.zeros((2, C), dtype=torch.float32, device=DEV)
+    gzd = gz.to(DEV)
+    o.bn_bwd_reduce(gzd, yd, scale, shift, mean, invstd, o.ACT_RELU, M, C, red)
+    dy = torch.empty((M, C), dtype=dtype, device=DEV)
+    o.bn_bwd_apply(gzd, yd, scale, shift, mean, invstd, o.ACT_RELU, red, M, C, dy)
+    # gradients w.r.t. beta / gamma recomputed from the same bf16-rounded forward
+    g_eff = gz.double() * (z_ref.view(M, C) > 0).double()
+    xhat = (y.double() - y.double().mean(0)) / torch.sqrt(y.double().var(0, unbiased=False) + eps)
+    check("bn dbeta", red[0], g_eff.sum(0), 2e-3, 2e-3 * math.sqrt(M))
+    check("bn dgamma", red[1], (g_eff * xhat).sum(0), 2e-3, 2e-3 * math.sqrt(M))
+    check("bn dx", dy, yr.grad.view(M, C), rt, at)
+
+
+def test_bn_fold_inference():
+    o = ops()
+    C = 48
+    gamma, beta = rnd((C,), torch.float32, 1) + 1, rnd((C,), torch.float32, 2)
+    mm, mv = rnd((C,), torch.float32, 3), rnd((C,), torch.float32, 4).abs() + 0.1
+    scale, shift = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    o.bn_fold(gamma.to(DEV), beta.to(DEV), mm.to(DEV), mv.to(DEV), C, 1e-3, scale, shift)
+    x = rnd((1, 1, 5, C), torch.float32, 5)
+    ref, _, _ = O.batch_norm(x.double(), gamma.double(), beta.double(), mm.double(), mv.double(), 1e-3, False)
+    check("bn fold", x.to(DEV) * scale + shift, ref, 1e-5, 1e-5)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("HW", [(254, 254), (127, 127), (64, 64), (9, 12)])
+def test_maxpool_add(HW, dtype):
+    o = ops()
+    H, W = HW
+    N, C = 1, 16
+    x = rnd((N, H, W, C), dtype, 101)
+    xr = x.double().requires_grad_(True)
+    y_ref = O.max_pool_3x3_s2_same(xr)
+    res = rnd(tuple(y_ref.shape), dtype, 102)
+    gy = rnd(tuple(y_ref.shape), dtype, 103)
+    y_ref.backward(gy.double())
+    am = torch.empty(tuple(y_ref.shape), dtype=torch.uint8, device=DEV)
+    y = o.maxpool3x3s2_fwd(x.to(DEV), argmax=am, addend=res.to(DEV))
+    rt, at = tol(dtype)
+    check("maxpool", y, y_ref + res.double(), rt, at)
+    add = rnd((N, H, W, C), dtype, 104)
+    dx = o.maxpool3x3s2_bwd(gy.to(DEV), am, (N, H, W, C), addend=add.to(DEV))
+    check("maxpool bwd", dx, xr.grad + add.double(), rt, at * 2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_avgpool(dtype):
+    o = ops()
+    x = rnd((2, 8, 12, 32), dtype, 111)
+    xr = x.double().requires_grad_(True)
+    y_ref = O.avg_pool_valid(xr, 4)
+    gy = rnd(tuple(y_ref.shape), dtype, 112)
+    y_ref.backward(gy.double())
+    y = o.avgpool_fwd(x.to(DEV), 4)
+    rt, at = tol(dtype)
+    check("avgpool", y, y_ref, rt, at)
+    dx = o.avgpool_bwd(gy.to(DEV), (2, 8, 12, 32), 4)
+    check("avgpool bwd", dx, xr.grad, rt, at)
+
+
+@pytest.mark.parametrize("case", [(2, 5, 7, 21, 16, 16, torch.float32), (1, 9, 9, 48, 8, 8, torch.bfloat16),
+                                  (1, 6, 5, 256, 4, 4, torch.bfloat16), (2, 4, 4, 21, 2, 2, torch.float32),
+                                  (1, 3, 4, 8, 1, 1, torch.float32), (1, 33, 33, 21, 16, 16, torch.float32)])
+def test_bilinear(case):
+    o = ops()
+    N, H, W, C, fh, fw, dtype = case
+    x = rnd((N, H, W, C), dtype, 121)
+    xr = x.double().requires_grad_(True)
+    y_ref = O.resize_bilinear(xr, fh, fw)
+    t_ref = torch.nn.functional.interpolate(x.double().permute(0, 3, 1, 2), scale_factor=(fh, fw), mode="bilinear",
+                                            align_corners=False).permute(0, 2, 3, 1)
+    check("oracle resize vs torch", y_ref, t_ref, 1e-12, 1e-12)
+    gy = rnd(tuple(y_ref.shape), dtype, 122)
+    y_ref.backward(gy.double())
+    y = o.bilinear_fwd(x.to(DEV), fh, fw)
+    rt, at = tol(dtype)
+    check("bilinear", y, y_ref, rt, at)
+    dx = o.bilinear_bwd(gy.to(DEV), (N, H, W, C), fh, fw)
+    check("bilinear bwd", dx, xr.grad, rt, at * fh)
+
+
+def _labels(shape, C, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, C, shape, generator=g, dtype=torch.int32)
+
+
+PW = [0.29754999, 0.99106889, 0.99236374, 0.99122957, 0.99350396, 0.99455487, 0.98728424, 0.98090446, 0.96883489,
+      0.98753125, 0.99376389, 0.98942612, 0.97222875, 0.99080578, 0.98845309, 0.92606652, 0.99393374, 0.99374322,
+      0.98782171, 0.98659656, 0.99233476]
+NW = [1.0 - v for v in PW]
+
+
+def test_softmax_cbloss():
+    o = ops()
+    P, C = 5000, 21
+    z = rnd((P, C), torch.float32, 131, 3.0)
+    lab = _labels((P,), C, 132)
+    zr = z.double().requires_grad_(True)
+    p_ref = O.softmax(zr)
+    loss_ref = O.class_balanced_loss(O.one_hot(lab, C), p_ref, PW, NW)
+    loss_ref.backward()
+    pw, nw = torch.tensor(PW, device=DEV), torch.tensor(NW, device=DEV)
+    ls = torch.zeros(1, device=DEV)
+    probs = torch.empty((P, C), device=DEV)
+    o.softmax_cbloss_fwd(z.to(DEV), lab.to(DEV), pw, nw, 1e-7, P, C, ls, probs)
+    check("probs", probs, p_ref, 1e-5, 1e-6)
+    check("loss", ls / P, loss_ref.reshape(1), 1e-4, 1e-6)
+    dz = torch.empty((P, C), device=DEV)
+    o.softmax_cbloss_bwd(z.to(DEV), lab.to(DEV), pw, nw, 1e-7, P, C, 1.0 / P, dz)
+    check("dz", dz, zr.grad, 1e-3, 1e-8)
+    # argmax / label map
+    labels = torch.empty(P, dtype=torch.int32, device=DEV)
+    o.softmax_argmax(z.to(DEV), P, C, labels=labels)
+    assert torch.equal(labels.cpu().long(), O.argmax_labels(z))
+    # dense (Keras-signature) loss
+    yt = O.one_hot(lab, C, torch.float32)
+    ls2 = torch.zeros(1, device=DEV)
+    o.cbloss_dense_fwd(yt.to(DEV), probs, pw, nw, 1e-7, P, C, ls2)
+    check("dense loss", ls2 / P, loss_ref.reshape(1), 1e-4, 1e-6)
+    pr = p_ref.detach().clone().requires_grad_(True)
+    O.class_balanced_loss(O.one_hot(lab, C), pr, PW, NW).backward()
+    dyp = torch.empty((P, C), device=DEV)
+    o.cbloss_dense_bwd(yt.to(DEV), probs, pw, nw, 1e-7, P, C, 1.0 / P, dyp)
+    check("dense dloss", dyp, pr.grad, 2e-3, 1e-9)
+    dz2 = torch.empty((P, C), device=DEV)
+    o.softmax_bwd(probs, dyp, P, C, dz2)
+    check("softmax bwd", dz2, zr.grad, 2e-3, 1e-8)
+    cm = torch.zeros((C, C), dtype=torch.float64, device=DEV)
+    o.confusion_matrix(lab.to(DEV), labels, P, C, cm)
+    check("confusion", cm, O.confusion_matrix(lab, labels.cpu(), C), 0, 0)
+
+
+@pytest.mark.parametrize("case", [(2, 6, 7, 21, 16), (1, 5, 5, 21, 2), (1, 4, 6, 19, 8), (2, 3, 3, 21, 4)])
+def test_fused_upsample_softmax_cbloss(case):
+    o = ops()
+    N, H, W, C, f = case
+    zl = rnd((N, H, W, C), torch.float32, 141, 2.0)
+    lab = _labels((N, H * f, W * f), C, 142)
+    zr = zl.double().requires_grad_(True)
+    p_ref = O.softmax(O.resize_bilinear(zr, f, f))
+    loss_ref = O.class_balanced_loss(O.one_hot(lab, C), p_ref, PW[:C], NW[:C])
+    loss_ref.backward()
+    pw, nw = torch.tensor(PW[:C], device=DEV), torch.tensor(NW[:C], device=DEV)
+    P = N * H * f * W * f
+    ls = torch.zeros(1, device=DEV)
+    o.upsample_softmax_cbloss_fwd(zl.to(DEV), lab.to(DEV), pw, nw, 1e-7, N, H, W, C, f, ls)
+    check("fused loss", ls / P, loss_ref.reshape(1), 1e-4, 1e-6)
+    dzl = torch.zeros((N, H, W, C), device=DEV)
+    o.upsample_softmax_cbloss_bwd(zl.to(DEV), lab.to(DEV), pw, nw, 1e-7, N, H, W, C, f, 1.0 / P, dzl)
+    check("fused dzl", dzl, zr.grad, 2e-3, 1e-7)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_eltwise_misc(dtype):
+    o = ops()
+    a, b = rnd((3, 5, 7, 24), dtype, 151), rnd((3, 5, 7, 24), dtype, 152)
+    out = torch.empty_like(a, device=DEV)
+    rt, at = tol(dtype)
+    check("add", o.add(a.to(DEV), b.to(DEV), out), a.double() + b.double(), rt, at)
+    dx = torch.empty_like(a, device=DEV)
+    o.act_bwd(a.to(DEV), b.to(DEV), o.ACT_RELU6, dx, addend=a.to(DEV))
+    m = ((b.double() > 0) & (b.double() < 6)).double()
+    check("act bwd", dx, a.double() * m + a.double(), rt, at)
+    # concat slice copy
+    big = torch.zeros((3 * 5 * 7, 64), dtype=dtype, device=DEV)
+    o.copy2d(a.to(DEV), 24, big, 64, 3 * 5 * 7, 24, y_off=16)
+    check("copy2d", big[:, 16:40], a.view(-1, 24), 0, 0)
+    assert float(big[:, :16].abs().max()) == 0 and float(big[:, 40:].abs().max()) == 0
+    # dropout: same mask fwd/bwd, keep-rate statistics
+    x = torch.ones((1 << 16,), dtype=dtype, device=DEV)
+    y1, y2 = torch.empty_like(x), torch.empty_like(x)
+    o.dropout(x, 0.5, 1234, y1)
+    o.dropout(x, 0.5, 1234, y2)
+    assert torch.equal(y1, y2)
+    keep = float((y1 > 0).float().mean())
+    assert abs(keep - 0.5) < 0.02 and float(y1.max()) == 2.0
+    c = torch.empty((3, 5, 7, 24), dtype=torch.float32 if dtype == torch.bfloat16 else torch.bfloat16, device=DEV)
+    check("cast", o.cast(a.to(DEV), c), a.double(), 1e-2, 1e-2)
+
+
+def test_adam_sumsq():
+    o = ops()
+    n = 10007
+    w, g = rnd((n,), torch.float32, 161), rnd((n,), torch.float32, 162)
+    m, v = torch.zeros(n), torch.zeros(n)
+    lr, b1, b2, eps, l2 = 1e-3, 0.5, 0.99, 1e-7, 4e-5
+    wd, md, vd = w.to(DEV), m.to(DEV), v.to(DEV)
+    wr, mr, vr = w.double().clone(), m.double(), v.double()
+    for t in range(1, 4):
+        lr_t = lr * math.sqrt(1 - b2 ** t) / (1 - b1 ** t)
+        o.adam(wd, g.to(DEV), md, vd, n, lr_t, b1, b2, eps, 1.0, l2)
+        ge = g.double() + 2 * l2 * wr
+        mr = b1 * mr + (1 - b1) * ge
+        vr = b2 * vr + (1 - b2) * ge * ge
+        wr = wr - lr_t * mr / (vr.sqrt() + eps)
+    check("adam", wd, wr, 1e-4, 1e-6)
+    s = torch.zeros(1, device=DEV)
+    o.sumsq(w.to(DEV), n, s)
+    check("sumsq", s, (w.double() ** 2).sum().reshape(1), 1e-4, 0)
+
+
+def test_errors_are_loud():
+    o = ops()
+    x = torch.zeros((1, 4, 4, 12), device=DEV)
+    w = torch.zeros((3, 3, 12), device=DEV)
+    with pytest.raises(ValueError):
+        o.dwconv3x3_fwd(x, w)          # C not a multiple of 8
+    with pytest.raises(ValueError):
+        o.dwconv3x3_fwd(torch.zeros((1, 4, 4, 8)), torch.zeros((3, 3, 8)))   # CPU tensor: no CPU path
