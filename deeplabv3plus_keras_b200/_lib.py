@@ -55,14 +55,16 @@ SIGNATURES = {
     "dlv3p_cbloss_dense_bwd": [_p, _p, _p, _p, _f, _l, _i, _f, _p, _p],
     "dlv3p_softmax_bwd": [_p, _p, _l, _i, _p, _p],
     "dlv3p_confusion_matrix": [_p, _p, _l, _i, _p, _p],
-    "dlv3p_dropout": [_p, _p, _l, _f, _u64, _p, _i, _p],
+    "dlv3p_dropout": [_p, _p, _l, _f, _u64, _p, _p, _i, _p],
     "dlv3p_adam": [_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _p],
     "dlv3p_sumsq": [_p, _l, _p, _p],
     "dlv3p_cast": [_p, _i, _p, _i, _l, _p],
+    "dlv3p_cast2d": [_p, _l, _i, _p, _l, _i, _l, _i, _p],
 }
 _PLAIN = {"dlv3p_version": [], "dlv3p_device_arch": []}
 
 _lib = None
+PROFILER = None      # set to a profiler.KernelProfiler to bracket every entry-point call with CUDA events
 
 
 def load() -> C.CDLL:
@@ -92,7 +94,13 @@ def last_error() -> str:
 def call(name: str, *args) -> None:
     """Invoke an entry point; translate a negative status into the Python exception the reference would raise
     (ValueError for bad shapes/config — cf. ss.py:771,858 — RuntimeError for device failures)."""
-    rc = getattr(load(), name)(*args)
+    prof = PROFILER
+    if prof is not None:
+        tok = prof.before(name, args)
+        rc = getattr(load(), name)(*args)
+        prof.after(tok)
+    else:
+        rc = getattr(load(), name)(*args)
     if rc != 0:
         msg = f"{name} failed ({rc}): {last_error()}"
         if rc in (ERR_SHAPE, ERR_DTYPE, ERR_ALIGN, ERR_UNSUPPORTED):

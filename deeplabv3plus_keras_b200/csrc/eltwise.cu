@@ -642,9 +642,10 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, float rate, uint64_t seed,
-               const T* __restrict__ addend) {
+               const uint64_t* __restrict__ seed_offset, const T* __restrict__ addend) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (seed_offset != nullptr) seed += *seed_offset;
     const uint64_t h = splitmix64(seed * 0xD1342543DE82EF95ull + (uint64_t)i);
     const float u = (float)(h >> 40) * (1.0f / 16777216.0f);   // [0,1)
     float v = (u >= rate) ? to_f<T>(x[i]) / (1.f - rate) : 0.f;
@@ -679,6 +680,15 @@ sumsq_kernel(const float* __restrict__ w, long long n, float* __restrict__ out) 
         for (int k = 0; k < 8; ++k) tsum += part[k];
         atomicAdd(out, tsum);
     }
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+cast2d_kernel(const TI* __restrict__ x, long long ld_x, TO* __restrict__ y, long long ld_y, long long M, int C) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * C) return;
+    const long long r = i / C; const int c = (int)(i % C);
+    y[r * ld_y + c] = from_f<TO>(to_f<TI>(x[r * ld_x + c]));
 }
 
 template <typename TI, typename TO>
@@ -1040,12 +1050,12 @@ extern "C" int dlv3p_weight_prep(const float* w, int K, int N, void* wt, int64_t
     return check_launch("weight_prep");
 }
 
-extern "C" int dlv3p_dropout(const void* x, void* y, int64_t n, float rate, uint64_t seed, const void* addend,
-                             int dtype, void* stream) {
+extern "C" int dlv3p_dropout(const void* x, void* y, int64_t n, float rate, uint64_t seed,
+                             const uint64_t* seed_offset, const void* addend, int dtype, void* stream) {
     DLV3P_REQUIRE(x && y && n > 0 && rate >= 0.f && rate < 1.f, DLV3P_ERR_SHAPE, "dropout: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     DLV3P_DISPATCH_DTYPE(dtype, T, {
-        dropout_kernel<T><<<cdiv(n, 256), 256, 0, st>>>((const T*)x, (T*)y, n, rate, seed, (const T*)addend);
+        dropout_kernel<T><<<cdiv(n, 256), 256, 0, st>>>((const T*)x, (T*)y, n, rate, seed, seed_offset, (const T*)addend);
         return check_launch("dropout");
     });
     return 0;
@@ -1072,6 +1082,17 @@ extern "C" int dlv3p_cast(const void* x, int x_dtype, void* y, int y_dtype, int6
     DLV3P_DISPATCH_2DTYPE(x_dtype, TI, y_dtype, TO, {
         cast_kernel<TI, TO><<<cdiv(n, 256), 256, 0, st>>>((const TI*)x, (TO*)y, n);
         return check_launch("cast");
+    });
+    return 0;
+}
+
+extern "C" int dlv3p_cast2d(const void* x, int64_t ld_x, int x_dtype, void* y, int64_t ld_y, int y_dtype, int64_t M,
+                            int C, void* stream) {
+    DLV3P_REQUIRE(x && y && M > 0 && C > 0 && ld_x >= C && ld_y >= C, DLV3P_ERR_SHAPE, "cast2d: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    DLV3P_DISPATCH_2DTYPE(x_dtype, TI, y_dtype, TO, {
+        cast2d_kernel<TI, TO><<<cdiv(M * C, 256), 256, 0, st>>>((const TI*)x, ld_x, (TO*)y, ld_y, M, C);
+        return check_launch("cast2d");
     });
     return 0;
 }

@@ -1,0 +1,999 @@
+"""Execution engine: lowers a keras.Model layer graph to a static schedule of libdlv3p kernel launches.
+
+No tracing compiler: the graph is flattened (nested models expanded, repeated calls of a shared sub-model on the
+same tensor de-duplicated), neighbouring layers are fused into macro-ops by pattern (Conv/SeparableConv/Depthwise
+-> BatchNormalization -> ReLU/ReLU6 -> Add; MaxPooling -> Add; pre-activation ReLU -> depthwise prologue), every
+activation / gradient / workspace buffer is allocated once at plan time, and forward + explicit backward are lists
+of closures over raw device pointers, so that a whole training step can be captured in a CUDA graph and replayed.
+The backward schedule is written by hand per macro-op (there is no autograd anywhere on the product path).
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import ACT_NONE, ACT_RELU, ACT_RELU6
+from .keras import layers as L
+from .keras.base import InputLayer, KTensor, Layer
+from .keras.models import Model
+
+_TORCH_DT = {"float32": torch.float32, "bfloat16": torch.bfloat16}
+
+
+def _ceil8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+class Value:
+    """A materialised NHWC activation, its gradient buffer and pending (zero-copy) gradient contributions."""
+
+    def __init__(self, shape, dtype, buf=None, name=""):
+        self.shape = tuple(shape)
+        self.dtype = dtype
+        self.buf: Optional[torch.Tensor] = buf
+        self.name = name
+        self.needs_grad = False
+        self.grad: Optional[torch.Tensor] = None
+        self.grad_written = False          # plan-time state of the backward schedule
+        self.pending: List[torch.Tensor] = []
+        self.pre_act = ACT_NONE            # consumers must apply this activation on load (virtual pre-activation)
+
+    @property
+    def M(self):
+        return self.shape[0] * self.shape[1] * self.shape[2]
+
+    @property
+    def C(self):
+        return self.shape[3]
+
+
+class FlatNode:
+    def __init__(self, layer: Layer, inputs: List[int], output: int, shape, dtype):
+        self.layer, self.inputs, self.output, self.shape, self.dtype = layer, inputs, output, shape, dtype
+        self.calls = 1
+        self.absorbed = False
+
+
+def flatten(model: Model) -> Tuple[List[FlatNode], List[int], List[int]]:
+    """Expand nested models; identical (layer, inputs) applications are merged (the reference calls the shared
+    `base` twice on the same image when boundary refinement is on, ss.py:802 and :930)."""
+    nodes: List[FlatNode] = []
+    cse: Dict[Tuple, int] = {}
+    counter = [0]
+
+    def new_id():
+        counter[0] += 1
+        return counter[0]
+
+    def run(m: Model, in_ids: List[int]) -> List[int]:
+        env: Dict[int, int] = {id(t): i for t, i in zip(m.inputs, in_ids)}
+        for n in m.nodes:
+            out_t = n.outputs
+            if isinstance(n.layer, InputLayer):
+                if id(out_t[0]) not in env:
+                    raise ValueError(f"unbound input {n.layer.name}")
+                continue
+            ins = [env[id(t)] for t in n.inputs]
+            if isinstance(n.layer, Model):
+                outs = run(n.layer, ins)
+                for t, o in zip(out_t, outs):
+                    env[id(t)] = o
+                continue
+            key = (id(n.layer), tuple(ins))
+            if key in cse:
+                fn = nodes[cse[key]]
+                fn.calls += 1
+                env[id(out_t[0])] = fn.output
+                continue
+            oid = new_id()
+            cse[key] = len(nodes)
+            nodes.append(FlatNode(n.layer, ins, oid, out_t[0].shape, out_t[0].dtype))
+            env[id(out_t[0])] = oid
+        return [env[id(t)] for t in m.outputs]
+
+    in_ids = [new_id() for _ in model.inputs]
+    out_ids = run(model, in_ids)
+    return nodes, in_ids, out_ids
+
+
+class ParamStore:
+    """Flat fp32 arenas: trainable weights (L2-regularised kernels first), their gradients and Adam moments, and
+    the non-trainable BatchNormalization moving statistics."""
+
+    def __init__(self, layers_in_order: List[Layer], device):
+        self.device = device
+        self.entries: Dict[Tuple[int, str], Tuple[str, int, Tuple]] = {}
+        reg, plain, frozen = [], [], []
+        for l in layers_in_order:
+            for n in l.weight_names():
+                w = l._weights[n]
+                if not l._trainable[n]:
+                    frozen.append((l, n, w))
+                elif n == "kernel" and getattr(l, "kernel_regularizer", None) is not None:
+                    reg.append((l, n, w))
+                else:
+                    plain.append((l, n, w))
+        self.l2 = 0.0
+        for l, _, _ in reg:
+            lam = l.kernel_regularizer.l2
+            if self.l2 and abs(lam - self.l2) > 0:
+                raise ValueError("a single L2 coefficient per model is supported (hps.weight_decay)")
+            self.l2 = lam
+
+        def lay(items, kind, start=0):
+            off = start
+            for l, n, w in items:
+                self.entries[(id(l), n)] = (kind, off, tuple(w.shape))
+                off += _ceil8(w.size)          # keep every parameter 32-byte aligned
+            return off
+
+        self.n_reg = lay(reg, "w")
+        self.n_train = lay(plain, "w", self.n_reg)
+        self.n_frozen = lay(frozen, "f")
+        self._items = reg + plain + frozen
+        self.w = torch.zeros(max(self.n_train, 8), dtype=torch.float32, device=device)
+        self.g = torch.zeros_like(self.w)
+        self.m = torch.zeros_like(self.w)
+        self.v = torch.zeros_like(self.w)
+        self.f = torch.zeros(max(self.n_frozen, 8), dtype=torch.float32, device=device)
+        self.num_params = int(sum(w.size for _, n, w in reg + plain))
+
+    def view(self, layer: Layer, name: str, grad=False) -> torch.Tensor:
+        kind, off, shape = self.entries[(id(layer), name)]
+        n = int(np.prod(shape))
+        arena = (self.g if grad else self.w) if kind == "w" else self.f
+        return arena[off:off + n].view(shape)
+
+    def has(self, layer: Layer, name: str) -> bool:
+        return (id(layer), name) in self.entries
+
+    def upload(self):
+        host_w = np.zeros(self.w.numel(), dtype=np.float32)
+        host_f = np.zeros(self.f.numel(), dtype=np.float32)
+        for l, n, w in self._items:
+            kind, off, _ = self.entries[(id(l), n)]
+            (host_w if kind == "w" else host_f)[off:off + w.size] = w.reshape(-1)
+        self.w.copy_(torch.from_numpy(host_w))
+        self.f.copy_(torch.from_numpy(host_f))
+
+    def download(self):
+        host_w, host_f = self.w.cpu().numpy(), self.f.cpu().numpy()
+        for l, n, w in self._items:
+            kind, off, _ = self.entries[(id(l), n)]
+            w[...] = (host_w if kind == "w" else host_f)[off:off + w.size].reshape(w.shape)
+
+
+class Plan:
+    """A model lowered for one (batch size, training flag, dtype).  See module docstring."""
+
+    def __init__(self, model: Model, batch_size: int, training: bool = False, dtype: Optional[str] = None,
+                 device: Optional[str] = None, dropout_seed: int = 1024, fused_tail: bool = True):
+        fake = getattr(ops, "FAKE", False)       # tests/fake_ops.py test double (host-logic tests without a GPU)
+        if not torch.cuda.is_available() and not fake:
+            raise RuntimeError("engine.Plan needs a CUDA device: there is no CPU execution path")
+        self.model, self.N, self.training = model, batch_size, training
+        self.device = torch.device("cpu") if fake else torch.device(device or f"cuda:{torch.cuda.current_device()}")
+        act_dtype = dtype or model.inputs[0].dtype
+        if act_dtype not in _TORCH_DT:
+            raise ValueError(f"hps.dtype must be 'float32' or 'bfloat16', got {act_dtype!r}")
+        self.dt = _TORCH_DT[act_dtype]
+        self.bf16 = self.dt == torch.bfloat16
+        self.fused_tail = fused_tail
+        self.dropout_seed = dropout_seed
+        self.fwd: List[Callable[[], None]] = []
+        self.bwd: List[Callable[[], None]] = []
+        self.prep: List[Callable[[], None]] = []        # bf16 weight copies / BN folding, after each weight update
+        self._bwd_thunks: List[Callable[[], None]] = []
+        self.launches_fwd = self.launches_bwd = 0
+        self._scratch: Dict[str, torch.Tensor] = {}
+        self._stat_slices: List[Tuple[int, int]] = []
+        self._stats_total = 0
+        self.step_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+
+        self.nodes, in_ids, out_ids = flatten(model)
+        if len(in_ids) != 1 or len(out_ids) != 1:
+            raise ValueError("Plan supports single-input single-output models (the DeepLabV3+ graph)")
+        weight_layers = [l for l in model.flat_layers() if l._weights]
+        self.params = ParamStore(weight_layers, self.device)
+        self.params.upload()
+
+        self.values: Dict[int, Value] = {}
+        H, W, Cin = model.inputs[0].shape[1:]
+        self.x_in = Value((self.N, H, W, Cin), self.dt, self._alloc((self.N, H, W, Cin), self.dt), "image")
+        self.values[in_ids[0]] = self.x_in
+        self._lower(out_ids[0])
+        self.stats = torch.zeros(max(self._stats_total, 8), dtype=torch.float32, device=self.device)
+        self.run_prep()
+        self.graph = None
+        self.finalize()
+
+    # ------------------------------------------------------------------------------------------------ utils
+    def _alloc(self, shape, dtype, zero=False):
+        return (torch.zeros if zero else torch.empty)(tuple(shape), dtype=dtype, device=self.device)
+
+    def scratch(self, key: str, numel: int, dtype) -> torch.Tensor:
+        """Shared workspace for temporaries that only live inside one macro-op's backward."""
+        nbytes = numel * torch.tensor([], dtype=dtype).element_size()
+        cur = self._scratch.get(key)
+        if cur is None or cur.numel() < nbytes:
+            self._scratch[key] = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+            # earlier closures captured views of the old buffer; force re-resolution by always going through _sv
+        return self._scratch[key]
+
+    def _sv(self, key: str, shape, dtype) -> torch.Tensor:
+        numel = int(np.prod(shape))
+        buf = self._scratch[key]
+        esz = torch.tensor([], dtype=dtype).element_size()
+        return buf[:numel * esz].view(dtype).view(shape)
+
+    def _reserve(self, key: str, shape, dtype):
+        self.scratch(key, int(np.prod(shape)), dtype)
+        return lambda: self._sv(key, shape, dtype)
+
+    def _stat_slot(self, C: int) -> Callable[[], torch.Tensor]:
+        off = self._stats_total
+        self._stats_total += 2 * C
+        return lambda: self.stats[off:off + 2 * C]
+
+    def _grad_of(self, v: Value) -> torch.Tensor:
+        if v.grad is None:
+            gd = torch.float32 if v.dtype == torch.float32 else self.dt
+            v.grad = self._alloc(v.shape, gd)
+        return v.grad
+
+    def _grad_target(self, v: Value) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        """(buffer to write, addend) for a real gradient writer, given what the schedule has emitted so far."""
+        g = self._grad_of(v)
+        if v.grad_written:
+            return g, g
+        v.grad_written = True
+        if v.pending:
+            return g, v.pending.pop()
+        return g, None
+
+    def _final_grad(self, v: Value) -> Optional[torch.Tensor]:
+        """The complete gradient of `v` at the point its producer's backward runs (emits adds if needed)."""
+        if not v.grad_written:
+            if not v.pending:
+                return None
+            if len(v.pending) == 1:
+                return v.pending[0]                      # pure pass-through: alias, no copy
+            g = self._grad_of(v)
+            a, b = v.pending.pop(), v.pending.pop()
+            self.bwd_seq(lambda a=a, b=b, g=g: ops.add(a, b, g))
+            v.grad_written = True
+        g = self._grad_of(v)
+        while v.pending:
+            p = v.pending.pop()
+            self.bwd_seq(lambda p=p, g=g: ops.add(g, p, g))
+        return g
+
+    # ---------------------------------------------------------------------------------------------- lowering
+    def _lower(self, out_id: int):
+        nodes = self.nodes
+        consumers: Dict[int, List[FlatNode]] = {}
+        for n in nodes:
+            for i in n.inputs:
+                consumers.setdefault(i, []).append(n)
+        producer = {n.output: n for n in nodes}
+
+        def sole(tid) -> Optional[FlatNode]:
+            c = consumers.get(tid, [])
+            return c[0] if len(c) == 1 and tid != out_id else None
+
+        def act_code(layer) -> Optional[int]:
+            if isinstance(layer, L.Activation) and layer.activation == "relu":
+                return ACT_RELU
+            if isinstance(layer, L.ReLU):
+                return ACT_RELU6 if layer.max_value else ACT_RELU
+            return None
+
+        conv_like = (L.Conv2D, L.SeparableConv2D, L.DepthwiseConv2D)
+        # ---- pattern pass: build macro-ops -------------------------------------------------------------
+        macros: Dict[int, dict] = {}            # keyed by index of the node where the macro is emitted
+        index = {id(n): i for i, n in enumerate(nodes)}
+        for n in nodes:
+            if n.absorbed:
+                continue
+            if isinstance(n.layer, L.ZeroPadding2D):
+                c = sole(n.output)
+                if c is None or not isinstance(c.layer, (L.DepthwiseConv2D, L.Conv2D)) or c.layer.padding != "valid":
+                    raise NotImplementedError("ZeroPadding2D is only supported directly before a VALID convolution")
+                n.absorbed = True
+                c.explicit_pad = n.layer.padding
+                c.inputs = list(n.inputs)
+                consumers[n.inputs[0]] = [c if x is n else x for x in consumers[n.inputs[0]]]
+                continue
+            if isinstance(n.layer, conv_like):
+                m = dict(kind="conv", conv=n, bn=None, act=ACT_NONE, other=None, out=n.output, tail=n)
+                nxt = sole(n.output)
+                if nxt is not None and isinstance(nxt.layer, L.BatchNormalization):
+                    m["bn"], m["out"], m["tail"] = nxt, nxt.output, nxt
+                    nxt.absorbed = True
+                    nxt = sole(nxt.output)
+                    if nxt is not None and act_code(nxt.layer) is not None:
+                        m["act"], m["out"], m["tail"] = act_code(nxt.layer), nxt.output, nxt
+                        nxt.absorbed = True
+                        nxt = sole(nxt.output)
+                    elif nxt is not None and isinstance(nxt.layer, L.Add) and not nxt.absorbed:
+                        other = [i for i in nxt.inputs if i != m["out"]]
+                        if len(other) == 1:
+                            m["other"], m["out"], m["tail"] = other[0], nxt.output, nxt
+                            nxt.absorbed = True
+                n.absorbed = True
+                macros[index[id(m["tail"])]] = m
+            elif isinstance(n.layer, L.MaxPooling2D):
+                m = dict(kind="maxpool", node=n, other=None, out=n.output, tail=n)
+                nxt = sole(n.output)
+                if nxt is not None and isinstance(nxt.layer, L.Add) and not nxt.absorbed:
+                    other = [i for i in nxt.inputs if i != n.output]
+                    if len(other) == 1:
+                        m["other"], m["out"], m["tail"] = other[0], nxt.output, nxt
+                        nxt.absorbed = True
+                n.absorbed = True
+                macros[index[id(m["tail"])]] = m
+
+        # ---- emission in topological order ---------------------------------------------------------------
+        for i, n in enumerate(nodes):
+            if i in macros:
+                m = macros[i]
+                if m["kind"] == "conv":
+                    self._emit_conv(m, out_id)
+                else:
+                    self._emit_maxpool(m)
+                continue
+            if n.absorbed:
+                continue
+            lay = n.layer
+            code = act_code(lay)
+            if code is not None:
+                self._emit_act(n, code, consumers)
+            elif isinstance(lay, L.Activation) and lay.activation == "softmax":
+                if n.output != out_id:
+                    raise NotImplementedError("softmax is only supported as the model output")
+                self._emit_softmax_tail(n, producer)
+            elif isinstance(lay, L.Activation) and lay.activation == "linear":
+                self.values[n.output] = self.values[n.inputs[0]]
+            elif isinstance(lay, L.Add):
+                self._emit_add(n)
+            elif isinstance(lay, L.AveragePooling2D):
+                self._emit_avgpool(n)
+            elif isinstance(lay, L.ResizeImages):
+                self._emit_resize(n, out_id, consumers)
+            elif isinstance(lay, L.Concatenate):
+                self._emit_concat(n)
+            elif isinstance(lay, L.Dropout):
+                self._emit_dropout(n)
+            elif isinstance(lay, L.BatchNormalization):
+                raise NotImplementedError(f"BatchNormalization '{lay.name}' not preceded by a convolution")
+            else:
+                raise NotImplementedError(f"layer type {type(lay).__name__} is not on the hot path")
+        self.out_value = self.values.get(out_id)
+
+    def _input_of(self, tid: int, allow_pre_act: bool) -> Value:
+        v = self.values[tid]
+        if v.pre_act != ACT_NONE and not allow_pre_act:
+            raise NotImplementedError("internal: virtual activation reached a consumer that cannot fuse it")
+        return v
+
+    # ---- conv macro-op ---------------------------------------------------------------------------------
+    def _emit_conv(self, m: dict, out_id: int):
+        P, N = self.params, self.N
+        node: FlatNode = m["conv"]
+        lay = node.layer
+        x = self._input_of(node.inputs[0], allow_pre_act=isinstance(lay, (L.SeparableConv2D, L.DepthwiseConv2D)))
+        _, H, W, Cin = x.shape
+        training = self.training
+        bn_node, act, other_id = m["bn"], m["act"], m["other"]
+        is_sep, is_dw = isinstance(lay, L.SeparableConv2D), isinstance(lay, L.DepthwiseConv2D)
+        stride = lay.strides[0]
+        dil = lay.dilation_rate
+        k = 3 if (is_sep or is_dw) else lay.kernel_size[0]
+        # geometry (TF SAME / VALID, or the explicit ZeroPadding2D folded in front of a VALID conv)
+        if getattr(node, "explicit_pad", None) is not None:
+            (pt, pb), (pl, pr) = node.explicit_pad
+            Ho = (H + pt + pb - ((k - 1) * dil[0] + 1)) // stride + 1
+            Wo = (W + pl + pr - ((k - 1) * dil[1] + 1)) // stride + 1
+        else:
+            Ho, Wo, pt, pl = ops.conv_geometry(H, W, k, stride, dil, lay.padding)
+        Mo = N * Ho * Wo
+        Cout = Cin if is_dw else lay.filters
+        out_shape = (N, Ho, Wo, Cout)
+        assert tuple(m["conv"].shape[1:]) == out_shape[1:], (lay.name, m["conv"].shape, out_shape)
+
+        # output dtype: logits (conv without BN feeding the softmax tail) stay fp32
+        is_logits = bn_node is None and not is_dw
+        y_dtype = torch.float32 if is_logits else self.dt
+        ld_out = Cout
+        out = Value(out_shape, y_dtype, self._alloc((N, Ho, Wo, ld_out), y_dtype), lay.name)
+        self.values[m["out"]] = out
+        other = self.values[other_id] if other_id is not None else None
+        needs_in_grad = x.needs_grad
+        out.needs_grad = training
+
+        # ---- parameters
+        dw_w = P.view(lay, "depthwise_kernel").view(3, 3, Cin) if (is_sep or is_dw) else None
+        dw_g = P.view(lay, "depthwise_kernel", grad=True).view(3, 3, Cin) if (is_sep or is_dw) else None
+        gemm = not is_dw
+        if gemm:
+            wname = "pointwise_kernel" if is_sep else "kernel"
+            Kdim = Cin if (is_sep or k == 1) else 9 * Cin
+            Kp = _ceil8(Kdim)
+            Np = _ceil8(Cout)
+            w32 = P.view(lay, wname).view(Kdim, Cout)
+            g32 = P.view(lay, wname, grad=True).view(Kdim, Cout)
+            if self.bf16:
+                wt = self._alloc((Cout, Kp), torch.bfloat16, zero=True)       # [N,K] K-major: forward B operand
+                wn = self._alloc((Kdim, Np), torch.bfloat16, zero=True) if training else None   # dgrad B operand
+                self.prep.append(lambda: ops.weight_prep(w32, Kdim, Cout, wt, Kp, wn, Np))
+        # ---- BatchNormalization state
+        if bn_node is not None:
+            bn = bn_node.layer
+            C = Cout
+            gamma = P.view(bn, "gamma") if P.has(bn, "gamma") else None
+            beta = P.view(bn, "beta") if P.has(bn, "beta") else None
+            mm, mv = P.view(bn, "moving_mean"), P.view(bn, "moving_variance")
+            scale, shift = self._alloc((C,), torch.float32), self._alloc((C,), torch.float32)
+            if training:
+                mean, invstd = self._alloc((C,), torch.float32), self._alloc((C,), torch.float32)
+                stat = self._stat_slot(C)
+                # BN parameter gradients: [dbeta | dgamma] must be contiguous for the reduce kernel
+                red_slot = self._stat_slot(C)
+                y = self._alloc((N, Ho, Wo, Cout), self.dt)          # raw conv output, saved for backward
+            else:
+                self.prep.append(lambda: ops.bn_fold(gamma, beta, mm, mv, C, bn.epsilon, scale, shift))
+                y = None
+        else:
+            y = out.buf
+
+        in_act = x.pre_act
+        pad4 = (Ho, Wo, pt, pl)
+        xb = x.buf
+        launches_f = 0
+
+        # ---- forward ------------------------------------------------------------------------------------
+        # A operand of the GEMM
+        if is_sep or is_dw:
+            d = self._alloc((N, Ho, Wo, Cin), self.dt) if is_sep else None
+            dw_out = d if is_sep else (y if (bn_node is not None and training) else None)
+            if is_dw and dw_out is None:
+                # inference depthwise+BN: conv into `out`, then fold BN in place
+                dw_out = out.buf
+            self.fwd.append(lambda: ops.dwconv3x3_fwd(xb, dw_w, stride, dil, in_act=in_act, out=dw_out, pad=pad4))
+            launches_f += 1
+            A, lda = d, Cin
+        elif k == 1 and stride == 1:
+            A, lda = xb, Cin
+        elif k == 1:
+            xs = self._alloc((N, Ho, Wo, Cin), self.dt)
+            self.fwd.append(lambda: ops.subsample_fwd(xb, stride, out=xs))
+            launches_f += 1
+            A, lda = xs, Cin
+        else:
+            col = self._alloc((Mo, Kp), self.dt)
+            self.fwd.append(lambda: ops.im2col3x3(xb, stride, dil[0], Ho, Wo, pt, pl, Kp, out=col))
+            launches_f += 1
+            A, lda = col, Kp
+
+        fuse_epi = (bn_node is not None and not training)      # inference: BN folded into the GEMM epilogue
+        addend_f = other.buf if other is not None else None
+        if gemm:
+            Kg = lda if (k == 3 and not is_sep) else Kdim
+            if self.bf16:
+                tgt = out.buf if (fuse_epi or bn_node is None) else y
+                stats_fn = stat if (bn_node is not None and training) else None
+                self.fwd.append(lambda: ops.gemm_bf16(
+                    A, wt, Mo, Cout, Kg, tgt, lda=lda, ldb=Kp, ldc=Cout,
+                    col_scale=scale if fuse_epi else None, col_shift=shift if fuse_epi else None,
+                    act=act if fuse_epi else ACT_NONE, addend=addend_f if fuse_epi else None, ld_addend=Cout,
+                    col_stats=stats_fn() if stats_fn else None))
+            else:
+                tgt = out.buf if (fuse_epi or bn_node is None) else y
+                self.fwd.append(lambda: ops.gemm_simt(
+                    A, lda, 1, w32, Cout, 1, tgt, Cout, Mo, Cout, Kdim,
+                    col_scale=scale if fuse_epi else None, col_shift=shift if fuse_epi else None,
+                    act=act if fuse_epi else ACT_NONE, addend=addend_f if fuse_epi else None, ld_addend=Cout))
+            launches_f += 1
+        if bn_node is not None and training:
+            if not (gemm and self.bf16):
+                self.fwd.append(lambda: ops.bn_stats(y, Mo, Cout, stat()))
+                launches_f += 1
+            upd = bn_node.calls
+            for r in range(upd):
+                self.fwd.append(lambda r=r: ops.bn_finalize(stat(), gamma, beta, mm, mv, Cout, Mo, bn.epsilon,
+                                                            bn.momentum, scale, shift, mean, invstd, True))
+                launches_f += 1
+            self.fwd.append(lambda: ops.affine_act(y, Mo, Cout, out.buf, scale, shift, act, addend=addend_f))
+            launches_f += 1
+        elif bn_node is not None and is_dw:
+            self.fwd.append(lambda: ops.affine_act(out.buf, Mo, Cout, out.buf, scale, shift, act, addend=addend_f))
+            launches_f += 1
+        self.launches_fwd += launches_f
+        if not training:
+            return
+
+        # ---- backward (emitted in forward order; the list is reversed at the end, so write steps in REVERSE) --
+        def sched():
+            g = self._final_grad(out)
+            if g is None:
+                raise RuntimeError(f"no gradient reaches {lay.name}")
+            if other is not None:
+                other.pending.append(g)
+            # dy: gradient w.r.t. the raw conv output
+            if bn_node is not None:
+                dy_get = self._reserve("dy", (Mo, Cout), self.dt)
+                red = red_slot
+                self.bwd_seq(lambda: ops.bn_bwd_reduce(g, y, scale, shift, mean, invstd, act, Mo, Cout, red()))
+                self.bwd_seq(lambda: ops.bn_bwd_apply(g, y, scale, shift, mean, invstd, act, red(), Mo, Cout,
+                                                      dy_get()))
+                # parameter gradients live in the stats arena; copy into the grad arena
+                if beta is not None:
+                    gb = P.view(bn, "beta", grad=True)
+                    self.bwd_seq(lambda: gb.add_(red()[:Cout]))
+                if gamma is not None:
+                    gg = P.view(bn, "gamma", grad=True)
+                    self.bwd_seq(lambda: gg.add_(red()[Cout:]))
+            else:
+                if y_dtype == torch.float32 and self.bf16:
+                    # logits gradient arrives fp32 [M,Cout]; tensor-core operands need bf16 with ld % 8 == 0
+                    dyb = self._alloc((Mo, Np), torch.bfloat16, zero=True)
+                    self.bwd_seq(lambda: ops.cast2d(g, Cout, dyb, Np, Mo, Cout))
+                    dy_get = lambda: dyb
+                else:
+                    dy_get = lambda: g
+            ld_dy = Np if (bn_node is None and y_dtype == torch.float32 and self.bf16) else Cout
+
+            if gemm:
+                # filter gradient
+                if self.bf16:
+                    self.bwd_seq(lambda: ops.gemm_wgrad_bf16(A, dy_get(), g32, Mo, Kdim, Cout, ldx=lda, ldy=ld_dy,
+                                                             ldw=Cout))
+                else:
+                    self.bwd_seq(lambda: ops.gemm_simt(A, 1, lda, dy_get(), ld_dy, 1, g32, Cout, Kdim, Cout, Mo,
+                                                       accumulate=True))
+                need_dA = needs_in_grad
+                if need_dA:
+                    direct = (k == 1 and stride == 1 and not is_sep)
+                    if direct:
+                        tgt, addend = self._grad_target(x)
+                        dA_get = lambda: tgt
+                    else:
+                        shape_dA = (Mo, lda)
+                        dA_get = self._reserve("dA", shape_dA, self.dt)
+                        addend = None
+                    if self.bf16:
+                        # dA[M,K] = dy[M,N] * W[K,N]^T : B operand = wn (rows = K, contraction over Np, zero padded)
+                        self.bwd_seq(lambda: ops.gemm_bf16(dy_get(), wn, Mo, Kdim, ld_dy, dA_get(), lda=ld_dy,
+                                                           ldb=Np, ldc=lda, addend=addend, ld_addend=lda))
+                    else:
+                        self.bwd_seq(lambda: ops.gemm_simt(dy_get(), ld_dy, 1, w32, 1, Cout, dA_get(), lda, Mo, Kdim,
+                                                           Cout, addend=addend, ld_addend=lda))
+                    if is_sep:
+                        self._dw_backward(x, dw_w, dw_g, dA_get, stride, dil, pad4, in_act)
+                    elif k == 1 and stride != 1:
+                        tgt, addend2 = self._grad_target(x)
+                        self.bwd_seq(lambda: ops.subsample_bwd(dA_get().view(N, Ho, Wo, Cin), x.shape, stride,
+                                                               addend=addend2, out=tgt))
+                    elif k == 3:
+                        tgt, addend2 = self._grad_target(x)
+                        self.bwd_seq(lambda: ops.col2im3x3(dA_get(), x.shape, stride, dil[0], Ho, Wo, pt, pl, Kp,
+                                                           addend=addend2, out=tgt))
+                elif is_sep:
+                    # depthwise filter gradient still needs d(dw out) even if the input itself needs no gradient
+                    dA_get = self._reserve("dA", (Mo, lda), self.dt)
+                    if self.bf16:
+                        self.bwd_seq(lambda: ops.gemm_bf16(dy_get(), wn, Mo, Kdim, ld_dy, dA_get(), lda=ld_dy, ldb=Np,
+                                                           ldc=lda))
+                    else:
+                        self.bwd_seq(lambda: ops.gemm_simt(dy_get(), ld_dy, 1, w32, 1, Cout, dA_get(), lda, Mo, Kdim,
+                                                           Cout))
+                    self._dw_backward(x, dw_w, dw_g, dA_get, stride, dil, pad4, in_act, need_dx=False)
+            else:
+                self._dw_backward(x, dw_w, dw_g, dy_get, stride, dil, pad4, in_act, need_dx=needs_in_grad)
+
+        self._defer_backward(sched)
+
+    def _dw_backward(self, x: Value, dw_w, dw_g, dd_get, stride, dil, pad4, in_act, need_dx=True):
+        N = self.N
+        Ho, Wo = pad4[0], pad4[1]
+        Cin = x.C
+        xb = x.buf
+        self.bwd_seq(lambda: ops.dwconv3x3_wgrad(xb, dd_get().view(N, Ho, Wo, Cin), dw_g, stride, dil, in_act=in_act,
+                                                 pad=pad4))
+        if need_dx:
+            tgt, addend = self._grad_target(x)
+            self.bwd_seq(lambda: ops.dwconv3x3_dgrad(dd_get().view(N, Ho, Wo, Cin), dw_w, x.shape, stride, dil,
+                                                     x_pre=xb if in_act != ACT_NONE else None, in_act=in_act,
+                                                     addend=addend, out=tgt, pad=pad4))
+
+    # The backward schedule is generated in REVERSE topological order (so that _final_grad sees every consumer's
+    # contribution): forward emission records one scheduling thunk per macro-op, finalize() runs them backwards
+    # and each thunk appends its kernel launches (in execution order) through bwd_seq.
+    def _defer_backward(self, sched: Callable[[], None]):
+        self._bwd_thunks.append(sched)
+
+    def bwd_seq(self, fn: Callable[[], None]):
+        self.bwd.append(fn)
+        self.launches_bwd += 1
+
+    # ---- other ops ---------------------------------------------------------------------------------------
+    def _emit_maxpool(self, m: dict):
+        n = m["node"]
+        x = self._input_of(n.inputs[0], False)
+        N, H, W, C = x.shape
+        Ho, Wo = -(-H // 2), -(-W // 2)
+        out = Value((N, Ho, Wo, C), self.dt, self._alloc((N, Ho, Wo, C), self.dt), n.layer.name)
+        other = self.values[m["other"]] if m["other"] is not None else None
+        am = self._alloc((N, Ho, Wo, C), torch.uint8) if self.training else None
+        self.values[m["out"]] = out
+        out.needs_grad = self.training
+        addend = other.buf if other is not None else None
+        self.fwd.append(lambda: ops.maxpool3x3s2_fwd(x.buf, out=out.buf, argmax=am, addend=addend))
+        self.launches_fwd += 1
+        if not self.training:
+            return
+
+        def sched():
+            g = self._final_grad(out)
+            if other is not None:
+                other.pending.append(g)
+            if x.needs_grad:
+                tgt, add2 = self._grad_target(x)
+                self.bwd_seq(lambda: ops.maxpool3x3s2_bwd(g, am, x.shape, addend=add2, out=tgt))
+        self._defer_backward(sched)
+
+    def _emit_act(self, n: FlatNode, code: int, consumers):
+        x = self._input_of(n.inputs[0], False)
+        cons = consumers.get(n.output, [])
+        fusable = cons and all(isinstance(c.layer, (L.SeparableConv2D, L.DepthwiseConv2D)) for c in cons)
+        if fusable:
+            # virtual pre-activation: consumers apply it on load and mask it in their input gradient
+            self.values[n.output] = _AliasValue(x, code)
+            return
+        out = Value(x.shape, self.dt, self._alloc(x.shape, self.dt), n.layer.name)
+        out.needs_grad = self.training and x.needs_grad
+        self.values[n.output] = out
+        self.fwd.append(lambda: ops.affine_act(x.buf, x.M, x.C, out.buf, None, None, code))
+        self.launches_fwd += 1
+        if self.training and x.needs_grad:
+            def sched():
+                g = self._final_grad(out)
+                tgt, add2 = self._grad_target(x)
+                self.bwd_seq(lambda: ops.act_bwd(g, x.buf, code, tgt, addend=add2))
+            self._defer_backward(sched)
+
+    def _emit_add(self, n: FlatNode):
+        a, b = self._input_of(n.inputs[0], False), self._input_of(n.inputs[1], False)
+        out = Value(a.shape, self.dt, self._alloc(a.shape, self.dt), n.layer.name)
+        out.needs_grad = self.training
+        self.values[n.output] = out
+        self.fwd.append(lambda: ops.add(a.buf, b.buf, out.buf))
+        self.launches_fwd += 1
+        if self.training:
+            def sched():
+                g = self._final_grad(out)
+                a.pending.append(g)
+                b.pending.append(g)
+            self._defer_backward(sched)
+
+    def _emit_avgpool(self, n: FlatNode):
+        x = self._input_of(n.inputs[0], False)
+        k = n.layer.pool_size[0]
+        if k == 1:
+            self.values[n.output] = x           # identity pool in every shipped config (conf.json:51)
+            return
+        N, H, W, C = x.shape
+        out = Value((N, H // k, W // k, C), self.dt, self._alloc((N, H // k, W // k, C), self.dt), n.layer.name)
+        out.needs_grad = self.training
+        self.values[n.output] = out
+        self.fwd.append(lambda: ops.avgpool_fwd(x.buf, k, out=out.buf))
+        self.launches_fwd += 1
+        if self.training and x.needs_grad:
+            def sched():
+                g = self._final_grad(out)
+                tgt, add2 = self._grad_target(x)
+                self.bwd_seq(lambda: ops.avgpool_bwd(g, x.shape, k, addend=add2, out=tgt))
+            self._defer_backward(sched)
+
+    def _emit_resize(self, n: FlatNode, out_id: int, consumers):
+        x = self._input_of(n.inputs[0], False)
+        fh, fw = n.layer.factors
+        if (fh, fw) == (1, 1):
+            self.values[n.output] = x
+            return
+        N, H, W, C = x.shape
+        cons = consumers.get(n.output, [])
+        tail = (len(cons) == 1 and isinstance(cons[0].layer, L.Activation) and cons[0].layer.activation == "softmax"
+                and cons[0].output == out_id)
+        if tail:
+            # decoder tail: handled by _emit_softmax_tail (fused with the loss in training)
+            self.values[n.output] = _TailResize(x, fh, fw)
+            return
+        out = Value((N, H * fh, W * fw, C), x.dtype, self._alloc((N, H * fh, W * fw, C), x.dtype), n.layer.name)
+        out.needs_grad = self.training
+        self.values[n.output] = out
+        self.fwd.append(lambda: ops.bilinear_fwd(x.buf, fh, fw, out=out.buf))
+        self.launches_fwd += 1
+        if self.training and x.needs_grad:
+            def sched():
+                g = self._final_grad(out)
+                tgt, add2 = self._grad_target(x)
+                self.bwd_seq(lambda: ops.bilinear_bwd(g, x.shape, fh, fw, out=tgt, addend=add2))
+            self._defer_backward(sched)
+
+    def _emit_concat(self, n: FlatNode):
+        ins = [self._input_of(i, False) for i in n.inputs]
+        N, H, W, _ = ins[0].shape
+        Ct = sum(v.C for v in ins)
+        out = Value((N, H, W, Ct), self.dt, self._alloc((N, H, W, Ct), self.dt), n.layer.name)
+        out.needs_grad = self.training
+        self.values[n.output] = out
+        M = N * H * W
+        off = 0
+        for v in ins:
+            self.fwd.append(lambda v=v, off=off: ops.copy2d(v.buf, v.C, out.buf, Ct, M, v.C, y_off=off))
+            self.launches_fwd += 1
+            off += v.C
+        if self.training:
+            def sched():
+                g = self._final_grad(out)
+                o = 0
+                for v in ins:
+                    if v.needs_grad:
+                        tgt, add2 = self._grad_target(v)
+                        self.bwd_seq(lambda v=v, o=o, tgt=tgt, add2=add2: ops.copy2d(
+                            g, Ct, tgt, v.C, M, v.C, addend=add2, ld_addend=v.C, x_off=o))
+                    o += v.C
+            self._defer_backward(sched)
+
+    def _emit_dropout(self, n: FlatNode):
+        x = self._input_of(n.inputs[0], False)
+        rate = n.layer.rate
+        if not self.training or rate == 0.0:
+            self.values[n.output] = x
+            return
+        out = Value(x.shape, self.dt, self._alloc(x.shape, self.dt), n.layer.name)
+        out.needs_grad = True
+        self.values[n.output] = out
+        seed = self.dropout_seed + 7919 * len(self.fwd)
+        ctr = self.step_counter
+        self.fwd.append(lambda: ops.dropout(x.buf, rate, seed, out.buf, seed_offset=ctr))
+        self.launches_fwd += 1
+
+        def sched():
+            g = self._final_grad(out)
+            tgt, add2 = self._grad_target(x)
+            self.bwd_seq(lambda: ops.dropout(g, rate, seed, tgt, addend=add2, seed_offset=ctr))
+        self._defer_backward(sched)
+
+    def _emit_softmax_tail(self, n: FlatNode, producer):
+        src = self.values[n.inputs[0]]
+        if isinstance(src, _TailResize):
+            logits, f = src.x, src.fh
+            if src.fh != src.fw:
+                raise NotImplementedError("decoder tail: isotropic resize factor expected")
+        else:
+            logits, f = src, 1
+        if logits.dtype != torch.float32:
+            raise NotImplementedError("decoder tail expects fp32 logits (num_classes not a multiple of 8)")
+        self.logits, self.tail_factor = logits, f
+        N, H, W, C = logits.shape
+        if C > 32:
+            raise NotImplementedError("softmax tail supports up to 32 classes")
+        self.out_shape = (N, H * f, W * f, C)
+        self.labels = self._alloc((N, H * f, W * f), torch.int32, zero=True)
+        self.loss_sum = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.reg_sum = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._tail_bufs: Dict[str, torch.Tensor] = {}
+        if self.training:
+            logits.needs_grad = True
+            self._grad_of(logits)
+            logits.grad_written = True
+
+    def tail_buf(self, name, shape, dtype):
+        if name not in self._tail_bufs:
+            self._tail_bufs[name] = self._alloc(shape, dtype)
+        return self._tail_bufs[name]
+
+    # ---------------------------------------------------------------------------------------------- running
+    def upload_weights(self):
+        self.params.upload()
+        self.run_prep()
+
+    def run_prep(self):
+        for fn in self.prep:
+            fn()
+
+    def finalize(self):
+        """Generate the backward schedule (once)."""
+        if getattr(self, "_finalized", False):
+            return
+        self._finalized = True
+        if self.training:
+            self.bwd = []
+            for t in reversed(self._bwd_thunks):
+                t()
+
+    def set_loss(self, pos_weights, neg_weights, epsilon=1e-7):
+        C = self.logits.C
+        if len(pos_weights) != C or len(neg_weights) != C:
+            raise ValueError(f"loss weights have {len(pos_weights)} entries for {C} classes (ss.py:443)")
+        self.pw = torch.tensor(pos_weights, dtype=torch.float32, device=self.device)
+        self.nw = torch.tensor(neg_weights, dtype=torch.float32, device=self.device)
+        self.eps = float(epsilon)
+
+    def zero_grads(self):
+        self.params.g.zero_()
+        self.stats.zero_()
+        self.loss_sum.zero_()
+        self.reg_sum.zero_()
+
+    def forward(self):
+        for fn in self.fwd:
+            fn()
+
+    def loss_forward_backward(self):
+        """Fused decoder tail on the low-resolution logits: loss value + gradient w.r.t. the logits."""
+        N, H, W, C = self.logits.shape
+        f = self.tail_factor
+        P = N * H * f * W * f
+        z = self.logits.buf
+        if self.fused_tail and f > 1:
+            ops.upsample_softmax_cbloss_fwd(z, self.labels, self.pw, self.nw, self.eps, N, H, W, C, f, self.loss_sum)
+            g = self.logits.grad
+            g.zero_()
+            ops.upsample_softmax_cbloss_bwd(z, self.labels, self.pw, self.nw, self.eps, N, H, W, C, f, 1.0 / P, g)
+        else:
+            zh = self.tail_buf("zh", (N, H * f, W * f, C), torch.float32)
+            dzh = self.tail_buf("dzh", (N, H * f, W * f, C), torch.float32)
+            if f > 1:
+                ops.bilinear_fwd(z, f, f, out=zh)
+            else:
+                zh = z
+            ops.softmax_cbloss_fwd(zh, self.labels, self.pw, self.nw, self.eps, P, C, self.loss_sum)
+            ops.softmax_cbloss_bwd(zh, self.labels, self.pw, self.nw, self.eps, P, C, 1.0 / P, dzh)
+            if f > 1:
+                ops.bilinear_bwd(dzh, self.logits.shape, f, f, out=self.logits.grad)
+            else:
+                self.logits.grad.copy_(dzh)
+
+    def backward(self):
+        for fn in self.bwd:
+            fn()
+
+    def step_fwd_bwd(self):
+        """One forward + backward pass over the batch already resident in self.x_in / self.labels."""
+        self.finalize()
+        self.zero_grads()
+        self.forward()
+        self.loss_forward_backward()
+        self.backward()
+
+    def regularization(self):
+        if self.params.l2 and self.params.n_reg:
+            ops.sumsq(self.params.w, self.params.n_reg, self.reg_sum)
+
+    def adam_step(self, opt, grad_scale: float = 1.0):
+        P = self.params
+        lr_t = opt.step_size()
+        if P.n_reg:
+            ops.adam(P.w, P.g, P.m, P.v, P.n_reg, lr_t, opt.beta_1, opt.beta_2, opt.epsilon, grad_scale, P.l2)
+        if P.n_train > P.n_reg:
+            ops.adam(P.w, P.g, P.m, P.v, P.n_train - P.n_reg, lr_t, opt.beta_1, opt.beta_2, opt.epsilon, grad_scale,
+                     0.0, w_off=P.n_reg)
+        opt.iterations += 1
+        self.step_counter.add_(1)
+        self.run_prep()
+
+    def loss_value(self) -> float:
+        P = self.N * self.out_shape[1] * self.out_shape[2]
+        return float(self.loss_sum.item()) / P + self.params.l2 * float(self.reg_sum.item())
+
+    # ---- host-facing API -------------------------------------------------------------------------------
+    def load_batch(self, images, labels=None):
+        x = torch.as_tensor(images)
+        if tuple(x.shape) != self.x_in.shape:
+            raise ValueError(f"expected images of shape {self.x_in.shape}, got {tuple(x.shape)}")
+        self.x_in.buf.copy_(x.to(self.device, non_blocking=True))
+        if labels is not None:
+            y = torch.as_tensor(labels)
+            if y.dim() == 4:                      # one-hot [B,H,W,C] (reference Sequence output, ss.py:1602)
+                y = y.argmax(dim=-1)
+            if tuple(y.shape) != tuple(self.labels.shape):
+                raise ValueError(f"expected labels of shape {tuple(self.labels.shape)}, got {tuple(y.shape)}")
+            self.labels.copy_(y.to(self.device, non_blocking=True))
+
+    def train_on_batch(self, images, labels) -> float:
+        m = self.model
+        if not hasattr(self, "pw"):
+            self.set_loss(m.loss.pos_weights, m.loss.neg_weights, m.loss.epsilon)
+        self.load_batch(images, labels)
+        self.step_fwd_bwd()
+        self.regularization()
+        self.adam_step(m.optimizer)
+        return self.loss_value()
+
+    def logits_highres(self) -> torch.Tensor:
+        N, H, W, C = self.logits.shape
+        f = self.tail_factor
+        if f == 1:
+            return self.logits.buf
+        zh = self.tail_buf("zh", (N, H * f, W * f, C), torch.float32)
+        ops.bilinear_fwd(self.logits.buf, f, f, out=zh)
+        return zh
+
+    def predict_device(self) -> torch.Tensor:
+        self.forward()
+        zh = self.logits_highres()
+        probs = self.tail_buf("probs", self.out_shape, torch.float32)
+        ops.softmax_argmax(zh, zh.numel() // zh.shape[-1], zh.shape[-1], probs=probs)
+        return probs
+
+    def predict(self, images) -> np.ndarray:
+        self.load_batch(images)
+        return self.predict_device().cpu().numpy()
+
+    def segment(self, images) -> np.ndarray:
+        self.load_batch(images)
+        self.forward()
+        zh = self.logits_highres()
+        lab = self.tail_buf("lab", self.out_shape[:3], torch.int32)
+        ops.softmax_argmax(zh, zh.numel() // zh.shape[-1], zh.shape[-1], labels=lab)
+        return lab.cpu().numpy().astype(np.int64)
+
+    def gradients(self) -> Dict[str, np.ndarray]:
+        """{'layer/weight': gradient} after step_fwd_bwd (parity tests)."""
+        out = {}
+        for l in self.model.flat_layers():
+            for n in l.weight_names():
+                if l._trainable[n]:
+                    out[f"{l.name}/{n}"] = self.params.view(l, n, grad=True).detach().cpu().numpy().copy()
+        return out
+
+
+class _AliasValue(Value):
+    """A tensor that is `act(x)` for a materialised x, never written to memory: consumers fuse the activation."""
+
+    def __init__(self, x: Value, act: int):
+        self._x = x
+        self.pre_act = act
+        self.shape, self.dtype, self.name = x.shape, x.dtype, x.name + "/act"
+
+    @property
+    def buf(self):
+        return self._x.buf
+
+    @property
+    def needs_grad(self):
+        return self._x.needs_grad
+
+    # gradient writes go to the underlying tensor (the consumer applies the activation mask itself)
+    @property
+    def grad(self):
+        return self._x.grad
+
+    @grad.setter
+    def grad(self, v):
+        self._x.grad = v
+
+    @property
+    def grad_written(self):
+        return self._x.grad_written
+
+    @grad_written.setter
+    def grad_written(self, v):
+        self._x.grad_written = v
+
+    @property
+    def pending(self):
+        return self._x.pending
+
+
+class _TailResize:
+    def __init__(self, x: Value, fh: int, fw: int):
+        self.x, self.fh, self.fw = x, fh, fw
+        self.pre_act = ACT_NONE

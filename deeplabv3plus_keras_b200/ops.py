@@ -322,8 +322,8 @@ def confusion_matrix(y_true, y_pred, P, Cc, cm):
     call("dlv3p_confusion_matrix", _p(y_true), _p(y_pred), P, Cc, _p(cm), _stream())
 
 
-def dropout(x: Tensor, rate: float, seed: int, out: Tensor, addend=None):
-    call("dlv3p_dropout", _p(x), _p(out), x.numel(), rate, seed, _p(addend), _dt(x), _stream())
+def dropout(x: Tensor, rate: float, seed: int, out: Tensor, addend=None, seed_offset=None):
+    call("dlv3p_dropout", _p(x), _p(out), x.numel(), rate, seed, _p(seed_offset), _p(addend), _dt(x), _stream())
     return out
 
 
@@ -339,4 +339,9 @@ def sumsq(w, n, out, w_off=0):
 
 def cast(x: Tensor, out: Tensor):
     call("dlv3p_cast", _p(x), _dt(x), _p(out), _dt(out), x.numel(), _stream())
+    return out
+
+
+def cast2d(x: Tensor, ld_x: int, out: Tensor, ld_y: int, M: int, Cc: int):
+    call("dlv3p_cast2d", _p(x), ld_x, _dt(x), _p(out), ld_y, _dt(out), M, Cc, _stream())
     return out

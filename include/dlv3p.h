@@ -201,9 +201,10 @@ int dlv3p_confusion_matrix(const int32_t* y_true, const int32_t* y_pred, int64_t
                            void* stream);
 
 /* Dropout (ss.py:864): y = x * mask / (1-rate), mask ~ Bernoulli(1-rate) from a counter-based hash of
- * (seed, element index); bwd applies the same mask. */
-int dlv3p_dropout(const void* x, void* y, int64_t n, float rate, uint64_t seed, const void* addend, int dtype,
-                  void* stream);
+ * (seed + *seed_offset, element index); bwd applies the same mask.  seed_offset (nullable) is a DEVICE counter so a
+ * captured CUDA graph draws a fresh mask on every replay. */
+int dlv3p_dropout(const void* x, void* y, int64_t n, float rate, uint64_t seed, const uint64_t* seed_offset,
+                  const void* addend, int dtype, void* stream);
 
 /* Adam (ss.py:477-480; Keras: lr_t = lr*sqrt(1-b2^t)/(1-b1^t), w -= lr_t*m/(sqrt(v)+eps)); g may carry an L2
  * term: g_eff = g*grad_scale + l2*2*w  (Keras regularizers.l2(l) = l*sum(w^2)). */
@@ -211,8 +212,10 @@ int dlv3p_adam(float* w, const float* g, float* m, float* v, int64_t n, float lr
                float eps, float grad_scale, float l2, void* stream);
 /* sum of squares (for the L2 regulariser term of the reported loss): out[0] += sum w^2 */
 int dlv3p_sumsq(const float* w, int64_t n, float* out, void* stream);
-/* dtype conversion fp32 <-> bf16 */
+/* dtype conversion fp32 <-> bf16 (flat, and row-strided [M,C] with independent leading dimensions) */
 int dlv3p_cast(const void* x, int x_dtype, void* y, int y_dtype, int64_t n, void* stream);
+int dlv3p_cast2d(const void* x, int64_t ld_x, int x_dtype, void* y, int64_t ld_y, int y_dtype, int64_t M, int C,
+                 void* stream);
 
 #ifdef __cplusplus
 }

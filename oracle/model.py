@@ -1,0 +1,208 @@
+"""ORACLE (test infrastructure only) — straight-line CPU restatement of the reference's DeepLabV3+ graph.
+
+Follows bodhi/deeplabv3plus_keras/semantic_segmentation.py: base-model taps ss.py:494-525, _make_encoder
+ss.py:790-876, _make_decoder ss.py:878-913, _refine_boundary ss.py:915-954, loss ss.py:438-447 (+ Keras L2
+regularisers of the Conv2D layers created with kernel_regularizer, ss.py:818,838,847,869,897,935), and the
+keras.applications Xception / MobileNetV2 topologies (TF 2.4; source not vendored in the reference — restated from
+the published architectures, pinned by their parameter totals).  PARITY UNPINNED against TensorFlow itself: see
+oracle/tf_ops.py.  Deliberately written as plain functions over a {"layer/weight": tensor} dict — it shares no
+code with the product's layer graph / engine, so a topology bug in one is caught by the other.
+
+Weights are keyed with the names tf.keras would give the layers, including the automatic ones
+(conv2d, conv2d_1, ..., separable_conv2d, batch_normalization_k) in creation order.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import tf_ops as T
+
+
+class Names:
+    """tf.keras automatic layer naming: prefix, prefix_1, prefix_2, ..."""
+
+    def __init__(self):
+        self.n: Dict[str, int] = {}
+
+    def __call__(self, prefix: str) -> str:
+        k = self.n.get(prefix, 0)
+        self.n[prefix] = k + 1
+        return prefix if k == 0 else f"{prefix}_{k}"
+
+
+class Ctx:
+    def __init__(self, weights: Dict[str, torch.Tensor], training: bool, bn_momentum_new: Dict[str, torch.Tensor]):
+        self.w, self.training, self.new_stats = weights, training, bn_momentum_new
+        self.names = Names()
+        self.l2_terms: List[torch.Tensor] = []
+        self.seen: List[str] = []
+
+
+def _bn(ctx: Ctx, x, name: str, momentum: float, eps: float = 1e-3, scale: bool = True):
+    w = ctx.w
+    gamma = w[f"{name}/gamma"] if scale else None
+    y, mm, mv = T.batch_norm(x, gamma, w[f"{name}/beta"], w[f"{name}/moving_mean"], w[f"{name}/moving_variance"],
+                             eps, ctx.training, momentum)
+    if ctx.training:
+        # a layer applied twice (shared base under boundary refinement) updates its moving statistics twice
+        prev = ctx.new_stats.get(f"{name}/moving_mean")
+        if prev is not None:
+            _, mm, mv = T.batch_norm(x, gamma, w[f"{name}/beta"], prev, ctx.new_stats[f"{name}/moving_variance"],
+                                     eps, True, momentum)
+        ctx.new_stats[f"{name}/moving_mean"] = mm
+        ctx.new_stats[f"{name}/moving_variance"] = mv
+    return y
+
+
+def _conv(ctx: Ctx, x, name, stride=1, padding="same", l2: float = 0.0):
+    k = ctx.w[f"{name}/kernel"]
+    if l2:
+        ctx.l2_terms.append(l2 * (k * k).sum())
+    return T.conv2d(x, k, stride, padding)
+
+
+def _sep(ctx: Ctx, x, name, dilation=(1, 1)):
+    d = T.depthwise_conv2d(x, ctx.w[f"{name}/depthwise_kernel"], 1, "same", dilation)
+    return T.conv2d(d, ctx.w[f"{name}/pointwise_kernel"], 1, "same")
+
+
+# ---- keras.applications.Xception, truncated where the reference taps it (ss.py:517-520) --------------------
+def xception_base(ctx: Ctx, img, output_stride: int):
+    nm, M = ctx.names, 0.99
+    x = T.relu(_bn(ctx, _conv(ctx, img, "block1_conv1", 2, "valid"), "block1_conv1_bn", M))
+    x = T.relu(_bn(ctx, _conv(ctx, x, "block1_conv2", 1, "valid"), "block1_conv2_bn", M))
+    for blk, first_relu in ((2, False), (3, True), (4, True)):
+        cname, bname = nm("conv2d"), nm("batch_normalization")
+        tap_here = (blk == 4 and output_stride == 8)
+        # the strided 1x1 shortcut; pruned from the graph when the network is tapped before the pool (OS8)
+        res = None if tap_here else _bn(ctx, _conv(ctx, x, cname, 2, "same"), bname, M)
+        if first_relu:
+            x = T.relu(x)
+        x = _bn(ctx, _sep(ctx, x, f"block{blk}_sepconv1"), f"block{blk}_sepconv1_bn", M)
+        x = T.relu(x)
+        x = _bn(ctx, _sep(ctx, x, f"block{blk}_sepconv2"), f"block{blk}_sepconv2_bn", M)
+        if tap_here:
+            nm("conv2d"); nm("batch_normalization")       # block13's shortcut layers exist in Keras, pruned here
+            return x
+        x = T.max_pool_3x3_s2_same(x) + res
+    for blk in range(5, 13):
+        res = x
+        for j in (1, 2, 3):
+            x = _bn(ctx, _sep(ctx, T.relu(x), f"block{blk}_sepconv{j}"), f"block{blk}_sepconv{j}_bn", M)
+        x = x + res
+    nm("conv2d"); nm("batch_normalization")               # block13 shortcut: created by Keras, not on the tapped path
+    x = _bn(ctx, _sep(ctx, T.relu(x), "block13_sepconv1"), "block13_sepconv1_bn", M)
+    x = _bn(ctx, _sep(ctx, T.relu(x), "block13_sepconv2"), "block13_sepconv2_bn", M)
+    return x
+
+
+_MNV2 = ((16, 1, 1, 0), (24, 2, 6, 1), (24, 1, 6, 2), (32, 2, 6, 3), (32, 1, 6, 4), (32, 1, 6, 5), (64, 2, 6, 6),
+         (64, 1, 6, 7), (64, 1, 6, 8), (64, 1, 6, 9), (96, 1, 6, 10), (96, 1, 6, 11), (96, 1, 6, 12))
+
+
+def mobilenetv2_base(ctx: Ctx, img, output_stride: int):
+    M = 0.999
+    x = T.relu6(_bn(ctx, _conv(ctx, img, "Conv1", 2, "same"), "bn_Conv1", M))
+    last = 5 if output_stride == 8 else 12
+    for cout, stride, exp, bid in _MNV2:
+        p = f"block_{bid}_" if bid else "expanded_conv_"
+        inp, cin = x, x.shape[-1]
+        if bid:
+            x = T.relu6(_bn(ctx, _conv(ctx, x, p + "expand"), p + "expand_BN", M))
+        k = ctx.w[p + "depthwise/depthwise_kernel"]
+        if stride == 2:
+            h, w = x.shape[1], x.shape[2]
+            x = T.zero_pad2d(x, ((1 - (1 - h % 2), 1), (1 - (1 - w % 2), 1)))     # keras correct_pad
+            x = T.depthwise_conv2d(x, k, 2, "valid")
+        else:
+            x = T.depthwise_conv2d(x, k, 1, "same")
+        x = T.relu6(_bn(ctx, x, p + "depthwise_BN", M))
+        x = _bn(ctx, _conv(ctx, x, p + "project"), p + "project_BN", M)
+        if cin == cout and stride == 1:
+            x = inp + x
+        if bid == last:
+            return x
+    raise AssertionError
+
+
+def forward(conf: dict, weights: Dict[str, torch.Tensor], image, training: bool = False,
+            dropout_mask: Optional[torch.Tensor] = None):
+    """Returns dict(logits=[B,h,w,C] low-res, probs=[B,H,W,C], l2=regularisation term, new_stats={...}).
+    `dropout_mask` (keep mask / (1-rate), shape of the concat) is required when training with dropout_rate > 0."""
+    arch, hps = conf["nn_arch"], conf["hps"]
+    ctx = Ctx(weights, training, {})
+    osd = arch["output_stride"]
+    base_fn = {"xception": xception_base, "mobilenetv2": mobilenetv2_base}[conf["base_model"]]
+    names_after_base = None
+
+    def run_base(x):
+        nonlocal names_after_base
+        saved = ctx.names
+        ctx.names = Names()                     # the base's automatic names do not depend on the call site
+        y = base_fn(ctx, x, osd)
+        names_after_base = ctx.names
+        ctx.names = saved
+        return y
+
+    feats = run_base(image)
+    ctx.names = names_after_base                # head layers continue the counters of the Keras application
+    nm = ctx.names
+    mom, sc, wd = hps["bn_momentum"], hps["bn_scale"], hps["weight_decay"]
+    width, mult = arch["reduction_size"], arch["conv_rate_multiplier"]
+
+    def project(x):
+        c, b = nm("conv2d"), nm("batch_normalization")
+        return T.relu(_bn(ctx, _conv(ctx, x, c, 1, "same", wd), b, mom, scale=sc))
+
+    branches = []
+    for spec in arch["encoder_middle_conf"]:
+        src = feats if spec["input"] == -1 else branches[spec["input"]]
+        if spec["op"] == "conv" and spec["kernel"] == 1:
+            out = project(src)
+        elif spec["op"] == "conv":
+            s, b = nm("separable_conv2d"), nm("batch_normalization")
+            rate = (spec["rate"][0] * mult, spec["rate"][1] * mult)
+            out = T.relu(_bn(ctx, _sep(ctx, src, s, rate), b, mom, scale=sc))
+            out = project(out)
+        elif spec["op"] == "pyramid_pooling":
+            out = project(T.avg_pool_valid(src, spec["kernel"]))
+            out = T.resize_bilinear(out, *spec["target_size_factor"])
+        else:
+            raise ValueError("Invalid operation.")
+        branches.append(out)
+    x = torch.cat(branches, dim=-1)
+    if training and arch["dropout_rate"] > 0:
+        if dropout_mask is None:
+            raise ValueError("training with dropout needs an explicit mask for parity")
+        x = x * dropout_mask
+    enc = project(x)
+
+    if arch["boundary_refinement"]:
+        low = run_base(image)                   # shared weights, second pass (ss.py:930)
+        low = project(low)
+        f = int(osd / 2)
+        x = torch.cat([T.resize_bilinear(low, f, f), T.resize_bilinear(enc, f, f)], dim=-1)
+        up = int(osd / 8 if osd == 16 else osd / 4)
+    else:
+        x, up = enc, osd
+    logits = _conv(ctx, x, nm("conv2d"), 1, "same", wd)
+    probs = T.softmax(T.resize_bilinear(logits, up, up))
+    l2 = sum(ctx.l2_terms) if ctx.l2_terms else torch.zeros((), dtype=image.dtype)
+    return dict(logits=logits, probs=probs, l2=l2, new_stats=ctx.new_stats, encoder=enc, features=feats)
+
+
+def loss_and_grads(conf, weights, image, labels, pos_w, neg_w, eps=1e-7, dropout_mask=None, wrt_logits=False):
+    """Training-mode forward + backward through autograd: returns (data_loss, l2, grads dict, forward dict)."""
+    ws = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith(("moving_mean", "moving_variance"))
+              else v) for k, v in weights.items()}
+    out = forward(conf, ws, image, training=True, dropout_mask=dropout_mask)
+    C = out["probs"].shape[-1]
+    y = T.one_hot(labels, C, out["probs"].dtype)
+    data = T.class_balanced_loss(y, out["probs"], pos_w, neg_w, eps)
+    if wrt_logits:
+        out["logits"].retain_grad()
+    (data + out["l2"]).backward()
+    grads = {k: v.grad for k, v in ws.items() if v.requires_grad and v.grad is not None}
+    return data.detach(), out["l2"].detach(), grads, out
