@@ -32,69 +32,104 @@ class Names:
         return prefix if k == 0 else f"{prefix}_{k}"
 
 
+def _bf16(t):
+    """Round to bfloat16 and back (differentiable: the cast's gradient is the cast)."""
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
 class Ctx:
-    def __init__(self, weights: Dict[str, torch.Tensor], training: bool, bn_momentum_new: Dict[str, torch.Tensor]):
+    """`emulate_bf16`: round exactly where the product STORES bfloat16 — GEMM operands (1x1 / im2col'd kernels and
+    their inputs), every tensor a kernel writes to HBM (depthwise output, GEMM output, fused BN+activation(+add)
+    output, pool(+add), resize, concat) — while arithmetic stays in the oracle's precision, as the kernels' fp32
+    accumulators do.  Logits and BatchNormalization statistics (taken from the fp32 accumulators) are not rounded.
+    With it off (default) the oracle is the plain fp64/fp32 restatement."""
+
+    def __init__(self, weights: Dict[str, torch.Tensor], training: bool, bn_momentum_new: Dict[str, torch.Tensor],
+                 emulate_bf16: bool = False, momentum_override: Optional[float] = None):
         self.w, self.training, self.new_stats = weights, training, bn_momentum_new
         self.names = Names()
         self.l2_terms: List[torch.Tensor] = []
-        self.seen: List[str] = []
+        self.q = _bf16 if emulate_bf16 else (lambda t: t)
+        self.momentum_override = momentum_override
 
 
-def _bn(ctx: Ctx, x, name: str, momentum: float, eps: float = 1e-3, scale: bool = True):
+def _bn(ctx: Ctx, x, name: str, momentum: float, eps: float = 1e-3, scale: bool = True, stats_from=None):
+    """x: the tensor as stored (possibly bf16-rounded); stats_from: the unrounded conv accumulator the product takes
+    its batch statistics from (defaults to x)."""
     w = ctx.w
+    if ctx.momentum_override is not None:
+        momentum = ctx.momentum_override
     gamma = w[f"{name}/gamma"] if scale else None
-    y, mm, mv = T.batch_norm(x, gamma, w[f"{name}/beta"], w[f"{name}/moving_mean"], w[f"{name}/moving_variance"],
-                             eps, ctx.training, momentum)
+    beta, mm0, mv0 = w[f"{name}/beta"], w[f"{name}/moving_mean"], w[f"{name}/moving_variance"]
+    src = x if stats_from is None else stats_from
     if ctx.training:
-        # a layer applied twice (shared base under boundary refinement) updates its moving statistics twice
-        prev = ctx.new_stats.get(f"{name}/moving_mean")
-        if prev is not None:
-            _, mm, mv = T.batch_norm(x, gamma, w[f"{name}/beta"], prev, ctx.new_stats[f"{name}/moving_variance"],
-                                     eps, True, momentum)
+        mean = src.mean(dim=(0, 1, 2))
+        var = src.var(dim=(0, 1, 2), unbiased=False)
+        y = (x - mean) * torch.rsqrt(var + eps)
+        y = y * gamma if gamma is not None else y
+        y = y + beta
+        # moving statistics; a layer applied twice (shared base under boundary refinement) updates them twice
+        pm = ctx.new_stats.get(f"{name}/moving_mean", mm0)
+        pv = ctx.new_stats.get(f"{name}/moving_variance", mv0)
+        _, mm, mv = T.batch_norm(src.detach(), None, None, pm, pv, eps, True, momentum)
         ctx.new_stats[f"{name}/moving_mean"] = mm
         ctx.new_stats[f"{name}/moving_variance"] = mv
+        return y
+    y, _, _ = T.batch_norm(x, gamma, beta, mm0, mv0, eps, False, momentum)
     return y
 
 
 def _conv(ctx: Ctx, x, name, stride=1, padding="same", l2: float = 0.0):
+    """Returns the UNROUNDED accumulator; callers store it through ctx.q."""
     k = ctx.w[f"{name}/kernel"]
     if l2:
         ctx.l2_terms.append(l2 * (k * k).sum())
-    return T.conv2d(x, k, stride, padding)
+    return T.conv2d(x, ctx.q(k), stride, padding)
 
 
 def _sep(ctx: Ctx, x, name, dilation=(1, 1)):
-    d = T.depthwise_conv2d(x, ctx.w[f"{name}/depthwise_kernel"], 1, "same", dilation)
-    return T.conv2d(d, ctx.w[f"{name}/pointwise_kernel"], 1, "same")
+    d = ctx.q(T.depthwise_conv2d(x, ctx.w[f"{name}/depthwise_kernel"], 1, "same", dilation))
+    return T.conv2d(d, ctx.q(ctx.w[f"{name}/pointwise_kernel"]), 1, "same")
+
+
+def _cbn(ctx: Ctx, acc, bn_name, momentum, act=None, add=None, scale=True, stats_rounded=False):
+    """conv accumulator -> stored (rounded) -> BN(+activation)(+residual add) -> stored (rounded): one fused
+    macro-op of the product (engine._emit_conv)."""
+    y = ctx.q(acc)
+    z = _bn(ctx, y, bn_name, momentum, scale=scale, stats_from=(y if stats_rounded else acc))
+    if act is not None:
+        z = act(z)
+    if add is not None:
+        z = z + add
+    return ctx.q(z)
 
 
 # ---- keras.applications.Xception, truncated where the reference taps it (ss.py:517-520) --------------------
 def xception_base(ctx: Ctx, img, output_stride: int):
     nm, M = ctx.names, 0.99
-    x = T.relu(_bn(ctx, _conv(ctx, img, "block1_conv1", 2, "valid"), "block1_conv1_bn", M))
-    x = T.relu(_bn(ctx, _conv(ctx, x, "block1_conv2", 1, "valid"), "block1_conv2_bn", M))
+    x = _cbn(ctx, _conv(ctx, img, "block1_conv1", 2, "valid"), "block1_conv1_bn", M, T.relu)
+    x = _cbn(ctx, _conv(ctx, x, "block1_conv2", 1, "valid"), "block1_conv2_bn", M, T.relu)
     for blk, first_relu in ((2, False), (3, True), (4, True)):
         cname, bname = nm("conv2d"), nm("batch_normalization")
         tap_here = (blk == 4 and output_stride == 8)
         # the strided 1x1 shortcut; pruned from the graph when the network is tapped before the pool (OS8)
-        res = None if tap_here else _bn(ctx, _conv(ctx, x, cname, 2, "same"), bname, M)
+        res = None if tap_here else _cbn(ctx, _conv(ctx, x, cname, 2, "same"), bname, M)
         if first_relu:
             x = T.relu(x)
-        x = _bn(ctx, _sep(ctx, x, f"block{blk}_sepconv1"), f"block{blk}_sepconv1_bn", M)
-        x = T.relu(x)
-        x = _bn(ctx, _sep(ctx, x, f"block{blk}_sepconv2"), f"block{blk}_sepconv2_bn", M)
+        x = _cbn(ctx, _sep(ctx, x, f"block{blk}_sepconv1"), f"block{blk}_sepconv1_bn", M, T.relu)
+        x = _cbn(ctx, _sep(ctx, x, f"block{blk}_sepconv2"), f"block{blk}_sepconv2_bn", M)
         if tap_here:
             nm("conv2d"); nm("batch_normalization")       # block13's shortcut layers exist in Keras, pruned here
             return x
-        x = T.max_pool_3x3_s2_same(x) + res
+        x = ctx.q(T.max_pool_3x3_s2_same(x) + res)
     for blk in range(5, 13):
         res = x
         for j in (1, 2, 3):
-            x = _bn(ctx, _sep(ctx, T.relu(x), f"block{blk}_sepconv{j}"), f"block{blk}_sepconv{j}_bn", M)
-        x = x + res
+            x = _cbn(ctx, _sep(ctx, T.relu(x), f"block{blk}_sepconv{j}"), f"block{blk}_sepconv{j}_bn", M,
+                     add=res if j == 3 else None)
     nm("conv2d"); nm("batch_normalization")               # block13 shortcut: created by Keras, not on the tapped path
-    x = _bn(ctx, _sep(ctx, T.relu(x), "block13_sepconv1"), "block13_sepconv1_bn", M)
-    x = _bn(ctx, _sep(ctx, T.relu(x), "block13_sepconv2"), "block13_sepconv2_bn", M)
+    x = _cbn(ctx, _sep(ctx, T.relu(x), "block13_sepconv1"), "block13_sepconv1_bn", M)
+    x = _cbn(ctx, _sep(ctx, T.relu(x), "block13_sepconv2"), "block13_sepconv2_bn", M)
     return x
 
 
@@ -104,13 +139,13 @@ _MNV2 = ((16, 1, 1, 0), (24, 2, 6, 1), (24, 1, 6, 2), (32, 2, 6, 3), (32, 1, 6, 
 
 def mobilenetv2_base(ctx: Ctx, img, output_stride: int):
     M = 0.999
-    x = T.relu6(_bn(ctx, _conv(ctx, img, "Conv1", 2, "same"), "bn_Conv1", M))
+    x = _cbn(ctx, _conv(ctx, img, "Conv1", 2, "same"), "bn_Conv1", M, T.relu6)
     last = 5 if output_stride == 8 else 12
     for cout, stride, exp, bid in _MNV2:
         p = f"block_{bid}_" if bid else "expanded_conv_"
         inp, cin = x, x.shape[-1]
         if bid:
-            x = T.relu6(_bn(ctx, _conv(ctx, x, p + "expand"), p + "expand_BN", M))
+            x = _cbn(ctx, _conv(ctx, x, p + "expand"), p + "expand_BN", M, T.relu6)
         k = ctx.w[p + "depthwise/depthwise_kernel"]
         if stride == 2:
             h, w = x.shape[1], x.shape[2]
@@ -118,21 +153,22 @@ def mobilenetv2_base(ctx: Ctx, img, output_stride: int):
             x = T.depthwise_conv2d(x, k, 2, "valid")
         else:
             x = T.depthwise_conv2d(x, k, 1, "same")
-        x = T.relu6(_bn(ctx, x, p + "depthwise_BN", M))
-        x = _bn(ctx, _conv(ctx, x, p + "project"), p + "project_BN", M)
-        if cin == cout and stride == 1:
-            x = inp + x
+        x = _cbn(ctx, x, p + "depthwise_BN", M, T.relu6, stats_rounded=True)   # stats kernel reads the stored tensor
+        x = _cbn(ctx, _conv(ctx, x, p + "project"), p + "project_BN", M,
+                 add=inp if (cin == cout and stride == 1) else None)
         if bid == last:
             return x
     raise AssertionError
 
 
 def forward(conf: dict, weights: Dict[str, torch.Tensor], image, training: bool = False,
-            dropout_mask: Optional[torch.Tensor] = None):
+            dropout_mask: Optional[torch.Tensor] = None, emulate_bf16: bool = False,
+            momentum_override: Optional[float] = None):
     """Returns dict(logits=[B,h,w,C] low-res, probs=[B,H,W,C], l2=regularisation term, new_stats={...}).
     `dropout_mask` (keep mask / (1-rate), shape of the concat) is required when training with dropout_rate > 0."""
     arch, hps = conf["nn_arch"], conf["hps"]
-    ctx = Ctx(weights, training, {})
+    ctx = Ctx(weights, training, {}, emulate_bf16, momentum_override)
+    q = ctx.q
     osd = arch["output_stride"]
     base_fn = {"xception": xception_base, "mobilenetv2": mobilenetv2_base}[conf["base_model"]]
     names_after_base = None
@@ -154,7 +190,7 @@ def forward(conf: dict, weights: Dict[str, torch.Tensor], image, training: bool 
 
     def project(x):
         c, b = nm("conv2d"), nm("batch_normalization")
-        return T.relu(_bn(ctx, _conv(ctx, x, c, 1, "same", wd), b, mom, scale=sc))
+        return _cbn(ctx, _conv(ctx, x, c, 1, "same", wd), b, mom, T.relu, scale=sc)
 
     branches = []
     for spec in arch["encoder_middle_conf"]:
@@ -164,11 +200,11 @@ def forward(conf: dict, weights: Dict[str, torch.Tensor], image, training: bool 
         elif spec["op"] == "conv":
             s, b = nm("separable_conv2d"), nm("batch_normalization")
             rate = (spec["rate"][0] * mult, spec["rate"][1] * mult)
-            out = T.relu(_bn(ctx, _sep(ctx, src, s, rate), b, mom, scale=sc))
+            out = _cbn(ctx, _sep(ctx, src, s, rate), b, mom, T.relu, scale=sc)
             out = project(out)
         elif spec["op"] == "pyramid_pooling":
-            out = project(T.avg_pool_valid(src, spec["kernel"]))
-            out = T.resize_bilinear(out, *spec["target_size_factor"])
+            out = project(q(T.avg_pool_valid(src, spec["kernel"])))
+            out = q(T.resize_bilinear(out, *spec["target_size_factor"]))
         else:
             raise ValueError("Invalid operation.")
         branches.append(out)
@@ -176,14 +212,14 @@ def forward(conf: dict, weights: Dict[str, torch.Tensor], image, training: bool 
     if training and arch["dropout_rate"] > 0:
         if dropout_mask is None:
             raise ValueError("training with dropout needs an explicit mask for parity")
-        x = x * dropout_mask
+        x = q(x * dropout_mask)
     enc = project(x)
 
     if arch["boundary_refinement"]:
         low = run_base(image)                   # shared weights, second pass (ss.py:930)
         low = project(low)
         f = int(osd / 2)
-        x = torch.cat([T.resize_bilinear(low, f, f), T.resize_bilinear(enc, f, f)], dim=-1)
+        x = torch.cat([q(T.resize_bilinear(low, f, f)), q(T.resize_bilinear(enc, f, f))], dim=-1)
         up = int(osd / 8 if osd == 16 else osd / 4)
     else:
         x, up = enc, osd
@@ -193,11 +229,12 @@ def forward(conf: dict, weights: Dict[str, torch.Tensor], image, training: bool 
     return dict(logits=logits, probs=probs, l2=l2, new_stats=ctx.new_stats, encoder=enc, features=feats)
 
 
-def loss_and_grads(conf, weights, image, labels, pos_w, neg_w, eps=1e-7, dropout_mask=None, wrt_logits=False):
+def loss_and_grads(conf, weights, image, labels, pos_w, neg_w, eps=1e-7, dropout_mask=None, wrt_logits=False,
+                   emulate_bf16=False):
     """Training-mode forward + backward through autograd: returns (data_loss, l2, grads dict, forward dict)."""
     ws = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith(("moving_mean", "moving_variance"))
               else v) for k, v in weights.items()}
-    out = forward(conf, ws, image, training=True, dropout_mask=dropout_mask)
+    out = forward(conf, ws, image, training=True, dropout_mask=dropout_mask, emulate_bf16=emulate_bf16)
     C = out["probs"].shape[-1]
     y = T.one_hot(labels, C, out["probs"].dtype)
     data = T.class_balanced_loss(y, out["probs"], pos_w, neg_w, eps)
