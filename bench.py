@@ -314,7 +314,8 @@ def main():
                                                  else (a["GBps"] / hbm_peak), 4)}
                                for k, a in list(summ.items())[:14]}
             if args.profile_json:
-                json.dump({k: dict(a) for k, a in summ.items()}, open(args.profile_json, "w"), indent=1)
+                json.dump({"per_kernel": {k: dict(a) for k, a in summ.items()}, "per_shape": kp.detail(60)},
+                          open(args.profile_json, "w"), indent=1)
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_baseline()
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

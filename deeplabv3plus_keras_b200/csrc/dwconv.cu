@@ -276,6 +276,110 @@ dw_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __rest
     }
 }
 
+// Dense-tap (stride 1, dil_w 1) filter gradient: each thread walks strips of TW=4 output columns, so every input
+// vector is loaded / converted / activated once and reused by the three taps of its row (22 vector loads per 4
+// pixels instead of 40), which is what the issue-bound per-pixel kernel above spends most of its slots on.
+template <typename T, int CVB>
+__global__ void __launch_bounds__(128)
+dw_wgrad_strip_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, int N, int H, int W,
+                      int C, int Ho, int Wo, int dil_h, int pad_t, int pad_l, const float* __restrict__ in_scale,
+                      const float* __restrict__ in_shift, int in_act, long long nstrips, long long strips_per_block) {
+    constexpr int TW = 4;
+    constexpr int PL = 128 / CVB;
+    const int CV = C >> 3;
+    const int WS = (Wo + TW - 1) / TW;
+    const int tx = threadIdx.x % CVB;
+    const int ty = threadIdx.x / CVB;
+    const int cv = blockIdx.x * CVB + tx;
+    const bool active = cv < CV;
+    const int c0 = cv << 3;
+    float acc[9][8];
+#pragma unroll
+    for (int a = 0; a < 9; ++a)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[a][k] = 0.f;
+    float sc[8], sh[8];
+    const bool affine = (in_scale != nullptr);
+    if (active && affine) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { sc[k] = __ldg(in_scale + c0 + k); sh[k] = __ldg(in_shift + c0 + k); }
+    }
+    const long long q_begin = (long long)blockIdx.y * strips_per_block;
+    long long q_end = q_begin + strips_per_block;
+    if (q_end > nstrips) q_end = nstrips;
+    if (active) {
+        for (long long q = q_begin + ty; q < q_end; q += PL) {
+            const int ws = (int)(q % WS);
+            long long t = q / WS;
+            const int ho = (int)(t % Ho);
+            const int n = (int)(t / Ho);
+            const int wo0 = ws * TW;
+            float g[TW][8];
+            const T* dyp = dy + (((long long)n * Ho + ho) * Wo + wo0) * C + c0;
+#pragma unroll
+            for (int o = 0; o < TW; ++o) {
+                if (wo0 + o < Wo) {
+                    Vec8<T> v; v.load_stream(dyp + (long long)o * C);
+                    v.to_float(g[o]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) g[o][k] = 0.f;
+                }
+            }
+            const T* xn = x + (long long)n * H * W * C + c0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int hi = ho - pad_t + i * dil_h;
+                if (hi < 0 || hi >= H) continue;
+                const T* xr = xn + (long long)hi * W * C;
+                Vec8<T> raw[TW + 2];
+                bool ok[TW + 2];
+#pragma unroll
+                for (int c = 0; c < TW + 2; ++c) {
+                    const int wi = wo0 - pad_l + c;
+                    ok[c] = (wi >= 0 && wi < W);
+                    if (ok[c]) raw[c].load(xr + (long long)wi * C); else raw[c].zero();
+                }
+#pragma unroll
+                for (int c = 0; c < TW + 2; ++c) {
+                    float f[8];
+                    raw[c].to_float(f);
+                    if (ok[c] && (affine || in_act != DLV3P_ACT_NONE)) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) f[k] = apply_act(affine ? fmaf(f[k], sc[k], sh[k]) : f[k], in_act);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const int o = c - j;            // output column of the strip that sees this input under tap j
+                        if (o >= 0 && o < TW) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) acc[i * 3 + j][k] = fmaf(f[k], g[o][k], acc[i * 3 + j][k]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __shared__ float red[PL][CVB][8];
+#pragma unroll
+    for (int a = 0; a < 9; ++a) {
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) red[ty][tx][k] = acc[a][k];
+        __syncthreads();
+        for (int col = threadIdx.x; col < CVB * 8; col += 128) {
+            const int cx = col >> 3, k = col & 7;
+            const int cvv = blockIdx.x * CVB + cx;
+            if (cvv < CV) {
+                float s = 0.f;
+#pragma unroll
+                for (int r = 0; r < PL; ++r) s += red[r][cx][k];
+                atomicAdd(dw + a * C + (cvv << 3) + k, s);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 template <typename T, bool HAS_AFFINE, bool HAS_EPI>
 static int launch_dw_conv(const T* in, const float* w, T* out, int N, int Hin, int Win, int C, int Hout, int Wout,
@@ -374,6 +478,21 @@ extern "C" int dlv3p_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, i
     const int CV = C / 8;
     const long long npix = (long long)N * Ho * Wo;
     DLV3P_DISPATCH_DTYPE(dtype, T, {
+        if (stride == 1 && dil_w == 1) {
+            const long long nstrips = (long long)N * Ho * ((Wo + 3) / 4);
+            pick_cvb(CV, [&](auto cvb) {
+                constexpr int CVB = decltype(cvb)::value;
+                constexpr int PL = 128 / CVB;
+                const int gx = cdiv(CV, CVB);
+                long long want = (long long)kNumSMs * 12 / gx; if (want < 1) want = 1;
+                long long spb = (nstrips + want - 1) / want; spb = ((spb + PL - 1) / PL) * PL; if (spb < PL) spb = PL;
+                const int gy = cdiv(nstrips, spb);
+                dw_wgrad_strip_kernel<T, CVB><<<dim3(gx, gy), 128, 0, st>>>((const T*)x, (const T*)dy, dw, N, H, W, C,
+                                                                            Ho, Wo, dil_h, pad_t, pad_l, in_scale,
+                                                                            in_shift, in_act, nstrips, spb);
+            });
+            return check_launch("dwconv3x3_wgrad");
+        }
         pick_cvb(CV, [&](auto cvb) {
             constexpr int CVB = decltype(cvb)::value;
             constexpr int PL = 256 / CVB;

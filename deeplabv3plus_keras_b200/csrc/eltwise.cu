@@ -170,33 +170,107 @@ affine_act_kernel(const T* __restrict__ y, long long ld_y, const float* __restri
     o.store(out + r * ld_o + c0);
 }
 
-template <typename T>
+// Row-loop variants: block = CVB channel-packs x (256/CVB) row lanes; every thread keeps the per-channel
+// parameters of its 8 channels in registers and walks down the rows, so the kernel issues only the streaming
+// 16-byte loads/stores (the flat variant re-fetched 40 scalar parameters per 16 bytes of payload and was LSU-bound).
+template <typename T, int CVB>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const T* __restrict__ dz, long long ld_dz, const T* __restrict__ y, long long ld_y,
                     const float* __restrict__ scale, const float* __restrict__ shift,
                     const float* __restrict__ mean, const float* __restrict__ invstd, int act,
-                    const float* __restrict__ red, long long M, int C, T* __restrict__ dy, long long ld_dy) {
-    const int CV = C >> 3;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= M * CV) return;
-    const int c0 = (int)(idx % CV) << 3;
-    const long long r = idx / CV;
-    Vec8<T> a, b; a.load_stream(dz + r * ld_dz + c0); b.load_stream(y + r * ld_y + c0);
-    float g[8], v[8]; a.to_float(g); b.to_float(v);
+                    const float* __restrict__ red, long long M, int C, T* __restrict__ dy, long long ld_dy,
+                    long long rows_per_block) {
+    constexpr int PL = 256 / CVB;
+    const int tx = threadIdx.x % CVB, ty = threadIdx.x / CVB;
+    const int cv = blockIdx.x * CVB + tx;
+    if (cv >= (C >> 3)) return;
+    const int c0 = cv << 3;
+    // dy = sc*g + y*A + B with A = -sc*invstd*red1/M, B = -sc*red0/M + mean*sc*invstd*red1/M
+    float sc[8], sh[8], A[8], B[8];
     const float invM = 1.f / (float)M;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const float sc = __ldg(scale + c0 + k);
-        const float gg = g[k] * act_mask(fmaf(v[k], sc, __ldg(shift + c0 + k)), act);
+        sc[k] = __ldg(scale + c0 + k); sh[k] = __ldg(shift + c0 + k);
         if (mean != nullptr) {
-            const float xh = (v[k] - __ldg(mean + c0 + k)) * __ldg(invstd + c0 + k);
-            g[k] = sc * (gg - __ldg(red + c0 + k) * invM - xh * __ldg(red + C + c0 + k) * invM);
+            const float t = sc[k] * __ldg(invstd + c0 + k) * __ldg(red + C + c0 + k) * invM;
+            A[k] = -t;
+            B[k] = -sc[k] * __ldg(red + c0 + k) * invM + __ldg(mean + c0 + k) * t;
         } else {
-            g[k] = sc * gg;
+            A[k] = 0.f; B[k] = 0.f;
         }
     }
-    Vec8<T> o; o.from_float(g);
-    o.store(dy + r * ld_dy + c0);
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    long long r1 = r0 + rows_per_block; if (r1 > M) r1 = M;
+    long long r = r0 + ty;
+    for (; r + PL < r1; r += 2 * PL) {
+        Vec8<T> a0, b0, a1, b1;
+        a0.load_stream(dz + r * ld_dz + c0); b0.load_stream(y + r * ld_y + c0);
+        a1.load_stream(dz + (r + PL) * ld_dz + c0); b1.load_stream(y + (r + PL) * ld_y + c0);
+        float g0[8], v0[8], g1[8], v1[8];
+        a0.to_float(g0); b0.to_float(v0); a1.to_float(g1); b1.to_float(v1);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            g0[k] = fmaf(sc[k], g0[k] * act_mask(fmaf(v0[k], sc[k], sh[k]), act), fmaf(v0[k], A[k], B[k]));
+            g1[k] = fmaf(sc[k], g1[k] * act_mask(fmaf(v1[k], sc[k], sh[k]), act), fmaf(v1[k], A[k], B[k]));
+        }
+        Vec8<T> o0, o1; o0.from_float(g0); o1.from_float(g1);
+        o0.store(dy + r * ld_dy + c0); o1.store(dy + (r + PL) * ld_dy + c0);
+    }
+    for (; r < r1; r += PL) {
+        Vec8<T> a0, b0; a0.load_stream(dz + r * ld_dz + c0); b0.load_stream(y + r * ld_y + c0);
+        float g0[8], v0[8]; a0.to_float(g0); b0.to_float(v0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            g0[k] = fmaf(sc[k], g0[k] * act_mask(fmaf(v0[k], sc[k], sh[k]), act), fmaf(v0[k], A[k], B[k]));
+        Vec8<T> o0; o0.from_float(g0);
+        o0.store(dy + r * ld_dy + c0);
+    }
+}
+
+template <typename T, int CVB>
+__global__ void __launch_bounds__(256)
+affine_act_rows_kernel(const T* __restrict__ y, long long ld_y, const float* __restrict__ scale,
+                       const float* __restrict__ shift, int act, const T* __restrict__ addend, long long ld_a,
+                       T* __restrict__ out, long long ld_o, long long M, int C, long long rows_per_block) {
+    constexpr int PL = 256 / CVB;
+    const int tx = threadIdx.x % CVB, ty = threadIdx.x / CVB;
+    const int cv = blockIdx.x * CVB + tx;
+    if (cv >= (C >> 3)) return;
+    const int c0 = cv << 3;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        sc[k] = scale ? __ldg(scale + c0 + k) : 1.f;
+        sh[k] = scale ? __ldg(shift + c0 + k) : 0.f;
+    }
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    long long r1 = r0 + rows_per_block; if (r1 > M) r1 = M;
+    for (long long r = r0 + ty; r < r1; r += 2 * PL) {
+        const bool two = (r + PL < r1);
+        Vec8<T> a0, a1, d0, d1;
+        a0.load_stream(y + r * ld_y + c0);
+        if (two) a1.load_stream(y + (r + PL) * ld_y + c0);
+        if (addend != nullptr) {
+            d0.load_stream(addend + r * ld_a + c0);
+            if (two) d1.load_stream(addend + (r + PL) * ld_a + c0);
+        }
+        float f0[8], f1[8], e0[8], e1[8];
+        a0.to_float(f0);
+        if (two) a1.to_float(f1);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            f0[k] = apply_act(fmaf(f0[k], sc[k], sh[k]), act);
+            if (two) f1[k] = apply_act(fmaf(f1[k], sc[k], sh[k]), act);
+        }
+        if (addend != nullptr) {
+            d0.to_float(e0);
+            if (two) d1.to_float(e1);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { f0[k] += e0[k]; if (two) f1[k] += e1[k]; }
+        }
+        Vec8<T> o0; o0.from_float(f0); o0.store(out + r * ld_o + c0);
+        if (two) { Vec8<T> o1; o1.from_float(f1); o1.store(out + (r + PL) * ld_o + c0); }
+    }
 }
 
 template <typename T, int V>
@@ -698,10 +772,10 @@ cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long n) {
     if (i < n) y[i] = from_f<TO>(to_f<TI>(x[i]));
 }
 
-static void col_reduce_grid(int CV, int CVB, long long M, int& gx, int& gy, long long& rpb) {
+static void col_reduce_grid(int CV, int CVB, long long M, int& gx, int& gy, long long& rpb, int waves = 8) {
     gx = cdiv(CV, CVB);
     const int PL = 256 / CVB;
-    long long want = (long long)kNumSMs * 8 / gx; if (want < 1) want = 1;
+    long long want = (long long)kNumSMs * waves / gx; if (want < 1) want = 1;
     rpb = (M + want - 1) / want;
     rpb = ((rpb + 2 * PL - 1) / (2 * PL)) * (2 * PL);
     if (rpb < 2 * PL) rpb = 2 * PL;
@@ -766,10 +840,14 @@ extern "C" int dlv3p_affine_act(const void* y, int64_t ld_y, const float* scale,
     const bool v8 = vec_ok(C, {ld_y, ld_out, addend ? ld_addend : 0}, {y, out, addend});
     DLV3P_DISPATCH_DTYPE(dtype, T, {
         if (v8) {
-            const long long total = M * (C / 8);
-            affine_act_kernel<T, 8><<<cdiv(total, 256), 256, 0, st>>>((const T*)y, ld_y, scale, shift, act,
-                                                                      (const T*)addend, ld_addend, (T*)out, ld_out,
-                                                                      M, C);
+            pick_cvb(C / 8, [&](auto cvb) {
+                constexpr int CVB = decltype(cvb)::value;
+                int gx, gy; long long rpb;
+                col_reduce_grid(C / 8, CVB, M, gx, gy, rpb, 16);
+                affine_act_rows_kernel<T, CVB><<<dim3(gx, gy), 256, 0, st>>>((const T*)y, ld_y, scale, shift, act,
+                                                                             (const T*)addend, ld_addend, (T*)out,
+                                                                             ld_out, M, C, rpb);
+            });
         } else {
             const long long total = M * C;
             affine_act_kernel<T, 1><<<cdiv(total, 256), 256, 0, st>>>((const T*)y, ld_y, scale, shift, act,
@@ -811,9 +889,14 @@ extern "C" int dlv3p_bn_bwd_apply(const void* dz, int64_t ld_dz, const void* y, 
                   "bn_bwd_apply: C/ld must be multiples of 8");
     cudaStream_t st = (cudaStream_t)stream;
     DLV3P_DISPATCH_DTYPE(dtype, T, {
-        const long long total = M * (C / 8);
-        bn_bwd_apply_kernel<T><<<cdiv(total, 256), 256, 0, st>>>((const T*)dz, ld_dz, (const T*)y, ld_y, scale, shift,
-                                                                 mean, invstd, act, red, M, C, (T*)dy, ld_dy);
+        pick_cvb(C / 8, [&](auto cvb) {
+            constexpr int CVB = decltype(cvb)::value;
+            int gx, gy; long long rpb;
+            col_reduce_grid(C / 8, CVB, M, gx, gy, rpb, 16);
+            bn_bwd_apply_kernel<T, CVB><<<dim3(gx, gy), 256, 0, st>>>((const T*)dz, ld_dz, (const T*)y, ld_y, scale,
+                                                                     shift, mean, invstd, act, red, M, C, (T*)dy,
+                                                                     ld_dy, rpb);
+        });
         return check_launch("bn_bwd_apply");
     });
     return 0;

@@ -26,7 +26,7 @@ namespace dlv3p {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;            // 64 bf16 = 128 B = one swizzle atom row
-constexpr int kStages = 4;
+constexpr int kMaxStages = 4;
 constexpr int kThreads = 192;
 
 struct GemmParams {
@@ -113,8 +113,10 @@ __device__ __forceinline__ float warp_col_sums(float (&v)[32], int lane) {
     return v[0];
 }
 
-template <int BLOCK_N, bool WGRAD>
-__global__ void __launch_bounds__(kThreads, 1)
+// kStages is matched to the depth of the K loop: the HBM-bound GEMMs of the entry flow (K = 64..256, i.e. 1-4
+// k-blocks) take 1-2 stages so that 2-3 CTAs share an SM and one CTA's epilogue overlaps another's loads.
+template <int BLOCK_N, bool WGRAD, int kStages>
+__global__ void __launch_bounds__(kThreads, (kStages <= 2 && BLOCK_N <= 128) ? 3 : (kStages <= 2 ? 2 : 1))
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     constexpr int A_BYTES = kBlockM * kBlockK * 2;
     constexpr int B_BYTES = BLOCK_N * kBlockK * 2;
@@ -248,11 +250,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
             if (p.col_stats != nullptr) {
                 // rows beyond M were zero-filled by TMA, so they add nothing
-                float s1[32], s2[32];
+                float sbuf[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) { s1[j] = v[j]; s2[j] = v[j] * v[j]; }
-                const float c1 = warp_col_sums(s1, lane);
-                const float c2 = warp_col_sums(s2, lane);
+                for (int j = 0; j < 32; ++j) sbuf[j] = v[j];
+                const float c1 = warp_col_sums(sbuf, lane);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sbuf[j] = v[j] * v[j];
+                const float c2 = warp_col_sums(sbuf, lane);
                 if (n_base + lane < p.N) {
                     atomicAdd(p.col_stats + n_base + lane, c1);
                     atomicAdd(p.col_stats + p.N + n_base + lane, c2);
@@ -361,17 +365,26 @@ static int make_tmap(CUtensorMap* map, const void* base, long long d0, long long
     return 0;
 }
 
-template <int BLOCK_N, bool WGRAD>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, dim3 grid, cudaStream_t st) {
+template <int BLOCK_N, bool WGRAD, int kStages>
+static int launch_gemm_s(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, dim3 grid, cudaStream_t st) {
     constexpr int smem = kStages * (kBlockM * kBlockK * 2 + BLOCK_N * kBlockK * 2) + 1024 /*align*/ + 256 /*barriers*/;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, WGRAD, kStages>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         DLV3P_REQUIRE(e == cudaSuccess, DLV3P_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
         configured = true;
     }
-    gemm_tc_kernel<BLOCK_N, WGRAD><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+    gemm_tc_kernel<BLOCK_N, WGRAD, kStages><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
     return check_launch(WGRAD ? "gemm_wgrad_bf16" : "gemm_bf16");
+}
+
+template <int BLOCK_N, bool WGRAD>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, dim3 grid, cudaStream_t st,
+                       int k_blocks) {
+    if (k_blocks <= 1) return launch_gemm_s<BLOCK_N, WGRAD, 1>(tmA, tmB, p, grid, st);
+    if (k_blocks <= 3) return launch_gemm_s<BLOCK_N, WGRAD, 2>(tmA, tmB, p, grid, st);
+    return launch_gemm_s<BLOCK_N, WGRAD, kMaxStages>(tmA, tmB, p, grid, st);
 }
 
 }  // namespace dlv3p
@@ -400,11 +413,12 @@ extern "C" int dlv3p_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
     p.col_scale = col_scale; p.col_shift = col_shift; p.act = act;
     p.addend = addend; p.ld_add = ld_addend; p.col_stats = col_stats; p.kb_per_split = 0;
     dim3 grid(cdiv(N, bn), cdiv(M, kBlockM), 1);
+    const int kbs = cdiv(K, kBlockK);
     switch (bn) {
-        case 32: return launch_gemm<32, false>(tmA, tmB, p, grid, st);
-        case 64: return launch_gemm<64, false>(tmA, tmB, p, grid, st);
-        case 128: return launch_gemm<128, false>(tmA, tmB, p, grid, st);
-        default: return launch_gemm<256, false>(tmA, tmB, p, grid, st);
+        case 32: return launch_gemm<32, false>(tmA, tmB, p, grid, st, kbs);
+        case 64: return launch_gemm<64, false>(tmA, tmB, p, grid, st, kbs);
+        case 128: return launch_gemm<128, false>(tmA, tmB, p, grid, st, kbs);
+        default: return launch_gemm<256, false>(tmA, tmB, p, grid, st, kbs);
     }
 }
 
@@ -436,8 +450,8 @@ extern "C" int dlv3p_gemm_wgrad_bf16(const void* X, int64_t ldx, const void* dY,
     p.kb_per_split = kb_per_split;
     dim3 grid(cdiv(N, bn), cdiv(K, kBlockM), splits);
     switch (bn) {
-        case 64: return launch_gemm<64, true>(tmA, tmB, p, grid, st);
-        case 128: return launch_gemm<128, true>(tmA, tmB, p, grid, st);
-        default: return launch_gemm<256, true>(tmA, tmB, p, grid, st);
+        case 64: return launch_gemm<64, true>(tmA, tmB, p, grid, st, kb_per_split);
+        case 128: return launch_gemm<128, true>(tmA, tmB, p, grid, st, kb_per_split);
+        default: return launch_gemm<256, true>(tmA, tmB, p, grid, st, kb_per_split);
     }
 }

@@ -18,17 +18,20 @@ __device__ __forceinline__ float warp_max(float v) {
 // softmax of one pixel held one-class-per-lane; inactive lanes (lane >= C) return 0
 __device__ __forceinline__ float lane_softmax(float z, bool active) {
     const float m = warp_max(active ? z : -INFINITY);
-    const float e = active ? expf(z - m) : 0.f;
+    // ex2.approx / rcp.approx based intrinsics (<= 2 ulp): these kernels are issue-bound, not HBM-bound — the
+    // accurate expf/logf/div expansions cost ~4x the instructions for no measurable change in the loss (parity
+    // tests: loss within 1e-4, gradient within 1e-3 of the fp64 oracle)
+    const float e = active ? __expf(z - m) : 0.f;
     const float s = warp_sum(e);
-    return e / s;
+    return __fdividef(e, s);
 }
 
 // per-lane loss term and dL/dp for class `lane`
 __device__ __forceinline__ float cb_term(float p, float y, float pw, float nw, float eps) {
-    return -(pw * y * logf(p + eps) + nw * (1.f - y) * logf(1.f - p + eps));
+    return -(pw * y * __logf(p + eps) + nw * (1.f - y) * __logf(1.f - p + eps));
 }
 __device__ __forceinline__ float cb_dterm(float p, float y, float pw, float nw, float eps) {
-    return -(pw * y / (p + eps)) + nw * (1.f - y) / (1.f - p + eps);
+    return -__fdividef(pw * y, p + eps) + __fdividef(nw * (1.f - y), 1.f - p + eps);
 }
 
 __device__ __forceinline__ void block_atomic_sum(float v, float* out) {

@@ -116,3 +116,20 @@ class KernelProfiler:
             a["GBps"] = a["bytes"] / sec / 1e9
             a["TFLOPs"] = a["flops"] / sec / 1e12
         return out
+
+    def detail(self, top: int = 40):
+        """Per (entry point, shape) breakdown: [(name, small-int args, calls, ms, GB/s, TFLOP/s)] sorted by time."""
+        torch.cuda.synchronize()
+        agg = defaultdict(lambda: [0, 0.0, 0, 0])
+        for name, args, e0, e1 in self.records:
+            sig = tuple(a for a in args if isinstance(a, int) and not isinstance(a, bool) and 0 <= a < (1 << 24))
+            b, f = cost(name, args)
+            a = agg[(name, sig)]
+            a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += b; a[3] += f
+        rows = []
+        for (name, sig), (calls, ms, b, f) in agg.items():
+            sec = max(ms, 1e-9) / 1e3
+            rows.append(dict(kernel=name, args=list(sig), calls=calls, ms=ms, GBps=b / sec / 1e9,
+                             TFLOPs=f / sec / 1e12))
+        rows.sort(key=lambda r: -r["ms"])
+        return rows[:top]
