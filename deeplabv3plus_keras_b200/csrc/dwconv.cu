@@ -484,7 +484,8 @@ extern "C" int dlv3p_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, i
                 constexpr int CVB = decltype(cvb)::value;
                 constexpr int PL = 128 / CVB;
                 const int gx = cdiv(CV, CVB);
-                long long want = (long long)kNumSMs * 12 / gx; if (want < 1) want = 1;
+                // few fat blocks: every block ends with 72 x CVB fp32 atomics on the same 9*C addresses
+                long long want = (long long)kNumSMs * 4 / gx; if (want < 1) want = 1;
                 long long spb = (nstrips + want - 1) / want; spb = ((spb + PL - 1) / PL) * PL; if (spb < PL) spb = PL;
                 const int gy = cdiv(nstrips, spb);
                 dw_wgrad_strip_kernel<T, CVB><<<dim3(gx, gy), 128, 0, st>>>((const T*)x, (const T*)dy, dw, N, H, W, C,

@@ -4,17 +4,21 @@
 // SeparableConv2D, the ASPP / decoder projections (ss.py:814-818,833-838,843-847,865-869,931-935) and, after
 // im2col, the dense 3x3 convs (ss.py:893-897).
 //
-// Structure (one 128 x BLOCK_N output tile per CTA, 192 threads):
-//   warp 0, one lane : TMA producer  — cp.async.bulk.tensor 2D tiles (128B swizzle) into a 4-stage smem ring,
-//                                      completion on mbarriers (expect_tx)
+// Persistent kernel: one CTA per SM (192 threads) walks a static list of 128 x BLOCK_N output tiles.
+//   warp 0, one lane : TMA producer  — cp.async.bulk.tensor 2D tiles (128B swizzle) into a 4-stage smem ring that
+//                                      runs ahead across tile boundaries; completion on mbarriers (expect_tx)
 //   warp 1, one lane : MMA issuer    — tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N, K=16 per instruction,
-//                                      fp32 accumulator in TMEM (BLOCK_N columns); tcgen05.commit releases smem slots
-//   warps 2..5       : epilogue      — tcgen05.ld 32x32b (one accumulator row per thread), fused per-column
-//                                      scale/shift (folded BatchNorm) + ReLU/ReLU6 + residual addend, optional
-//                                      per-column sum / sum-of-squares (training-mode BatchNorm statistics), store
+//                                      fp32 accumulators in TMEM, TWO accumulator stages (2*BLOCK_N columns) so the
+//                                      epilogue of tile i overlaps the main loop of tile i+1
+//   warps 2..5       : epilogue      — tcgen05.ld 32x32b (one accumulator row per lane) -> 32x33 fp32 smem transpose
+//                                      -> column-per-lane pass: fused per-column scale/shift (folded BatchNorm) +
+//                                      ReLU/ReLU6 + residual addend, shuffle-free per-column sum / sum-of-squares
+//                                      (training-mode BatchNorm statistics), coalesced stores (or coalesced fp32 REDs
+//                                      for the filter gradient)
 // Forward / input-gradient use K-major operands (A[M,K], B[N,K], K contiguous).  The filter gradient
 // dW = X^T dY contracts over the pixel axis, which is NOT contiguous in NHWC: both operands are fed MN-major
-// (64-element x 64-row TMA boxes, same 128B swizzle) so no transposed copy of the activations is ever written.
+// (64-element x 64-row TMA boxes, same 128B swizzle) so no transposed copy of the activations is ever written;
+// its work list is (pixel-range split) x (tile), split-major so that concurrently running CTAs share operands in L2.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -26,8 +30,9 @@ namespace dlv3p {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;            // 64 bf16 = 128 B = one swizzle atom row
-constexpr int kMaxStages = 4;
+constexpr int kStages = 4;
 constexpr int kThreads = 192;
+constexpr int kEpiStageFloats = 32 * 33;          // per epilogue warp: 32 rows x 32 cols, padded
 
 struct GemmParams {
     int M, N, K;                       // logical GEMM extents (for WGRAD: rows=K(cin), cols=N(cout), reduction=M)
@@ -35,7 +40,9 @@ struct GemmParams {
     const float* col_scale; const float* col_shift; int act;
     const void* addend; long long ld_add;
     float* col_stats;
-    int kb_per_split;                  // WGRAD: reduction blocks (of 64 rows) handled by one CTA
+    int kb_per_split;                  // WGRAD: reduction blocks (of 64 rows) handled by one work item
+    int splits;                        // WGRAD: number of pixel-range splits
+    int n_tiles, m_tiles;              // output tile grid
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------
@@ -46,6 +53,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
@@ -97,38 +107,42 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
            ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
-// column sums over the 32 lanes (= 32 accumulator rows) of a warp for 32 columns held as v[0..31] per lane:
-// recursive halving, 31 shuffles; on return lane L holds the sum of column L in v[0].
-__device__ __forceinline__ float warp_col_sums(float (&v)[32], int lane) {
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-        const bool up = (lane & o) != 0;
-#pragma unroll
-        for (int i = 0; i < o; ++i) {
-            const float send = up ? v[i] : v[i + o];
-            const float keep = up ? v[i + o] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-        }
+// decode a work item: forward -> output tile (n fastest, so neighbouring CTAs share the A rows in L2);
+// filter gradient -> (split, tile), split-major
+template <int BLOCK_N, bool WGRAD>
+__device__ __forceinline__ void decode_work(const GemmParams& p, int w, int& row0, int& col0, int& kb_begin,
+                                            int& kb_end) {
+    const int tiles = p.n_tiles * p.m_tiles;
+    const int tile = WGRAD ? (w % tiles) : w;
+    row0 = (tile / p.n_tiles) * kBlockM;
+    col0 = (tile % p.n_tiles) * BLOCK_N;
+    if (WGRAD) {
+        const int total_kb = (p.M + kBlockK - 1) / kBlockK;
+        kb_begin = (w / tiles) * p.kb_per_split;
+        kb_end = min(kb_begin + p.kb_per_split, total_kb);
+    } else {
+        kb_begin = 0;
+        kb_end = (p.K + kBlockK - 1) / kBlockK;
     }
-    return v[0];
 }
 
-// kStages is matched to the depth of the K loop: the HBM-bound GEMMs of the entry flow (K = 64..256, i.e. 1-4
-// k-blocks) take 1-2 stages so that 2-3 CTAs share an SM and one CTA's epilogue overlaps another's loads.
-template <int BLOCK_N, bool WGRAD, int kStages>
-__global__ void __launch_bounds__(kThreads, (kStages <= 2 && BLOCK_N <= 128) ? 3 : (kStages <= 2 ? 2 : 1))
+template <int BLOCK_N, bool WGRAD>
+__global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     constexpr int A_BYTES = kBlockM * kBlockK * 2;
     constexpr int B_BYTES = BLOCK_N * kBlockK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;            // two accumulator stages (64 .. 512, power of two)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES);
+    float* epi_stage = reinterpret_cast<float*>(smem + kStages * STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES + 4 * kEpiStageFloats * 4);
     const uint32_t smem_base = smem_u32(smem);
-    const uint32_t full_bar = smem_u32(bars);                    // kStages barriers
-    const uint32_t empty_bar = smem_u32(bars + kStages);         // kStages barriers
-    const uint32_t tmem_full_bar = smem_u32(bars + 2 * kStages);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+    const uint32_t full_bar = smem_u32(bars);                      // kStages
+    const uint32_t empty_bar = smem_u32(bars + kStages);           // kStages
+    const uint32_t tmem_full_bar = smem_u32(bars + 2 * kStages);   // 2
+    const uint32_t tmem_empty_bar = smem_u32(bars + 2 * kStages + 2);  // 2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -136,12 +150,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
         for (int s = 0; s < kStages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
-        mbar_init(tmem_full_bar, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + 8 * s, 1); mbar_init(tmem_empty_bar + 8 * s, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"((uint32_t)BLOCK_N) : "memory");
+                     "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -149,42 +163,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-    // tile coordinates.  Forward: rows = pixels (blockIdx.y), cols = out channels (blockIdx.x), reduce over K.
-    // WGRAD: rows = in channels (blockIdx.y), cols = out channels (blockIdx.x), reduce over pixels (split blockIdx.z).
-    const int row0 = blockIdx.y * kBlockM;
-    const int col0 = blockIdx.x * BLOCK_N;
-    int kb_begin, kb_end;
-    if (WGRAD) {
-        const int total_kb = (p.M + kBlockK - 1) / kBlockK;
-        kb_begin = blockIdx.z * p.kb_per_split;
-        kb_end = min(kb_begin + p.kb_per_split, total_kb);
-    } else {
-        kb_begin = 0;
-        kb_end = (p.K + kBlockK - 1) / kBlockK;
-    }
-    const int num_kb = kb_end - kb_begin;     // host guarantees >= 1
+    const int num_work = p.n_tiles * p.m_tiles * (WGRAD ? p.splits : 1);
 
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer =====
-            for (int i = 0; i < num_kb; ++i) {
-                const int s = i % kStages;
-                const uint32_t ph = (uint32_t)(i / kStages) & 1u;
-                mbar_wait(empty_bar + 8 * s, ph ^ 1u);
-                const uint32_t a_dst = smem_base + s * STAGE_BYTES;
-                const uint32_t b_dst = a_dst + A_BYTES;
-                const uint32_t fb = full_bar + 8 * s;
-                mbar_expect_tx(fb, STAGE_BYTES);
-                const int kk = (kb_begin + i) * kBlockK;
-                if (WGRAD) {
-                    // MN-major operands: boxes of 64 channels (inner, 128 B) x 64 pixels
+            uint32_t it = 0;                                   // ring position, continues across tiles
+            for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+                int row0, col0, kb_begin, kb_end;
+                decode_work<BLOCK_N, WGRAD>(p, w, row0, col0, kb_begin, kb_end);
+                for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+                    const uint32_t s = it % kStages;
+                    const uint32_t ph = (it / kStages) & 1u;
+                    mbar_wait(empty_bar + 8 * s, ph ^ 1u);
+                    const uint32_t a_dst = smem_base + s * STAGE_BYTES;
+                    const uint32_t b_dst = a_dst + A_BYTES;
+                    const uint32_t fb = full_bar + 8 * s;
+                    mbar_expect_tx(fb, STAGE_BYTES);
+                    const int kk = kb * kBlockK;
+                    if (WGRAD) {
+                        // MN-major operands: boxes of 64 channels (inner, 128 B) x 64 pixels
 #pragma unroll
-                    for (int h = 0; h < kBlockM / 64; ++h) tma_load_2d(a_dst + h * 8192, &tmA, fb, row0 + 64 * h, kk);
+                        for (int h = 0; h < kBlockM / 64; ++h) tma_load_2d(a_dst + h * 8192, &tmA, fb, row0 + 64 * h, kk);
 #pragma unroll
-                    for (int h = 0; h < BLOCK_N / 64; ++h) tma_load_2d(b_dst + h * 8192, &tmB, fb, col0 + 64 * h, kk);
-                } else {
-                    tma_load_2d(a_dst, &tmA, fb, kk, row0);
-                    tma_load_2d(b_dst, &tmB, fb, kk, col0);
+                        for (int h = 0; h < BLOCK_N / 64; ++h) tma_load_2d(b_dst + h * 8192, &tmB, fb, col0 + 64 * h, kk);
+                    } else {
+                        tma_load_2d(a_dst, &tmA, fb, kk, row0);
+                        tma_load_2d(b_dst, &tmB, fb, kk, col0);
+                    }
                 }
             }
         }
@@ -194,143 +200,167 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             constexpr uint32_t idesc = (1u << 4) /*D=f32*/ | (1u << 7) /*A=bf16*/ | (1u << 10) /*B=bf16*/ |
                                        ((WGRAD ? 1u : 0u) << 15) | ((WGRAD ? 1u : 0u) << 16) |
                                        ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
-            for (int i = 0; i < num_kb; ++i) {
-                const int s = i % kStages;
-                const uint32_t ph = (uint32_t)(i / kStages) & 1u;
-                mbar_wait(full_bar + 8 * s, ph);
+            uint32_t it = 0, t = 0;
+            for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++t) {
+                int row0, col0, kb_begin, kb_end;
+                decode_work<BLOCK_N, WGRAD>(p, w, row0, col0, kb_begin, kb_end);
+                const uint32_t as = t & 1u;                    // accumulator stage
+                mbar_wait(tmem_empty_bar + 8 * as, ((t >> 1) & 1u) ^ 1u);   // epilogue has drained this stage
                 tc_fence_after();
-                const uint32_t a_src = smem_base + s * STAGE_BYTES;
-                const uint32_t b_src = a_src + A_BYTES;
+                const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+                for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+                    const uint32_t s = it % kStages;
+                    const uint32_t ph = (it / kStages) & 1u;
+                    mbar_wait(full_bar + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t a_src = smem_base + s * STAGE_BYTES;
+                    const uint32_t b_src = a_src + A_BYTES;
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
-                    uint64_t ad, bd;
-                    if (WGRAD) {
-                        // MN-major SW128: LBO = next 64-element MN chunk (one 8 KB box), SBO = next 8 K-rows (1 KB);
-                        // a K=16 step is 16 rows of 128 B
-                        ad = umma_desc(a_src + k * 2048, 8192, 1024);
-                        bd = umma_desc(b_src + k * 2048, 8192, 1024);
-                    } else {
-                        // K-major SW128: SBO = next 8 rows (1 KB); a K=16 step is 32 B inside the swizzle atom
-                        ad = umma_desc(a_src + k * 32, 16, 1024);
-                        bd = umma_desc(b_src + k * 32, 16, 1024);
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        uint64_t ad, bd;
+                        if (WGRAD) {
+                            // MN-major SW128: LBO = next 64-element MN chunk (one 8 KB box), SBO = next 8 K-rows
+                            // (1 KB); a K=16 step is 16 rows of 128 B
+                            ad = umma_desc(a_src + k * 2048, 8192, 1024);
+                            bd = umma_desc(b_src + k * 2048, 8192, 1024);
+                        } else {
+                            // K-major SW128: SBO = next 8 rows (1 KB); a K=16 step is 32 B inside the swizzle atom
+                            ad = umma_desc(a_src + k * 32, 16, 1024);
+                            bd = umma_desc(b_src + k * 32, 16, 1024);
+                        }
+                        tc_mma_bf16(d_tmem, ad, bd, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
                     }
-                    tc_mma_bf16(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    tc_commit(empty_bar + 8 * s);              // smem slot reusable once these MMAs retire
                 }
-                tc_commit(empty_bar + 8 * s);          // smem slot reusable once these MMAs retire
+                tc_commit(tmem_full_bar + 8 * as);             // accumulator stage complete
             }
-            tc_commit(tmem_full_bar);                  // accumulator complete
         }
     } else {
         // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
         const int q = warp & 3;
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
-        const int r = row0 + q * 32 + lane;            // output row owned by this thread
+        float* stage = epi_stage + q * kEpiStageFloats;
         const int row_limit = WGRAD ? p.K : p.M;
-        const bool row_ok = r < row_limit;
+        const bool out_bf16 = (p.c_dtype == DLV3P_BF16);
+        // bf16 outputs are written as packed pairs: lane -> (row parity, column pair)
+        const int half = lane >> 4, c2 = (lane & 15) * 2;
+        const bool pair_ok = out_bf16 && ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 3) == 0) &&
+                             (p.addend == nullptr || (((p.ld_add & 1) == 0) &&
+                                                      ((reinterpret_cast<uintptr_t>(p.addend) & 3) == 0)));
+        uint32_t t = 0;
+        for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++t) {
+            int row0, col0, kb_begin, kb_end;
+            decode_work<BLOCK_N, WGRAD>(p, w, row0, col0, kb_begin, kb_end);
+            const uint32_t as = t & 1u;
+            mbar_wait(tmem_full_bar + 8 * as, (t >> 1) & 1u);
+            tc_fence_after();
+            const int rbase = row0 + q * 32;                   // first output row of this warp
 #pragma unroll 1
-        for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
-            const int n_base = col0 + ch * 32;
-            if (n_base >= p.N) break;                  // warp-uniform
-            uint32_t raw[32];
-            tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), raw);
-            float v[32];
+            for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+                const int n_base = col0 + ch * 32;
+                const bool last_chunk = (ch == BLOCK_N / 32 - 1) || (n_base + 32 >= p.N);
+                uint32_t raw[32];
+                tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N + (uint32_t)(ch * 32), raw);
+                if (last_chunk) {
+                    // every TMEM read of this accumulator stage has completed: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty_bar + 8 * as);
+                }
+                // transpose through shared memory: row-per-lane -> column-per-lane
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+                for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(raw[j]);
+                __syncwarp();
 
-            if (WGRAD) {
-                if (row_ok) {
-                    float* dst = reinterpret_cast<float*>(p.C) + (long long)r * p.ldc + n_base;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (n_base + j < p.N) atomicAdd(dst + j, v[j]);
-                }
-                continue;
-            }
-
-            if (p.col_stats != nullptr) {
-                // rows beyond M were zero-filled by TMA, so they add nothing
-                float sbuf[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) sbuf[j] = v[j];
-                const float c1 = warp_col_sums(sbuf, lane);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) sbuf[j] = v[j] * v[j];
-                const float c2 = warp_col_sums(sbuf, lane);
-                if (n_base + lane < p.N) {
-                    atomicAdd(p.col_stats + n_base + lane, c1);
-                    atomicAdd(p.col_stats + p.N + n_base + lane, c2);
-                }
-            }
-            if (!row_ok) continue;
-            if (p.col_scale != nullptr) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = min(n_base + j, p.N - 1);
-                    v[j] = fmaf(v[j], __ldg(p.col_scale + n), __ldg(p.col_shift + n));
-                }
-            }
-            if (p.act != DLV3P_ACT_NONE) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
-            }
-            const bool full = (n_base + 32 <= p.N);
-            if (p.c_dtype == DLV3P_BF16) {
-                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)r * p.ldc + n_base;
-                const __nv_bfloat16* add =
-                    p.addend ? reinterpret_cast<const __nv_bfloat16*>(p.addend) + (long long)r * p.ld_add + n_base : nullptr;
-                const bool vec = full && ((p.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
-                                 (add == nullptr || (((p.ld_add & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.addend) & 15) == 0)));
-                if (vec) {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        float f[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) f[j] = v[g * 8 + j];
-                        if (add != nullptr) {
-                            Vec8<__nv_bfloat16> a; a.load(add + g * 8);
-                            float af[8]; a.to_float(af);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) f[j] += af[j];
-                        }
-                        Vec8<__nv_bfloat16> o; o.from_float(f);
-                        o.store(dst + g * 8);
+                if (WGRAD) {
+                    const int col = n_base + lane;
+                    if (col < p.N) {
+                        float* dst = reinterpret_cast<float*>(p.C) + (long long)rbase * p.ldc + col;
+#pragma unroll 8
+                        for (int r = 0; r < 32; ++r)
+                            if (rbase + r < row_limit) atomicAdd(dst + (long long)r * p.ldc, stage[r * 33 + lane]);
                     }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (n_base + j < p.N) {
-                            float f = v[j];
-                            if (add != nullptr) f += __bfloat162float(add[j]);
-                            dst[j] = __float2bfloat16_rn(f);
+                } else if (pair_ok) {
+                    const int col = n_base + c2;
+                    const bool ok0 = col < p.N, ok1 = col + 1 < p.N;
+                    float sc0 = 1.f, sc1 = 1.f, sh0 = 0.f, sh1 = 0.f;
+                    if (p.col_scale != nullptr) {
+                        if (ok0) { sc0 = __ldg(p.col_scale + col); sh0 = __ldg(p.col_shift + col); }
+                        if (ok1) { sc1 = __ldg(p.col_scale + col + 1); sh1 = __ldg(p.col_shift + col + 1); }
+                    }
+                    float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+                    __nv_bfloat16* cbase = reinterpret_cast<__nv_bfloat16*>(p.C);
+                    const __nv_bfloat16* abase = reinterpret_cast<const __nv_bfloat16*>(p.addend);
+#pragma unroll 4
+                    for (int i = 0; i < 16; ++i) {
+                        const int r = 2 * i + half;
+                        float v0 = stage[r * 33 + c2], v1 = stage[r * 33 + c2 + 1];
+                        s1a += v0; s1b += v1; s2a = fmaf(v0, v0, s2a); s2b = fmaf(v1, v1, s2b);
+                        const int row = rbase + r;
+                        if (row < row_limit && ok0) {
+                            v0 = apply_act(fmaf(v0, sc0, sh0), p.act);
+                            v1 = apply_act(fmaf(v1, sc1, sh1), p.act);
+                            const long long off = (long long)row * p.ldc + col;
+                            if (ok1) {
+                                if (abase != nullptr) {
+                                    const __nv_bfloat162 a2 =
+                                        *reinterpret_cast<const __nv_bfloat162*>(abase + (long long)row * p.ld_add + col);
+                                    v0 += __low2float(a2); v1 += __high2float(a2);
+                                }
+                                *reinterpret_cast<__nv_bfloat162*>(cbase + off) = __floats2bfloat162_rn(v0, v1);
+                            } else {
+                                if (abase != nullptr) v0 += __bfloat162float(abase[(long long)row * p.ld_add + col]);
+                                cbase[off] = __float2bfloat16_rn(v0);
+                            }
                         }
                     }
-                }
-            } else {
-                float* dst = reinterpret_cast<float*>(p.C) + (long long)r * p.ldc + n_base;
-                const float* add = p.addend ? reinterpret_cast<const float*>(p.addend) + (long long)r * p.ld_add + n_base : nullptr;
-                const bool vec = full && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (add != nullptr && n_base + j < p.N) v[j] += add[j];
-                if (vec) {
-#pragma unroll
-                    for (int g = 0; g < 8; ++g)
-                        reinterpret_cast<float4*>(dst)[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                    if (p.col_stats != nullptr) {
+                        s1a += __shfl_xor_sync(0xffffffffu, s1a, 16); s1b += __shfl_xor_sync(0xffffffffu, s1b, 16);
+                        s2a += __shfl_xor_sync(0xffffffffu, s2a, 16); s2b += __shfl_xor_sync(0xffffffffu, s2b, 16);
+                        if (half == 0) {
+                            if (ok0) { atomicAdd(p.col_stats + col, s1a); atomicAdd(p.col_stats + p.N + col, s2a); }
+                            if (ok1) { atomicAdd(p.col_stats + col + 1, s1b); atomicAdd(p.col_stats + p.N + col + 1, s2b); }
+                        }
+                    }
                 } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (n_base + j < p.N) dst[j] = v[j];
+                    // one column per lane: fp32 outputs (logits) and odd leading dimensions
+                    const int col = n_base + lane;
+                    const bool ok = col < p.N;
+                    float sc = 1.f, sh = 0.f;
+                    if (ok && p.col_scale != nullptr) { sc = __ldg(p.col_scale + col); sh = __ldg(p.col_shift + col); }
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+                    for (int r = 0; r < 32; ++r) {
+                        float v = stage[r * 33 + lane];
+                        s1 += v; s2 = fmaf(v, v, s2);
+                        const int row = rbase + r;
+                        if (ok && row < row_limit) {
+                            v = apply_act(fmaf(v, sc, sh), p.act);
+                            if (out_bf16) {
+                                if (p.addend != nullptr)
+                                    v += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.addend)[(long long)row * p.ld_add + col]);
+                                reinterpret_cast<__nv_bfloat16*>(p.C)[(long long)row * p.ldc + col] = __float2bfloat16_rn(v);
+                            } else {
+                                if (p.addend != nullptr)
+                                    v += reinterpret_cast<const float*>(p.addend)[(long long)row * p.ld_add + col];
+                                reinterpret_cast<float*>(p.C)[(long long)row * p.ldc + col] = v;
+                            }
+                        }
+                    }
+                    if (ok && p.col_stats != nullptr) {
+                        atomicAdd(p.col_stats + col, s1);
+                        atomicAdd(p.col_stats + p.N + col, s2);
+                    }
                 }
+                __syncwarp();                                  // stage buffer is reused by the next chunk
+                if (last_chunk) break;
             }
         }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BLOCK_N)
-                     : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -365,26 +395,20 @@ static int make_tmap(CUtensorMap* map, const void* base, long long d0, long long
     return 0;
 }
 
-template <int BLOCK_N, bool WGRAD, int kStages>
-static int launch_gemm_s(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, dim3 grid, cudaStream_t st) {
-    constexpr int smem = kStages * (kBlockM * kBlockK * 2 + BLOCK_N * kBlockK * 2) + 1024 /*align*/ + 256 /*barriers*/;
+template <int BLOCK_N, bool WGRAD>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+    constexpr int smem = kStages * (kBlockM * kBlockK * 2 + BLOCK_N * kBlockK * 2) + 4 * kEpiStageFloats * 4 +
+                         1024 /*align*/ + 256 /*barriers*/;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, WGRAD, kStages>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         DLV3P_REQUIRE(e == cudaSuccess, DLV3P_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
         configured = true;
     }
-    gemm_tc_kernel<BLOCK_N, WGRAD, kStages><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+    const int work = p.n_tiles * p.m_tiles * (WGRAD ? p.splits : 1);
+    const int grid = work < kNumSMs ? work : kNumSMs;         // persistent: one CTA per SM
+    gemm_tc_kernel<BLOCK_N, WGRAD><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
     return check_launch(WGRAD ? "gemm_wgrad_bf16" : "gemm_bf16");
-}
-
-template <int BLOCK_N, bool WGRAD>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, dim3 grid, cudaStream_t st,
-                       int k_blocks) {
-    if (k_blocks <= 1) return launch_gemm_s<BLOCK_N, WGRAD, 1>(tmA, tmB, p, grid, st);
-    if (k_blocks <= 3) return launch_gemm_s<BLOCK_N, WGRAD, 2>(tmA, tmB, p, grid, st);
-    return launch_gemm_s<BLOCK_N, WGRAD, kMaxStages>(tmA, tmB, p, grid, st);
 }
 
 }  // namespace dlv3p
@@ -411,14 +435,13 @@ extern "C" int dlv3p_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
     GemmParams p;
     p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.c_dtype = c_dtype;
     p.col_scale = col_scale; p.col_shift = col_shift; p.act = act;
-    p.addend = addend; p.ld_add = ld_addend; p.col_stats = col_stats; p.kb_per_split = 0;
-    dim3 grid(cdiv(N, bn), cdiv(M, kBlockM), 1);
-    const int kbs = cdiv(K, kBlockK);
+    p.addend = addend; p.ld_add = ld_addend; p.col_stats = col_stats; p.kb_per_split = 0; p.splits = 1;
+    p.n_tiles = cdiv(N, bn); p.m_tiles = cdiv(M, kBlockM);
     switch (bn) {
-        case 32: return launch_gemm<32, false>(tmA, tmB, p, grid, st, kbs);
-        case 64: return launch_gemm<64, false>(tmA, tmB, p, grid, st, kbs);
-        case 128: return launch_gemm<128, false>(tmA, tmB, p, grid, st, kbs);
-        default: return launch_gemm<256, false>(tmA, tmB, p, grid, st, kbs);
+        case 32: return launch_gemm<32, false>(tmA, tmB, p, st);
+        case 64: return launch_gemm<64, false>(tmA, tmB, p, st);
+        case 128: return launch_gemm<128, false>(tmA, tmB, p, st);
+        default: return launch_gemm<256, false>(tmA, tmB, p, st);
     }
 }
 
@@ -437,21 +460,21 @@ extern "C" int dlv3p_gemm_wgrad_bf16(const void* X, int64_t ldx, const void* dY,
     if (rc) return rc;
     rc = make_tmap(&tmB, dY, N, M, ldy, 64, kBlockK);
     if (rc) return rc;
-    const int tiles = cdiv(N, bn) * cdiv(K, kBlockM);
-    const int total_kb = cdiv(M, kBlockK);
-    int splits = cdiv(2 * kNumSMs, tiles);
-    if (splits > total_kb) splits = total_kb;
-    if (splits < 1) splits = 1;
-    const int kb_per_split = cdiv(total_kb, splits);
-    splits = cdiv(total_kb, kb_per_split);
     GemmParams p;
     p.M = M; p.N = N; p.K = K; p.C = dW; p.ldc = ldw; p.c_dtype = DLV3P_F32;
     p.col_scale = nullptr; p.col_shift = nullptr; p.act = 0; p.addend = nullptr; p.ld_add = 0; p.col_stats = nullptr;
-    p.kb_per_split = kb_per_split;
-    dim3 grid(cdiv(N, bn), cdiv(K, kBlockM), splits);
+    p.n_tiles = cdiv(N, bn); p.m_tiles = cdiv(K, kBlockM);
+    const int tiles = p.n_tiles * p.m_tiles;
+    const int total_kb = cdiv(M, kBlockK);
+    // one wave of work items: every extra split costs a full tile of fp32 REDs
+    int splits = kNumSMs / tiles;
+    if (splits < 1) splits = 1;
+    if (splits > total_kb) splits = total_kb;
+    p.kb_per_split = cdiv(total_kb, splits);
+    p.splits = cdiv(total_kb, p.kb_per_split);
     switch (bn) {
-        case 64: return launch_gemm<64, true>(tmA, tmB, p, grid, st, kb_per_split);
-        case 128: return launch_gemm<128, true>(tmA, tmB, p, grid, st, kb_per_split);
-        default: return launch_gemm<256, true>(tmA, tmB, p, grid, st, kb_per_split);
+        case 64: return launch_gemm<64, true>(tmA, tmB, p, st);
+        case 128: return launch_gemm<128, true>(tmA, tmB, p, st);
+        default: return launch_gemm<256, true>(tmA, tmB, p, st);
     }
 }

@@ -152,8 +152,8 @@ def test_inference_parity_and_labels(case, dtype):
         return
     emu = OM.forward(conf, w, xin, training=False, emulate_bf16=True)["probs"].numpy()
     emu2 = OM.forward(conf, perturbed(w), xin, training=False, emulate_bf16=True)["probs"].numpy()
-    floor = np.abs(emu2 - emu).max()
-    assert np.abs(probs - emu).max() <= 1.5 * floor + 2e-2, (np.abs(probs - emu).max(), floor)
+    floor = rms_rel(emu2, emu)
+    assert rms_rel(probs, emu) <= 1.5 * floor + 2e-2, (rms_rel(probs, emu), floor)
     # label maps: as close to the exact labels as the bf16 oracle itself is (random-init logits are nearly tied)
     a_mine = (labels == exact.argmax(-1)).mean()
     a_floor = min((emu.argmax(-1) == exact.argmax(-1)).mean(), (emu2.argmax(-1) == exact.argmax(-1)).mean())
@@ -192,7 +192,8 @@ def test_trainer_graph_replay_matches_eager():
         xs, ys = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
         losses.append([tr.train_step_e2e(xs, ys) for _ in range(4)])
     a, b = np.array(losses[0]), np.array(losses[1])
-    assert np.all(np.isfinite(a)) and np.allclose(a, b, rtol=1e-3), (a, b)
+    # fp32 atomics make summation order run-dependent; the difference is amplified step over step
+    assert np.all(np.isfinite(a)) and np.allclose(a[:2], b[:2], rtol=1e-5) and np.allclose(a, b, rtol=2e-2), (a, b)
     assert a[3] != a[0], "weights did not change between steps"
 
 
