@@ -772,7 +772,7 @@ cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long n) {
     if (i < n) y[i] = from_f<TO>(to_f<TI>(x[i]));
 }
 
-static void col_reduce_grid(int CV, int CVB, long long M, int& gx, int& gy, long long& rpb, int waves = 8) {
+static void col_reduce_grid(int CV, int CVB, long long M, int& gx, int& gy, long long& rpb, int waves = 3) {
     gx = cdiv(CV, CVB);
     const int PL = 256 / CVB;
     long long want = (long long)kNumSMs * waves / gx; if (want < 1) want = 1;

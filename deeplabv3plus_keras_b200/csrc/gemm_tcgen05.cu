@@ -33,6 +33,7 @@ constexpr int kBlockK = 64;            // 64 bf16 = 128 B = one swizzle atom row
 constexpr int kStages = 4;
 constexpr int kThreads = 192;
 constexpr int kEpiStageFloats = 32 * 33;          // per epilogue warp: 32 rows x 32 cols, padded
+constexpr int kMaxStatCols = 1024;                // per-CTA smem accumulators for the BN column statistics
 
 struct GemmParams {
     int M, N, K;                       // logical GEMM extents (for WGRAD: rows=K(cin), cols=N(cout), reduction=M)
@@ -136,7 +137,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     float* epi_stage = reinterpret_cast<float*>(smem + kStages * STAGE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES + 4 * kEpiStageFloats * 4);
+    float* stat_smem = epi_stage + 4 * kEpiStageFloats;                      // [2][kMaxStatCols]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES + 4 * kEpiStageFloats * 4 +
+                                                 2 * kMaxStatCols * 4);
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t full_bar = smem_u32(bars);                      // kStages
     const uint32_t empty_bar = smem_u32(bars + kStages);           // kStages
@@ -146,6 +149,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    if (!WGRAD && p.col_stats != nullptr)
+        for (int i = threadIdx.x; i < 2 * kMaxStatCols; i += kThreads) stat_smem[i] = 0.f;
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
@@ -240,12 +245,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;
         float* stage = epi_stage + q * kEpiStageFloats;
         const int row_limit = WGRAD ? p.K : p.M;
-        const bool out_bf16 = (p.c_dtype == DLV3P_BF16);
-        // bf16 outputs are written as packed pairs: lane -> (row parity, column pair)
-        const int half = lane >> 4, c2 = (lane & 15) * 2;
-        const bool pair_ok = out_bf16 && ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 3) == 0) &&
-                             (p.addend == nullptr || (((p.ld_add & 1) == 0) &&
-                                                      ((reinterpret_cast<uintptr_t>(p.addend) & 3) == 0)));
+        const bool use_smem_stats = (!WGRAD) && (p.col_stats != nullptr) && (p.N <= kMaxStatCols);
         uint32_t t = 0;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++t) {
             int row0, col0, kb_begin, kb_end;
@@ -254,6 +254,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(tmem_full_bar + 8 * as, (t >> 1) & 1u);
             tc_fence_after();
             const int rbase = row0 + q * 32;                   // first output row of this warp
+            const int r = rbase + lane;                        // output row owned by this lane (row-per-lane layout)
+            const bool row_ok = r < row_limit;
 #pragma unroll 1
             for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
                 const int n_base = col0 + ch * 32;
@@ -266,93 +268,120 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tmem_empty_bar + 8 * as);
                 }
-                // transpose through shared memory: row-per-lane -> column-per-lane
+                float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(raw[j]);
-                __syncwarp();
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
 
-                if (WGRAD) {
+                if (WGRAD || p.col_stats != nullptr) {
+                    // 32x33 smem transpose (row-per-lane -> column-per-lane): coalesced fp32 REDs for the filter
+                    // gradient, shuffle-free column sums for the BatchNormalization statistics
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = v[j];
+                    __syncwarp();
                     const int col = n_base + lane;
-                    if (col < p.N) {
-                        float* dst = reinterpret_cast<float*>(p.C) + (long long)rbase * p.ldc + col;
+                    if (WGRAD) {
+                        if (col < p.N) {
+                            float* dst = reinterpret_cast<float*>(p.C) + (long long)rbase * p.ldc + col;
 #pragma unroll 8
-                        for (int r = 0; r < 32; ++r)
-                            if (rbase + r < row_limit) atomicAdd(dst + (long long)r * p.ldc, stage[r * 33 + lane]);
+                            for (int rr = 0; rr < 32; ++rr)
+                                if (rbase + rr < row_limit) atomicAdd(dst + (long long)rr * p.ldc, stage[rr * 33 + lane]);
+                        }
+                    } else {
+                        float s1 = 0.f, s2 = 0.f;          // rows beyond M were zero-filled by TMA: they add nothing
+#pragma unroll 8
+                        for (int rr = 0; rr < 32; ++rr) {
+                            const float u = stage[rr * 33 + lane];
+                            s1 += u; s2 = fmaf(u, u, s2);
+                        }
+                        if (col < p.N) {
+                            if (use_smem_stats) {
+                                atomicAdd(stat_smem + col, s1);
+                                atomicAdd(stat_smem + kMaxStatCols + col, s2);
+                            } else {
+                                atomicAdd(p.col_stats + col, s1);
+                                atomicAdd(p.col_stats + p.N + col, s2);
+                            }
+                        }
                     }
-                } else if (pair_ok) {
-                    const int col = n_base + c2;
-                    const bool ok0 = col < p.N, ok1 = col + 1 < p.N;
-                    float sc0 = 1.f, sc1 = 1.f, sh0 = 0.f, sh1 = 0.f;
+                    __syncwarp();                              // stage buffer is reused by the next chunk
+                    if (WGRAD) { if (last_chunk) break; continue; }
+                }
+
+                if (row_ok) {
                     if (p.col_scale != nullptr) {
-                        if (ok0) { sc0 = __ldg(p.col_scale + col); sh0 = __ldg(p.col_shift + col); }
-                        if (ok1) { sc1 = __ldg(p.col_scale + col + 1); sh1 = __ldg(p.col_shift + col + 1); }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int n = min(n_base + j, p.N - 1);
+                            v[j] = fmaf(v[j], __ldg(p.col_scale + n), __ldg(p.col_shift + n));
+                        }
                     }
-                    float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-                    __nv_bfloat16* cbase = reinterpret_cast<__nv_bfloat16*>(p.C);
-                    const __nv_bfloat16* abase = reinterpret_cast<const __nv_bfloat16*>(p.addend);
-#pragma unroll 4
-                    for (int i = 0; i < 16; ++i) {
-                        const int r = 2 * i + half;
-                        float v0 = stage[r * 33 + c2], v1 = stage[r * 33 + c2 + 1];
-                        s1a += v0; s1b += v1; s2a = fmaf(v0, v0, s2a); s2b = fmaf(v1, v1, s2b);
-                        const int row = rbase + r;
-                        if (row < row_limit && ok0) {
-                            v0 = apply_act(fmaf(v0, sc0, sh0), p.act);
-                            v1 = apply_act(fmaf(v1, sc1, sh1), p.act);
-                            const long long off = (long long)row * p.ldc + col;
-                            if (ok1) {
-                                if (abase != nullptr) {
-                                    const __nv_bfloat162 a2 =
-                                        *reinterpret_cast<const __nv_bfloat162*>(abase + (long long)row * p.ld_add + col);
-                                    v0 += __low2float(a2); v1 += __high2float(a2);
+                    if (p.act != DLV3P_ACT_NONE) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+                    }
+                    const bool full = (n_base + 32 <= p.N);
+                    if (p.c_dtype == DLV3P_BF16) {
+                        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)r * p.ldc + n_base;
+                        const __nv_bfloat16* add =
+                            p.addend ? reinterpret_cast<const __nv_bfloat16*>(p.addend) + (long long)r * p.ld_add + n_base : nullptr;
+                        const bool vec = full && ((p.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                                         (add == nullptr || (((p.ld_add & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.addend) & 15) == 0)));
+                        if (vec) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                float f[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) f[j] = v[g * 8 + j];
+                                if (add != nullptr) {
+                                    Vec8<__nv_bfloat16> a8; a8.load(add + g * 8);
+                                    float af[8]; a8.to_float(af);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) f[j] += af[j];
                                 }
-                                *reinterpret_cast<__nv_bfloat162*>(cbase + off) = __floats2bfloat162_rn(v0, v1);
-                            } else {
-                                if (abase != nullptr) v0 += __bfloat162float(abase[(long long)row * p.ld_add + col]);
-                                cbase[off] = __float2bfloat16_rn(v0);
+                                Vec8<__nv_bfloat16> o; o.from_float(f);
+                                o.store(dst + g * 8);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                if (n_base + j < p.N) {
+                                    float f = v[j];
+                                    if (add != nullptr) f += __bfloat162float(add[j]);
+                                    dst[j] = __float2bfloat16_rn(f);
+                                }
                             }
                         }
-                    }
-                    if (p.col_stats != nullptr) {
-                        s1a += __shfl_xor_sync(0xffffffffu, s1a, 16); s1b += __shfl_xor_sync(0xffffffffu, s1b, 16);
-                        s2a += __shfl_xor_sync(0xffffffffu, s2a, 16); s2b += __shfl_xor_sync(0xffffffffu, s2b, 16);
-                        if (half == 0) {
-                            if (ok0) { atomicAdd(p.col_stats + col, s1a); atomicAdd(p.col_stats + p.N + col, s2a); }
-                            if (ok1) { atomicAdd(p.col_stats + col + 1, s1b); atomicAdd(p.col_stats + p.N + col + 1, s2b); }
+                    } else {
+                        float* dst = reinterpret_cast<float*>(p.C) + (long long)r * p.ldc + n_base;
+                        const float* add = p.addend ? reinterpret_cast<const float*>(p.addend) + (long long)r * p.ld_add + n_base : nullptr;
+                        const bool vec = full && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (add != nullptr && n_base + j < p.N) v[j] += add[j];
+                        if (vec) {
+#pragma unroll
+                            for (int g = 0; g < 8; ++g)
+                                reinterpret_cast<float4*>(dst)[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (n_base + j < p.N) dst[j] = v[j];
                         }
-                    }
-                } else {
-                    // one column per lane: fp32 outputs (logits) and odd leading dimensions
-                    const int col = n_base + lane;
-                    const bool ok = col < p.N;
-                    float sc = 1.f, sh = 0.f;
-                    if (ok && p.col_scale != nullptr) { sc = __ldg(p.col_scale + col); sh = __ldg(p.col_shift + col); }
-                    float s1 = 0.f, s2 = 0.f;
-#pragma unroll 4
-                    for (int r = 0; r < 32; ++r) {
-                        float v = stage[r * 33 + lane];
-                        s1 += v; s2 = fmaf(v, v, s2);
-                        const int row = rbase + r;
-                        if (ok && row < row_limit) {
-                            v = apply_act(fmaf(v, sc, sh), p.act);
-                            if (out_bf16) {
-                                if (p.addend != nullptr)
-                                    v += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.addend)[(long long)row * p.ld_add + col]);
-                                reinterpret_cast<__nv_bfloat16*>(p.C)[(long long)row * p.ldc + col] = __float2bfloat16_rn(v);
-                            } else {
-                                if (p.addend != nullptr)
-                                    v += reinterpret_cast<const float*>(p.addend)[(long long)row * p.ld_add + col];
-                                reinterpret_cast<float*>(p.C)[(long long)row * p.ldc + col] = v;
-                            }
-                        }
-                    }
-                    if (ok && p.col_stats != nullptr) {
-                        atomicAdd(p.col_stats + col, s1);
-                        atomicAdd(p.col_stats + p.N + col, s2);
                     }
                 }
-                __syncwarp();                                  // stage buffer is reused by the next chunk
                 if (last_chunk) break;
+            }
+        }
+        if (use_smem_stats) {
+            // one flush per CTA: contended global atomics cost ~35 ns per cache line (serialised at L2)
+            asm volatile("bar.sync 1, 128;" ::: "memory");    // the four epilogue warps only
+            const int e = threadIdx.x - 64;
+            for (int c = e; c < p.N; c += 128) {
+                const float a1 = stat_smem[c], a2 = stat_smem[kMaxStatCols + c];
+                if (a1 != 0.f || a2 != 0.f) {
+                    atomicAdd(p.col_stats + c, a1);
+                    atomicAdd(p.col_stats + p.N + c, a2);
+                }
             }
         }
     }
@@ -398,7 +427,7 @@ static int make_tmap(CUtensorMap* map, const void* base, long long d0, long long
 template <int BLOCK_N, bool WGRAD>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
     constexpr int smem = kStages * (kBlockM * kBlockK * 2 + BLOCK_N * kBlockK * 2) + 4 * kEpiStageFloats * 4 +
-                         1024 /*align*/ + 256 /*barriers*/;
+                         2 * kMaxStatCols * 4 + 1024 /*align*/ + 256 /*barriers*/;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
