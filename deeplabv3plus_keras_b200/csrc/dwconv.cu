@@ -15,6 +15,12 @@
 
 namespace dlv3p {
 
+// dwconv_tma.cu: TMA halo-staged kernel for the dense-tap bf16 case; returns 1 if it took the launch
+int launch_dw_conv_tma(const __nv_bfloat16* in, const float* w, __nv_bfloat16* out, int N, int Hin, int Win, int C,
+                       int Hout, int Wout, int pad_t, int pad_l, int flip, int in_act, const __nv_bfloat16* mask_src,
+                       const float* m_scale, const float* m_shift, int m_act, const __nv_bfloat16* addend,
+                       cudaStream_t st);
+
 template <typename T, int TW, bool DENSE_W, bool HAS_AFFINE, bool HAS_EPI>
 __global__ void __launch_bounds__(256)
 dw_conv_kernel(const T* __restrict__ in, const float* __restrict__ w, T* __restrict__ out, int N, int Hin, int Win,
@@ -430,6 +436,11 @@ extern "C" int dlv3p_dwconv3x3_fwd(const void* x, const float* w, void* y, int N
     DLV3P_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), DLV3P_ERR_SHAPE,
                   "dwconv3x3_fwd: in_scale and in_shift must both be given or both be NULL");
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == DLV3P_BF16 && stride == 1 && dil_h == 1 && dil_w == 1 && in_scale == nullptr) {
+        rc = launch_dw_conv_tma((const __nv_bfloat16*)x, w, (__nv_bfloat16*)y, N, H, W, C, Ho, Wo, pad_t, pad_l, 0,
+                                in_act, nullptr, nullptr, nullptr, 0, nullptr, st);
+        if (rc != 0) return rc < 0 ? rc : 0;
+    }
     DLV3P_DISPATCH_DTYPE(dtype, T, {
         if (in_scale)
             return launch_dw_conv<T, true, false>((const T*)x, w, (T*)y, N, H, W, C, Ho, Wo, stride, dil_h, dil_w,
@@ -451,6 +462,12 @@ extern "C" int dlv3p_dwconv3x3_dgrad(const void* dy, const float* w, void* dx, i
     DLV3P_REQUIRE(in_act == DLV3P_ACT_NONE || x_pre != nullptr, DLV3P_ERR_SHAPE,
                   "dwconv3x3_dgrad: x_pre required when in_act != NONE");
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == DLV3P_BF16 && stride == 1 && dil_h == 1 && dil_w == 1) {
+        rc = launch_dw_conv_tma((const __nv_bfloat16*)dy, w, (__nv_bfloat16*)dx, N, Ho, Wo, C, H, W, 2 - pad_t, 2 - pad_l,
+                                1, DLV3P_ACT_NONE, (const __nv_bfloat16*)x_pre, in_scale, in_shift, in_act,
+                                (const __nv_bfloat16*)addend, st);
+        if (rc != 0) return rc < 0 ? rc : 0;
+    }
     DLV3P_DISPATCH_DTYPE(dtype, T, {
         if (stride == 1) {
             // conv-transpose of a stride-1 conv = conv with flipped taps and complementary padding

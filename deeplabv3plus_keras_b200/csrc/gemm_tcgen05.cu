@@ -19,12 +19,7 @@
 // dW = X^T dY contracts over the pixel axis, which is NOT contiguous in NHWC: both operands are fed MN-major
 // (64-element x 64-row TMA boxes, same 128B swizzle) so no transposed copy of the activations is ever written;
 // its work list is (pixel-range split) x (tile), split-major so that concurrently running CTAs share operands in L2.
-#include <cuda.h>
-#include <cudaTypedefs.h>
-
-#include <mutex>
-
-#include "common.cuh"
+#include "tma.cuh"
 
 namespace dlv3p {
 
@@ -46,34 +41,6 @@ struct GemmParams {
     int n_tiles, m_tiles;              // output tile grid
 };
 
-// ---- PTX wrappers ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -394,36 +361,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---- host side --------------------------------------------------------------------------------------------------
-static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
-    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
-    });
-    return fn;
-}
-
-// 2D bf16 tensor map: inner extent d0 (contiguous), outer extent d1 with row pitch ld elements
-static int make_tmap(CUtensorMap* map, const void* base, long long d0, long long d1, long long ld, int box0, int box1) {
-    auto fn = get_encode_fn();
-    DLV3P_REQUIRE(fn != nullptr, DLV3P_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
-    cuuint64_t dims[2] = {(cuuint64_t)d0, (cuuint64_t)d1};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    DLV3P_REQUIRE(rc == CUDA_SUCCESS, DLV3P_ERR_CUDA,
-                  "cuTensorMapEncodeTiled failed (%d) dims=(%lld,%lld) ld=%lld box=(%d,%d)", (int)rc, d0, d1, ld, box0,
-                  box1);
-    return 0;
-}
-
 template <int BLOCK_N, bool WGRAD>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
     constexpr int smem = kStages * (kBlockM * kBlockK * 2 + BLOCK_N * kBlockK * 2) + 4 * kEpiStageFloats * 4 +
