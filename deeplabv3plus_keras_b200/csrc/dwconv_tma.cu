@@ -3,22 +3,24 @@
 // The entry-flow depthwise convolutions ([16,254,254,128] etc.) are the HBM-bound launches that decide K1's share
 // of the step.  Design:
 //   * persistent CTAs walk output tiles of TH x TW pixels x 64 channels; one elected thread issues ONE 4D TMA box
-//     {64 ch, TW+2, TH+2, 1} per tile into a double-buffered shared-memory stage (mbarrier expect_tx) — rows/cols
-//     outside the image are zero-filled by TMA, which IS the convolution's zero padding (TF SAME or VALID);
-//   * 256 threads = 8 channel-octets x 32 columns; each thread slides a 3-row register window down the TH rows of
-//     its column: 3 LDS.128 + 1 STG.128 per output (the direct kernel issues 4.5-9 global loads per output), the
-//     bf16->fp32 conversion and the fused pre-activation are done once per loaded element, and the 72 MACs per
-//     output run as 36 packed FFMA2 (fma.rn.f32x2, sm_100);
-//   * the next tile's TMA is in flight while the current one is computed.
+//     {64 ch, TW+2, TH+2, 1} per tile into a 4-deep shared-memory ring (mbarrier expect_tx) — rows/cols outside the
+//     image are zero-filled by TMA, which IS the convolution's zero padding (TF SAME or VALID);
+//   * 512 threads = 16 channel-quads x 32 columns; each thread slides a 3-row register window down the TH rows of
+//     its column: 3 LDS.64 + 1 STG.64 per output (the direct kernel issues 4.5-9 global loads per output); the
+//     fused pre-activation runs on packed bf16x2 (HMNMX2) BEFORE the bf16->fp32 widening, and the 36 MACs per
+//     4-channel output run as 18 packed FFMA2 (fma.rn.f32x2, sm_100).  4 channels per thread keeps the kernel at
+//     <= 128 registers so that 16 warps are resident: the kernel is issue-bound, not latency-bound (measured);
+//   * the TMA boxes of the next three tiles are in flight while the current one is computed.
 // The same kernel serves the input gradient (flipped taps, complementary padding, activation-derivative mask and
-// gradient-accumulation addend in the epilogue).
+// gradient-accumulation addend in the epilogue, whose operands are prefetched into L2 one tile ahead).
 #include "tma.cuh"
 
 namespace dlv3p {
 
 constexpr int kDwTH = 8, kDwTW = 32, kDwCB = 64;
 constexpr int kDwStageBytes = (kDwTH + 2) * (kDwTW + 2) * kDwCB * 2;      // 43,520 B
-constexpr int kDwThreads = 256;
+constexpr int kDwThreads = 512;
+constexpr int kDwStages = 4;          // 4 x 43.5 KB boxes in flight per SM
 
 struct DwTmaParams {
     int N, Hin, Win, C, Hout, Wout, pad_t, pad_l, flip, in_act;
@@ -30,109 +32,135 @@ struct DwTmaParams {
     long long num_tiles;
 };
 
-__device__ __forceinline__ void bf16x8_to_f32x2(const uint4& raw, float2 (&f)[4]) {
-    const uint32_t u[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        f[i].x = __uint_as_float(u[i] << 16);
-        f[i].y = __uint_as_float(u[i] & 0xffff0000u);
+// 4 bf16 (uint2) -> optional packed ReLU/ReLU6 -> two float2
+__device__ __forceinline__ void widen4(uint2 raw, int act, float2 (&f)[2]) {
+    if (act != DLV3P_ACT_NONE) {
+        __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&raw.x);
+        __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&raw.y);
+        const __nv_bfloat162 zero = __float2bfloat162_rn(0.f);
+        a = __hmax2(a, zero); b = __hmax2(b, zero);
+        if (act == DLV3P_ACT_RELU6) {
+            const __nv_bfloat162 six = __float2bfloat162_rn(6.f);
+            a = __hmin2(a, six); b = __hmin2(b, six);
+        }
+        raw.x = *reinterpret_cast<uint32_t*>(&a);
+        raw.y = *reinterpret_cast<uint32_t*>(&b);
     }
+    f[0].x = __uint_as_float(raw.x << 16); f[0].y = __uint_as_float(raw.x & 0xffff0000u);
+    f[1].x = __uint_as_float(raw.y << 16); f[1].y = __uint_as_float(raw.y & 0xffff0000u);
+}
+
+__device__ __forceinline__ void decode_tile(const DwTmaParams& p, long long tile, int& n, int& th, int& tw, int& cb) {
+    // channel block fastest so that neighbouring CTAs stream the same pixels
+    cb = (int)(tile % p.tiles_c); long long t = tile / p.tiles_c;
+    tw = (int)(t % p.tiles_w); t /= p.tiles_w;
+    th = (int)(t % p.tiles_h);
+    n = (int)(t / p.tiles_h);
 }
 
 __global__ void __launch_bounds__(kDwThreads, 1)
 dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTmaParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kDwStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDwStages * kDwStageBytes);
     const uint32_t bar0 = smem_u32(bars);
     const uint32_t stage0 = smem_u32(smem);
 
     const int tid = threadIdx.x;
-    const int cv = tid & 7;                 // channel octet inside the 64-channel block
-    const int col = tid >> 3;               // output column inside the tile, 0..31
+    const int cq = tid & 15;                // channel quad inside the 64-channel block
+    const int col = tid >> 4;               // output column inside the tile, 0..31
 
     if (tid == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_in)) : "memory");
-        mbar_init(bar0, 1);
-        mbar_init(bar0 + 8, 1);
+        for (int s = 0; s < kDwStages; ++s) mbar_init(bar0 + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     auto issue = [&](long long tile, int s) {
-        // tile -> (n, th, tw, cb), channel block fastest so that neighbouring CTAs stream the same pixels
-        const int cb = (int)(tile % p.tiles_c); long long t = tile / p.tiles_c;
-        const int tw = (int)(t % p.tiles_w); t /= p.tiles_w;
-        const int th = (int)(t % p.tiles_h);
-        const int n = (int)(t / p.tiles_h);
+        int n, th, tw, cb;
+        decode_tile(p, tile, n, th, tw, cb);
         mbar_expect_tx(bar0 + 8 * s, kDwStageBytes);
         tma_load_4d(stage0 + s * kDwStageBytes, &tm_in, bar0 + 8 * s, cb * kDwCB, tw * kDwTW - p.pad_l,
                     th * kDwTH - p.pad_t, n);
     };
 
     long long tile = blockIdx.x;
-    if (tile < p.num_tiles && tid == 0) issue(tile, 0);
+    if (tid == 0) {
+        for (int a = 0; a < kDwStages - 1; ++a)
+            if (tile + (long long)a * gridDim.x < p.num_tiles) issue(tile + (long long)a * gridDim.x, a);
+    }
 
     uint32_t it = 0;
     for (; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const int s = it & 1;
-        const long long next = tile + gridDim.x;
-        if (next < p.num_tiles && tid == 0) issue(next, s ^ 1);      // stage s^1 was released by the barrier below
+        const int s = it % kDwStages;
+        // refill the stage released by the barrier at the end of the previous iteration, kDwStages-1 tiles ahead
+        const long long ahead = tile + (long long)(kDwStages - 1) * gridDim.x;
+        if (ahead < p.num_tiles && tid == 0) issue(ahead, (it + kDwStages - 1) % kDwStages);
 
-        const int cb = (int)(tile % p.tiles_c); long long t = tile / p.tiles_c;
-        const int tw = (int)(t % p.tiles_w); t /= p.tiles_w;
-        const int th = (int)(t % p.tiles_h);
-        const int n = (int)(t / p.tiles_h);
-        const int c0 = cb * kDwCB + cv * 8;
+        int n, th, tw, cb;
+        decode_tile(p, tile, n, th, tw, cb);
+        const int c0 = cb * kDwCB + cq * 4;
         const int wo = tw * kDwTW + col;
         const bool lane_ok = (c0 < p.C) && (wo < p.Wout);
 
-        // filter taps of this thread's 8 channels as packed pairs (flipped for the input gradient)
-        float2 wgt[9][4];
+        // filter taps of this thread's 4 channels as packed pairs (flipped for the input gradient)
+        float2 wgt[9][2];
         if (lane_ok) {
 #pragma unroll
             for (int a = 0; a < 9; ++a) {
                 const int tap = p.flip ? (8 - a) : a;
-                const float4 lo = __ldg(reinterpret_cast<const float4*>(p.w + tap * p.C + c0));
-                const float4 hi = __ldg(reinterpret_cast<const float4*>(p.w + tap * p.C + c0) + 1);
-                wgt[a][0] = make_float2(lo.x, lo.y); wgt[a][1] = make_float2(lo.z, lo.w);
-                wgt[a][2] = make_float2(hi.x, hi.y); wgt[a][3] = make_float2(hi.z, hi.w);
+                const float4 v = __ldg(reinterpret_cast<const float4*>(p.w + tap * p.C + c0));
+                wgt[a][0] = make_float2(v.x, v.y); wgt[a][1] = make_float2(v.z, v.w);
             }
         }
 
-        mbar_wait(bar0 + 8 * s, (it >> 1) & 1u);
-
-        if (lane_ok) {
-            const uint8_t* tile_smem = smem + s * kDwStageBytes;
-            // smem tile layout: [row 0..TH+1][col 0..TW+1][64 ch] bf16
-            auto load_row = [&](int row, float2 (&dst)[3][4]) {
+        // the epilogue operands (activation-mask source, gradient addend) are read straight from global memory:
+        // pull the NEXT tile's lines into L2 now so those loads do not pay HBM latency inside the row loop
+        if (cq == 0 && (p.mask_src != nullptr || p.addend != nullptr)) {
+            const long long nt = tile + gridDim.x;
+            if (nt < p.num_tiles) {
+                int n2, th2, tw2, cb2;
+                decode_tile(p, nt, n2, th2, tw2, cb2);
+                const int wo2 = tw2 * kDwTW + col;
+                if (wo2 < p.Wout) {
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const uint4 raw = *reinterpret_cast<const uint4*>(
-                        tile_smem + ((row * (kDwTW + 2) + col + j) * kDwCB + cv * 8) * 2);
-                    bf16x8_to_f32x2(raw, dst[j]);
-                    if (p.in_act != DLV3P_ACT_NONE) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            dst[j][k].x = apply_act(dst[j][k].x, p.in_act);
-                            dst[j][k].y = apply_act(dst[j][k].y, p.in_act);
+                    for (int r = 0; r < kDwTH; ++r) {
+                        const int ho2 = th2 * kDwTH + r;
+                        if (ho2 < p.Hout) {
+                            const long long o2 = (((long long)n2 * p.Hout + ho2) * p.Wout + wo2) * p.C + cb2 * kDwCB;
+                            if (p.mask_src != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.mask_src + o2));
+                            if (p.addend != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.addend + o2));
                         }
                     }
                 }
+            }
+        }
+
+        mbar_wait(bar0 + 8 * s, (it / kDwStages) & 1u);
+
+        if (lane_ok) {
+            // smem tile layout: [row 0..TH+1][col 0..TW+1][64 ch] bf16; this thread's 3 input columns start here
+            const uint8_t* base = smem + s * kDwStageBytes + (col * kDwCB + cq * 4) * 2;
+            auto load_row = [&](int row, float2 (&dst)[3][2]) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const uint2 raw = *reinterpret_cast<const uint2*>(base + (row * (kDwTW + 2) + j) * (kDwCB * 2));
+                    widen4(raw, p.in_act, dst[j]);
+                }
             };
-            float2 r0[3][4], r1[3][4], r2[3][4];
+            float2 r0[3][2], r1[3][2], r2[3][2];
             load_row(0, r0);
             load_row(1, r1);
 #pragma unroll
             for (int r = 0; r < kDwTH; ++r) {
                 load_row(r + 2, r2);
-                float2 acc[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) acc[k] = make_float2(0.f, 0.f);
+                float2 acc[2];
+                acc[0] = make_float2(0.f, 0.f); acc[1] = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
+                    for (int k = 0; k < 2; ++k) {
                         acc[k] = __ffma2_rn(r0[j][k], wgt[0 * 3 + j][k], acc[k]);
                         acc[k] = __ffma2_rn(r1[j][k], wgt[1 * 3 + j][k], acc[k]);
                         acc[k] = __ffma2_rn(r2[j][k], wgt[2 * 3 + j][k], acc[k]);
@@ -141,32 +169,34 @@ dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTmaParams 
                 const int ho = th * kDwTH + r;
                 if (ho < p.Hout) {
                     const long long off = (((long long)n * p.Hout + ho) * p.Wout + wo) * p.C + c0;
-                    float f[8];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) { f[2 * k] = acc[k].x; f[2 * k + 1] = acc[k].y; }
+                    float f[4] = {acc[0].x, acc[0].y, acc[1].x, acc[1].y};
                     if (p.mask_src != nullptr && p.m_act != DLV3P_ACT_NONE) {
-                        Vec8<__nv_bfloat16> mv; mv.load(p.mask_src + off);
-                        float mf[8]; mv.to_float(mf);
+                        const uint2 mraw = __ldg(reinterpret_cast<const uint2*>(p.mask_src + off));
+                        float2 mf[2];
+                        widen4(mraw, DLV3P_ACT_NONE, mf);
+                        float u[4] = {mf[0].x, mf[0].y, mf[1].x, mf[1].y};
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            float u = mf[k];
-                            if (p.m_scale != nullptr) u = fmaf(u, __ldg(p.m_scale + c0 + k), __ldg(p.m_shift + c0 + k));
-                            f[k] *= act_mask(u, p.m_act);
+                        for (int k = 0; k < 4; ++k) {
+                            if (p.m_scale != nullptr) u[k] = fmaf(u[k], __ldg(p.m_scale + c0 + k), __ldg(p.m_shift + c0 + k));
+                            f[k] *= act_mask(u[k], p.m_act);
                         }
                     }
                     if (p.addend != nullptr) {
-                        Vec8<__nv_bfloat16> av; av.load(p.addend + off);
-                        float af[8]; av.to_float(af);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) f[k] += af[k];
+                        const uint2 araw = __ldg(reinterpret_cast<const uint2*>(p.addend + off));
+                        float2 af[2];
+                        widen4(araw, DLV3P_ACT_NONE, af);
+                        f[0] += af[0].x; f[1] += af[0].y; f[2] += af[1].x; f[3] += af[1].y;
                     }
-                    Vec8<__nv_bfloat16> o; o.from_float(f);
-                    o.store(p.out + off);
+                    uint2 o;
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(f[0], f[1]), hi = __floats2bfloat162_rn(f[2], f[3]);
+                    o.x = *reinterpret_cast<uint32_t*>(&lo);
+                    o.y = *reinterpret_cast<uint32_t*>(&hi);
+                    *reinterpret_cast<uint2*>(p.out + off) = o;
                 }
 #pragma unroll
                 for (int j = 0; j < 3; ++j)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) { r0[j][k] = r1[j][k]; r1[j][k] = r2[j][k]; }
+                    for (int k = 0; k < 2; ++k) { r0[j][k] = r1[j][k]; r1[j][k] = r2[j][k]; }
             }
         }
         __syncthreads();                     // everyone is done reading stage s: it may be refilled next iteration
@@ -188,19 +218,14 @@ int launch_dw_conv_tma(const __nv_bfloat16* in, const float* w, __nv_bfloat16* o
     p.m_shift = m_shift; p.m_act = m_act; p.addend = addend;
     p.tiles_h = cdiv(Hout, kDwTH); p.tiles_w = cdiv(Wout, kDwTW); p.tiles_c = cdiv(C, kDwCB);
     p.num_tiles = (long long)N * p.tiles_h * p.tiles_w * p.tiles_c;
-    constexpr int smem = 2 * kDwStageBytes + 128 + 64;
+    constexpr int smem = kDwStages * kDwStageBytes + 128 + 64;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(dw_conv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         DLV3P_REQUIRE(e == cudaSuccess, DLV3P_ERR_CUDA, "cudaFuncSetAttribute(dw tma smem=%d): %s", smem, cudaGetErrorString(e));
         configured = true;
     }
-    static int ctas_per_sm = 0;
-    if (ctas_per_sm == 0) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, dw_conv_tma_kernel, kDwThreads, smem);
-        if (ctas_per_sm < 1) ctas_per_sm = 1;
-    }
-    const long long resident = (long long)kNumSMs * ctas_per_sm;      // persistent: exactly one wave
+    const long long resident = kNumSMs;                               // persistent: one CTA per SM
     long long grid = p.num_tiles < resident ? p.num_tiles : resident;
     dw_conv_tma_kernel<<<(int)grid, kDwThreads, smem, st>>>(tm, p);
     rc = check_launch("dwconv3x3 (tma)");
