@@ -29,7 +29,7 @@ struct DwTmaParams {
     const __nv_bfloat16* mask_src; const float* m_scale; const float* m_shift; int m_act;
     const __nv_bfloat16* addend;
     int tiles_h, tiles_w, tiles_c;
-    long long num_tiles;
+    int num_tiles;
 };
 
 // 4 bf16 (uint2) -> optional packed ReLU/ReLU6 -> two float2
@@ -50,12 +50,13 @@ __device__ __forceinline__ void widen4(uint2 raw, int act, float2 (&f)[2]) {
     f[1].x = __uint_as_float(raw.y << 16); f[1].y = __uint_as_float(raw.y & 0xffff0000u);
 }
 
-__device__ __forceinline__ void decode_tile(const DwTmaParams& p, long long tile, int& n, int& th, int& tw, int& cb) {
-    // channel block fastest so that neighbouring CTAs stream the same pixels
-    cb = (int)(tile % p.tiles_c); long long t = tile / p.tiles_c;
-    tw = (int)(t % p.tiles_w); t /= p.tiles_w;
-    th = (int)(t % p.tiles_h);
-    n = (int)(t / p.tiles_h);
+__device__ __forceinline__ void decode_tile(const DwTmaParams& p, int tile, int& n, int& th, int& tw, int& cb) {
+    // channel block slowest: a CTA's consecutive tiles (stride gridDim.x) keep their filter taps in registers;
+    // different channel blocks touch disjoint bytes, so this costs no L2 locality
+    tw = tile % p.tiles_w; int t = tile / p.tiles_w;
+    th = t % p.tiles_h; t /= p.tiles_h;
+    n = t % p.N;
+    cb = t / p.N;
 }
 
 __global__ void __launch_bounds__(kDwThreads, 1)
@@ -77,7 +78,7 @@ dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTmaParams 
     }
     __syncthreads();
 
-    auto issue = [&](long long tile, int s) {
+    auto issue = [&](int tile, int s) {
         int n, th, tw, cb;
         decode_tile(p, tile, n, th, tw, cb);
         mbar_expect_tx(bar0 + 8 * s, kDwStageBytes);
@@ -85,17 +86,20 @@ dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTmaParams 
                     th * kDwTH - p.pad_t, n);
     };
 
-    long long tile = blockIdx.x;
+    int tile = blockIdx.x;
+    const int gstride = gridDim.x;
     if (tid == 0) {
         for (int a = 0; a < kDwStages - 1; ++a)
-            if (tile + (long long)a * gridDim.x < p.num_tiles) issue(tile + (long long)a * gridDim.x, a);
+            if (tile + a * gstride < p.num_tiles) issue(tile + a * gstride, a);
     }
 
+    float2 wgt[9][2];
+    int wgt_c0 = -1;
     uint32_t it = 0;
-    for (; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (; tile < p.num_tiles; tile += gstride, ++it) {
         const int s = it % kDwStages;
         // refill the stage released by the barrier at the end of the previous iteration, kDwStages-1 tiles ahead
-        const long long ahead = tile + (long long)(kDwStages - 1) * gridDim.x;
+        const int ahead = tile + (kDwStages - 1) * gstride;
         if (ahead < p.num_tiles && tid == 0) issue(ahead, (it + kDwStages - 1) % kDwStages);
 
         int n, th, tw, cb;
@@ -105,8 +109,8 @@ dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTmaParams 
         const bool lane_ok = (c0 < p.C) && (wo < p.Wout);
 
         // filter taps of this thread's 4 channels as packed pairs (flipped for the input gradient)
-        float2 wgt[9][2];
-        if (lane_ok) {
+        if (c0 < p.C && c0 != wgt_c0) {
+            wgt_c0 = c0;
 #pragma unroll
             for (int a = 0; a < 9; ++a) {
                 const int tap = p.flip ? (8 - a) : a;
@@ -118,7 +122,7 @@ dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTmaParams 
         // the epilogue operands (activation-mask source, gradient addend) are read straight from global memory:
         // pull the NEXT tile's lines into L2 now so those loads do not pay HBM latency inside the row loop
         if (cq == 0 && (p.mask_src != nullptr || p.addend != nullptr)) {
-            const long long nt = tile + gridDim.x;
+            const int nt = tile + gstride;
             if (nt < p.num_tiles) {
                 int n2, th2, tw2, cb2;
                 decode_tile(p, nt, n2, th2, tw2, cb2);
@@ -141,45 +145,49 @@ dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTmaParams 
 
         if (lane_ok) {
             // smem tile layout: [row 0..TH+1][col 0..TW+1][64 ch] bf16; this thread's 3 input columns start here
-            const uint8_t* base = smem + s * kDwStageBytes + (col * kDwCB + cq * 4) * 2;
+            const uint32_t base = stage0 + s * kDwStageBytes + (col * kDwCB + cq * 4) * 2;
+            const int in_act = p.in_act;
             auto load_row = [&](int row, float2 (&dst)[3][2]) {
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
-                    const uint2 raw = *reinterpret_cast<const uint2*>(base + (row * (kDwTW + 2) + j) * (kDwCB * 2));
-                    widen4(raw, p.in_act, dst[j]);
+                    uint2 raw;
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];"
+                                 : "=r"(raw.x), "=r"(raw.y)
+                                 : "r"(base + (uint32_t)((row * (kDwTW + 2) + j) * (kDwCB * 2))));
+                    widen4(raw, in_act, dst[j]);
                 }
             };
-            float2 r0[3][2], r1[3][2], r2[3][2];
-            load_row(0, r0);
-            load_row(1, r1);
+            const long long row_stride = (long long)p.Wout * p.C;
+            long long off = (((long long)n * p.Hout + th * kDwTH) * p.Wout + wo) * p.C + c0;
+            const int rows_valid = min(kDwTH, p.Hout - th * kDwTH);
+            const bool has_mask = (p.mask_src != nullptr && p.m_act != DLV3P_ACT_NONE);
+            float msc[4] = {1.f, 1.f, 1.f, 1.f}, msh[4] = {0.f, 0.f, 0.f, 0.f};
+            if (has_mask && p.m_scale != nullptr) {
 #pragma unroll
-            for (int r = 0; r < kDwTH; ++r) {
-                load_row(r + 2, r2);
+                for (int k = 0; k < 4; ++k) { msc[k] = __ldg(p.m_scale + c0 + k); msh[k] = __ldg(p.m_shift + c0 + k); }
+            }
+            // one output row from the three window rows (ra above, rb centre, rc below)
+            auto emit = [&](int r, const float2 (&ra)[3][2], const float2 (&rb)[3][2], const float2 (&rc)[3][2]) {
                 float2 acc[2];
                 acc[0] = make_float2(0.f, 0.f); acc[1] = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
-                        acc[k] = __ffma2_rn(r0[j][k], wgt[0 * 3 + j][k], acc[k]);
-                        acc[k] = __ffma2_rn(r1[j][k], wgt[1 * 3 + j][k], acc[k]);
-                        acc[k] = __ffma2_rn(r2[j][k], wgt[2 * 3 + j][k], acc[k]);
+                        acc[k] = __ffma2_rn(ra[j][k], wgt[0 * 3 + j][k], acc[k]);
+                        acc[k] = __ffma2_rn(rb[j][k], wgt[1 * 3 + j][k], acc[k]);
+                        acc[k] = __ffma2_rn(rc[j][k], wgt[2 * 3 + j][k], acc[k]);
                     }
                 }
-                const int ho = th * kDwTH + r;
-                if (ho < p.Hout) {
-                    const long long off = (((long long)n * p.Hout + ho) * p.Wout + wo) * p.C + c0;
+                if (r < rows_valid) {
                     float f[4] = {acc[0].x, acc[0].y, acc[1].x, acc[1].y};
-                    if (p.mask_src != nullptr && p.m_act != DLV3P_ACT_NONE) {
+                    if (has_mask) {
                         const uint2 mraw = __ldg(reinterpret_cast<const uint2*>(p.mask_src + off));
                         float2 mf[2];
                         widen4(mraw, DLV3P_ACT_NONE, mf);
-                        float u[4] = {mf[0].x, mf[0].y, mf[1].x, mf[1].y};
+                        const float u[4] = {mf[0].x, mf[0].y, mf[1].x, mf[1].y};
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (p.m_scale != nullptr) u[k] = fmaf(u[k], __ldg(p.m_scale + c0 + k), __ldg(p.m_shift + c0 + k));
-                            f[k] *= act_mask(u[k], p.m_act);
-                        }
+                        for (int k = 0; k < 4; ++k) f[k] *= act_mask(fmaf(u[k], msc[k], msh[k]), p.m_act);
                     }
                     if (p.addend != nullptr) {
                         const uint2 araw = __ldg(reinterpret_cast<const uint2*>(p.addend + off));
@@ -193,11 +201,21 @@ dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTmaParams 
                     o.y = *reinterpret_cast<uint32_t*>(&hi);
                     *reinterpret_cast<uint2*>(p.out + off) = o;
                 }
-#pragma unroll
-                for (int j = 0; j < 3; ++j)
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) { r0[j][k] = r1[j][k]; r1[j][k] = r2[j][k]; }
-            }
+                off += row_stride;
+            };
+            // the three window rows rotate roles instead of being copied (no register moves)
+            float2 r0[3][2], r1[3][2], r2[3][2];
+            load_row(0, r0);
+            load_row(1, r1);
+            static_assert(kDwTH == 8, "row loop below is unrolled for TH = 8");
+            load_row(2, r2); emit(0, r0, r1, r2);
+            load_row(3, r0); emit(1, r1, r2, r0);
+            load_row(4, r1); emit(2, r2, r0, r1);
+            load_row(5, r2); emit(3, r0, r1, r2);
+            load_row(6, r0); emit(4, r1, r2, r0);
+            load_row(7, r1); emit(5, r2, r0, r1);
+            load_row(8, r2); emit(6, r0, r1, r2);
+            load_row(9, r0); emit(7, r1, r2, r0);
         }
         __syncthreads();                     // everyone is done reading stage s: it may be refilled next iteration
     }
@@ -217,7 +235,9 @@ int launch_dw_conv_tma(const __nv_bfloat16* in, const float* w, __nv_bfloat16* o
     p.flip = flip; p.in_act = in_act; p.w = w; p.out = out; p.mask_src = mask_src; p.m_scale = m_scale;
     p.m_shift = m_shift; p.m_act = m_act; p.addend = addend;
     p.tiles_h = cdiv(Hout, kDwTH); p.tiles_w = cdiv(Wout, kDwTW); p.tiles_c = cdiv(C, kDwCB);
-    p.num_tiles = (long long)N * p.tiles_h * p.tiles_w * p.tiles_c;
+    const long long nt = (long long)N * p.tiles_h * p.tiles_w * p.tiles_c;
+    if (nt > 0x7fffffffLL) return 0;
+    p.num_tiles = (int)nt;
     constexpr int smem = kDwStages * kDwStageBytes + 128 + 64;
     static bool configured = false;
     if (!configured) {
@@ -225,9 +245,8 @@ int launch_dw_conv_tma(const __nv_bfloat16* in, const float* w, __nv_bfloat16* o
         DLV3P_REQUIRE(e == cudaSuccess, DLV3P_ERR_CUDA, "cudaFuncSetAttribute(dw tma smem=%d): %s", smem, cudaGetErrorString(e));
         configured = true;
     }
-    const long long resident = kNumSMs;                               // persistent: one CTA per SM
-    long long grid = p.num_tiles < resident ? p.num_tiles : resident;
-    dw_conv_tma_kernel<<<(int)grid, kDwThreads, smem, st>>>(tm, p);
+    const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;   // persistent: one CTA per SM
+    dw_conv_tma_kernel<<<grid, kDwThreads, smem, st>>>(tm, p);
     rc = check_launch("dwconv3x3 (tma)");
     return rc ? rc : 1;
 }
