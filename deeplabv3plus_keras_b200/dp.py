@@ -1,0 +1,45 @@
+"""Data-parallel plumbing (new here — the reference has no multi-GPU path).
+
+The batch axis shards across ranks with no data-path collective (every image is independent through the graph and
+BatchNormalization statistics stay per replica, as in a single-GPU Keras run); the only exchange is one sum
+all-reduce of the flat fp32 gradient arena per step, cut into contiguous buckets so that NCCL can pipeline them.
+The mean over replicas (each replica's loss is the mean over its own shard) is applied as `grad_scale = 1/world`
+inside the fused Adam kernel rather than as a separate pass over the arena.
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(global_batch: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous shard [lo, hi) of the global batch owned by `rank`; requires an even split (Keras DP semantics)."""
+    if global_batch % world:
+        raise ValueError(f"global batch {global_batch} does not divide over {world} replicas")
+    per = global_batch // world
+    return rank * per, (rank + 1) * per
+
+
+def bucket_ranges(n: int, buckets: int, align: int = 8) -> List[Tuple[int, int]]:
+    """Cut [0, n) into `buckets` contiguous ranges whose boundaries are multiples of `align` elements."""
+    buckets = max(1, min(buckets, n // align if n >= align else 1))
+    step = -(-n // buckets)
+    step = -(-step // align) * align
+    out, lo = [], 0
+    while lo < n:
+        hi = min(lo + step, n)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def allreduce_gradients(g: torch.Tensor, n: int, group=None, buckets: int = 4) -> None:
+    """In-place SUM all-reduce of g[:n] over the group (asynchronous per bucket, then waited)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    works = [dist.all_reduce(g[lo:hi], op=dist.ReduceOp.SUM, group=group, async_op=True)
+             for lo, hi in bucket_ranges(n, buckets)]
+    for w in works:
+        w.wait()

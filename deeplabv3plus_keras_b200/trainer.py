@@ -13,7 +13,7 @@ from typing import List, Optional
 
 import torch
 
-from . import ops
+from . import dp, ops
 from .engine import Plan
 
 
@@ -30,6 +30,7 @@ class Trainer:
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         self.use_graph = use_graph
+        self.buckets = buckets
         self.stream = torch.cuda.Stream()
         self.comm_stream = torch.cuda.Stream() if self.world > 1 else None
         self._segments: List = []          # (graph or callable, grad-arena range completed by it)
@@ -117,7 +118,7 @@ class Trainer:
         ev.record(self.stream)
         self.comm_stream.wait_event(ev)
         with torch.cuda.stream(self.comm_stream):
-            torch.distributed.all_reduce(g[:n], group=self.pg)
+            dp.allreduce_gradients(g, n, self.pg, self.buckets)
         ev2 = torch.cuda.Event()
         ev2.record(self.comm_stream)
         self.stream.wait_event(ev2)

@@ -1,0 +1,88 @@
+"""N>1 host logic on CPU: two gloo ranks, each running the engine (through the tests/fake_ops.py test double) on its
+shard of the batch, exchange gradients with dp.allreduce_gradients; the averaged gradient must equal the mean of the
+oracle's per-shard gradients (BatchNormalization statistics stay per replica)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tests import util
+from tests.test_ops_gpu import NW, PW
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from deeplabv3plus_keras_b200 import dp, engine
+    from tests import fake_ops
+    engine.ops = fake_ops
+    conf = util.make_conf(base="mobilenetv2", image_size=65, width=32, aspp=util.DEFAULT_ASPP)
+    ss = util.build(conf)
+    util.randomize_weights(ss.model)
+    G = 4
+    lo, hi = dp.shard_bounds(G, rank, world)
+    plan = engine.Plan(ss.model, hi - lo, training=True)
+    x, y = util.synthetic_batch(conf, G, plan.out_shape[1:3])
+    plan.set_loss(PW, NW)
+    plan.load_batch(x[lo:hi], y[lo:hi])
+    plan.step_fwd_bwd()
+    n = plan.params.n_train
+    dp.allreduce_gradients(plan.params.g, n, None, buckets=3)
+    g = (plan.params.g[:n] / world).numpy().copy()
+    names = {k: v for k, v in plan.gradients().items()}
+    if rank == 0:
+        q.put((g, {k: v / world for k, v in names.items()}, x, y))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_exchange_matches_mean_of_shards():
+    from oracle import model as OM
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    g, named, x, y = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    conf = util.make_conf(base="mobilenetv2", image_size=65, width=32, aspp=util.DEFAULT_ASPP)
+    ss = util.build(conf)
+    util.randomize_weights(ss.model)
+    w = util.torch_weights(ss.model)
+    lam = conf["hps"]["weight_decay"]
+    acc = None
+    for lo, hi in ((0, 2), (2, 4)):
+        _, _, grads, _ = OM.loss_and_grads(conf, w, torch.from_numpy(x[lo:hi]).double(), torch.from_numpy(y[lo:hi]), PW, NW)
+        acc = grads if acc is None else {k: acc[k] + grads[k] for k in grads}
+    for k, v in acc.items():
+        want = (v / 2).numpy().copy()
+        if k.endswith("/kernel") and k.split("/")[0].startswith("conv2d"):
+            want -= 2 * lam * w[k].numpy()
+        scale = max(np.abs(want).max(), 1e-3)
+        err = np.abs(named[k] - want) / scale
+        assert (err > 3e-2).mean() <= 2e-3 and err.max() < 0.3, (k, float(err.max()))
+
+
+def test_bucket_ranges_cover_and_align():
+    from deeplabv3plus_keras_b200 import dp
+    for n in (8, 1000, 16_540_000):
+        for b in (1, 3, 8):
+            r = dp.bucket_ranges(n, b)
+            assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == c[0] for a, c in zip(r, r[1:]))
+            assert all(lo % 8 == 0 for lo, _ in r)
+    with pytest.raises(ValueError):
+        dp.shard_bounds(10, 0, 4)
