@@ -50,6 +50,7 @@ SIGNATURES = {
     "dlv3p_softmax_cbloss_bwd": [_p, _p, _p, _p, _f, _l, _i, _f, _p, _p],
     "dlv3p_upsample_softmax_cbloss_fwd": [_p, _p, _p, _p, _f, _i, _i, _i, _i, _i, _p, _p],
     "dlv3p_upsample_softmax_cbloss_bwd": [_p, _p, _p, _p, _f, _i, _i, _i, _i, _i, _f, _p, _p],
+    "dlv3p_upsample_softmax_cbloss_fwd_bwd": [_p, _p, _p, _p, _f, _i, _i, _i, _i, _i, _f, _p, _p, _p],
     "dlv3p_softmax_argmax": [_p, _l, _i, _p, _p, _p],
     "dlv3p_cbloss_dense_fwd": [_p, _p, _p, _p, _f, _l, _i, _p, _p],
     "dlv3p_cbloss_dense_bwd": [_p, _p, _p, _p, _f, _l, _i, _f, _p, _p],

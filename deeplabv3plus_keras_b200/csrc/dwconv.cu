@@ -21,6 +21,9 @@ int launch_dw_conv_tma(const __nv_bfloat16* in, const float* w, __nv_bfloat16* o
                        const float* m_scale, const float* m_shift, int m_act, const __nv_bfloat16* addend,
                        cudaStream_t st);
 
+int launch_dw_wgrad_tma(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int N, int H, int W, int C, int Ho,
+                        int Wo, int pad_t, int pad_l, int in_act, cudaStream_t st);
+
 template <typename T, int TW, bool DENSE_W, bool HAS_AFFINE, bool HAS_EPI>
 __global__ void __launch_bounds__(256)
 dw_conv_kernel(const T* __restrict__ in, const float* __restrict__ w, T* __restrict__ out, int N, int Hin, int Win,
@@ -494,6 +497,11 @@ extern "C" int dlv3p_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, i
     cudaStream_t st = (cudaStream_t)stream;
     const int CV = C / 8;
     const long long npix = (long long)N * Ho * Wo;
+    if (dtype == DLV3P_BF16 && stride == 1 && dil_h == 1 && dil_w == 1 && in_scale == nullptr) {
+        rc = launch_dw_wgrad_tma((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw, N, H, W, C, Ho, Wo, pad_t, pad_l,
+                                 in_act, st);
+        if (rc != 0) return rc < 0 ? rc : 0;
+    }
     DLV3P_DISPATCH_DTYPE(dtype, T, {
         if (stride == 1 && dil_w == 1) {
             const long long nstrips = (long long)N * Ho * ((Wo + 3) / 4);

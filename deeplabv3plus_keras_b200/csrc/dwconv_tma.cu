@@ -20,7 +20,6 @@ namespace dlv3p {
 constexpr int kDwTH = 8, kDwTW = 32, kDwCB = 64;
 constexpr int kDwStageBytes = (kDwTH + 2) * (kDwTW + 2) * kDwCB * 2;      // 43,520 B
 constexpr int kDwThreads = 512;
-constexpr int kDwStages = 4;          // 4 x 43.5 KB boxes in flight per SM
 
 struct DwTmaParams {
     int N, Hin, Win, C, Hout, Wout, pad_t, pad_l, flip, in_act;
@@ -29,7 +28,7 @@ struct DwTmaParams {
     const __nv_bfloat16* mask_src; const float* m_scale; const float* m_shift; int m_act;
     const __nv_bfloat16* addend;
     int tiles_h, tiles_w, tiles_c;
-    int num_tiles;
+    int spatial_tiles, ctas_per_cb;
 };
 
 // 4 bf16 (uint2) -> optional packed ReLU/ReLU6 -> two float2
@@ -50,103 +49,127 @@ __device__ __forceinline__ void widen4(uint2 raw, int act, float2 (&f)[2]) {
     f[1].x = __uint_as_float(raw.y << 16); f[1].y = __uint_as_float(raw.y & 0xffff0000u);
 }
 
-__device__ __forceinline__ void decode_tile(const DwTmaParams& p, int tile, int& n, int& th, int& tw, int& cb) {
-    // channel block slowest: a CTA's consecutive tiles (stride gridDim.x) keep their filter taps in registers;
-    // different channel blocks touch disjoint bytes, so this costs no L2 locality
-    tw = tile % p.tiles_w; int t = tile / p.tiles_w;
-    th = t % p.tiles_h; t /= p.tiles_h;
-    n = t % p.N;
-    cb = t / p.N;
+// Compile-time specialisation: the row loop is pure straight-line code (the first version branched on the activation /
+// mask / addend codes at run time and spent 14 % of its issue slots on ISETP+BRA and 2x the HMNMX2 it needed — ncu
+// source page, profiles/r1_dwfwd728_*).  IN_ACT: activation fused on load; M_ACT: activation whose derivative masks
+// the result (input gradient), 0 = none; M_AFFINE: mask argument is m_scale*x+m_shift; HAS_ADD: gradient addend.
+template <int ACT>
+__device__ __forceinline__ void widen4_t(uint2 raw, float2 (&f)[2]) {
+    if (ACT != DLV3P_ACT_NONE) {
+        __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&raw.x);
+        __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&raw.y);
+        const __nv_bfloat162 zero = __float2bfloat162_rn(0.f);
+        a = __hmax2(a, zero); b = __hmax2(b, zero);
+        if (ACT == DLV3P_ACT_RELU6) {
+            const __nv_bfloat162 six = __float2bfloat162_rn(6.f);
+            a = __hmin2(a, six); b = __hmin2(b, six);
+        }
+        raw.x = *reinterpret_cast<uint32_t*>(&a);
+        raw.y = *reinterpret_cast<uint32_t*>(&b);
+    }
+    f[0].x = __uint_as_float(raw.x << 16); f[0].y = __uint_as_float(raw.x & 0xffff0000u);
+    f[1].x = __uint_as_float(raw.y << 16); f[1].y = __uint_as_float(raw.y & 0xffff0000u);
 }
 
+// Epilogue operands (mask source, addend) arrive through their own TMA boxes {64 ch, TW, TH} in the same stage, so
+// the row loop never waits on a global load; the ring gets shallower as the stage grows (4 / 3 / 2 stages).
+template <int M_ACT, bool HAS_ADD>
+struct DwStageCfg {
+    static constexpr int kBoxes = 1 + (M_ACT != DLV3P_ACT_NONE ? 1 : 0) + (HAS_ADD ? 1 : 0);
+    static constexpr int kEpiBytes = kDwTH * kDwTW * kDwCB * 2;                    // 32,768 B
+    static constexpr int kStageBytes = kDwStageBytes + (kBoxes - 1) * kEpiBytes;
+    static constexpr int kStages = kBoxes == 1 ? 4 : (kBoxes == 2 ? 3 : 2);
+    static constexpr int kMaskOff = kDwStageBytes;
+    static constexpr int kAddOff = kDwStageBytes + (M_ACT != DLV3P_ACT_NONE ? kEpiBytes : 0);
+};
+
+template <int IN_ACT, int M_ACT, bool M_AFFINE, bool HAS_ADD>
 __global__ void __launch_bounds__(kDwThreads, 1)
-dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTmaParams p) {
+dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_mask,
+                   const __grid_constant__ CUtensorMap tm_add, const DwTmaParams p) {
+    using Cfg = DwStageCfg<M_ACT, HAS_ADD>;
+    constexpr int kDwStages = Cfg::kStages;
+    constexpr int kStageBytes = Cfg::kStageBytes;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDwStages * kDwStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDwStages * kStageBytes);
     const uint32_t bar0 = smem_u32(bars);
     const uint32_t stage0 = smem_u32(smem);
 
     const int tid = threadIdx.x;
     const int cq = tid & 15;                // channel quad inside the 64-channel block
     const int col = tid >> 4;               // output column inside the tile, 0..31
+    // every CTA owns ONE 64-channel block: its filter taps are loaded once and the tile decode needs no channel term
+    const int cb = blockIdx.x / p.ctas_per_cb;
+    const int gstride = p.ctas_per_cb;
+    const int c0 = cb * kDwCB + cq * 4;
 
     if (tid == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_in)) : "memory");
+        if (M_ACT != DLV3P_ACT_NONE) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_mask)) : "memory");
+        if (HAS_ADD) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_add)) : "memory");
         for (int s = 0; s < kDwStages; ++s) mbar_init(bar0 + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
+    auto decode = [&](int tile, int& n, int& th, int& tw) {
+        tw = tile % p.tiles_w; const int t = tile / p.tiles_w;
+        th = t % p.tiles_h; n = t / p.tiles_h;
+    };
     auto issue = [&](int tile, int s) {
-        int n, th, tw, cb;
-        decode_tile(p, tile, n, th, tw, cb);
-        mbar_expect_tx(bar0 + 8 * s, kDwStageBytes);
-        tma_load_4d(stage0 + s * kDwStageBytes, &tm_in, bar0 + 8 * s, cb * kDwCB, tw * kDwTW - p.pad_l,
-                    th * kDwTH - p.pad_t, n);
+        int n, th, tw;
+        decode(tile, n, th, tw);
+        mbar_expect_tx(bar0 + 8 * s, kStageBytes);
+        const uint32_t dst = stage0 + s * kStageBytes;
+        tma_load_4d(dst, &tm_in, bar0 + 8 * s, cb * kDwCB, tw * kDwTW - p.pad_l, th * kDwTH - p.pad_t, n);
+        if (M_ACT != DLV3P_ACT_NONE)
+            tma_load_4d(dst + Cfg::kMaskOff, &tm_mask, bar0 + 8 * s, cb * kDwCB, tw * kDwTW, th * kDwTH, n);
+        if (HAS_ADD)
+            tma_load_4d(dst + Cfg::kAddOff, &tm_add, bar0 + 8 * s, cb * kDwCB, tw * kDwTW, th * kDwTH, n);
     };
 
-    int tile = blockIdx.x;
-    const int gstride = gridDim.x;
+    int tile = blockIdx.x % p.ctas_per_cb;
     if (tid == 0) {
         for (int a = 0; a < kDwStages - 1; ++a)
-            if (tile + a * gstride < p.num_tiles) issue(tile + a * gstride, a);
+            if (tile + a * gstride < p.spatial_tiles) issue(tile + a * gstride, a);
     }
 
+    // filter taps of this thread's 4 channels as packed pairs (flipped for the input gradient)
     float2 wgt[9][2];
-    int wgt_c0 = -1;
+    float msc[4] = {1.f, 1.f, 1.f, 1.f}, msh[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool ch_ok = c0 < p.C;
+    if (ch_ok) {
+#pragma unroll
+        for (int a = 0; a < 9; ++a) {
+            const int tap = p.flip ? (8 - a) : a;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p.w + tap * p.C + c0));
+            wgt[a][0] = make_float2(v.x, v.y); wgt[a][1] = make_float2(v.z, v.w);
+        }
+        if (M_ACT != DLV3P_ACT_NONE && M_AFFINE) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { msc[k] = __ldg(p.m_scale + c0 + k); msh[k] = __ldg(p.m_shift + c0 + k); }
+        }
+    }
+    const long long row_stride = (long long)p.Wout * p.C;
+
     uint32_t it = 0;
-    for (; tile < p.num_tiles; tile += gstride, ++it) {
+    for (; tile < p.spatial_tiles; tile += gstride, ++it) {
         const int s = it % kDwStages;
         // refill the stage released by the barrier at the end of the previous iteration, kDwStages-1 tiles ahead
         const int ahead = tile + (kDwStages - 1) * gstride;
-        if (ahead < p.num_tiles && tid == 0) issue(ahead, (it + kDwStages - 1) % kDwStages);
+        if (ahead < p.spatial_tiles && tid == 0) issue(ahead, (it + kDwStages - 1) % kDwStages);
 
-        int n, th, tw, cb;
-        decode_tile(p, tile, n, th, tw, cb);
-        const int c0 = cb * kDwCB + cq * 4;
+        int n, th, tw;
+        decode(tile, n, th, tw);
         const int wo = tw * kDwTW + col;
-        const bool lane_ok = (c0 < p.C) && (wo < p.Wout);
-
-        // filter taps of this thread's 4 channels as packed pairs (flipped for the input gradient)
-        if (c0 < p.C && c0 != wgt_c0) {
-            wgt_c0 = c0;
-#pragma unroll
-            for (int a = 0; a < 9; ++a) {
-                const int tap = p.flip ? (8 - a) : a;
-                const float4 v = __ldg(reinterpret_cast<const float4*>(p.w + tap * p.C + c0));
-                wgt[a][0] = make_float2(v.x, v.y); wgt[a][1] = make_float2(v.z, v.w);
-            }
-        }
-
-        // the epilogue operands (activation-mask source, gradient addend) are read straight from global memory:
-        // pull the NEXT tile's lines into L2 now so those loads do not pay HBM latency inside the row loop
-        if (cq == 0 && (p.mask_src != nullptr || p.addend != nullptr)) {
-            const int nt = tile + gstride;
-            if (nt < p.num_tiles) {
-                int n2, th2, tw2, cb2;
-                decode_tile(p, nt, n2, th2, tw2, cb2);
-                const int wo2 = tw2 * kDwTW + col;
-                if (wo2 < p.Wout) {
-#pragma unroll
-                    for (int r = 0; r < kDwTH; ++r) {
-                        const int ho2 = th2 * kDwTH + r;
-                        if (ho2 < p.Hout) {
-                            const long long o2 = (((long long)n2 * p.Hout + ho2) * p.Wout + wo2) * p.C + cb2 * kDwCB;
-                            if (p.mask_src != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.mask_src + o2));
-                            if (p.addend != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.addend + o2));
-                        }
-                    }
-                }
-            }
-        }
+        const bool lane_ok = ch_ok && (wo < p.Wout);
 
         mbar_wait(bar0 + 8 * s, (it / kDwStages) & 1u);
 
         if (lane_ok) {
             // smem tile layout: [row 0..TH+1][col 0..TW+1][64 ch] bf16; this thread's 3 input columns start here
-            const uint32_t base = stage0 + s * kDwStageBytes + (col * kDwCB + cq * 4) * 2;
-            const int in_act = p.in_act;
+            const uint32_t base = stage0 + s * kStageBytes + (col * kDwCB + cq * 4) * 2;
             auto load_row = [&](int row, float2 (&dst)[3][2]) {
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
@@ -154,45 +177,53 @@ dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTmaParams 
                     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];"
                                  : "=r"(raw.x), "=r"(raw.y)
                                  : "r"(base + (uint32_t)((row * (kDwTW + 2) + j) * (kDwCB * 2))));
-                    widen4(raw, in_act, dst[j]);
+                    widen4_t<IN_ACT>(raw, dst[j]);
                 }
             };
-            const long long row_stride = (long long)p.Wout * p.C;
+            auto lds_epi = [&](int byte_off, int r) {
+                uint2 raw;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];"
+                             : "=r"(raw.x), "=r"(raw.y)
+                             : "r"(base + (uint32_t)(byte_off + r * kDwTW * kDwCB * 2)));
+                return raw;
+            };
             long long off = (((long long)n * p.Hout + th * kDwTH) * p.Wout + wo) * p.C + c0;
-            const int rows_valid = min(kDwTH, p.Hout - th * kDwTH);
-            const bool has_mask = (p.mask_src != nullptr && p.m_act != DLV3P_ACT_NONE);
-            float msc[4] = {1.f, 1.f, 1.f, 1.f}, msh[4] = {0.f, 0.f, 0.f, 0.f};
-            if (has_mask && p.m_scale != nullptr) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { msc[k] = __ldg(p.m_scale + c0 + k); msh[k] = __ldg(p.m_shift + c0 + k); }
-            }
-            // one output row from the three window rows (ra above, rb centre, rc below)
+            const int rows_valid = p.Hout - th * kDwTH;
+            // one output row from the three window rows (ra above, rb centre, rc below); three independent
+            // accumulation chains per channel pair (one per window row) keep the FMA pipe fed at 4 warps/scheduler
             auto emit = [&](int r, const float2 (&ra)[3][2], const float2 (&rb)[3][2], const float2 (&rc)[3][2]) {
                 float2 acc[2];
-                acc[0] = make_float2(0.f, 0.f); acc[1] = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        acc[k] = __ffma2_rn(ra[j][k], wgt[0 * 3 + j][k], acc[k]);
-                        acc[k] = __ffma2_rn(rb[j][k], wgt[1 * 3 + j][k], acc[k]);
-                        acc[k] = __ffma2_rn(rc[j][k], wgt[2 * 3 + j][k], acc[k]);
-                    }
+                for (int k = 0; k < 2; ++k) {
+                    float2 a0 = __fmul2_rn(ra[0][k], wgt[0][k]);
+                    float2 a1 = __fmul2_rn(rb[0][k], wgt[3][k]);
+                    float2 a2 = __fmul2_rn(rc[0][k], wgt[6][k]);
+                    a0 = __ffma2_rn(ra[1][k], wgt[1][k], a0);
+                    a1 = __ffma2_rn(rb[1][k], wgt[4][k], a1);
+                    a2 = __ffma2_rn(rc[1][k], wgt[7][k], a2);
+                    a0 = __ffma2_rn(ra[2][k], wgt[2][k], a0);
+                    a1 = __ffma2_rn(rb[2][k], wgt[5][k], a1);
+                    a2 = __ffma2_rn(rc[2][k], wgt[8][k], a2);
+                    acc[k] = __fadd2_rn(__fadd2_rn(a0, a1), a2);
                 }
                 if (r < rows_valid) {
                     float f[4] = {acc[0].x, acc[0].y, acc[1].x, acc[1].y};
-                    if (has_mask) {
-                        const uint2 mraw = __ldg(reinterpret_cast<const uint2*>(p.mask_src + off));
+                    if (M_ACT != DLV3P_ACT_NONE) {
+                        const uint2 mraw = lds_epi(Cfg::kMaskOff, r);
                         float2 mf[2];
-                        widen4(mraw, DLV3P_ACT_NONE, mf);
+                        widen4_t<DLV3P_ACT_NONE>(mraw, mf);
                         const float u[4] = {mf[0].x, mf[0].y, mf[1].x, mf[1].y};
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) f[k] *= act_mask(fmaf(u[k], msc[k], msh[k]), p.m_act);
+                        for (int k = 0; k < 4; ++k) {
+                            const float v = M_AFFINE ? fmaf(u[k], msc[k], msh[k]) : u[k];
+                            const bool on = (M_ACT == DLV3P_ACT_RELU) ? (v > 0.f) : (v > 0.f && v < 6.f);
+                            f[k] = on ? f[k] : 0.f;
+                        }
                     }
-                    if (p.addend != nullptr) {
-                        const uint2 araw = __ldg(reinterpret_cast<const uint2*>(p.addend + off));
+                    if (HAS_ADD) {
+                        const uint2 araw = lds_epi(Cfg::kAddOff, r);
                         float2 af[2];
-                        widen4(araw, DLV3P_ACT_NONE, af);
+                        widen4_t<DLV3P_ACT_NONE>(araw, af);
                         f[0] += af[0].x; f[1] += af[0].y; f[2] += af[1].x; f[3] += af[1].y;
                     }
                     uint2 o;
@@ -221,33 +252,233 @@ dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTmaParams 
     }
 }
 
+template <int IN_ACT, int M_ACT, bool M_AFFINE, bool HAS_ADD>
+static int launch_dw_tma_inst(const CUtensorMap& tm, const CUtensorMap& tmm, const CUtensorMap& tma,
+                              const DwTmaParams& p, int grid, cudaStream_t st) {
+    using Cfg = DwStageCfg<M_ACT, HAS_ADD>;
+    constexpr int smem = Cfg::kStages * Cfg::kStageBytes + 128 + 64;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(dw_conv_tma_kernel<IN_ACT, M_ACT, M_AFFINE, HAS_ADD>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        DLV3P_REQUIRE(e == cudaSuccess, DLV3P_ERR_CUDA, "cudaFuncSetAttribute(dw tma smem=%d): %s", smem, cudaGetErrorString(e));
+        configured = true;
+    }
+    dw_conv_tma_kernel<IN_ACT, M_ACT, M_AFFINE, HAS_ADD><<<grid, kDwThreads, smem, st>>>(tm, tmm, tma, p);
+    return check_launch("dwconv3x3 (tma)");
+}
+
 // Returns 1 if the TMA kernel took the launch, 0 if the caller must use the direct kernel, < 0 on error.
 int launch_dw_conv_tma(const __nv_bfloat16* in, const float* w, __nv_bfloat16* out, int N, int Hin, int Win, int C,
                        int Hout, int Wout, int pad_t, int pad_l, int flip, int in_act, const __nv_bfloat16* mask_src,
                        const float* m_scale, const float* m_shift, int m_act, const __nv_bfloat16* addend,
                        cudaStream_t st) {
     if (get_encode_fn() == nullptr) return 0;
-    CUtensorMap tm;
+    if (mask_src == nullptr) m_act = DLV3P_ACT_NONE;
+    if (in_act != DLV3P_ACT_NONE && (m_act != DLV3P_ACT_NONE || addend != nullptr)) return 0;   // not a used combination
+    CUtensorMap tm, tmm, tma;
     int rc = make_tmap_nhwc(&tm, in, N, Hin, Win, C, kDwCB, kDwTW + 2, kDwTH + 2);
     if (rc) return rc;
+    tmm = tm; tma = tm;                          // placeholders when the operand is absent (never dereferenced)
+    if (m_act != DLV3P_ACT_NONE) {
+        rc = make_tmap_nhwc(&tmm, mask_src, N, Hout, Wout, C, kDwCB, kDwTW, kDwTH);
+        if (rc) return rc;
+    }
+    if (addend != nullptr) {
+        rc = make_tmap_nhwc(&tma, addend, N, Hout, Wout, C, kDwCB, kDwTW, kDwTH);
+        if (rc) return rc;
+    }
     DwTmaParams p;
     p.N = N; p.Hin = Hin; p.Win = Win; p.C = C; p.Hout = Hout; p.Wout = Wout; p.pad_t = pad_t; p.pad_l = pad_l;
     p.flip = flip; p.in_act = in_act; p.w = w; p.out = out; p.mask_src = mask_src; p.m_scale = m_scale;
     p.m_shift = m_shift; p.m_act = m_act; p.addend = addend;
     p.tiles_h = cdiv(Hout, kDwTH); p.tiles_w = cdiv(Wout, kDwTW); p.tiles_c = cdiv(C, kDwCB);
-    const long long nt = (long long)N * p.tiles_h * p.tiles_w * p.tiles_c;
+    const long long nt = (long long)N * p.tiles_h * p.tiles_w;
     if (nt > 0x7fffffffLL) return 0;
-    p.num_tiles = (int)nt;
-    constexpr int smem = kDwStages * kDwStageBytes + 128 + 64;
+    p.spatial_tiles = (int)nt;
+    int per = kNumSMs / p.tiles_c; if (per < 1) per = 1;
+    if (per > p.spatial_tiles) per = p.spatial_tiles;
+    p.ctas_per_cb = per;
+    const int grid = p.tiles_c * per;
+    const bool aff = (m_scale != nullptr);
+    const bool add = (addend != nullptr);
+#define DLV3P_DW(IA, MA, AF, AD) rc = launch_dw_tma_inst<IA, MA, AF, AD>(tm, tmm, tma, p, grid, st)
+    if (m_act == DLV3P_ACT_NONE && !add) {
+        if (in_act == DLV3P_ACT_NONE) DLV3P_DW(0, 0, false, false);
+        else if (in_act == DLV3P_ACT_RELU) DLV3P_DW(1, 0, false, false);
+        else DLV3P_DW(2, 0, false, false);
+    } else if (m_act == DLV3P_ACT_NONE) {
+        DLV3P_DW(0, 0, false, true);
+    } else if (m_act == DLV3P_ACT_RELU) {
+        if (aff) { if (add) DLV3P_DW(0, 1, true, true); else DLV3P_DW(0, 1, true, false); }
+        else { if (add) DLV3P_DW(0, 1, false, true); else DLV3P_DW(0, 1, false, false); }
+    } else {
+        if (aff) { if (add) DLV3P_DW(0, 2, true, true); else DLV3P_DW(0, 2, true, false); }
+        else { if (add) DLV3P_DW(0, 2, false, true); else DLV3P_DW(0, 2, false, false); }
+    }
+#undef DLV3P_DW
+    return rc ? rc : 1;
+}
+
+// ---- filter gradient (dense taps, bf16): dw[i][j][c] += sum_{n,ho,wo} act(x[n,ho-pt+i,wo-pl+j,c]) * dy[n,ho,wo,c] ----
+// Same tiling as the forward kernel, two TMA boxes per tile (x with halo, dy without); OOB zero fill makes ragged
+// tile edges, the convolution padding and the channel tail contribute exact zeros, so no masking is needed.
+// Every CTA owns ONE 64-channel block (grid = channel blocks x CTAs per block) and keeps its 9 x 4 partial sums per
+// thread in registers across all its spatial tiles; one shared-memory reduction over the 32 columns and one fp32 RED
+// per (tap, channel) per CTA at the end.  The direct kernels (dwconv.cu) keep 16-22 independent 16-byte global loads
+// in flight per thread at <= 16 warps/SM, i.e. ~6 KB/SM — an order of magnitude short of what HBM latency needs;
+// here 2 x 76 KB of TMA boxes are in flight per SM while the third is reduced.
+constexpr int kWgDyBytes = kDwTH * kDwTW * kDwCB * 2;                     // 32,768 B
+constexpr int kWgStageBytes = kDwStageBytes + kWgDyBytes;                 // 76,288 B
+constexpr int kWgStages = 3;
+
+struct DwWgradParams {
+    int N, C, Ho, Wo, pad_t, pad_l, in_act;
+    float* dw;                              // [3,3,C] fp32, accumulated
+    int tiles_h, tiles_w, ctas_per_cb, spatial_tiles;
+};
+
+template <int IN_ACT>
+__global__ void __launch_bounds__(kDwThreads, 1)
+dw_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy,
+                    const DwWgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
+    const uint32_t bar0 = smem_u32(bars);
+    const uint32_t stage0 = smem_u32(smem);
+    const int tid = threadIdx.x;
+    const int cq = tid & 15, col = tid >> 4;
+    const int cb = blockIdx.x / p.ctas_per_cb;
+    const int first = blockIdx.x % p.ctas_per_cb;
+    const int gstride = p.ctas_per_cb;
+
+    if (tid == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_x)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_dy)) : "memory");
+        for (int s = 0; s < kWgStages; ++s) mbar_init(bar0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int tile, int s) {
+        const int tw = tile % p.tiles_w; int t = tile / p.tiles_w;
+        const int th = t % p.tiles_h; const int n = t / p.tiles_h;
+        const uint32_t dst = stage0 + s * kWgStageBytes;
+        mbar_expect_tx(bar0 + 8 * s, kWgStageBytes);
+        tma_load_4d(dst, &tm_x, bar0 + 8 * s, cb * kDwCB, tw * kDwTW - p.pad_l, th * kDwTH - p.pad_t, n);
+        tma_load_4d(dst + kDwStageBytes, &tm_dy, bar0 + 8 * s, cb * kDwCB, tw * kDwTW, th * kDwTH, n);
+    };
+    int tile = first;
+    if (tid == 0) {
+        for (int a = 0; a < kWgStages - 1; ++a)
+            if (tile + a * gstride < p.spatial_tiles) issue(tile + a * gstride, a);
+    }
+
+    float2 acc[9][2];
+#pragma unroll
+    for (int a = 0; a < 9; ++a) { acc[a][0] = make_float2(0.f, 0.f); acc[a][1] = make_float2(0.f, 0.f); }
+    uint32_t it = 0;
+    for (; tile < p.spatial_tiles; tile += gstride, ++it) {
+        const int s = it % kWgStages;
+        const int ahead = tile + (kWgStages - 1) * gstride;
+        if (ahead < p.spatial_tiles && tid == 0) issue(ahead, (it + kWgStages - 1) % kWgStages);
+        mbar_wait(bar0 + 8 * s, (it / kWgStages) & 1u);
+
+        const uint32_t xbase = stage0 + s * kWgStageBytes + (col * kDwCB + cq * 4) * 2;
+        const uint32_t gbase = stage0 + s * kWgStageBytes + kDwStageBytes + (col * kDwCB + cq * 4) * 2;
+        auto load_row = [&](int row, float2 (&dst)[3][2]) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                uint2 raw;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];"
+                             : "=r"(raw.x), "=r"(raw.y)
+                             : "r"(xbase + (uint32_t)((row * (kDwTW + 2) + j) * (kDwCB * 2))));
+                widen4_t<IN_ACT>(raw, dst[j]);
+            }
+        };
+        auto accum = [&](int r, const float2 (&ra)[3][2], const float2 (&rb)[3][2], const float2 (&rc)[3][2]) {
+            uint2 raw;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];"
+                         : "=r"(raw.x), "=r"(raw.y) : "r"(gbase + (uint32_t)(r * kDwTW * kDwCB * 2)));
+            float2 g[2];
+            widen4_t<DLV3P_ACT_NONE>(raw, g);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    acc[0 * 3 + j][k] = __ffma2_rn(ra[j][k], g[k], acc[0 * 3 + j][k]);
+                    acc[1 * 3 + j][k] = __ffma2_rn(rb[j][k], g[k], acc[1 * 3 + j][k]);
+                    acc[2 * 3 + j][k] = __ffma2_rn(rc[j][k], g[k], acc[2 * 3 + j][k]);
+                }
+            }
+        };
+        float2 r0[3][2], r1[3][2], r2[3][2];
+        load_row(0, r0);
+        load_row(1, r1);
+        static_assert(kDwTH == 8, "row loop below is unrolled for TH = 8");
+        load_row(2, r2); accum(0, r0, r1, r2);
+        load_row(3, r0); accum(1, r1, r2, r0);
+        load_row(4, r1); accum(2, r2, r0, r1);
+        load_row(5, r2); accum(3, r0, r1, r2);
+        load_row(6, r0); accum(4, r1, r2, r0);
+        load_row(7, r1); accum(5, r2, r0, r1);
+        load_row(8, r2); accum(6, r0, r1, r2);
+        load_row(9, r0); accum(7, r1, r2, r0);
+        __syncthreads();
+    }
+    // every TMA box this CTA issued has been consumed: reuse stage 0 as the reduction buffer [9][32 cols][64 ch]
+    float* red = reinterpret_cast<float*>(smem);
+#pragma unroll
+    for (int a = 0; a < 9; ++a) {
+        float4 v = make_float4(acc[a][0].x, acc[a][0].y, acc[a][1].x, acc[a][1].y);
+        *reinterpret_cast<float4*>(red + (a * kDwTW + col) * kDwCB + cq * 4) = v;
+    }
+    __syncthreads();
+    for (int o = tid; o < 9 * kDwCB; o += kDwThreads) {
+        const int a = o / kDwCB, c = o % kDwCB;
+        const int ch = cb * kDwCB + c;
+        if (ch < p.C) {
+            float sum = 0.f;
+#pragma unroll 8
+            for (int q = 0; q < kDwTW; ++q) sum += red[(a * kDwTW + q) * kDwCB + c];
+            atomicAdd(p.dw + a * p.C + ch, sum);
+        }
+    }
+}
+
+// Returns 1 if the TMA kernel took the launch, 0 if the caller must use the direct kernel, < 0 on error.
+int launch_dw_wgrad_tma(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int N, int H, int W, int C, int Ho,
+                        int Wo, int pad_t, int pad_l, int in_act, cudaStream_t st) {
+    if (get_encode_fn() == nullptr) return 0;
+    CUtensorMap tmx, tmg;
+    int rc = make_tmap_nhwc(&tmx, x, N, H, W, C, kDwCB, kDwTW + 2, kDwTH + 2);
+    if (rc) return rc;
+    rc = make_tmap_nhwc(&tmg, dy, N, Ho, Wo, C, kDwCB, kDwTW, kDwTH);
+    if (rc) return rc;
+    DwWgradParams p;
+    p.N = N; p.C = C; p.Ho = Ho; p.Wo = Wo; p.pad_t = pad_t; p.pad_l = pad_l; p.in_act = in_act; p.dw = dw;
+    p.tiles_h = cdiv(Ho, kDwTH); p.tiles_w = cdiv(Wo, kDwTW);
+    const int tiles_c = cdiv(C, kDwCB);
+    const long long spatial = (long long)N * p.tiles_h * p.tiles_w;
+    if (spatial > 0x7fffffffLL) return 0;
+    p.spatial_tiles = (int)spatial;
+    int per = kNumSMs / tiles_c; if (per < 1) per = 1;
+    if (per > p.spatial_tiles) per = p.spatial_tiles;
+    p.ctas_per_cb = per;
+    constexpr int smem = kWgStages * kWgStageBytes + 128 + 64;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(dw_conv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        DLV3P_REQUIRE(e == cudaSuccess, DLV3P_ERR_CUDA, "cudaFuncSetAttribute(dw tma smem=%d): %s", smem, cudaGetErrorString(e));
+        cudaError_t e = cudaFuncSetAttribute(dw_wgrad_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(dw_wgrad_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(dw_wgrad_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        DLV3P_REQUIRE(e == cudaSuccess, DLV3P_ERR_CUDA, "cudaFuncSetAttribute(dw wgrad tma smem=%d): %s", smem, cudaGetErrorString(e));
         configured = true;
     }
-    const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;   // persistent: one CTA per SM
-    dw_conv_tma_kernel<<<grid, kDwThreads, smem, st>>>(tm, p);
-    rc = check_launch("dwconv3x3 (tma)");
+    if (in_act == DLV3P_ACT_NONE) dw_wgrad_tma_kernel<0><<<tiles_c * per, kDwThreads, smem, st>>>(tmx, tmg, p);
+    else if (in_act == DLV3P_ACT_RELU) dw_wgrad_tma_kernel<1><<<tiles_c * per, kDwThreads, smem, st>>>(tmx, tmg, p);
+    else dw_wgrad_tma_kernel<2><<<tiles_c * per, kDwThreads, smem, st>>>(tmx, tmg, p);
+    rc = check_launch("dwconv3x3_wgrad (tma)");
     return rc ? rc : 1;
 }
 

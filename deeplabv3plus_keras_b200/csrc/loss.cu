@@ -246,6 +246,190 @@ upsample_softmax_cbloss_kernel(const float* __restrict__ zl, const int32_t* __re
     if (!BWD) block_atomic_sum(loss_acc, loss_sum);
 }
 
+
+// ---- fused tail, fast path (f in {2,4,8,16}): one THREAD per output pixel ----------------------------------------
+// The warp-per-pixel kernel above is issue-bound (4.2 M warp iterations of ~100 instructions at cfg-2).  Here a block
+// of 256 threads owns a 16x16 patch of output pixels aligned to the half-factor-shifted grid, i.e. S x S (S = 16/f)
+// sub-tiles whose pixels interpolate between the same 2x2 low-resolution logits.  The (S+1)^2 x C corner logits are
+// staged in shared memory; each thread keeps its pixel's C logits / probabilities in registers (softmax without any
+// shuffle), and the transposed-resize gradient is reduced separably through shared memory (over x, then over y) into
+// an (S+1)^2 x C accumulator that is flushed with one global RED per (corner, class).  Forward and backward share one
+// pass (`fwd_bwd`), so the softmax is evaluated once per pixel per step.
+template <int CMAX, bool FWD, bool BWD>
+__global__ void __launch_bounds__(256)
+tail_pixel_kernel(const float* __restrict__ zl, const int32_t* __restrict__ labels, const float* __restrict__ pw,
+                  const float* __restrict__ nw, float eps, int N, int H, int W, int C, int f, float gscale,
+                  float* __restrict__ loss_sum, float* __restrict__ dzl, int nby, int nbx) {
+    constexpr int CS = CMAX | 1;                    // odd class stride: conflict-free per-pixel rows in smem
+    extern __shared__ float sm[];
+    const int S = 16 / f;
+    const int PS = S + 1;
+    float* patch = sm;                              // [PS][PS][CS]   corner logits
+    float* G = patch + PS * PS * CS;                // [PS][PS][CS]   corner gradient accumulators
+    float* spw = G + PS * PS * CS;                  // [32]
+    float* snw = spw + 32;                          // [32]
+    float* D = snw + 32;                            // [256][CS]      per-pixel logit gradients
+    float* R = D + 256 * CS;                        // [16][S][2][CS] x-reduced partials
+
+    const int tid = threadIdx.x;
+    int b = blockIdx.x;
+    const int bx = b % nbx; b /= nbx;
+    const int by = b % nby;
+    const int n = b / nby;
+    const int Ho = H * f, Wo = W * f;
+    const int ly0 = S * by - 1, lx0 = S * bx - 1;   // low-res coordinates of patch row/col 0 (before clamping)
+
+    for (int i = tid; i < PS * PS * CS; i += 256) {
+        const int c = i % CS;
+        const int r = i / CS;
+        const int pr = r / PS, pc = r % PS;
+        const int yy = min(max(ly0 + pr, 0), H - 1), xx = min(max(lx0 + pc, 0), W - 1);
+        patch[i] = (c < C) ? __ldg(zl + (((long long)n * H + yy) * W + xx) * C + c) : 0.f;
+        if (BWD) G[i] = 0.f;
+    }
+    if (tid < 32) { spw[tid] = tid < C ? __ldg(pw + tid) : 0.f; snw[tid] = tid < C ? __ldg(nw + tid) : 0.f; }
+    __syncthreads();
+
+    const int py = tid >> 4, px = tid & 15;
+    const int yo = 16 * by + py - f / 2, xo = 16 * bx + px - f / 2;
+    const bool valid = (yo >= 0 && yo < Ho && xo >= 0 && xo < Wo);
+    const int sy = py / f, sx = px / f;
+    const float inv_f = 1.f / (float)f;
+    const float ly = ((float)(py - sy * f) + 0.5f) * inv_f;     // TF half-pixel lerp: frac((o+0.5)/f - 0.5)
+    const float lx = ((float)(px - sx * f) + 0.5f) * inv_f;
+    float loss_acc = 0.f;
+    float d[CMAX];
+    if (valid) {
+        const float* p00 = patch + (sy * PS + sx) * CS;
+        const float* p01 = p00 + CS;
+        const float* p10 = p00 + PS * CS;
+        const float* p11 = p10 + CS;
+        float z[CMAX];
+        float m = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) {
+            if (c < C) {
+                const float top = p00[c] + (p01[c] - p00[c]) * lx;
+                const float bot = p10[c] + (p11[c] - p10[c]) * lx;
+                z[c] = top + (bot - top) * ly;
+                m = fmaxf(m, z[c]);
+            } else z[c] = -INFINITY;
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) { z[c] = (c < C) ? __expf(z[c] - m) : 0.f; s += z[c]; }
+        const float inv = __fdividef(1.f, s);
+        const int lab = __ldg(labels + ((long long)n * Ho + yo) * Wo + xo);
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) {
+            if (c < C) {
+                const float p = z[c] * inv;
+                const bool hit = (c == lab);
+                if (FWD) {
+                    // -(pw*y*log(p+eps) + nw*(1-y)*log(1-p+eps)), y one-hot
+                    const float arg = hit ? (p + eps) : (1.f - p + eps);
+                    loss_acc -= (hit ? spw[c] : snw[c]) * __logf(arg);
+                }
+                if (BWD) {
+                    const float g = hit ? -__fdividef(spw[c], p + eps) : __fdividef(snw[c], 1.f - p + eps);
+                    dot = fmaf(g, p, dot);
+                    d[c] = g;
+                    z[c] = p;
+                }
+            }
+        }
+        if (BWD) {
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) d[c] = (c < C) ? gscale * z[c] * (d[c] - dot) : 0.f;
+        }
+    } else if (BWD) {
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) d[c] = 0.f;
+    }
+    if (FWD) block_atomic_sum(loss_acc, loss_sum);
+    if (!BWD) return;
+
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) D[tid * CS + c] = d[c];
+    __syncthreads();
+    // phase A: reduce over x inside each sub-tile: R[py][sx][kx][c] = sum_px D[py][px][c] * (kx ? lx : 1-lx)
+    const int itemsA = 16 * S * 2 * C;
+    for (int i = tid; i < itemsA; i += 256) {
+        const int c = i % C;
+        int r = i / C;
+        const int kx = r & 1; r >>= 1;
+        const int ssx = r % S;
+        const int ppy = r / S;
+        float acc = 0.f;
+        for (int j = 0; j < f; ++j) {
+            const float l = ((float)j + 0.5f) * inv_f;
+            acc = fmaf(D[(ppy * 16 + ssx * f + j) * CS + c], kx ? l : 1.f - l, acc);
+        }
+        R[((ppy * S + ssx) * 2 + kx) * CS + c] = acc;
+    }
+    __syncthreads();
+    // phase B: reduce over y, accumulate the four corner contributions of every sub-tile into G
+    const int itemsB = S * 2 * S * 2 * C;
+    for (int i = tid; i < itemsB; i += 256) {
+        const int c = i % C;
+        int r = i / C;
+        const int kx = r & 1; r >>= 1;
+        const int ssx = r % S; r /= S;
+        const int ky = r & 1; r >>= 1;
+        const int ssy = r;
+        float acc = 0.f;
+        for (int j = 0; j < f; ++j) {
+            const float l = ((float)j + 0.5f) * inv_f;
+            acc = fmaf(R[(((ssy * f + j) * S + ssx) * 2 + kx) * CS + c], ky ? l : 1.f - l, acc);
+        }
+        atomicAdd(&G[((ssy + ky) * PS + ssx + kx) * CS + c], acc);
+    }
+    __syncthreads();
+    for (int i = tid; i < PS * PS * C; i += 256) {
+        const int c = i % C;
+        const int r = i / C;
+        const int pr = r / PS, pc = r % PS;
+        const float v = G[(pr * PS + pc) * CS + c];
+        if (v != 0.f) {
+            const int yy = min(max(ly0 + pr, 0), H - 1), xx = min(max(lx0 + pc, 0), W - 1);
+            atomicAdd(dzl + (((long long)n * H + yy) * W + xx) * C + c, v);
+        }
+    }
+}
+
+template <bool FWD, bool BWD>
+static int launch_tail_pixel(const float* zl, const int32_t* labels, const float* pw, const float* nw, float eps, int N,
+                             int H, int W, int C, int f, float gscale, float* loss_sum, float* dzl, cudaStream_t st) {
+    const int S = 16 / f, PS = S + 1;
+    const int nby = (H * f + f / 2 + 15) / 16, nbx = (W * f + f / 2 + 15) / 16;
+    const long long blocks = (long long)N * nby * nbx;
+    DLV3P_REQUIRE(blocks < 0x7fffffffLL, DLV3P_ERR_SHAPE, "fused tail: too many tiles");
+#define DLV3P_TAIL(CM)                                                                                             \
+    do {                                                                                                           \
+        constexpr int CS = (CM) | 1;                                                                               \
+        const int smem = (2 * PS * PS * CS + 64 + (BWD ? 256 * CS + 16 * S * 2 * CS : 0)) * 4;                     \
+        static int configured = 0;                                                                                 \
+        if (smem > configured) {                                                                                   \
+            cudaError_t e = cudaFuncSetAttribute(tail_pixel_kernel<CM, FWD, BWD>,                                  \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem);               \
+            DLV3P_REQUIRE(e == cudaSuccess, DLV3P_ERR_CUDA, "fused tail smem=%d: %s", smem, cudaGetErrorString(e)); \
+            configured = smem;                                                                                     \
+        }                                                                                                          \
+        tail_pixel_kernel<CM, FWD, BWD><<<(int)blocks, 256, smem, st>>>(zl, labels, pw, nw, eps, N, H, W, C, f,    \
+                                                                        gscale, loss_sum, dzl, nby, nbx);          \
+    } while (0)
+    if (C <= 8) DLV3P_TAIL(8);
+    else if (C <= 16) DLV3P_TAIL(16);
+    else if (C <= 21) DLV3P_TAIL(21);
+    else if (C <= 24) DLV3P_TAIL(24);
+    else DLV3P_TAIL(32);
+#undef DLV3P_TAIL
+    return check_launch("upsample_softmax_cbloss (pixel)");
+}
+
+static inline bool tail_fast_ok(int f) { return f == 2 || f == 4 || f == 8 || f == 16; }
+
 static int warp_grid(long long work_items) {
     long long blocks = (work_items + 7) / 8;          // 8 warps per block
     const long long cap = (long long)kNumSMs * 16;
@@ -285,6 +469,9 @@ extern "C" int dlv3p_upsample_softmax_cbloss_fwd(const float* zl, const int32_t*
     DLV3P_REQUIRE(zl && labels && pw && nw && loss_sum, DLV3P_ERR_SHAPE, "upsample_softmax_cbloss_fwd: null pointer");
     DLV3P_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C <= 32 && f >= 1 && (f == 1 || f % 2 == 0), DLV3P_ERR_SHAPE,
                   "upsample_softmax_cbloss_fwd: need C <= 32 and an even (or unit) factor, got C=%d f=%d", C, f);
+    if (tail_fast_ok(f))
+        return launch_tail_pixel<true, false>(zl, labels, pw, nw, eps, N, H, W, C, f, 0.f, loss_sum, nullptr,
+                                              (cudaStream_t)stream);
     const long long ntiles = (long long)N * (H + 1) * (W + 1);
     upsample_softmax_cbloss_kernel<false><<<warp_grid(ntiles), 256, 0, (cudaStream_t)stream>>>(
         zl, labels, pw, nw, eps, N, H, W, C, f, 0.f, loss_sum, nullptr, ntiles);
@@ -297,10 +484,31 @@ extern "C" int dlv3p_upsample_softmax_cbloss_bwd(const float* zl, const int32_t*
     DLV3P_REQUIRE(zl && labels && pw && nw && dzl, DLV3P_ERR_SHAPE, "upsample_softmax_cbloss_bwd: null pointer");
     DLV3P_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C <= 32 && f >= 1 && (f == 1 || f % 2 == 0), DLV3P_ERR_SHAPE,
                   "upsample_softmax_cbloss_bwd: need C <= 32 and an even (or unit) factor, got C=%d f=%d", C, f);
+    if (tail_fast_ok(f))
+        return launch_tail_pixel<false, true>(zl, labels, pw, nw, eps, N, H, W, C, f, grad_scale, nullptr, dzl,
+                                              (cudaStream_t)stream);
     const long long ntiles = (long long)N * (H + 1) * (W + 1);
     upsample_softmax_cbloss_kernel<true><<<warp_grid(ntiles), 256, 0, (cudaStream_t)stream>>>(
         zl, labels, pw, nw, eps, N, H, W, C, f, grad_scale, nullptr, dzl, ntiles);
     return check_launch("upsample_softmax_cbloss_bwd");
+}
+
+extern "C" int dlv3p_upsample_softmax_cbloss_fwd_bwd(const float* zl, const int32_t* labels, const float* pw,
+                                                     const float* nw, float eps, int N, int H, int W, int C, int f,
+                                                     float grad_scale, float* loss_sum, float* dzl, void* stream) {
+    DLV3P_REQUIRE(zl && labels && pw && nw && loss_sum && dzl, DLV3P_ERR_SHAPE,
+                  "upsample_softmax_cbloss_fwd_bwd: null pointer");
+    DLV3P_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C <= 32 && f >= 1 && (f == 1 || f % 2 == 0), DLV3P_ERR_SHAPE,
+                  "upsample_softmax_cbloss_fwd_bwd: need C <= 32 and an even (or unit) factor, got C=%d f=%d", C, f);
+    if (tail_fast_ok(f))
+        return launch_tail_pixel<true, true>(zl, labels, pw, nw, eps, N, H, W, C, f, grad_scale, loss_sum, dzl,
+                                             (cudaStream_t)stream);
+    const long long ntiles = (long long)N * (H + 1) * (W + 1);
+    upsample_softmax_cbloss_kernel<false><<<warp_grid(ntiles), 256, 0, (cudaStream_t)stream>>>(
+        zl, labels, pw, nw, eps, N, H, W, C, f, 0.f, loss_sum, nullptr, ntiles);
+    upsample_softmax_cbloss_kernel<true><<<warp_grid(ntiles), 256, 0, (cudaStream_t)stream>>>(
+        zl, labels, pw, nw, eps, N, H, W, C, f, grad_scale, nullptr, dzl, ntiles);
+    return check_launch("upsample_softmax_cbloss_fwd_bwd");
 }
 
 extern "C" int dlv3p_softmax_argmax(const float* z, int64_t P, int C, float* probs, int32_t* labels, void* stream) {

@@ -109,7 +109,12 @@ class ParamStore:
         self.entries: Dict[Tuple[int, str], Tuple[str, int, Tuple]] = {}
         reg, plain, frozen = [], [], []
         for l in layers_in_order:
-            for n in l.weight_names():
+            names = list(l.weight_names())
+            if "beta" in names and "gamma" in names:
+                # BatchNormalization: keep [dbeta | dgamma] adjacent in the gradient arena so that the backward
+                # reduction kernel (red[0..C) = sum g, red[C..2C) = sum g*xhat) accumulates straight into it
+                names = ["beta", "gamma"] + [n for n in names if n not in ("beta", "gamma")]
+            for n in names:
                 w = l._weights[n]
                 if not l._trainable[n]:
                     frozen.append((l, n, w))
@@ -441,8 +446,18 @@ class Plan:
             if training:
                 mean, invstd = self._alloc((C,), torch.float32), self._alloc((C,), torch.float32)
                 stat = self._stat_slot(C)
-                # BN parameter gradients: [dbeta | dgamma] must be contiguous for the reduce kernel
-                red_slot = self._stat_slot(C)
+                # BN parameter gradients: [dbeta | dgamma] must be contiguous for the reduce kernel.  When both
+                # exist and C % 8 == 0 they are adjacent in the gradient arena (ParamStore) and the kernel writes
+                # there directly; otherwise it reduces into a scratch slot that is then added to the arena.
+                red_direct = False
+                if gamma is not None and beta is not None:
+                    gb_, gg_ = P.view(bn, "beta", grad=True), P.view(bn, "gamma", grad=True)
+                    if gb_.data_ptr() + 4 * C == gg_.data_ptr():
+                        red_direct = True
+                        k0 = P.entries[(id(bn), "beta")][1]
+                        red_slot = lambda k0=k0, C=C: P.g[k0:k0 + 2 * C]
+                if not red_direct:
+                    red_slot = self._stat_slot(C)
                 y = self._alloc((N, Ho, Wo, Cout), self.dt)          # raw conv output, saved for backward
             else:
                 self.prep.append(lambda: ops.bn_fold(gamma, beta, mm, mv, C, bn.epsilon, scale, shift))
@@ -531,10 +546,10 @@ class Plan:
                 self.bwd_seq(lambda: ops.bn_bwd_apply(g, y, scale, shift, mean, invstd, act, red(), Mo, Cout,
                                                       dy_get()))
                 # parameter gradients live in the stats arena; copy into the grad arena
-                if beta is not None:
+                if beta is not None and not red_direct:
                     gb = P.view(bn, "beta", grad=True)
                     self.bwd_seq(lambda: gb.add_(red()[:Cout]))
-                if gamma is not None:
+                if gamma is not None and not red_direct:
                     gg = P.view(bn, "gamma", grad=True)
                     self.bwd_seq(lambda: gg.add_(red()[Cout:]))
             else:
@@ -843,10 +858,10 @@ class Plan:
         P = N * H * f * W * f
         z = self.logits.buf
         if self.fused_tail and f > 1:
-            ops.upsample_softmax_cbloss_fwd(z, self.labels, self.pw, self.nw, self.eps, N, H, W, C, f, self.loss_sum)
             g = self.logits.grad
             g.zero_()
-            ops.upsample_softmax_cbloss_bwd(z, self.labels, self.pw, self.nw, self.eps, N, H, W, C, f, 1.0 / P, g)
+            ops.upsample_softmax_cbloss_fwd_bwd(z, self.labels, self.pw, self.nw, self.eps, N, H, W, C, f, 1.0 / P,
+                                                self.loss_sum, g)
         else:
             zh = self.tail_buf("zh", (N, H * f, W * f, C), torch.float32)
             dzh = self.tail_buf("dzh", (N, H * f, W * f, C), torch.float32)

@@ -301,6 +301,12 @@ def upsample_softmax_cbloss_bwd(zl, labels, pw, nw, eps, N, H, W, Cc, f, grad_sc
          _p(dzl), _stream())
 
 
+def upsample_softmax_cbloss_fwd_bwd(zl, labels, pw, nw, eps, N, H, W, Cc, f, grad_scale, loss_sum, dzl):
+    """loss_sum += sum of per-pixel losses and dzl += grad_scale * d(loss)/d(zl) in one pass (caller zeroes both)."""
+    call("dlv3p_upsample_softmax_cbloss_fwd_bwd", _p(zl), _p(labels), _p(pw), _p(nw), eps, N, H, W, Cc, f, grad_scale,
+         _p(loss_sum), _p(dzl), _stream())
+
+
 def softmax_argmax(z, P, Cc, probs=None, labels=None):
     call("dlv3p_softmax_argmax", _p(z), P, Cc, _p(probs), _p(labels), _stream())
 

@@ -54,6 +54,7 @@ COSTS: Dict[str, Tuple[str, Callable]] = {
     "dlv3p_bilinear_bwd": ("hbm", lambda a: (a[4] * a[5] * a[6] * a[7] * (a[8] * a[9] * _esz(a[11]) + _esz(a[12])), 0)),
     "dlv3p_upsample_softmax_cbloss_fwd": ("hbm", lambda a: (a[5] * a[6] * a[7] * (a[9] * a[9] * 4 + a[8] * 4), 0)),
     "dlv3p_upsample_softmax_cbloss_bwd": ("hbm", lambda a: (a[5] * a[6] * a[7] * (a[9] * a[9] * 4 + 2 * a[8] * 4), 0)),
+    "dlv3p_upsample_softmax_cbloss_fwd_bwd": ("hbm", lambda a: (a[5] * a[6] * a[7] * (a[9] * a[9] * 4 + 2 * a[8] * 4), 0)),
     "dlv3p_softmax_cbloss_fwd": ("hbm", lambda a: (a[5] * (a[6] * 4 * (1 + _opt(a[8])) + 4), 0)),
     "dlv3p_softmax_cbloss_bwd": ("hbm", lambda a: (a[5] * (2 * a[6] * 4 + 4), 0)),
     "dlv3p_softmax_argmax": ("hbm", lambda a: (a[1] * a[2] * 4 * (1 + _opt(a[3])) + a[1] * 4 * _opt(a[4]), 0)),

@@ -187,6 +187,11 @@ int dlv3p_upsample_softmax_cbloss_fwd(const float* zl, const int32_t* labels, co
 int dlv3p_upsample_softmax_cbloss_bwd(const float* zl, const int32_t* labels, const float* pw, const float* nw,
                                       float eps, int N, int H, int W, int C, int f, float grad_scale, float* dzl,
                                       void* stream);
+/* both of the above in ONE pass over the label map (the training step): loss_sum[0] += sum_pix L_pix and
+ * dzl += grad_scale * gradient; caller zeroes loss_sum and dzl. */
+int dlv3p_upsample_softmax_cbloss_fwd_bwd(const float* zl, const int32_t* labels, const float* pw, const float* nw,
+                                          float eps, int N, int H, int W, int C, int f, float grad_scale,
+                                          float* loss_sum, float* dzl, void* stream);
 /* inference tail: probs = softmax(z) and/or label map = argmax(z) (first max wins; MeanIoUExt ss.py:310-311) */
 int dlv3p_softmax_argmax(const float* z, int64_t P, int C, float* probs, int32_t* labels, void* stream);
 /* the Keras-signature loss on dense tensors (one-hot or soft y_true, probabilities y_pred), fwd and grad wrt y_pred */

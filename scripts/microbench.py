@@ -76,11 +76,13 @@ def t(shape, dtype=bf):
 # ---- K1 depthwise: entry flow (HBM-resident) and middle flow (L2-resident) ----
 for (H, C, dil) in [(254, 128, 1), (127, 256, 1), (64, 728, 1), (32, 728, 1), (32, 256, 12)]:
     x, w = t((N, H, H, C)), t((3, 3, C), torch.float32)
-    y = torch.empty_like(x)
+    y, dx, res = torch.empty_like(x), torch.empty_like(x), t((N, H, H, C))
     dwg = torch.zeros((3, 3, C), device=dev)
     tag = f"{H}x{H}x{C} r{dil}"
     timeit(f"dw_fwd {tag}", lambda: ops.dwconv3x3_fwd(x, w, 1, (dil, dil), in_act=1, out=y))
-    timeit(f"dw_dgrad {tag}", lambda: ops.dwconv3x3_dgrad(y, w, x.shape, 1, (dil, dil), x_pre=x, in_act=1, out=y))
+    timeit(f"dw_dgrad {tag}", lambda: ops.dwconv3x3_dgrad(y, w, x.shape, 1, (dil, dil), x_pre=x, in_act=1, out=dx))
+    timeit(f"dw_dgrad+add {tag}", lambda: ops.dwconv3x3_dgrad(y, w, x.shape, 1, (dil, dil), x_pre=x, in_act=1,
+                                                              addend=res, out=dx))
     timeit(f"dw_wgrad {tag}", lambda: ops.dwconv3x3_wgrad(x, y, dwg, 1, (dil, dil), in_act=1))
 
 # ---- K2 GEMMs ----
@@ -117,5 +119,7 @@ ls, dzl = torch.zeros(1, device=dev), torch.zeros_like(zl)
 timeit("fused_loss_fwd 512x512x21", lambda: ops.upsample_softmax_cbloss_fwd(zl, lab, pw, nw, 1e-7, N, 32, 32, 21, 16, ls))
 timeit("fused_loss_bwd 512x512x21", lambda: ops.upsample_softmax_cbloss_bwd(zl, lab, pw, nw, 1e-7, N, 32, 32, 21, 16,
                                                                               1.0, dzl))
+timeit("fused_loss_fwd_bwd 512x512x21", lambda: ops.upsample_softmax_cbloss_fwd_bwd(zl, lab, pw, nw, 1e-7, N, 32, 32, 21,
+                                                                                      16, 1.0, ls, dzl))
 if args.json:
     json.dump(results, open(args.json, "w"), indent=1)

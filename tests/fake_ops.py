@@ -378,6 +378,11 @@ def upsample_softmax_cbloss_bwd(zl, labels, pw, nw, eps, N, H, W, Cc, f, grad_sc
     dzl += zz.grad
 
 
+def upsample_softmax_cbloss_fwd_bwd(zl, labels, pw, nw, eps, N, H, W, Cc, f, grad_scale, loss_sum, dzl):
+    upsample_softmax_cbloss_fwd(zl, labels, pw, nw, eps, N, H, W, Cc, f, loss_sum)
+    upsample_softmax_cbloss_bwd(zl, labels, pw, nw, eps, N, H, W, Cc, f, grad_scale, dzl)
+
+
 def softmax_argmax(z, P, Cc, probs=None, labels=None):
     zz = z.reshape(P, Cc).float()
     if probs is not None:

@@ -448,7 +448,8 @@ def test_softmax_cbloss():
     check("confusion", cm, O.confusion_matrix(lab, labels.cpu(), C), 0, 0)
 
 
-@pytest.mark.parametrize("case", [(2, 6, 7, 21, 16), (1, 5, 5, 21, 2), (1, 4, 6, 19, 8), (2, 3, 3, 21, 4)])
+@pytest.mark.parametrize("case", [(2, 6, 7, 21, 16), (1, 5, 5, 21, 2), (1, 4, 6, 19, 8), (2, 3, 3, 21, 4),
+                                  (1, 3, 4, 21, 6), (1, 2, 3, 5, 16), (1, 3, 3, 16, 8), (1, 2, 2, 12, 4)])
 def test_fused_upsample_softmax_cbloss(case):
     o = ops()
     N, H, W, C, f = case
@@ -466,6 +467,11 @@ def test_fused_upsample_softmax_cbloss(case):
     dzl = torch.zeros((N, H, W, C), device=DEV)
     o.upsample_softmax_cbloss_bwd(zl.to(DEV), lab.to(DEV), pw, nw, 1e-7, N, H, W, C, f, 1.0 / P, dzl)
     check("fused dzl", dzl, zr.grad, 2e-3, 1e-7)
+    # the one-pass training entry point gives the same loss and gradient
+    ls2, dzl2 = torch.zeros(1, device=DEV), torch.zeros((N, H, W, C), device=DEV)
+    o.upsample_softmax_cbloss_fwd_bwd(zl.to(DEV), lab.to(DEV), pw, nw, 1e-7, N, H, W, C, f, 1.0 / P, ls2, dzl2)
+    check("fused loss (fwd_bwd)", ls2 / P, loss_ref.reshape(1), 1e-4, 1e-6)
+    check("fused dzl (fwd_bwd)", dzl2, zr.grad, 2e-3, 1e-7)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
