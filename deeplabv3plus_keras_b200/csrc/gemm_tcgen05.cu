@@ -10,11 +10,17 @@
 //   warp 1, one lane : MMA issuer    — tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N, K=16 per instruction,
 //                                      fp32 accumulators in TMEM, TWO accumulator stages (2*BLOCK_N columns) so the
 //                                      epilogue of tile i overlaps the main loop of tile i+1
-//   warps 2..5       : epilogue      — tcgen05.ld 32x32b (one accumulator row per lane) -> 32x33 fp32 smem transpose
-//                                      -> column-per-lane pass: fused per-column scale/shift (folded BatchNorm) +
-//                                      ReLU/ReLU6 + residual addend, shuffle-free per-column sum / sum-of-squares
-//                                      (training-mode BatchNorm statistics), coalesced stores (or coalesced fp32 REDs
-//                                      for the filter gradient)
+//   warps 2..5       : epilogue      — tcgen05.ld 32x32b (one accumulator row per lane) -> fused per-column
+//                                      scale/shift (folded BatchNorm) + ReLU/ReLU6 -> bf16 rows into a 128B-swizzled
+//                                      smem staging tile (32 rows x 64 cols, double buffered per warp) -> ONE TMA
+//                                      tensor store per tile (full-line coalesced writes, OOB clipping); training-mode
+//                                      BatchNorm statistics (per-column sum / sum of squares) are read back
+//                                      column-per-lane from the same staging tile (conflict-free, shuffle-free).
+//                                      The filter gradient stages fp32 rows and issues TMA reduce-adds
+//                                      (cp.reduce.async.bulk.tensor ... add.f32) instead of per-element REDs.
+//                                      [A lane-per-row direct store touches 32 different 128 B lines per STG: ncu
+//                                      showed the K=64..288 GEMMs bound by exactly that, profiles/r1_*]
+//                                      Fallback (fp32 C, residual addend, unaligned ldc): direct stores / REDs.
 // Forward / input-gradient use K-major operands (A[M,K], B[N,K], K contiguous).  The filter gradient
 // dW = X^T dY contracts over the pixel axis, which is NOT contiguous in NHWC: both operands are fed MN-major
 // (64-element x 64-row TMA boxes, same 128B swizzle) so no transposed copy of the activations is ever written;
@@ -25,10 +31,18 @@ namespace dlv3p {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;            // 64 bf16 = 128 B = one swizzle atom row
-constexpr int kStages = 4;
 constexpr int kThreads = 192;
-constexpr int kEpiStageFloats = 32 * 33;          // per epilogue warp: 32 rows x 32 cols, padded
+constexpr int kEpiStageFloats = 32 * 33;          // fallback path, per epilogue warp: 32 rows x 32 cols, padded
+constexpr int kEpiBufBytes = 32 * 128;            // TMA-store path: one staging tile = 32 rows x 128 B
+constexpr int kEpiBytes = 4 * 2 * kEpiBufBytes;   // 4 epilogue warps x 2 buffers (also holds the fallback transposes)
 constexpr int kMaxStatCols = 1024;                // per-CTA smem accumulators for the BN column statistics
+static_assert(kEpiBytes >= 4 * kEpiStageFloats * 4, "staging area must hold the fallback transposes");
+template <int BLOCK_N> struct GemmCfg {
+    static constexpr int kStageBytes = kBlockM * kBlockK * 2 + BLOCK_N * kBlockK * 2;
+    static constexpr int kStages = BLOCK_N == 256 ? 3 : 4;          // 3 x 48 KB / 4 x <=32 KB operand ring
+    static constexpr int kSmem = kStages * kStageBytes + kEpiBytes + 2 * kMaxStatCols * 4 + 1024 /*align*/ + 256 /*barriers*/;
+    static_assert(kSmem <= 232448, "shared memory budget");
+};
 
 struct GemmParams {
     int M, N, K;                       // logical GEMM extents (for WGRAD: rows=K(cin), cols=N(cout), reduction=M)
@@ -39,6 +53,7 @@ struct GemmParams {
     int kb_per_split;                  // WGRAD: reduction blocks (of 64 rows) handled by one work item
     int splits;                        // WGRAD: number of pixel-range splits
     int n_tiles, m_tiles;              // output tile grid
+    int tma_store;                     // epilogue through the smem staging tile + TMA store / reduce-add
 };
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -96,17 +111,19 @@ __device__ __forceinline__ void decode_work(const GemmParams& p, int w, int& row
 
 template <int BLOCK_N, bool WGRAD>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
     constexpr int A_BYTES = kBlockM * kBlockK * 2;
     constexpr int B_BYTES = BLOCK_N * kBlockK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int kStages = GemmCfg<BLOCK_N>::kStages;
     constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;            // two accumulator stages (64 .. 512, power of two)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    float* epi_stage = reinterpret_cast<float*>(smem + kStages * STAGE_BYTES);
-    float* stat_smem = epi_stage + 4 * kEpiStageFloats;                      // [2][kMaxStatCols]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES + 4 * kEpiStageFloats * 4 +
-                                                 2 * kMaxStatCols * 4);
+    uint8_t* epi_bytes = smem + kStages * STAGE_BYTES;                       // 1024-aligned (stage sizes are)
+    float* epi_stage = reinterpret_cast<float*>(epi_bytes);
+    float* stat_smem = reinterpret_cast<float*>(epi_bytes + kEpiBytes);      // [2][kMaxStatCols]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_bytes + kEpiBytes + 2 * kMaxStatCols * 4);
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t full_bar = smem_u32(bars);                      // kStages
     const uint32_t empty_bar = smem_u32(bars + kStages);           // kStages
@@ -121,6 +138,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+        if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
         for (int s = 0; s < kStages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + 8 * s, 1); mbar_init(tmem_empty_bar + 8 * s, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -213,6 +231,108 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float* stage = epi_stage + q * kEpiStageFloats;
         const int row_limit = WGRAD ? p.K : p.M;
         const bool use_smem_stats = (!WGRAD) && (p.col_stats != nullptr) && (p.N <= kMaxStatCols);
+        if (p.tma_store) {
+            // ---- staged epilogue: TMEM -> registers -> swizzled smem tile -> TMA store / reduce-add ----
+            constexpr int CW = WGRAD ? 32 : 64;                 // columns per staging tile (128-byte rows)
+            const uint32_t stg0 = smem_u32(epi_bytes) + (uint32_t)q * 2u * kEpiBufBytes;
+            const uint32_t lane_row = (uint32_t)lane * 128u;
+            const uint32_t sw = (uint32_t)(lane & 7);
+            uint32_t buf = 0, t = 0;
+            for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++t) {
+                int row0, col0, kb_begin, kb_end;
+                decode_work<BLOCK_N, WGRAD>(p, w, row0, col0, kb_begin, kb_end);
+                const uint32_t as = t & 1u;
+                mbar_wait(tmem_full_bar + 8 * as, (t >> 1) & 1u);
+                tc_fence_after();
+                const int rbase = row0 + q * 32;
+                const int ncols = min(BLOCK_N, p.N - col0);
+                const int n_chunks = (ncols + CW - 1) / CW;
+#pragma unroll 1
+                for (int ch = 0; ch < n_chunks; ++ch) {
+                    const int n_base = col0 + ch * CW;
+                    const uint32_t stg = stg0 + buf * kEpiBufBytes;
+                    if (lane == 0) tma_wait_group_read<1>();    // the store that last read this buffer has drained it
+                    __syncwarp();
+#pragma unroll
+                    for (int h = 0; h < CW / 32; ++h) {
+                        uint32_t raw[32];
+                        tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N +
+                                             (uint32_t)(ch * CW + h * 32), raw);
+                        if (ch == n_chunks - 1 && h == CW / 32 - 1) {
+                            // every TMEM read of this accumulator stage has completed: hand it back to the MMA warp
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(tmem_empty_bar + 8 * as);
+                        }
+                        if (WGRAD) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane_row + (((uint32_t)j ^ sw) << 4)),
+                                             "r"(raw[4 * j]), "r"(raw[4 * j + 1]), "r"(raw[4 * j + 2]), "r"(raw[4 * j + 3]) : "memory");
+                        } else {
+                            float v[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+                            if (p.col_scale != nullptr) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    const int n = min(n_base + h * 32 + j, p.N - 1);
+                                    v[j] = fmaf(v[j], __ldg(p.col_scale + n), __ldg(p.col_shift + n));
+                                }
+                            }
+                            if (p.act != DLV3P_ACT_NONE) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+                            }
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                uint32_t o[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    __nv_bfloat162 pr = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+                                    o[e] = *reinterpret_cast<uint32_t*>(&pr);
+                                }
+                                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane_row + (((uint32_t)(h * 4 + g) ^ sw) << 4)),
+                                             "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+                            }
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0 && rbase < (WGRAD ? p.K : p.M)) {
+                        if (WGRAD) tma_reduce_add_2d(&tmC, stg, n_base, rbase);
+                        else tma_store_2d(&tmC, stg, n_base, rbase);
+                        tma_commit_group();
+                    }
+                    if (!WGRAD && p.col_stats != nullptr) {
+                        // BatchNormalization batch statistics of the STORED (bf16) conv output: lane L owns columns
+                        // n_base+2L, n_base+2L+1 and walks the 32 rows of the staging tile (one 32-bit word per row,
+                        // all 32 banks distinct); rows >= M hold exact zeros (TMA zero-filled A)
+                        float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
+                        const uint32_t cj = (uint32_t)(lane >> 2), cw = (uint32_t)(lane & 3) << 2;
+#pragma unroll 8
+                        for (int rr = 0; rr < 32; ++rr) {
+                            uint32_t word;
+                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word)
+                                         : "r"(stg + (uint32_t)rr * 128u + ((cj ^ (uint32_t)(rr & 7)) << 4) + cw));
+                            const float a = __uint_as_float(word << 16), b = __uint_as_float(word & 0xffff0000u);
+                            s1a += a; s2a = fmaf(a, a, s2a);
+                            s1b += b; s2b = fmaf(b, b, s2b);
+                        }
+                        const int col = n_base + 2 * lane;
+                        if (use_smem_stats) {
+                            if (col < p.N) { atomicAdd(stat_smem + col, s1a); atomicAdd(stat_smem + kMaxStatCols + col, s2a); }
+                            if (col + 1 < p.N) { atomicAdd(stat_smem + col + 1, s1b); atomicAdd(stat_smem + kMaxStatCols + col + 1, s2b); }
+                        } else {
+                            if (col < p.N) { atomicAdd(p.col_stats + col, s1a); atomicAdd(p.col_stats + p.N + col, s2a); }
+                            if (col + 1 < p.N) { atomicAdd(p.col_stats + col + 1, s1b); atomicAdd(p.col_stats + p.N + col + 1, s2b); }
+                        }
+                    }
+                    buf ^= 1u;
+                }
+            }
+            if (lane == 0) tma_wait_group_all();
+        } else {
         uint32_t t = 0;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++t) {
             int row0, col0, kb_begin, kb_end;
@@ -339,6 +459,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (last_chunk) break;
             }
         }
+        }   // direct-store fallback
         if (use_smem_stats) {
             // one flush per CTA: contended global atomics cost ~35 ns per cache line (serialised at L2)
             asm volatile("bar.sync 1, 128;" ::: "memory");    // the four epilogue warps only
@@ -362,9 +483,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // ---- host side --------------------------------------------------------------------------------------------------
 template <int BLOCK_N, bool WGRAD>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
-    constexpr int smem = kStages * (kBlockM * kBlockK * 2 + BLOCK_N * kBlockK * 2) + 4 * kEpiStageFloats * 4 +
-                         2 * kMaxStatCols * 4 + 1024 /*align*/ + 256 /*barriers*/;
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
+                       cudaStream_t st) {
+    constexpr int smem = GemmCfg<BLOCK_N>::kSmem;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -373,7 +494,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     }
     const int work = p.n_tiles * p.m_tiles * (WGRAD ? p.splits : 1);
     const int grid = work < kNumSMs ? work : kNumSMs;         // persistent: one CTA per SM
-    gemm_tc_kernel<BLOCK_N, WGRAD><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+    gemm_tc_kernel<BLOCK_N, WGRAD><<<grid, kThreads, smem, st>>>(tmA, tmB, tmC, p);
     return check_launch(WGRAD ? "gemm_wgrad_bf16" : "gemm_bf16");
 }
 
@@ -403,11 +524,17 @@ extern "C" int dlv3p_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
     p.col_scale = col_scale; p.col_shift = col_shift; p.act = act;
     p.addend = addend; p.ld_add = ld_addend; p.col_stats = col_stats; p.kb_per_split = 0; p.splits = 1;
     p.n_tiles = cdiv(N, bn); p.m_tiles = cdiv(M, kBlockM);
+    p.tma_store = (c_dtype == DLV3P_BF16 && addend == nullptr && (ldc % 8) == 0 && aligned16(C) && bn >= 64) ? 1 : 0;
+    CUtensorMap tmC = tmA;
+    if (p.tma_store) {
+        rc = make_tmap(&tmC, C, N, M, ldc, 64, 32);
+        if (rc) return rc;
+    }
     switch (bn) {
-        case 32: return launch_gemm<32, false>(tmA, tmB, p, st);
-        case 64: return launch_gemm<64, false>(tmA, tmB, p, st);
-        case 128: return launch_gemm<128, false>(tmA, tmB, p, st);
-        default: return launch_gemm<256, false>(tmA, tmB, p, st);
+        case 32: return launch_gemm<32, false>(tmA, tmB, tmC, p, st);
+        case 64: return launch_gemm<64, false>(tmA, tmB, tmC, p, st);
+        case 128: return launch_gemm<128, false>(tmA, tmB, tmC, p, st);
+        default: return launch_gemm<256, false>(tmA, tmB, tmC, p, st);
     }
 }
 
@@ -438,9 +565,15 @@ extern "C" int dlv3p_gemm_wgrad_bf16(const void* X, int64_t ldx, const void* dY,
     if (splits > total_kb) splits = total_kb;
     p.kb_per_split = cdiv(total_kb, splits);
     p.splits = cdiv(total_kb, p.kb_per_split);
+    p.tma_store = ((ldw % 4) == 0 && aligned16(dW)) ? 1 : 0;
+    CUtensorMap tmC = tmA;
+    if (p.tma_store) {
+        rc = make_tmap(&tmC, dW, N, K, ldw, 32, 32, /*f32=*/true);
+        if (rc) return rc;
+    }
     switch (bn) {
-        case 64: return launch_gemm<64, true>(tmA, tmB, p, st);
-        case 128: return launch_gemm<128, true>(tmA, tmB, p, st);
-        default: return launch_gemm<256, true>(tmA, tmB, p, st);
+        case 64: return launch_gemm<64, true>(tmA, tmB, tmC, p, st);
+        case 128: return launch_gemm<128, true>(tmA, tmB, tmC, p, st);
+        default: return launch_gemm<256, true>(tmA, tmB, tmC, p, st);
     }
 }

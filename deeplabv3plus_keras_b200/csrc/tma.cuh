@@ -46,6 +46,21 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
+// smem -> global tensor stores (and fp32 reduce-adds) through TMA: coalesced full-line writes with OOB clipping
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_wait_group_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ---- host side --------------------------------------------------------------------------------------------------
 static inline PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -60,15 +75,18 @@ static inline PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     return fn;
 }
 
-// 2D bf16 tensor map: inner extent d0 (contiguous), outer extent d1 with row pitch ld elements
-static inline int make_tmap(CUtensorMap* map, const void* base, long long d0, long long d1, long long ld, int box0, int box1) {
+// 2D tensor map (bf16, or fp32 with f32 = true), 128B swizzle: inner extent d0 (contiguous), outer extent d1 with row
+// pitch ld elements
+static inline int make_tmap(CUtensorMap* map, const void* base, long long d0, long long d1, long long ld, int box0,
+                            int box1, bool f32 = false) {
     auto fn = get_encode_fn();
     DLV3P_REQUIRE(fn != nullptr, DLV3P_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t dims[2] = {(cuuint64_t)d0, (cuuint64_t)d1};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * (f32 ? 4 : 2)};
     cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
     cuuint32_t estr[2] = {1, 1};
-    CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult rc = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                     const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DLV3P_REQUIRE(rc == CUDA_SUCCESS, DLV3P_ERR_CUDA,

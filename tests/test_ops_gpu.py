@@ -166,6 +166,33 @@ def test_gemm_bf16_epilogue(case):
     check("gemm stats sumsq", stats[1], (acc * acc).sum(0), 1e-3, 1e-3 * M)
 
 
+@pytest.mark.parametrize("case", [(517, 728, 728), (1000, 256, 256), (300, 64, 64), (4100, 96, 576), (16384, 1024, 128),
+                                  (130, 200, 72)])
+def test_gemm_bf16_tma_store_stats(case):
+    """bf16 output without addend takes the staged TMA-store epilogue: channel-slice write (ldc > N), fused
+    scale/shift/ReLU, and the BatchNormalization statistics of the STORED (bf16-rounded) accumulator."""
+    o = ops()
+    M, N, K = case
+    a = rnd((M, K), torch.bfloat16, 26)
+    b = rnd((N, K), torch.bfloat16, 27, 1.0 / math.sqrt(K))
+    acc = a.double() @ b.double().t()
+    ldc = N + 16
+    out = torch.zeros((M, ldc), dtype=torch.bfloat16, device=DEV)
+    stats = torch.zeros((2, N), dtype=torch.float32, device=DEV)
+    o.gemm_bf16(a.to(DEV), b.to(DEV), M, N, K, out, ldc=ldc, col_stats=stats)
+    check("gemm tma store", out[:, :N], acc, 1e-2, 1e-2)
+    assert float(out[:, N:].abs().max()) == 0.0, "gemm wrote outside its channel slice"
+    stored = out[:, :N].double().cpu()
+    check("stats sum (stored)", stats[0], stored.sum(0), 1e-4, 1e-4 * math.sqrt(M))
+    check("stats sumsq (stored)", stats[1], (stored * stored).sum(0), 1e-4, 1e-4 * M)
+    sc = rnd((N,), torch.float32, 28, 0.2) + 1.0
+    sh = rnd((N,), torch.float32, 29, 0.5)
+    out2 = torch.zeros((M, ldc), dtype=torch.bfloat16, device=DEV)
+    o.gemm_bf16(a.to(DEV), b.to(DEV), M, N, K, out2, ldc=ldc, col_scale=sc.to(DEV), col_shift=sh.to(DEV), act=o.ACT_RELU)
+    check("gemm tma store epi", out2[:, :N], torch.relu(acc * sc.double() + sh.double()), 1e-2, 2e-2)
+    assert float(out2[:, N:].abs().max()) == 0.0
+
+
 def test_gemm_bf16_strided_a():
     """A is a channel slice of a wider tensor (lda > K), as when a branch reads part of a concat."""
     o = ops()
