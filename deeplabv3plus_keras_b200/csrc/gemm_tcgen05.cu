@@ -25,6 +25,8 @@
 // dW = X^T dY contracts over the pixel axis, which is NOT contiguous in NHWC: both operands are fed MN-major
 // (64-element x 64-row TMA boxes, same 128B swizzle) so no transposed copy of the activations is ever written;
 // its work list is (pixel-range split) x (tile), split-major so that concurrently running CTAs share operands in L2.
+#include <stdlib.h>
+
 #include "tma.cuh"
 
 namespace dlv3p {
@@ -106,6 +108,106 @@ __device__ __forceinline__ void decode_work(const GemmParams& p, int w, int& row
     } else {
         kb_begin = 0;
         kb_end = (p.K + kBlockK - 1) / kBlockK;
+    }
+}
+
+// ---- staged epilogue of ONE accumulator tile (TMEM -> registers -> swizzled smem tile -> TMA store / reduce-add) ----
+// `acc_tmem` = TMEM address of this warp's lane quadrant at the accumulator stage; `rbase` = first output row of the
+// warp; `empty_bar` is arrived on once every TMEM read of the tile has completed (REMOTE: it is a shared::cluster
+// address in the leader CTA of a 2-CTA pair).
+template <int BLOCK_N, bool WGRAD, bool REMOTE>
+__device__ __forceinline__ void staged_tile_epilogue(const GemmParams& p, const CUtensorMap* tmC, uint32_t acc_tmem,
+                                                     int rbase, int col0, int lane, uint32_t stg0, uint32_t& buf,
+                                                     uint32_t empty_bar, float* stat_smem, bool use_smem_stats) {
+    constexpr int CW = WGRAD ? 32 : 64;                 // columns per staging tile (128-byte rows)
+    const uint32_t lane_row = (uint32_t)lane * 128u;
+    const uint32_t sw = (uint32_t)(lane & 7);
+    const int ncols = min(BLOCK_N, p.N - col0);
+    const int n_chunks = (ncols + CW - 1) / CW;
+#pragma unroll 1
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        const int n_base = col0 + ch * CW;
+        const uint32_t stg = stg0 + buf * kEpiBufBytes;
+        if (lane == 0) tma_wait_group_read<1>();    // the store that last read this buffer has drained it
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < CW / 32; ++h) {
+            uint32_t raw[32];
+            tc_ld_32x32b_x32(acc_tmem + (uint32_t)(ch * CW + h * 32), raw);
+            if (ch == n_chunks - 1 && h == CW / 32 - 1) {
+                // every TMEM read of this accumulator stage has completed: hand it back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (REMOTE) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(empty_bar) : "memory");
+                    else mbar_arrive(empty_bar);
+                }
+            }
+            if (WGRAD) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane_row + (((uint32_t)j ^ sw) << 4)),
+                                 "r"(raw[4 * j]), "r"(raw[4 * j + 1]), "r"(raw[4 * j + 2]), "r"(raw[4 * j + 3]) : "memory");
+            } else {
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+                if (p.col_scale != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = min(n_base + h * 32 + j, p.N - 1);
+                        v[j] = fmaf(v[j], __ldg(p.col_scale + n), __ldg(p.col_shift + n));
+                    }
+                }
+                if (p.act != DLV3P_ACT_NONE) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint32_t o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        __nv_bfloat162 pr = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+                        o[e] = *reinterpret_cast<uint32_t*>(&pr);
+                    }
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane_row + (((uint32_t)(h * 4 + g) ^ sw) << 4)),
+                                 "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+                }
+            }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && rbase < (WGRAD ? p.K : p.M)) {
+            if (WGRAD) tma_reduce_add_2d(tmC, stg, n_base, rbase);
+            else tma_store_2d(tmC, stg, n_base, rbase);
+            tma_commit_group();
+        }
+        if (!WGRAD && p.col_stats != nullptr) {
+            // BatchNormalization batch statistics of the STORED (bf16) conv output: lane L owns columns
+            // n_base+2L, n_base+2L+1 and walks the 32 rows of the staging tile (one 32-bit word per row,
+            // all 32 banks distinct); rows >= M hold exact zeros (TMA zero-filled A)
+            float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
+            const uint32_t cj = (uint32_t)(lane >> 2), cw = (uint32_t)(lane & 3) << 2;
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) {
+                uint32_t word;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word)
+                             : "r"(stg + (uint32_t)rr * 128u + ((cj ^ (uint32_t)(rr & 7)) << 4) + cw));
+                const float a = __uint_as_float(word << 16), b = __uint_as_float(word & 0xffff0000u);
+                s1a += a; s2a = fmaf(a, a, s2a);
+                s1b += b; s2b = fmaf(b, b, s2b);
+            }
+            const int col = n_base + 2 * lane;
+            if (use_smem_stats) {
+                if (col < p.N) { atomicAdd(stat_smem + col, s1a); atomicAdd(stat_smem + kMaxStatCols + col, s2a); }
+                if (col + 1 < p.N) { atomicAdd(stat_smem + col + 1, s1b); atomicAdd(stat_smem + kMaxStatCols + col + 1, s2b); }
+            } else {
+                if (col < p.N) { atomicAdd(p.col_stats + col, s1a); atomicAdd(p.col_stats + p.N + col, s2a); }
+                if (col + 1 < p.N) { atomicAdd(p.col_stats + col + 1, s1b); atomicAdd(p.col_stats + p.N + col + 1, s2b); }
+            }
+        }
+        buf ^= 1u;
     }
 }
 
@@ -232,11 +334,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int row_limit = WGRAD ? p.K : p.M;
         const bool use_smem_stats = (!WGRAD) && (p.col_stats != nullptr) && (p.N <= kMaxStatCols);
         if (p.tma_store) {
-            // ---- staged epilogue: TMEM -> registers -> swizzled smem tile -> TMA store / reduce-add ----
-            constexpr int CW = WGRAD ? 32 : 64;                 // columns per staging tile (128-byte rows)
             const uint32_t stg0 = smem_u32(epi_bytes) + (uint32_t)q * 2u * kEpiBufBytes;
-            const uint32_t lane_row = (uint32_t)lane * 128u;
-            const uint32_t sw = (uint32_t)(lane & 7);
             uint32_t buf = 0, t = 0;
             for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++t) {
                 int row0, col0, kb_begin, kb_end;
@@ -244,92 +342,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t as = t & 1u;
                 mbar_wait(tmem_full_bar + 8 * as, (t >> 1) & 1u);
                 tc_fence_after();
-                const int rbase = row0 + q * 32;
-                const int ncols = min(BLOCK_N, p.N - col0);
-                const int n_chunks = (ncols + CW - 1) / CW;
-#pragma unroll 1
-                for (int ch = 0; ch < n_chunks; ++ch) {
-                    const int n_base = col0 + ch * CW;
-                    const uint32_t stg = stg0 + buf * kEpiBufBytes;
-                    if (lane == 0) tma_wait_group_read<1>();    // the store that last read this buffer has drained it
-                    __syncwarp();
-#pragma unroll
-                    for (int h = 0; h < CW / 32; ++h) {
-                        uint32_t raw[32];
-                        tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N +
-                                             (uint32_t)(ch * CW + h * 32), raw);
-                        if (ch == n_chunks - 1 && h == CW / 32 - 1) {
-                            // every TMEM read of this accumulator stage has completed: hand it back to the MMA warp
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(tmem_empty_bar + 8 * as);
-                        }
-                        if (WGRAD) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane_row + (((uint32_t)j ^ sw) << 4)),
-                                             "r"(raw[4 * j]), "r"(raw[4 * j + 1]), "r"(raw[4 * j + 2]), "r"(raw[4 * j + 3]) : "memory");
-                        } else {
-                            float v[32];
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-                            if (p.col_scale != nullptr) {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) {
-                                    const int n = min(n_base + h * 32 + j, p.N - 1);
-                                    v[j] = fmaf(v[j], __ldg(p.col_scale + n), __ldg(p.col_shift + n));
-                                }
-                            }
-                            if (p.act != DLV3P_ACT_NONE) {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
-                            }
-#pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                uint32_t o[4];
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    __nv_bfloat162 pr = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
-                                    o[e] = *reinterpret_cast<uint32_t*>(&pr);
-                                }
-                                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane_row + (((uint32_t)(h * 4 + g) ^ sw) << 4)),
-                                             "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
-                            }
-                        }
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0 && rbase < (WGRAD ? p.K : p.M)) {
-                        if (WGRAD) tma_reduce_add_2d(&tmC, stg, n_base, rbase);
-                        else tma_store_2d(&tmC, stg, n_base, rbase);
-                        tma_commit_group();
-                    }
-                    if (!WGRAD && p.col_stats != nullptr) {
-                        // BatchNormalization batch statistics of the STORED (bf16) conv output: lane L owns columns
-                        // n_base+2L, n_base+2L+1 and walks the 32 rows of the staging tile (one 32-bit word per row,
-                        // all 32 banks distinct); rows >= M hold exact zeros (TMA zero-filled A)
-                        float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
-                        const uint32_t cj = (uint32_t)(lane >> 2), cw = (uint32_t)(lane & 3) << 2;
-#pragma unroll 8
-                        for (int rr = 0; rr < 32; ++rr) {
-                            uint32_t word;
-                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word)
-                                         : "r"(stg + (uint32_t)rr * 128u + ((cj ^ (uint32_t)(rr & 7)) << 4) + cw));
-                            const float a = __uint_as_float(word << 16), b = __uint_as_float(word & 0xffff0000u);
-                            s1a += a; s2a = fmaf(a, a, s2a);
-                            s1b += b; s2b = fmaf(b, b, s2b);
-                        }
-                        const int col = n_base + 2 * lane;
-                        if (use_smem_stats) {
-                            if (col < p.N) { atomicAdd(stat_smem + col, s1a); atomicAdd(stat_smem + kMaxStatCols + col, s2a); }
-                            if (col + 1 < p.N) { atomicAdd(stat_smem + col + 1, s1b); atomicAdd(stat_smem + kMaxStatCols + col + 1, s2b); }
-                        } else {
-                            if (col < p.N) { atomicAdd(p.col_stats + col, s1a); atomicAdd(p.col_stats + p.N + col, s2a); }
-                            if (col + 1 < p.N) { atomicAdd(p.col_stats + col + 1, s1b); atomicAdd(p.col_stats + p.N + col + 1, s2b); }
-                        }
-                    }
-                    buf ^= 1u;
-                }
+                staged_tile_epilogue<BLOCK_N, WGRAD, false>(p, &tmC, tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N,
+                                                            row0 + q * 32, col0, lane, stg0, buf, tmem_empty_bar + 8 * as,
+                                                            stat_smem, use_smem_stats);
             }
             if (lane == 0) tma_wait_group_all();
         } else {
@@ -481,6 +496,191 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// =====================================================================================================================
+// 2-CTA variant (forward / input-gradient GEMMs with N > 128): a cluster of two CTAs on one TPC computes a 256 x 256
+// output tile with tcgen05.mma.cta_group::2 (UMMA M = 256).  Each CTA stages its own 128 rows of A and HALF of the B
+// tile (128 of the 256 output channels), so per CTA a k-block costs 16 + 16 KB of TMA writes and 4 + 4 KB of tensor-core
+// operand reads instead of 16 + 32 and 4 + 8: the single-CTA kernel is bound by shared-memory bandwidth (ncu: tensor
+// pipe 35 % active, MMA queue always full, L2 / DRAM far from saturated — profiles/r1_gemm728_v2_*).
+//   * both CTAs run a TMA producer (own A rows, own B half) that signals the LEADER's full barrier;
+//   * only the leader issues MMAs; tcgen05.commit multicasts the "slot free" / "accumulator ready" arrivals to the
+//     barriers of both CTAs;
+//   * each CTA's epilogue warps drain their own 128 accumulator rows from their own TMEM and arrive (remotely for the
+//     peer) on the leader's "accumulator free" barrier.
+// =====================================================================================================================
+constexpr int kStages2 = 5;            // 5 x 32 KB operand ring per CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+    constexpr int A_BYTES = kBlockM * kBlockK * 2;               // this CTA's 128 rows
+    constexpr int B_BYTES = (BLOCK_N / 2) * kBlockK * 2;         // this CTA's half of the output channels
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* epi_bytes = smem + kStages2 * STAGE_BYTES;
+    float* stat_smem = reinterpret_cast<float*>(epi_bytes + kEpiBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_bytes + kEpiBytes + 2 * kMaxStatCols * 4);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t full_bar = smem_u32(bars);                        // kStages2 (used in the leader only)
+    const uint32_t empty_bar = smem_u32(bars + kStages2);            // kStages2 (one per CTA, multicast arrivals)
+    const uint32_t tmem_full_bar = smem_u32(bars + 2 * kStages2);    // 2 (per CTA, multicast arrivals)
+    const uint32_t tmem_empty_bar = smem_u32(bars + 2 * kStages2 + 2);   // 2 (leader only, 8 arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages2 + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = (rank == 0);
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+    if (p.col_stats != nullptr)
+        for (int i = threadIdx.x; i < 2 * kMaxStatCols; i += kThreads) stat_smem[i] = 0.f;
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
+        for (int s = 0; s < kStages2; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + 8 * s, 1); mbar_init(tmem_empty_bar + 8 * s, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                      // barriers of both CTAs initialised, TMEM allocated in both
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+    const int num_work = p.n_tiles * p.m_tiles;          // 256 x BLOCK_N pair tiles, n fastest
+    const int num_kb = (p.K + kBlockK - 1) / kBlockK;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer (both CTAs): own A rows + own B half, completion on the LEADER's full barrier =====
+            const uint32_t leader_full = mapa_rank(full_bar, 0);
+            uint32_t it = 0;
+            for (int w = pair; w < num_work; w += num_pairs) {
+                const int row0 = (w / p.n_tiles) * (2 * kBlockM) + (int)rank * kBlockM;
+                const int col0 = (w % p.n_tiles) * BLOCK_N + (int)rank * (BLOCK_N / 2);
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const uint32_t s = it % kStages2;
+                    const uint32_t ph = (it / kStages2) & 1u;
+                    mbar_wait(empty_bar + 8 * s, ph ^ 1u);
+                    const uint32_t a_dst = smem_base + s * STAGE_BYTES;
+                    const uint32_t b_dst = a_dst + A_BYTES;
+                    if (leader) mbar_expect_tx(full_bar + 8 * s, 2 * STAGE_BYTES);     // both CTAs' boxes
+                    const uint32_t fb = leader_full + 8 * s;
+                    tma_load_2d_2sm(a_dst, &tmA, fb, kb * kBlockK, row0);
+                    tma_load_2d_2sm(b_dst, &tmB, fb, kb * kBlockK, col0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            // ===== MMA issuer (leader only) =====
+            constexpr uint32_t idesc = (1u << 4) /*D=f32*/ | (1u << 7) /*A=bf16*/ | (1u << 10) /*B=bf16*/ |
+                                       ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)((2 * kBlockM) >> 4) << 24);
+            uint32_t it = 0, t = 0;
+            for (int w = pair; w < num_work; w += num_pairs, ++t) {
+                const uint32_t as = t & 1u;
+                mbar_wait(tmem_empty_bar + 8 * as, ((t >> 1) & 1u) ^ 1u);   // both CTAs' epilogues drained this stage
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const uint32_t s = it % kStages2;
+                    const uint32_t ph = (it / kStages2) & 1u;
+                    mbar_wait(full_bar + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t a_src = smem_base + s * STAGE_BYTES;
+                    const uint32_t b_src = a_src + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        const uint64_t ad = umma_desc(a_src + k * 32, 16, 1024);
+                        const uint64_t bd = umma_desc(b_src + k * 32, 16, 1024);
+                        tc_mma_bf16_2sm(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    tc_commit_2sm(empty_bar + 8 * s);          // slot reusable in BOTH CTAs once these MMAs retire
+                }
+                tc_commit_2sm(tmem_full_bar + 8 * as);         // accumulator stage complete in BOTH CTAs
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs): warps 2..5, TMEM lane quadrant = warp % 4 =====
+        const int q = warp & 3;
+        const bool use_smem_stats = (p.col_stats != nullptr) && (p.N <= kMaxStatCols);
+        const uint32_t stg0 = smem_u32(epi_bytes) + (uint32_t)q * 2u * kEpiBufBytes;
+        const uint32_t leader_tmem_empty = mapa_rank(tmem_empty_bar, 0);
+        uint32_t buf = 0, t = 0;
+        for (int w = pair; w < num_work; w += num_pairs, ++t) {
+            const int row0 = (w / p.n_tiles) * (2 * kBlockM) + (int)rank * kBlockM;
+            const int col0 = (w % p.n_tiles) * BLOCK_N;
+            const uint32_t as = t & 1u;
+            mbar_wait(tmem_full_bar + 8 * as, (t >> 1) & 1u);
+            tc_fence_after();
+            staged_tile_epilogue<BLOCK_N, false, true>(p, &tmC, tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N,
+                                                       row0 + q * 32, col0, lane, stg0, buf, leader_tmem_empty + 8 * as,
+                                                       stat_smem, use_smem_stats);
+        }
+        if (lane == 0) tma_wait_group_all();
+        if (use_smem_stats) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");    // the four epilogue warps only
+            const int e = threadIdx.x - 64;
+            for (int c = e; c < p.N; c += 128) {
+                const float a1 = stat_smem[c], a2 = stat_smem[kMaxStatCols + c];
+                if (a1 != 0.f || a2 != 0.f) {
+                    atomicAdd(p.col_stats + c, a1);
+                    atomicAdd(p.col_stats + p.N + c, a2);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                      // neither CTA may exit (or free TMEM) while its peer still uses it
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 // ---- host side --------------------------------------------------------------------------------------------------
 template <int BLOCK_N, bool WGRAD>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
@@ -497,6 +697,27 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     gemm_tc_kernel<BLOCK_N, WGRAD><<<grid, kThreads, smem, st>>>(tmA, tmB, tmC, p);
     return check_launch(WGRAD ? "gemm_wgrad_bf16" : "gemm_bf16");
 }
+
+template <int BLOCK_N>
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, GemmParams p,
+                        cudaStream_t st) {
+    constexpr int smem = kStages2 * (kBlockM * kBlockK * 2 + (BLOCK_N / 2) * kBlockK * 2) + kEpiBytes +
+                         2 * kMaxStatCols * 4 + 1024 + 256;
+    static_assert(smem <= 232448, "shared memory budget");
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        DLV3P_REQUIRE(e == cudaSuccess, DLV3P_ERR_CUDA, "cudaFuncSetAttribute(2-CTA smem=%d): %s", smem, cudaGetErrorString(e));
+        configured = true;
+    }
+    p.m_tiles = cdiv(p.M, 2 * kBlockM);
+    const int work = p.n_tiles * p.m_tiles;
+    const int pairs = work < kNumSMs / 2 ? work : kNumSMs / 2;
+    gemm_tc2_kernel<BLOCK_N><<<2 * pairs, kThreads, smem, st>>>(tmA, tmB, tmC, p);
+    return check_launch("gemm_bf16 (2-CTA)");
+}
+
+static int g_gemm_2cta = -1;      // DLV3P_GEMM_2CTA=0 disables the 2-CTA path (A/B measurements)
 
 }  // namespace dlv3p
 
@@ -529,6 +750,14 @@ extern "C" int dlv3p_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
     if (p.tma_store) {
         rc = make_tmap(&tmC, C, N, M, ldc, 64, 32);
         if (rc) return rc;
+    }
+    if (g_gemm_2cta < 0) { const char* e = getenv("DLV3P_GEMM_2CTA"); g_gemm_2cta = (e && e[0] == '0') ? 0 : 1; }
+    // (short reductions are epilogue-bound and gain nothing from pairing: measured 64 vs 51 us at M=258064 N=K=256)
+    if (g_gemm_2cta && bn == 256 && p.tma_store && M >= 2 * kBlockM && K >= 512) {
+        // 2-CTA pairs: every CTA loads half of the B tile (128 rows of the [N,K] operand)
+        rc = make_tmap(&tmB, B, K, N, ldb, kBlockK, bn / 2);
+        if (rc) return rc;
+        return launch_gemm2<256>(tmA, tmB, tmC, p, st);
     }
     switch (bn) {
         case 32: return launch_gemm<32, false>(tmA, tmB, tmC, p, st);
