@@ -249,12 +249,13 @@ bn_bwd_apply_kernel(const T* __restrict__ dz, long long ld_dz, const T* __restri
     }
 }
 
-template <typename T, int CVB>
-__global__ void __launch_bounds__(256)
+template <typename T, int CVB, int ACT, bool HAS_ADD>
+__global__ void __launch_bounds__(256, HAS_ADD ? 2 : 3)
 affine_act_rows_kernel(const T* __restrict__ y, long long ld_y, const float* __restrict__ scale,
-                       const float* __restrict__ shift, int act, const T* __restrict__ addend, long long ld_a,
+                       const float* __restrict__ shift, const T* __restrict__ addend, long long ld_a,
                        T* __restrict__ out, long long ld_o, long long M, int C, long long rows_per_block) {
     constexpr int PL = 256 / CVB;
+    constexpr int U = 4;
     const int tx = threadIdx.x % CVB, ty = threadIdx.x / CVB;
     const int cv = blockIdx.x * CVB + tx;
     if (cv >= (C >> 3)) return;
@@ -267,31 +268,36 @@ affine_act_rows_kernel(const T* __restrict__ y, long long ld_y, const float* __r
     }
     const long long r0 = (long long)blockIdx.y * rows_per_block;
     long long r1 = r0 + rows_per_block; if (r1 > M) r1 = M;
-    for (long long r = r0 + ty; r < r1; r += 2 * PL) {
-        const bool two = (r + PL < r1);
-        Vec8<T> a0, a1, d0, d1;
-        a0.load_stream(y + r * ld_y + c0);
-        if (two) a1.load_stream(y + (r + PL) * ld_y + c0);
-        if (addend != nullptr) {
-            d0.load_stream(addend + r * ld_a + c0);
-            if (two) d1.load_stream(addend + (r + PL) * ld_a + c0);
-        }
-        float f0[8], f1[8], e0[8], e1[8];
-        a0.to_float(f0);
-        if (two) a1.to_float(f1);
+    for (long long r = r0 + ty; r < r1; r += U * PL) {
+        Vec8<T> a[U], d[U];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            f0[k] = apply_act(fmaf(f0[k], sc[k], sh[k]), act);
-            if (two) f1[k] = apply_act(fmaf(f1[k], sc[k], sh[k]), act);
+        for (int u = 0; u < U; ++u) {
+            const long long rr = r + u * PL;
+            if (rr < r1) {
+                a[u].load_stream(y + rr * ld_y + c0);
+                if (HAS_ADD) d[u].load_stream(addend + rr * ld_a + c0);
+            }
         }
-        if (addend != nullptr) {
-            d0.to_float(e0);
-            if (two) d1.to_float(e1);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { f0[k] += e0[k]; if (two) f1[k] += e1[k]; }
+        for (int u = 0; u < U; ++u) {
+            const long long rr = r + u * PL;
+            if (rr < r1) {
+                float f[8]; a[u].to_float(f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    f[k] = fmaf(f[k], sc[k], sh[k]);
+                    if (ACT == DLV3P_ACT_RELU) f[k] = fmaxf(f[k], 0.f);
+                    if (ACT == DLV3P_ACT_RELU6) f[k] = fminf(fmaxf(f[k], 0.f), 6.f);
+                }
+                if (HAS_ADD) {
+                    float e[8]; d[u].to_float(e);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) f[k] += e[k];
+                }
+                Vec8<T> o; o.from_float(f);
+                o.store(out + rr * ld_o + c0);
+            }
         }
-        Vec8<T> o0; o0.from_float(f0); o0.store(out + r * ld_o + c0);
-        if (two) { Vec8<T> o1; o1.from_float(f1); o1.store(out + (r + PL) * ld_o + c0); }
     }
 }
 
@@ -794,13 +800,18 @@ cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long n) {
     if (i < n) y[i] = from_f<TO>(to_f<TI>(x[i]));
 }
 
-static void col_reduce_grid(int CV, int CVB, long long M, int& gx, int& gy, long long& rpb, int waves = 3, int unroll = 2) {
+// One wave of long-lived blocks: gx column groups x gy row ranges with gx*gy <= 148 * blocks-per-SM, so that no
+// second, mostly empty wave runs (ncu: 384 blocks at 2 blocks/SM = 1.3 waves cost two full rounds) and every block
+// ends with a single set of atomics.  rows-per-block is a multiple of the row lanes PL (ragged tails are predicated).
+static void col_reduce_grid(int CV, int CVB, long long M, int& gx, int& gy, long long& rpb, int blocks_per_sm = 2,
+                            int unroll = 1) {
+    (void)unroll;
     gx = cdiv(CV, CVB);
     const int PL = 256 / CVB;
-    long long want = (long long)kNumSMs * waves / gx; if (want < 1) want = 1;
+    long long want = (long long)kNumSMs * blocks_per_sm / gx; if (want < 1) want = 1;
     rpb = (M + want - 1) / want;
-    rpb = ((rpb + unroll * PL - 1) / (unroll * PL)) * (unroll * PL);
-    if (rpb < unroll * PL) rpb = unroll * PL;
+    rpb = ((rpb + PL - 1) / PL) * PL;
+    if (rpb < PL) rpb = PL;
     gy = cdiv(M, rpb);
 }
 
@@ -824,7 +835,7 @@ extern "C" int dlv3p_bn_stats(const void* y, int64_t ld, int64_t M, int C, float
         pick_cvb(C / 8, [&](auto cvb) {
             constexpr int CVB = decltype(cvb)::value;
             int gx, gy; long long rpb;
-            col_reduce_grid(C / 8, CVB, M, gx, gy, rpb);
+            col_reduce_grid(C / 8, CVB, M, gx, gy, rpb, 4);
             bn_stats_kernel<T, CVB><<<dim3(gx, gy), 256, 0, st>>>((const T*)y, ld, M, C, sums, rpb);
         });
         return check_launch("bn_stats");
@@ -853,6 +864,9 @@ extern "C" int dlv3p_bn_fold(const float* gamma, const float* beta, const float*
     return check_launch("bn_fold");
 }
 
+#define DLV3P_AFF(A, AD) affine_act_rows_kernel<T, CVB, A, AD><<<dim3(gx, gy), 256, 0, st>>>((const T*)y, ld_y, scale, shift, \
+                                                                             (const T*)addend, ld_addend, (T*)out, ld_out, M, C, rpb)
+
 extern "C" int dlv3p_affine_act(const void* y, int64_t ld_y, const float* scale, const float* shift, int act,
                                 const void* addend, int64_t ld_addend, void* out, int64_t ld_out, int64_t M, int C,
                                 int dtype, void* stream) {
@@ -865,10 +879,12 @@ extern "C" int dlv3p_affine_act(const void* y, int64_t ld_y, const float* scale,
             pick_cvb(C / 8, [&](auto cvb) {
                 constexpr int CVB = decltype(cvb)::value;
                 int gx, gy; long long rpb;
-                col_reduce_grid(C / 8, CVB, M, gx, gy, rpb, 16);
-                affine_act_rows_kernel<T, CVB><<<dim3(gx, gy), 256, 0, st>>>((const T*)y, ld_y, scale, shift, act,
-                                                                             (const T*)addend, ld_addend, (T*)out,
-                                                                             ld_out, M, C, rpb);
+                col_reduce_grid(C / 8, CVB, M, gx, gy, rpb, addend ? 2 : 3);
+                if (addend) {
+                    if (act == DLV3P_ACT_NONE) DLV3P_AFF(0, true); else if (act == DLV3P_ACT_RELU) DLV3P_AFF(1, true); else DLV3P_AFF(2, true);
+                } else {
+                    if (act == DLV3P_ACT_NONE) DLV3P_AFF(0, false); else if (act == DLV3P_ACT_RELU) DLV3P_AFF(1, false); else DLV3P_AFF(2, false);
+                }
             });
         } else {
             const long long total = M * C;
@@ -897,7 +913,7 @@ extern "C" int dlv3p_bn_bwd_reduce(const void* dz, int64_t ld_dz, const void* y,
         pick_cvb(C / 8, [&](auto cvb) {
             constexpr int CVB = decltype(cvb)::value;
             int gx, gy; long long rpb;
-            col_reduce_grid(C / 8, CVB, M, gx, gy, rpb, 3, 4);
+            col_reduce_grid(C / 8, CVB, M, gx, gy, rpb, act == DLV3P_ACT_NONE ? 3 : 2);
             if (act == DLV3P_ACT_NONE) DLV3P_BNR(0); else if (act == DLV3P_ACT_RELU) DLV3P_BNR(1); else DLV3P_BNR(2);
         });
         return check_launch("bn_bwd_reduce");
@@ -918,7 +934,7 @@ extern "C" int dlv3p_bn_bwd_apply(const void* dz, int64_t ld_dz, const void* y, 
         pick_cvb(C / 8, [&](auto cvb) {
             constexpr int CVB = decltype(cvb)::value;
             int gx, gy; long long rpb;
-            col_reduce_grid(C / 8, CVB, M, gx, gy, rpb, 6, 4);
+            col_reduce_grid(C / 8, CVB, M, gx, gy, rpb, 2);
             if (act == DLV3P_ACT_NONE) DLV3P_BNA(0); else if (act == DLV3P_ACT_RELU) DLV3P_BNA(1); else DLV3P_BNA(2);
         });
         return check_launch("bn_bwd_apply");

@@ -350,9 +350,17 @@ def test_batchnorm_train(MC, dtype):
     # gradients w.r.t. beta / gamma recomputed from the same bf16-rounded forward
     g_eff = gz.double() * (z_ref.view(M, C) > 0).double()
     xhat = (y.double() - y.double().mean(0)) / torch.sqrt(y.double().var(0, unbiased=False) + eps)
-    check("bn dbeta", red[0], g_eff.sum(0), 2e-3, 2e-3 * math.sqrt(M))
-    check("bn dgamma", red[1], (g_eff * xhat).sum(0), 2e-3, 2e-3 * math.sqrt(M))
-    check("bn dx", dy, yr.grad.view(M, C), rt, at)
+    # a pre-activation within fp32 rounding of zero may land on either side of the ReLU (the batch mean depends on the
+    # summation order): such elements may flip, each moving a per-channel sum by |g| — budget exactly that
+    amb = (z_ref.view(M, C).abs() < 1e-5).detach()
+    slack = (gz.double().abs() * amb).sum(0)
+    for name, got, want, extra in (("bn dbeta", red[0], g_eff.sum(0), slack),
+                                   ("bn dgamma", red[1], (g_eff * xhat).sum(0), slack * xhat.abs().max())):
+        err = (got.double().cpu() - want).abs()
+        bound = 2e-3 * want.abs() + 2e-3 * math.sqrt(M) + 1.01 * extra
+        assert bool((err <= bound).all()), (name, float(err.max()), float(bound.min()))
+    keep = (~amb).double()
+    check("bn dx", dy.double().cpu() * keep, yr.grad.view(M, C) * keep, rt, at + float(slack.max()) * 8.0 / M)
 
 
 def test_bn_fold_inference():
