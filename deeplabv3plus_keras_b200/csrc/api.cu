@@ -1,5 +1,6 @@
 // Error plumbing and library identity for the C-ABI (include/dlv3p.h).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -21,6 +22,12 @@ int check_launch(const char* what) {
         return DLV3P_ERR_CUDA;
     }
     return DLV3P_OK;
+}
+
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("DLV3P_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on != 0;
 }
 
 }  // namespace dlv3p

@@ -7,6 +7,7 @@
 #include <string.h>
 #include <initializer_list>
 #include <type_traits>
+#include <utility>
 
 #include "../../include/dlv3p.h"
 
@@ -28,6 +29,30 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 static inline int  cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------
+// The hot kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization (also inside a captured CUDA
+// graph, where it becomes a programmatic edge): a kernel releases its dependents as soon as all of its CTAs are
+// resident (pdl_launch_dependents at the top), so the next kernel's CTAs are scheduled onto SMs as they drain and run
+// their prologue (barrier init, TMEM allocation, tensor-map prefetch) under the previous kernel's tail; pdl_wait()
+// then blocks until the previous kernel has completed and its writes are visible.  Every kernel launched this way
+// calls pdl_wait() before its first global-memory access.  DLV3P_PDL=0 in the environment disables the attribute.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);      // errors surface through check_launch()
+}
 
 // ---- element access: fp32 math, storage in T ------------------------------------------------
 template <typename T> struct Vec8;     // 8 elements of T (16 B for bf16, 32 B for fp32)

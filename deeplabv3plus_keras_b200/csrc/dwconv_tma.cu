@@ -103,6 +103,7 @@ dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
     const int cb = blockIdx.x / p.ctas_per_cb;
     const int gstride = p.ctas_per_cb;
     const int c0 = cb * kDwCB + cq * 4;
+    pdl_launch_dependents();
 
     if (tid == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_in)) : "memory");
@@ -112,6 +113,7 @@ dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    pdl_wait();
 
     auto decode = [&](int tile, int& n, int& th, int& tw) {
         tw = tile % p.tiles_w; const int t = tile / p.tiles_w;
@@ -264,7 +266,7 @@ static int launch_dw_tma_inst(const CUtensorMap& tm, const CUtensorMap& tmm, con
         DLV3P_REQUIRE(e == cudaSuccess, DLV3P_ERR_CUDA, "cudaFuncSetAttribute(dw tma smem=%d): %s", smem, cudaGetErrorString(e));
         configured = true;
     }
-    dw_conv_tma_kernel<IN_ACT, M_ACT, M_AFFINE, HAS_ADD><<<grid, kDwThreads, smem, st>>>(tm, tmm, tma, p);
+    launch_pdl(dw_conv_tma_kernel<IN_ACT, M_ACT, M_AFFINE, HAS_ADD>, dim3(grid), dim3(kDwThreads), smem, st, tm, tmm, tma, p);
     return check_launch("dwconv3x3 (tma)");
 }
 
@@ -352,6 +354,7 @@ dw_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     const int cb = blockIdx.x / p.ctas_per_cb;
     const int first = blockIdx.x % p.ctas_per_cb;
     const int gstride = p.ctas_per_cb;
+    pdl_launch_dependents();
 
     if (tid == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_x)) : "memory");
@@ -360,6 +363,7 @@ dw_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    pdl_wait();
 
     auto issue = [&](int tile, int s) {
         const int tw = tile % p.tiles_w; int t = tile / p.tiles_w;
@@ -475,9 +479,9 @@ int launch_dw_wgrad_tma(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* 
         DLV3P_REQUIRE(e == cudaSuccess, DLV3P_ERR_CUDA, "cudaFuncSetAttribute(dw wgrad tma smem=%d): %s", smem, cudaGetErrorString(e));
         configured = true;
     }
-    if (in_act == DLV3P_ACT_NONE) dw_wgrad_tma_kernel<0><<<tiles_c * per, kDwThreads, smem, st>>>(tmx, tmg, p);
-    else if (in_act == DLV3P_ACT_RELU) dw_wgrad_tma_kernel<1><<<tiles_c * per, kDwThreads, smem, st>>>(tmx, tmg, p);
-    else dw_wgrad_tma_kernel<2><<<tiles_c * per, kDwThreads, smem, st>>>(tmx, tmg, p);
+    if (in_act == DLV3P_ACT_NONE) launch_pdl(dw_wgrad_tma_kernel<0>, dim3(tiles_c * per), dim3(kDwThreads), smem, st, tmx, tmg, p);
+    else if (in_act == DLV3P_ACT_RELU) launch_pdl(dw_wgrad_tma_kernel<1>, dim3(tiles_c * per), dim3(kDwThreads), smem, st, tmx, tmg, p);
+    else launch_pdl(dw_wgrad_tma_kernel<2>, dim3(tiles_c * per), dim3(kDwThreads), smem, st, tmx, tmg, p);
     rc = check_launch("dwconv3x3_wgrad (tma)");
     return rc ? rc : 1;
 }

@@ -83,6 +83,8 @@ bn_bwd_reduce_kernel(const T* __restrict__ dz, long long ld_dz, const T* __restr
                      const float* __restrict__ scale, const float* __restrict__ shift,
                      const float* __restrict__ mean, const float* __restrict__ invstd, long long M, int C,
                      float* __restrict__ red, long long rows_per_block) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int PL = 256 / CVB;
     constexpr int U = 4;
     const int CV = C >> 3;
@@ -132,6 +134,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, const float* 
                                    float* __restrict__ moving_var, int C, double count, float eps, float momentum,
                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean,
                                    float* __restrict__ invstd, int update_moving) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     // the two sums are fp32; finish in fp64 so that E[x^2]-E[x]^2 does not lose more than the sums already did
@@ -202,6 +206,8 @@ bn_bwd_apply_kernel(const T* __restrict__ dz, long long ld_dz, const T* __restri
                     const float* __restrict__ mean, const float* __restrict__ invstd,
                     const float* __restrict__ red, long long M, int C, T* __restrict__ dy, long long ld_dy,
                     long long rows_per_block) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int PL = 256 / CVB;
     constexpr int U = 4;
     const int tx = threadIdx.x % CVB, ty = threadIdx.x / CVB;
@@ -254,6 +260,8 @@ __global__ void __launch_bounds__(256, HAS_ADD ? 2 : 3)
 affine_act_rows_kernel(const T* __restrict__ y, long long ld_y, const float* __restrict__ scale,
                        const float* __restrict__ shift, const T* __restrict__ addend, long long ld_a,
                        T* __restrict__ out, long long ld_o, long long M, int C, long long rows_per_block) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int PL = 256 / CVB;
     constexpr int U = 4;
     const int tx = threadIdx.x % CVB, ty = threadIdx.x / CVB;
@@ -717,6 +725,8 @@ weight_prep_kernel(const float* __restrict__ w, int K, int N, __nv_bfloat16* __r
                    __nv_bfloat16* __restrict__ wn, long long ldn) {
     // 32x32 smem tile transpose so both the read of w and the write of wt are coalesced
     __shared__ float tile[32][33];
+    pdl_launch_dependents();
+    pdl_wait();
     const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
     for (int r = ty; r < 32; r += 8) {
@@ -850,9 +860,8 @@ extern "C" int dlv3p_bn_finalize(const float* sums, const float* gamma, const fl
                   "bn_finalize: bad arguments");
     DLV3P_REQUIRE(!update_moving || (moving_mean && moving_var), DLV3P_ERR_SHAPE,
                   "bn_finalize: moving statistics required when update_moving");
-    bn_finalize_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, gamma, beta, moving_mean, moving_var,
-                                                                       C, count, eps, momentum, scale, shift, mean,
-                                                                       invstd, update_moving);
+    launch_pdl(bn_finalize_kernel, dim3(cdiv(C, 128)), dim3(128), 0, (cudaStream_t)stream, sums, gamma, beta, moving_mean,
+               moving_var, C, count, eps, momentum, scale, shift, mean, invstd, update_moving);
     return check_launch("bn_finalize");
 }
 
@@ -864,8 +873,8 @@ extern "C" int dlv3p_bn_fold(const float* gamma, const float* beta, const float*
     return check_launch("bn_fold");
 }
 
-#define DLV3P_AFF(A, AD) affine_act_rows_kernel<T, CVB, A, AD><<<dim3(gx, gy), 256, 0, st>>>((const T*)y, ld_y, scale, shift, \
-                                                                             (const T*)addend, ld_addend, (T*)out, ld_out, M, C, rpb)
+#define DLV3P_AFF(A, AD) launch_pdl(affine_act_rows_kernel<T, CVB, A, AD>, dim3(gx, gy), dim3(256), 0, st, (const T*)y, (long long)ld_y, \
+                                    scale, shift, (const T*)addend, (long long)ld_addend, (T*)out, (long long)ld_out, (long long)M, C, rpb)
 
 extern "C" int dlv3p_affine_act(const void* y, int64_t ld_y, const float* scale, const float* shift, int act,
                                 const void* addend, int64_t ld_addend, void* out, int64_t ld_out, int64_t M, int C,
@@ -897,10 +906,10 @@ extern "C" int dlv3p_affine_act(const void* y, int64_t ld_y, const float* scale,
     return 0;
 }
 
-#define DLV3P_BNR(A) bn_bwd_reduce_kernel<T, CVB, A><<<dim3(gx, gy), 256, 0, st>>>((const T*)dz, ld_dz, (const T*)y, ld_y, \
-                                                                      scale, shift, mean, invstd, M, C, red, rpb)
-#define DLV3P_BNA(A) bn_bwd_apply_kernel<T, CVB, A><<<dim3(gx, gy), 256, 0, st>>>((const T*)dz, ld_dz, (const T*)y, ld_y, \
-                                                                     scale, shift, mean, invstd, red, M, C, (T*)dy, ld_dy, rpb)
+#define DLV3P_BNR(A) launch_pdl(bn_bwd_reduce_kernel<T, CVB, A>, dim3(gx, gy), dim3(256), 0, st, (const T*)dz, (long long)ld_dz, \
+                                (const T*)y, (long long)ld_y, scale, shift, mean, invstd, (long long)M, C, red, rpb)
+#define DLV3P_BNA(A) launch_pdl(bn_bwd_apply_kernel<T, CVB, A>, dim3(gx, gy), dim3(256), 0, st, (const T*)dz, (long long)ld_dz, \
+                                (const T*)y, (long long)ld_y, scale, shift, mean, invstd, red, (long long)M, C, (T*)dy, (long long)ld_dy, rpb)
 
 extern "C" int dlv3p_bn_bwd_reduce(const void* dz, int64_t ld_dz, const void* y, int64_t ld_y, const float* scale,
                                    const float* shift, const float* mean, const float* invstd, int act, int64_t M,
@@ -1168,8 +1177,8 @@ extern "C" int dlv3p_weight_prep(const float* w, int K, int N, void* wt, int64_t
                                  void* stream) {
     DLV3P_REQUIRE(w && wt && K > 0 && N > 0 && ldt >= K && (wn == nullptr || ldn >= N), DLV3P_ERR_SHAPE,
                   "weight_prep: bad arguments");
-    weight_prep_kernel<<<dim3(cdiv(N, 32), cdiv(K, 32)), 256, 0, (cudaStream_t)stream>>>(
-        w, K, N, (__nv_bfloat16*)wt, ldt, (__nv_bfloat16*)wn, ldn);
+    launch_pdl(weight_prep_kernel, dim3(cdiv(N, 32), cdiv(K, 32)), dim3(256), 0, (cudaStream_t)stream, w, K, N,
+               (__nv_bfloat16*)wt, (long long)ldt, (__nv_bfloat16*)wn, (long long)ldn);
     return check_launch("weight_prep");
 }
 

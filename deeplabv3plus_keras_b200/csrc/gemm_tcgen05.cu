@@ -234,6 +234,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_launch_dependents();
 
     if (!WGRAD && p.col_stats != nullptr)
         for (int i = threadIdx.x; i < 2 * kMaxStatCols; i += kThreads) stat_smem[i] = 0.f;
@@ -254,6 +255,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    pdl_wait();                              // prologue done; the operands may still be in flight from the previous kernel
 
     const int num_work = p.n_tiles * p.m_tiles * (WGRAD ? p.splits : 1);
 
@@ -567,6 +569,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t rank = cluster_ctarank();
     const bool leader = (rank == 0);
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    pdl_launch_dependents();
 
     if (p.col_stats != nullptr)
         for (int i = threadIdx.x; i < 2 * kMaxStatCols; i += kThreads) stat_smem[i] = 0.f;
@@ -588,6 +591,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     cluster_sync_all();                      // barriers of both CTAs initialised, TMEM allocated in both
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    pdl_wait();
 
     const int num_work = p.n_tiles * p.m_tiles;          // 256 x BLOCK_N pair tiles, n fastest
     const int num_kb = (p.K + kBlockK - 1) / kBlockK;
@@ -694,7 +698,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     }
     const int work = p.n_tiles * p.m_tiles * (WGRAD ? p.splits : 1);
     const int grid = work < kNumSMs ? work : kNumSMs;         // persistent: one CTA per SM
-    gemm_tc_kernel<BLOCK_N, WGRAD><<<grid, kThreads, smem, st>>>(tmA, tmB, tmC, p);
+    launch_pdl(gemm_tc_kernel<BLOCK_N, WGRAD>, dim3(grid), dim3(kThreads), smem, st, tmA, tmB, tmC, p);
     return check_launch(WGRAD ? "gemm_wgrad_bf16" : "gemm_bf16");
 }
 
@@ -713,7 +717,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
     p.m_tiles = cdiv(p.M, 2 * kBlockM);
     const int work = p.n_tiles * p.m_tiles;
     const int pairs = work < kNumSMs / 2 ? work : kNumSMs / 2;
-    gemm_tc2_kernel<BLOCK_N><<<2 * pairs, kThreads, smem, st>>>(tmA, tmB, tmC, p);
+    launch_pdl(gemm_tc2_kernel<BLOCK_N>, dim3(2 * pairs), dim3(kThreads), smem, st, tmA, tmB, tmC, p);
     return check_launch("gemm_bf16 (2-CTA)");
 }
 
