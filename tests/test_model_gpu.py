@@ -229,3 +229,74 @@ def test_full_size_properties():
 def test_smoke_entry():
     import __graft_entry__
     __graft_entry__.smoke()
+
+
+GOLDEN = __import__("os").path.join(__import__("os").path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("name", ["xception_os16_65", "mobilenetv2_os16_65", "xception_os8_br_49"])
+def test_golden_fixtures_gpu(name):
+    """The CUDA path (fp32 mode) against the COMMITTED golden vectors (tests/golden/*.npz, scripts/make_golden.py):
+    no oracle code runs here — logits, loss and a sample of parameter gradients come straight from the fixture."""
+    from deeplabv3plus_keras_b200.engine import Plan
+    g = np.load(__import__("os").path.join(GOLDEN, name + ".npz"), allow_pickle=True)
+    conf = g["conf"].item()
+    ss = util.build(conf)
+    util.randomize_weights(ss.model, seed=int(g["weight_seed"]))
+    chk = float(sum(float(np.abs(v).sum()) for v in ss.model.named_weights().values()))
+    assert abs(chk - float(g["weight_checksum"])) < 1e-5 * float(g["weight_checksum"]), "numpy RNG stream changed"
+    plan = Plan(ss.model, g["x"].shape[0], training=True, dtype="float32")
+    plan.set_loss(list(g["pw"]), list(g["nw"]))
+    plan.load_batch(g["x"], g["y"])
+    plan.step_fwd_bwd()
+    plan.regularization()
+    torch.cuda.synchronize()
+    got = plan.logits.buf.float().cpu().numpy()
+    ref = g["logits"]
+    assert np.abs(got - ref).max() < 1e-3 * np.abs(ref).max()
+    assert (got.argmax(-1) == ref.argmax(-1)).mean() >= 0.999
+    assert abs(plan.loss_value() - float(g["loss"]) - float(g["l2"])) < 1e-4 * max(1.0, abs(float(g["loss"])))
+    lam = conf["hps"]["weight_decay"]
+    mine = plan.gradients()
+    named = ss.model.named_weights()
+    for k in g["grad_keys"]:
+        k = str(k)
+        want = g["grad/" + k].copy()
+        if k.endswith("/kernel") and k.split("/")[0].startswith("conv2d"):
+            want -= 2 * lam * named[k]          # the product applies the L2 term inside the Adam kernel
+        if np.abs(want).max() < 1e-9:
+            continue
+        assert rms_rel(mine[k], want) < 5e-2, (k, rms_rel(mine[k], want))
+
+
+def test_other_baseline_configs_full_geometry():
+    """BASELINE cfg-4 (Xception OS8, rate multiplier 2, boundary refinement, 513^2, fwd+bwd) and cfg-5 (MobileNetV2
+    OS16, 1024x2048, 19 classes, inference) at full image size (reduced batch): the reference graph's geometry,
+    finite values, probabilities summing to one, a loss that decreases."""
+    from deeplabv3plus_keras_b200.trainer import Trainer
+    conf = util.make_conf(base="xception", output_stride=8, image_size=513, refine=True, rate_mult=2, dtype="bfloat16")
+    ss = util.build(conf)
+    util.randomize_weights(ss.model)
+    ss.model.optimizer.lr = 1e-3
+    tr = Trainer(ss.model, 2, use_graph=True)
+    assert tr.plan.out_shape == (2, 512, 512, 21)           # 513 -> 64x64 features -> x4 -> x2 (ss.py:899-908)
+    x, y = util.synthetic_batch(conf, 2, (512, 512))
+    xs, ys = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
+    losses = [tr.train_step_e2e(xs, ys) for _ in range(5)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+
+    conf = util.make_conf(base="mobilenetv2", output_stride=16, image_size=[1024, 2048], num_classes=19,
+                          dtype="bfloat16")
+    f = np.random.default_rng(7).dirichlet(np.ones(19))
+    conf["class_weights"] = {"pos": list(1.0 - f), "neg": list(f)}
+    ss = util.build(conf)
+    util.randomize_weights(ss.model)
+    plan = ss.model.plan(1, training=False)
+    assert plan.out_shape == (1, 1024, 2048, 19)
+    x, _ = util.synthetic_batch(conf, 1, (1024, 2048))
+    plan.load_batch(x)
+    probs = plan.predict_device()
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(probs).all()) and float((probs.sum(-1) - 1).abs().max()) < 1e-5
+    lab = plan.segment(x)
+    assert lab.shape == (1, 1024, 2048) and 0 <= lab.min() and lab.max() <= 18
