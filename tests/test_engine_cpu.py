@@ -71,3 +71,26 @@ def test_inference_matches_oracle(cpu_engine):
     assert probs.shape == (1, 80, 80, 21)            # 65 -> 5x5 features -> x16 (the reference's own arithmetic)
     np.testing.assert_allclose(probs, out["probs"].numpy(), rtol=1e-3, atol=1e-5)
     assert (plan.segment(x) == out["probs"].argmax(-1).numpy()).mean() >= 0.999
+
+
+def test_weight_npz_round_trip(tmp_path):
+    """save_weights_npz / load_weights_npz move every weight by its tf.keras layer name (checkpoint / resume path of
+    the reference: ModelCheckpoint + model_loading, ss.py:482-485, 983-986)."""
+    import numpy as np
+    from deeplabv3plus_keras_b200 import SemanticSegmentation
+    from deeplabv3plus_keras_b200.utils import load_weights_npz, save_weights_npz
+    from tests import util
+    conf = util.make_conf(base="mobilenetv2", image_size=33, width=32)
+    a = util.build(conf)
+    util.randomize_weights(a.model, seed=5)
+    path = str(tmp_path / "semantic_segmentation_deeplabv3plus.npz")
+    save_weights_npz(a.model, path)
+    b = util.build(conf)
+    rep = load_weights_npz(b.model, path)
+    assert set(rep.values()) == {"loaded"} and "Conv1/kernel" in rep and "bn_Conv1/moving_variance" in rep
+    for k, v in a.model.named_weights().items():
+        np.testing.assert_array_equal(v, b.model.named_weights()[k])
+    conf2 = dict(conf, model_loading=True, resource_path=str(tmp_path))
+    c = util.build(conf2)                                   # the reference's resume switch
+    np.testing.assert_array_equal(c.model.named_weights()["Conv1/kernel"], a.model.named_weights()["Conv1/kernel"])
+    assert SemanticSegmentation is type(c)
