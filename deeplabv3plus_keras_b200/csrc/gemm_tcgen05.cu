@@ -545,7 +545,7 @@ __device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t tmem_d, uint64_t adesc,
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool WGRAD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
@@ -571,7 +571,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
     pdl_launch_dependents();
 
-    if (p.col_stats != nullptr)
+    if (!WGRAD && p.col_stats != nullptr)
         for (int i = threadIdx.x; i < 2 * kMaxStatCols; i += kThreads) stat_smem[i] = 0.f;
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -593,8 +593,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     pdl_wait();
 
-    const int num_work = p.n_tiles * p.m_tiles;          // 256 x BLOCK_N pair tiles, n fastest
-    const int num_kb = (p.K + kBlockK - 1) / kBlockK;
+    // forward: 256 x BLOCK_N pair tiles, n fastest.  filter gradient: (pixel-range split) x (tile), split-major; rows =
+    // input channels (p.K), columns = output channels (p.N), reduction over the p.M pixels
+    const int tiles = p.n_tiles * p.m_tiles;
+    const int num_work = tiles * (WGRAD ? p.splits : 1);
+    const int total_kb = ((WGRAD ? p.M : p.K) + kBlockK - 1) / kBlockK;
+    auto kb_range = [&](int w, int& kb0, int& kb1) {
+        if (WGRAD) { kb0 = (w / tiles) * p.kb_per_split; kb1 = min(kb0 + p.kb_per_split, total_kb); }
+        else { kb0 = 0; kb1 = total_kb; }
+    };
 
     if (warp == 0) {
         if (lane == 0) {
@@ -602,9 +609,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t leader_full = mapa_rank(full_bar, 0);
             uint32_t it = 0;
             for (int w = pair; w < num_work; w += num_pairs) {
-                const int row0 = (w / p.n_tiles) * (2 * kBlockM) + (int)rank * kBlockM;
-                const int col0 = (w % p.n_tiles) * BLOCK_N + (int)rank * (BLOCK_N / 2);
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int tile = w % tiles;
+                const int row0 = (tile / p.n_tiles) * (2 * kBlockM) + (int)rank * kBlockM;
+                const int col0 = (tile % p.n_tiles) * BLOCK_N + (int)rank * (BLOCK_N / 2);
+                int kb0, kb1;
+                kb_range(w, kb0, kb1);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const uint32_t s = it % kStages2;
                     const uint32_t ph = (it / kStages2) & 1u;
                     mbar_wait(empty_bar + 8 * s, ph ^ 1u);
@@ -612,8 +622,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const uint32_t b_dst = a_dst + A_BYTES;
                     if (leader) mbar_expect_tx(full_bar + 8 * s, 2 * STAGE_BYTES);     // both CTAs' boxes
                     const uint32_t fb = leader_full + 8 * s;
-                    tma_load_2d_2sm(a_dst, &tmA, fb, kb * kBlockK, row0);
-                    tma_load_2d_2sm(b_dst, &tmB, fb, kb * kBlockK, col0);
+                    if (WGRAD) {
+                        // MN-major operands: boxes of 64 channels (inner, 128 B) x 64 pixels
+#pragma unroll
+                        for (int h = 0; h < kBlockM / 64; ++h)
+                            tma_load_2d_2sm(a_dst + h * 8192, &tmA, fb, row0 + 64 * h, kb * kBlockK);
+#pragma unroll
+                        for (int h = 0; h < BLOCK_N / 2 / 64; ++h)
+                            tma_load_2d_2sm(b_dst + h * 8192, &tmB, fb, col0 + 64 * h, kb * kBlockK);
+                    } else {
+                        tma_load_2d_2sm(a_dst, &tmA, fb, kb * kBlockK, row0);
+                        tma_load_2d_2sm(b_dst, &tmB, fb, kb * kBlockK, col0);
+                    }
                 }
             }
         }
@@ -621,14 +641,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (lane == 0 && leader) {
             // ===== MMA issuer (leader only) =====
             constexpr uint32_t idesc = (1u << 4) /*D=f32*/ | (1u << 7) /*A=bf16*/ | (1u << 10) /*B=bf16*/ |
+                                       ((WGRAD ? 1u : 0u) << 15) | ((WGRAD ? 1u : 0u) << 16) |
                                        ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)((2 * kBlockM) >> 4) << 24);
             uint32_t it = 0, t = 0;
             for (int w = pair; w < num_work; w += num_pairs, ++t) {
+                int kb0, kb1;
+                kb_range(w, kb0, kb1);
                 const uint32_t as = t & 1u;
                 mbar_wait(tmem_empty_bar + 8 * as, ((t >> 1) & 1u) ^ 1u);   // both CTAs' epilogues drained this stage
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const uint32_t s = it % kStages2;
                     const uint32_t ph = (it / kStages2) & 1u;
                     mbar_wait(full_bar + 8 * s, ph);
@@ -637,9 +660,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const uint32_t b_src = a_src + A_BYTES;
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
-                        const uint64_t ad = umma_desc(a_src + k * 32, 16, 1024);
-                        const uint64_t bd = umma_desc(b_src + k * 32, 16, 1024);
-                        tc_mma_bf16_2sm(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        // K-major SW128: a K=16 step is 32 B inside the swizzle atom; MN-major SW128: LBO = next
+                        // 64-element MN chunk (one 8 KB box), SBO = next 8 K-rows, a K=16 step is 16 rows of 128 B
+                        const uint64_t ad = WGRAD ? umma_desc(a_src + k * 2048, 8192, 1024) : umma_desc(a_src + k * 32, 16, 1024);
+                        const uint64_t bd = WGRAD ? umma_desc(b_src + k * 2048, 8192, 1024) : umma_desc(b_src + k * 32, 16, 1024);
+                        tc_mma_bf16_2sm(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
                     tc_commit_2sm(empty_bar + 8 * s);          // slot reusable in BOTH CTAs once these MMAs retire
                 }
@@ -649,17 +674,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     } else {
         // ===== epilogue (both CTAs): warps 2..5, TMEM lane quadrant = warp % 4 =====
         const int q = warp & 3;
-        const bool use_smem_stats = (p.col_stats != nullptr) && (p.N <= kMaxStatCols);
+        const bool use_smem_stats = (!WGRAD) && (p.col_stats != nullptr) && (p.N <= kMaxStatCols);
         const uint32_t stg0 = smem_u32(epi_bytes) + (uint32_t)q * 2u * kEpiBufBytes;
         const uint32_t leader_tmem_empty = mapa_rank(tmem_empty_bar, 0);
         uint32_t buf = 0, t = 0;
         for (int w = pair; w < num_work; w += num_pairs, ++t) {
-            const int row0 = (w / p.n_tiles) * (2 * kBlockM) + (int)rank * kBlockM;
-            const int col0 = (w % p.n_tiles) * BLOCK_N;
+            const int tile = w % tiles;
+            const int row0 = (tile / p.n_tiles) * (2 * kBlockM) + (int)rank * kBlockM;
+            const int col0 = (tile % p.n_tiles) * BLOCK_N;
             const uint32_t as = t & 1u;
             mbar_wait(tmem_full_bar + 8 * as, (t >> 1) & 1u);
             tc_fence_after();
-            staged_tile_epilogue<BLOCK_N, false, true>(p, &tmC, tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N,
+            staged_tile_epilogue<BLOCK_N, WGRAD, true>(p, &tmC, tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N,
                                                        row0 + q * 32, col0, lane, stg0, buf, leader_tmem_empty + 8 * as,
                                                        stat_smem, use_smem_stats);
         }
@@ -702,7 +728,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     return check_launch(WGRAD ? "gemm_wgrad_bf16" : "gemm_bf16");
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool WGRAD>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, GemmParams p,
                         cudaStream_t st) {
     constexpr int smem = kStages2 * (kBlockM * kBlockK * 2 + (BLOCK_N / 2) * kBlockK * 2) + kEpiBytes +
@@ -710,14 +736,13 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
     static_assert(smem <= 232448, "shared memory budget");
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BLOCK_N, WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         DLV3P_REQUIRE(e == cudaSuccess, DLV3P_ERR_CUDA, "cudaFuncSetAttribute(2-CTA smem=%d): %s", smem, cudaGetErrorString(e));
         configured = true;
     }
-    p.m_tiles = cdiv(p.M, 2 * kBlockM);
-    const int work = p.n_tiles * p.m_tiles;
+    const int work = p.n_tiles * p.m_tiles * (WGRAD ? p.splits : 1);
     const int pairs = work < kNumSMs / 2 ? work : kNumSMs / 2;
-    launch_pdl(gemm_tc2_kernel<BLOCK_N>, dim3(2 * pairs), dim3(kThreads), smem, st, tmA, tmB, tmC, p);
+    launch_pdl(gemm_tc2_kernel<BLOCK_N, WGRAD>, dim3(2 * pairs), dim3(kThreads), smem, st, tmA, tmB, tmC, p);
     return check_launch("gemm_bf16 (2-CTA)");
 }
 
@@ -761,7 +786,8 @@ extern "C" int dlv3p_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
         // 2-CTA pairs: every CTA loads half of the B tile (128 rows of the [N,K] operand)
         rc = make_tmap(&tmB, B, K, N, ldb, kBlockK, bn / 2);
         if (rc) return rc;
-        return launch_gemm2<256>(tmA, tmB, tmC, p, st);
+        p.m_tiles = cdiv(M, 2 * kBlockM);
+        return launch_gemm2<256, false>(tmA, tmB, tmC, p, st);
     }
     switch (bn) {
         case 32: return launch_gemm<32, false>(tmA, tmB, tmC, p, st);
@@ -803,6 +829,16 @@ extern "C" int dlv3p_gemm_wgrad_bf16(const void* X, int64_t ldx, const void* dY,
     if (p.tma_store) {
         rc = make_tmap(&tmC, dW, N, K, ldw, 32, 32, /*f32=*/true);
         if (rc) return rc;
+    }
+    if (g_gemm_2cta < 0) { const char* e = getenv("DLV3P_GEMM_2CTA"); g_gemm_2cta = (e && e[0] == '0') ? 0 : 1; }
+    if (g_gemm_2cta && bn == 256 && p.tma_store && K > kBlockM && M >= 4096) {
+        // 2-CTA pairs: 256 input channels x 256 output channels per pair tile, one wave of (split, tile) items
+        p.m_tiles = cdiv(K, 2 * kBlockM);
+        const int tiles2 = p.n_tiles * p.m_tiles;
+        int sp = (kNumSMs / 2) / tiles2; if (sp < 1) sp = 1; if (sp > total_kb) sp = total_kb;
+        p.kb_per_split = cdiv(total_kb, sp);
+        p.splits = cdiv(total_kb, p.kb_per_split);
+        return launch_gemm2<256, true>(tmA, tmB, tmC, p, st);
     }
     switch (bn) {
         case 64: return launch_gemm<64, true>(tmA, tmB, tmC, p, st);

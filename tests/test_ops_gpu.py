@@ -208,7 +208,7 @@ def test_gemm_bf16_strided_a():
 
 
 @pytest.mark.parametrize("case", [(1000, 64, 64), (4096, 128, 256), (5000, 728, 728), (16384, 256, 24),
-                                  (3000, 32, 64), (2000, 1024, 256), (900, 304, 24)])
+                                  (3000, 32, 64), (2000, 1024, 256), (900, 304, 24), (8192, 256, 1024), (4100, 304, 256)])
 def test_gemm_wgrad_bf16(case):
     o = ops()
     M, K, N = case
