@@ -181,6 +181,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--profile-json", default="")
+    ap.add_argument("--no-overlap", action="store_true", help="run the filter-gradient kernels in line (A/B)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -213,7 +214,7 @@ def main():
         warnings.simplefilter("ignore")
         ss = SemanticSegmentation(conf)
     he_init(ss.model)
-    tr = Trainer(ss.model, args.batch, use_graph=not args.no_graph, process_group=pg)
+    tr = Trainer(ss.model, args.batch, use_graph=not args.no_graph, process_group=pg, overlap_wgrad=not args.no_overlap)
     plan = tr.plan
     x, y = synthetic(conf, args.batch, plan.out_shape[1:3], 1024 + rank)
     xs, ys = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
@@ -291,12 +292,14 @@ def main():
         peak_src = "measured" if peaks else "fallback"
         if not args.no_profile:
             # instrumented eager pass of the same step: CUDA events around every kernel launch
+            side, plan.side_stream = plan.side_stream, None        # serialise: per-kernel times must not overlap
             with torch.cuda.stream(tr.stream):
                 with KernelProfiler() as kp:
                     for _ in range(2):
                         plan.zero_grads(); plan.forward(); plan.loss_forward_backward(); plan.backward()
                         plan.regularization(); tr._adam(); plan.run_prep()
                 summ = kp.summary()
+            plan.side_stream = side
             total_ms = sum(a["ms"] for a in summ.values())
             top_name, top = next(iter(summ.items()))
             per_launch_ms = top["ms"] / top["calls"]

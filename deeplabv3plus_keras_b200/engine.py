@@ -190,7 +190,9 @@ class Plan:
         self.fused_tail = fused_tail
         self.dropout_seed = dropout_seed
         self.fwd: List[Callable[[], None]] = []
-        self.bwd: List[Callable[[], None]] = []
+        self.bwd: List[Tuple[Callable[[], None], bool, Optional[int]]] = []   # (launch, side-stream ok, scratch slot)
+        self.side_stream = None            # set by the Trainer: filter-gradient kernels overlap the main backward chain
+        self._bwd_macro = 0
         self.prep: List[Callable[[], None]] = []        # bf16 weight copies / BN folding, after each weight update
         self._bwd_thunks: List[Callable[[], None]] = []
         self.launches_fwd = self.launches_bwd = 0
@@ -538,9 +540,12 @@ class Plan:
                 raise RuntimeError(f"no gradient reaches {lay.name}")
             if other is not None:
                 other.pending.append(g)
+            slot = self._bwd_macro & 1                     # scratch copy used by this macro-op (see bwd_seq)
+            self._bwd_macro += 1
+            self.bwd_seq(None, slot=slot)
             # dy: gradient w.r.t. the raw conv output
             if bn_node is not None:
-                dy_get = self._reserve("dy", (Mo, Cout), self.dt)
+                dy_get = self._reserve(f"dy{slot}", (Mo, Cout), self.dt)
                 red = red_slot
                 self.bwd_seq(lambda: ops.bn_bwd_reduce(g, y, scale, shift, mean, invstd, act, Mo, Cout, red()))
                 self.bwd_seq(lambda: ops.bn_bwd_apply(g, y, scale, shift, mean, invstd, act, red(), Mo, Cout,
@@ -566,10 +571,10 @@ class Plan:
                 # filter gradient
                 if self.bf16:
                     self.bwd_seq(lambda: ops.gemm_wgrad_bf16(A, dy_get(), g32, Mo, Kdim, Cout, ldx=lda, ldy=ld_dy,
-                                                             ldw=Cout))
+                                                             ldw=Cout), side=True, slot=slot)
                 else:
                     self.bwd_seq(lambda: ops.gemm_simt(A, 1, lda, dy_get(), ld_dy, 1, g32, Cout, Kdim, Cout, Mo,
-                                                       accumulate=True))
+                                                       accumulate=True), side=True, slot=slot)
                 need_dA = needs_in_grad
                 if need_dA:
                     direct = (k == 1 and stride == 1 and not is_sep)
@@ -578,7 +583,7 @@ class Plan:
                         dA_get = lambda: tgt
                     else:
                         shape_dA = (Mo, lda)
-                        dA_get = self._reserve("dA", shape_dA, self.dt)
+                        dA_get = self._reserve(f"dA{slot}", shape_dA, self.dt)
                         addend = None
                     if self.bf16:
                         # dA[M,K] = dy[M,N] * W[K,N]^T : B operand = wn (rows = K, contraction over Np, zero padded)
@@ -588,7 +593,7 @@ class Plan:
                         self.bwd_seq(lambda: ops.gemm_simt(dy_get(), ld_dy, 1, w32, 1, Cout, dA_get(), lda, Mo, Kdim,
                                                            Cout, addend=addend, ld_addend=lda))
                     if is_sep:
-                        self._dw_backward(x, dw_w, dw_g, dA_get, stride, dil, pad4, in_act)
+                        self._dw_backward(x, dw_w, dw_g, dA_get, stride, dil, pad4, in_act, slot=slot)
                     elif k == 1 and stride != 1:
                         tgt, addend2 = self._grad_target(x)
                         self.bwd_seq(lambda: ops.subsample_bwd(dA_get().view(N, Ho, Wo, Cin), x.shape, stride,
@@ -599,26 +604,26 @@ class Plan:
                                                            addend=addend2, out=tgt))
                 elif is_sep:
                     # depthwise filter gradient still needs d(dw out) even if the input itself needs no gradient
-                    dA_get = self._reserve("dA", (Mo, lda), self.dt)
+                    dA_get = self._reserve(f"dA{slot}", (Mo, lda), self.dt)
                     if self.bf16:
                         self.bwd_seq(lambda: ops.gemm_bf16(dy_get(), wn, Mo, Kdim, ld_dy, dA_get(), lda=ld_dy, ldb=Np,
                                                            ldc=lda))
                     else:
                         self.bwd_seq(lambda: ops.gemm_simt(dy_get(), ld_dy, 1, w32, 1, Cout, dA_get(), lda, Mo, Kdim,
                                                            Cout))
-                    self._dw_backward(x, dw_w, dw_g, dA_get, stride, dil, pad4, in_act, need_dx=False)
+                    self._dw_backward(x, dw_w, dw_g, dA_get, stride, dil, pad4, in_act, need_dx=False, slot=slot)
             else:
-                self._dw_backward(x, dw_w, dw_g, dy_get, stride, dil, pad4, in_act, need_dx=needs_in_grad)
+                self._dw_backward(x, dw_w, dw_g, dy_get, stride, dil, pad4, in_act, need_dx=needs_in_grad, slot=slot)
 
         self._defer_backward(sched)
 
-    def _dw_backward(self, x: Value, dw_w, dw_g, dd_get, stride, dil, pad4, in_act, need_dx=True):
+    def _dw_backward(self, x: Value, dw_w, dw_g, dd_get, stride, dil, pad4, in_act, need_dx=True, slot=None):
         N = self.N
         Ho, Wo = pad4[0], pad4[1]
         Cin = x.C
         xb = x.buf
         self.bwd_seq(lambda: ops.dwconv3x3_wgrad(xb, dd_get().view(N, Ho, Wo, Cin), dw_g, stride, dil, in_act=in_act,
-                                                 pad=pad4))
+                                                 pad=pad4), side=True, slot=slot)
         if need_dx:
             tgt, addend = self._grad_target(x)
             self.bwd_seq(lambda: ops.dwconv3x3_dgrad(dd_get().view(N, Ho, Wo, Cin), dw_w, x.shape, stride, dil,
@@ -631,9 +636,44 @@ class Plan:
     def _defer_backward(self, sched: Callable[[], None]):
         self._bwd_thunks.append(sched)
 
-    def bwd_seq(self, fn: Callable[[], None]):
-        self.bwd.append(fn)
-        self.launches_bwd += 1
+    def bwd_seq(self, fn: Callable[[], None], side: bool = False, slot: Optional[int] = None):
+        """Append one backward launch.  `side`: a filter-gradient kernel nothing downstream in backward depends on —
+        it may run on the side stream, concurrently with the input-gradient chain, filling the SMs the ~20-30 us
+        kernels of the middle flow leave idle in their ramp and tail.  `slot`: the scratch slot (0/1) the launch READS
+        (side) or whose macro-op is about to WRITE (marker with fn=None): the two scratch copies alternate between
+        consecutive macro-ops, so the main stream only has to wait for the side kernels of the macro before last."""
+        self.bwd.append((fn, side, slot))
+        if fn is not None:
+            self.launches_bwd += 1
+
+    def run_bwd_range(self, a: int, b: int):
+        side = self.side_stream
+        if side is None:
+            for fn, _, _ in self.bwd[a:b]:
+                if fn is not None:
+                    fn()
+            return
+        main = torch.cuda.current_stream()
+        pending: Dict[int, torch.cuda.Event] = {}
+        for fn, on_side, slot in self.bwd[a:b]:
+            if fn is None:                                   # macro-op boundary: it is about to overwrite scratch `slot`
+                ev = pending.pop(slot, None)
+                if ev is not None:
+                    main.wait_event(ev)
+                continue
+            if on_side:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    fn()
+                    done = torch.cuda.Event()
+                    done.record(side)
+                pending[slot if slot is not None else -1] = done
+            else:
+                fn()
+        for ev in pending.values():                          # join: the gradient arena is complete after this range
+            main.wait_event(ev)
 
     # ---- other ops ---------------------------------------------------------------------------------------
     def _emit_maxpool(self, m: dict):
@@ -877,8 +917,7 @@ class Plan:
                 self.logits.grad.copy_(dzh)
 
     def backward(self):
-        for fn in self.bwd:
-            fn()
+        self.run_bwd_range(0, len(self.bwd))
 
     def step_fwd_bwd(self):
         """One forward + backward pass over the batch already resident in self.x_in / self.labels."""

@@ -19,7 +19,7 @@ from .engine import Plan
 
 class Trainer:
     def __init__(self, model, batch_size: int, dtype: Optional[str] = None, use_graph: bool = True,
-                 buckets: int = 4, process_group=None, fused_tail: bool = True):
+                 buckets: int = 4, process_group=None, fused_tail: bool = True, overlap_wgrad: bool = True):
         self.model = model
         self.plan: Plan = model.plan(batch_size, training=True, **({"dtype": dtype} if dtype else {}),
                                      fused_tail=fused_tail)
@@ -32,6 +32,8 @@ class Trainer:
         self.use_graph = use_graph
         self.buckets = buckets
         self.stream = torch.cuda.Stream()
+        if overlap_wgrad:
+            p.side_stream = torch.cuda.Stream()
         self.comm_stream = torch.cuda.Stream() if self.world > 1 else None
         self._segments: List = []          # (graph or callable, grad-arena range completed by it)
         self._prep_graph = None
@@ -58,7 +60,7 @@ class Trainer:
             p.forward()
             p.loss_forward_backward()
 
-        parts = [head] + [(lambda a=a, b=b: [fn() for fn in bwd[a:b]]) for a, b in zip(cuts[:-1], cuts[1:])]
+        parts = [head] + [(lambda a=a, b=b: p.run_bwd_range(a, b)) for a, b in zip(cuts[:-1], cuts[1:])]
 
         def tail():
             p.regularization()
