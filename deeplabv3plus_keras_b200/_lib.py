@@ -31,6 +31,9 @@ SIGNATURES = {
     "dlv3p_subsample_fwd": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "dlv3p_subsample_bwd": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p],
     "dlv3p_weight_prep": [_p, _i, _i, _p, _l, _p, _l, _p],
+    "dlv3p_weight_prep_batch": [_p, _i, _i, _p],
+    "dlv3p_bn_train_apply": [_p, _l, _p, _p, _p, _p, _p, _d, _f, _f, _i, _i, _p, _l, _p, _l, _l, _i, _p, _p, _p, _p,
+                             _i, _p],
     "dlv3p_bn_stats": [_p, _l, _l, _i, _p, _i, _p],
     "dlv3p_bn_finalize": [_p, _p, _p, _p, _p, _i, _d, _f, _f, _p, _p, _p, _p, _i, _p],
     "dlv3p_bn_fold": [_p, _p, _p, _p, _i, _f, _p, _p, _p],

@@ -309,6 +309,88 @@ affine_act_rows_kernel(const T* __restrict__ y, long long ld_y, const float* __r
     }
 }
 
+// Training-mode BatchNormalization forward in ONE launch: every thread finishes the statistics of its own 8 channels
+// (what bn_finalize_kernel does, fp64 for E[x^2]-E[x]^2) and then streams rows like affine_act_rows_kernel; the
+// blockIdx.y == 0 row of blocks also publishes scale / shift / mean / invstd for the backward pass and applies the
+// moving-statistics update (`updates` times: a layer shared by two call sites updates twice, ss.py:802 + :930).
+template <typename T, int CVB, int ACT, bool HAS_ADD>
+__global__ void __launch_bounds__(256, HAS_ADD ? 2 : 3)
+bn_train_apply_kernel(const T* __restrict__ y, long long ld_y, const float* __restrict__ sums,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ moving_mean,
+                      float* __restrict__ moving_var, double count, float eps, float momentum, int updates,
+                      const T* __restrict__ addend, long long ld_a, T* __restrict__ out, long long ld_o, long long M,
+                      int C, float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean,
+                      float* __restrict__ invstd, long long rows_per_block) {
+    pdl_launch_dependents();
+    pdl_wait();
+    constexpr int PL = 256 / CVB;
+    constexpr int U = 4;
+    const int tx = threadIdx.x % CVB, ty = threadIdx.x / CVB;
+    const int cv = blockIdx.x * CVB + tx;
+    if (cv >= (C >> 3)) return;
+    const int c0 = cv << 3;
+    float sc[8], sh[8];
+    const bool publish = (blockIdx.y == 0 && ty == 0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = c0 + k;
+        const double inv_count = 1.0 / count;
+        const double m = (double)__ldg(sums + c) * inv_count;
+        double var = (double)__ldg(sums + C + c) * inv_count - m * m;
+        if (var < 0.0) var = 0.0;
+        const float is = (float)rsqrt(var + (double)eps);
+        const float g = gamma ? __ldg(gamma + c) : 1.f;
+        const float b = beta ? __ldg(beta + c) : 0.f;
+        sc[k] = g * is;
+        sh[k] = b - (float)m * sc[k];
+        if (publish) {
+            scale[c] = sc[k]; shift[c] = sh[k]; mean[c] = (float)m; invstd[c] = is;
+            if (updates > 0) {
+                const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+                float mm = moving_mean[c], mv = moving_var[c];
+                for (int u = 0; u < updates; ++u) {
+                    mm = momentum * mm + (1.f - momentum) * (float)m;
+                    mv = momentum * mv + (1.f - momentum) * (float)unbiased;
+                }
+                moving_mean[c] = mm; moving_var[c] = mv;
+            }
+        }
+    }
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    long long r1 = r0 + rows_per_block; if (r1 > M) r1 = M;
+    for (long long r = r0 + ty; r < r1; r += U * PL) {
+        Vec8<T> a[U], d[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long rr = r + u * PL;
+            if (rr < r1) {
+                a[u].load_stream(y + rr * ld_y + c0);
+                if (HAS_ADD) d[u].load_stream(addend + rr * ld_a + c0);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long rr = r + u * PL;
+            if (rr < r1) {
+                float f[8]; a[u].to_float(f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    f[k] = fmaf(f[k], sc[k], sh[k]);
+                    if (ACT == DLV3P_ACT_RELU) f[k] = fmaxf(f[k], 0.f);
+                    if (ACT == DLV3P_ACT_RELU6) f[k] = fminf(fmaxf(f[k], 0.f), 6.f);
+                }
+                if (HAS_ADD) {
+                    float e[8]; d[u].to_float(e);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) f[k] += e[k];
+                }
+                Vec8<T> o; o.from_float(f);
+                o.store(out + rr * ld_o + c0);
+            }
+        }
+    }
+}
+
 template <typename T, int V>
 __global__ void __launch_bounds__(256)
 act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx, int act,
@@ -743,6 +825,39 @@ weight_prep_kernel(const float* __restrict__ w, int K, int N, __nv_bfloat16* __r
     }
 }
 
+// All GEMM weights of the model in ONE launch (48 launches of a ~3 us kernel per optimizer step otherwise):
+// blockIdx.y = table entry, blockIdx.x strides over that entry's 32x32 tiles.
+struct WeightPrepEntry {
+    const float* w; __nv_bfloat16* wt; __nv_bfloat16* wn; long long ldt, ldn; int K, N;
+};
+static_assert(sizeof(WeightPrepEntry) == 48, "table layout is part of the C-ABI (dlv3p_weight_prep_batch)");
+
+__global__ void __launch_bounds__(256)
+weight_prep_batch_kernel(const WeightPrepEntry* __restrict__ table) {
+    __shared__ float tile[32][33];
+    pdl_launch_dependents();
+    pdl_wait();
+    const WeightPrepEntry e = table[blockIdx.y];
+    const int tiles_n = (e.N + 31) / 32, tiles_k = (e.K + 31) / 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int t = blockIdx.x; t < tiles_n * tiles_k; t += gridDim.x) {
+        const int k0 = (t / tiles_n) * 32, n0 = (t % tiles_n) * 32;
+        for (int r = ty; r < 32; r += 8) {
+            const int k = k0 + r, n = n0 + tx;
+            float v = 0.f;
+            if (k < e.K && n < e.N) v = e.w[(long long)k * e.N + n];
+            tile[r][tx] = v;
+            if (e.wn != nullptr && k < e.K && n < e.N) e.wn[(long long)k * e.ldn + n] = __float2bfloat16_rn(v);
+        }
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {
+            const int n = n0 + r, k = k0 + tx;
+            if (n < e.N && k < e.K) e.wt[(long long)n * e.ldt + k] = __float2bfloat16_rn(tile[tx][r]);
+        }
+        __syncthreads();
+    }
+}
+
 // ---- dropout / adam / misc ----------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
     z += 0x9E3779B97F4A7C15ull;
@@ -906,6 +1021,38 @@ extern "C" int dlv3p_affine_act(const void* y, int64_t ld_y, const float* scale,
     return 0;
 }
 
+#define DLV3P_BNT(A, AD) launch_pdl(bn_train_apply_kernel<T, CVB, A, AD>, dim3(gx, gy), dim3(256), 0, st, (const T*)y, (long long)ld_y, \
+                                    sums, gamma, beta, moving_mean, moving_var, count, eps, momentum, updates, (const T*)addend,    \
+                                    (long long)ld_addend, (T*)out, (long long)ld_out, (long long)M, C, scale, shift, mean, invstd, rpb)
+
+extern "C" int dlv3p_bn_train_apply(const void* y, int64_t ld_y, const float* sums, const float* gamma, const float* beta,
+                                    float* moving_mean, float* moving_var, double count, float eps, float momentum,
+                                    int updates, int act, const void* addend, int64_t ld_addend, void* out,
+                                    int64_t ld_out, int64_t M, int C, float* scale, float* shift, float* mean,
+                                    float* invstd, int dtype, void* stream) {
+    DLV3P_REQUIRE(y && out && sums && scale && shift && mean && invstd && M > 0 && C > 0 && count > 0, DLV3P_ERR_SHAPE,
+                  "bn_train_apply: bad arguments");
+    DLV3P_REQUIRE(updates == 0 || (moving_mean && moving_var), DLV3P_ERR_SHAPE,
+                  "bn_train_apply: moving statistics required when updates > 0");
+    DLV3P_REQUIRE(vec_ok(C, {ld_y, ld_out, addend ? ld_addend : 0}, {y, out, addend}), DLV3P_ERR_ALIGN,
+                  "bn_train_apply: C/ld must be multiples of 8 (use bn_finalize + affine_act otherwise)");
+    cudaStream_t st = (cudaStream_t)stream;
+    DLV3P_DISPATCH_DTYPE(dtype, T, {
+        pick_cvb(C / 8, [&](auto cvb) {
+            constexpr int CVB = decltype(cvb)::value;
+            int gx, gy; long long rpb;
+            col_reduce_grid(C / 8, CVB, M, gx, gy, rpb, addend ? 2 : 3);
+            if (addend) {
+                if (act == DLV3P_ACT_NONE) DLV3P_BNT(0, true); else if (act == DLV3P_ACT_RELU) DLV3P_BNT(1, true); else DLV3P_BNT(2, true);
+            } else {
+                if (act == DLV3P_ACT_NONE) DLV3P_BNT(0, false); else if (act == DLV3P_ACT_RELU) DLV3P_BNT(1, false); else DLV3P_BNT(2, false);
+            }
+        });
+        return check_launch("bn_train_apply");
+    });
+    return 0;
+}
+
 #define DLV3P_BNR(A) launch_pdl(bn_bwd_reduce_kernel<T, CVB, A>, dim3(gx, gy), dim3(256), 0, st, (const T*)dz, (long long)ld_dz, \
                                 (const T*)y, (long long)ld_y, scale, shift, mean, invstd, (long long)M, C, red, rpb)
 #define DLV3P_BNA(A) launch_pdl(bn_bwd_apply_kernel<T, CVB, A>, dim3(gx, gy), dim3(256), 0, st, (const T*)dz, (long long)ld_dz, \
@@ -1000,6 +1147,131 @@ extern "C" int dlv3p_maxpool3x3s2_fwd(const void* x, void* y, uint8_t* argmax, i
     return 0;
 }
 
+namespace dlv3p {
+// bf16 specialisation of the max-pool input gradient: the winning-tap test is a packed byte compare (__vcmpeq4 on four
+// argmax bytes), the byte masks are widened to bf16x2 lane masks with one PRMT each and applied with AND, and the <= 4
+// window contributions are summed with packed bf16 adds — 16 instructions per window instead of ~40 scalar ones (the
+// scalar kernel was issue-bound at 1.4 TB/s).  Two terms sum exactly like the fp32 path (one rounding); three or four
+// (only even-row/even-column pixels that win several windows) round at most twice more.
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ argmax,
+                             __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int pad_t, int pad_l, int Ho,
+                             int Wo, const __nv_bfloat16* __restrict__ addend, long long total) {
+    const int CV = C >> 3;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c0 = (int)(idx % CV) << 3;
+    long long t = idx / CV;
+    const int wi = (int)(t % W); t /= W;
+    const int hi = (int)(t % H);
+    const int n = (int)(t / H);
+    __nv_bfloat162 acc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = __float2bfloat162_rn(0.f);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int hn = hi + pad_t - i;
+        if (hn < 0 || (hn & 1)) continue;
+        const int ho = hn >> 1;
+        if (ho >= Ho) continue;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int wn = wi + pad_l - j;
+            if (wn < 0 || (wn & 1)) continue;
+            const int wo = wn >> 1;
+            if (wo >= Wo) continue;
+            const long long off = (((long long)n * Ho + ho) * Wo + wo) * C + c0;
+            const uint2 pk = __ldg(reinterpret_cast<const uint2*>(argmax + off));
+            const uint4 g = __ldg(reinterpret_cast<const uint4*>(dy + off));
+            const uint32_t tapv = (uint32_t)(i * 3 + j) * 0x01010101u;
+            const uint32_t mlo = __vcmpeq4(pk.x, tapv), mhi = __vcmpeq4(pk.y, tapv);
+            uint32_t v[4] = {g.x & __byte_perm(mlo, 0, 0x1100), g.y & __byte_perm(mlo, 0, 0x3322),
+                             g.z & __byte_perm(mhi, 0, 0x1100), g.w & __byte_perm(mhi, 0, 0x3322)};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[k] = __hadd2(acc[k], *reinterpret_cast<__nv_bfloat162*>(&v[k]));
+        }
+    }
+    const long long off = (((long long)n * H + hi) * W + wi) * C + c0;
+    if (addend != nullptr) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(addend + off));
+        const uint32_t av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 x = __bfloat1622float2(acc[k]);
+            const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&av[k]));
+            acc[k] = __floats2bfloat162_rn(x.x + y.x, x.y + y.y);
+        }
+    }
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&acc[0]); o.y = *reinterpret_cast<uint32_t*>(&acc[1]);
+    o.z = *reinterpret_cast<uint32_t*>(&acc[2]); o.w = *reinterpret_cast<uint32_t*>(&acc[3]);
+    *reinterpret_cast<uint4*>(dx + off) = o;
+}
+
+// im2col for channel counts that are not a multiple of 8 (the 3-channel image of block1_conv1 / Conv1): one thread
+// gathers 8 consecutive columns (scalar loads) and issues ONE 16-byte store — the element-per-thread kernel wrote 2
+// bytes per thread (400 GB/s).  ld_col % 8 == 0, col 16-byte aligned.
+__global__ void __launch_bounds__(256)
+im2col3x3_gather8_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int H, int W,
+                              int C, int stride, int dil, int pad_t, int pad_l, int Ho, int Wo, long long ld_col,
+                              long long total) {
+    const int JV = (int)(ld_col / 8);
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int j0 = (int)(idx % JV) * 8;
+    const long long p = idx / JV;
+    const int wo = (int)(p % Wo); long long t = p / Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    const unsigned short* xs = reinterpret_cast<const unsigned short*>(x);
+    unsigned short v[8];
+    int tap = j0 / C, c = j0 % C;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        v[k] = 0;
+        if (tap < 9) {
+            const int hi = ho * stride - pad_t + (tap / 3) * dil;
+            const int wi = wo * stride - pad_l + (tap % 3) * dil;
+            if (hi >= 0 && hi < H && wi >= 0 && wi < W) v[k] = __ldg(xs + (((long long)n * H + hi) * W + wi) * C + c);
+        }
+        if (++c == C) { c = 0; ++tap; }
+    }
+    uint4 o;
+    o.x = (uint32_t)v[0] | ((uint32_t)v[1] << 16); o.y = (uint32_t)v[2] | ((uint32_t)v[3] << 16);
+    o.z = (uint32_t)v[4] | ((uint32_t)v[5] << 16); o.w = (uint32_t)v[6] | ((uint32_t)v[7] << 16);
+    *reinterpret_cast<uint4*>(col + p * ld_col + j0) = o;
+}
+
+// dropout, 8 elements per thread (16-byte accesses): four 64-bit hashes give eight 24-bit uniforms
+template <typename T>
+__global__ void __launch_bounds__(256)
+dropout8_kernel(const T* __restrict__ x, T* __restrict__ y, long long n8, float rate, uint64_t seed,
+                const uint64_t* __restrict__ seed_offset, const T* __restrict__ addend) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    if (seed_offset != nullptr) seed += *seed_offset;
+    Vec8<T> a; a.load_stream(x + i * 8);
+    float f[8]; a.to_float(f);
+    const float keep = 1.f / (1.f - rate);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint64_t h = splitmix64(seed * 0xD1342543DE82EF95ull + (uint64_t)(i * 4 + q));
+        const float u0 = (float)(h >> 40) * (1.0f / 16777216.0f);
+        const float u1 = (float)((h >> 8) & 0xFFFFFFull) * (1.0f / 16777216.0f);
+        f[2 * q] = (u0 >= rate) ? f[2 * q] * keep : 0.f;
+        f[2 * q + 1] = (u1 >= rate) ? f[2 * q + 1] * keep : 0.f;
+    }
+    if (addend != nullptr) {
+        Vec8<T> d; d.load_stream(addend + i * 8);
+        float e[8]; d.to_float(e);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] += e[k];
+    }
+    Vec8<T> o; o.from_float(f);
+    o.store(y + i * 8);
+}
+}  // namespace dlv3p
+
 extern "C" int dlv3p_maxpool3x3s2_bwd(const void* dy, const uint8_t* argmax, void* dx, int N, int H, int W, int C,
                                       int pad_t, int pad_l, int Ho, int Wo, const void* addend, int dtype,
                                       void* stream) {
@@ -1007,6 +1279,12 @@ extern "C" int dlv3p_maxpool3x3s2_bwd(const void* dy, const uint8_t* argmax, voi
     DLV3P_REQUIRE(C % 8 == 0 && aligned16(dy) && aligned16(dx), DLV3P_ERR_ALIGN, "maxpool_bwd: C %% 8 and alignment");
     cudaStream_t st = (cudaStream_t)stream;
     const long long total = (long long)N * H * W * (C / 8);
+    if (dtype == DLV3P_BF16 && (addend == nullptr || aligned16(addend))) {
+        maxpool3x3s2_bwd_bf16_kernel<<<cdiv(total, 256), 256, 0, st>>>(
+            (const __nv_bfloat16*)dy, argmax, (__nv_bfloat16*)dx, N, H, W, C, pad_t, pad_l, Ho, Wo,
+            (const __nv_bfloat16*)addend, total);
+        return check_launch("maxpool3x3s2_bwd");
+    }
     DLV3P_DISPATCH_DTYPE(dtype, T, {
         maxpool3x3s2_bwd_kernel<T><<<cdiv(total, 256), 256, 0, st>>>((const T*)dy, argmax, (T*)dx, N, H, W, C, pad_t,
                                                                      pad_l, Ho, Wo, (const T*)addend, total);
@@ -1105,6 +1383,12 @@ extern "C" int dlv3p_im2col3x3(const void* x, void* col, int N, int H, int W, in
     cudaStream_t st = (cudaStream_t)stream;
     const bool v8 = vec_ok(C, {ld_col}, {x, col});
     const long long P = (long long)N * Ho * Wo;
+    if (!v8 && dtype == DLV3P_BF16 && (ld_col % 8) == 0 && aligned16(col)) {
+        const long long total = P * (ld_col / 8);
+        im2col3x3_gather8_bf16_kernel<<<cdiv(total, 256), 256, 0, st>>>(
+            (const __nv_bfloat16*)x, (__nv_bfloat16*)col, N, H, W, C, stride, dil, pad_t, pad_l, Ho, Wo, ld_col, total);
+        return check_launch("im2col3x3");
+    }
     DLV3P_DISPATCH_DTYPE(dtype, T, {
         if (v8) {
             const long long total = P * (ld_col / 8);
@@ -1182,12 +1466,21 @@ extern "C" int dlv3p_weight_prep(const float* w, int K, int N, void* wt, int64_t
     return check_launch("weight_prep");
 }
 
+extern "C" int dlv3p_weight_prep_batch(const void* table, int count, int blocks_per_entry, void* stream) {
+    DLV3P_REQUIRE(table && count > 0 && blocks_per_entry > 0, DLV3P_ERR_SHAPE, "weight_prep_batch: bad arguments");
+    launch_pdl(weight_prep_batch_kernel, dim3(blocks_per_entry, count), dim3(256), 0, (cudaStream_t)stream,
+               (const WeightPrepEntry*)table);
+    return check_launch("weight_prep_batch");
+}
+
 extern "C" int dlv3p_dropout(const void* x, void* y, int64_t n, float rate, uint64_t seed,
                              const uint64_t* seed_offset, const void* addend, int dtype, void* stream) {
     DLV3P_REQUIRE(x && y && n > 0 && rate >= 0.f && rate < 1.f, DLV3P_ERR_SHAPE, "dropout: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
+    const bool v8 = (n % 8 == 0) && aligned16(x) && aligned16(y) && (addend == nullptr || aligned16(addend));
     DLV3P_DISPATCH_DTYPE(dtype, T, {
-        dropout_kernel<T><<<cdiv(n, 256), 256, 0, st>>>((const T*)x, (T*)y, n, rate, seed, seed_offset, (const T*)addend);
+        if (v8) dropout8_kernel<T><<<cdiv(n / 8, 256), 256, 0, st>>>((const T*)x, (T*)y, n / 8, rate, seed, seed_offset, (const T*)addend);
+        else dropout_kernel<T><<<cdiv(n, 256), 256, 0, st>>>((const T*)x, (T*)y, n, rate, seed, seed_offset, (const T*)addend);
         return check_launch("dropout");
     });
     return 0;

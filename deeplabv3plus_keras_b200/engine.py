@@ -194,6 +194,8 @@ class Plan:
         self.side_stream = None            # set by the Trainer: filter-gradient kernels overlap the main backward chain
         self._bwd_macro = 0
         self.prep: List[Callable[[], None]] = []        # bf16 weight copies / BN folding, after each weight update
+        self._wprep: List[Tuple] = []                   # GEMM weights re-quantised by ONE batched launch
+        self._wprep_table = None
         self._bwd_thunks: List[Callable[[], None]] = []
         self.launches_fwd = self.launches_bwd = 0
         self._scratch: Dict[str, torch.Tensor] = {}
@@ -436,7 +438,7 @@ class Plan:
             if self.bf16:
                 wt = self._alloc((Cout, Kp), torch.bfloat16, zero=True)       # [N,K] K-major: forward B operand
                 wn = self._alloc((Kdim, Np), torch.bfloat16, zero=True) if training else None   # dgrad B operand
-                self.prep.append(lambda: ops.weight_prep(w32, Kdim, Cout, wt, Kp, wn, Np))
+                self._wprep.append((w32, Kdim, Cout, wt, Kp, wn, Np))
         # ---- BatchNormalization state
         if bn_node is not None:
             bn = bn_node.layer
@@ -520,12 +522,19 @@ class Plan:
                 self.fwd.append(lambda: ops.bn_stats(y, Mo, Cout, stat()))
                 launches_f += 1
             upd = bn_node.calls
-            for r in range(upd):
-                self.fwd.append(lambda r=r: ops.bn_finalize(stat(), gamma, beta, mm, mv, Cout, Mo, bn.epsilon,
-                                                            bn.momentum, scale, shift, mean, invstd, True))
+            if Cout % 8 == 0:
+                # statistics -> scale/shift, moving-statistics update and BN+activation(+add) in one launch
+                self.fwd.append(lambda: ops.bn_train_apply(y, Mo, Cout, stat(), gamma, beta, mm, mv, Mo, bn.epsilon,
+                                                           bn.momentum, upd, act, out.buf, scale, shift, mean, invstd,
+                                                           addend=addend_f))
                 launches_f += 1
-            self.fwd.append(lambda: ops.affine_act(y, Mo, Cout, out.buf, scale, shift, act, addend=addend_f))
-            launches_f += 1
+            else:
+                for r in range(upd):
+                    self.fwd.append(lambda r=r: ops.bn_finalize(stat(), gamma, beta, mm, mv, Cout, Mo, bn.epsilon,
+                                                                bn.momentum, scale, shift, mean, invstd, True))
+                    launches_f += 1
+                self.fwd.append(lambda: ops.affine_act(y, Mo, Cout, out.buf, scale, shift, act, addend=addend_f))
+                launches_f += 1
         elif bn_node is not None and is_dw:
             self.fwd.append(lambda: ops.affine_act(out.buf, Mo, Cout, out.buf, scale, shift, act, addend=addend_f))
             launches_f += 1
@@ -860,6 +869,10 @@ class Plan:
         self.run_prep()
 
     def run_prep(self):
+        if self._wprep:
+            if self._wprep_table is None:
+                self._wprep_table = ops.weight_prep_table(self._wprep, self.device)
+            ops.weight_prep_batch(self._wprep_table, len(self._wprep))
         for fn in self.prep:
             fn()
 

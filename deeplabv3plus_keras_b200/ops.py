@@ -171,6 +171,20 @@ def weight_prep(w: Tensor, K: int, N: int, wt: Tensor, ldt: int, wn: Optional[Te
     call("dlv3p_weight_prep", _p(w), K, N, _p(wt), ldt, _p(wn), ldn, _stream())
 
 
+def weight_prep_table(entries, device) -> Tensor:
+    """Device table for weight_prep_batch from [(w, K, N, wt, ldt, wn, ldn), ...] (include/dlv3p.h layout)."""
+    import numpy as np
+    rec = np.zeros(len(entries), dtype=np.dtype([("w", "<u8"), ("wt", "<u8"), ("wn", "<u8"), ("ldt", "<i8"),
+                                                  ("ldn", "<i8"), ("K", "<i4"), ("N", "<i4")]))
+    for i, (w, K, N, wt, ldt, wn, ldn) in enumerate(entries):
+        rec[i] = (w.data_ptr(), wt.data_ptr(), wn.data_ptr() if wn is not None else 0, ldt, ldn, K, N)
+    return torch.from_numpy(rec.view(np.uint8).copy()).to(device)
+
+
+def weight_prep_batch(table: Tensor, count: int, blocks_per_entry: int = 32):
+    call("dlv3p_weight_prep_batch", _p(table), count, blocks_per_entry, _stream())
+
+
 # ---------------------------------------------------------------------------------------------- K3
 def bn_stats(y: Tensor, M: int, Cc: int, sums: Tensor, ld=None):
     call("dlv3p_bn_stats", _p(y), Cc if ld is None else ld, M, Cc, _p(sums), _dt(y), _stream())
@@ -181,6 +195,15 @@ def bn_finalize(sums, gamma, beta, moving_mean, moving_var, Cc, count, eps, mome
                 update_moving=True):
     call("dlv3p_bn_finalize", _p(sums), _p(gamma), _p(beta), _p(moving_mean), _p(moving_var), Cc, float(count),
          eps, momentum, _p(scale), _p(shift), _p(mean), _p(invstd), int(update_moving), _stream())
+
+
+def bn_train_apply(y, M, Cc, sums, gamma, beta, moving_mean, moving_var, count, eps, momentum, updates, act, out,
+                   scale, shift, mean, invstd, addend=None):
+    """Training-mode BatchNormalization (+activation, +residual add) forward from the batch sums, in one launch."""
+    call("dlv3p_bn_train_apply", _p(y), Cc, _p(sums), _p(gamma), _p(beta), _p(moving_mean), _p(moving_var),
+         float(count), eps, momentum, int(updates), act, _p(addend), Cc, _p(out), Cc, M, Cc, _p(scale), _p(shift),
+         _p(mean), _p(invstd), _dt(y), _stream())
+    return out
 
 
 def bn_fold(gamma, beta, moving_mean, moving_var, Cc, eps, scale, shift):

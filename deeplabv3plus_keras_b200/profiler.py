@@ -41,6 +41,8 @@ COSTS: Dict[str, Tuple[str, Callable]] = {
     "dlv3p_subsample_fwd": ("hbm", lambda a: (2 * a[2] * a[7] * a[8] * a[5] * _esz(a[9]), 0)),
     "dlv3p_subsample_bwd": ("hbm", lambda a: ((a[2] * a[7] * a[8] * a[5] + a[2] * a[3] * a[4] * a[5] * (1 + _opt(a[9]))) * _esz(a[10]), 0)),
     "dlv3p_weight_prep": ("hbm", lambda a: (a[1] * a[2] * (4 + 2 + (2 if a[5] else 0)), 0)),
+    "dlv3p_bn_train_apply": ("hbm", lambda a: ((2 + _opt(a[12])) * a[16] * a[17] * _esz(a[22]), 2 * a[16] * a[17])),
+    "dlv3p_weight_prep_batch": ("hbm", lambda a: (0, 0)),
     "dlv3p_bn_stats": ("hbm", lambda a: (a[2] * a[3] * _esz(a[5]), 3 * a[2] * a[3])),
     "dlv3p_affine_act": ("hbm", lambda a: ((2 + _opt(a[5])) * a[9] * a[10] * _esz(a[11]), 2 * a[9] * a[10])),
     "dlv3p_bn_bwd_reduce": ("hbm", lambda a: (2 * a[9] * a[10] * _esz(a[12]), 6 * a[9] * a[10])),

@@ -109,6 +109,9 @@ int dlv3p_subsample_bwd(const void* dy, void* dx, int N, int H, int W, int C, in
 /* fp32 master weight [K,N] -> bf16 copies: wt [N,ldt] (transposed, K contiguous, zero padded to ldt) and,
  * if wn != NULL, wn [K,ldn] (same orientation, N contiguous, zero padded).  Used once per optimizer step. */
 int dlv3p_weight_prep(const float* w, int K, int N, void* wt, int64_t ldt, void* wn, int64_t ldn, void* stream);
+/* the same for `count` weights in one launch; `table` is a DEVICE array of 48-byte entries
+ * { const float* w; bf16* wt; bf16* wn; int64 ldt; int64 ldn; int32 K; int32 N; } */
+int dlv3p_weight_prep_batch(const void* table, int count, int blocks_per_entry, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K3 — memory-bound fused kernels.
@@ -122,6 +125,13 @@ int dlv3p_bn_stats(const void* y, int64_t ld, int64_t M, int C, float* sums, int
 int dlv3p_bn_finalize(const float* sums, const float* gamma, const float* beta, float* moving_mean,
                       float* moving_var, int C, double count, float eps, float momentum, float* scale,
                       float* shift, float* mean, float* invstd, int update_moving, void* stream);
+/* bn_finalize + affine_act in one launch (the training forward of BatchNormalization + Activation + Add):
+ * statistics are finished per thread, scale/shift/mean/invstd are published for the backward pass and the moving
+ * statistics receive `updates` momentum updates (0 = frozen; 2 = layer applied at two call sites).  C % 8 == 0. */
+int dlv3p_bn_train_apply(const void* y, int64_t ld_y, const float* sums, const float* gamma, const float* beta,
+                         float* moving_mean, float* moving_var, double count, float eps, float momentum, int updates,
+                         int act, const void* addend, int64_t ld_addend, void* out, int64_t ld_out, int64_t M, int C,
+                         float* scale, float* shift, float* mean, float* invstd, int dtype, void* stream);
 /* inference: scale = gamma*rsqrt(moving_var+eps), shift = beta - moving_mean*scale */
 int dlv3p_bn_fold(const float* gamma, const float* beta, const float* moving_mean, const float* moving_var, int C,
                   float eps, float* scale, float* shift, void* stream);

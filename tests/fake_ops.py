@@ -211,6 +211,23 @@ def bn_finalize(sums, gamma, beta, moving_mean, moving_var, Cc, count, eps, mome
         moving_var.copy_(momentum * moving_var + (1 - momentum) * unb.float())
 
 
+def bn_train_apply(y, M, Cc, sums, gamma, beta, moving_mean, moving_var, count, eps, momentum, updates, act, out,
+                   scale, shift, mean, invstd, addend=None):
+    for u in range(max(updates, 1)):
+        bn_finalize(sums, gamma, beta, moving_mean, moving_var, Cc, count, eps, momentum, scale, shift, mean, invstd,
+                    update_moving=u < updates)
+    return affine_act(y, M, Cc, out, scale, shift, act, addend=addend)
+
+
+def weight_prep_table(entries, device):
+    return list(entries)
+
+
+def weight_prep_batch(table, count, blocks_per_entry=32):
+    for w, K, N, wt, ldt, wn, ldn in table:
+        weight_prep(w, K, N, wt, ldt, wn, ldn)
+
+
 def bn_fold(gamma, beta, moving_mean, moving_var, Cc, eps, scale, shift):
     s = (gamma if gamma is not None else 1.0) / torch.sqrt(moving_var + eps)
     scale.copy_(s)

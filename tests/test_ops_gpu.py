@@ -566,3 +566,52 @@ def test_errors_are_loud():
         o.dwconv3x3_fwd(x, w)          # C not a multiple of 8
     with pytest.raises(ValueError):
         o.dwconv3x3_fwd(torch.zeros((1, 4, 4, 8)), torch.zeros((3, 3, 8)))   # CPU tensor: no CPU path
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("MC", [(1000, 64), (4097, 728), (20000, 256)])
+def test_bn_train_apply_matches_two_step(MC, dtype):
+    """The one-launch training BatchNormalization forward equals bn_finalize (x updates) + affine_act."""
+    o = ops()
+    M, C = MC
+    y = (rnd((M, C), torch.float64, 191) * 1.5 + 0.7).to(dtype).to(DEV)
+    res = rnd((M, C), dtype, 192).to(DEV)
+    gamma, beta = (rnd((C,), torch.float32, 193, 0.2) + 1.0).to(DEV), rnd((C,), torch.float32, 194, 0.3).to(DEV)
+    mm0, mv0 = rnd((C,), torch.float32, 195), rnd((C,), torch.float32, 196).abs() + 0.5
+    sums = torch.zeros((2, C), dtype=torch.float32, device=DEV)
+    o.bn_stats(y, M, C, sums)
+    for updates, act, use_add in ((1, o.ACT_RELU, True), (2, o.ACT_NONE, False), (0, o.ACT_RELU6, False)):
+        ref = [torch.empty(C, dtype=torch.float32, device=DEV) for _ in range(4)]
+        mm_r, mv_r = mm0.to(DEV), mv0.to(DEV)
+        for u in range(max(updates, 1)):
+            o.bn_finalize(sums, gamma, beta, mm_r, mv_r, C, M, 1e-3, 0.9, *ref, update_moving=u < updates)
+        out_r = torch.empty((M, C), dtype=dtype, device=DEV)
+        o.affine_act(y, M, C, out_r, ref[0], ref[1], act, addend=res if use_add else None)
+        got = [torch.empty(C, dtype=torch.float32, device=DEV) for _ in range(4)]
+        mm_g, mv_g = mm0.to(DEV), mv0.to(DEV)
+        out_g = torch.empty((M, C), dtype=dtype, device=DEV)
+        o.bn_train_apply(y, M, C, sums, gamma, beta, mm_g, mv_g, M, 1e-3, 0.9, updates, act, out_g, *got,
+                         addend=res if use_add else None)
+        for a, b, nm in zip(got + [mm_g, mv_g], ref + [mm_r, mv_r], ("scale", "shift", "mean", "invstd", "mm", "mv")):
+            check(f"bn_train_apply {nm}", a, b, 1e-6, 1e-6)
+        assert torch.equal(out_g, out_r)
+
+
+def test_weight_prep_batch_matches_single():
+    o = ops()
+    entries, singles = [], []
+    for i, (K, N) in enumerate([(728, 728), (27, 32), (2304, 21), (64, 128)]):
+        w = rnd((K, N), torch.float32, 200 + i).to(DEV)
+        Kp, Np = (K + 7) // 8 * 8, (N + 7) // 8 * 8
+        wt = torch.zeros((N, Kp), dtype=torch.bfloat16, device=DEV)
+        wn = torch.zeros((K, Np), dtype=torch.bfloat16, device=DEV) if i % 2 == 0 else None
+        wt2, wn2 = torch.zeros_like(wt), (torch.zeros_like(wn) if wn is not None else None)
+        o.weight_prep(w, K, N, wt2, Kp, wn2, Np)
+        entries.append((w, K, N, wt, Kp, wn, Np))
+        singles.append((wt2, wn2))
+    table = o.weight_prep_table(entries, DEV)
+    o.weight_prep_batch(table, len(entries))
+    for (w, K, N, wt, Kp, wn, Np), (wt2, wn2) in zip(entries, singles):
+        assert torch.equal(wt, wt2)
+        if wn is not None:
+            assert torch.equal(wn, wn2)
