@@ -41,6 +41,8 @@ SS_NW = [0.70245001, 0.00893111, 0.00763626, 0.00877043, 0.00649604, 0.00544513,
          0.01246875, 0.00623611, 0.01057388, 0.02777125, 0.00919422, 0.01154691, 0.07393348, 0.00606626, 0.00625678,
          0.01217829, 0.01340344, 0.00766524]
 FLOP_PER_IMG_FWD_BWD = 142.3e9       # SURVEY.md §8(d) ledger, Xception(ref-truncated)/OS16/513^2
+WORKLOAD = ("Xception(ref-truncated, block13_sepconv2_bn tap) OS16 513x513x3 -> 512x512x21, batch {batch}/GPU, "
+            "fwd + class-balanced loss + bwd + Adam, training-mode BN, dropout 0.5, random init")
 
 
 def make_conf(dtype, image_size=513):
@@ -162,7 +164,8 @@ def run_reference(args, rank):
             "unit": "img/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
             "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "Xception(ref-truncated) OS16 513x513 fwd+bwd, batch 2 per step on host cores"},
+            "config": {"workload": WORKLOAD.format(batch=16), "global_batch": 16, "parallelism": "cpu",
+                       "sample": "each step = 2 images of the 16-image batch on the host cores (bounded sample)"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -270,9 +273,7 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.dtype == "bfloat16" else "f32", "data": "synthetic",
-        "config": {"workload": f"Xception(ref-truncated, block13_sepconv2_bn tap) OS16 513x513x3 -> 512x512x21, "
-                               f"batch {args.batch}/GPU, fwd + class-balanced loss + bwd + Adam, training-mode BN, "
-                               f"dropout 0.5, random init", "global_batch": args.batch * world,
+        "config": {"workload": WORKLOAD.format(batch=args.batch), "global_batch": args.batch * world,
                    "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
                    "l2_policy": "per-step working set (several GB of activations) far exceeds the 126 MB L2"},
         "clocks": clocks, "loss": loss,
@@ -307,10 +308,26 @@ def main():
                 ach, peak, unit = top["TFLOPs"], tc_peak, "TFLOP/s"
             else:
                 ach, peak, unit = top["GBps"], hbm_peak, "GB/s"
+            traffic, traffic_src = None, None
+            try:      # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` capture
+                tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+                if top_name in tj:
+                    traffic, traffic_src = tj[top_name]["bytes_per_launch"], tj[top_name]["source"]
+            except Exception:
+                pass
             line["roofline"] = {"bound": "tensor" if top["bound"] == "tensor" else "hbm", "kernel": top_name,
-                                "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": None,
+                                "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": traffic,
+                                "traffic_source": traffic_src,
                                 "peak_source": peak_src, "share_of_step": top["ms"] / total_ms,
                                 "avg_launch_ms": per_launch_ms, "launches_per_step": top["calls"] // 2}
+            shapes = [r for r in kp.detail(200) if r["kernel"] == top_name]
+            if shapes:       # the single most expensive problem size of the dominant entry point
+                d0 = shapes[0]
+                line["roofline"]["dominant_shape"] = {
+                    "args": d0["args"], "launches_per_step": d0["calls"] // 2, "ms_per_step": d0["ms"] / 2,
+                    "avg_launch_ms": d0["ms"] / d0["calls"], "TFLOPs": round(d0["TFLOPs"], 1),
+                    "GBps": round(d0["GBps"], 1),
+                    "frac": round(d0["TFLOPs"] / tc_peak if top["bound"] == "tensor" else d0["GBps"] / hbm_peak, 4)}
             line["kernels"] = {k: {"calls_per_step": a["calls"] // 2, "ms_per_step": a["ms"] / 2,
                                    "GBps": round(a["GBps"], 1), "TFLOPs": round(a["TFLOPs"], 2), "bound": a["bound"],
                                    "frac": round((a["TFLOPs"] / tc_peak) if a["bound"] == "tensor"

@@ -1157,14 +1157,15 @@ __global__ void __launch_bounds__(256)
 maxpool3x3s2_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ argmax,
                              __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int pad_t, int pad_l, int Ho,
                              int Wo, const __nv_bfloat16* __restrict__ addend, long long total) {
+    // grid: x = (column, channel-pack) inside one input row, y = (image, row): no 64-bit divisions per thread
     const int CV = C >> 3;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int c0 = (int)(idx % CV) << 3;
-    long long t = idx / CV;
-    const int wi = (int)(t % W); t /= W;
-    const int hi = (int)(t % H);
-    const int n = (int)(t / H);
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= W * CV) return;
+    const int c0 = (e % CV) << 3;
+    const int wi = e / CV;
+    const int hi = blockIdx.y % H;
+    const int n = blockIdx.y / H;
+    (void)total;
     __nv_bfloat162 acc[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) acc[k] = __float2bfloat162_rn(0.f);
@@ -1279,8 +1280,8 @@ extern "C" int dlv3p_maxpool3x3s2_bwd(const void* dy, const uint8_t* argmax, voi
     DLV3P_REQUIRE(C % 8 == 0 && aligned16(dy) && aligned16(dx), DLV3P_ERR_ALIGN, "maxpool_bwd: C %% 8 and alignment");
     cudaStream_t st = (cudaStream_t)stream;
     const long long total = (long long)N * H * W * (C / 8);
-    if (dtype == DLV3P_BF16 && (addend == nullptr || aligned16(addend))) {
-        maxpool3x3s2_bwd_bf16_kernel<<<cdiv(total, 256), 256, 0, st>>>(
+    if (dtype == DLV3P_BF16 && (addend == nullptr || aligned16(addend)) && (long long)N * H <= 65535) {
+        maxpool3x3s2_bwd_bf16_kernel<<<dim3(cdiv((long long)W * (C / 8), 256), N * H), 256, 0, st>>>(
             (const __nv_bfloat16*)dy, argmax, (__nv_bfloat16*)dx, N, H, W, C, pad_t, pad_l, Ho, Wo,
             (const __nv_bfloat16*)addend, total);
         return check_launch("maxpool3x3s2_bwd");
