@@ -196,6 +196,10 @@ def main():
     if world != args.gpus and not (world == 1 and args.gpus == 1):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
     args.warmup = max(args.warmup, 3)
+    # the contract is ONE JSON line on stdout: libraries that write to fd 1 (NCCL prints its version there on init) are
+    # diverted to stderr; the JSON line goes to the saved descriptor
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     import torch.distributed as dist
 
@@ -339,7 +343,8 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_baseline()
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line), flush=True)
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

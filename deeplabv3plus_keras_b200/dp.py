@@ -43,3 +43,14 @@ def allreduce_gradients(g: torch.Tensor, n: int, group=None, buckets: int = 4) -
              for lo, hi in bucket_ranges(n, buckets)]
     for w in works:
         w.wait()
+
+
+def allreduce_ranges(g: torch.Tensor, ranges, group=None) -> None:
+    """In-place SUM all-reduce of the given [lo, hi) slices of the flat gradient arena, enqueued on the current
+    stream (the trainer's communication stream): the slices are the arena prefixes that became final during the
+    backward segment just launched, so the exchange overlaps the rest of backward."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    for lo, hi in ranges:
+        if hi > lo:
+            dist.all_reduce(g[lo:hi], op=dist.ReduceOp.SUM, group=group)

@@ -113,7 +113,8 @@ class ParamStore:
             if "beta" in names and "gamma" in names:
                 # BatchNormalization: keep [dbeta | dgamma] adjacent in the gradient arena so that the backward
                 # reduction kernel (red[0..C) = sum g, red[C..2C) = sum g*xhat) accumulates straight into it
-                names = ["beta", "gamma"] + [n for n in names if n not in ("beta", "gamma")]
+                # (the lists are reversed below, hence gamma before beta here)
+                names = [n for n in names if n not in ("beta", "gamma")] + ["gamma", "beta"]
             for n in names:
                 w = l._weights[n]
                 if not l._trainable[n]:
@@ -136,8 +137,14 @@ class ParamStore:
                 off += _ceil8(w.size)          # keep every parameter 32-byte aligned
             return off
 
+        # REVERSE forward order: backward finishes the head first and block1 last, so the gradients of a growing PREFIX
+        # of each region are final while backward is still running — the data-parallel exchange all-reduces prefix
+        # increments behind backward instead of the whole arena after it (trainer.py).
+        reg.reverse()
+        plain.reverse()
         self.n_reg = lay(reg, "w")
         self.n_train = lay(plain, "w", self.n_reg)
+        self.order_w = [(id(l), n) for l, n, _ in reg + plain]          # arena order of the trainable entries
         self.n_frozen = lay(frozen, "f")
         self._items = reg + plain + frozen
         self.w = torch.zeros(max(self.n_train, 8), dtype=torch.float32, device=device)
@@ -193,6 +200,7 @@ class Plan:
         self.bwd: List[Tuple[Callable[[], None], bool, Optional[int]]] = []   # (launch, side-stream ok, scratch slot)
         self.side_stream = None            # set by the Trainer: filter-gradient kernels overlap the main backward chain
         self._bwd_macro = 0
+        self._grad_done: List[Tuple[int, List[Tuple[int, str]]]] = []   # (bwd index, parameters final from there on)
         self.prep: List[Callable[[], None]] = []        # bf16 weight copies / BN folding, after each weight update
         self._wprep: List[Tuple] = []                   # GEMM weights re-quantised by ONE batched launch
         self._wprep_table = None
@@ -623,6 +631,11 @@ class Plan:
                     self._dw_backward(x, dw_w, dw_g, dA_get, stride, dil, pad4, in_act, need_dx=False, slot=slot)
             else:
                 self._dw_backward(x, dw_w, dw_g, dy_get, stride, dil, pad4, in_act, need_dx=needs_in_grad, slot=slot)
+            # every parameter gradient of this macro-op is final once the launches appended so far have run
+            done = [(id(lay), n) for n in lay.weight_names() if lay._trainable[n]]
+            if bn_node is not None:
+                done += [(id(bn_node.layer), n) for n in bn_node.layer.weight_names() if bn_node.layer._trainable[n]]
+            self._grad_done.append((len(self.bwd), done))
 
         self._defer_backward(sched)
 
@@ -654,6 +667,26 @@ class Plan:
         self.bwd.append((fn, side, slot))
         if fn is not None:
             self.launches_bwd += 1
+
+    def final_prefixes(self, cut: int) -> Tuple[int, int]:
+        """Arena offsets (a, b) such that g[0:a] (L2-regularised region) and g[n_reg:b] are FINAL once the backward
+        launches [0, cut) have run — what the data-parallel exchange may all-reduce behind backward."""
+        P = self.params
+        done = set()
+        for idx, entries in self._grad_done:
+            if idx <= cut:
+                done.update(entries)
+        a, b = 0, P.n_reg
+        for key in P.order_w:
+            _, off, shape = P.entries[key]
+            size = _ceil8(int(np.prod(shape)))
+            if off < P.n_reg:
+                if key in done and off == a:
+                    a = off + size
+            else:
+                if key in done and off == b:
+                    b = off + size
+        return a, b
 
     def run_bwd_range(self, a: int, b: int):
         side = self.side_stream

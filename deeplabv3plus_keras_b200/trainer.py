@@ -61,6 +61,14 @@ class Trainer:
             p.loss_forward_backward()
 
         parts = [head] + [(lambda a=a, b=b: p.run_bwd_range(a, b)) for a, b in zip(cuts[:-1], cuts[1:])]
+        # gradient-arena slices that are final after each backward segment (the arena is laid out in backward order)
+        P = p.params
+        self._ranges: List = [[]]                      # nothing to exchange after the head
+        pa, pb = 0, P.n_reg
+        for i, c in enumerate(cuts[1:]):
+            a, b = (P.n_reg, P.n_train) if i == n_buckets - 1 else p.final_prefixes(c)
+            self._ranges.append([(pa, a), (pb, b)])
+            pa, pb = a, b
 
         def tail():
             p.regularization()
@@ -104,26 +112,26 @@ class Trainer:
         """One training step on the batch resident in the plan's input buffers."""
         p = self.plan
         with torch.cuda.stream(self.stream):
-            for part in self._parts:
+            for part, ranges in zip(self._parts, self._ranges):
                 part()
+                if self.world > 1 and ranges:
+                    self._exchange(ranges)      # all-reduce what this segment finished while the next one runs
             if self.world > 1:
-                self._exchange()
+                self.stream.wait_event(self._comm_done)
             if optimizer_step:
                 p.regularization()
                 self._adam()
                 self._prep()
 
-    def _exchange(self):
+    def _exchange(self, ranges):
         g = self.plan.params.g
-        n = self.plan.params.n_train
         ev = torch.cuda.Event()
         ev.record(self.stream)
         self.comm_stream.wait_event(ev)
         with torch.cuda.stream(self.comm_stream):
-            dp.allreduce_gradients(g, n, self.pg, self.buckets)
-        ev2 = torch.cuda.Event()
-        ev2.record(self.comm_stream)
-        self.stream.wait_event(ev2)
+            dp.allreduce_ranges(g, ranges, self.pg)
+            self._comm_done = torch.cuda.Event()
+            self._comm_done.record(self.comm_stream)
 
     def _adam(self):
         P, opt = self.plan.params, self.opt

@@ -94,3 +94,36 @@ def test_weight_npz_round_trip(tmp_path):
     c = util.build(conf2)                                   # the reference's resume switch
     np.testing.assert_array_equal(c.model.named_weights()["Conv1/kernel"], a.model.named_weights()["Conv1/kernel"])
     assert SemanticSegmentation is type(c)
+
+
+@pytest.mark.parametrize("case", [CASES[0], CASES[1], CASES[2]], ids=["xception", "xception-br", "mobilenetv2"])
+def test_gradient_prefixes_are_final_during_backward(cpu_engine, case):
+    """Data-parallel overlap (trainer.py): after the backward launches [0, cut) the arena prefixes reported by
+    Plan.final_prefixes must already hold their FINAL values, and the last cut must cover a growing share."""
+    conf = util.make_conf(width=32, **case)
+    ss = util.build(conf)
+    util.randomize_weights(ss.model)
+    plan = cpu_engine.Plan(ss.model, 2, training=True)
+    x, y = util.synthetic_batch(conf, 2, plan.out_shape[1:3])
+    plan.set_loss(PW, NW)
+    plan.load_batch(x, y)
+    plan.zero_grads()
+    plan.forward()
+    plan.loss_forward_backward()
+    P = plan.params
+    n = len(plan.bwd)
+    cuts = [round(i * n / 4) for i in range(1, 5)]
+    snaps, pos = [], 0
+    for c in cuts:
+        plan.run_bwd_range(pos, c)
+        pos = c
+        snaps.append((plan.final_prefixes(c), P.g.clone()))
+    final = P.g
+    prev = (0, P.n_reg)
+    for (a, b), g in snaps:
+        assert a >= prev[0] and b >= prev[1]
+        torch.testing.assert_close(g[:a], final[:a], rtol=0, atol=0)
+        torch.testing.assert_close(g[P.n_reg:b], final[P.n_reg:b], rtol=0, atol=0)
+        prev = (a, b)
+    assert prev == (P.n_reg, P.n_train), "every trainable parameter has a gradient producer"
+    assert snaps[1][0][1] > P.n_reg, "half-way through backward a non-empty prefix is already final"
