@@ -33,10 +33,11 @@ namespace dlv3p {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;            // 64 bf16 = 128 B = one swizzle atom row
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;             // two per TMEM lane quadrant: they split the column chunks of a tile
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kEpiStageFloats = 32 * 33;          // fallback path, per epilogue warp: 32 rows x 32 cols, padded
 constexpr int kEpiBufBytes = 32 * 128;            // TMA-store path: one staging tile = 32 rows x 128 B
-constexpr int kEpiBytes = 4 * 2 * kEpiBufBytes;   // 4 epilogue warps x 2 buffers (also holds the fallback transposes)
+constexpr int kEpiBytes = kEpiWarps * 2 * kEpiBufBytes;   // per epilogue warp 2 buffers (also holds the fallback transposes)
 constexpr int kMaxStatCols = 1024;                // per-CTA smem accumulators for the BN column statistics
 static_assert(kEpiBytes >= 4 * kEpiStageFloats * 4, "staging area must hold the fallback transposes");
 template <int BLOCK_N> struct GemmCfg {
@@ -117,15 +118,23 @@ __device__ __forceinline__ void decode_work(const GemmParams& p, int w, int& row
 // address in the leader CTA of a 2-CTA pair).
 template <int BLOCK_N, bool WGRAD, bool REMOTE>
 __device__ __forceinline__ void staged_tile_epilogue(const GemmParams& p, const CUtensorMap* tmC, uint32_t acc_tmem,
-                                                     int rbase, int col0, int lane, uint32_t stg0, uint32_t& buf,
+                                                     int rbase, int col0, int lane, int half, uint32_t stg0, uint32_t& buf,
                                                      uint32_t empty_bar, float* stat_smem, bool use_smem_stats) {
     constexpr int CW = WGRAD ? 32 : 64;                 // columns per staging tile (128-byte rows)
     const uint32_t lane_row = (uint32_t)lane * 128u;
     const uint32_t sw = (uint32_t)(lane & 7);
     const int ncols = min(BLOCK_N, p.N - col0);
     const int n_chunks = (ncols + CW - 1) / CW;
+    if (half >= n_chunks) {
+        // the two warps of a lane quadrant take alternate column chunks; this one has none in this tile
+        if (lane == 0) {
+            if (REMOTE) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(empty_bar) : "memory");
+            else mbar_arrive(empty_bar);
+        }
+        return;
+    }
 #pragma unroll 1
-    for (int ch = 0; ch < n_chunks; ++ch) {
+    for (int ch = half; ch < n_chunks; ch += 2) {
         const int n_base = col0 + ch * CW;
         const uint32_t stg = stg0 + buf * kEpiBufBytes;
         if (lane == 0) tma_wait_group_read<1>();    // the store that last read this buffer has drained it
@@ -134,8 +143,8 @@ __device__ __forceinline__ void staged_tile_epilogue(const GemmParams& p, const 
         for (int h = 0; h < CW / 32; ++h) {
             uint32_t raw[32];
             tc_ld_32x32b_x32(acc_tmem + (uint32_t)(ch * CW + h * 32), raw);
-            if (ch == n_chunks - 1 && h == CW / 32 - 1) {
-                // every TMEM read of this accumulator stage has completed: hand it back to the MMA warp
+            if (ch + 2 >= n_chunks && h == CW / 32 - 1) {
+                // every TMEM read of this warp in this accumulator stage has completed: hand it back to the MMA warp
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
@@ -243,7 +252,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
         if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
         for (int s = 0; s < kStages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + 8 * s, 1); mbar_init(tmem_empty_bar + 8 * s, 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + 8 * s, 1); mbar_init(tmem_empty_bar + 8 * s, kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -330,13 +339,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else {
-        // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
+        // ===== epilogue: warps 2..9, TMEM lane quadrant = warp % 4, two warps per quadrant =====
         const int q = warp & 3;
+        const int ew = warp - 2, half = ew >> 2;
         float* stage = epi_stage + q * kEpiStageFloats;
         const int row_limit = WGRAD ? p.K : p.M;
         const bool use_smem_stats = (!WGRAD) && (p.col_stats != nullptr) && (p.N <= kMaxStatCols);
         if (p.tma_store) {
-            const uint32_t stg0 = smem_u32(epi_bytes) + (uint32_t)q * 2u * kEpiBufBytes;
+            const uint32_t stg0 = smem_u32(epi_bytes) + (uint32_t)ew * 2u * kEpiBufBytes;
             uint32_t buf = 0, t = 0;
             for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++t) {
                 int row0, col0, kb_begin, kb_end;
@@ -345,8 +355,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(tmem_full_bar + 8 * as, (t >> 1) & 1u);
                 tc_fence_after();
                 staged_tile_epilogue<BLOCK_N, WGRAD, false>(p, &tmC, tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N,
-                                                            row0 + q * 32, col0, lane, stg0, buf, tmem_empty_bar + 8 * as,
-                                                            stat_smem, use_smem_stats);
+                                                            row0 + q * 32, col0, lane, half, stg0, buf,
+                                                            tmem_empty_bar + 8 * as, stat_smem, use_smem_stats);
             }
             if (lane == 0) tma_wait_group_all();
         } else {
@@ -357,6 +367,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t as = t & 1u;
             mbar_wait(tmem_full_bar + 8 * as, (t >> 1) & 1u);
             tc_fence_after();
+            if (half == 1) {                                   // the direct-store fallback uses one warp per quadrant
+                if (lane == 0) mbar_arrive(tmem_empty_bar + 8 * as);
+                continue;
+            }
             const int rbase = row0 + q * 32;                   // first output row of this warp
             const int r = rbase + lane;                        // output row owned by this lane (row-per-lane layout)
             const bool row_ok = r < row_limit;
@@ -479,9 +493,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }   // direct-store fallback
         if (use_smem_stats) {
             // one flush per CTA: contended global atomics cost ~35 ns per cache line (serialised at L2)
-            asm volatile("bar.sync 1, 128;" ::: "memory");    // the four epilogue warps only
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");    // the epilogue warps only
             const int e = threadIdx.x - 64;
-            for (int c = e; c < p.N; c += 128) {
+            for (int c = e; c < p.N; c += 32 * kEpiWarps) {
                 const float a1 = stat_smem[c], a2 = stat_smem[kMaxStatCols + c];
                 if (a1 != 0.f || a2 != 0.f) {
                     atomicAdd(p.col_stats + c, a1);
@@ -510,7 +524,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 //   * each CTA's epilogue warps drain their own 128 accumulator rows from their own TMEM and arrive (remotely for the
 //     peer) on the leader's "accumulator free" barrier.
 // =====================================================================================================================
-constexpr int kStages2 = 5;            // 5 x 32 KB operand ring per CTA
+constexpr int kStages2 = 4;            // 4 x 32 KB operand ring per CTA
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -578,7 +592,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
         for (int s = 0; s < kStages2; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + 8 * s, 1); mbar_init(tmem_empty_bar + 8 * s, 8); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + 8 * s, 1); mbar_init(tmem_empty_bar + 8 * s, 2 * kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -672,10 +686,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
     } else {
-        // ===== epilogue (both CTAs): warps 2..5, TMEM lane quadrant = warp % 4 =====
+        // ===== epilogue (both CTAs): warps 2..9, TMEM lane quadrant = warp % 4, two warps per quadrant =====
         const int q = warp & 3;
+        const int ew = warp - 2, half = ew >> 2;
         const bool use_smem_stats = (!WGRAD) && (p.col_stats != nullptr) && (p.N <= kMaxStatCols);
-        const uint32_t stg0 = smem_u32(epi_bytes) + (uint32_t)q * 2u * kEpiBufBytes;
+        const uint32_t stg0 = smem_u32(epi_bytes) + (uint32_t)ew * 2u * kEpiBufBytes;
         const uint32_t leader_tmem_empty = mapa_rank(tmem_empty_bar, 0);
         uint32_t buf = 0, t = 0;
         for (int w = pair; w < num_work; w += num_pairs, ++t) {
@@ -686,14 +701,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_wait(tmem_full_bar + 8 * as, (t >> 1) & 1u);
             tc_fence_after();
             staged_tile_epilogue<BLOCK_N, WGRAD, true>(p, &tmC, tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N,
-                                                       row0 + q * 32, col0, lane, stg0, buf, leader_tmem_empty + 8 * as,
-                                                       stat_smem, use_smem_stats);
+                                                       row0 + q * 32, col0, lane, half, stg0, buf,
+                                                       leader_tmem_empty + 8 * as, stat_smem, use_smem_stats);
         }
         if (lane == 0) tma_wait_group_all();
         if (use_smem_stats) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");    // the four epilogue warps only
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");    // the epilogue warps only
             const int e = threadIdx.x - 64;
-            for (int c = e; c < p.N; c += 128) {
+            for (int c = e; c < p.N; c += 32 * kEpiWarps) {
                 const float a1 = stat_smem[c], a2 = stat_smem[kMaxStatCols + c];
                 if (a1 != 0.f || a2 != 0.f) {
                     atomicAdd(p.col_stats + c, a1);
