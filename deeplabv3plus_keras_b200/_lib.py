@@ -63,6 +63,8 @@ SIGNATURES = {
     "dlv3p_adam": [_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _p],
     "dlv3p_sumsq": [_p, _l, _p, _p],
     "dlv3p_cast": [_p, _i, _p, _i, _l, _p],
+    "dlv3p_preprocess_image_batch": [_p, _i, _p, _i, _i, _p],
+    "dlv3p_preprocess_label_batch": [_p, _i, _p, _i, _i, _p],
     "dlv3p_cast2d": [_p, _l, _i, _p, _l, _i, _l, _i, _p],
 }
 _PLAIN = {"dlv3p_version": [], "dlv3p_device_arch": []}

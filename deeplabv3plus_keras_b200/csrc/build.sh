@@ -8,7 +8,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
        -I"${HERE}/../../include")
 mkdir -p "${HERE}/build"
 pids=()
-for f in api dwconv dwconv_tma eltwise loss gemm_simt gemm_tcgen05; do
+for f in api dwconv dwconv_tma eltwise loss preprocess gemm_simt gemm_tcgen05; do
   "${NVCC}" "${FLAGS[@]}" -c "${HERE}/${f}.cu" -o "${HERE}/build/${f}.o" > "${HERE}/build/${f}.log" 2>&1 &
   pids+=($!)
 done

@@ -232,6 +232,20 @@ int dlv3p_cast(const void* x, int x_dtype, void* y, int y_dtype, int64_t n, void
 int dlv3p_cast2d(const void* x, int64_t ld_x, int x_dtype, void* y, int64_t ld_y, int y_dtype, int64_t M, int C,
                  void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Input pipeline (next row): what the reference's keras Sequence does per sample on one CPU thread
+ * (ss.py:1528-1560 with the helpers resize() ss.py:130-195 and resize_image_to_target_symmeric_size() ss.py:198-280).
+ * `table` is a DEVICE array of `count` 48-byte entries
+ *   { const uint8_t* src; double inv_fy, inv_fx; int32 h, w, hp, wp, off_y, off_x; }
+ * describing decoded uint8 samples (HWC, 3 channels for images, 1 for labels): source extent h x w, resized extent
+ * hp x wp, top/left zero padding, inv_f = 1/(hp/h), 1/(wp/w) evaluated in fp64 by the caller.
+ *   image: out[i] [S,S,3] (out_dtype) = pad(affine_transform(2*(src/255-0.5), order=1, mode='nearest'))
+ *   label: out[i] [S,S] int32 = class ids > num_classes-1 cleared, resized likewise with scipy's integer rounding,
+ *          cleared again (the index map of the reference's one-hot tensor)
+ * ---------------------------------------------------------------------------------------------- */
+int dlv3p_preprocess_image_batch(const void* table, int count, void* out, int S, int out_dtype, void* stream);
+int dlv3p_preprocess_label_batch(const void* table, int count, int32_t* out, int S, int num_classes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
