@@ -59,6 +59,38 @@ class Adam:
         return lr * math.sqrt(1.0 - self.beta_2 ** t) / (1.0 - self.beta_1 ** t)
 
 
+class ReduceLROnPlateau:
+    """keras.callbacks.ReduceLROnPlateau as configured at ss.py:978-982 (monitor='loss', factor=hps.reduce_lr_factor,
+    patience=5, min_lr=1e-8; Keras defaults mode='auto' -> min, min_delta=1e-4, cooldown=0): call `on_epoch_end(loss)`
+    once per epoch; the new learning rate is written to the optimizer and used by the next Adam launch."""
+
+    def __init__(self, optimizer: "Adam", monitor="loss", factor=0.1, patience=10, min_lr=0.0, min_delta=1e-4,
+                 cooldown=0, verbose=0):
+        if factor >= 1.0:
+            raise ValueError("ReduceLROnPlateau does not support a factor >= 1.0.")        # Keras' own check
+        self.optimizer, self.monitor, self.factor, self.patience = optimizer, monitor, float(factor), int(patience)
+        self.min_lr, self.min_delta, self.cooldown, self.verbose = float(min_lr), float(min_delta), int(cooldown), verbose
+        self.best, self.wait, self.cooldown_counter = float("inf"), 0, 0
+
+    def on_epoch_end(self, value: float) -> float:
+        if self.cooldown_counter > 0:
+            self.cooldown_counter -= 1
+            self.wait = 0
+        if value < self.best - self.min_delta:
+            self.best, self.wait = value, 0
+        elif self.cooldown_counter <= 0:
+            self.wait += 1
+            if self.wait >= self.patience:
+                old = self.optimizer.lr
+                if old > self.min_lr:
+                    self.optimizer.lr = max(old * self.factor, self.min_lr)
+                    if self.verbose:
+                        print(f"ReduceLROnPlateau reducing learning rate to {self.optimizer.lr}.")
+                    self.cooldown_counter = self.cooldown
+                    self.wait = 0
+        return self.optimizer.lr
+
+
 class ClassBalancedLoss:
     """LossFunctionWrapper around class_balanced_loss (ss.py:423-435); serialisable by name."""
 

@@ -127,3 +127,20 @@ def test_gradient_prefixes_are_final_during_backward(cpu_engine, case):
         prev = (a, b)
     assert prev == (P.n_reg, P.n_train), "every trainable parameter has a gradient producer"
     assert snaps[1][0][1] > P.n_reg, "half-way through backward a non-empty prefix is already final"
+
+
+def test_reduce_lr_on_plateau_keras_semantics():
+    """ss.py:978-982: monitor loss, patience 5, min_lr 1e-8 — the learning rate drops by `factor` after `patience`
+    epochs without an improvement larger than min_delta, never below min_lr, and Adam's step size follows."""
+    from deeplabv3plus_keras_b200.deeplab import Adam, ReduceLROnPlateau
+    opt = Adam(lr=1e-4, beta_1=0.5, beta_2=0.99)
+    cb = ReduceLROnPlateau(opt, monitor="loss", factor=0.5, patience=5, min_lr=3e-5)
+    lrs = [cb.on_epoch_end(v) for v in [1.0, 0.9, 0.9, 0.9, 0.9, 0.9, 0.9, 0.89995, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5]]
+    assert lrs[:6] == [1e-4] * 6                  # epochs 2..6 are the 5 patient ones
+    assert lrs[6] == 5e-5 and lrs[7] == 5e-5      # reduced once; 0.89995 is within min_delta of the best
+    assert lrs[8] == 5e-5 and lrs[-1] == 3e-5     # improvement resets the wait; second reduction clamps at min_lr
+    t1 = opt.step_size()
+    opt.lr = 1e-4
+    assert abs(opt.step_size() / t1 - 1e-4 / 3e-5) < 1e-9
+    with pytest.raises(ValueError):
+        ReduceLROnPlateau(opt, factor=1.0)
