@@ -1169,28 +1169,37 @@ maxpool3x3s2_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t
     __nv_bfloat162 acc[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) acc[k] = __float2bfloat162_rn(0.f);
+    // an input pixel belongs to one window per axis when (coordinate + pad) is odd (tap 1) and to two when it is even
+    // (taps 0 and 2): enumerate the <= 2 x 2 candidates up front so that all their loads are in flight together (the
+    // tap-loop version issued them one window at a time behind data-dependent branches)
+    int hos[2], his[2], wos[2], wis[2];
+    {
+        const int hp = hi + pad_t, wp = wi + pad_l;
+        if (hp & 1) { hos[0] = (hp - 1) >> 1; his[0] = 1; hos[1] = -1; his[1] = 0; }
+        else { hos[0] = hp >> 1; his[0] = 0; hos[1] = (hp >> 1) - 1; his[1] = 2; }
+        if (wp & 1) { wos[0] = (wp - 1) >> 1; wis[0] = 1; wos[1] = -1; wis[1] = 0; }
+        else { wos[0] = wp >> 1; wis[0] = 0; wos[1] = (wp >> 1) - 1; wis[1] = 2; }
+    }
+    uint2 pk[4]; uint4 g[4]; uint32_t tapv[4]; bool ok[4];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const int hn = hi + pad_t - i;
-        if (hn < 0 || (hn & 1)) continue;
-        const int ho = hn >> 1;
-        if (ho >= Ho) continue;
+    for (int a = 0; a < 2; ++a) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const int wn = wi + pad_l - j;
-            if (wn < 0 || (wn & 1)) continue;
-            const int wo = wn >> 1;
-            if (wo >= Wo) continue;
-            const long long off = (((long long)n * Ho + ho) * Wo + wo) * C + c0;
-            const uint2 pk = __ldg(reinterpret_cast<const uint2*>(argmax + off));
-            const uint4 g = __ldg(reinterpret_cast<const uint4*>(dy + off));
-            const uint32_t tapv = (uint32_t)(i * 3 + j) * 0x01010101u;
-            const uint32_t mlo = __vcmpeq4(pk.x, tapv), mhi = __vcmpeq4(pk.y, tapv);
-            uint32_t v[4] = {g.x & __byte_perm(mlo, 0, 0x1100), g.y & __byte_perm(mlo, 0, 0x3322),
-                             g.z & __byte_perm(mhi, 0, 0x1100), g.w & __byte_perm(mhi, 0, 0x3322)};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) acc[k] = __hadd2(acc[k], *reinterpret_cast<__nv_bfloat162*>(&v[k]));
+        for (int b = 0; b < 2; ++b) {
+            const int q = a * 2 + b;
+            ok[q] = hos[a] >= 0 && hos[a] < Ho && wos[b] >= 0 && wos[b] < Wo;
+            tapv[q] = (uint32_t)(his[a] * 3 + wis[b]) * 0x01010101u;
+            const long long off = (((long long)n * Ho + (ok[q] ? hos[a] : 0)) * Wo + (ok[q] ? wos[b] : 0)) * C + c0;
+            pk[q] = ok[q] ? __ldg(reinterpret_cast<const uint2*>(argmax + off)) : make_uint2(0xffffffffu, 0xffffffffu);
+            g[q] = ok[q] ? __ldg(reinterpret_cast<const uint4*>(dy + off)) : make_uint4(0, 0, 0, 0);
         }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t mlo = __vcmpeq4(pk[q].x, tapv[q]), mhi = __vcmpeq4(pk[q].y, tapv[q]);
+        uint32_t v[4] = {g[q].x & __byte_perm(mlo, 0, 0x1100), g[q].y & __byte_perm(mlo, 0, 0x3322),
+                         g[q].z & __byte_perm(mhi, 0, 0x1100), g[q].w & __byte_perm(mhi, 0, 0x3322)};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] = __hadd2(acc[k], *reinterpret_cast<__nv_bfloat162*>(&v[k]));
     }
     const long long off = (((long long)n * H + hi) * W + wi) * C + c0;
     if (addend != nullptr) {
