@@ -1132,6 +1132,73 @@ extern "C" int dlv3p_copy2d(const void* x, int64_t ld_x, void* y, int64_t ld_y, 
                             stream);
 }
 
+namespace dlv3p {
+// bf16 forward max-pool (+ residual add): packed bf16x2 compares (__hgt2_mask) with bitwise selects for the running
+// maximum and the winning tap (16-bit lanes), 32-bit indexing, 2D blocks (16 channel-packs x 16 output columns) that
+// walk kMpRowsF output rows.  First maximum wins (strict >), padding never wins (it is never visited).
+constexpr int kMpRowsF = 4;
+
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                             uint8_t* __restrict__ argmax, int N, int H, int W, int C, int pad_t, int pad_l, int Ho,
+                             int Wo, const __nv_bfloat16* __restrict__ addend, int ncvb) {
+    const int cvb = blockIdx.x % ncvb, wb = blockIdx.x / ncvb;
+    const int cv = cvb * 16 + (int)threadIdx.x;
+    const int wo = wb * 16 + (int)threadIdx.y;
+    if (cv >= (C >> 3) || wo >= Wo) return;
+    const int c0 = cv << 3;
+    const int hblocks = (Ho + kMpRowsF - 1) / kMpRowsF;
+    const int n = blockIdx.y / hblocks;
+    const int h0 = (blockIdx.y % hblocks) * kMpRowsF;
+    const int wi0 = wo * 2 - pad_l;
+    for (int ho = h0; ho < min(h0 + kMpRowsF, Ho); ++ho) {
+        uint32_t best[4], arg[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { best[k] = 0xff80ff80u; arg[k] = 0u; }        // -inf, tap 0
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int hi = ho * 2 - pad_t + i;
+            if (hi < 0 || hi >= H) continue;
+            const int rowoff = ((n * H + hi) * W) * C + c0;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int wi = wi0 + j;
+                if (wi < 0 || wi >= W) continue;
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + rowoff + wi * C));
+                const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+                const uint32_t tap2 = (uint32_t)(i * 3 + j) * 0x00010001u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t m = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&vv[k]),
+                                                   *reinterpret_cast<const __nv_bfloat162*>(&best[k]));
+                    best[k] = (vv[k] & m) | (best[k] & ~m);
+                    arg[k] = (tap2 & m) | (arg[k] & ~m);
+                }
+            }
+        }
+        const int off = ((n * Ho + ho) * Wo + wo) * C + c0;
+        if (argmax != nullptr) {
+            uint2 pk;
+            pk.x = __byte_perm(arg[0], arg[1], 0x6420);
+            pk.y = __byte_perm(arg[2], arg[3], 0x6420);
+            *reinterpret_cast<uint2*>(argmax + off) = pk;
+        }
+        if (addend != nullptr) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(addend + off));
+            const uint32_t av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 p = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&best[k]));
+                const float2 q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&av[k]));
+                const __nv_bfloat162 r = __floats2bfloat162_rn(p.x + q.x, p.y + q.y);
+                best[k] = *reinterpret_cast<const uint32_t*>(&r);
+            }
+        }
+        *reinterpret_cast<uint4*>(y + off) = make_uint4(best[0], best[1], best[2], best[3]);
+    }
+}
+}  // namespace dlv3p
+
 extern "C" int dlv3p_maxpool3x3s2_fwd(const void* x, void* y, uint8_t* argmax, int N, int H, int W, int C,
                                       int pad_t, int pad_l, int Ho, int Wo, const void* addend, int dtype,
                                       void* stream) {
@@ -1139,6 +1206,14 @@ extern "C" int dlv3p_maxpool3x3s2_fwd(const void* x, void* y, uint8_t* argmax, i
     DLV3P_REQUIRE(C % 8 == 0 && aligned16(x) && aligned16(y), DLV3P_ERR_ALIGN, "maxpool_fwd: C %% 8 and alignment");
     cudaStream_t st = (cudaStream_t)stream;
     const long long total = (long long)N * Ho * Wo * (C / 8);
+    if (dtype == DLV3P_BF16 && (addend == nullptr || aligned16(addend)) && (argmax == nullptr || aligned16(argmax)) &&
+        (long long)N * cdiv(Ho, kMpRowsF) <= 65535 && (long long)N * H * W * C < 0x7fffffffLL) {
+        const int ncvb = cdiv(C / 8, 16);
+        maxpool3x3s2_fwd_bf16_kernel<<<dim3(ncvb * cdiv(Wo, 16), N * cdiv(Ho, kMpRowsF)), dim3(16, 16), 0, st>>>(
+            (const __nv_bfloat16*)x, (__nv_bfloat16*)y, argmax, N, H, W, C, pad_t, pad_l, Ho, Wo,
+            (const __nv_bfloat16*)addend, ncvb);
+        return check_launch("maxpool3x3s2_fwd");
+    }
     DLV3P_DISPATCH_DTYPE(dtype, T, {
         maxpool3x3s2_fwd_kernel<T><<<cdiv(total, 256), 256, 0, st>>>((const T*)x, (T*)y, argmax, N, H, W, C, pad_t,
                                                                      pad_l, Ho, Wo, (const T*)addend, total);
@@ -1153,69 +1228,86 @@ namespace dlv3p {
 // window contributions are summed with packed bf16 adds — 16 instructions per window instead of ~40 scalar ones (the
 // scalar kernel was issue-bound at 1.4 TB/s).  Two terms sum exactly like the fp32 path (one rounding); three or four
 // (only even-row/even-column pixels that win several windows) round at most twice more.
+constexpr int kMpRows = 4;          // 2x2 pixel blocks walked by one thread along H
+
+// One thread owns 8 channels of a 2x2 block of input pixels {2a, 2a+1} x {2b, 2b+1} (in padded coordinates): the block
+// touches only the windows {a-1, a} x {b-1, b}, so four (argmax, dy) loads serve four output pixels and nine
+// (pixel, window) pairs — the pixel-per-thread version issued up to four loads per pixel.
 __global__ void __launch_bounds__(256)
 maxpool3x3s2_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ argmax,
                              __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int pad_t, int pad_l, int Ho,
-                             int Wo, const __nv_bfloat16* __restrict__ addend, long long total) {
-    // grid: x = (column, channel-pack) inside one input row, y = (image, row): no 64-bit divisions per thread
-    const int CV = C >> 3;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= W * CV) return;
-    const int c0 = (e % CV) << 3;
-    const int wi = e / CV;
-    const int hi = blockIdx.y % H;
-    const int n = blockIdx.y / H;
-    (void)total;
-    __nv_bfloat162 acc[4];
+                             int Wo, const __nv_bfloat16* __restrict__ addend, int ncvb) {
+    // block = 16 channel-packs x 16 column pairs; grid.x = (channel-pack block, column block), grid.y = (image, row
+    // block).  All index arithmetic is 32-bit and the only divisions are per-block (uniform).
+    const int cvb = blockIdx.x % ncvb, wb = blockIdx.x / ncvb;
+    const int cv = cvb * 16 + (int)threadIdx.x;
+    const int b2 = wb * 16 + (int)threadIdx.y;             // column pair index in padded coordinates
+    const int PW = (W + pad_l + 1) >> 1;                   // number of column pairs covering [pad_l, W + pad_l)
+    const int PH = (H + pad_t + 1) >> 1;
+    if (cv >= (C >> 3) || b2 >= PW) return;
+    const int c0 = cv << 3;
+    const int hblocks = (PH + kMpRows - 1) / kMpRows;
+    const int n = blockIdx.y / hblocks;
+    const int a0 = (blockIdx.y % hblocks) * kMpRows;
+    const int img = n * Ho;
+    const __nv_bfloat162 zero2 = __float2bfloat162_rn(0.f);
+    for (int a2 = a0; a2 < min(a0 + kMpRows, PH); ++a2) {
+        // windows (a2-1+u, b2-1+v), u,v in {0,1}
+        uint2 pk[2][2]; uint4 g[2][2];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) acc[k] = __float2bfloat162_rn(0.f);
-    // an input pixel belongs to one window per axis when (coordinate + pad) is odd (tap 1) and to two when it is even
-    // (taps 0 and 2): enumerate the <= 2 x 2 candidates up front so that all their loads are in flight together (the
-    // tap-loop version issued them one window at a time behind data-dependent branches)
-    int hos[2], his[2], wos[2], wis[2];
-    {
-        const int hp = hi + pad_t, wp = wi + pad_l;
-        if (hp & 1) { hos[0] = (hp - 1) >> 1; his[0] = 1; hos[1] = -1; his[1] = 0; }
-        else { hos[0] = hp >> 1; his[0] = 0; hos[1] = (hp >> 1) - 1; his[1] = 2; }
-        if (wp & 1) { wos[0] = (wp - 1) >> 1; wis[0] = 1; wos[1] = -1; wis[1] = 0; }
-        else { wos[0] = wp >> 1; wis[0] = 0; wos[1] = (wp >> 1) - 1; wis[1] = 2; }
-    }
-    uint2 pk[4]; uint4 g[4]; uint32_t tapv[4]; bool ok[4];
+        for (int u = 0; u < 2; ++u) {
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
+            for (int v = 0; v < 2; ++v) {
+                const int ho = a2 - 1 + u, wo = b2 - 1 + v;
+                const bool ok = ho >= 0 && ho < Ho && wo >= 0 && wo < Wo;
+                const int off = ok ? ((img + ho) * Wo + wo) * C + c0 : 0;
+                pk[u][v] = ok ? __ldg(reinterpret_cast<const uint2*>(argmax + off)) : make_uint2(0xffffffffu, 0xffffffffu);
+                g[u][v] = ok ? __ldg(reinterpret_cast<const uint4*>(dy + off)) : make_uint4(0, 0, 0, 0);
+            }
+        }
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-            const int q = a * 2 + b;
-            ok[q] = hos[a] >= 0 && hos[a] < Ho && wos[b] >= 0 && wos[b] < Wo;
-            tapv[q] = (uint32_t)(his[a] * 3 + wis[b]) * 0x01010101u;
-            const long long off = (((long long)n * Ho + (ok[q] ? hos[a] : 0)) * Wo + (ok[q] ? wos[b] : 0)) * C + c0;
-            pk[q] = ok[q] ? __ldg(reinterpret_cast<const uint2*>(argmax + off)) : make_uint2(0xffffffffu, 0xffffffffu);
-            g[q] = ok[q] ? __ldg(reinterpret_cast<const uint4*>(dy + off)) : make_uint4(0, 0, 0, 0);
+        for (int r = 0; r < 2; ++r) {
+            const int hi = 2 * a2 + r - pad_t;
+            if (hi < 0 || hi >= H) continue;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int wi = 2 * b2 + c - pad_l;
+                if (wi < 0 || wi >= W) continue;
+                __nv_bfloat162 acc[4] = {zero2, zero2, zero2, zero2};
+                // pixel (r, c) of the block is tap (r, c) of window (a2, b2), tap (r, 2) of window (a2, b2-1) when
+                // c == 0, tap (2, c) of window (a2-1, b2) when r == 0, and tap (2, 2) of (a2-1, b2-1) when r == c == 0
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+#pragma unroll
+                    for (int v = 0; v < 2; ++v) {
+                        if ((u == 0 && r != 0) || (v == 0 && c != 0)) continue;
+                        const int ti = (u == 1) ? r : 2, tj = (v == 1) ? c : 2;
+                        const uint32_t tapv = (uint32_t)(ti * 3 + tj) * 0x01010101u;
+                        const uint32_t mlo = __vcmpeq4(pk[u][v].x, tapv), mhi = __vcmpeq4(pk[u][v].y, tapv);
+                        uint32_t w4[4] = {g[u][v].x & __byte_perm(mlo, 0, 0x1100), g[u][v].y & __byte_perm(mlo, 0, 0x3322),
+                                          g[u][v].z & __byte_perm(mhi, 0, 0x1100), g[u][v].w & __byte_perm(mhi, 0, 0x3322)};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) acc[k] = __hadd2(acc[k], *reinterpret_cast<__nv_bfloat162*>(&w4[k]));
+                    }
+                }
+                const int off = ((n * H + hi) * W + wi) * C + c0;
+                if (addend != nullptr) {
+                    const uint4 ad = __ldg(reinterpret_cast<const uint4*>(addend + off));
+                    const uint32_t av[4] = {ad.x, ad.y, ad.z, ad.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 p = __bfloat1622float2(acc[k]);
+                        const float2 q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&av[k]));
+                        acc[k] = __floats2bfloat162_rn(p.x + q.x, p.y + q.y);
+                    }
+                }
+                uint4 o;
+                o.x = *reinterpret_cast<uint32_t*>(&acc[0]); o.y = *reinterpret_cast<uint32_t*>(&acc[1]);
+                o.z = *reinterpret_cast<uint32_t*>(&acc[2]); o.w = *reinterpret_cast<uint32_t*>(&acc[3]);
+                *reinterpret_cast<uint4*>(dx + off) = o;
+            }
         }
     }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const uint32_t mlo = __vcmpeq4(pk[q].x, tapv[q]), mhi = __vcmpeq4(pk[q].y, tapv[q]);
-        uint32_t v[4] = {g[q].x & __byte_perm(mlo, 0, 0x1100), g[q].y & __byte_perm(mlo, 0, 0x3322),
-                         g[q].z & __byte_perm(mhi, 0, 0x1100), g[q].w & __byte_perm(mhi, 0, 0x3322)};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) acc[k] = __hadd2(acc[k], *reinterpret_cast<__nv_bfloat162*>(&v[k]));
-    }
-    const long long off = (((long long)n * H + hi) * W + wi) * C + c0;
-    if (addend != nullptr) {
-        const uint4 a = __ldg(reinterpret_cast<const uint4*>(addend + off));
-        const uint32_t av[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float2 x = __bfloat1622float2(acc[k]);
-            const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&av[k]));
-            acc[k] = __floats2bfloat162_rn(x.x + y.x, x.y + y.y);
-        }
-    }
-    uint4 o;
-    o.x = *reinterpret_cast<uint32_t*>(&acc[0]); o.y = *reinterpret_cast<uint32_t*>(&acc[1]);
-    o.z = *reinterpret_cast<uint32_t*>(&acc[2]); o.w = *reinterpret_cast<uint32_t*>(&acc[3]);
-    *reinterpret_cast<uint4*>(dx + off) = o;
 }
 
 // im2col for channel counts that are not a multiple of 8 (the 3-channel image of block1_conv1 / Conv1): one thread
@@ -1289,10 +1381,13 @@ extern "C" int dlv3p_maxpool3x3s2_bwd(const void* dy, const uint8_t* argmax, voi
     DLV3P_REQUIRE(C % 8 == 0 && aligned16(dy) && aligned16(dx), DLV3P_ERR_ALIGN, "maxpool_bwd: C %% 8 and alignment");
     cudaStream_t st = (cudaStream_t)stream;
     const long long total = (long long)N * H * W * (C / 8);
-    if (dtype == DLV3P_BF16 && (addend == nullptr || aligned16(addend)) && (long long)N * H <= 65535) {
-        maxpool3x3s2_bwd_bf16_kernel<<<dim3(cdiv((long long)W * (C / 8), 256), N * H), 256, 0, st>>>(
+    if (dtype == DLV3P_BF16 && (addend == nullptr || aligned16(addend)) && (long long)N * H <= 65535 &&
+        (long long)N * H * W * C < 0x7fffffffLL) {
+        const int ncvb = cdiv(C / 8, 16);
+        const int PWp = (W + pad_l + 1) / 2, PHp = (H + pad_t + 1) / 2;
+        maxpool3x3s2_bwd_bf16_kernel<<<dim3(ncvb * cdiv(PWp, 16), N * cdiv(PHp, kMpRows)), dim3(16, 16), 0, st>>>(
             (const __nv_bfloat16*)dy, argmax, (__nv_bfloat16*)dx, N, H, W, C, pad_t, pad_l, Ho, Wo,
-            (const __nv_bfloat16*)addend, total);
+            (const __nv_bfloat16*)addend, ncvb);
         return check_launch("maxpool3x3s2_bwd");
     }
     DLV3P_DISPATCH_DTYPE(dtype, T, {
