@@ -685,15 +685,15 @@ bilinear_bwd_kernel(const TI* __restrict__ dy, long long ld_dy, TO* __restrict__
 }
 
 // ---- im2col / col2im / subsample ----------------------------------------------------------------------------
-template <typename T, int V>
+template <typename T, int V, typename I>
 __global__ void __launch_bounds__(256)
 im2col3x3_kernel(const T* __restrict__ x, T* __restrict__ col, int N, int H, int W, int C, int stride, int dil,
-                 int pad_t, int pad_l, int Ho, int Wo, long long ld_col, long long total) {
+                 int pad_t, int pad_l, int Ho, int Wo, long long ld_col, I total) {
     const int JV = (int)(ld_col / V);
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const I idx = (I)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int j0 = (int)(idx % JV) * V;
-    long long p = idx / JV;
+    I p = idx / JV;
     T* dst = col + p * ld_col + j0;
     float f[V];
 #pragma unroll
@@ -701,26 +701,26 @@ im2col3x3_kernel(const T* __restrict__ x, T* __restrict__ col, int N, int H, int
     Pack<T, V> o; o.from_float(f);
     if (j0 < 9 * C) {
         const int tap = j0 / C, c = j0 % C;
-        const int wo = (int)(p % Wo); long long t = p / Wo;
+        const int wo = (int)(p % Wo); I t = p / Wo;
         const int ho = (int)(t % Ho);
         const int n = (int)(t / Ho);
         const int hi = ho * stride - pad_t + (tap / 3) * dil;
         const int wi = wo * stride - pad_l + (tap % 3) * dil;
-        if (hi >= 0 && hi < H && wi >= 0 && wi < W) o.load(x + (((long long)n * H + hi) * W + wi) * C + c);
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) o.load(x + (((I)n * H + hi) * W + wi) * C + c);
     }
     o.store(dst);
 }
 
-template <typename T, int V>
+template <typename T, int V, typename I>
 __global__ void __launch_bounds__(256)
 col2im3x3_kernel(const T* __restrict__ col, T* __restrict__ dx, int N, int H, int W, int C, int stride, int dil,
                  int pad_t, int pad_l, int Ho, int Wo, long long ld_col, const T* __restrict__ addend,
-                 long long total) {
+                 I total) {
     const int CV = C / V;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const I idx = (I)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int c0 = (int)(idx % CV) * V;
-    long long t = idx / CV;
+    I t = idx / CV;
     const int wi = (int)(t % W); t /= W;
     const int hi = (int)(t % H);
     const int n = (int)(t / H);
@@ -739,13 +739,13 @@ col2im3x3_kernel(const T* __restrict__ col, T* __restrict__ dx, int N, int H, in
             if (wn < 0 || (wn % stride) != 0) continue;
             const int wo = wn / stride;
             if (wo >= Wo) continue;
-            Pack<T, V> g; g.load(col + (((long long)n * Ho + ho) * Wo + wo) * ld_col + (i * 3 + j) * C + c0);
+            Pack<T, V> g; g.load(col + (((I)n * Ho + ho) * Wo + wo) * ld_col + (i * 3 + j) * C + c0);
             float gf[V]; g.to_float(gf);
 #pragma unroll
             for (int k = 0; k < V; ++k) acc[k] += gf[k];
         }
     }
-    const long long off = (((long long)n * H + hi) * W + wi) * C + c0;
+    const I off = (((I)n * H + hi) * W + wi) * C + c0;
     if (addend != nullptr) {
         Pack<T, V> a; a.load(addend + off);
         float g[V]; a.to_float(g);
@@ -756,31 +756,31 @@ col2im3x3_kernel(const T* __restrict__ col, T* __restrict__ dx, int N, int H, in
     o.store(dx + off);
 }
 
-template <typename T>
+template <typename T, typename I>
 __global__ void __launch_bounds__(256)
 subsample_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int stride, int Ho,
-                     int Wo, long long total) {
+                     int Wo, I total) {
     const int CV = C >> 3;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const I idx = (I)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int c0 = (int)(idx % CV) << 3;
-    long long t = idx / CV;
+    I t = idx / CV;
     const int wo = (int)(t % Wo); t /= Wo;
     const int ho = (int)(t % Ho);
     const int n = (int)(t / Ho);
-    Vec8<T> v; v.load(x + (((long long)n * H + ho * stride) * W + wo * stride) * C + c0);
-    v.store(y + (((long long)n * Ho + ho) * Wo + wo) * C + c0);
+    Vec8<T> v; v.load(x + (((I)n * H + ho * stride) * W + wo * stride) * C + c0);
+    v.store(y + (((I)n * Ho + ho) * Wo + wo) * C + c0);
 }
 
-template <typename T>
+template <typename T, typename I>
 __global__ void __launch_bounds__(256)
 subsample_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int N, int H, int W, int C, int stride, int Ho,
-                     int Wo, const T* __restrict__ addend, long long total) {
+                     int Wo, const T* __restrict__ addend, I total) {
     const int CV = C >> 3;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const I idx = (I)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int c0 = (int)(idx % CV) << 3;
-    long long t = idx / CV;
+    I t = idx / CV;
     const int wi = (int)(t % W); t /= W;
     const int hi = (int)(t % H);
     const int n = (int)(t / H);
@@ -788,10 +788,10 @@ subsample_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int N, int H,
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.f;
     if ((hi % stride) == 0 && (wi % stride) == 0 && hi / stride < Ho && wi / stride < Wo) {
-        Vec8<T> v; v.load(dy + (((long long)n * Ho + hi / stride) * Wo + wi / stride) * C + c0);
+        Vec8<T> v; v.load(dy + (((I)n * Ho + hi / stride) * Wo + wi / stride) * C + c0);
         v.to_float(acc);
     }
-    const long long off = (((long long)n * H + hi) * W + wi) * C + c0;
+    const I off = (((I)n * H + hi) * W + wi) * C + c0;
     if (addend != nullptr) {
         Vec8<T> a; a.load(addend + off);
         float g[8]; a.to_float(g);
@@ -1497,11 +1497,15 @@ extern "C" int dlv3p_im2col3x3(const void* x, void* col, int N, int H, int W, in
     DLV3P_DISPATCH_DTYPE(dtype, T, {
         if (v8) {
             const long long total = P * (ld_col / 8);
-            im2col3x3_kernel<T, 8><<<cdiv(total, 256), 256, 0, st>>>((const T*)x, (T*)col, N, H, W, C, stride, dil,
-                                                                     pad_t, pad_l, Ho, Wo, ld_col, total);
+            if (P * ld_col < 0x7fffffffLL && (long long)N * H * W * C < 0x7fffffffLL)
+                im2col3x3_kernel<T, 8, int><<<cdiv(total, 256), 256, 0, st>>>((const T*)x, (T*)col, N, H, W, C, stride, dil,
+                                                                              pad_t, pad_l, Ho, Wo, ld_col, (int)total);
+            else
+                im2col3x3_kernel<T, 8, long long><<<cdiv(total, 256), 256, 0, st>>>((const T*)x, (T*)col, N, H, W, C, stride,
+                                                                                    dil, pad_t, pad_l, Ho, Wo, ld_col, total);
         } else {
             const long long total = P * ld_col;
-            im2col3x3_kernel<T, 1><<<cdiv(total, 256), 256, 0, st>>>((const T*)x, (T*)col, N, H, W, C, stride, dil,
+            im2col3x3_kernel<T, 1, long long><<<cdiv(total, 256), 256, 0, st>>>((const T*)x, (T*)col, N, H, W, C, stride, dil,
                                                                      pad_t, pad_l, Ho, Wo, ld_col, total);
         }
         return check_launch("im2col3x3");
@@ -1519,12 +1523,17 @@ extern "C" int dlv3p_col2im3x3(const void* col, void* dx, int N, int H, int W, i
     DLV3P_DISPATCH_DTYPE(dtype, T, {
         if (v8) {
             const long long total = (long long)N * H * W * (C / 8);
-            col2im3x3_kernel<T, 8><<<cdiv(total, 256), 256, 0, st>>>((const T*)col, (T*)dx, N, H, W, C, stride, dil,
-                                                                     pad_t, pad_l, Ho, Wo, ld_col, (const T*)addend,
-                                                                     total);
+            if ((long long)N * Ho * Wo * ld_col < 0x7fffffffLL && (long long)N * H * W * C < 0x7fffffffLL)
+                col2im3x3_kernel<T, 8, int><<<cdiv(total, 256), 256, 0, st>>>((const T*)col, (T*)dx, N, H, W, C, stride, dil,
+                                                                              pad_t, pad_l, Ho, Wo, ld_col, (const T*)addend,
+                                                                              (int)total);
+            else
+                col2im3x3_kernel<T, 8, long long><<<cdiv(total, 256), 256, 0, st>>>((const T*)col, (T*)dx, N, H, W, C, stride,
+                                                                                    dil, pad_t, pad_l, Ho, Wo, ld_col,
+                                                                                    (const T*)addend, total);
         } else {
             const long long total = (long long)N * H * W * C;
-            col2im3x3_kernel<T, 1><<<cdiv(total, 256), 256, 0, st>>>((const T*)col, (T*)dx, N, H, W, C, stride, dil,
+            col2im3x3_kernel<T, 1, long long><<<cdiv(total, 256), 256, 0, st>>>((const T*)col, (T*)dx, N, H, W, C, stride, dil,
                                                                      pad_t, pad_l, Ho, Wo, ld_col, (const T*)addend,
                                                                      total);
         }
@@ -1541,8 +1550,12 @@ extern "C" int dlv3p_subsample_fwd(const void* x, void* y, int N, int H, int W, 
     cudaStream_t st = (cudaStream_t)stream;
     const long long total = (long long)N * Ho * Wo * (C / 8);
     DLV3P_DISPATCH_DTYPE(dtype, T, {
-        subsample_fwd_kernel<T><<<cdiv(total, 256), 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C, stride, Ho, Wo,
-                                                                  total);
+        if ((long long)N * H * W * C < 0x7fffffffLL)
+            subsample_fwd_kernel<T, int><<<cdiv(total, 256), 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C, stride, Ho, Wo,
+                                                                           (int)total);
+        else
+            subsample_fwd_kernel<T, long long><<<cdiv(total, 256), 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C, stride, Ho,
+                                                                                 Wo, total);
         return check_launch("subsample_fwd");
     });
     return 0;
@@ -1555,8 +1568,12 @@ extern "C" int dlv3p_subsample_bwd(const void* dy, void* dx, int N, int H, int W
     cudaStream_t st = (cudaStream_t)stream;
     const long long total = (long long)N * H * W * (C / 8);
     DLV3P_DISPATCH_DTYPE(dtype, T, {
-        subsample_bwd_kernel<T><<<cdiv(total, 256), 256, 0, st>>>((const T*)dy, (T*)dx, N, H, W, C, stride, Ho, Wo,
-                                                                  (const T*)addend, total);
+        if ((long long)N * H * W * C < 0x7fffffffLL)
+            subsample_bwd_kernel<T, int><<<cdiv(total, 256), 256, 0, st>>>((const T*)dy, (T*)dx, N, H, W, C, stride, Ho, Wo,
+                                                                           (const T*)addend, (int)total);
+        else
+            subsample_bwd_kernel<T, long long><<<cdiv(total, 256), 256, 0, st>>>((const T*)dy, (T*)dx, N, H, W, C, stride, Ho,
+                                                                                 Wo, (const T*)addend, total);
         return check_launch("subsample_bwd");
     });
     return 0;

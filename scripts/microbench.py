@@ -112,6 +112,15 @@ am = torch.empty((N, 127, 127, 128), device=dev, dtype=torch.uint8)
 yo = torch.empty((N, 127, 127, 128), device=dev, dtype=bf)
 timeit("maxpool_fwd 254x254x128", lambda: ops.maxpool3x3s2_fwd(x, out=yo, argmax=am))
 timeit("maxpool_bwd 254x254x128", lambda: ops.maxpool3x3s2_bwd(yo, am, x.shape, out=x))
+x1 = t((N, 256, 256, 32))
+colb = torch.empty((N * 254 * 254, 288), device=dev, dtype=bf)
+timeit("im2col 256x256x32 -> K288", lambda: ops.im2col3x3(x1, 1, 1, 254, 254, 0, 0, 288, out=colb))
+timeit("col2im K288 -> 256x256x32", lambda: ops.col2im3x3(colb, x1.shape, 1, 1, 254, 254, 0, 0, 288, out=x1))
+xs = torch.empty((N, 127, 127, 64), device=dev, dtype=bf)
+xb = t((N, 254, 254, 64))
+timeit("subsample_fwd 254x254x64 s2", lambda: ops.subsample_fwd(xb, 2, out=xs))
+timeit("subsample_bwd 254x254x64 s2", lambda: ops.subsample_bwd(xs, xb.shape, 2, out=xb))
+del colb
 zl = t((N, 32, 32, 21), torch.float32)
 lab = torch.randint(0, 21, (N, 512, 512), device=dev, dtype=torch.int32)
 pw, nw = torch.rand(21, device=dev), torch.rand(21, device=dev)
