@@ -19,10 +19,12 @@ namespace dlv3p {
 int launch_dw_conv_tma(const __nv_bfloat16* in, const float* w, __nv_bfloat16* out, int N, int Hin, int Win, int C,
                        int Hout, int Wout, int pad_t, int pad_l, int flip, int in_act, const __nv_bfloat16* mask_src,
                        const float* m_scale, const float* m_shift, int m_act, const __nv_bfloat16* addend,
-                       cudaStream_t st);
+                       cudaStream_t st, const float* in_scale = nullptr, const float* in_shift = nullptr,
+                       const float* bn_mean = nullptr, const float* bn_invstd = nullptr, float* bn_red = nullptr);
 
 int launch_dw_wgrad_tma(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int N, int H, int W, int C, int Ho,
-                        int Wo, int pad_t, int pad_l, int in_act, cudaStream_t st);
+                        int Wo, int pad_t, int pad_l, int in_act, cudaStream_t st, const float* in_scale = nullptr,
+                        const float* in_shift = nullptr);
 
 template <typename T, int TW, bool DENSE_W, bool HAS_AFFINE, bool HAS_EPI>
 __global__ void __launch_bounds__(256)
@@ -439,9 +441,10 @@ extern "C" int dlv3p_dwconv3x3_fwd(const void* x, const float* w, void* y, int N
     DLV3P_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), DLV3P_ERR_SHAPE,
                   "dwconv3x3_fwd: in_scale and in_shift must both be given or both be NULL");
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == DLV3P_BF16 && stride == 1 && dil_h == 1 && dil_w == 1 && in_scale == nullptr) {
+    if (dtype == DLV3P_BF16 && stride == 1 && dil_h == 1 && dil_w == 1) {
+        // (with in_scale: BatchNormalization + ReLU/ReLU6 of the producing layer fused on load, NaN-filled halo)
         rc = launch_dw_conv_tma((const __nv_bfloat16*)x, w, (__nv_bfloat16*)y, N, H, W, C, Ho, Wo, pad_t, pad_l, 0,
-                                in_act, nullptr, nullptr, nullptr, 0, nullptr, st);
+                                in_act, nullptr, nullptr, nullptr, 0, nullptr, st, in_scale, in_shift);
         if (rc != 0) return rc < 0 ? rc : 0;
     }
     DLV3P_DISPATCH_DTYPE(dtype, T, {
@@ -488,6 +491,24 @@ extern "C" int dlv3p_dwconv3x3_dgrad(const void* dy, const float* w, void* dx, i
     return 0;
 }
 
+extern "C" int dlv3p_dwconv3x3_dgrad_bnred(const void* dy, const float* w, void* dx, int N, int H, int W, int C,
+                                           int pad_t, int pad_l, int Ho, int Wo, const void* x_pre,
+                                           const float* in_scale, const float* in_shift, int in_act,
+                                           const float* bn_mean, const float* bn_invstd, float* bn_red, int dtype,
+                                           void* stream) {
+    int rc = check_dw_args(dy, w, dx, N, H, W, C, 1, 1, 1, Ho, Wo);
+    if (rc) return rc;
+    DLV3P_REQUIRE(x_pre && in_scale && in_shift && in_act != DLV3P_ACT_NONE && bn_mean && bn_invstd && bn_red,
+                  DLV3P_ERR_SHAPE, "dwconv3x3_dgrad_bnred: x_pre, in_scale/in_shift, an activation and the BN operands are required");
+    DLV3P_REQUIRE(dtype == DLV3P_BF16, DLV3P_ERR_DTYPE, "dwconv3x3_dgrad_bnred: bf16 only (use dgrad + bn_bwd_reduce)");
+    rc = launch_dw_conv_tma((const __nv_bfloat16*)dy, w, (__nv_bfloat16*)dx, N, Ho, Wo, C, H, W, 2 - pad_t, 2 - pad_l, 1,
+                            DLV3P_ACT_NONE, (const __nv_bfloat16*)x_pre, in_scale, in_shift, in_act, nullptr,
+                            (cudaStream_t)stream, nullptr, nullptr, bn_mean, bn_invstd, bn_red);
+    if (rc < 0) return rc;
+    DLV3P_REQUIRE(rc == 1, DLV3P_ERR_CUDA, "dwconv3x3_dgrad_bnred: the TMA path is unavailable");
+    return 0;
+}
+
 extern "C" int dlv3p_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int C,
                                      int stride, int dil_h, int dil_w, int pad_t, int pad_l, int Ho, int Wo,
                                      const float* in_scale, const float* in_shift, int in_act, int dtype,
@@ -497,9 +518,9 @@ extern "C" int dlv3p_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, i
     cudaStream_t st = (cudaStream_t)stream;
     const int CV = C / 8;
     const long long npix = (long long)N * Ho * Wo;
-    if (dtype == DLV3P_BF16 && stride == 1 && dil_h == 1 && dil_w == 1 && in_scale == nullptr) {
+    if (dtype == DLV3P_BF16 && stride == 1 && dil_h == 1 && dil_w == 1) {
         rc = launch_dw_wgrad_tma((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw, N, H, W, C, Ho, Wo, pad_t, pad_l,
-                                 in_act, st);
+                                 in_act, st, in_scale, in_shift);
         if (rc != 0) return rc < 0 ? rc : 0;
     }
     DLV3P_DISPATCH_DTYPE(dtype, T, {

@@ -27,9 +27,25 @@ struct DwTmaParams {
     __nv_bfloat16* out;
     const __nv_bfloat16* mask_src; const float* m_scale; const float* m_shift; int m_act;
     const __nv_bfloat16* addend;
+    const float* in_scale; const float* in_shift;             // IN_AFFINE: x := act(in_scale*x + in_shift) on load
+    const float* bn_mean; const float* bn_invstd; float* bn_red;   // STATS: BN-backward reductions of the masked result
     int tiles_h, tiles_w, tiles_c;
     int spatial_tiles, ctas_per_cb;
 };
+
+// fused BatchNormalization + ReLU/ReLU6 on load (IN_AFFINE): the tile arrives through a tensor map whose out-of-bounds
+// fill is NaN, NaN survives the affine map and max(NaN, 0) = 0 (FMNMX returns the non-NaN operand), so the
+// convolution's zero padding comes out exact without a single border predicate in the row loop.
+template <int ACT>
+__device__ __forceinline__ void affine_act4(float2 (&f)[2], const float2 (&sc)[2], const float2 (&sh)[2]) {
+    static_assert(ACT != DLV3P_ACT_NONE, "the NaN padding needs a clamping activation");
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        f[k] = __ffma2_rn(f[k], sc[k], sh[k]);
+        f[k].x = fmaxf(f[k].x, 0.f); f[k].y = fmaxf(f[k].y, 0.f);
+        if (ACT == DLV3P_ACT_RELU6) { f[k].x = fminf(f[k].x, 6.f); f[k].y = fminf(f[k].y, 6.f); }
+    }
+}
 
 // 4 bf16 (uint2) -> optional packed ReLU/ReLU6 -> two float2
 __device__ __forceinline__ void widen4(uint2 raw, int act, float2 (&f)[2]) {
@@ -83,7 +99,7 @@ struct DwStageCfg {
     static constexpr int kAddOff = kDwStageBytes + (M_ACT != DLV3P_ACT_NONE ? kEpiBytes : 0);
 };
 
-template <int IN_ACT, int M_ACT, bool M_AFFINE, bool HAS_ADD>
+template <int IN_ACT, int M_ACT, bool M_AFFINE, bool HAS_ADD, bool IN_AFFINE, bool STATS>
 __global__ void __launch_bounds__(kDwThreads, 1)
 dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_mask,
                    const __grid_constant__ CUtensorMap tm_add, const DwTmaParams p) {
@@ -140,6 +156,8 @@ dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
     // filter taps of this thread's 4 channels as packed pairs (flipped for the input gradient)
     float2 wgt[9][2];
     float msc[4] = {1.f, 1.f, 1.f, 1.f}, msh[4] = {0.f, 0.f, 0.f, 0.f};
+    float2 isc[2], ish[2];
+    float bs1[4] = {0.f, 0.f, 0.f, 0.f}, bs2[4] = {0.f, 0.f, 0.f, 0.f};
     const bool ch_ok = c0 < p.C;
     if (ch_ok) {
 #pragma unroll
@@ -147,6 +165,12 @@ dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
             const int tap = p.flip ? (8 - a) : a;
             const float4 v = __ldg(reinterpret_cast<const float4*>(p.w + tap * p.C + c0));
             wgt[a][0] = make_float2(v.x, v.y); wgt[a][1] = make_float2(v.z, v.w);
+        }
+        if (IN_AFFINE) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(p.in_scale + c0));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.in_shift + c0));
+            isc[0] = make_float2(a.x, a.y); isc[1] = make_float2(a.z, a.w);
+            ish[0] = make_float2(b.x, b.y); ish[1] = make_float2(b.z, b.w);
         }
         if (M_ACT != DLV3P_ACT_NONE && M_AFFINE) {
 #pragma unroll
@@ -179,7 +203,12 @@ dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
                     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];"
                                  : "=r"(raw.x), "=r"(raw.y)
                                  : "r"(base + (uint32_t)((row * (kDwTW + 2) + j) * (kDwCB * 2))));
-                    widen4_t<IN_ACT>(raw, dst[j]);
+                    if (IN_AFFINE) {
+                        widen4_t<DLV3P_ACT_NONE>(raw, dst[j]);
+                        affine_act4<IN_AFFINE ? (IN_ACT == DLV3P_ACT_NONE ? DLV3P_ACT_RELU : IN_ACT) : DLV3P_ACT_RELU>(dst[j], isc, ish);
+                    } else {
+                        widen4_t<IN_ACT>(raw, dst[j]);
+                    }
                 }
             };
             auto lds_epi = [&](int byte_off, int r) {
@@ -220,6 +249,7 @@ dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
                             const float v = M_AFFINE ? fmaf(u[k], msc[k], msh[k]) : u[k];
                             const bool on = (M_ACT == DLV3P_ACT_RELU) ? (v > 0.f) : (v > 0.f && v < 6.f);
                             f[k] = on ? f[k] : 0.f;
+                            if (STATS) { bs1[k] += f[k]; bs2[k] = fmaf(f[k], u[k], bs2[k]); }
                         }
                     }
                     if (HAS_ADD) {
@@ -252,21 +282,42 @@ dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
         }
         __syncthreads();                     // everyone is done reading stage s: it may be refilled next iteration
     }
+    if (STATS) {
+        // BatchNormalization-backward reductions of the layer that produced the mask source y (its raw conv output):
+        // red[0..C) += sum g, red[C..2C) += sum g*xhat with g = the masked gradient written above and
+        // sum g*xhat = invstd * (sum g*y - mean * sum g) — the contract of dlv3p_bn_bwd_reduce.  Every TMA box this CTA
+        // issued has been consumed: stage 0 is reused as the [2][32 cols][64 ch] reduction buffer.
+        float* red = reinterpret_cast<float*>(smem);
+        *reinterpret_cast<float4*>(red + col * kDwCB + cq * 4) = make_float4(bs1[0], bs1[1], bs1[2], bs1[3]);
+        *reinterpret_cast<float4*>(red + (kDwTW + col) * kDwCB + cq * 4) = make_float4(bs2[0], bs2[1], bs2[2], bs2[3]);
+        __syncthreads();
+        if (tid < kDwCB) {
+            const int ch = cb * kDwCB + tid;
+            if (ch < p.C) {
+                float a1 = 0.f, a2 = 0.f;
+#pragma unroll 8
+                for (int q = 0; q < kDwTW; ++q) { a1 += red[q * kDwCB + tid]; a2 += red[(kDwTW + q) * kDwCB + tid]; }
+                a2 = (a2 - __ldg(p.bn_mean + ch) * a1) * __ldg(p.bn_invstd + ch);
+                atomicAdd(p.bn_red + ch, a1);
+                atomicAdd(p.bn_red + p.C + ch, a2);
+            }
+        }
+    }
 }
 
-template <int IN_ACT, int M_ACT, bool M_AFFINE, bool HAS_ADD>
+template <int IN_ACT, int M_ACT, bool M_AFFINE, bool HAS_ADD, bool IN_AFFINE = false, bool STATS = false>
 static int launch_dw_tma_inst(const CUtensorMap& tm, const CUtensorMap& tmm, const CUtensorMap& tma,
                               const DwTmaParams& p, int grid, cudaStream_t st) {
     using Cfg = DwStageCfg<M_ACT, HAS_ADD>;
     constexpr int smem = Cfg::kStages * Cfg::kStageBytes + 128 + 64;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(dw_conv_tma_kernel<IN_ACT, M_ACT, M_AFFINE, HAS_ADD>,
+        cudaError_t e = cudaFuncSetAttribute(dw_conv_tma_kernel<IN_ACT, M_ACT, M_AFFINE, HAS_ADD, IN_AFFINE, STATS>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         DLV3P_REQUIRE(e == cudaSuccess, DLV3P_ERR_CUDA, "cudaFuncSetAttribute(dw tma smem=%d): %s", smem, cudaGetErrorString(e));
         configured = true;
     }
-    launch_pdl(dw_conv_tma_kernel<IN_ACT, M_ACT, M_AFFINE, HAS_ADD>, dim3(grid), dim3(kDwThreads), smem, st, tm, tmm, tma, p);
+    launch_pdl(dw_conv_tma_kernel<IN_ACT, M_ACT, M_AFFINE, HAS_ADD, IN_AFFINE, STATS>, dim3(grid), dim3(kDwThreads), smem, st, tm, tmm, tma, p);
     return check_launch("dwconv3x3 (tma)");
 }
 
@@ -274,12 +325,17 @@ static int launch_dw_tma_inst(const CUtensorMap& tm, const CUtensorMap& tmm, con
 int launch_dw_conv_tma(const __nv_bfloat16* in, const float* w, __nv_bfloat16* out, int N, int Hin, int Win, int C,
                        int Hout, int Wout, int pad_t, int pad_l, int flip, int in_act, const __nv_bfloat16* mask_src,
                        const float* m_scale, const float* m_shift, int m_act, const __nv_bfloat16* addend,
-                       cudaStream_t st) {
+                       cudaStream_t st, const float* in_scale, const float* in_shift, const float* bn_mean,
+                       const float* bn_invstd, float* bn_red) {
     if (get_encode_fn() == nullptr) return 0;
     if (mask_src == nullptr) m_act = DLV3P_ACT_NONE;
     if (in_act != DLV3P_ACT_NONE && (m_act != DLV3P_ACT_NONE || addend != nullptr)) return 0;   // not a used combination
+    const bool in_aff = (in_scale != nullptr);
+    if (in_aff && (in_act == DLV3P_ACT_NONE || (C & 3))) return 0;          // NaN padding needs a clamping activation
+    const bool stats = (bn_red != nullptr);
+    if (stats && (m_act == DLV3P_ACT_NONE || m_scale == nullptr || addend != nullptr || in_aff)) return 0;
     CUtensorMap tm, tmm, tma;
-    int rc = make_tmap_nhwc(&tm, in, N, Hin, Win, C, kDwCB, kDwTW + 2, kDwTH + 2);
+    int rc = make_tmap_nhwc(&tm, in, N, Hin, Win, C, kDwCB, kDwTW + 2, kDwTH + 2, /*nan_fill=*/in_aff);
     if (rc) return rc;
     tmm = tm; tma = tm;                          // placeholders when the operand is absent (never dereferenced)
     if (m_act != DLV3P_ACT_NONE) {
@@ -294,6 +350,7 @@ int launch_dw_conv_tma(const __nv_bfloat16* in, const float* w, __nv_bfloat16* o
     p.N = N; p.Hin = Hin; p.Win = Win; p.C = C; p.Hout = Hout; p.Wout = Wout; p.pad_t = pad_t; p.pad_l = pad_l;
     p.flip = flip; p.in_act = in_act; p.w = w; p.out = out; p.mask_src = mask_src; p.m_scale = m_scale;
     p.m_shift = m_shift; p.m_act = m_act; p.addend = addend;
+    p.in_scale = in_scale; p.in_shift = in_shift; p.bn_mean = bn_mean; p.bn_invstd = bn_invstd; p.bn_red = bn_red;
     p.tiles_h = cdiv(Hout, kDwTH); p.tiles_w = cdiv(Wout, kDwTW); p.tiles_c = cdiv(C, kDwCB);
     const long long nt = (long long)N * p.tiles_h * p.tiles_w;
     if (nt > 0x7fffffffLL) return 0;
@@ -305,7 +362,13 @@ int launch_dw_conv_tma(const __nv_bfloat16* in, const float* w, __nv_bfloat16* o
     const bool aff = (m_scale != nullptr);
     const bool add = (addend != nullptr);
 #define DLV3P_DW(IA, MA, AF, AD) rc = launch_dw_tma_inst<IA, MA, AF, AD>(tm, tmm, tma, p, grid, st)
-    if (m_act == DLV3P_ACT_NONE && !add) {
+    if (in_aff) {
+        if (in_act == DLV3P_ACT_RELU) rc = launch_dw_tma_inst<1, 0, false, false, true, false>(tm, tmm, tma, p, grid, st);
+        else rc = launch_dw_tma_inst<2, 0, false, false, true, false>(tm, tmm, tma, p, grid, st);
+    } else if (stats) {
+        if (m_act == DLV3P_ACT_RELU) rc = launch_dw_tma_inst<0, 1, true, false, false, true>(tm, tmm, tma, p, grid, st);
+        else rc = launch_dw_tma_inst<0, 2, true, false, false, true>(tm, tmm, tma, p, grid, st);
+    } else if (m_act == DLV3P_ACT_NONE && !add) {
         if (in_act == DLV3P_ACT_NONE) DLV3P_DW(0, 0, false, false);
         else if (in_act == DLV3P_ACT_RELU) DLV3P_DW(1, 0, false, false);
         else DLV3P_DW(2, 0, false, false);
@@ -335,12 +398,13 @@ constexpr int kWgStageBytes = kDwStageBytes + kWgDyBytes;                 // 76,
 constexpr int kWgStages = 3;
 
 struct DwWgradParams {
+    const float* in_scale; const float* in_shift;             // IN_AFFINE: x := act(in_scale*x + in_shift) on load
     int N, C, Ho, Wo, pad_t, pad_l, in_act;
     float* dw;                              // [3,3,C] fp32, accumulated
     int tiles_h, tiles_w, ctas_per_cb, spatial_tiles;
 };
 
-template <int IN_ACT>
+template <int IN_ACT, bool IN_AFFINE>
 __global__ void __launch_bounds__(kDwThreads, 1)
 dw_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy,
                     const DwWgradParams p) {
@@ -382,6 +446,15 @@ dw_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     float2 acc[9][2];
 #pragma unroll
     for (int a = 0; a < 9; ++a) { acc[a][0] = make_float2(0.f, 0.f); acc[a][1] = make_float2(0.f, 0.f); }
+    float2 isc[2], ish[2];
+    if (IN_AFFINE) {
+        // channels beyond C compute garbage from NaN-filled lanes; they are never written (ch < p.C below)
+        const int c0 = min(cb * kDwCB + cq * 4, p.C - 4);
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p.in_scale + c0));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.in_shift + c0));
+        isc[0] = make_float2(a.x, a.y); isc[1] = make_float2(a.z, a.w);
+        ish[0] = make_float2(b.x, b.y); ish[1] = make_float2(b.z, b.w);
+    }
     uint32_t it = 0;
     for (; tile < p.spatial_tiles; tile += gstride, ++it) {
         const int s = it % kWgStages;
@@ -398,7 +471,12 @@ dw_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                 asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];"
                              : "=r"(raw.x), "=r"(raw.y)
                              : "r"(xbase + (uint32_t)((row * (kDwTW + 2) + j) * (kDwCB * 2))));
-                widen4_t<IN_ACT>(raw, dst[j]);
+                if (IN_AFFINE) {
+                    widen4_t<DLV3P_ACT_NONE>(raw, dst[j]);
+                    affine_act4<IN_ACT == DLV3P_ACT_NONE ? DLV3P_ACT_RELU : IN_ACT>(dst[j], isc, ish);
+                } else {
+                    widen4_t<IN_ACT>(raw, dst[j]);
+                }
             }
         };
         auto accum = [&](int r, const float2 (&ra)[3][2], const float2 (&rb)[3][2], const float2 (&rc)[3][2]) {
@@ -453,15 +531,19 @@ dw_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
 
 // Returns 1 if the TMA kernel took the launch, 0 if the caller must use the direct kernel, < 0 on error.
 int launch_dw_wgrad_tma(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int N, int H, int W, int C, int Ho,
-                        int Wo, int pad_t, int pad_l, int in_act, cudaStream_t st) {
+                        int Wo, int pad_t, int pad_l, int in_act, cudaStream_t st, const float* in_scale,
+                        const float* in_shift) {
     if (get_encode_fn() == nullptr) return 0;
+    const bool in_aff = (in_scale != nullptr);
+    if (in_aff && (in_act == DLV3P_ACT_NONE || (C & 3))) return 0;          // NaN padding needs a clamping activation
     CUtensorMap tmx, tmg;
-    int rc = make_tmap_nhwc(&tmx, x, N, H, W, C, kDwCB, kDwTW + 2, kDwTH + 2);
+    int rc = make_tmap_nhwc(&tmx, x, N, H, W, C, kDwCB, kDwTW + 2, kDwTH + 2, /*nan_fill=*/in_aff);
     if (rc) return rc;
     rc = make_tmap_nhwc(&tmg, dy, N, Ho, Wo, C, kDwCB, kDwTW, kDwTH);
     if (rc) return rc;
     DwWgradParams p;
     p.N = N; p.C = C; p.Ho = Ho; p.Wo = Wo; p.pad_t = pad_t; p.pad_l = pad_l; p.in_act = in_act; p.dw = dw;
+    p.in_scale = in_scale; p.in_shift = in_shift;
     p.tiles_h = cdiv(Ho, kDwTH); p.tiles_w = cdiv(Wo, kDwTW);
     const int tiles_c = cdiv(C, kDwCB);
     const long long spatial = (long long)N * p.tiles_h * p.tiles_w;
@@ -473,15 +555,19 @@ int launch_dw_wgrad_tma(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* 
     constexpr int smem = kWgStages * kWgStageBytes + 128 + 64;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(dw_wgrad_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(dw_wgrad_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(dw_wgrad_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(dw_wgrad_tma_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(dw_wgrad_tma_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(dw_wgrad_tma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(dw_wgrad_tma_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(dw_wgrad_tma_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         DLV3P_REQUIRE(e == cudaSuccess, DLV3P_ERR_CUDA, "cudaFuncSetAttribute(dw wgrad tma smem=%d): %s", smem, cudaGetErrorString(e));
         configured = true;
     }
-    if (in_act == DLV3P_ACT_NONE) launch_pdl(dw_wgrad_tma_kernel<0>, dim3(tiles_c * per), dim3(kDwThreads), smem, st, tmx, tmg, p);
-    else if (in_act == DLV3P_ACT_RELU) launch_pdl(dw_wgrad_tma_kernel<1>, dim3(tiles_c * per), dim3(kDwThreads), smem, st, tmx, tmg, p);
-    else launch_pdl(dw_wgrad_tma_kernel<2>, dim3(tiles_c * per), dim3(kDwThreads), smem, st, tmx, tmg, p);
+    if (in_aff && in_act == DLV3P_ACT_RELU) launch_pdl(dw_wgrad_tma_kernel<1, true>, dim3(tiles_c * per), dim3(kDwThreads), smem, st, tmx, tmg, p);
+    else if (in_aff) launch_pdl(dw_wgrad_tma_kernel<2, true>, dim3(tiles_c * per), dim3(kDwThreads), smem, st, tmx, tmg, p);
+    else if (in_act == DLV3P_ACT_NONE) launch_pdl(dw_wgrad_tma_kernel<0, false>, dim3(tiles_c * per), dim3(kDwThreads), smem, st, tmx, tmg, p);
+    else if (in_act == DLV3P_ACT_RELU) launch_pdl(dw_wgrad_tma_kernel<1, false>, dim3(tiles_c * per), dim3(kDwThreads), smem, st, tmx, tmg, p);
+    else launch_pdl(dw_wgrad_tma_kernel<2, false>, dim3(tiles_c * per), dim3(kDwThreads), smem, st, tmx, tmg, p);
     rc = check_launch("dwconv3x3_wgrad (tma)");
     return rc ? rc : 1;
 }

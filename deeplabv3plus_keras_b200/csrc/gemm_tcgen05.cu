@@ -57,6 +57,7 @@ struct GemmParams {
     int splits;                        // WGRAD: number of pixel-range splits
     int n_tiles, m_tiles;              // output tile grid
     int tma_store;                     // epilogue through the smem staging tile + TMA store / reduce-add
+    int dbg;                           // diagnostics only (DLV3P_GEMM_DBG): 1 = no operand loads, 2 = no epilogue work, 4 = no MMAs, 8 = no C stores, 16 = no TMEM reads
 };
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -142,7 +143,12 @@ __device__ __forceinline__ void staged_tile_epilogue(const GemmParams& p, const 
 #pragma unroll
         for (int h = 0; h < CW / 32; ++h) {
             uint32_t raw[32];
-            tc_ld_32x32b_x32(acc_tmem + (uint32_t)(ch * CW + h * 32), raw);
+            if (p.dbg & 16) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) raw[j] = 0x3f800000u + (uint32_t)(lane + j);
+            } else {
+                tc_ld_32x32b_x32(acc_tmem + (uint32_t)(ch * CW + h * 32), raw);
+            }
             if (ch + 2 >= n_chunks && h == CW / 32 - 1) {
                 // every TMEM read of this warp in this accumulator stage has completed: hand it back to the MMA warp
                 tc_fence_before();
@@ -187,7 +193,7 @@ __device__ __forceinline__ void staged_tile_epilogue(const GemmParams& p, const 
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0 && rbase < (WGRAD ? p.K : p.M)) {
+        if (lane == 0 && rbase < (WGRAD ? p.K : p.M) && !(p.dbg & 8)) {
             if (WGRAD) tma_reduce_add_2d(tmC, stg, n_base, rbase);
             else tma_store_2d(tmC, stg, n_base, rbase);
             tma_commit_group();
@@ -634,6 +640,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     mbar_wait(empty_bar + 8 * s, ph ^ 1u);
                     const uint32_t a_dst = smem_base + s * STAGE_BYTES;
                     const uint32_t b_dst = a_dst + A_BYTES;
+                    if (p.dbg & 1) { if (leader) mbar_arrive(full_bar + 8 * s); continue; }
                     if (leader) mbar_expect_tx(full_bar + 8 * s, 2 * STAGE_BYTES);     // both CTAs' boxes
                     const uint32_t fb = leader_full + 8 * s;
                     if (WGRAD) {
@@ -678,7 +685,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         // 64-element MN chunk (one 8 KB box), SBO = next 8 K-rows, a K=16 step is 16 rows of 128 B
                         const uint64_t ad = WGRAD ? umma_desc(a_src + k * 2048, 8192, 1024) : umma_desc(a_src + k * 32, 16, 1024);
                         const uint64_t bd = WGRAD ? umma_desc(b_src + k * 2048, 8192, 1024) : umma_desc(b_src + k * 32, 16, 1024);
-                        tc_mma_bf16_2sm(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        if (!(p.dbg & 4)) tc_mma_bf16_2sm(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
                     tc_commit_2sm(empty_bar + 8 * s);          // slot reusable in BOTH CTAs once these MMAs retire
                 }
@@ -700,6 +707,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t as = t & 1u;
             mbar_wait(tmem_full_bar + 8 * as, (t >> 1) & 1u);
             tc_fence_after();
+            if (p.dbg & 2) {
+                if (lane == 0) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_tmem_empty + 8 * as) : "memory");
+                continue;
+            }
             staged_tile_epilogue<BLOCK_N, WGRAD, true>(p, &tmC, tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N,
                                                        row0 + q * 32, col0, lane, half, stg0, buf,
                                                        leader_tmem_empty + 8 * as, stat_smem, use_smem_stats);
@@ -762,6 +773,14 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
 }
 
 static int g_gemm_2cta = -1;      // DLV3P_GEMM_2CTA=0 disables the 2-CTA path (A/B measurements)
+// DLV3P_GEMM_DBG (re-read on every call once DLV3P_GEMM_DBG_ENABLE is set at first use): bottleneck decomposition of the
+// 2-CTA kernel by switching off operand loads (1), epilogue work (2) and/or MMAs (4); results are garbage by design
+static int gemm_dbg_mode() {
+    static const bool enabled = getenv("DLV3P_GEMM_DBG_ENABLE") != nullptr;
+    if (!enabled) return 0;
+    const char* e = getenv("DLV3P_GEMM_DBG");
+    return e ? atoi(e) : 0;
+}
 
 }  // namespace dlv3p
 
@@ -788,6 +807,7 @@ extern "C" int dlv3p_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
     p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.c_dtype = c_dtype;
     p.col_scale = col_scale; p.col_shift = col_shift; p.act = act;
     p.addend = addend; p.ld_add = ld_addend; p.col_stats = col_stats; p.kb_per_split = 0; p.splits = 1;
+    p.dbg = gemm_dbg_mode();
     p.n_tiles = cdiv(N, bn); p.m_tiles = cdiv(M, kBlockM);
     p.tma_store = (c_dtype == DLV3P_BF16 && addend == nullptr && (ldc % 8) == 0 && aligned16(C) && bn >= 64) ? 1 : 0;
     CUtensorMap tmC = tmA;
@@ -830,6 +850,7 @@ extern "C" int dlv3p_gemm_wgrad_bf16(const void* X, int64_t ldx, const void* dY,
     GemmParams p;
     p.M = M; p.N = N; p.K = K; p.C = dW; p.ldc = ldw; p.c_dtype = DLV3P_F32;
     p.col_scale = nullptr; p.col_shift = nullptr; p.act = 0; p.addend = nullptr; p.ld_add = 0; p.col_stats = nullptr;
+    p.dbg = gemm_dbg_mode();
     p.n_tiles = cdiv(N, bn); p.m_tiles = cdiv(K, kBlockM);
     const int tiles = p.n_tiles * p.m_tiles;
     const int total_kb = cdiv(M, kBlockK);

@@ -98,8 +98,9 @@ static inline int make_tmap(CUtensorMap* map, const void* base, long long d0, lo
 
 // 4D bf16 NHWC tensor map (dims C, W, H, N), no swizzle, zero fill outside the tensor: the halo of a tile that
 // crosses the image border comes back as the convolution's zero padding.
+// nan_fill: elements outside the tensor come back as NaN instead (fused BN+ReLU on load, dwconv_tma.cu).
 static inline int make_tmap_nhwc(CUtensorMap* map, const void* base, int N, int H, int W, int C, int box_c, int box_w,
-                                 int box_h) {
+                                 int box_h, bool nan_fill = false) {
     auto fn = get_encode_fn();
     DLV3P_REQUIRE(fn != nullptr, DLV3P_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -108,7 +109,7 @@ static inline int make_tmap_nhwc(CUtensorMap* map, const void* base, int N, int 
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     nan_fill ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DLV3P_REQUIRE(rc == CUDA_SUCCESS, DLV3P_ERR_CUDA,
                   "cuTensorMapEncodeTiled(4D) failed (%d) N=%d H=%d W=%d C=%d box=(%d,%d,%d)", (int)rc, N, H, W, C,
                   box_c, box_w, box_h);

@@ -28,6 +28,25 @@ def _ceil8(n: int) -> int:
     return (n + 7) // 8 * 8
 
 
+def phys_channels(c: int) -> int:
+    """Channel count as laid out in HBM.  Xception's 728-channel tensors have a 1456-byte pixel pitch: every other
+    pixel row starts mid-sector, a 128-byte TMA box row then costs five 32-byte sectors over two L2 lines instead of four
+    over one, and the operand feed of the 728-wide GEMMs drops from 11.5 to 8.2 TB/s (profiles/r1_gemm_feed.md).  Such
+    tensors are stored with the channel axis padded to a multiple of 16 (728 -> 736); the pad channels of every
+    parameter are zero, so the pad activations, their gradients and the pad parameter gradients are exact zeros and
+    Adam leaves them at zero — the logical model is unchanged.  Small / already aligned counts are left alone."""
+    return c if (c < 64 or c % 16 == 0) else (c + 15) // 16 * 16
+
+
+_CHANNEL_AXES = {"depthwise_kernel": (2,), "pointwise_kernel": (2, 3), "kernel": (2, 3), "bias": (0,), "gamma": (0,),
+                 "beta": (0,), "moving_mean": (0,), "moving_variance": (0,)}
+
+
+def _phys_shape(name: str, shape) -> Tuple[int, ...]:
+    axes = _CHANNEL_AXES.get(name, ())
+    return tuple(phys_channels(d) if i in axes else d for i, d in enumerate(shape))
+
+
 class Value:
     """A materialised NHWC activation, its gradient buffer and pending (zero-copy) gradient contributions."""
 
@@ -41,6 +60,7 @@ class Value:
         self.grad_written = False          # plan-time state of the backward schedule
         self.pending: List[torch.Tensor] = []
         self.pre_act = ACT_NONE            # consumers must apply this activation on load (virtual pre-activation)
+        self.clog = self.shape[3]          # logical (Keras) channel count; shape[3] is the physical one (phys_channels)
 
     @property
     def M(self):
@@ -133,8 +153,9 @@ class ParamStore:
         def lay(items, kind, start=0):
             off = start
             for l, n, w in items:
-                self.entries[(id(l), n)] = (kind, off, tuple(w.shape))
-                off += _ceil8(w.size)          # keep every parameter 32-byte aligned
+                pshape = _phys_shape(n, w.shape)       # physical (channel-padded) layout, see phys_channels
+                self.entries[(id(l), n)] = (kind, off, pshape)
+                off += _ceil8(int(np.prod(pshape)))    # keep every parameter 32-byte aligned
             return off
 
         # REVERSE forward order: backward finishes the head first and block1 last, so the gradients of a growing PREFIX
@@ -155,10 +176,16 @@ class ParamStore:
         self.num_params = int(sum(w.size for _, n, w in reg + plain))
 
     def view(self, layer: Layer, name: str, grad=False) -> torch.Tensor:
+        """Contiguous view in the PHYSICAL (channel-padded) shape — what the kernels see."""
         kind, off, shape = self.entries[(id(layer), name)]
         n = int(np.prod(shape))
         arena = (self.g if grad else self.w) if kind == "w" else self.f
         return arena[off:off + n].view(shape)
+
+    def logical(self, layer: Layer, name: str, grad=False) -> torch.Tensor:
+        """The Keras-shaped part of a parameter (pad channels sliced away)."""
+        v = self.view(layer, name, grad)
+        return v[tuple(slice(0, d) for d in layer._weights[name].shape)]
 
     def has(self, layer: Layer, name: str) -> bool:
         return (id(layer), name) in self.entries
@@ -167,23 +194,26 @@ class ParamStore:
         host_w = np.zeros(self.w.numel(), dtype=np.float32)
         host_f = np.zeros(self.f.numel(), dtype=np.float32)
         for l, n, w in self._items:
-            kind, off, _ = self.entries[(id(l), n)]
-            (host_w if kind == "w" else host_f)[off:off + w.size] = w.reshape(-1)
+            kind, off, pshape = self.entries[(id(l), n)]
+            dst = (host_w if kind == "w" else host_f)[off:off + int(np.prod(pshape))].reshape(pshape)
+            dst[tuple(slice(0, d) for d in w.shape)] = w        # pad channels stay zero
         self.w.copy_(torch.from_numpy(host_w))
         self.f.copy_(torch.from_numpy(host_f))
 
     def download(self):
         host_w, host_f = self.w.cpu().numpy(), self.f.cpu().numpy()
         for l, n, w in self._items:
-            kind, off, _ = self.entries[(id(l), n)]
-            w[...] = (host_w if kind == "w" else host_f)[off:off + w.size].reshape(w.shape)
+            kind, off, pshape = self.entries[(id(l), n)]
+            src = (host_w if kind == "w" else host_f)[off:off + int(np.prod(pshape))].reshape(pshape)
+            w[...] = src[tuple(slice(0, d) for d in w.shape)]
 
 
 class Plan:
     """A model lowered for one (batch size, training flag, dtype).  See module docstring."""
 
     def __init__(self, model: Model, batch_size: int, training: bool = False, dtype: Optional[str] = None,
-                 device: Optional[str] = None, dropout_seed: int = 1024, fused_tail: bool = True):
+                 device: Optional[str] = None, dropout_seed: int = 1024, fused_tail: bool = True,
+                 fuse_bn_dw: bool = True):
         fake = getattr(ops, "FAKE", False)       # tests/fake_ops.py test double (host-logic tests without a GPU)
         if not torch.cuda.is_available() and not fake:
             raise RuntimeError("engine.Plan needs a CUDA device: there is no CPU execution path")
@@ -195,6 +225,7 @@ class Plan:
         self.dt = _TORCH_DT[act_dtype]
         self.bf16 = self.dt == torch.bfloat16
         self.fused_tail = fused_tail
+        self.fuse_bn_dw = fuse_bn_dw        # Conv->BN->ReLU->depthwise: BN+ReLU applied on load (False: A/B, materialise it)
         self.dropout_seed = dropout_seed
         self.fwd: List[Callable[[], None]] = []
         self.bwd: List[Tuple[Callable[[], None], bool, Optional[int]]] = []   # (launch, side-stream ok, scratch slot)
@@ -336,6 +367,12 @@ class Plan:
                         m["act"], m["out"], m["tail"] = act_code(nxt.layer), nxt.output, nxt
                         nxt.absorbed = True
                         nxt = sole(nxt.output)
+                        # Conv -> BN -> ReLU whose only reader is a dense-tap depthwise stage: the BN+ReLU output is
+                        # never written, the reader applies it on load (see _BnActValue)
+                        if (nxt is not None and isinstance(nxt.layer, (L.SeparableConv2D, L.DepthwiseConv2D))
+                                and nxt.layer.strides[0] == 1 and tuple(nxt.layer.dilation_rate) == (1, 1)
+                                and nxt.layer.padding == "same"):
+                            m["virt"] = True
                     elif nxt is not None and isinstance(nxt.layer, L.Add) and not nxt.absorbed:
                         other = [i for i in nxt.inputs if i != m["out"]]
                         if len(other) == 1:
@@ -418,15 +455,22 @@ class Plan:
         else:
             Ho, Wo, pt, pl = ops.conv_geometry(H, W, k, stride, dil, lay.padding)
         Mo = N * Ho * Wo
-        Cout = Cin if is_dw else lay.filters
+        Cout = Cin if is_dw else phys_channels(lay.filters)
+        Cout_log = x.clog if is_dw else lay.filters
         out_shape = (N, Ho, Wo, Cout)
-        assert tuple(m["conv"].shape[1:]) == out_shape[1:], (lay.name, m["conv"].shape, out_shape)
+        assert tuple(m["conv"].shape[1:]) == (Ho, Wo, Cout_log), (lay.name, m["conv"].shape, out_shape)
 
         # output dtype: logits (conv without BN feeding the softmax tail) stay fp32
         is_logits = bn_node is None and not is_dw
         y_dtype = torch.float32 if is_logits else self.dt
         ld_out = Cout
-        out = Value(out_shape, y_dtype, self._alloc((N, Ho, Wo, ld_out), y_dtype), lay.name)
+        virt = (bool(m.get("virt")) and self.fuse_bn_dw and training and bn_node is not None and act != ACT_NONE
+                and other_id is None and m["out"] != out_id and Cout % 8 == 0)
+        if virt:
+            out = _BnActValue(out_shape, y_dtype, lay.name, act)       # buffers / BN operands attached below
+        else:
+            out = Value(out_shape, y_dtype, self._alloc((N, Ho, Wo, ld_out), y_dtype), lay.name)
+        out.clog = Cout_log
         self.values[m["out"]] = out
         other = self.values[other_id] if other_id is not None else None
         needs_in_grad = x.needs_grad
@@ -471,6 +515,8 @@ class Plan:
                 if not red_direct:
                     red_slot = self._stat_slot(C)
                 y = self._alloc((N, Ho, Wo, Cout), self.dt)          # raw conv output, saved for backward
+                if virt:
+                    out.attach(y, scale, shift, mean, invstd, red_slot)
             else:
                 self.prep.append(lambda: ops.bn_fold(gamma, beta, mm, mv, C, bn.epsilon, scale, shift))
                 y = None
@@ -478,6 +524,7 @@ class Plan:
             y = out.buf
 
         in_act = x.pre_act
+        in_sc, in_sh = getattr(x, "pre_scale", None), getattr(x, "pre_shift", None)
         pad4 = (Ho, Wo, pt, pl)
         xb = x.buf
         launches_f = 0
@@ -490,7 +537,8 @@ class Plan:
             if is_dw and dw_out is None:
                 # inference depthwise+BN: conv into `out`, then fold BN in place
                 dw_out = out.buf
-            self.fwd.append(lambda: ops.dwconv3x3_fwd(xb, dw_w, stride, dil, in_act=in_act, out=dw_out, pad=pad4))
+            self.fwd.append(lambda: ops.dwconv3x3_fwd(xb, dw_w, stride, dil, in_scale=in_sc, in_shift=in_sh,
+                                                      in_act=in_act, out=dw_out, pad=pad4))
             launches_f += 1
             A, lda = d, Cin
         elif k == 1 and stride == 1:
@@ -530,7 +578,13 @@ class Plan:
                 self.fwd.append(lambda: ops.bn_stats(y, Mo, Cout, stat()))
                 launches_f += 1
             upd = bn_node.calls
-            if Cout % 8 == 0:
+            if virt:
+                # statistics -> scale/shift (+ moving statistics); the BN+ReLU map itself runs inside the reader
+                for r in range(upd):
+                    self.fwd.append(lambda r=r: ops.bn_finalize(stat(), gamma, beta, mm, mv, Cout, Mo, bn.epsilon,
+                                                                bn.momentum, scale, shift, mean, invstd, True))
+                    launches_f += 1
+            elif Cout % 8 == 0:
                 # statistics -> scale/shift, moving-statistics update and BN+activation(+add) in one launch
                 self.fwd.append(lambda: ops.bn_train_apply(y, Mo, Cout, stat(), gamma, beta, mm, mv, Mo, bn.epsilon,
                                                            bn.momentum, upd, act, out.buf, scale, shift, mean, invstd,
@@ -564,8 +618,12 @@ class Plan:
             if bn_node is not None:
                 dy_get = self._reserve(f"dy{slot}", (Mo, Cout), self.dt)
                 red = red_slot
-                self.bwd_seq(lambda: ops.bn_bwd_reduce(g, y, scale, shift, mean, invstd, act, Mo, Cout, red()))
-                self.bwd_seq(lambda: ops.bn_bwd_apply(g, y, scale, shift, mean, invstd, act, red(), Mo, Cout,
+                # virtual BN+ReLU output: g arrives as the gradient w.r.t. the BN output, ReLU mask already applied
+                # by the reader's input-gradient kernel (which may also have produced the two reductions)
+                act_b = ACT_NONE if virt else act
+                if not (virt and out.red_done):
+                    self.bwd_seq(lambda: ops.bn_bwd_reduce(g, y, scale, shift, mean, invstd, act_b, Mo, Cout, red()))
+                self.bwd_seq(lambda: ops.bn_bwd_apply(g, y, scale, shift, mean, invstd, act_b, red(), Mo, Cout,
                                                       dy_get()))
                 # parameter gradients live in the stats arena; copy into the grad arena
                 if beta is not None and not red_direct:
@@ -644,13 +702,23 @@ class Plan:
         Ho, Wo = pad4[0], pad4[1]
         Cin = x.C
         xb = x.buf
-        self.bwd_seq(lambda: ops.dwconv3x3_wgrad(xb, dd_get().view(N, Ho, Wo, Cin), dw_g, stride, dil, in_act=in_act,
-                                                 pad=pad4), side=True, slot=slot)
+        in_sc, in_sh = getattr(x, "pre_scale", None), getattr(x, "pre_shift", None)
+        self.bwd_seq(lambda: ops.dwconv3x3_wgrad(xb, dd_get().view(N, Ho, Wo, Cin), dw_g, stride, dil, in_scale=in_sc,
+                                                 in_shift=in_sh, in_act=in_act, pad=pad4), side=True, slot=slot)
         if need_dx:
             tgt, addend = self._grad_target(x)
-            self.bwd_seq(lambda: ops.dwconv3x3_dgrad(dd_get().view(N, Ho, Wo, Cin), dw_w, x.shape, stride, dil,
-                                                     x_pre=xb if in_act != ACT_NONE else None, in_act=in_act,
-                                                     addend=addend, out=tgt, pad=pad4))
+            if (isinstance(x, _BnActValue) and addend is None and stride == 1 and tuple(dil) == (1, 1)
+                    and (self.bf16 or FORCE_BNRED)):
+                # input gradient + the BN-backward reductions of the layer that produced x, in one launch
+                x.red_done = True
+                self.bwd_seq(lambda: ops.dwconv3x3_dgrad_bnred(dd_get().view(N, Ho, Wo, Cin), dw_w, x.shape, xb, in_sc,
+                                                               in_sh, in_act, x.bn_mean, x.bn_invstd, x.bn_red(),
+                                                               out=tgt, pad=pad4))
+            else:
+                self.bwd_seq(lambda: ops.dwconv3x3_dgrad(dd_get().view(N, Ho, Wo, Cin), dw_w, x.shape, stride, dil,
+                                                         x_pre=xb if in_act != ACT_NONE else None, in_scale=in_sc,
+                                                         in_shift=in_sh, in_act=in_act, addend=addend, out=tgt,
+                                                         pad=pad4))
 
     # The backward schedule is generated in REVERSE topological order (so that _final_grad sees every consumer's
     # contribution): forward emission records one scheduling thunk per macro-op, finalize() runs them backwards
@@ -724,6 +792,7 @@ class Plan:
         N, H, W, C = x.shape
         Ho, Wo = -(-H // 2), -(-W // 2)
         out = Value((N, Ho, Wo, C), self.dt, self._alloc((N, Ho, Wo, C), self.dt), n.layer.name)
+        out.clog = x.clog
         other = self.values[m["other"]] if m["other"] is not None else None
         am = self._alloc((N, Ho, Wo, C), torch.uint8) if self.training else None
         self.values[m["out"]] = out
@@ -752,6 +821,7 @@ class Plan:
             self.values[n.output] = _AliasValue(x, code)
             return
         out = Value(x.shape, self.dt, self._alloc(x.shape, self.dt), n.layer.name)
+        out.clog = x.clog
         out.needs_grad = self.training and x.needs_grad
         self.values[n.output] = out
         self.fwd.append(lambda: ops.affine_act(x.buf, x.M, x.C, out.buf, None, None, code))
@@ -766,6 +836,7 @@ class Plan:
     def _emit_add(self, n: FlatNode):
         a, b = self._input_of(n.inputs[0], False), self._input_of(n.inputs[1], False)
         out = Value(a.shape, self.dt, self._alloc(a.shape, self.dt), n.layer.name)
+        out.clog = a.clog
         out.needs_grad = self.training
         self.values[n.output] = out
         self.fwd.append(lambda: ops.add(a.buf, b.buf, out.buf))
@@ -785,6 +856,7 @@ class Plan:
             return
         N, H, W, C = x.shape
         out = Value((N, H // k, W // k, C), self.dt, self._alloc((N, H // k, W // k, C), self.dt), n.layer.name)
+        out.clog = x.clog
         out.needs_grad = self.training
         self.values[n.output] = out
         self.fwd.append(lambda: ops.avgpool_fwd(x.buf, k, out=out.buf))
@@ -811,6 +883,7 @@ class Plan:
             self.values[n.output] = _TailResize(x, fh, fw)
             return
         out = Value((N, H * fh, W * fw, C), x.dtype, self._alloc((N, H * fh, W * fw, C), x.dtype), n.layer.name)
+        out.clog = x.clog
         out.needs_grad = self.training
         self.values[n.output] = out
         self.fwd.append(lambda: ops.bilinear_fwd(x.buf, fh, fw, out=out.buf))
@@ -824,6 +897,8 @@ class Plan:
 
     def _emit_concat(self, n: FlatNode):
         ins = [self._input_of(i, False) for i in n.inputs]
+        if any(v.clog != v.C for v in ins):
+            raise NotImplementedError("Concatenate of a channel-padded tensor (phys_channels) is not on the hot path")
         N, H, W, _ = ins[0].shape
         Ct = sum(v.C for v in ins)
         out = Value((N, H, W, Ct), self.dt, self._alloc((N, H, W, Ct), self.dt), n.layer.name)
@@ -854,6 +929,7 @@ class Plan:
             self.values[n.output] = x
             return
         out = Value(x.shape, self.dt, self._alloc(x.shape, self.dt), n.layer.name)
+        out.clog = x.clog
         out.needs_grad = True
         self.values[n.output] = out
         seed = self.dropout_seed + 7919 * len(self.fwd)
@@ -1051,7 +1127,7 @@ class Plan:
         for l in self.model.flat_layers():
             for n in l.weight_names():
                 if l._trainable[n]:
-                    out[f"{l.name}/{n}"] = self.params.view(l, n, grad=True).detach().cpu().numpy().copy()
+                    out[f"{l.name}/{n}"] = self.params.logical(l, n, grad=True).detach().cpu().numpy().copy()
         return out
 
 
@@ -1062,6 +1138,7 @@ class _AliasValue(Value):
         self._x = x
         self.pre_act = act
         self.shape, self.dtype, self.name = x.shape, x.dtype, x.name + "/act"
+        self.clog = x.clog
 
     @property
     def buf(self):
@@ -1091,6 +1168,26 @@ class _AliasValue(Value):
     @property
     def pending(self):
         return self._x.pending
+
+
+class _BnActValue(Value):
+    """`act(scale * y + shift)` for the raw conv output y of a training-mode Conv -> BatchNormalization -> ReLU/ReLU6
+    macro-op whose only reader is a dense-tap depthwise stage.  Never written to memory: the reader's forward and
+    filter-gradient kernels apply the map on load (dlv3p_dwconv3x3_fwd / _wgrad in_scale/in_shift/in_act), its
+    input-gradient kernel masks with act' and writes the gradient w.r.t. the BN OUTPUT into `grad` (and, on the TMA
+    path, the two BN-backward reductions into `bn_red`)."""
+
+    def __init__(self, shape, dtype, name, act):
+        super().__init__(shape, dtype, None, name + "/bn_act")
+        self.pre_act = act
+        self.red_done = False
+
+    def attach(self, y, scale, shift, mean, invstd, red_slot):
+        self.buf, self.pre_scale, self.pre_shift = y, scale, shift
+        self.bn_mean, self.bn_invstd, self.bn_red = mean, invstd, red_slot
+
+
+FORCE_BNRED = False     # tests: take the fused dgrad+reduction schedule in fp32 too (through tests/fake_ops.py)
 
 
 class _TailResize:

@@ -93,6 +93,20 @@ def dwconv3x3_dgrad(dy: Tensor, w: Tensor, x_shape, stride=1, dil=(1, 1), paddin
     return out
 
 
+def dwconv3x3_dgrad_bnred(dy: Tensor, w: Tensor, x_shape, x_pre: Tensor, in_scale: Tensor, in_shift: Tensor, in_act: int,
+                          bn_mean: Tensor, bn_invstd: Tensor, bn_red: Tensor, out: Optional[Tensor] = None, pad=None):
+    """dwconv3x3_dgrad (stride 1, dilation 1, bf16) + the BN-backward reductions of x_pre's layer into bn_red[2C]."""
+    _chk(dy, "dy")
+    N, H, W, Cc = x_shape
+    ho, wo, pt, pl = pad if pad is not None else conv_geometry(H, W, 3, 1, (1, 1), "same")
+    assert tuple(dy.shape) == (N, ho, wo, Cc), (dy.shape, (N, ho, wo, Cc))
+    if out is None:
+        out = torch.empty((N, H, W, Cc), dtype=dy.dtype, device=dy.device)
+    call("dlv3p_dwconv3x3_dgrad_bnred", _p(dy), _p(w), _p(out), N, H, W, Cc, pt, pl, ho, wo, _p(x_pre), _p(in_scale),
+         _p(in_shift), in_act, _p(bn_mean), _p(bn_invstd), _p(bn_red), _dt(dy), _stream())
+    return out
+
+
 def dwconv3x3_wgrad(x: Tensor, dy: Tensor, dw: Tensor, stride=1, dil=(1, 1), padding="same", in_scale=None,
                     in_shift=None, in_act=ACT_NONE, pad=None):
     """dw [3,3,C] fp32 is ACCUMULATED into."""

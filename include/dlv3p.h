@@ -64,6 +64,18 @@ int dlv3p_dwconv3x3_dgrad(const void* dy, const float* w, void* dx, int N, int H
                           int dil_h, int dil_w, int pad_t, int pad_l, int Ho, int Wo, const void* x_pre,
                           const float* in_scale, const float* in_shift, int in_act, const void* addend, int dtype,
                           void* stream);
+/* dlv3p_dwconv3x3_dgrad (stride 1, dilation 1, bf16, no addend) that ALSO produces the BatchNormalization-backward
+ * reductions of the layer whose raw conv output is x_pre (tf.raw_ops.FusedBatchNormGradV3's two sums, i.e. what
+ * dlv3p_bn_bwd_reduce computes with act = NONE from the dx written here):
+ *   bn_red[0..C) += sum dx,  bn_red[C..2C) += sum dx * (x_pre - bn_mean) * bn_invstd.
+ * The engine uses it when Conv -> BatchNormalization -> ReLU feeds a SeparableConv2D (Xception blocks,
+ * keras.applications.xception; ss.py:823-830): the BN+ReLU output is never written, the consumer applies it on load
+ * (in_scale/in_shift/in_act of dlv3p_dwconv3x3_fwd / _wgrad) and this call hands the masked gradient and its
+ * reductions straight to dlv3p_bn_bwd_apply. */
+int dlv3p_dwconv3x3_dgrad_bnred(const void* dy, const float* w, void* dx, int N, int H, int W, int C, int pad_t,
+                                int pad_l, int Ho, int Wo, const void* x_pre, const float* in_scale,
+                                const float* in_shift, int in_act, const float* bn_mean, const float* bn_invstd,
+                                float* bn_red, int dtype, void* stream);
 /* dw[3,3,C] (fp32) += sum over N,Ho,Wo of act(in_scale*x+in_shift)[tap] * dy */
 int dlv3p_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int C, int stride,
                           int dil_h, int dil_w, int pad_t, int pad_l, int Ho, int Wo, const float* in_scale,

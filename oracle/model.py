@@ -94,9 +94,11 @@ def _sep(ctx: Ctx, x, name, dilation=(1, 1)):
     return T.conv2d(d, ctx.q(ctx.w[f"{name}/pointwise_kernel"]), 1, "same")
 
 
-def _cbn(ctx: Ctx, acc, bn_name, momentum, act=None, add=None, scale=True, stats_rounded=None):
+def _cbn(ctx: Ctx, acc, bn_name, momentum, act=None, add=None, scale=True, stats_rounded=None, virtual=False):
     """conv accumulator -> stored (rounded) -> BN(+activation)(+residual add) -> stored (rounded): one fused
-    macro-op of the product (engine._emit_conv)."""
+    macro-op of the product (engine._emit_conv).  `virtual`: in training the product never stores this BN+ReLU output —
+    its only reader, a dense-tap stride-1 depthwise stage, applies the map on load in fp32 (engine._BnActValue) — so
+    there is no rounding point; in inference the BN is folded into the GEMM epilogue and the output is stored."""
     y = ctx.q(acc)
     if stats_rounded is None:
         # the product's rule (gemm_tcgen05.cu): GEMMs with more than 32 output channels take the staged TMA-store
@@ -107,7 +109,7 @@ def _cbn(ctx: Ctx, acc, bn_name, momentum, act=None, add=None, scale=True, stats
         z = act(z)
     if add is not None:
         z = z + add
-    return ctx.q(z)
+    return z if (virtual and ctx.training) else ctx.q(z)
 
 
 # ---- keras.applications.Xception, truncated where the reference taps it (ss.py:517-520) --------------------
@@ -122,7 +124,7 @@ def xception_base(ctx: Ctx, img, output_stride: int):
         res = None if tap_here else _cbn(ctx, _conv(ctx, x, cname, 2, "same"), bname, M)
         if first_relu:
             x = T.relu(x)
-        x = _cbn(ctx, _sep(ctx, x, f"block{blk}_sepconv1"), f"block{blk}_sepconv1_bn", M, T.relu)
+        x = _cbn(ctx, _sep(ctx, x, f"block{blk}_sepconv1"), f"block{blk}_sepconv1_bn", M, T.relu, virtual=True)
         x = _cbn(ctx, _sep(ctx, x, f"block{blk}_sepconv2"), f"block{blk}_sepconv2_bn", M)
         if tap_here:
             nm("conv2d"); nm("batch_normalization")       # block13's shortcut layers exist in Keras, pruned here
@@ -131,10 +133,11 @@ def xception_base(ctx: Ctx, img, output_stride: int):
     for blk in range(5, 13):
         res = x
         for j in (1, 2, 3):
+            # sepconv1/2: BN -> the next iteration's ReLU -> dense-tap depthwise stage: virtual in training
             x = _cbn(ctx, _sep(ctx, T.relu(x), f"block{blk}_sepconv{j}"), f"block{blk}_sepconv{j}_bn", M,
-                     add=res if j == 3 else None)
+                     add=res if j == 3 else None, virtual=(j < 3))
     nm("conv2d"); nm("batch_normalization")               # block13 shortcut: created by Keras, not on the tapped path
-    x = _cbn(ctx, _sep(ctx, T.relu(x), "block13_sepconv1"), "block13_sepconv1_bn", M)
+    x = _cbn(ctx, _sep(ctx, T.relu(x), "block13_sepconv1"), "block13_sepconv1_bn", M, virtual=True)
     x = _cbn(ctx, _sep(ctx, T.relu(x), "block13_sepconv2"), "block13_sepconv2_bn", M)
     return x
 
@@ -145,13 +148,13 @@ _MNV2 = ((16, 1, 1, 0), (24, 2, 6, 1), (24, 1, 6, 2), (32, 2, 6, 3), (32, 1, 6, 
 
 def mobilenetv2_base(ctx: Ctx, img, output_stride: int):
     M = 0.999
-    x = _cbn(ctx, _conv(ctx, img, "Conv1", 2, "same"), "bn_Conv1", M, T.relu6)
+    x = _cbn(ctx, _conv(ctx, img, "Conv1", 2, "same"), "bn_Conv1", M, T.relu6, virtual=True)   # -> stride-1 depthwise
     last = 5 if output_stride == 8 else 12
     for cout, stride, exp, bid in _MNV2:
         p = f"block_{bid}_" if bid else "expanded_conv_"
         inp, cin = x, x.shape[-1]
         if bid:
-            x = _cbn(ctx, _conv(ctx, x, p + "expand"), p + "expand_BN", M, T.relu6)
+            x = _cbn(ctx, _conv(ctx, x, p + "expand"), p + "expand_BN", M, T.relu6, virtual=(stride == 1))
         k = ctx.w[p + "depthwise/depthwise_kernel"]
         if stride == 2:
             h, w = x.shape[1], x.shape[2]

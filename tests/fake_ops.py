@@ -85,6 +85,20 @@ def dwconv3x3_dgrad(dy, w, x_shape, stride=1, dil=(1, 1), padding="same", x_pre=
     return out
 
 
+def dwconv3x3_dgrad_bnred(dy, w, x_shape, x_pre, in_scale, in_shift, in_act, bn_mean, bn_invstd, bn_red, out=None,
+                          pad=None):
+    if out is None:
+        out = torch.empty(tuple(x_shape), dtype=dy.dtype)
+    dwconv3x3_dgrad(dy, w, x_shape, 1, (1, 1), x_pre=x_pre, in_scale=in_scale, in_shift=in_shift, in_act=in_act,
+                    out=out, pad=pad)
+    Cc = x_shape[3]
+    g = out.float().reshape(-1, Cc)
+    Y = x_pre.float().reshape(-1, Cc)
+    bn_red[:Cc] += g.sum(0)
+    bn_red[Cc:2 * Cc] += (g * (Y - bn_mean) * bn_invstd).sum(0)
+    return out
+
+
 def dwconv3x3_wgrad(x, dy, dw, stride=1, dil=(1, 1), padding="same", in_scale=None, in_shift=None, in_act=ACT_NONE,
                     pad=None):
     N, H, W, C = x.shape

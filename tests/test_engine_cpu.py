@@ -60,6 +60,43 @@ def test_train_step_matches_oracle(cpu_engine, case):
         np.testing.assert_allclose(ss.model.named_weights()[k], v.numpy(), rtol=1e-3, atol=1e-4, err_msg=k)
 
 
+@pytest.mark.parametrize("fuse", [False, True], ids=["materialised-bn", "bn-fused-into-depthwise"])
+def test_bn_relu_fused_into_depthwise_schedule(cpu_engine, monkeypatch, fuse):
+    """Conv -> BN -> ReLU -> SeparableConv2D: with the fusion on, the BN+ReLU output is virtual (applied on load by the
+    reader), the reader's input-gradient launch also produces the BN-backward reductions (dwconv3x3_dgrad_bnred) and
+    the separate bn_bwd_reduce disappears; logits, loss and every gradient must equal the materialised schedule."""
+    monkeypatch.setattr(cpu_engine, "FORCE_BNRED", True)
+    conf = util.make_conf(width=64, base="xception", output_stride=16, image_size=65)
+    ss = util.build(conf)
+    util.randomize_weights(ss.model)
+    calls = []
+    for name in ("bn_bwd_reduce", "dwconv3x3_dgrad_bnred", "bn_train_apply", "bn_finalize"):
+        orig = getattr(fake_ops, name)
+        monkeypatch.setattr(fake_ops, name, (lambda orig, name: lambda *a, **k: (calls.append(name), orig(*a, **k))[1])(orig, name))
+    plan = cpu_engine.Plan(ss.model, 2, training=True, fuse_bn_dw=fuse)
+    x, y = util.synthetic_batch(conf, 2, plan.out_shape[1:3])
+    plan.set_loss(PW, NW)
+    plan.load_batch(x, y)
+    plan.step_fwd_bwd()
+    n_virtual = sum(isinstance(v, cpu_engine._BnActValue) for v in plan.values.values())
+    if fuse:
+        # Xception(ref-truncated): block2/3/4/13 sepconv1 + 2 per middle block (8 blocks) = 20 virtual tensors
+        assert n_virtual == 20 and calls.count("dwconv3x3_dgrad_bnred") == 20
+        assert calls.count("bn_finalize") >= 20
+    else:
+        assert n_virtual == 0 and "dwconv3x3_dgrad_bnred" not in calls
+    ref = cpu_engine.Plan(ss.model, 2, training=True, fuse_bn_dw=False)
+    ref.set_loss(PW, NW)
+    ref.load_batch(x, y)
+    ref.step_fwd_bwd()
+    np.testing.assert_allclose(plan.logits.buf.numpy(), ref.logits.buf.numpy(), rtol=1e-4, atol=1e-5)
+    assert abs(plan.loss_value() - ref.loss_value()) < 1e-5
+    ga, gb = plan.gradients(), ref.gradients()
+    for k in gb:
+        scale = max(np.abs(gb[k]).max(), 1e-3)
+        assert np.abs(ga[k] - gb[k]).max() <= 2e-3 * scale, k
+
+
 def test_inference_matches_oracle(cpu_engine):
     conf = util.make_conf(base="mobilenetv2", image_size=65, aspp=util.DEFAULT_ASPP, width=32)
     ss = util.build(conf)

@@ -114,6 +114,46 @@ def test_dwconv3x3_fwd_dgrad_wgrad(case, dtype, prologue):
     check("dw wgrad", dw, wr.grad, 2e-3, 2e-3 * math.sqrt(N * ho * wo))
 
 
+@pytest.mark.parametrize("case", [(2, 17, 19, 64), (2, 30, 31, 728), (1, 32, 32, 736), (3, 40, 70, 128)])
+@pytest.mark.parametrize("act", ["relu", "relu6"])
+def test_dwconv3x3_dgrad_bnred(case, act):
+    """Input gradient of a dense-tap depthwise conv + the BatchNormalization-backward reductions of the producing
+    layer in one launch, against the fp64 restatement (masked conv-transpose, sum g, sum g*xhat)."""
+    o = ops()
+    N, H, W, C = case
+    dtype = torch.bfloat16
+    code = o.ACT_RELU if act == "relu" else o.ACT_RELU6
+    y = rnd((N, H, W, C), dtype, 1, 2.0)                    # raw conv output of the producing layer
+    w = rnd((3, 3, C), torch.float32, 2, 0.3)
+    sc = rnd((C,), torch.float32, 3, 0.2) + 1.0
+    sh = rnd((C,), torch.float32, 4, 0.5) + (2.0 if act == "relu6" else 0.0)
+    mean = rnd((C,), torch.float32, 7, 0.3)
+    invstd = rnd((C,), torch.float32, 8, 0.1).abs() + 0.6
+    gy = rnd((N, H, W, C), dtype, 5)
+    pad = dw_pad(H, W, 1, (1, 1), "same")
+
+    zr = torch.zeros((N, H, W, C), dtype=torch.float64, requires_grad=True)
+    O.depthwise_conv2d(zr, w.double().view(3, 3, C, 1), 1, "same", (1, 1)).backward(gy.double())
+    pre = y.double() * sc.double() + sh.double()
+    mask = (pre > 0) if act == "relu" else ((pre > 0) & (pre < 6))
+    g_ref = zr.grad * mask.double()
+    red_ref = torch.cat([g_ref.sum((0, 1, 2)), (g_ref * (y.double() - mean.double()) * invstd.double()).sum((0, 1, 2))])
+
+    red = torch.zeros(2 * C, dtype=torch.float32, device=DEV)
+    dx = o.dwconv3x3_dgrad_bnred(gy.to(DEV), w.to(DEV), (N, H, W, C), y.to(DEV), sc.to(DEV), sh.to(DEV), code,
+                                 mean.to(DEV), invstd.to(DEV), red, pad=pad)
+    rt, at = tol(dtype)
+    check("dgrad_bnred dx", dx, g_ref, rt, at * 4)
+    check("dgrad_bnred red", red, red_ref, 2e-3, 2e-3 * math.sqrt(N * H * W))
+    # accumulates (the caller zeroes once per step): a second call doubles the sums
+    o.dwconv3x3_dgrad_bnred(gy.to(DEV), w.to(DEV), (N, H, W, C), y.to(DEV), sc.to(DEV), sh.to(DEV), code,
+                            mean.to(DEV), invstd.to(DEV), red, pad=pad)
+    check("dgrad_bnred red x2", red, 2 * red_ref, 2e-3, 4e-3 * math.sqrt(N * H * W))
+    with pytest.raises(ValueError):
+        o.dwconv3x3_dgrad_bnred(gy.float().to(DEV), w.to(DEV), (N, H, W, C), y.float().to(DEV), sc.to(DEV), sh.to(DEV),
+                                code, mean.to(DEV), invstd.to(DEV), red, pad=pad)       # fp32: unfused path only
+
+
 GEMM_CASES = [
     # M, N, K
     (128, 32, 64),
