@@ -26,6 +26,7 @@
 // (64-element x 64-row TMA boxes, same 128B swizzle) so no transposed copy of the activations is ever written;
 // its work list is (pixel-range split) x (tile), split-major so that concurrently running CTAs share operands in L2.
 #include <stdlib.h>
+#include <string.h>
 
 #include "tma.cuh"
 
@@ -57,6 +58,15 @@ struct GemmParams {
     int splits;                        // WGRAD: number of pixel-range splits
     int n_tiles, m_tiles;              // output tile grid
     int tma_store;                     // epilogue through the smem staging tile + TMA store / reduce-add
+    // implicit-GEMM 3x3 VALID stride-1 convolution (no im2col buffer): 0 = plain GEMM, 1 = forward, 2 = input gradient,
+    // 3 = filter gradient.  Output/M tiles never cross an image row; A comes straight from the NHWC tensor.
+    int conv_mode;
+    int cv_rows_in;                    // image rows of the A-side tensor per image (fwd/wgrad: H of x; dgrad: Ho of dy)
+    int cv_rows_out;                   // rows per image of the M-side index (fwd/wgrad: Ho; dgrad: H)
+    int cv_width;                      // filter gradient: Wo (pixel index of a dy reduction block)
+    int cv_rlimit;                     // epilogue clip inside a C "row": fwd Wo, dgrad W, wgrad 3*Cin
+    int cv_tpr;                        // fwd/dgrad: 128-pixel M tiles per row; wgrad: 64-pixel reduction blocks per row
+    int cv_kbr;                        // fwd/wgrad: 64-element k-blocks per filter row; dgrad: 64-channel blocks per tap
     int dbg;                           // diagnostics only (DLV3P_GEMM_DBG): 1 = no operand loads, 2 = no epilogue work, 4 = no MMAs, 8 = no C stores, 16 = no TMEM reads
 };
 
@@ -120,7 +130,8 @@ __device__ __forceinline__ void decode_work(const GemmParams& p, int w, int& row
 template <int BLOCK_N, bool WGRAD, bool REMOTE>
 __device__ __forceinline__ void staged_tile_epilogue(const GemmParams& p, const CUtensorMap* tmC, uint32_t acc_tmem,
                                                      int rbase, int col0, int lane, int half, uint32_t stg0, uint32_t& buf,
-                                                     uint32_t empty_bar, float* stat_smem, bool use_smem_stats) {
+                                                     uint32_t empty_bar, float* stat_smem, bool use_smem_stats,
+                                                     int row_limit, int c2) {
     constexpr int CW = WGRAD ? 32 : 64;                 // columns per staging tile (128-byte rows)
     const uint32_t lane_row = (uint32_t)lane * 128u;
     const uint32_t sw = (uint32_t)(lane & 7);
@@ -193,9 +204,10 @@ __device__ __forceinline__ void staged_tile_epilogue(const GemmParams& p, const 
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0 && rbase < (WGRAD ? p.K : p.M) && !(p.dbg & 8)) {
-            if (WGRAD) tma_reduce_add_2d(tmC, stg, n_base, rbase);
-            else tma_store_2d(tmC, stg, n_base, rbase);
+        if (lane == 0 && rbase < row_limit && !(p.dbg & 8)) {
+            // c2 >= 0: implicit-convolution tile, rank-3 C map (channel, column in the row, row) clips the ragged row end
+            if (WGRAD) { if (c2 >= 0) tma_reduce_add_3d(tmC, stg, n_base, rbase, c2); else tma_reduce_add_2d(tmC, stg, n_base, rbase); }
+            else { if (c2 >= 0) tma_store_3d(tmC, stg, n_base, rbase, c2); else tma_store_2d(tmC, stg, n_base, rbase); }
             tma_commit_group();
         }
         if (!WGRAD && p.col_stats != nullptr) {
@@ -290,7 +302,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t fb = full_bar + 8 * s;
                     mbar_expect_tx(fb, STAGE_BYTES);
                     const int kk = kb * kBlockK;
-                    if (WGRAD) {
+                    if (p.conv_mode != 0) {
+                        if (WGRAD) {
+                            // filter gradient: output rows = the 128-element padded K-run of filter row i, reduction
+                            // block kb = 64 consecutive output pixels of one image row
+                            const int i = row0 / kBlockM;
+                            const int r = kb / p.cv_tpr, qd = kb % p.cv_tpr;
+                            const int n = r / p.cv_rows_out, ho = r % p.cv_rows_out;
+#pragma unroll
+                            for (int h = 0; h < kBlockM / 64; ++h)
+                                tma_load_3d(a_dst + h * 8192, &tmA, fb, 64 * h, qd * 64, n * p.cv_rows_in + ho + i);
+#pragma unroll
+                            for (int h = 0; h < BLOCK_N / 64; ++h)
+                                tma_load_2d(b_dst + h * 8192, &tmB, fb, col0 + 64 * h, r * p.cv_width + qd * 64);
+                        } else {
+                            const int mt = row0 / kBlockM;
+                            const int r = mt / p.cv_tpr, w0 = (mt % p.cv_tpr) * kBlockM;
+                            const int n = r / p.cv_rows_out, hh = r % p.cv_rows_out;
+                            if (p.conv_mode == 1) {
+                                // forward: k-block = 64 elements of the 3*Cin-element run under filter row i (elements
+                                // beyond the run and columns beyond the row are zero-filled by TMA)
+                                const int i = kb / p.cv_kbr, part = kb % p.cv_kbr;
+                                tma_load_3d(a_dst, &tmA, fb, part * 64, w0, n * p.cv_rows_in + hh + i);
+                            } else {
+                                // input gradient: k-block = 64 output channels of dy under tap (i, j), window shifted by
+                                // (-i, -j); positions outside dy are zero-filled (full correlation)
+                                const int tap = kb / p.cv_kbr, part = kb % p.cv_kbr;
+                                tma_load_4d(a_dst, &tmA, fb, part * 64, w0 - tap % 3, hh - tap / 3, n);
+                            }
+                            tma_load_2d(b_dst, &tmB, fb, kk, col0);
+                        }
+                    } else if (WGRAD) {
                         // MN-major operands: boxes of 64 channels (inner, 128 B) x 64 pixels
 #pragma unroll
                         for (int h = 0; h < kBlockM / 64; ++h) tma_load_2d(a_dst + h * 8192, &tmA, fb, row0 + 64 * h, kk);
@@ -360,9 +402,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t as = t & 1u;
                 mbar_wait(tmem_full_bar + 8 * as, (t >> 1) & 1u);
                 tc_fence_after();
+                int rb = row0 + q * 32, rl = row_limit, c2 = -1;
+                if (p.conv_mode != 0) {
+                    const int mt = row0 / kBlockM;
+                    if (WGRAD) { rb = q * 32; rl = p.cv_rlimit; c2 = mt; }               // (cout, element of the run, filter row)
+                    else { rb = (mt % p.cv_tpr) * kBlockM + q * 32; rl = p.cv_rlimit; c2 = mt / p.cv_tpr; }   // (ch, column, row)
+                }
                 staged_tile_epilogue<BLOCK_N, WGRAD, false>(p, &tmC, tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N,
-                                                            row0 + q * 32, col0, lane, half, stg0, buf,
-                                                            tmem_empty_bar + 8 * as, stat_smem, use_smem_stats);
+                                                            rb, col0, lane, half, stg0, buf,
+                                                            tmem_empty_bar + 8 * as, stat_smem, use_smem_stats, rl, c2);
             }
             if (lane == 0) tma_wait_group_all();
         } else {
@@ -713,7 +761,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             staged_tile_epilogue<BLOCK_N, WGRAD, true>(p, &tmC, tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N,
                                                        row0 + q * 32, col0, lane, half, stg0, buf,
-                                                       leader_tmem_empty + 8 * as, stat_smem, use_smem_stats);
+                                                       leader_tmem_empty + 8 * as, stat_smem, use_smem_stats,
+                                                       WGRAD ? p.K : p.M, -1);
         }
         if (lane == 0) tma_wait_group_all();
         if (use_smem_stats) {
@@ -807,7 +856,7 @@ extern "C" int dlv3p_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
     p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.c_dtype = c_dtype;
     p.col_scale = col_scale; p.col_shift = col_shift; p.act = act;
     p.addend = addend; p.ld_add = ld_addend; p.col_stats = col_stats; p.kb_per_split = 0; p.splits = 1;
-    p.dbg = gemm_dbg_mode();
+    p.dbg = gemm_dbg_mode(); p.conv_mode = 0;
     p.n_tiles = cdiv(N, bn); p.m_tiles = cdiv(M, kBlockM);
     p.tma_store = (c_dtype == DLV3P_BF16 && addend == nullptr && (ldc % 8) == 0 && aligned16(C) && bn >= 64) ? 1 : 0;
     CUtensorMap tmC = tmA;
@@ -850,7 +899,7 @@ extern "C" int dlv3p_gemm_wgrad_bf16(const void* X, int64_t ldx, const void* dY,
     GemmParams p;
     p.M = M; p.N = N; p.K = K; p.C = dW; p.ldc = ldw; p.c_dtype = DLV3P_F32;
     p.col_scale = nullptr; p.col_shift = nullptr; p.act = 0; p.addend = nullptr; p.ld_add = 0; p.col_stats = nullptr;
-    p.dbg = gemm_dbg_mode();
+    p.dbg = gemm_dbg_mode(); p.conv_mode = 0;
     p.n_tiles = cdiv(N, bn); p.m_tiles = cdiv(K, kBlockM);
     const int tiles = p.n_tiles * p.m_tiles;
     const int total_kb = cdiv(M, kBlockK);
@@ -876,6 +925,149 @@ extern "C" int dlv3p_gemm_wgrad_bf16(const void* X, int64_t ldx, const void* dY,
         p.splits = cdiv(total_kb, p.kb_per_split);
         return launch_gemm2<256, true>(tmA, tmB, tmC, p, st);
     }
+    switch (bn) {
+        case 64: return launch_gemm<64, true>(tmA, tmB, tmC, p, st);
+        case 128: return launch_gemm<128, true>(tmA, tmB, tmC, p, st);
+        default: return launch_gemm<256, true>(tmA, tmB, tmC, p, st);
+    }
+}
+
+
+// =====================================================================================================================
+// Implicit-GEMM 3x3 VALID stride-1 convolution (Xception block1_conv2, keras.applications.xception; the reference
+// reaches it through ss.py:512-515).  The im2col matrix [N*Ho*Wo, 9*Cin] is never written: under one filter row the
+// three taps of an output pixel are 3*Cin CONTIGUOUS NHWC elements, so a rank-3 tensor map whose rows overlap (row
+// length 3*Cin elements, row pitch Cin elements) hands the GEMM its A tiles directly; the run is cut into 64-element
+// k-blocks and TMA zero-fills what lies beyond the run / the image row, so K = 3 * 64*ceil(3*Cin/64) with matching zero
+// columns in the prepared filter matrix.  M tiles are 128 output pixels of ONE image row (rank-3 C map clips the
+// ragged row end), so BatchNormalization statistics see exact zeros for the clipped pixels.
+//   wk (forward B operand)  bf16 [Cout, 3*KR], wk[o, i*KR + j*Cin + c] = W[i,j,c,o], KR = 64*ceil(3*Cin/64), zero elsewhere
+//   wd (dgrad B operand)    bf16 [Cin, 9*Cout], wd[c, (i*3+j)*Cout + o] = W[i,j,c,o]
+// =====================================================================================================================
+static int conv_check(const void* a, const void* b, const void* c, int N, int H, int W, int Cin, int Cout) {
+    DLV3P_REQUIRE(a && b && c && N > 0 && H >= 3 && W >= 3 && Cin > 0 && Cout > 0, DLV3P_ERR_SHAPE,
+                  "conv3x3_valid: bad arguments N=%d H=%d W=%d Cin=%d Cout=%d", N, H, W, Cin, Cout);
+    DLV3P_REQUIRE((Cin % 8) == 0 && (Cout % 8) == 0 && aligned16(a) && aligned16(b) && aligned16(c), DLV3P_ERR_ALIGN,
+                  "conv3x3_valid: Cin/Cout must be multiples of 8 and the pointers 16-byte aligned");
+    return 0;
+}
+
+extern "C" int dlv3p_conv3x3_valid_fwd_bf16(const void* x, const void* wk, void* y, int N, int H, int W, int Cin,
+                                            int Cout, const float* col_scale, const float* col_shift, int act,
+                                            float* col_stats, void* stream) {
+    int rc = conv_check(x, wk, y, N, H, W, Cin, Cout);
+    if (rc) return rc;
+    DLV3P_REQUIRE(Cout <= 256 && Cout >= 64, DLV3P_ERR_UNSUPPORTED, "conv3x3_valid_fwd: 64 <= Cout <= 256 (got %d)", Cout);
+    const int Ho = H - 2, Wo = W - 2;
+    const int kbr = cdiv(3 * Cin, kBlockK), KR = kbr * kBlockK;
+    const int bn = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
+    CUtensorMap tmA, tmB, tmC;
+    {
+        const long long dims[3] = {3LL * Cin, Wo, (long long)N * H};
+        const long long str[2] = {2LL * Cin, 2LL * W * Cin};
+        const int box[3] = {kBlockK, kBlockM, 1};
+        rc = make_tmap_nd(&tmA, x, 3, dims, str, box);
+        if (rc) return rc;
+    }
+    rc = make_tmap(&tmB, wk, 3LL * KR, Cout, 3LL * KR, kBlockK, bn);
+    if (rc) return rc;
+    {
+        const long long dims[3] = {Cout, Wo, (long long)N * Ho};
+        const long long str[2] = {2LL * Cout, 2LL * Wo * Cout};
+        const int box[3] = {64, 32, 1};
+        rc = make_tmap_nd(&tmC, y, 3, dims, str, box);
+        if (rc) return rc;
+    }
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.cv_tpr = cdiv(Wo, kBlockM);
+    p.m_tiles = N * Ho * p.cv_tpr; p.n_tiles = cdiv(Cout, bn);
+    p.M = p.m_tiles * kBlockM; p.N = Cout; p.K = 3 * KR;
+    DLV3P_REQUIRE((col_scale == nullptr) == (col_shift == nullptr), DLV3P_ERR_SHAPE, "conv3x3_valid_fwd: scale/shift mismatch");
+    p.C = y; p.ldc = Cout; p.c_dtype = DLV3P_BF16; p.col_scale = col_scale; p.col_shift = col_shift; p.act = act;
+    p.col_stats = col_stats; p.splits = 1; p.tma_store = 1; p.dbg = 0;
+    p.conv_mode = 1; p.cv_rows_in = H; p.cv_rows_out = Ho; p.cv_width = Wo; p.cv_rlimit = Wo; p.cv_kbr = kbr;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (bn) {
+        case 64: return launch_gemm<64, false>(tmA, tmB, tmC, p, st);
+        case 128: return launch_gemm<128, false>(tmA, tmB, tmC, p, st);
+        default: return launch_gemm<256, false>(tmA, tmB, tmC, p, st);
+    }
+}
+
+extern "C" int dlv3p_conv3x3_valid_dgrad_bf16(const void* dy, const void* wd, void* dx, int N, int H, int W, int Cin,
+                                              int Cout, void* stream) {
+    int rc = conv_check(dy, wd, dx, N, H, W, Cin, Cout);
+    if (rc) return rc;
+    DLV3P_REQUIRE((Cout % 64) == 0 && Cin <= 64, DLV3P_ERR_UNSUPPORTED,
+                  "conv3x3_valid_dgrad: Cout %% 64 == 0 and Cin <= 64 (got Cin=%d Cout=%d)", Cin, Cout);
+    const int Ho = H - 2, Wo = W - 2;
+    CUtensorMap tmA, tmB, tmC;
+    {
+        const long long dims[4] = {Cout, Wo, Ho, N};
+        const long long str[3] = {2LL * Cout, 2LL * Wo * Cout, 2LL * Ho * Wo * Cout};
+        const int box[4] = {kBlockK, kBlockM, 1, 1};
+        rc = make_tmap_nd(&tmA, dy, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    rc = make_tmap(&tmB, wd, 9LL * Cout, Cin, 9LL * Cout, kBlockK, 64);
+    if (rc) return rc;
+    {
+        const long long dims[3] = {Cin, W, (long long)N * H};
+        const long long str[2] = {2LL * Cin, 2LL * W * Cin};
+        const int box[3] = {64, 32, 1};
+        rc = make_tmap_nd(&tmC, dx, 3, dims, str, box);
+        if (rc) return rc;
+    }
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.cv_tpr = cdiv(W, kBlockM);
+    p.m_tiles = N * H * p.cv_tpr; p.n_tiles = 1;
+    p.M = p.m_tiles * kBlockM; p.N = Cin; p.K = 9 * Cout;
+    p.C = dx; p.ldc = Cin; p.c_dtype = DLV3P_BF16; p.act = DLV3P_ACT_NONE; p.splits = 1; p.tma_store = 1;
+    p.conv_mode = 2; p.cv_rows_in = Ho; p.cv_rows_out = H; p.cv_width = W; p.cv_rlimit = W; p.cv_kbr = Cout / 64;
+    return launch_gemm<64, false>(tmA, tmB, tmC, p, (cudaStream_t)stream);
+}
+
+extern "C" int dlv3p_conv3x3_valid_wgrad_bf16(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin,
+                                              int Cout, void* stream) {
+    int rc = conv_check(x, dy, dw, N, H, W, Cin, Cout);
+    if (rc) return rc;
+    DLV3P_REQUIRE(3 * Cin > 64 && 3 * Cin <= 128 && Cout <= 256, DLV3P_ERR_UNSUPPORTED,
+                  "conv3x3_valid_wgrad: 64 < 3*Cin <= 128 and Cout <= 256 (got Cin=%d Cout=%d)", Cin, Cout);
+    const int Ho = H - 2, Wo = W - 2;
+    const int bn = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
+    CUtensorMap tmA, tmB, tmC;
+    {
+        const long long dims[3] = {3LL * Cin, Wo, (long long)N * H};
+        const long long str[2] = {2LL * Cin, 2LL * W * Cin};
+        const int box[3] = {64, kBlockK, 1};
+        rc = make_tmap_nd(&tmA, x, 3, dims, str, box);
+        if (rc) return rc;
+    }
+    rc = make_tmap(&tmB, dy, Cout, (long long)N * Ho * Wo, Cout, 64, kBlockK);
+    if (rc) return rc;
+    {
+        // dw = HWIO [3][3*Cin][Cout] fp32: rank-3 map clips the zero-padded tail of every 128-element run
+        const long long dims[3] = {Cout, 3LL * Cin, 3};
+        const long long str[2] = {4LL * Cout, 4LL * 3 * Cin * Cout};
+        const int box[3] = {32, 32, 1};
+        rc = make_tmap_nd(&tmC, dw, 3, dims, str, box, /*f32=*/true);
+        if (rc) return rc;
+    }
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.cv_tpr = cdiv(Wo, kBlockK);                         // 64-pixel reduction blocks per output row
+    const int total_kb = N * Ho * p.cv_tpr;
+    p.m_tiles = 3; p.n_tiles = cdiv(Cout, bn);
+    p.M = total_kb * kBlockK; p.N = Cout; p.K = 3 * kBlockM;
+    p.C = dw; p.ldc = Cout; p.c_dtype = DLV3P_F32; p.tma_store = 1;
+    const int tiles = p.m_tiles * p.n_tiles;
+    int splits = kNumSMs / tiles; if (splits < 1) splits = 1; if (splits > total_kb) splits = total_kb;
+    p.kb_per_split = cdiv(total_kb, splits);
+    p.splits = cdiv(total_kb, p.kb_per_split);
+    p.conv_mode = 3; p.cv_rows_in = H; p.cv_rows_out = Ho; p.cv_width = Wo; p.cv_rlimit = 3 * Cin; p.cv_kbr = 2;
+    cudaStream_t st = (cudaStream_t)stream;
     switch (bn) {
         case 64: return launch_gemm<64, true>(tmA, tmB, tmC, p, st);
         case 128: return launch_gemm<128, true>(tmA, tmB, tmC, p, st);

@@ -39,6 +39,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3) {
     asm volatile(
@@ -54,6 +59,14 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
 __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
     asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -95,6 +108,27 @@ static inline int make_tmap(CUtensorMap* map, const void* base, long long d0, lo
     return 0;
 }
 
+
+// General rank-3/4 tensor map with 128B swizzle (bf16, or fp32 with f32 = true): dims[0] is the contiguous axis,
+// strides_bytes[i] is the pitch of dims[i+1].  The implicit-GEMM convolutions (gemm_tcgen05.cu) use it with
+// OVERLAPPING rows: dims[0] = 3*Cin elements (the three horizontally adjacent pixels under one filter row) while the
+// pitch of dims[1] (the output column) is only Cin elements.
+static inline int make_tmap_nd(CUtensorMap* map, const void* base, int rank, const long long* dims,
+                               const long long* strides_bytes, const int* box, bool f32 = false) {
+    auto fn = get_encode_fn();
+    DLV3P_REQUIRE(fn != nullptr, DLV3P_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t d[5], st[4];
+    cuuint32_t b[5], estr[5] = {1, 1, 1, 1, 1};
+    for (int i = 0; i < rank; ++i) { d[i] = (cuuint64_t)dims[i]; b[i] = (cuuint32_t)box[i]; }
+    for (int i = 0; i + 1 < rank; ++i) st[i] = (cuuint64_t)strides_bytes[i];
+    CUresult rc = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+                     const_cast<void*>(base), d, st, b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DLV3P_REQUIRE(rc == CUDA_SUCCESS, DLV3P_ERR_CUDA,
+                  "cuTensorMapEncodeTiled(rank %d) failed (%d) dims=(%lld,%lld,%lld) box=(%d,%d,%d)", rank, (int)rc,
+                  dims[0], dims[1], rank > 2 ? dims[2] : 0, box[0], box[1], rank > 2 ? box[2] : 0);
+    return 0;
+}
 
 // 4D bf16 NHWC tensor map (dims C, W, H, N), no swizzle, zero fill outside the tensor: the halo of a tile that
 // crosses the image border comes back as the convolution's zero padding.

@@ -213,7 +213,7 @@ class Plan:
 
     def __init__(self, model: Model, batch_size: int, training: bool = False, dtype: Optional[str] = None,
                  device: Optional[str] = None, dropout_seed: int = 1024, fused_tail: bool = True,
-                 fuse_bn_dw: bool = True):
+                 fuse_bn_dw: bool = True, implicit_conv: bool = True):
         fake = getattr(ops, "FAKE", False)       # tests/fake_ops.py test double (host-logic tests without a GPU)
         if not torch.cuda.is_available() and not fake:
             raise RuntimeError("engine.Plan needs a CUDA device: there is no CPU execution path")
@@ -226,6 +226,7 @@ class Plan:
         self.bf16 = self.dt == torch.bfloat16
         self.fused_tail = fused_tail
         self.fuse_bn_dw = fuse_bn_dw        # Conv->BN->ReLU->depthwise: BN+ReLU applied on load (False: A/B, materialise it)
+        self.implicit_conv = implicit_conv  # dense 3x3 VALID stride-1 convs as implicit GEMMs (False: A/B, im2col + GEMM)
         self.dropout_seed = dropout_seed
         self.fwd: List[Callable[[], None]] = []
         self.bwd: List[Tuple[Callable[[], None], bool, Optional[int]]] = []   # (launch, side-stream ok, scratch slot)
@@ -480,6 +481,7 @@ class Plan:
         dw_w = P.view(lay, "depthwise_kernel").view(3, 3, Cin) if (is_sep or is_dw) else None
         dw_g = P.view(lay, "depthwise_kernel", grad=True).view(3, 3, Cin) if (is_sep or is_dw) else None
         gemm = not is_dw
+        implicit = False
         if gemm:
             wname = "pointwise_kernel" if is_sep else "kernel"
             Kdim = Cin if (is_sep or k == 1) else 9 * Cin
@@ -487,7 +489,23 @@ class Plan:
             Np = _ceil8(Cout)
             w32 = P.view(lay, wname).view(Kdim, Cout)
             g32 = P.view(lay, wname, grad=True).view(Kdim, Cout)
-            if self.bf16:
+            # dense 3x3 VALID stride-1 conv (Xception block1_conv2): implicit GEMM straight from the NHWC tensor
+            implicit = (self.implicit_conv and (self.bf16 or FORCE_IMPLICIT) and k == 3 and not is_sep and stride == 1
+                        and tuple(dil) == (1, 1) and lay.padding == "valid"
+                        and getattr(node, "explicit_pad", None) is None and not is_logits and other_id is None
+                        and ops.conv3x3_valid_supported(Cin, Cout))
+            if implicit:
+                KR = ops.conv3x3_valid_kr(Cin)
+                wdt = torch.bfloat16 if self.bf16 else torch.float32          # (fp32 only under FORCE_IMPLICIT, CPU tests)
+                wk = self._alloc((Cout, 3 * KR), wdt, zero=True)              # forward B operand (zero-padded runs)
+                wd = self._alloc((Cin, 9 * Cout), wdt) if training else None  # input-gradient B operand
+
+                def prep_implicit():
+                    wk.view(Cout, 3, KR)[:, :, :3 * Cin].copy_(w32.view(3, 3 * Cin, Cout).permute(2, 0, 1))
+                    if wd is not None:
+                        wd.view(Cin, 9, Cout).copy_(w32.view(9, Cin, Cout).permute(1, 0, 2))
+                self.prep.append(prep_implicit)
+            elif self.bf16:
                 wt = self._alloc((Cout, Kp), torch.bfloat16, zero=True)       # [N,K] K-major: forward B operand
                 wn = self._alloc((Kdim, Np), torch.bfloat16, zero=True) if training else None   # dgrad B operand
                 self._wprep.append((w32, Kdim, Cout, wt, Kp, wn, Np))
@@ -548,6 +566,8 @@ class Plan:
             self.fwd.append(lambda: ops.subsample_fwd(xb, stride, out=xs))
             launches_f += 1
             A, lda = xs, Cin
+        elif implicit:
+            A, lda = None, Kp
         else:
             col = self._alloc((Mo, Kp), self.dt)
             self.fwd.append(lambda: ops.im2col3x3(xb, stride, dil[0], Ho, Wo, pt, pl, Kp, out=col))
@@ -558,7 +578,13 @@ class Plan:
         addend_f = other.buf if other is not None else None
         if gemm:
             Kg = lda if (k == 3 and not is_sep) else Kdim
-            if self.bf16:
+            if implicit:
+                tgt = out.buf if (fuse_epi or bn_node is None) else y
+                stats_fn = stat if (bn_node is not None and training) else None
+                self.fwd.append(lambda: ops.conv3x3_valid_fwd(
+                    xb, wk, tgt, Cout, col_scale=scale if fuse_epi else None, col_shift=shift if fuse_epi else None,
+                    act=act if fuse_epi else ACT_NONE, col_stats=stats_fn() if stats_fn else None))
+            elif self.bf16:
                 tgt = out.buf if (fuse_epi or bn_node is None) else y
                 stats_fn = stat if (bn_node is not None and training) else None
                 self.fwd.append(lambda: ops.gemm_bf16(
@@ -574,7 +600,7 @@ class Plan:
                     act=act if fuse_epi else ACT_NONE, addend=addend_f if fuse_epi else None, ld_addend=Cout))
             launches_f += 1
         if bn_node is not None and training:
-            if not (gemm and self.bf16):
+            if not (gemm and (self.bf16 or implicit)):
                 self.fwd.append(lambda: ops.bn_stats(y, Mo, Cout, stat()))
                 launches_f += 1
             upd = bn_node.calls
@@ -642,7 +668,19 @@ class Plan:
                     dy_get = lambda: g
             ld_dy = Np if (bn_node is None and y_dtype == torch.float32 and self.bf16) else Cout
 
-            if gemm:
+            if gemm and implicit:
+                self.bwd_seq(lambda: ops.conv3x3_valid_wgrad(xb, dy_get().view(N, Ho, Wo, Cout), g32, Cout), side=True,
+                             slot=slot)
+                if needs_in_grad:
+                    tgt, addend2 = self._grad_target(x)
+                    if addend2 is None:
+                        self.bwd_seq(lambda: ops.conv3x3_valid_dgrad(dy_get().view(N, Ho, Wo, Cout), wd, x.shape, Cout, tgt))
+                    else:
+                        tmp_get = self._reserve(f"dA{slot}", x.shape, self.dt)
+                        self.bwd_seq(lambda: ops.conv3x3_valid_dgrad(dy_get().view(N, Ho, Wo, Cout), wd, x.shape, Cout,
+                                                                     tmp_get()))
+                        self.bwd_seq(lambda: ops.add(tmp_get(), addend2, tgt))
+            elif gemm:
                 # filter gradient
                 if self.bf16:
                     self.bwd_seq(lambda: ops.gemm_wgrad_bf16(A, dy_get(), g32, Mo, Kdim, Cout, ldx=lda, ldy=ld_dy,
@@ -1187,6 +1225,7 @@ class _BnActValue(Value):
         self.bn_mean, self.bn_invstd, self.bn_red = mean, invstd, red_slot
 
 
+FORCE_IMPLICIT = False  # tests: take the implicit-GEMM 3x3 schedule in fp32 too (through tests/fake_ops.py)
 FORCE_BNRED = False     # tests: take the fused dgrad+reduction schedule in fp32 too (through tests/fake_ops.py)
 
 

@@ -137,6 +137,41 @@ def gemm_wgrad_bf16(x: Tensor, dy: Tensor, dw: Tensor, M: int, K: int, N: int, l
     return dw
 
 
+def conv3x3_valid_supported(Cin: int, Cout: int) -> bool:
+    """Shapes all three implicit-GEMM entry points accept (see include/dlv3p.h)."""
+    return Cin % 8 == 0 and Cout % 64 == 0 and 64 <= Cout <= 256 and 64 < 3 * Cin <= 128
+
+
+def conv3x3_valid_kr(Cin: int) -> int:
+    return (3 * Cin + 63) // 64 * 64
+
+
+def conv3x3_valid_fwd(x: Tensor, wk: Tensor, out: Tensor, Cout: int, col_scale=None, col_shift=None, act=ACT_NONE,
+                      col_stats=None):
+    """out[N,H-2,W-2,Cout] = epi(conv3x3_valid(x[N,H,W,Cin])), implicit GEMM; wk bf16 [Cout, 3*KR]."""
+    _chk(x, "x")
+    N, H, W, Cin = x.shape
+    call("dlv3p_conv3x3_valid_fwd_bf16", _p(x), _p(wk), _p(out), N, H, W, Cin, Cout, _p(col_scale), _p(col_shift), act,
+         _p(col_stats), _stream())
+    return out
+
+
+def conv3x3_valid_dgrad(dy: Tensor, wd: Tensor, x_shape, Cout: int, out: Tensor):
+    """out[N,H,W,Cin] = conv_transpose(dy[N,H-2,W-2,Cout]); wd bf16 [Cin, 9*Cout]."""
+    _chk(dy, "dy")
+    N, H, W, Cin = x_shape
+    call("dlv3p_conv3x3_valid_dgrad_bf16", _p(dy), _p(wd), _p(out), N, H, W, Cin, Cout, _stream())
+    return out
+
+
+def conv3x3_valid_wgrad(x: Tensor, dy: Tensor, dw: Tensor, Cout: int):
+    """dw (fp32 HWIO [3,3,Cin,Cout], accumulated) += x-windows^T dy."""
+    _chk(x, "x"); _chk(dy, "dy")
+    N, H, W, Cin = x.shape
+    call("dlv3p_conv3x3_valid_wgrad_bf16", _p(x), _p(dy), _p(dw), N, H, W, Cin, Cout, _stream())
+    return dw
+
+
 def gemm_simt(a: Tensor, sam: int, sak: int, b: Tensor, sbk: int, sbn: int, out: Tensor, ldc: int, M: int, N: int,
               K: int, col_scale=None, col_shift=None, act=ACT_NONE, addend=None, ld_addend=0, accumulate=False):
     call("dlv3p_gemm_simt", _p(a), sam, sak, _p(b), sbk, sbn, _p(out), ldc, M, N, K, _dt(a), _dt(out),

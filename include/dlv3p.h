@@ -97,6 +97,25 @@ int dlv3p_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void
 /* filter gradient: dW[K,N] (fp32, row stride ldw) += X[M,K]^T * dY[M,N]   (split over M, fp32 atomics) */
 int dlv3p_gemm_wgrad_bf16(const void* X, int64_t ldx, const void* dY, int64_t ldy, float* dW, int64_t ldw, int M,
                           int K, int N, void* stream);
+
+/* Implicit-GEMM 3x3 VALID stride-1 convolution, bf16 NHWC, no im2col matrix (Xception block1_conv2 =
+ * keras.applications.xception Conv2D(64, (3,3), use_bias=False), reached through ss.py:512-515; TF runs it as one
+ * cuDNN Conv2D + Conv2DBackpropInput + Conv2DBackpropFilter).  Ho = H-2, Wo = W-2.
+ *   fwd:   y[N,Ho,Wo,Cout] = epilogue(conv(x[N,H,W,Cin], W)); epilogue and col_stats as dlv3p_gemm_bf16.
+ *          wk = bf16 [Cout, 3*KR], KR = 64*ceil(3*Cin/64), wk[o, i*KR + j*Cin + c] = W[i,j,c,o], zeros elsewhere.
+ *          64 <= Cout <= 256.
+ *   dgrad: dx[N,H,W,Cin] = conv_transpose(dy[N,Ho,Wo,Cout], W); wd = bf16 [Cin, 9*Cout], wd[c,(i*3+j)*Cout+o] = W[i,j,c,o].
+ *          Cout % 64 == 0, Cin <= 64.
+ *   wgrad: dw (fp32 HWIO [3,3,Cin,Cout]) += sum_pixels x-window * dy.  64 < 3*Cin <= 128.
+ * Cin, Cout multiples of 8; all pointers 16-byte aligned; anything else returns DLV3P_ERR_UNSUPPORTED and the caller
+ * uses dlv3p_im2col3x3 + dlv3p_gemm_bf16. */
+int dlv3p_conv3x3_valid_fwd_bf16(const void* x, const void* wk, void* y, int N, int H, int W, int Cin, int Cout,
+                                 const float* col_scale, const float* col_shift, int act, float* col_stats,
+                                 void* stream);
+int dlv3p_conv3x3_valid_dgrad_bf16(const void* dy, const void* wd, void* dx, int N, int H, int W, int Cin, int Cout,
+                                   void* stream);
+int dlv3p_conv3x3_valid_wgrad_bf16(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout,
+                                   void* stream);
 /* generic fp32-accumulate SIMT GEMM for the fp32 parity mode and shapes the TMA path cannot take:
  *   C[m,n] = sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] (+ C if accumulate), same epilogue as above.
  *   ab_dtype: storage of A and B; c_dtype: storage of C. */

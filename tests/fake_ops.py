@@ -137,6 +137,46 @@ def gemm_wgrad_bf16(x, dy, dw, M, K, N, ldx=None, ldy=None, ldw=None):
     return dw
 
 
+def conv3x3_valid_supported(Cin, Cout):
+    return Cin % 8 == 0 and Cout % 64 == 0 and 64 <= Cout <= 256 and 64 < 3 * Cin <= 128
+
+
+def conv3x3_valid_kr(Cin):
+    return (3 * Cin + 63) // 64 * 64
+
+
+def _hwio_from_wk(wk, Cin, Cout):
+    KR = conv3x3_valid_kr(Cin)
+    return wk.float().view(Cout, 3, KR)[:, :, :3 * Cin].reshape(Cout, 3, 3, Cin).permute(1, 2, 3, 0)    # [3,3,Cin,Cout]
+
+
+def conv3x3_valid_fwd(x, wk, out, Cout, col_scale=None, col_shift=None, act=ACT_NONE, col_stats=None):
+    N, H, W, Cin = x.shape
+    w = _hwio_from_wk(wk, Cin, Cout)
+    acc = F.conv2d(x.float().permute(0, 3, 1, 2), w.permute(3, 2, 0, 1)).permute(0, 2, 3, 1).reshape(-1, Cout)
+    if col_stats is not None:
+        col_stats[:Cout] += acc.sum(0)
+        col_stats[Cout:2 * Cout] += (acc * acc).sum(0)
+    out.view(-1, Cout).copy_(_epi(acc, col_scale, col_shift, act, None))
+    return out
+
+
+def conv3x3_valid_dgrad(dy, wd, x_shape, Cout, out):
+    N, H, W, Cin = x_shape
+    w = wd.float().view(Cin, 3, 3, Cout).permute(1, 2, 0, 3)                  # [3,3,Cin,Cout]
+    g = F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), w.permute(3, 2, 0, 1)).permute(0, 2, 3, 1)
+    out.copy_(g)
+    return out
+
+
+def conv3x3_valid_wgrad(x, dy, dw, Cout):
+    N, H, W, Cin = x.shape
+    wz = torch.zeros((Cout, Cin, 3, 3), dtype=torch.float32, requires_grad=True)
+    F.conv2d(x.float().permute(0, 3, 1, 2), wz).backward(dy.float().permute(0, 3, 1, 2))
+    dw.view(3, 3, Cin, Cout).add_(wz.grad.permute(2, 3, 1, 0))
+    return dw
+
+
 def gemm_simt(a, sam, sak, b, sbk, sbn, out, ldc, M, N, K, col_scale=None, col_shift=None, act=ACT_NONE, addend=None,
               ld_addend=0, accumulate=False):
     A = a.reshape(-1).as_strided((M, K), (sam, sak)).float()

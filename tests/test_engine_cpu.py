@@ -97,6 +97,38 @@ def test_bn_relu_fused_into_depthwise_schedule(cpu_engine, monkeypatch, fuse):
         assert np.abs(ga[k] - gb[k]).max() <= 2e-3 * scale, k
 
 
+def test_implicit_conv_schedule(cpu_engine, monkeypatch):
+    """Xception block1_conv2 (3x3 VALID stride 1, 32 -> 64): the implicit-GEMM schedule (no im2col / col2im, prepared
+    wk / wd filter matrices) must reproduce the im2col + GEMM schedule."""
+    monkeypatch.setattr(cpu_engine, "FORCE_IMPLICIT", True)
+    conf = util.make_conf(width=64, base="xception", output_stride=16, image_size=65)
+    ss = util.build(conf)
+    util.randomize_weights(ss.model)
+    calls = []
+    for name in ("im2col3x3", "col2im3x3", "conv3x3_valid_fwd", "conv3x3_valid_dgrad", "conv3x3_valid_wgrad"):
+        orig = getattr(fake_ops, name)
+        monkeypatch.setattr(fake_ops, name, (lambda orig, name: lambda *a, **k: (calls.append(name), orig(*a, **k))[1])(orig, name))
+    plan = cpu_engine.Plan(ss.model, 2, training=True)
+    x, y = util.synthetic_batch(conf, 2, plan.out_shape[1:3])
+    plan.set_loss(PW, NW)
+    plan.load_batch(x, y)
+    plan.step_fwd_bwd()
+    assert calls.count("conv3x3_valid_fwd") == 1 and calls.count("conv3x3_valid_dgrad") == 1
+    assert calls.count("conv3x3_valid_wgrad") == 1
+    n_im2col = calls.count("im2col3x3")
+    calls.clear()
+    ref = cpu_engine.Plan(ss.model, 2, training=True, implicit_conv=False)
+    ref.set_loss(PW, NW)
+    ref.load_batch(x, y)
+    ref.step_fwd_bwd()
+    assert calls.count("im2col3x3") == n_im2col + 1 and "conv3x3_valid_fwd" not in calls
+    np.testing.assert_allclose(plan.logits.buf.numpy(), ref.logits.buf.numpy(), rtol=1e-4, atol=1e-5)
+    ga, gb = plan.gradients(), ref.gradients()
+    for k in gb:
+        scale = max(np.abs(gb[k]).max(), 1e-3)
+        assert np.abs(ga[k] - gb[k]).max() <= 2e-3 * scale, k
+
+
 def test_inference_matches_oracle(cpu_engine):
     conf = util.make_conf(base="mobilenetv2", image_size=65, aspp=util.DEFAULT_ASPP, width=32)
     ss = util.build(conf)

@@ -154,6 +154,62 @@ def test_dwconv3x3_dgrad_bnred(case, act):
                                 code, mean.to(DEV), invstd.to(DEV), red, pad=pad)       # fp32: unfused path only
 
 
+@pytest.mark.parametrize("case", [(2, 20, 37, 32, 64), (1, 9, 131, 32, 64), (2, 12, 260, 40, 128), (1, 5, 3, 32, 64)])
+def test_conv3x3_valid_implicit_gemm(case):
+    """Implicit-GEMM 3x3 VALID stride-1 convolution (overlapping-row tensor maps, no im2col matrix): forward with BN
+    statistics, input gradient and filter gradient against the fp64 convolution on the same bf16 operands.  Widths
+    straddle the 128-pixel M tile / 64-pixel reduction block (ragged row ends are clipped by the rank-3 C map)."""
+    o = ops()
+    N, H, W, Cin, Cout = case
+    bf = torch.bfloat16
+    x = rnd((N, H, W, Cin), bf, 1)
+    w = rnd((3, 3, Cin, Cout), torch.float32, 2, 0.1).to(bf)             # HWIO, bf16-representable
+    KR = o.conv3x3_valid_kr(Cin)
+    wk = torch.zeros((Cout, 3, KR), dtype=bf)
+    wk[:, :, :3 * Cin] = w.reshape(3, 3 * Cin, Cout).permute(2, 0, 1)
+    wd = w.reshape(9, Cin, Cout).permute(1, 0, 2).reshape(Cin, 9 * Cout).contiguous()
+    Ho, Wo = H - 2, W - 2
+
+    xr = x.double().requires_grad_(True)
+    wr = w.double().requires_grad_(True)
+    y_ref = torch.nn.functional.conv2d(xr.permute(0, 3, 1, 2), wr.permute(3, 2, 0, 1)).permute(0, 2, 3, 1)
+    gy = rnd((N, Ho, Wo, Cout), bf, 5)
+    y_ref.backward(gy.double())
+
+    y = torch.full((N, Ho, Wo, Cout), float("nan"), dtype=bf, device=DEV)
+    stats = torch.zeros(2 * Cout, dtype=torch.float32, device=DEV)
+    o.conv3x3_valid_fwd(x.to(DEV), wk.view(Cout, 3 * KR).to(DEV), y, Cout, col_stats=stats)
+    check("implicit conv fwd", y, y_ref, 1e-2, 2e-2)
+    yq = y.double().cpu().reshape(-1, Cout)                              # statistics are those of the stored tile
+    check("implicit conv stats", stats, torch.cat([yq.sum(0), (yq * yq).sum(0)]), 2e-3, 2e-3 * math.sqrt(N * Ho * Wo))
+    if o.conv3x3_valid_supported(Cin, Cout):
+        dx = torch.full((N, H, W, Cin), float("nan"), dtype=bf, device=DEV)
+        o.conv3x3_valid_dgrad(gy.to(DEV), wd.to(DEV), (N, H, W, Cin), Cout, dx)
+        check("implicit conv dgrad", dx, xr.grad, 1e-2, 2e-2 * math.sqrt(9 * Cout / 64))
+        dw = torch.zeros((3, 3, Cin, Cout), dtype=torch.float32, device=DEV)
+        o.conv3x3_valid_wgrad(x.to(DEV), gy.to(DEV), dw, Cout)
+        check("implicit conv wgrad", dw, wr.grad, 2e-3, 2e-3 * math.sqrt(N * Ho * Wo))
+        o.conv3x3_valid_wgrad(x.to(DEV), gy.to(DEV), dw, Cout)           # accumulates
+        check("implicit conv wgrad x2", dw, 2 * wr.grad, 2e-3, 4e-3 * math.sqrt(N * Ho * Wo))
+    # fused inference epilogue (folded BN + ReLU)
+    sc = (rnd((Cout,), torch.float32, 3, 0.2) + 1.0)
+    sh = rnd((Cout,), torch.float32, 4, 0.3)
+    o.conv3x3_valid_fwd(x.to(DEV), wk.view(Cout, 3 * KR).to(DEV), y, Cout, col_scale=sc.to(DEV), col_shift=sh.to(DEV),
+                        act=o.ACT_RELU)
+    check("implicit conv fwd+bn+relu", y, torch.relu(y_ref.detach() * sc.double() + sh.double()), 1e-2, 3e-2)
+
+
+def test_conv3x3_valid_unsupported_shapes():
+    o = ops()
+    x = torch.zeros((1, 8, 8, 16), dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(ValueError):
+        o.conv3x3_valid_fwd(x, torch.zeros((32, 192), dtype=torch.bfloat16, device=DEV),
+                            torch.zeros((1, 6, 6, 32), dtype=torch.bfloat16, device=DEV), 32)    # Cout < 64
+    with pytest.raises(ValueError):
+        o.conv3x3_valid_wgrad(x, torch.zeros((1, 6, 6, 64), dtype=torch.bfloat16, device=DEV),
+                              torch.zeros((3, 3, 16, 64), device=DEV), 64)                       # 3*Cin <= 64
+
+
 GEMM_CASES = [
     # M, N, K
     (128, 32, 64),
