@@ -995,38 +995,181 @@ extern "C" int dlv3p_conv3x3_valid_fwd_bf16(const void* x, const void* wk, void*
     }
 }
 
+// ---- input gradient of the 3x3 VALID convolution: halo-staged implicit GEMM --------------------------------------
+// dx[n,h,w,c] = sum_{i,j,o} dy[n,h-i,w-j,o] * W[i,j,c,o].  M tile = 128 consecutive pixels of one dx row, K = 9 taps x 64
+// output channels, N = Cin (<= 32).  The generic implicit path above would fetch nine shifted 16 KB windows of dy per
+// tile (measured 226 us at [16,256,256,32]: 1.8 GB of L2 -> SM boxes, feed-bound).  Here ONE stage holds the three dy
+// rows h, h-1, h-2 as 130-pixel boxes (pixels w0-2 .. w0+127, zero-filled outside dy = full correlation), and the nine
+// taps are nine VIEWS of that stage: the A descriptor of tap (i, j) simply starts (2-j) pixel rows (128 B each) into row
+// buffer i.  The 128B swizzle of both TMA and UMMA is a function of the absolute shared-memory address (bits 4..6 ^= bits
+// 7..9), so a start address that is off the 1024-byte swizzle period needs nothing else: measured on B200, descriptor
+// base_offset (bits 49..51) = 0 reproduces the fp64 reference bit-for-bit-in-bf16, (start >> 7) & 7 does not.
+// The 9 x [Cin x 64] filter slices stay resident in shared memory for the whole kernel.
+namespace dlv3p {
+constexpr int kDgBoxPix = 130;                          // 128 + 2 halo pixels
+constexpr int kDgRowBytes = 17 * 1024;                  // 130 x 128 B rounded up to the swizzle period
+constexpr int kDgStageBytes = 3 * kDgRowBytes;
+constexpr int kDgStages = 3;
+constexpr int kDgBTapBytes = 32 * 128;                  // [32 input channels x 64 output channels] bf16, K-major
+constexpr int kDgThreads = 192;                         // producer, issuer, 4 epilogue warps
+constexpr int kDgSmem = kDgStages * kDgStageBytes + 9 * kDgBTapBytes + 1024 + 256;
+static_assert(kDgSmem <= 232448, "shared memory budget");
+
+struct ConvDgradParams {
+    __nv_bfloat16* dx;
+    int N, H, W, Cin, tpr, tiles;
+};
+
+__global__ void __launch_bounds__(kDgThreads, 1)
+conv3x3_valid_dgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                           const ConvDgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t b_base = smem_base + kDgStages * kDgStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDgStages * kDgStageBytes + 9 * kDgBTapBytes);
+    const uint32_t full_bar = smem_u32(bars);                      // kDgStages
+    const uint32_t empty_bar = smem_u32(bars + kDgStages);         // kDgStages
+    const uint32_t tmem_full_bar = smem_u32(bars + 2 * kDgStages);     // 2
+    const uint32_t tmem_empty_bar = smem_u32(bars + 2 * kDgStages + 2);    // 2
+    const uint32_t b_bar = smem_u32(bars + 2 * kDgStages + 4);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kDgStages + 5);
+    constexpr uint32_t TMEM_COLS = 64;                     // two accumulator stages of 32 columns
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_launch_dependents();
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+        for (int s = 0; s < kDgStages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + 8 * s, 1); mbar_init(tmem_empty_bar + 8 * s, 4); }
+        mbar_init(b_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // filter slices: resident for the whole kernel
+            mbar_expect_tx(b_bar, 9 * kDgBTapBytes);
+            for (int tap = 0; tap < 9; ++tap) tma_load_2d(b_base + tap * kDgBTapBytes, &tmB, b_bar, tap * 64, 0);
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
+                const uint32_t s = it % kDgStages, ph = (it / kDgStages) & 1u;
+                const int r = t / p.tpr, w0 = (t % p.tpr) * kBlockM;
+                const int n = r / p.H, h = r % p.H;
+                mbar_wait(empty_bar + 8 * s, ph ^ 1u);
+                mbar_expect_tx(full_bar + 8 * s, 3 * kDgBoxPix * 128);
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    tma_load_4d(smem_base + s * kDgStageBytes + i * kDgRowBytes, &tmA, full_bar + 8 * s, 0, w0 - 2, h - i, n);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) |
+                                       ((uint32_t)(kBlockM >> 4) << 24);
+            mbar_wait(b_bar, 0);
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
+                const uint32_t s = it % kDgStages, ph = (it / kDgStages) & 1u;
+                const uint32_t as = it & 1u;
+                mbar_wait(tmem_empty_bar + 8 * as, ((it >> 1) & 1u) ^ 1u);
+                mbar_wait(full_bar + 8 * s, ph);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * 32;
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int i = tap / 3, j = tap % 3;
+                    const uint32_t a_src = smem_base + s * kDgStageBytes + i * kDgRowBytes + (uint32_t)(2 - j) * 128u;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t ad = umma_desc(a_src + k * 32, 16, 1024);
+                        const uint64_t bd = umma_desc(b_base + tap * kDgBTapBytes + k * 32, 16, 1024);
+                        tc_mma_bf16(d_tmem, ad, bd, idesc, (tap > 0 || k > 0) ? 1u : 0u);
+                    }
+                }
+                tc_commit(empty_bar + 8 * s);
+                tc_commit(tmem_full_bar + 8 * as);
+            }
+        }
+    } else {
+        const int q = warp & 3;                              // TMEM lane quadrant of this warp
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
+            const uint32_t as = it & 1u;
+            const int r = t / p.tpr, w = (t % p.tpr) * kBlockM + q * 32 + lane;
+            mbar_wait(tmem_full_bar + 8 * as, (it >> 1) & 1u);
+            tc_fence_after();
+            uint32_t raw[32];
+            tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * 32, raw);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar + 8 * as);
+            if (w < p.W) {
+                // one pixel per lane: Cin (<= 32) contiguous bf16 = up to four 16-byte stores
+                __nv_bfloat16* dst = p.dx + ((long long)r * p.W + w) * p.Cin;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if (g * 8 >= p.Cin) break;
+                    uint32_t o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        __nv_bfloat162 pr = __floats2bfloat162_rn(__uint_as_float(raw[g * 8 + 2 * e]),
+                                                                  __uint_as_float(raw[g * 8 + 2 * e + 1]));
+                        o[e] = *reinterpret_cast<uint32_t*>(&pr);
+                    }
+                    *reinterpret_cast<uint4*>(dst + g * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+}  // namespace dlv3p
+
 extern "C" int dlv3p_conv3x3_valid_dgrad_bf16(const void* dy, const void* wd, void* dx, int N, int H, int W, int Cin,
                                               int Cout, void* stream) {
     int rc = conv_check(dy, wd, dx, N, H, W, Cin, Cout);
     if (rc) return rc;
-    DLV3P_REQUIRE((Cout % 64) == 0 && Cin <= 64, DLV3P_ERR_UNSUPPORTED,
-                  "conv3x3_valid_dgrad: Cout %% 64 == 0 and Cin <= 64 (got Cin=%d Cout=%d)", Cin, Cout);
+    DLV3P_REQUIRE(Cout == 64 && Cin <= 32, DLV3P_ERR_UNSUPPORTED,
+                  "conv3x3_valid_dgrad: Cout == 64 and Cin <= 32 (got Cin=%d Cout=%d)", Cin, Cout);
     const int Ho = H - 2, Wo = W - 2;
-    CUtensorMap tmA, tmB, tmC;
+    CUtensorMap tmA, tmB;
     {
         const long long dims[4] = {Cout, Wo, Ho, N};
         const long long str[3] = {2LL * Cout, 2LL * Wo * Cout, 2LL * Ho * Wo * Cout};
-        const int box[4] = {kBlockK, kBlockM, 1, 1};
+        const int box[4] = {kBlockK, kDgBoxPix, 1, 1};
         rc = make_tmap_nd(&tmA, dy, 4, dims, str, box);
         if (rc) return rc;
     }
-    rc = make_tmap(&tmB, wd, 9LL * Cout, Cin, 9LL * Cout, kBlockK, 64);
+    rc = make_tmap(&tmB, wd, 9LL * Cout, Cin, 9LL * Cout, kBlockK, 32);
     if (rc) return rc;
-    {
-        const long long dims[3] = {Cin, W, (long long)N * H};
-        const long long str[2] = {2LL * Cin, 2LL * W * Cin};
-        const int box[3] = {64, 32, 1};
-        rc = make_tmap_nd(&tmC, dx, 3, dims, str, box);
-        if (rc) return rc;
+    ConvDgradParams p;
+    p.dx = (__nv_bfloat16*)dx; p.N = N; p.H = H; p.W = W; p.Cin = Cin;
+    p.tpr = cdiv(W, kBlockM); p.tiles = N * H * p.tpr;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_valid_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDgSmem);
+        DLV3P_REQUIRE(e == cudaSuccess, DLV3P_ERR_CUDA, "cudaFuncSetAttribute(conv dgrad smem=%d): %s", kDgSmem, cudaGetErrorString(e));
+        configured = true;
     }
-    GemmParams p;
-    memset(&p, 0, sizeof(p));
-    p.cv_tpr = cdiv(W, kBlockM);
-    p.m_tiles = N * H * p.cv_tpr; p.n_tiles = 1;
-    p.M = p.m_tiles * kBlockM; p.N = Cin; p.K = 9 * Cout;
-    p.C = dx; p.ldc = Cin; p.c_dtype = DLV3P_BF16; p.act = DLV3P_ACT_NONE; p.splits = 1; p.tma_store = 1;
-    p.conv_mode = 2; p.cv_rows_in = Ho; p.cv_rows_out = H; p.cv_width = W; p.cv_rlimit = W; p.cv_kbr = Cout / 64;
-    return launch_gemm<64, false>(tmA, tmB, tmC, p, (cudaStream_t)stream);
+    const int grid = p.tiles < kNumSMs ? p.tiles : kNumSMs;
+    launch_pdl(conv3x3_valid_dgrad_kernel, dim3(grid), dim3(kDgThreads), kDgSmem, (cudaStream_t)stream, tmA, tmB, p);
+    return check_launch("conv3x3_valid_dgrad");
 }
 
 extern "C" int dlv3p_conv3x3_valid_wgrad_bf16(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin,

@@ -139,7 +139,7 @@ def gemm_wgrad_bf16(x: Tensor, dy: Tensor, dw: Tensor, M: int, K: int, N: int, l
 
 def conv3x3_valid_supported(Cin: int, Cout: int) -> bool:
     """Shapes all three implicit-GEMM entry points accept (see include/dlv3p.h)."""
-    return Cin % 8 == 0 and Cout % 64 == 0 and 64 <= Cout <= 256 and 64 < 3 * Cin <= 128
+    return Cin % 8 == 0 and Cout == 64 and 64 < 3 * Cin <= 96
 
 
 def conv3x3_valid_kr(Cin: int) -> int:

@@ -105,7 +105,8 @@ int dlv3p_gemm_wgrad_bf16(const void* X, int64_t ldx, const void* dY, int64_t ld
  *          wk = bf16 [Cout, 3*KR], KR = 64*ceil(3*Cin/64), wk[o, i*KR + j*Cin + c] = W[i,j,c,o], zeros elsewhere.
  *          64 <= Cout <= 256.
  *   dgrad: dx[N,H,W,Cin] = conv_transpose(dy[N,Ho,Wo,Cout], W); wd = bf16 [Cin, 9*Cout], wd[c,(i*3+j)*Cout+o] = W[i,j,c,o].
- *          Cout % 64 == 0, Cin <= 64.
+ *          One stage holds the three dy rows a 128-pixel tile needs (130-pixel boxes); the nine taps are nine views of
+ *          it (UMMA descriptor base_offset), the filter slices stay resident in shared memory.  Cout == 64, Cin <= 32.
  *   wgrad: dw (fp32 HWIO [3,3,Cin,Cout]) += sum_pixels x-window * dy.  64 < 3*Cin <= 128.
  * Cin, Cout multiples of 8; all pointers 16-byte aligned; anything else returns DLV3P_ERR_UNSUPPORTED and the caller
  * uses dlv3p_im2col3x3 + dlv3p_gemm_bf16. */

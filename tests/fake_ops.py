@@ -138,7 +138,7 @@ def gemm_wgrad_bf16(x, dy, dw, M, K, N, ldx=None, ldy=None, ldw=None):
 
 
 def conv3x3_valid_supported(Cin, Cout):
-    return Cin % 8 == 0 and Cout % 64 == 0 and 64 <= Cout <= 256 and 64 < 3 * Cin <= 128
+    return Cin % 8 == 0 and Cout == 64 and 64 < 3 * Cin <= 96
 
 
 def conv3x3_valid_kr(Cin):
