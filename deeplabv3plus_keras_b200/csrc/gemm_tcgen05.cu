@@ -67,6 +67,7 @@ struct GemmParams {
     int cv_rlimit;                     // epilogue clip inside a C "row": fwd Wo, dgrad W, wgrad 3*Cin
     int cv_tpr;                        // fwd/dgrad: 128-pixel M tiles per row; wgrad: 64-pixel reduction blocks per row
     int cv_kbr;                        // fwd/wgrad: 64-element k-blocks per filter row; dgrad: 64-channel blocks per tap
+    int cv_run;                        // fwd: 3*Cin, the length of one filter row's run in the [Cout, 9*Cin] filter matrix
     int dbg;                           // diagnostics only (DLV3P_GEMM_DBG): 1 = no operand loads, 2 = no epilogue work, 4 = no MMAs, 8 = no C stores, 16 = no TMEM reads
 };
 
@@ -216,11 +217,15 @@ __device__ __forceinline__ void staged_tile_epilogue(const GemmParams& p, const 
             // all 32 banks distinct); rows >= M hold exact zeros (TMA zero-filled A)
             float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
             const uint32_t cj = (uint32_t)(lane >> 2), cw = (uint32_t)(lane & 3) << 2;
+            // (the halo-staged convolution kernel computes real values for the pixels beyond a ragged row end: they are
+            // clipped from the store and must be kept out of the statistics as well)
+            const int rv = row_limit - rbase;
 #pragma unroll 8
             for (int rr = 0; rr < 32; ++rr) {
                 uint32_t word;
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word)
                              : "r"(stg + (uint32_t)rr * 128u + ((cj ^ (uint32_t)(rr & 7)) << 4) + cw));
+                if (rr >= rv) word = 0u;
                 const float a = __uint_as_float(word << 16), b = __uint_as_float(word & 0xffff0000u);
                 s1a += a; s2a = fmaf(a, a, s2a);
                 s1b += b; s2b = fmaf(b, b, s2b);
@@ -324,13 +329,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 // beyond the run and columns beyond the row are zero-filled by TMA)
                                 const int i = kb / p.cv_kbr, part = kb % p.cv_kbr;
                                 tma_load_3d(a_dst, &tmA, fb, part * 64, w0, n * p.cv_rows_in + hh + i);
+                                // filter columns of the same 64 run elements; what the box takes beyond the run belongs
+                                // to the next filter row (or is zero-filled) and meets the zero-filled A elements
+                                tma_load_2d(b_dst, &tmB, fb, i * p.cv_run + part * 64, col0);
                             } else {
                                 // input gradient: k-block = 64 output channels of dy under tap (i, j), window shifted by
                                 // (-i, -j); positions outside dy are zero-filled (full correlation)
                                 const int tap = kb / p.cv_kbr, part = kb % p.cv_kbr;
                                 tma_load_4d(a_dst, &tmA, fb, part * 64, w0 - tap % 3, hh - tap / 3, n);
+                                tma_load_2d(b_dst, &tmB, fb, kk, col0);
                             }
-                            tma_load_2d(b_dst, &tmB, fb, kk, col0);
                         }
                     } else if (WGRAD) {
                         // MN-major operands: boxes of 64 channels (inner, 128 B) x 64 pixels
@@ -941,9 +949,151 @@ extern "C" int dlv3p_gemm_wgrad_bf16(const void* X, int64_t ldx, const void* dY,
 // k-blocks and TMA zero-fills what lies beyond the run / the image row, so K = 3 * 64*ceil(3*Cin/64) with matching zero
 // columns in the prepared filter matrix.  M tiles are 128 output pixels of ONE image row (rank-3 C map clips the
 // ragged row end), so BatchNormalization statistics see exact zeros for the clipped pixels.
-//   wk (forward B operand)  bf16 [Cout, 3*KR], wk[o, i*KR + j*Cin + c] = W[i,j,c,o], KR = 64*ceil(3*Cin/64), zero elsewhere
+//   wt (forward B operand)  bf16 [Cout, 9*Cin] K-major (row pitch ldw), wt[o, (i*3+j)*Cin + c] = W[i,j,c,o] — the same
+//                           matrix the im2col GEMM uses
 //   wd (dgrad B operand)    bf16 [Cin, 9*Cout], wd[c, (i*3+j)*Cout + o] = W[i,j,c,o]
 // =====================================================================================================================
+// ---- forward 3x3 VALID convolution with 32 input channels: halo-staged implicit GEMM ---------------------------------
+// Same idea as the input-gradient kernel below, on 64-byte pixels (Cin = 32): one stage holds the three input rows
+// ho, ho+1, ho+2 as 130-pixel boxes under the 64B swizzle, tap (i, j) is the view that starts j pixels (64 B each) into
+// row buffer i (K = 32 per tap, two UMMA K-steps), the nine [Cout x 32] filter slices stay resident.  Per 128-pixel tile
+// 25 KB arrive instead of the 144 KB of the run-based path (measured 163 us, feed-bound).  Epilogue = the GEMM's staged
+// TMA-store epilogue (bf16 tile, BatchNormalization statistics, rank-3 C map clips the ragged row end).
+namespace dlv3p {
+constexpr int kDgBoxPix = 130;                          // 128 + 2 halo pixels
+constexpr int kFwRowBytes = 9 * 1024;                   // 130 x 64 B rounded up to 1 KB
+constexpr int kFwStageBytes = 3 * kFwRowBytes;
+constexpr int kFwStages = 3;
+constexpr int kFwBTapBytes = 64 * 64;                   // [64 output channels x 32 input channels] bf16, K-major, SW64
+constexpr int kFwSmem = kFwStages * kFwStageBytes + 9 * kFwBTapBytes + kEpiBytes + 2 * kMaxStatCols * 4 + 1024 + 256;
+static_assert(kFwSmem <= 232448, "shared memory budget");
+
+// UMMA smem descriptor, K-major, 64B swizzle (layout type 4): 8-row groups are 512 B apart
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) |
+           (4ull << 61);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_valid_fwd32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                           const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t b_base = smem_base + kFwStages * kFwStageBytes;
+    uint8_t* epi_bytes = smem + kFwStages * kFwStageBytes + 9 * kFwBTapBytes;
+    float* stat_smem = reinterpret_cast<float*>(epi_bytes + kEpiBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_bytes + kEpiBytes + 2 * kMaxStatCols * 4);
+    const uint32_t full_bar = smem_u32(bars);
+    const uint32_t empty_bar = smem_u32(bars + kFwStages);
+    const uint32_t tmem_full_bar = smem_u32(bars + 2 * kFwStages);
+    const uint32_t tmem_empty_bar = smem_u32(bars + 2 * kFwStages + 2);
+    const uint32_t b_bar = smem_u32(bars + 2 * kFwStages + 4);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kFwStages + 5);
+    constexpr uint32_t TMEM_COLS = 128;                    // two accumulator stages of 64 columns
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_launch_dependents();
+    if (p.col_stats != nullptr)
+        for (int i = threadIdx.x; i < 2 * kMaxStatCols; i += kThreads) stat_smem[i] = 0.f;
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
+        for (int s = 0; s < kFwStages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + 8 * s, 1); mbar_init(tmem_empty_bar + 8 * s, kEpiWarps); }
+        mbar_init(b_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    pdl_wait();
+    const int tiles = p.m_tiles;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(b_bar, 9 * kFwBTapBytes);
+            for (int tap = 0; tap < 9; ++tap) tma_load_2d(b_base + tap * kFwBTapBytes, &tmB, b_bar, tap * 32, 0);
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+                const uint32_t s = it % kFwStages, ph = (it / kFwStages) & 1u;
+                const int r = t / p.cv_tpr, w0 = (t % p.cv_tpr) * kBlockM;
+                const int n = r / p.cv_rows_out, ho = r % p.cv_rows_out;
+                mbar_wait(empty_bar + 8 * s, ph ^ 1u);
+                mbar_expect_tx(full_bar + 8 * s, 3 * kDgBoxPix * 64);
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    tma_load_4d(smem_base + s * kFwStageBytes + i * kFwRowBytes, &tmA, full_bar + 8 * s, 0, w0, ho + i, n);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) |
+                                       ((uint32_t)(kBlockM >> 4) << 24);
+            mbar_wait(b_bar, 0);
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+                const uint32_t s = it % kFwStages, ph = (it / kFwStages) & 1u;
+                const uint32_t as = it & 1u;
+                mbar_wait(tmem_empty_bar + 8 * as, ((it >> 1) & 1u) ^ 1u);
+                mbar_wait(full_bar + 8 * s, ph);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * 64;
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const uint32_t a_src = smem_base + s * kFwStageBytes + (tap / 3) * kFwRowBytes + (uint32_t)(tap % 3) * 64u;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        tc_mma_bf16(d_tmem, umma_desc_sw64(a_src + k * 32), umma_desc_sw64(b_base + tap * kFwBTapBytes + k * 32),
+                                    idesc, (tap > 0 || k > 0) ? 1u : 0u);
+                }
+                tc_commit(empty_bar + 8 * s);
+                tc_commit(tmem_full_bar + 8 * as);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int ew = warp - 2, half = ew >> 2;
+        const bool use_smem_stats = (p.col_stats != nullptr) && (p.N <= kMaxStatCols);
+        const uint32_t stg0 = smem_u32(epi_bytes) + (uint32_t)ew * 2u * kEpiBufBytes;
+        uint32_t buf = 0, it = 0;
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+            const uint32_t as = it & 1u;
+            const int r = t / p.cv_tpr, w0 = (t % p.cv_tpr) * kBlockM;
+            mbar_wait(tmem_full_bar + 8 * as, (it >> 1) & 1u);
+            tc_fence_after();
+            staged_tile_epilogue<64, false, false>(p, &tmC, tmem_base + ((uint32_t)(q * 32) << 16) + as * 64, w0 + q * 32, 0,
+                                                   lane, half, stg0, buf, tmem_empty_bar + 8 * as, stat_smem,
+                                                   use_smem_stats, p.cv_rlimit, r);
+        }
+        if (lane == 0) tma_wait_group_all();
+        if (use_smem_stats) {
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+            const int e = threadIdx.x - 64;
+            for (int c = e; c < p.N; c += 32 * kEpiWarps) {
+                const float a1 = stat_smem[c], a2 = stat_smem[kMaxStatCols + c];
+                if (a1 != 0.f || a2 != 0.f) {
+                    atomicAdd(p.col_stats + c, a1);
+                    atomicAdd(p.col_stats + p.N + c, a2);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+}  // namespace dlv3p
+
 static int conv_check(const void* a, const void* b, const void* c, int N, int H, int W, int Cin, int Cout) {
     DLV3P_REQUIRE(a && b && c && N > 0 && H >= 3 && W >= 3 && Cin > 0 && Cout > 0, DLV3P_ERR_SHAPE,
                   "conv3x3_valid: bad arguments N=%d H=%d W=%d Cin=%d Cout=%d", N, H, W, Cin, Cout);
@@ -952,25 +1102,39 @@ static int conv_check(const void* a, const void* b, const void* c, int N, int H,
     return 0;
 }
 
-extern "C" int dlv3p_conv3x3_valid_fwd_bf16(const void* x, const void* wk, void* y, int N, int H, int W, int Cin,
-                                            int Cout, const float* col_scale, const float* col_shift, int act,
+extern "C" int dlv3p_conv3x3_valid_fwd_bf16(const void* x, const void* wt, int64_t ldw, void* y, int N, int H, int W,
+                                            int Cin, int Cout, const float* col_scale, const float* col_shift, int act,
                                             float* col_stats, void* stream) {
-    int rc = conv_check(x, wk, y, N, H, W, Cin, Cout);
+    int rc = conv_check(x, wt, y, N, H, W, Cin, Cout);
     if (rc) return rc;
     DLV3P_REQUIRE(Cout <= 256 && Cout >= 64, DLV3P_ERR_UNSUPPORTED, "conv3x3_valid_fwd: 64 <= Cout <= 256 (got %d)", Cout);
+    DLV3P_REQUIRE(ldw >= 9LL * Cin && (ldw % 8) == 0, DLV3P_ERR_ALIGN, "conv3x3_valid_fwd: ldw >= 9*Cin and a multiple of 8");
+    DLV3P_REQUIRE((col_scale == nullptr) == (col_shift == nullptr), DLV3P_ERR_SHAPE, "conv3x3_valid_fwd: scale/shift mismatch");
     const int Ho = H - 2, Wo = W - 2;
     const int kbr = cdiv(3 * Cin, kBlockK), KR = kbr * kBlockK;
     const int bn = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
+    const bool fast = (Cin == 32 && Cout == 64);             // 64-byte pixels: halo-staged kernel, taps as shifted views
     CUtensorMap tmA, tmB, tmC;
-    {
+    if (fast) {
+        const long long dims[4] = {Cin, W, H, N};
+        const long long str[3] = {2LL * Cin, 2LL * W * Cin, 2LL * H * W * Cin};
+        const int box[4] = {32, kDgBoxPix, 1, 1};
+        rc = make_tmap_nd(&tmA, x, 4, dims, str, box, false, /*swizzle64=*/true);
+        if (rc) return rc;
+        const long long bdims[2] = {9LL * Cin, Cout};
+        const long long bstr[1] = {2LL * ldw};
+        const int bbox[2] = {32, 64};
+        rc = make_tmap_nd(&tmB, wt, 2, bdims, bstr, bbox, false, /*swizzle64=*/true);
+        if (rc) return rc;
+    } else {
         const long long dims[3] = {3LL * Cin, Wo, (long long)N * H};
         const long long str[2] = {2LL * Cin, 2LL * W * Cin};
         const int box[3] = {kBlockK, kBlockM, 1};
         rc = make_tmap_nd(&tmA, x, 3, dims, str, box);
         if (rc) return rc;
+        rc = make_tmap(&tmB, wt, 9LL * Cin, Cout, ldw, kBlockK, bn);
+        if (rc) return rc;
     }
-    rc = make_tmap(&tmB, wk, 3LL * KR, Cout, 3LL * KR, kBlockK, bn);
-    if (rc) return rc;
     {
         const long long dims[3] = {Cout, Wo, (long long)N * Ho};
         const long long str[2] = {2LL * Cout, 2LL * Wo * Cout};
@@ -983,11 +1147,22 @@ extern "C" int dlv3p_conv3x3_valid_fwd_bf16(const void* x, const void* wk, void*
     p.cv_tpr = cdiv(Wo, kBlockM);
     p.m_tiles = N * Ho * p.cv_tpr; p.n_tiles = cdiv(Cout, bn);
     p.M = p.m_tiles * kBlockM; p.N = Cout; p.K = 3 * KR;
-    DLV3P_REQUIRE((col_scale == nullptr) == (col_shift == nullptr), DLV3P_ERR_SHAPE, "conv3x3_valid_fwd: scale/shift mismatch");
     p.C = y; p.ldc = Cout; p.c_dtype = DLV3P_BF16; p.col_scale = col_scale; p.col_shift = col_shift; p.act = act;
     p.col_stats = col_stats; p.splits = 1; p.tma_store = 1; p.dbg = 0;
     p.conv_mode = 1; p.cv_rows_in = H; p.cv_rows_out = Ho; p.cv_width = Wo; p.cv_rlimit = Wo; p.cv_kbr = kbr;
+    p.cv_run = 3 * Cin;
     cudaStream_t st = (cudaStream_t)stream;
+    if (fast) {
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(conv3x3_valid_fwd32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwSmem);
+            DLV3P_REQUIRE(e == cudaSuccess, DLV3P_ERR_CUDA, "cudaFuncSetAttribute(conv fwd smem=%d): %s", kFwSmem, cudaGetErrorString(e));
+            configured = true;
+        }
+        const int grid = p.m_tiles < kNumSMs ? p.m_tiles : kNumSMs;
+        launch_pdl(conv3x3_valid_fwd32_kernel, dim3(grid), dim3(kThreads), kFwSmem, st, tmA, tmB, tmC, p);
+        return check_launch("conv3x3_valid_fwd (halo-staged)");
+    }
     switch (bn) {
         case 64: return launch_gemm<64, false>(tmA, tmB, tmC, p, st);
         case 128: return launch_gemm<128, false>(tmA, tmB, tmC, p, st);
@@ -1006,7 +1181,6 @@ extern "C" int dlv3p_conv3x3_valid_fwd_bf16(const void* x, const void* wk, void*
 // base_offset (bits 49..51) = 0 reproduces the fp64 reference bit-for-bit-in-bf16, (start >> 7) & 7 does not.
 // The 9 x [Cin x 64] filter slices stay resident in shared memory for the whole kernel.
 namespace dlv3p {
-constexpr int kDgBoxPix = 130;                          // 128 + 2 halo pixels
 constexpr int kDgRowBytes = 17 * 1024;                  // 130 x 128 B rounded up to the swizzle period
 constexpr int kDgStageBytes = 3 * kDgRowBytes;
 constexpr int kDgStages = 3;

@@ -114,7 +114,7 @@ static inline int make_tmap(CUtensorMap* map, const void* base, long long d0, lo
 // OVERLAPPING rows: dims[0] = 3*Cin elements (the three horizontally adjacent pixels under one filter row) while the
 // pitch of dims[1] (the output column) is only Cin elements.
 static inline int make_tmap_nd(CUtensorMap* map, const void* base, int rank, const long long* dims,
-                               const long long* strides_bytes, const int* box, bool f32 = false) {
+                               const long long* strides_bytes, const int* box, bool f32 = false, bool swizzle64 = false) {
     auto fn = get_encode_fn();
     DLV3P_REQUIRE(fn != nullptr, DLV3P_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t d[5], st[4];
@@ -122,7 +122,8 @@ static inline int make_tmap_nd(CUtensorMap* map, const void* base, int rank, con
     for (int i = 0; i < rank; ++i) { d[i] = (cuuint64_t)dims[i]; b[i] = (cuuint32_t)box[i]; }
     for (int i = 0; i + 1 < rank; ++i) st[i] = (cuuint64_t)strides_bytes[i];
     CUresult rc = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
-                     const_cast<void*>(base), d, st, b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     const_cast<void*>(base), d, st, b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DLV3P_REQUIRE(rc == CUDA_SUCCESS, DLV3P_ERR_CUDA,
                   "cuTensorMapEncodeTiled(rank %d) failed (%d) dims=(%lld,%lld,%lld) box=(%d,%d,%d)", rank, (int)rc,

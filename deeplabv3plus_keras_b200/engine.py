@@ -495,13 +495,12 @@ class Plan:
                         and getattr(node, "explicit_pad", None) is None and not is_logits and other_id is None
                         and ops.conv3x3_valid_supported(Cin, Cout))
             if implicit:
-                KR = ops.conv3x3_valid_kr(Cin)
                 wdt = torch.bfloat16 if self.bf16 else torch.float32          # (fp32 only under FORCE_IMPLICIT, CPU tests)
-                wk = self._alloc((Cout, 3 * KR), wdt, zero=True)              # forward B operand (zero-padded runs)
+                wt = self._alloc((Cout, Kp), wdt, zero=True)                  # forward B operand = the im2col GEMM's
                 wd = self._alloc((Cin, 9 * Cout), wdt) if training else None  # input-gradient B operand
+                self._wprep.append((w32, Kdim, Cout, wt, Kp, None, Np))
 
                 def prep_implicit():
-                    wk.view(Cout, 3, KR)[:, :, :3 * Cin].copy_(w32.view(3, 3 * Cin, Cout).permute(2, 0, 1))
                     if wd is not None:
                         wd.view(Cin, 9, Cout).copy_(w32.view(9, Cin, Cout).permute(1, 0, 2))
                 self.prep.append(prep_implicit)
@@ -582,7 +581,7 @@ class Plan:
                 tgt = out.buf if (fuse_epi or bn_node is None) else y
                 stats_fn = stat if (bn_node is not None and training) else None
                 self.fwd.append(lambda: ops.conv3x3_valid_fwd(
-                    xb, wk, tgt, Cout, col_scale=scale if fuse_epi else None, col_shift=shift if fuse_epi else None,
+                    xb, wt, tgt, Cout, ldw=Kp, col_scale=scale if fuse_epi else None, col_shift=shift if fuse_epi else None,
                     act=act if fuse_epi else ACT_NONE, col_stats=stats_fn() if stats_fn else None))
             elif self.bf16:
                 tgt = out.buf if (fuse_epi or bn_node is None) else y

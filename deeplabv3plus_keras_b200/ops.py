@@ -142,17 +142,13 @@ def conv3x3_valid_supported(Cin: int, Cout: int) -> bool:
     return Cin % 8 == 0 and Cout == 64 and 64 < 3 * Cin <= 96
 
 
-def conv3x3_valid_kr(Cin: int) -> int:
-    return (3 * Cin + 63) // 64 * 64
-
-
-def conv3x3_valid_fwd(x: Tensor, wk: Tensor, out: Tensor, Cout: int, col_scale=None, col_shift=None, act=ACT_NONE,
-                      col_stats=None):
-    """out[N,H-2,W-2,Cout] = epi(conv3x3_valid(x[N,H,W,Cin])), implicit GEMM; wk bf16 [Cout, 3*KR]."""
+def conv3x3_valid_fwd(x: Tensor, wt: Tensor, out: Tensor, Cout: int, ldw=None, col_scale=None, col_shift=None,
+                      act=ACT_NONE, col_stats=None):
+    """out[N,H-2,W-2,Cout] = epi(conv3x3_valid(x[N,H,W,Cin])), implicit GEMM; wt bf16 [Cout, 9*Cin] K-major (pitch ldw)."""
     _chk(x, "x")
     N, H, W, Cin = x.shape
-    call("dlv3p_conv3x3_valid_fwd_bf16", _p(x), _p(wk), _p(out), N, H, W, Cin, Cout, _p(col_scale), _p(col_shift), act,
-         _p(col_stats), _stream())
+    call("dlv3p_conv3x3_valid_fwd_bf16", _p(x), _p(wt), 9 * Cin if ldw is None else ldw, _p(out), N, H, W, Cin, Cout,
+         _p(col_scale), _p(col_shift), act, _p(col_stats), _stream())
     return out
 
 

@@ -36,8 +36,8 @@ COSTS: Dict[str, Tuple[str, Callable]] = {
     "dlv3p_gemm_bf16": ("tensor", lambda a: ((a[6] * a[8] + a[7] * a[8]) * 2 + a[6] * a[7] * _esz(a[9]) * (1 + _opt(a[13])),
                                             2 * a[6] * a[7] * a[8])),
     "dlv3p_gemm_wgrad_bf16": ("tensor", lambda a: ((a[6] * a[7] + a[6] * a[8]) * 2 + a[7] * a[8] * 4, 2 * a[6] * a[7] * a[8])),
-    "dlv3p_conv3x3_valid_fwd_bf16": ("tensor", lambda a: ((a[3] * a[4] * a[5] * a[6] + a[3] * (a[4] - 2) * (a[5] - 2) * a[7]) * 2 + 18 * a[6] * a[7],
-                                                         18 * a[3] * (a[4] - 2) * (a[5] - 2) * a[6] * a[7])),
+    "dlv3p_conv3x3_valid_fwd_bf16": ("tensor", lambda a: ((a[4] * a[5] * a[6] * a[7] + a[4] * (a[5] - 2) * (a[6] - 2) * a[8]) * 2 + 18 * a[7] * a[8],
+                                                         18 * a[4] * (a[5] - 2) * (a[6] - 2) * a[7] * a[8])),
     "dlv3p_conv3x3_valid_dgrad_bf16": ("tensor", lambda a: ((a[3] * a[4] * a[5] * a[6] + a[3] * (a[4] - 2) * (a[5] - 2) * a[7]) * 2 + 18 * a[6] * a[7],
                                                            18 * a[3] * (a[4] - 2) * (a[5] - 2) * a[6] * a[7])),
     "dlv3p_conv3x3_valid_wgrad_bf16": ("tensor", lambda a: ((a[3] * a[4] * a[5] * a[6] + a[3] * (a[4] - 2) * (a[5] - 2) * a[7]) * 2 + 36 * a[6] * a[7],

@@ -102,16 +102,17 @@ int dlv3p_gemm_wgrad_bf16(const void* X, int64_t ldx, const void* dY, int64_t ld
  * keras.applications.xception Conv2D(64, (3,3), use_bias=False), reached through ss.py:512-515; TF runs it as one
  * cuDNN Conv2D + Conv2DBackpropInput + Conv2DBackpropFilter).  Ho = H-2, Wo = W-2.
  *   fwd:   y[N,Ho,Wo,Cout] = epilogue(conv(x[N,H,W,Cin], W)); epilogue and col_stats as dlv3p_gemm_bf16.
- *          wk = bf16 [Cout, 3*KR], KR = 64*ceil(3*Cin/64), wk[o, i*KR + j*Cin + c] = W[i,j,c,o], zeros elsewhere.
- *          64 <= Cout <= 256.
+ *          wt = bf16 [Cout, 9*Cin] K-major with row pitch ldw, wt[o, (i*3+j)*Cin + c] = W[i,j,c,o] (the im2col GEMM's B).
+ *          64 <= Cout <= 256.  Cin == 32, Cout == 64 takes the halo-staged kernel (three input rows per stage, nine taps
+ *          as shifted UMMA views of it); other shapes read overlapping 3*Cin-element runs through a rank-3 tensor map.
  *   dgrad: dx[N,H,W,Cin] = conv_transpose(dy[N,Ho,Wo,Cout], W); wd = bf16 [Cin, 9*Cout], wd[c,(i*3+j)*Cout+o] = W[i,j,c,o].
  *          One stage holds the three dy rows a 128-pixel tile needs (130-pixel boxes); the nine taps are nine views of
  *          it (UMMA descriptor base_offset), the filter slices stay resident in shared memory.  Cout == 64, Cin <= 32.
  *   wgrad: dw (fp32 HWIO [3,3,Cin,Cout]) += sum_pixels x-window * dy.  64 < 3*Cin <= 128.
  * Cin, Cout multiples of 8; all pointers 16-byte aligned; anything else returns DLV3P_ERR_UNSUPPORTED and the caller
  * uses dlv3p_im2col3x3 + dlv3p_gemm_bf16. */
-int dlv3p_conv3x3_valid_fwd_bf16(const void* x, const void* wk, void* y, int N, int H, int W, int Cin, int Cout,
-                                 const float* col_scale, const float* col_shift, int act, float* col_stats,
+int dlv3p_conv3x3_valid_fwd_bf16(const void* x, const void* wt, int64_t ldw, void* y, int N, int H, int W, int Cin,
+                                 int Cout, const float* col_scale, const float* col_shift, int act, float* col_stats,
                                  void* stream);
 int dlv3p_conv3x3_valid_dgrad_bf16(const void* dy, const void* wd, void* dx, int N, int H, int W, int Cin, int Cout,
                                    void* stream);

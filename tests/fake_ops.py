@@ -141,19 +141,11 @@ def conv3x3_valid_supported(Cin, Cout):
     return Cin % 8 == 0 and Cout == 64 and 64 < 3 * Cin <= 96
 
 
-def conv3x3_valid_kr(Cin):
-    return (3 * Cin + 63) // 64 * 64
-
-
-def _hwio_from_wk(wk, Cin, Cout):
-    KR = conv3x3_valid_kr(Cin)
-    return wk.float().view(Cout, 3, KR)[:, :, :3 * Cin].reshape(Cout, 3, 3, Cin).permute(1, 2, 3, 0)    # [3,3,Cin,Cout]
-
-
-def conv3x3_valid_fwd(x, wk, out, Cout, col_scale=None, col_shift=None, act=ACT_NONE, col_stats=None):
+def conv3x3_valid_fwd(x, wt, out, Cout, ldw=None, col_scale=None, col_shift=None, act=ACT_NONE, col_stats=None):
     N, H, W, Cin = x.shape
-    w = _hwio_from_wk(wk, Cin, Cout)
-    acc = F.conv2d(x.float().permute(0, 3, 1, 2), w.permute(3, 2, 0, 1)).permute(0, 2, 3, 1).reshape(-1, Cout)
+    ldw = ldw or 9 * Cin
+    w = _rows(wt, Cout, ldw, 9 * Cin).float().reshape(Cout, 3, 3, Cin)                 # [o, i, j, c]
+    acc = F.conv2d(x.float().permute(0, 3, 1, 2), w.permute(0, 3, 1, 2)).permute(0, 2, 3, 1).reshape(-1, Cout)
     if col_stats is not None:
         col_stats[:Cout] += acc.sum(0)
         col_stats[Cout:2 * Cout] += (acc * acc).sum(0)

@@ -164,9 +164,7 @@ def test_conv3x3_valid_implicit_gemm(case):
     bf = torch.bfloat16
     x = rnd((N, H, W, Cin), bf, 1)
     w = rnd((3, 3, Cin, Cout), torch.float32, 2, 0.1).to(bf)             # HWIO, bf16-representable
-    KR = o.conv3x3_valid_kr(Cin)
-    wk = torch.zeros((Cout, 3, KR), dtype=bf)
-    wk[:, :, :3 * Cin] = w.reshape(3, 3 * Cin, Cout).permute(2, 0, 1)
+    wt = w.reshape(9 * Cin, Cout).t().contiguous()                       # [Cout, 9*Cin] K-major, as the im2col GEMM's B
     wd = w.reshape(9, Cin, Cout).permute(1, 0, 2).reshape(Cin, 9 * Cout).contiguous()
     Ho, Wo = H - 2, W - 2
 
@@ -178,7 +176,7 @@ def test_conv3x3_valid_implicit_gemm(case):
 
     y = torch.full((N, Ho, Wo, Cout), float("nan"), dtype=bf, device=DEV)
     stats = torch.zeros(2 * Cout, dtype=torch.float32, device=DEV)
-    o.conv3x3_valid_fwd(x.to(DEV), wk.view(Cout, 3 * KR).to(DEV), y, Cout, col_stats=stats)
+    o.conv3x3_valid_fwd(x.to(DEV), wt.to(DEV), y, Cout, col_stats=stats)
     check("implicit conv fwd", y, y_ref, 1e-2, 2e-2)
     yq = y.double().cpu().reshape(-1, Cout)                              # statistics are those of the stored tile
     check("implicit conv stats", stats, torch.cat([yq.sum(0), (yq * yq).sum(0)]), 2e-3, 2e-3 * math.sqrt(N * Ho * Wo))
@@ -194,8 +192,7 @@ def test_conv3x3_valid_implicit_gemm(case):
     # fused inference epilogue (folded BN + ReLU)
     sc = (rnd((Cout,), torch.float32, 3, 0.2) + 1.0)
     sh = rnd((Cout,), torch.float32, 4, 0.3)
-    o.conv3x3_valid_fwd(x.to(DEV), wk.view(Cout, 3 * KR).to(DEV), y, Cout, col_scale=sc.to(DEV), col_shift=sh.to(DEV),
-                        act=o.ACT_RELU)
+    o.conv3x3_valid_fwd(x.to(DEV), wt.to(DEV), y, Cout, col_scale=sc.to(DEV), col_shift=sh.to(DEV), act=o.ACT_RELU)
     check("implicit conv fwd+bn+relu", y, torch.relu(y_ref.detach() * sc.double() + sh.double()), 1e-2, 3e-2)
 
 
@@ -203,7 +200,7 @@ def test_conv3x3_valid_unsupported_shapes():
     o = ops()
     x = torch.zeros((1, 8, 8, 16), dtype=torch.bfloat16, device=DEV)
     with pytest.raises(ValueError):
-        o.conv3x3_valid_fwd(x, torch.zeros((32, 192), dtype=torch.bfloat16, device=DEV),
+        o.conv3x3_valid_fwd(x, torch.zeros((32, 144), dtype=torch.bfloat16, device=DEV),
                             torch.zeros((1, 6, 6, 32), dtype=torch.bfloat16, device=DEV), 32)    # Cout < 64
     with pytest.raises(ValueError):
         o.conv3x3_valid_wgrad(x, torch.zeros((1, 6, 6, 64), dtype=torch.bfloat16, device=DEV),
