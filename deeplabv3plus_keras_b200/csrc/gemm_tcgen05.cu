@@ -963,7 +963,7 @@ namespace dlv3p {
 constexpr int kDgBoxPix = 130;                          // 128 + 2 halo pixels
 constexpr int kFwRowBytes = 9 * 1024;                   // 130 x 64 B rounded up to 1 KB
 constexpr int kFwStageBytes = 3 * kFwRowBytes;
-constexpr int kFwStages = 3;
+constexpr int kFwStages = 4;
 constexpr int kFwBTapBytes = 64 * 64;                   // [64 output channels x 32 input channels] bf16, K-major, SW64
 constexpr int kFwSmem = kFwStages * kFwStageBytes + 9 * kFwBTapBytes + kEpiBytes + 2 * kMaxStatCols * 4 + 1024 + 256;
 static_assert(kFwSmem <= 232448, "shared memory budget");
@@ -1068,8 +1068,10 @@ conv3x3_valid_fwd32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             const int r = t / p.cv_tpr, w0 = (t % p.cv_tpr) * kBlockM;
             mbar_wait(tmem_full_bar + 8 * as, (it >> 1) & 1u);
             tc_fence_after();
+            // one 64-column chunk per tile: the two warps of a TMEM lane quadrant take alternate TILES, so the epilogues of
+            // both accumulator stages run concurrently (the tile loop is epilogue-paced: 18 short MMAs per tile)
             staged_tile_epilogue<64, false, false>(p, &tmC, tmem_base + ((uint32_t)(q * 32) << 16) + as * 64, w0 + q * 32, 0,
-                                                   lane, half, stg0, buf, tmem_empty_bar + 8 * as, stat_smem,
+                                                   lane, half ^ (int)(it & 1u), stg0, buf, tmem_empty_bar + 8 * as, stat_smem,
                                                    use_smem_stats, p.cv_rlimit, r);
         }
         if (lane == 0) tma_wait_group_all();
@@ -1185,7 +1187,7 @@ constexpr int kDgRowBytes = 17 * 1024;                  // 130 x 128 B rounded u
 constexpr int kDgStageBytes = 3 * kDgRowBytes;
 constexpr int kDgStages = 3;
 constexpr int kDgBTapBytes = 32 * 128;                  // [32 input channels x 64 output channels] bf16, K-major
-constexpr int kDgThreads = 192;                         // producer, issuer, 4 epilogue warps
+constexpr int kDgThreads = 320;                         // producer, issuer, 8 epilogue warps (two per TMEM lane quadrant)
 constexpr int kDgSmem = kDgStages * kDgStageBytes + 9 * kDgBTapBytes + 1024 + 256;
 static_assert(kDgSmem <= 232448, "shared memory budget");
 
@@ -1216,7 +1218,7 @@ conv3x3_valid_dgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
         for (int s = 0; s < kDgStages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + 8 * s, 1); mbar_init(tmem_empty_bar + 8 * s, 4); }
-        mbar_init(b_bar, 1);
+        mbar_init(b_bar, 1);                                  // (accumulator stage `as` is drained by the 4 warps of one half)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -1277,9 +1279,11 @@ conv3x3_valid_dgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         }
     } else {
         const int q = warp & 3;                              // TMEM lane quadrant of this warp
+        const uint32_t half = (uint32_t)(warp - 2) >> 2;     // warps 2..5 drain the even tiles, 6..9 the odd ones
         uint32_t it = 0;
         for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
             const uint32_t as = it & 1u;
+            if (as != half) continue;
             const int r = t / p.tpr, w = (t % p.tpr) * kBlockM + q * 32 + lane;
             mbar_wait(tmem_full_bar + 8 * as, (it >> 1) & 1u);
             tc_fence_after();
