@@ -166,4 +166,10 @@ static inline void pick_cvb(int CV, F&& f) {
     else f(std::integral_constant<int, 4>{});
 }
 
+// BatchNormalization finalize operands folded into a reading depthwise kernel (dlv3p_dwconv3x3_bn_fwd)
+struct DwBnFold {
+    const float* sums; const float* gamma; const float* beta; float* moving_mean; float* moving_var;
+    float* scale; float* shift; float* mean; float* invstd;
+    double count; float eps, momentum; int updates;
+};
 }  // namespace dlv3p

@@ -20,7 +20,8 @@ int launch_dw_conv_tma(const __nv_bfloat16* in, const float* w, __nv_bfloat16* o
                        int Hout, int Wout, int pad_t, int pad_l, int flip, int in_act, const __nv_bfloat16* mask_src,
                        const float* m_scale, const float* m_shift, int m_act, const __nv_bfloat16* addend,
                        cudaStream_t st, const float* in_scale = nullptr, const float* in_shift = nullptr,
-                       const float* bn_mean = nullptr, const float* bn_invstd = nullptr, float* bn_red = nullptr);
+                       const float* bn_mean = nullptr, const float* bn_invstd = nullptr, float* bn_red = nullptr,
+                       const DwBnFold* fold = nullptr);
 
 int launch_dw_wgrad_tma(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int N, int H, int W, int C, int Ho,
                         int Wo, int pad_t, int pad_l, int in_act, cudaStream_t st, const float* in_scale = nullptr,
@@ -488,6 +489,29 @@ extern "C" int dlv3p_dwconv3x3_dgrad(const void* dy, const float* w, void* dx, i
             in_scale, in_shift, in_act, (const T*)addend, total);
         return check_launch("dwconv3x3_dgrad");
     });
+    return 0;
+}
+
+extern "C" int dlv3p_dwconv3x3_bn_fwd(const void* x, const float* w, void* y, int N, int H, int W, int C, int pad_t,
+                                      int pad_l, int Ho, int Wo, const float* bn_sums, const float* gamma,
+                                      const float* beta, float* moving_mean, float* moving_var, double count,
+                                      float eps, float momentum, int updates, int in_act, float* scale, float* shift,
+                                      float* mean, float* invstd, int dtype, void* stream) {
+    int rc = check_dw_args(x, w, y, N, H, W, C, 1, 1, 1, Ho, Wo);
+    if (rc) return rc;
+    DLV3P_REQUIRE(bn_sums && scale && shift && mean && invstd && count > 0 && in_act != DLV3P_ACT_NONE, DLV3P_ERR_SHAPE,
+                  "dwconv3x3_bn_fwd: BN sums, output arrays and a clamping activation are required");
+    DLV3P_REQUIRE(updates == 0 || (moving_mean && moving_var), DLV3P_ERR_SHAPE, "dwconv3x3_bn_fwd: moving statistics required");
+    DLV3P_REQUIRE(dtype == DLV3P_BF16, DLV3P_ERR_DTYPE, "dwconv3x3_bn_fwd: bf16 only (use bn_finalize + dwconv3x3_fwd)");
+    DwBnFold f;
+    f.sums = bn_sums; f.gamma = gamma; f.beta = beta; f.moving_mean = moving_mean; f.moving_var = moving_var;
+    f.scale = scale; f.shift = shift; f.mean = mean; f.invstd = invstd; f.count = count; f.eps = eps;
+    f.momentum = momentum; f.updates = updates;
+    rc = launch_dw_conv_tma((const __nv_bfloat16*)x, w, (__nv_bfloat16*)y, N, H, W, C, Ho, Wo, pad_t, pad_l, 0, in_act,
+                            nullptr, nullptr, nullptr, 0, nullptr, (cudaStream_t)stream, nullptr, nullptr, nullptr,
+                            nullptr, nullptr, &f);
+    if (rc < 0) return rc;
+    DLV3P_REQUIRE(rc == 1, DLV3P_ERR_CUDA, "dwconv3x3_bn_fwd: the TMA path is unavailable");
     return 0;
 }
 

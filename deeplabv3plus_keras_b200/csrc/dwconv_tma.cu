@@ -29,6 +29,12 @@ struct DwTmaParams {
     const __nv_bfloat16* addend;
     const float* in_scale; const float* in_shift;             // IN_AFFINE: x := act(in_scale*x + in_shift) on load
     const float* bn_mean; const float* bn_invstd; float* bn_red;   // STATS: BN-backward reductions of the masked result
+    // IN_BN: the BatchNormalization of the producing layer is FINISHED here (dlv3p_bn_finalize folded into the reader):
+    // in_scale/in_shift are computed per CTA from the batch sums; the first CTA of every channel block publishes
+    // scale/shift/mean/invstd for the backward pass and updates the moving statistics
+    const float* f_sums; const float* f_gamma; const float* f_beta; float* f_mm; float* f_mv;
+    float* f_scale; float* f_shift; float* f_mean; float* f_invstd;
+    double f_count; float f_eps, f_momentum; int f_updates;
     int tiles_h, tiles_w, tiles_c;
     int spatial_tiles, ctas_per_cb;
 };
@@ -99,7 +105,7 @@ struct DwStageCfg {
     static constexpr int kAddOff = kDwStageBytes + (M_ACT != DLV3P_ACT_NONE ? kEpiBytes : 0);
 };
 
-template <int IN_ACT, int M_ACT, bool M_AFFINE, bool HAS_ADD, bool IN_AFFINE, bool STATS>
+template <int IN_ACT, int M_ACT, bool M_AFFINE, bool HAS_ADD, bool IN_AFFINE, bool STATS, bool IN_BN = false>
 __global__ void __launch_bounds__(kDwThreads, 1)
 dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_mask,
                    const __grid_constant__ CUtensorMap tm_add, const DwTmaParams p) {
@@ -166,7 +172,35 @@ dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
             const float4 v = __ldg(reinterpret_cast<const float4*>(p.w + tap * p.C + c0));
             wgt[a][0] = make_float2(v.x, v.y); wgt[a][1] = make_float2(v.z, v.w);
         }
-        if (IN_AFFINE) {
+        if (IN_AFFINE && IN_BN) {
+            // same arithmetic as bn_finalize_kernel (eltwise.cu): fp64 for E[x^2] - E[x]^2, TF fused-BN conventions
+            float sc4[4], sh4[4];
+            const bool publish = (blockIdx.x % p.ctas_per_cb == 0) && (col == 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c = c0 + k;
+                const double m = (double)__ldcg(p.f_sums + c) / p.f_count;
+                double var = (double)__ldcg(p.f_sums + p.C + c) / p.f_count - m * m;
+                if (var < 0.0) var = 0.0;
+                const float is = (float)(1.0 / sqrt(var + (double)p.f_eps));
+                const float g = p.f_gamma ? __ldg(p.f_gamma + c) : 1.f;
+                const float b = p.f_beta ? __ldg(p.f_beta + c) : 0.f;
+                sc4[k] = g * is;
+                sh4[k] = b - (float)m * sc4[k];
+                if (publish) {
+                    p.f_scale[c] = sc4[k]; p.f_shift[c] = sh4[k]; p.f_mean[c] = (float)m; p.f_invstd[c] = is;
+                    const double unbiased = p.f_count > 1.0 ? var * p.f_count / (p.f_count - 1.0) : var;
+                    float mm = p.f_mm[c], mv = p.f_mv[c];
+                    for (int u = 0; u < p.f_updates; ++u) {
+                        mm = p.f_momentum * mm + (1.f - p.f_momentum) * (float)m;
+                        mv = p.f_momentum * mv + (1.f - p.f_momentum) * (float)unbiased;
+                    }
+                    p.f_mm[c] = mm; p.f_mv[c] = mv;
+                }
+            }
+            isc[0] = make_float2(sc4[0], sc4[1]); isc[1] = make_float2(sc4[2], sc4[3]);
+            ish[0] = make_float2(sh4[0], sh4[1]); ish[1] = make_float2(sh4[2], sh4[3]);
+        } else if (IN_AFFINE) {
             const float4 a = __ldg(reinterpret_cast<const float4*>(p.in_scale + c0));
             const float4 b = __ldg(reinterpret_cast<const float4*>(p.in_shift + c0));
             isc[0] = make_float2(a.x, a.y); isc[1] = make_float2(a.z, a.w);
@@ -305,19 +339,19 @@ dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
     }
 }
 
-template <int IN_ACT, int M_ACT, bool M_AFFINE, bool HAS_ADD, bool IN_AFFINE = false, bool STATS = false>
+template <int IN_ACT, int M_ACT, bool M_AFFINE, bool HAS_ADD, bool IN_AFFINE = false, bool STATS = false, bool IN_BN = false>
 static int launch_dw_tma_inst(const CUtensorMap& tm, const CUtensorMap& tmm, const CUtensorMap& tma,
                               const DwTmaParams& p, int grid, cudaStream_t st) {
     using Cfg = DwStageCfg<M_ACT, HAS_ADD>;
     constexpr int smem = Cfg::kStages * Cfg::kStageBytes + 128 + 64;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(dw_conv_tma_kernel<IN_ACT, M_ACT, M_AFFINE, HAS_ADD, IN_AFFINE, STATS>,
+        cudaError_t e = cudaFuncSetAttribute(dw_conv_tma_kernel<IN_ACT, M_ACT, M_AFFINE, HAS_ADD, IN_AFFINE, STATS, IN_BN>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         DLV3P_REQUIRE(e == cudaSuccess, DLV3P_ERR_CUDA, "cudaFuncSetAttribute(dw tma smem=%d): %s", smem, cudaGetErrorString(e));
         configured = true;
     }
-    launch_pdl(dw_conv_tma_kernel<IN_ACT, M_ACT, M_AFFINE, HAS_ADD, IN_AFFINE, STATS>, dim3(grid), dim3(kDwThreads), smem, st, tm, tmm, tma, p);
+    launch_pdl(dw_conv_tma_kernel<IN_ACT, M_ACT, M_AFFINE, HAS_ADD, IN_AFFINE, STATS, IN_BN>, dim3(grid), dim3(kDwThreads), smem, st, tm, tmm, tma, p);
     return check_launch("dwconv3x3 (tma)");
 }
 
@@ -326,11 +360,11 @@ int launch_dw_conv_tma(const __nv_bfloat16* in, const float* w, __nv_bfloat16* o
                        int Hout, int Wout, int pad_t, int pad_l, int flip, int in_act, const __nv_bfloat16* mask_src,
                        const float* m_scale, const float* m_shift, int m_act, const __nv_bfloat16* addend,
                        cudaStream_t st, const float* in_scale, const float* in_shift, const float* bn_mean,
-                       const float* bn_invstd, float* bn_red) {
+                       const float* bn_invstd, float* bn_red, const DwBnFold* fold) {
     if (get_encode_fn() == nullptr) return 0;
     if (mask_src == nullptr) m_act = DLV3P_ACT_NONE;
     if (in_act != DLV3P_ACT_NONE && (m_act != DLV3P_ACT_NONE || addend != nullptr)) return 0;   // not a used combination
-    const bool in_aff = (in_scale != nullptr);
+    const bool in_aff = (in_scale != nullptr) || (fold != nullptr);
     if (in_aff && (in_act == DLV3P_ACT_NONE || (C & 3))) return 0;          // NaN padding needs a clamping activation
     const bool stats = (bn_red != nullptr);
     if (stats && (m_act == DLV3P_ACT_NONE || m_scale == nullptr || addend != nullptr || in_aff)) return 0;
@@ -351,6 +385,13 @@ int launch_dw_conv_tma(const __nv_bfloat16* in, const float* w, __nv_bfloat16* o
     p.flip = flip; p.in_act = in_act; p.w = w; p.out = out; p.mask_src = mask_src; p.m_scale = m_scale;
     p.m_shift = m_shift; p.m_act = m_act; p.addend = addend;
     p.in_scale = in_scale; p.in_shift = in_shift; p.bn_mean = bn_mean; p.bn_invstd = bn_invstd; p.bn_red = bn_red;
+    p.f_sums = nullptr;
+    if (fold != nullptr) {
+        p.f_sums = fold->sums; p.f_gamma = fold->gamma; p.f_beta = fold->beta; p.f_mm = fold->moving_mean;
+        p.f_mv = fold->moving_var; p.f_scale = fold->scale; p.f_shift = fold->shift; p.f_mean = fold->mean;
+        p.f_invstd = fold->invstd; p.f_count = fold->count; p.f_eps = fold->eps; p.f_momentum = fold->momentum;
+        p.f_updates = fold->updates;
+    }
     p.tiles_h = cdiv(Hout, kDwTH); p.tiles_w = cdiv(Wout, kDwTW); p.tiles_c = cdiv(C, kDwCB);
     const long long nt = (long long)N * p.tiles_h * p.tiles_w;
     if (nt > 0x7fffffffLL) return 0;
@@ -362,7 +403,10 @@ int launch_dw_conv_tma(const __nv_bfloat16* in, const float* w, __nv_bfloat16* o
     const bool aff = (m_scale != nullptr);
     const bool add = (addend != nullptr);
 #define DLV3P_DW(IA, MA, AF, AD) rc = launch_dw_tma_inst<IA, MA, AF, AD>(tm, tmm, tma, p, grid, st)
-    if (in_aff) {
+    if (in_aff && fold != nullptr) {
+        if (in_act == DLV3P_ACT_RELU) rc = launch_dw_tma_inst<1, 0, false, false, true, false, true>(tm, tmm, tma, p, grid, st);
+        else rc = launch_dw_tma_inst<2, 0, false, false, true, false, true>(tm, tmm, tma, p, grid, st);
+    } else if (in_aff) {
         if (in_act == DLV3P_ACT_RELU) rc = launch_dw_tma_inst<1, 0, false, false, true, false>(tm, tmm, tma, p, grid, st);
         else rc = launch_dw_tma_inst<2, 0, false, false, true, false>(tm, tmm, tma, p, grid, st);
     } else if (stats) {

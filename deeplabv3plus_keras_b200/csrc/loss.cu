@@ -255,7 +255,22 @@ upsample_softmax_cbloss_kernel(const float* __restrict__ zl, const int32_t* __re
 // shuffle), and the transposed-resize gradient is reduced separably through shared memory (over x, then over y) into
 // an (S+1)^2 x C accumulator that is flushed with one global RED per (corner, class).  Forward and backward share one
 // pass (`fwd_bwd`), so the softmax is evaluated once per pixel per step.
-template <int CMAX, bool FWD, bool BWD>
+// ex2 / lg2 without the denormal fix-up sequences of __expf / __logf (16 % of the kernel's issue slots were ISETP/BRA and
+// @p FMUL range handling, profiles/r1_tail_ncu.md); flushing denormal probabilities to zero is far below the loss's
+// epsilon of 1e-7
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_log(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y * 0.6931471805599453f;
+}
+
+// EXACT: C == CMAX, the class loops carry no `c < C` predicates
+template <int CMAX, bool FWD, bool BWD, bool EXACT>
 __global__ void __launch_bounds__(256)
 tail_pixel_kernel(const float* __restrict__ zl, const int32_t* __restrict__ labels, const float* __restrict__ pw,
                   const float* __restrict__ nw, float eps, int N, int H, int W, int C, int f, float gscale,
@@ -268,7 +283,8 @@ tail_pixel_kernel(const float* __restrict__ zl, const int32_t* __restrict__ labe
     float* G = patch + PS * PS * CS;                // [PS][PS][CS]   corner gradient accumulators
     float* spw = G + PS * PS * CS;                  // [32]
     float* snw = spw + 32;                          // [32]
-    float* D = snw + 32;                            // [256][CS]      per-pixel logit gradients
+    float* wtab = snw + 32;                         // [2][16]        lerp weights of the gradient reduction: 1-l, l
+    float* D = wtab + 32;                           // [256][CS]      per-pixel logit gradients
     float* R = D + 256 * CS;                        // [16][S][2][CS] x-reduced partials
 
     const int tid = threadIdx.x;
@@ -287,7 +303,11 @@ tail_pixel_kernel(const float* __restrict__ zl, const int32_t* __restrict__ labe
         patch[i] = (c < C) ? __ldg(zl + (((long long)n * H + yy) * W + xx) * C + c) : 0.f;
         if (BWD) G[i] = 0.f;
     }
-    if (tid < 32) { spw[tid] = tid < C ? __ldg(pw + tid) : 0.f; snw[tid] = tid < C ? __ldg(nw + tid) : 0.f; }
+    if (tid < 32) {
+        spw[tid] = tid < C ? __ldg(pw + tid) : 0.f; snw[tid] = tid < C ? __ldg(nw + tid) : 0.f;
+        const float l = ((float)(tid & 15) + 0.5f) / (float)f;
+        wtab[tid] = (tid & 16) ? l : 1.f - l;
+    }
     __syncthreads();
 
     const int py = tid >> 4, px = tid & 15;
@@ -308,7 +328,7 @@ tail_pixel_kernel(const float* __restrict__ zl, const int32_t* __restrict__ labe
         float m = -INFINITY;
 #pragma unroll
         for (int c = 0; c < CMAX; ++c) {
-            if (c < C) {
+            if (EXACT || c < C) {
                 const float top = p00[c] + (p01[c] - p00[c]) * lx;
                 const float bot = p10[c] + (p11[c] - p10[c]) * lx;
                 z[c] = top + (bot - top) * ly;
@@ -317,19 +337,22 @@ tail_pixel_kernel(const float* __restrict__ zl, const int32_t* __restrict__ labe
         }
         float s = 0.f;
 #pragma unroll
-        for (int c = 0; c < CMAX; ++c) { z[c] = (c < C) ? __expf(z[c] - m) : 0.f; s += z[c]; }
+        for (int c = 0; c < CMAX; ++c) {
+            z[c] = (EXACT || c < C) ? fast_exp2((z[c] - m) * 1.4426950408889634f) : 0.f;
+            s += z[c];
+        }
         const float inv = __fdividef(1.f, s);
         const int lab = __ldg(labels + ((long long)n * Ho + yo) * Wo + xo);
         float dot = 0.f;
 #pragma unroll
         for (int c = 0; c < CMAX; ++c) {
-            if (c < C) {
+            if (EXACT || c < C) {
                 const float p = z[c] * inv;
                 const bool hit = (c == lab);
                 if (FWD) {
                     // -(pw*y*log(p+eps) + nw*(1-y)*log(1-p+eps)), y one-hot
                     const float arg = hit ? (p + eps) : (1.f - p + eps);
-                    loss_acc -= (hit ? spw[c] : snw[c]) * __logf(arg);
+                    loss_acc -= (hit ? spw[c] : snw[c]) * fast_log(arg);
                 }
                 if (BWD) {
                     const float g = hit ? -__fdividef(spw[c], p + eps) : __fdividef(snw[c], 1.f - p + eps);
@@ -341,7 +364,7 @@ tail_pixel_kernel(const float* __restrict__ zl, const int32_t* __restrict__ labe
         }
         if (BWD) {
 #pragma unroll
-            for (int c = 0; c < CMAX; ++c) d[c] = (c < C) ? gscale * z[c] * (d[c] - dot) : 0.f;
+            for (int c = 0; c < CMAX; ++c) d[c] = (EXACT || c < C) ? gscale * z[c] * (d[c] - dot) : 0.f;
         }
     } else if (BWD) {
 #pragma unroll
@@ -362,10 +385,9 @@ tail_pixel_kernel(const float* __restrict__ zl, const int32_t* __restrict__ labe
         const int ssx = r % S;
         const int ppy = r / S;
         float acc = 0.f;
-        for (int j = 0; j < f; ++j) {
-            const float l = ((float)j + 0.5f) * inv_f;
-            acc = fmaf(D[(ppy * 16 + ssx * f + j) * CS + c], kx ? l : 1.f - l, acc);
-        }
+        const float* dp = D + (ppy * 16 + ssx * f) * CS + c;
+        const float* wp = wtab + kx * 16;
+        for (int j = 0; j < f; ++j) acc = fmaf(dp[j * CS], wp[j], acc);
         R[((ppy * S + ssx) * 2 + kx) * CS + c] = acc;
     }
     __syncthreads();
@@ -379,10 +401,9 @@ tail_pixel_kernel(const float* __restrict__ zl, const int32_t* __restrict__ labe
         const int ky = r & 1; r >>= 1;
         const int ssy = r;
         float acc = 0.f;
-        for (int j = 0; j < f; ++j) {
-            const float l = ((float)j + 0.5f) * inv_f;
-            acc = fmaf(R[(((ssy * f + j) * S + ssx) * 2 + kx) * CS + c], ky ? l : 1.f - l, acc);
-        }
+        const float* rp = R + ((ssy * f * S + ssx) * 2 + kx) * CS + c;
+        const float* wp = wtab + ky * 16;
+        for (int j = 0; j < f; ++j) acc = fmaf(rp[j * S * 2 * CS], wp[j], acc);
         atomicAdd(&G[((ssy + ky) * PS + ssx + kx) * CS + c], acc);
     }
     __syncthreads();
@@ -408,16 +429,22 @@ static int launch_tail_pixel(const float* zl, const int32_t* labels, const float
 #define DLV3P_TAIL(CM)                                                                                             \
     do {                                                                                                           \
         constexpr int CS = (CM) | 1;                                                                               \
-        const int smem = (2 * PS * PS * CS + 64 + (BWD ? 256 * CS + 16 * S * 2 * CS : 0)) * 4;                     \
+        const int smem = (2 * PS * PS * CS + 96 + (BWD ? 256 * CS + 16 * S * 2 * CS : 0)) * 4;                     \
         static int configured = 0;                                                                                 \
         if (smem > configured) {                                                                                   \
-            cudaError_t e = cudaFuncSetAttribute(tail_pixel_kernel<CM, FWD, BWD>,                                  \
+            cudaError_t e = cudaFuncSetAttribute(tail_pixel_kernel<CM, FWD, BWD, false>,                           \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem);               \
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_pixel_kernel<CM, FWD, BWD, true>,                  \
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem);               \
             DLV3P_REQUIRE(e == cudaSuccess, DLV3P_ERR_CUDA, "fused tail smem=%d: %s", smem, cudaGetErrorString(e)); \
             configured = smem;                                                                                     \
         }                                                                                                          \
-        tail_pixel_kernel<CM, FWD, BWD><<<(int)blocks, 256, smem, st>>>(zl, labels, pw, nw, eps, N, H, W, C, f,    \
-                                                                        gscale, loss_sum, dzl, nby, nbx);          \
+        if (C == (CM))                                                                                             \
+            tail_pixel_kernel<CM, FWD, BWD, true><<<(int)blocks, 256, smem, st>>>(zl, labels, pw, nw, eps, N, H, W, C, f, \
+                                                                                  gscale, loss_sum, dzl, nby, nbx); \
+        else                                                                                                       \
+            tail_pixel_kernel<CM, FWD, BWD, false><<<(int)blocks, 256, smem, st>>>(zl, labels, pw, nw, eps, N, H, W, C, f, \
+                                                                                   gscale, loss_sum, dzl, nby, nbx); \
     } while (0)
     if (C <= 8) DLV3P_TAIL(8);
     else if (C <= 16) DLV3P_TAIL(16);

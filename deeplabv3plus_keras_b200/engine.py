@@ -554,8 +554,15 @@ class Plan:
             if is_dw and dw_out is None:
                 # inference depthwise+BN: conv into `out`, then fold BN in place
                 dw_out = out.buf
-            self.fwd.append(lambda: ops.dwconv3x3_fwd(xb, dw_w, stride, dil, in_scale=in_sc, in_shift=in_sh,
-                                                      in_act=in_act, out=dw_out, pad=pad4))
+            fold = getattr(x, "bn_fold", None)
+            if fold is not None:
+                self.fwd.append(lambda: ops.dwconv3x3_bn_fwd(
+                    xb, dw_w, fold["sums"](), fold["gamma"], fold["beta"], fold["mm"], fold["mv"], fold["count"],
+                    fold["eps"], fold["momentum"], fold["updates"], in_act, in_sc, in_sh, x.bn_mean, x.bn_invstd,
+                    out=dw_out, pad=pad4))
+            else:
+                self.fwd.append(lambda: ops.dwconv3x3_fwd(xb, dw_w, stride, dil, in_scale=in_sc, in_shift=in_sh,
+                                                          in_act=in_act, out=dw_out, pad=pad4))
             launches_f += 1
             A, lda = d, Cin
         elif k == 1 and stride == 1:
@@ -603,7 +610,12 @@ class Plan:
                 self.fwd.append(lambda: ops.bn_stats(y, Mo, Cout, stat()))
                 launches_f += 1
             upd = bn_node.calls
-            if virt:
+            if virt and (self.bf16 or FORCE_BNRED):
+                # statistics -> scale/shift (+ moving statistics) happen inside the reader's forward kernel
+                # (dlv3p_dwconv3x3_bn_fwd): nothing to launch here
+                out.bn_fold = dict(sums=stat, gamma=gamma, beta=beta, mm=mm, mv=mv, count=Mo, eps=bn.epsilon,
+                                   momentum=bn.momentum, updates=upd)
+            elif virt:
                 # statistics -> scale/shift (+ moving statistics); the BN+ReLU map itself runs inside the reader
                 for r in range(upd):
                     self.fwd.append(lambda r=r: ops.bn_finalize(stat(), gamma, beta, mm, mv, Cout, Mo, bn.epsilon,
@@ -1218,6 +1230,7 @@ class _BnActValue(Value):
         super().__init__(shape, dtype, None, name + "/bn_act")
         self.pre_act = act
         self.red_done = False
+        self.bn_fold = None                 # BN finalize operands when the reader's forward kernel finishes the BN
 
     def attach(self, y, scale, shift, mean, invstd, red_slot):
         self.buf, self.pre_scale, self.pre_shift = y, scale, shift

@@ -93,6 +93,20 @@ def dwconv3x3_dgrad(dy: Tensor, w: Tensor, x_shape, stride=1, dil=(1, 1), paddin
     return out
 
 
+def dwconv3x3_bn_fwd(x: Tensor, w: Tensor, bn_sums, gamma, beta, moving_mean, moving_var, count, eps, momentum,
+                     updates: int, in_act: int, scale, shift, mean, invstd, out: Optional[Tensor] = None, pad=None):
+    """dwconv3x3_fwd on act(BN_train(x)) with bn_finalize folded in (stride 1, dilation 1, bf16)."""
+    _chk(x, "x")
+    N, H, W, Cc = x.shape
+    ho, wo, pt, pl = pad if pad is not None else conv_geometry(H, W, 3, 1, (1, 1), "same")
+    if out is None:
+        out = torch.empty((N, ho, wo, Cc), dtype=x.dtype, device=x.device)
+    call("dlv3p_dwconv3x3_bn_fwd", _p(x), _p(w), _p(out), N, H, W, Cc, pt, pl, ho, wo, _p(bn_sums), _p(gamma), _p(beta),
+         _p(moving_mean), _p(moving_var), float(count), eps, momentum, updates, in_act, _p(scale), _p(shift), _p(mean),
+         _p(invstd), _dt(x), _stream())
+    return out
+
+
 def dwconv3x3_dgrad_bnred(dy: Tensor, w: Tensor, x_shape, x_pre: Tensor, in_scale: Tensor, in_shift: Tensor, in_act: int,
                           bn_mean: Tensor, bn_invstd: Tensor, bn_red: Tensor, out: Optional[Tensor] = None, pad=None):
     """dwconv3x3_dgrad (stride 1, dilation 1, bf16) + the BN-backward reductions of x_pre's layer into bn_red[2C]."""

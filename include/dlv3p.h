@@ -64,6 +64,15 @@ int dlv3p_dwconv3x3_dgrad(const void* dy, const float* w, void* dx, int N, int H
                           int dil_h, int dil_w, int pad_t, int pad_l, int Ho, int Wo, const void* x_pre,
                           const float* in_scale, const float* in_shift, int in_act, const void* addend, int dtype,
                           void* stream);
+/* dlv3p_dwconv3x3_fwd (stride 1, dilation 1, bf16) whose input is act(BatchNormalization(x)) of the producing layer in
+ * TRAINING mode, with dlv3p_bn_finalize folded in: every CTA derives scale/shift of its channels from the batch sums
+ * (bn_sums[0..C) = sum x, [C..2C) = sum x^2 over `count` samples, as written by dlv3p_gemm_bf16's col_stats); the first
+ * CTA of each channel block publishes scale/shift/mean/invstd (read by the backward kernels) and applies `updates`
+ * momentum updates to the moving statistics (tf.raw_ops.FusedBatchNormV3 conventions, see dlv3p_bn_finalize). */
+int dlv3p_dwconv3x3_bn_fwd(const void* x, const float* w, void* y, int N, int H, int W, int C, int pad_t, int pad_l,
+                           int Ho, int Wo, const float* bn_sums, const float* gamma, const float* beta,
+                           float* moving_mean, float* moving_var, double count, float eps, float momentum, int updates,
+                           int in_act, float* scale, float* shift, float* mean, float* invstd, int dtype, void* stream);
 /* dlv3p_dwconv3x3_dgrad (stride 1, dilation 1, bf16, no addend) that ALSO produces the BatchNormalization-backward
  * reductions of the layer whose raw conv output is x_pre (tf.raw_ops.FusedBatchNormGradV3's two sums, i.e. what
  * dlv3p_bn_bwd_reduce computes with act = NONE from the dx written here):

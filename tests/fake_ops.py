@@ -85,6 +85,15 @@ def dwconv3x3_dgrad(dy, w, x_shape, stride=1, dil=(1, 1), padding="same", x_pre=
     return out
 
 
+def dwconv3x3_bn_fwd(x, w, bn_sums, gamma, beta, moving_mean, moving_var, count, eps, momentum, updates, in_act, scale,
+                     shift, mean, invstd, out=None, pad=None):
+    Cc = x.shape[3]
+    for u in range(max(updates, 1)):
+        bn_finalize(bn_sums, gamma, beta, moving_mean, moving_var, Cc, count, eps, momentum, scale, shift, mean, invstd,
+                    update_moving=u < updates)
+    return dwconv3x3_fwd(x, w, 1, (1, 1), in_scale=scale, in_shift=shift, in_act=in_act, out=out, pad=pad)
+
+
 def dwconv3x3_dgrad_bnred(dy, w, x_shape, x_pre, in_scale, in_shift, in_act, bn_mean, bn_invstd, bn_red, out=None,
                           pad=None):
     if out is None:

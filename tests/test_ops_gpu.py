@@ -207,6 +207,42 @@ def test_conv3x3_valid_unsupported_shapes():
                               torch.zeros((3, 3, 16, 64), device=DEV), 64)                       # 3*Cin <= 64
 
 
+@pytest.mark.parametrize("case", [(2, 17, 19, 64), (2, 30, 31, 736), (1, 33, 70, 128)])
+@pytest.mark.parametrize("updates", [1, 2])
+def test_dwconv3x3_bn_fwd_equals_finalize_plus_conv(case, updates):
+    """Depthwise forward with the producing layer's training-mode BatchNormalization finished inside the kernel
+    (dlv3p_bn_finalize folded in) == dlv3p_bn_finalize followed by dlv3p_dwconv3x3_fwd with in_scale/in_shift: same
+    output, same published scale/shift/mean/invstd, same moving statistics."""
+    o = ops()
+    N, H, W, C = case
+    bf = torch.bfloat16
+    y = (rnd((N, H, W, C), bf, 1, 1.5) + 0.3).to(bf).to(DEV)
+    w = rnd((3, 3, C), torch.float32, 2, 0.3).to(DEV)
+    gamma = (rnd((C,), torch.float32, 3, 0.2) + 1.0).to(DEV)
+    beta = rnd((C,), torch.float32, 4, 0.3).to(DEV)
+    M = N * H * W
+    sums = torch.zeros(2 * C, dtype=torch.float32, device=DEV)
+    o.bn_stats(y, M, C, sums)
+
+    def fresh():
+        return (torch.full((C,), 0.25, device=DEV), torch.full((C,), 2.0, device=DEV),
+                *(torch.empty(C, device=DEV) for _ in range(4)))
+    mm_a, mv_a, sc_a, sh_a, mu_a, is_a = fresh()
+    for u in range(updates):
+        o.bn_finalize(sums, gamma, beta, mm_a, mv_a, C, M, 1e-3, 0.99, sc_a, sh_a, mu_a, is_a, True)
+    want = o.dwconv3x3_fwd(y, w, 1, (1, 1), in_scale=sc_a, in_shift=sh_a, in_act=o.ACT_RELU)
+    mm_b, mv_b, sc_b, sh_b, mu_b, is_b = fresh()
+    got = o.dwconv3x3_bn_fwd(y, w, sums, gamma, beta, mm_b, mv_b, M, 1e-3, 0.99, updates, o.ACT_RELU, sc_b, sh_b, mu_b, is_b)
+    torch.cuda.synchronize()
+    # same formulas in two kernels: equal up to fp32 contraction choices of the compiler
+    for name, a, b in (("scale", sc_a, sc_b), ("shift", sh_a, sh_b), ("mean", mu_a, mu_b), ("invstd", is_a, is_b),
+                       ("moving_mean", mm_a, mm_b), ("moving_var", mv_a, mv_b)):
+        check("bn_fwd " + name, b, a, 2e-6, 2e-6)
+    # outputs: bf16 roundings of fp32 values that differ by a few ulp(fp32) can land one bf16 ulp apart
+    check("bn_fwd out", got, want, 1e-2, 1e-2)
+    assert (got.float() != want.float()).float().mean().item() < 1e-2
+
+
 GEMM_CASES = [
     # M, N, K
     (128, 32, 64),
