@@ -42,9 +42,9 @@ _CHANNEL_AXES = {"depthwise_kernel": (2,), "pointwise_kernel": (2, 3), "kernel":
                  "beta": (0,), "moving_mean": (0,), "moving_variance": (0,)}
 
 
-def _phys_shape(name: str, shape) -> Tuple[int, ...]:
+def _phys_shape(name: str, shape, phys=phys_channels) -> Tuple[int, ...]:
     axes = _CHANNEL_AXES.get(name, ())
-    return tuple(phys_channels(d) if i in axes else d for i, d in enumerate(shape))
+    return tuple(phys(d) if i in axes else d for i, d in enumerate(shape))
 
 
 class Value:
@@ -124,8 +124,9 @@ class ParamStore:
     """Flat fp32 arenas: trainable weights (L2-regularised kernels first), their gradients and Adam moments, and
     the non-trainable BatchNormalization moving statistics."""
 
-    def __init__(self, layers_in_order: List[Layer], device):
+    def __init__(self, layers_in_order: List[Layer], device, phys=phys_channels):
         self.device = device
+        self.phys = phys
         self.entries: Dict[Tuple[int, str], Tuple[str, int, Tuple]] = {}
         reg, plain, frozen = [], [], []
         for l in layers_in_order:
@@ -153,7 +154,7 @@ class ParamStore:
         def lay(items, kind, start=0):
             off = start
             for l, n, w in items:
-                pshape = _phys_shape(n, w.shape)       # physical (channel-padded) layout, see phys_channels
+                pshape = _phys_shape(n, w.shape, self.phys)       # physical (channel-padded) layout, see phys_channels
                 self.entries[(id(l), n)] = (kind, off, pshape)
                 off += _ceil8(int(np.prod(pshape)))    # keep every parameter 32-byte aligned
             return off
@@ -246,8 +247,15 @@ class Plan:
         self.nodes, in_ids, out_ids = flatten(model)
         if len(in_ids) != 1 or len(out_ids) != 1:
             raise ValueError("Plan supports single-input single-output models (the DeepLabV3+ graph)")
+        # channel counts that reach a Concatenate keep their logical pitch: a padded operand would interleave pad
+        # channels into the concatenated axis and the consumer's kernel rows would no longer be a plain zero-extension
+        shape_of = {n.output: n.shape for n in self.nodes}
+        no_pad = {shape_of[i][-1] for n in self.nodes if isinstance(n.layer, L.Concatenate) for i in n.inputs
+                  if i in shape_of}
+        no_pad |= {n.shape[-1] for n in self.nodes if isinstance(n.layer, L.Concatenate)}
+        self.phys = lambda c: c if c in no_pad else phys_channels(c)
         weight_layers = [l for l in model.flat_layers() if l._weights]
-        self.params = ParamStore(weight_layers, self.device)
+        self.params = ParamStore(weight_layers, self.device, self.phys)
         self.params.upload()
 
         self.values: Dict[int, Value] = {}
@@ -456,7 +464,7 @@ class Plan:
         else:
             Ho, Wo, pt, pl = ops.conv_geometry(H, W, k, stride, dil, lay.padding)
         Mo = N * Ho * Wo
-        Cout = Cin if is_dw else phys_channels(lay.filters)
+        Cout = Cin if is_dw else self.phys(lay.filters)
         Cout_log = x.clog if is_dw else lay.filters
         out_shape = (N, Ho, Wo, Cout)
         assert tuple(m["conv"].shape[1:]) == (Ho, Wo, Cout_log), (lay.name, m["conv"].shape, out_shape)

@@ -97,6 +97,32 @@ def test_bn_relu_fused_into_depthwise_schedule(cpu_engine, monkeypatch, fuse):
         assert np.abs(ga[k] - gb[k]).max() <= 2e-3 * scale, k
 
 
+def test_channel_pitch_padding_is_invisible_and_skips_concatenated_widths(cpu_engine):
+    """728-channel tensors live on a 736-channel pitch (pad parameters zero, Keras-shaped views outside); a width that
+    reaches a Concatenate (ASPP reduction_size = 72 here) keeps its logical pitch."""
+    conf = util.make_conf(width=72, base="xception", output_stride=16, image_size=65)
+    ss = util.build(conf)
+    util.randomize_weights(ss.model)
+    plan = cpu_engine.Plan(ss.model, 2, training=True)
+    by_name = {v.name: v for v in plan.values.values() if hasattr(v, "name")}
+    assert by_name["block5_sepconv1/bn_act"].shape[3] == 736 and by_name["block5_sepconv1/bn_act"].clog == 728
+    assert all(v.shape[3] == v.clog for v in plan.values.values() if hasattr(v, "clog") and v.clog == 72)
+    lay = [l for l in ss.model.flat_layers() if l.name == "block5_sepconv2"][0]
+    assert tuple(plan.params.view(lay, "pointwise_kernel").shape) == (1, 1, 736, 736)
+    assert tuple(plan.params.logical(lay, "pointwise_kernel").shape) == (1, 1, 728, 728)
+    assert float(plan.params.view(lay, "pointwise_kernel")[0, 0, 728:, :].abs().max()) == 0.0
+    x, y = util.synthetic_batch(conf, 2, plan.out_shape[1:3])
+    plan.set_loss(PW, NW)
+    plan.load_batch(x, y)
+    plan.step_fwd_bwd()
+    g = plan.params.view(lay, "pointwise_kernel", grad=True)
+    assert float(g[0, 0, 728:, :].abs().max()) == 0.0 and float(g[0, 0, :, 728:].abs().max()) == 0.0
+    assert float(g.abs().max()) > 0.0
+    assert plan.gradients()["block5_sepconv2/pointwise_kernel"].shape == (1, 1, 728, 728)
+    assert plan.params.num_params == sum(int(np.prod(w.shape)) for l in ss.model.flat_layers()
+                                         for n, w in l._weights.items() if l._trainable[n])
+
+
 def test_implicit_conv_schedule(cpu_engine, monkeypatch):
     """Xception block1_conv2 (3x3 VALID stride 1, 32 -> 64): the implicit-GEMM schedule (no im2col / col2im, prepared
     wk / wd filter matrices) must reproduce the im2col + GEMM schedule."""
