@@ -43,6 +43,13 @@ class Trainer:
         self.host_loss = torch.zeros(2, dtype=torch.float32).pin_memory()
         self.dev_x32 = torch.empty(p.x_in.shape, dtype=torch.float32, device=p.device) \
             if p.x_in.buf.dtype != torch.float32 else None
+        # input double buffering (prefetch): the H2D copy of batch t+1 runs on a copy stream into staging buffers while
+        # step t computes; the step then starts with a device-side cast/copy (~15 us) out of the staging buffers
+        self.copy_stream = torch.cuda.Stream()
+        self.stage_x = torch.empty(p.x_in.shape, dtype=torch.float32, device=p.device)
+        self.stage_y = torch.empty(tuple(p.labels.shape), dtype=torch.int32, device=p.device)
+        self._staged = None                # event: staging buffers hold a complete batch
+        self._stage_free = None            # event: the training stream has consumed the staging buffers
         self._build(buckets if self.world > 1 else 1)
 
     # ------------------------------------------------------------------------------------------------------
@@ -108,6 +115,31 @@ class Trainer:
                 p.x_in.buf.copy_(images, non_blocking=True)
             p.labels.copy_(labels, non_blocking=True)
 
+    def prefetch(self, images: torch.Tensor, labels: torch.Tensor):
+        """Start the H2D copy of the NEXT batch (pinned host tensors) on the copy stream; returns immediately.  The next
+        train_step_e2e() call consumes it.  This is the input double buffering every training loop does (the
+        reference's Keras enqueuer prepares the next batches on worker threads, ss.py:1063-1073)."""
+        if self._stage_free is not None:
+            self.copy_stream.wait_event(self._stage_free)
+        with torch.cuda.stream(self.copy_stream):
+            self.stage_x.copy_(images, non_blocking=True)
+            self.stage_y.copy_(labels, non_blocking=True)
+            self._staged = torch.cuda.Event()
+            self._staged.record(self.copy_stream)
+
+    def _consume_staged(self):
+        p = self.plan
+        self.stream.wait_event(self._staged)
+        with torch.cuda.stream(self.stream):
+            if p.x_in.buf.dtype != torch.float32:
+                ops.cast(self.stage_x, p.x_in.buf)
+            else:
+                p.x_in.buf.copy_(self.stage_x, non_blocking=True)
+            p.labels.copy_(self.stage_y, non_blocking=True)
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record(self.stream)
+        self._staged = None
+
     def step(self, optimizer_step: bool = True):
         """One training step on the batch resident in the plan's input buffers."""
         p = self.plan
@@ -155,8 +187,17 @@ class Trainer:
         P = p.N * p.out_shape[1] * p.out_shape[2]
         return float(self.host_loss[0]) / P + p.params.l2 * float(self.host_loss[1])
 
-    def train_step_e2e(self, images: torch.Tensor, labels: torch.Tensor) -> float:
-        """The user-facing call: pinned host batch in, loss out (H2D + step + D2H)."""
-        self.stage_inputs(images, labels)
+    def train_step_e2e(self, images: Optional[torch.Tensor], labels: Optional[torch.Tensor],
+                       prefetch_next=None) -> float:
+        """The user-facing call: pinned host batch in, its loss out (H2D + step + D2H).
+        `prefetch_next=(images, labels)`: the batch of the NEXT call; its H2D copy is started behind this step's launch
+        and overlaps the step's compute.  A call that follows one with `prefetch_next` trains on that prefetched batch
+        (pass the same tensors, or None)."""
+        if self._staged is not None:
+            self._consume_staged()                     # prefetched by the previous call
+        else:
+            self.stage_inputs(images, labels)
         self.step()
+        if prefetch_next is not None:
+            self.prefetch(*prefetch_next)
         return self.read_loss()
