@@ -135,6 +135,19 @@ dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // filter taps of this thread's 4 channels as packed pairs (flipped for the input gradient).  Loaded BEFORE the
+    // programmatic-dependency wait: the fp32 master weights only change in the optimizer step, whose kernels do not
+    // trigger dependent launches, so this L2 round trip overlaps the previous kernel's tail
+    float2 wgt[9][2];
+    const bool ch_ok = c0 < p.C;
+    if (ch_ok) {
+#pragma unroll
+        for (int a = 0; a < 9; ++a) {
+            const int tap = p.flip ? (8 - a) : a;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p.w + tap * p.C + c0));
+            wgt[a][0] = make_float2(v.x, v.y); wgt[a][1] = make_float2(v.z, v.w);
+        }
+    }
     pdl_wait();
 
     auto decode = [&](int tile, int& n, int& th, int& tw) {
@@ -159,19 +172,10 @@ dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
             if (tile + a * gstride < p.spatial_tiles) issue(tile + a * gstride, a);
     }
 
-    // filter taps of this thread's 4 channels as packed pairs (flipped for the input gradient)
-    float2 wgt[9][2];
     float msc[4] = {1.f, 1.f, 1.f, 1.f}, msh[4] = {0.f, 0.f, 0.f, 0.f};
     float2 isc[2], ish[2];
     float bs1[4] = {0.f, 0.f, 0.f, 0.f}, bs2[4] = {0.f, 0.f, 0.f, 0.f};
-    const bool ch_ok = c0 < p.C;
     if (ch_ok) {
-#pragma unroll
-        for (int a = 0; a < 9; ++a) {
-            const int tap = p.flip ? (8 - a) : a;
-            const float4 v = __ldg(reinterpret_cast<const float4*>(p.w + tap * p.C + c0));
-            wgt[a][0] = make_float2(v.x, v.y); wgt[a][1] = make_float2(v.z, v.w);
-        }
         if (IN_AFFINE && IN_BN) {
             // same arithmetic as bn_finalize_kernel (eltwise.cu): fp64 for E[x^2] - E[x]^2, TF fused-BN conventions
             float sc4[4], sh4[4];
