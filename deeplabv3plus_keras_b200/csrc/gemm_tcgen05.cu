@@ -40,6 +40,14 @@ constexpr int kEpiStageFloats = 32 * 33;          // fallback path, per epilogue
 constexpr int kEpiBufBytes = 32 * 128;            // TMA-store path: one staging tile = 32 rows x 128 B
 constexpr int kEpiBytes = kEpiWarps * 2 * kEpiBufBytes;   // per epilogue warp 2 buffers (also holds the fallback transposes)
 constexpr int kMaxStatCols = 1024;                // per-CTA smem accumulators for the BN column statistics
+// The statistics region holds either ONE [2][kMaxStatCols] table updated with shared-memory atomics (mode 1) or, when the
+// columns fit, one PRIVATE [2][SC] table per TMEM lane quadrant (mode 2): the same lane always owns the same column of
+// its quadrant's table, so the per-tile update is a plain load-add-store.  atomicAdd(float) on shared memory has no
+// native instruction (SASS: ATOMS.CAST.SPIN loops behind a generic-address dispatch); four quadrant warps hammering the
+// same columns made the statistics the slowest part of the short-K GEMMs' epilogue.
+constexpr int kStatFloats1 = 2 * kMaxStatCols;    // 1-CTA kernels: 8 KB  -> 4 private tables of 256 columns
+constexpr int kStatFloats2 = 8 * kMaxStatCols;    // 2-CTA kernel: 32 KB -> 4 private tables of 1024 columns
+__host__ __device__ constexpr int stat_capacity(int region_floats, int slots) { return region_floats / (2 * slots); }
 static_assert(kEpiBytes >= 4 * kEpiStageFloats * 4, "staging area must hold the fallback transposes");
 template <int BLOCK_N> struct GemmCfg {
     static constexpr int kStageBytes = kBlockM * kBlockK * 2 + BLOCK_N * kBlockK * 2;
@@ -131,8 +139,8 @@ __device__ __forceinline__ void decode_work(const GemmParams& p, int w, int& row
 template <int BLOCK_N, bool WGRAD, bool REMOTE>
 __device__ __forceinline__ void staged_tile_epilogue(const GemmParams& p, const CUtensorMap* tmC, uint32_t acc_tmem,
                                                      int rbase, int col0, int lane, int half, uint32_t stg0, uint32_t& buf,
-                                                     uint32_t empty_bar, float* stat_smem, bool use_smem_stats,
-                                                     int row_limit, int c2) {
+                                                     uint32_t empty_bar, float* stat_smem, int stat_mode, int stat_slot,
+                                                     int stat_cap, int row_limit, int c2) {
     constexpr int CW = WGRAD ? 32 : 64;                 // columns per staging tile (128-byte rows)
     const uint32_t lane_row = (uint32_t)lane * 128u;
     const uint32_t sw = (uint32_t)(lane & 7);
@@ -231,7 +239,11 @@ __device__ __forceinline__ void staged_tile_epilogue(const GemmParams& p, const 
                 s1b += b; s2b = fmaf(b, b, s2b);
             }
             const int col = n_base + 2 * lane;
-            if (use_smem_stats) {
+            if (stat_mode == 2) {
+                float* mine = stat_smem + stat_slot * 2 * stat_cap;          // this quadrant's private table
+                if (col < p.N) { mine[col] += s1a; mine[stat_cap + col] += s2a; }
+                if (col + 1 < p.N) { mine[col + 1] += s1b; mine[stat_cap + col + 1] += s2b; }
+            } else if (stat_mode == 1) {
                 if (col < p.N) { atomicAdd(stat_smem + col, s1a); atomicAdd(stat_smem + kMaxStatCols + col, s2a); }
                 if (col + 1 < p.N) { atomicAdd(stat_smem + col + 1, s1b); atomicAdd(stat_smem + kMaxStatCols + col + 1, s2b); }
             } else {
@@ -400,7 +412,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ew = warp - 2, half = ew >> 2;
         float* stage = epi_stage + q * kEpiStageFloats;
         const int row_limit = WGRAD ? p.K : p.M;
+        constexpr int kCap1 = stat_capacity(kStatFloats1, 4);
         const bool use_smem_stats = (!WGRAD) && (p.col_stats != nullptr) && (p.N <= kMaxStatCols);
+        const int stat_mode = !use_smem_stats ? 0 : ((p.tma_store && p.N <= kCap1) ? 2 : 1);
         if (p.tma_store) {
             const uint32_t stg0 = smem_u32(epi_bytes) + (uint32_t)ew * 2u * kEpiBufBytes;
             uint32_t buf = 0, t = 0;
@@ -418,7 +432,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 staged_tile_epilogue<BLOCK_N, WGRAD, false>(p, &tmC, tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N,
                                                             rb, col0, lane, half, stg0, buf,
-                                                            tmem_empty_bar + 8 * as, stat_smem, use_smem_stats, rl, c2);
+                                                            tmem_empty_bar + 8 * as, stat_smem, stat_mode, q, kCap1, rl, c2);
             }
             if (lane == 0) tma_wait_group_all();
         } else {
@@ -558,7 +572,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");    // the epilogue warps only
             const int e = threadIdx.x - 64;
             for (int c = e; c < p.N; c += 32 * kEpiWarps) {
-                const float a1 = stat_smem[c], a2 = stat_smem[kMaxStatCols + c];
+                float a1, a2;
+                if (stat_mode == 2) {
+                    a1 = 0.f; a2 = 0.f;
+#pragma unroll
+                    for (int sl = 0; sl < 4; ++sl) { a1 += stat_smem[sl * 2 * kCap1 + c]; a2 += stat_smem[sl * 2 * kCap1 + kCap1 + c]; }
+                } else { a1 = stat_smem[c]; a2 = stat_smem[kMaxStatCols + c]; }
                 if (a1 != 0.f || a2 != 0.f) {
                     atomicAdd(p.col_stats + c, a1);
                     atomicAdd(p.col_stats + p.N + c, a2);
@@ -633,7 +652,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* epi_bytes = smem + kStages2 * STAGE_BYTES;
     float* stat_smem = reinterpret_cast<float*>(epi_bytes + kEpiBytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_bytes + kEpiBytes + 2 * kMaxStatCols * 4);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_bytes + kEpiBytes + kStatFloats2 * 4);
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t full_bar = smem_u32(bars);                        // kStages2 (used in the leader only)
     const uint32_t empty_bar = smem_u32(bars + kStages2);            // kStages2 (one per CTA, multicast arrivals)
@@ -648,7 +667,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     pdl_launch_dependents();
 
     if (!WGRAD && p.col_stats != nullptr)
-        for (int i = threadIdx.x; i < 2 * kMaxStatCols; i += kThreads) stat_smem[i] = 0.f;
+        for (int i = threadIdx.x; i < kStatFloats2; i += kThreads) stat_smem[i] = 0.f;
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
@@ -752,7 +771,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // ===== epilogue (both CTAs): warps 2..9, TMEM lane quadrant = warp % 4, two warps per quadrant =====
         const int q = warp & 3;
         const int ew = warp - 2, half = ew >> 2;
-        const bool use_smem_stats = (!WGRAD) && (p.col_stats != nullptr) && (p.N <= kMaxStatCols);
+        constexpr int kCap2 = stat_capacity(kStatFloats2, 4);
+        const bool use_smem_stats = (!WGRAD) && (p.col_stats != nullptr) && (p.N <= kCap2);
+        const int stat_mode = use_smem_stats ? 2 : 0;
         const uint32_t stg0 = smem_u32(epi_bytes) + (uint32_t)ew * 2u * kEpiBufBytes;
         const uint32_t leader_tmem_empty = mapa_rank(tmem_empty_bar, 0);
         uint32_t buf = 0, t = 0;
@@ -769,7 +790,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             staged_tile_epilogue<BLOCK_N, WGRAD, true>(p, &tmC, tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N,
                                                        row0 + q * 32, col0, lane, half, stg0, buf,
-                                                       leader_tmem_empty + 8 * as, stat_smem, use_smem_stats,
+                                                       leader_tmem_empty + 8 * as, stat_smem, stat_mode, q, kCap2,
                                                        WGRAD ? p.K : p.M, -1);
         }
         if (lane == 0) tma_wait_group_all();
@@ -777,7 +798,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");    // the epilogue warps only
             const int e = threadIdx.x - 64;
             for (int c = e; c < p.N; c += 32 * kEpiWarps) {
-                const float a1 = stat_smem[c], a2 = stat_smem[kMaxStatCols + c];
+                float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+                for (int sl = 0; sl < 4; ++sl) { a1 += stat_smem[sl * 2 * kCap2 + c]; a2 += stat_smem[sl * 2 * kCap2 + kCap2 + c]; }
                 if (a1 != 0.f || a2 != 0.f) {
                     atomicAdd(p.col_stats + c, a1);
                     atomicAdd(p.col_stats + p.N + c, a2);
@@ -815,7 +838,7 @@ template <int BLOCK_N, bool WGRAD>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, GemmParams p,
                         cudaStream_t st) {
     constexpr int smem = kStages2 * (kBlockM * kBlockK * 2 + (BLOCK_N / 2) * kBlockK * 2) + kEpiBytes +
-                         2 * kMaxStatCols * 4 + 1024 + 256;
+                         kStatFloats2 * 4 + 1024 + 256;
     static_assert(smem <= 232448, "shared memory budget");
     static bool configured = false;
     if (!configured) {
@@ -1060,7 +1083,9 @@ conv3x3_valid_fwd32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     } else {
         const int q = warp & 3;
         const int ew = warp - 2, half = ew >> 2;
-        const bool use_smem_stats = (p.col_stats != nullptr) && (p.N <= kMaxStatCols);
+        constexpr int kCapF = stat_capacity(kStatFloats1, kEpiWarps);       // one private table per epilogue WARP here
+        const bool use_smem_stats = (p.col_stats != nullptr) && (p.N <= kCapF);
+        const int stat_mode = use_smem_stats ? 2 : 0;
         const uint32_t stg0 = smem_u32(epi_bytes) + (uint32_t)ew * 2u * kEpiBufBytes;
         uint32_t buf = 0, it = 0;
         for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
@@ -1072,14 +1097,16 @@ conv3x3_valid_fwd32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             // both accumulator stages run concurrently (the tile loop is epilogue-paced: 18 short MMAs per tile)
             staged_tile_epilogue<64, false, false>(p, &tmC, tmem_base + ((uint32_t)(q * 32) << 16) + as * 64, w0 + q * 32, 0,
                                                    lane, half ^ (int)(it & 1u), stg0, buf, tmem_empty_bar + 8 * as, stat_smem,
-                                                   use_smem_stats, p.cv_rlimit, r);
+                                                   stat_mode, ew, kCapF, p.cv_rlimit, r);
         }
         if (lane == 0) tma_wait_group_all();
         if (use_smem_stats) {
             asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
             const int e = threadIdx.x - 64;
             for (int c = e; c < p.N; c += 32 * kEpiWarps) {
-                const float a1 = stat_smem[c], a2 = stat_smem[kMaxStatCols + c];
+                float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+                for (int sl = 0; sl < kEpiWarps; ++sl) { a1 += stat_smem[sl * 2 * kCapF + c]; a2 += stat_smem[sl * 2 * kCapF + kCapF + c]; }
                 if (a1 != 0.f || a2 != 0.f) {
                     atomicAdd(p.col_stats + c, a1);
                     atomicAdd(p.col_stats + p.N + c, a2);
