@@ -27,6 +27,11 @@ int launch_dw_wgrad_tma(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* 
                         int Wo, int pad_t, int pad_l, int in_act, cudaStream_t st, const float* in_scale = nullptr,
                         const float* in_shift = nullptr);
 
+// dwconv_tma.cu: whole-image smem staging for atrous taps on small feature maps; returns 1 if it took the launch
+int launch_dw_image(int mode, const __nv_bfloat16* in, const float* w, __nv_bfloat16* out, const __nv_bfloat16* dy,
+                    float* dwg, int N, int H, int W, int C, int dil_h, int dil_w, int flip, int in_act,
+                    const __nv_bfloat16* addend, cudaStream_t st);
+
 template <typename T, int TW, bool DENSE_W, bool HAS_AFFINE, bool HAS_EPI>
 __global__ void __launch_bounds__(256)
 dw_conv_kernel(const T* __restrict__ in, const float* __restrict__ w, T* __restrict__ out, int N, int Hin, int Win,
@@ -448,6 +453,13 @@ extern "C" int dlv3p_dwconv3x3_fwd(const void* x, const float* w, void* y, int N
                                 in_act, nullptr, nullptr, nullptr, 0, nullptr, st, in_scale, in_shift);
         if (rc != 0) return rc < 0 ? rc : 0;
     }
+    if (dtype == DLV3P_BF16 && stride == 1 && (dil_h > 1 || dil_w > 1) && in_scale == nullptr && pad_t == dil_h &&
+        pad_l == dil_w && Ho == H && Wo == W) {
+        // atrous taps (ASPP): the whole image of one (n, channel block) staged in shared memory by one TMA box
+        rc = launch_dw_image(0, (const __nv_bfloat16*)x, w, (__nv_bfloat16*)y, nullptr, nullptr, N, H, W, C, dil_h,
+                             dil_w, 0, in_act, nullptr, st);
+        if (rc != 0) return rc < 0 ? rc : 0;
+    }
     DLV3P_DISPATCH_DTYPE(dtype, T, {
         if (in_scale)
             return launch_dw_conv<T, true, false>((const T*)x, w, (T*)y, N, H, W, C, Ho, Wo, stride, dil_h, dil_w,
@@ -473,6 +485,12 @@ extern "C" int dlv3p_dwconv3x3_dgrad(const void* dy, const float* w, void* dx, i
         rc = launch_dw_conv_tma((const __nv_bfloat16*)dy, w, (__nv_bfloat16*)dx, N, Ho, Wo, C, H, W, 2 - pad_t, 2 - pad_l,
                                 1, DLV3P_ACT_NONE, (const __nv_bfloat16*)x_pre, in_scale, in_shift, in_act,
                                 (const __nv_bfloat16*)addend, st);
+        if (rc != 0) return rc < 0 ? rc : 0;
+    }
+    if (dtype == DLV3P_BF16 && stride == 1 && (dil_h > 1 || dil_w > 1) && in_act == DLV3P_ACT_NONE && pad_t == dil_h &&
+        pad_l == dil_w && Ho == H && Wo == W) {
+        rc = launch_dw_image(0, (const __nv_bfloat16*)dy, w, (__nv_bfloat16*)dx, nullptr, nullptr, N, H, W, C, dil_h,
+                             dil_w, 1, DLV3P_ACT_NONE, (const __nv_bfloat16*)addend, st);
         if (rc != 0) return rc < 0 ? rc : 0;
     }
     DLV3P_DISPATCH_DTYPE(dtype, T, {
@@ -545,6 +563,12 @@ extern "C" int dlv3p_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, i
     if (dtype == DLV3P_BF16 && stride == 1 && dil_h == 1 && dil_w == 1) {
         rc = launch_dw_wgrad_tma((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw, N, H, W, C, Ho, Wo, pad_t, pad_l,
                                  in_act, st, in_scale, in_shift);
+        if (rc != 0) return rc < 0 ? rc : 0;
+    }
+    if (dtype == DLV3P_BF16 && stride == 1 && (dil_h > 1 || dil_w > 1) && in_scale == nullptr && pad_t == dil_h &&
+        pad_l == dil_w && Ho == H && Wo == W) {
+        rc = launch_dw_image(1, (const __nv_bfloat16*)x, nullptr, nullptr, (const __nv_bfloat16*)dy, dw, N, H, W, C, dil_h,
+                             dil_w, 0, in_act, nullptr, st);
         if (rc != 0) return rc < 0 ? rc : 0;
     }
     DLV3P_DISPATCH_DTYPE(dtype, T, {
