@@ -414,7 +414,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int row_limit = WGRAD ? p.K : p.M;
         constexpr int kCap1 = stat_capacity(kStatFloats1, 4);
         const bool use_smem_stats = (!WGRAD) && (p.col_stats != nullptr) && (p.N <= kMaxStatCols);
-        const int stat_mode = !use_smem_stats ? 0 : ((p.tma_store && p.N <= kCap1) ? 2 : 1);
+        const int stat_mode = !use_smem_stats ? 0 : (p.N <= kCap1 ? 2 : 1);
         if (p.tma_store) {
             const uint32_t stg0 = smem_u32(epi_bytes) + (uint32_t)ew * 2u * kEpiBufBytes;
             uint32_t buf = 0, t = 0;
@@ -488,7 +488,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             s1 += u; s2 = fmaf(u, u, s2);
                         }
                         if (col < p.N) {
-                            if (use_smem_stats) {
+                            if (stat_mode == 2) {
+                                float* mine = stat_smem + q * 2 * kCap1;       // this quadrant's private table
+                                mine[col] += s1;
+                                mine[kCap1 + col] += s2;
+                            } else if (stat_mode == 1) {
                                 atomicAdd(stat_smem + col, s1);
                                 atomicAdd(stat_smem + kMaxStatCols + col, s2);
                             } else {
