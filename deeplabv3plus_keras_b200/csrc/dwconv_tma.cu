@@ -34,7 +34,7 @@ struct DwTmaParams {
     // scale/shift/mean/invstd for the backward pass and updates the moving statistics
     const float* f_sums; const float* f_gamma; const float* f_beta; float* f_mm; float* f_mv;
     float* f_scale; float* f_shift; float* f_mean; float* f_invstd;
-    double f_count; float f_eps, f_momentum; int f_updates;
+    double f_count, f_inv_count; float f_eps, f_momentum; int f_updates;
     int tiles_h, tiles_w, tiles_c;
     int spatial_tiles, ctas_per_cb;
 };
@@ -183,10 +183,14 @@ dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int c = c0 + k;
-                const double m = (double)__ldcg(p.f_sums + c) / p.f_count;
-                double var = (double)__ldcg(p.f_sums + p.C + c) / p.f_count - m * m;
+                // fp64 only where it matters (E[x^2] - E[x]^2 cancels); the division and the square root of
+                // bn_finalize_kernel are a multiplication by 1/count and an fp32 rsqrt here: every thread of the CTA runs
+                // this prologue on the critical path right after the dependency wait
+                const double inv_count = p.f_inv_count;
+                const double m = (double)__ldcg(p.f_sums + c) * inv_count;
+                double var = (double)__ldcg(p.f_sums + p.C + c) * inv_count - m * m;
                 if (var < 0.0) var = 0.0;
-                const float is = (float)(1.0 / sqrt(var + (double)p.f_eps));
+                const float is = rsqrtf((float)var + p.f_eps);
                 const float g = p.f_gamma ? __ldg(p.f_gamma + c) : 1.f;
                 const float b = p.f_beta ? __ldg(p.f_beta + c) : 0.f;
                 sc4[k] = g * is;
@@ -393,7 +397,7 @@ int launch_dw_conv_tma(const __nv_bfloat16* in, const float* w, __nv_bfloat16* o
     if (fold != nullptr) {
         p.f_sums = fold->sums; p.f_gamma = fold->gamma; p.f_beta = fold->beta; p.f_mm = fold->moving_mean;
         p.f_mv = fold->moving_var; p.f_scale = fold->scale; p.f_shift = fold->shift; p.f_mean = fold->mean;
-        p.f_invstd = fold->invstd; p.f_count = fold->count; p.f_eps = fold->eps; p.f_momentum = fold->momentum;
+        p.f_invstd = fold->invstd; p.f_count = fold->count; p.f_inv_count = 1.0 / fold->count; p.f_eps = fold->eps; p.f_momentum = fold->momentum;
         p.f_updates = fold->updates;
     }
     p.tiles_h = cdiv(Hout, kDwTH); p.tiles_w = cdiv(Wout, kDwTW); p.tiles_c = cdiv(C, kDwCB);

@@ -834,25 +834,43 @@ static_assert(sizeof(WeightPrepEntry) == 48, "table layout is part of the C-ABI 
 
 __global__ void __launch_bounds__(256)
 weight_prep_batch_kernel(const WeightPrepEntry* __restrict__ table) {
-    __shared__ float tile[32][33];
+    // 64 x 64 tiles, two adjacent elements per thread: 8-byte fp32 loads and 4-byte packed bf16 stores in BOTH
+    // orientations (the 32 x 32 / 2-byte-store version ran at 1.6 TB/s: 64-byte store segments)
+    __shared__ float tile[64][65];
     pdl_launch_dependents();
     pdl_wait();
     const WeightPrepEntry e = table[blockIdx.y];
-    const int tiles_n = (e.N + 31) / 32, tiles_k = (e.K + 31) / 32;
+    const int tiles_n = (e.N + 63) / 64, tiles_k = (e.K + 63) / 64;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const bool n_even = (e.N % 2 == 0) && (e.wn == nullptr || e.ldn % 2 == 0);
+    const bool k_even = (e.ldt % 2 == 0);
     for (int t = blockIdx.x; t < tiles_n * tiles_k; t += gridDim.x) {
-        const int k0 = (t / tiles_n) * 32, n0 = (t % tiles_n) * 32;
-        for (int r = ty; r < 32; r += 8) {
-            const int k = k0 + r, n = n0 + tx;
-            float v = 0.f;
-            if (k < e.K && n < e.N) v = e.w[(long long)k * e.N + n];
-            tile[r][tx] = v;
-            if (e.wn != nullptr && k < e.K && n < e.N) e.wn[(long long)k * e.ldn + n] = __float2bfloat16_rn(v);
+        const int k0 = (t / tiles_n) * 64, n0 = (t % tiles_n) * 64;
+        for (int r = ty; r < 64; r += 8) {
+            const int k = k0 + r, n = n0 + 2 * tx;
+            float v0 = 0.f, v1 = 0.f;
+            if (k < e.K) {
+                const float* src = e.w + (long long)k * e.N + n;
+                if (n_even && n + 1 < e.N) { const float2 v = *reinterpret_cast<const float2*>(src); v0 = v.x; v1 = v.y; }
+                else { if (n < e.N) v0 = src[0]; if (n + 1 < e.N) v1 = src[1]; }
+                if (e.wn != nullptr) {
+                    __nv_bfloat16* dst = e.wn + (long long)k * e.ldn + n;
+                    if (n_even && n + 1 < e.N) *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(v0, v1);
+                    else { if (n < e.N) dst[0] = __float2bfloat16_rn(v0); if (n + 1 < e.N) dst[1] = __float2bfloat16_rn(v1); }
+                }
+            }
+            tile[r][2 * tx] = v0;
+            tile[r][2 * tx + 1] = v1;
         }
         __syncthreads();
-        for (int r = ty; r < 32; r += 8) {
-            const int n = n0 + r, k = k0 + tx;
-            if (n < e.N && k < e.K) e.wt[(long long)n * e.ldt + k] = __float2bfloat16_rn(tile[tx][r]);
+        for (int r = ty; r < 64; r += 8) {
+            const int n = n0 + r, k = k0 + 2 * tx;
+            if (n < e.N) {
+                __nv_bfloat16* dst = e.wt + (long long)n * e.ldt + k;
+                const float a = tile[2 * tx][r], b = tile[2 * tx + 1][r];
+                if (k_even && k + 1 < e.K) *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(a, b);
+                else { if (k < e.K) dst[0] = __float2bfloat16_rn(a); if (k + 1 < e.K) dst[1] = __float2bfloat16_rn(b); }
+            }
         }
         __syncthreads();
     }
