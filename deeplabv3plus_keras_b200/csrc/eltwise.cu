@@ -317,10 +317,10 @@ template <typename T, int CVB, int ACT, bool HAS_ADD>
 __global__ void __launch_bounds__(256, HAS_ADD ? 2 : 3)
 bn_train_apply_kernel(const T* __restrict__ y, long long ld_y, const float* __restrict__ sums,
                       const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ moving_mean,
-                      float* __restrict__ moving_var, double count, float eps, float momentum, int updates,
-                      const T* __restrict__ addend, long long ld_a, T* __restrict__ out, long long ld_o, long long M,
-                      int C, float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean,
-                      float* __restrict__ invstd, long long rows_per_block) {
+                      float* __restrict__ moving_var, double count, double inv_count, float eps, float momentum,
+                      int updates, const T* __restrict__ addend, long long ld_a, T* __restrict__ out, long long ld_o,
+                      long long M, int C, float* __restrict__ scale, float* __restrict__ shift,
+                      float* __restrict__ mean, float* __restrict__ invstd, long long rows_per_block) {
     pdl_launch_dependents();
     pdl_wait();
     constexpr int PL = 256 / CVB;
@@ -334,11 +334,12 @@ bn_train_apply_kernel(const T* __restrict__ y, long long ld_y, const float* __re
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int c = c0 + k;
-        const double inv_count = 1.0 / count;
+        // fp64 only for the cancelling E[x^2] - E[x]^2 (two DFMA); 1/count comes from the host and the square root is an
+        // fp32 rsqrt: this prologue runs in every thread on the critical path behind the dependency wait
         const double m = (double)__ldg(sums + c) * inv_count;
         double var = (double)__ldg(sums + C + c) * inv_count - m * m;
         if (var < 0.0) var = 0.0;
-        const float is = (float)rsqrt(var + (double)eps);
+        const float is = rsqrtf((float)var + eps);
         const float g = gamma ? __ldg(gamma + c) : 1.f;
         const float b = beta ? __ldg(beta + c) : 0.f;
         sc[k] = g * is;
@@ -1040,7 +1041,7 @@ extern "C" int dlv3p_affine_act(const void* y, int64_t ld_y, const float* scale,
 }
 
 #define DLV3P_BNT(A, AD) launch_pdl(bn_train_apply_kernel<T, CVB, A, AD>, dim3(gx, gy), dim3(256), 0, st, (const T*)y, (long long)ld_y, \
-                                    sums, gamma, beta, moving_mean, moving_var, count, eps, momentum, updates, (const T*)addend,    \
+                                    sums, gamma, beta, moving_mean, moving_var, count, 1.0 / count, eps, momentum, updates, (const T*)addend, \
                                     (long long)ld_addend, (T*)out, (long long)ld_out, (long long)M, C, scale, shift, mean, invstd, rpb)
 
 extern "C" int dlv3p_bn_train_apply(const void* y, int64_t ld_y, const float* sums, const float* gamma, const float* beta,

@@ -722,8 +722,11 @@ def test_bn_train_apply_matches_two_step(MC, dtype):
         o.bn_train_apply(y, M, C, sums, gamma, beta, mm_g, mv_g, M, 1e-3, 0.9, updates, act, out_g, *got,
                          addend=res if use_add else None)
         for a, b, nm in zip(got + [mm_g, mv_g], ref + [mm_r, mv_r], ("scale", "shift", "mean", "invstd", "mm", "mv")):
-            check(f"bn_train_apply {nm}", a, b, 1e-6, 1e-6)
-        assert torch.equal(out_g, out_r)
+            check(f"bn_train_apply {nm}", a, b, 2e-6, 2e-6)
+        # the fused kernel finishes the statistics with an fp32 rsqrt (bn_finalize: fp64 1/sqrt): scale/shift agree to
+        # ~3e-7 relative, the outputs to that times |y| (bf16: an occasional one-ulp flip of the stored value)
+        rt = 1e-5 if dtype == torch.float32 else 1e-2
+        check("bn_train_apply out", out_g, out_r, rt, rt)
 
 
 def test_weight_prep_batch_matches_single():
