@@ -434,7 +434,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                                             rb, col0, lane, half, stg0, buf,
                                                             tmem_empty_bar + 8 * as, stat_smem, stat_mode, q, kCap1, rl, c2);
             }
-            if (lane == 0) tma_wait_group_all();
+            if (lane == 0) tma_wait_group_read<0>();      // smem may be released; the writes drain before the grid completes
         } else {
         uint32_t t = 0;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++t) {
@@ -797,7 +797,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                                        leader_tmem_empty + 8 * as, stat_smem, stat_mode, q, kCap2,
                                                        WGRAD ? p.K : p.M, -1);
         }
-        if (lane == 0) tma_wait_group_all();
+        if (lane == 0) tma_wait_group_read<0>();      // smem may be released; the writes drain before the grid completes
         if (use_smem_stats) {
             asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");    // the epilogue warps only
             const int e = threadIdx.x - 64;
@@ -1103,7 +1103,7 @@ conv3x3_valid_fwd32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                                                    lane, half ^ (int)(it & 1u), stg0, buf, tmem_empty_bar + 8 * as, stat_smem,
                                                    stat_mode, ew, kCapF, p.cv_rlimit, r);
         }
-        if (lane == 0) tma_wait_group_all();
+        if (lane == 0) tma_wait_group_read<0>();      // smem may be released; the writes drain before the grid completes
         if (use_smem_stats) {
             asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
             const int e = threadIdx.x - 64;
