@@ -214,7 +214,7 @@ class Plan:
 
     def __init__(self, model: Model, batch_size: int, training: bool = False, dtype: Optional[str] = None,
                  device: Optional[str] = None, dropout_seed: int = 1024, fused_tail: bool = True,
-                 fuse_bn_dw: bool = True, implicit_conv: bool = True):
+                 fuse_bn_dw: bool = True, implicit_conv: bool = True, concat_in_place: bool = True):
         fake = getattr(ops, "FAKE", False)       # tests/fake_ops.py test double (host-logic tests without a GPU)
         if not torch.cuda.is_available() and not fake:
             raise RuntimeError("engine.Plan needs a CUDA device: there is no CPU execution path")
@@ -227,6 +227,7 @@ class Plan:
         self.bf16 = self.dt == torch.bfloat16
         self.fused_tail = fused_tail
         self.fuse_bn_dw = fuse_bn_dw        # Conv->BN->ReLU->depthwise: BN+ReLU applied on load (False: A/B, materialise it)
+        self.concat_in_place = concat_in_place   # Conv->BN(->ReLU) read only by a Concatenate writes its slice directly
         self.implicit_conv = implicit_conv  # dense 3x3 VALID stride-1 convs as implicit GEMMs (False: A/B, im2col + GEMM)
         self.dropout_seed = dropout_seed
         self.fwd: List[Callable[[], None]] = []
@@ -337,6 +338,7 @@ class Plan:
             for i in n.inputs:
                 consumers.setdefault(i, []).append(n)
         producer = {n.output: n for n in nodes}
+        shape_of_node = {n.output: n.shape for n in nodes}
 
         def sole(tid) -> Optional[FlatNode]:
             c = consumers.get(tid, [])
@@ -399,6 +401,26 @@ class Plan:
                         nxt.absorbed = True
                 n.absorbed = True
                 macros[index[id(m["tail"])]] = m
+
+        # ---- Concatenate inputs written in place: a training-mode Conv -> BN (-> ReLU) macro-op whose only reader is
+        # a Concatenate writes its output straight into its channel slice of the concat buffer (bn_train_apply's ld_out)
+        # and reads its gradient from the same slice of the concat gradient (ld_dz): no slice copies either way
+        self._concat_slot: Dict[int, Tuple[int, int, int]] = {}       # tensor id -> (concat tensor id, offset, Ct)
+        self._concat_buf: Dict[int, torch.Tensor] = {}
+        if self.training and self.concat_in_place:
+            for n in nodes:
+                if isinstance(n.layer, L.Concatenate) and n.output != out_id:
+                    Ct, off = sum(shape_of_node[i][-1] for i in n.inputs), 0
+                    for i in n.inputs:
+                        src, reader = i, n
+                        # look through identity layers (x1 resize, 1x1 average pool: conf.json:51)
+                        while sole(src) is reader and src in producer and (
+                                (isinstance(producer[src].layer, L.ResizeImages) and tuple(producer[src].layer.factors) == (1, 1))
+                                or (isinstance(producer[src].layer, L.AveragePooling2D) and producer[src].layer.pool_size[0] == 1)):
+                            reader, src = producer[src], producer[src].inputs[0]
+                        if sole(src) is reader:
+                            self._concat_slot[src] = (n.output, off, Ct)
+                        off += shape_of_node[i][-1]
 
         # ---- emission in topological order ---------------------------------------------------------------
         for i, n in enumerate(nodes):
@@ -475,8 +497,18 @@ class Plan:
         ld_out = Cout
         virt = (bool(m.get("virt")) and self.fuse_bn_dw and training and bn_node is not None and act != ACT_NONE
                 and other_id is None and m["out"] != out_id and Cout % 8 == 0)
+        slot_c = self._concat_slot.get(m["out"])
+        in_place = (slot_c is not None and not virt and training and bn_node is not None and other_id is None
+                    and Cout % 8 == 0 and Cout == Cout_log and y_dtype == self.dt)
         if virt:
             out = _BnActValue(out_shape, y_dtype, lay.name, act)       # buffers / BN operands attached below
+        elif in_place:
+            cid, c_off, Ct = slot_c
+            if cid not in self._concat_buf:
+                self._concat_buf[cid] = self._alloc((N, Ho, Wo, Ct), self.dt)
+            ld_out = Ct
+            out = Value(out_shape, y_dtype, self._concat_buf[cid].view(N * Ho * Wo, Ct)[:, c_off:c_off + Cout], lay.name)
+            out.concat_slice = True
         else:
             out = Value(out_shape, y_dtype, self._alloc((N, Ho, Wo, ld_out), y_dtype), lay.name)
         out.clog = Cout_log
@@ -633,7 +665,7 @@ class Plan:
                 # statistics -> scale/shift, moving-statistics update and BN+activation(+add) in one launch
                 self.fwd.append(lambda: ops.bn_train_apply(y, Mo, Cout, stat(), gamma, beta, mm, mv, Mo, bn.epsilon,
                                                            bn.momentum, upd, act, out.buf, scale, shift, mean, invstd,
-                                                           addend=addend_f))
+                                                           addend=addend_f, ld_out=ld_out))
                 launches_f += 1
             else:
                 for r in range(upd):
@@ -666,10 +698,12 @@ class Plan:
                 # virtual BN+ReLU output: g arrives as the gradient w.r.t. the BN output, ReLU mask already applied
                 # by the reader's input-gradient kernel (which may also have produced the two reductions)
                 act_b = ACT_NONE if virt else act
+                ld_g = g.stride(0) if g.dim() == 2 else Cout          # 2-D: a channel slice of a concat gradient
                 if not (virt and out.red_done):
-                    self.bwd_seq(lambda: ops.bn_bwd_reduce(g, y, scale, shift, mean, invstd, act_b, Mo, Cout, red()))
+                    self.bwd_seq(lambda: ops.bn_bwd_reduce(g, y, scale, shift, mean, invstd, act_b, Mo, Cout, red(),
+                                                           ld_dz=ld_g))
                 self.bwd_seq(lambda: ops.bn_bwd_apply(g, y, scale, shift, mean, invstd, act_b, red(), Mo, Cout,
-                                                      dy_get()))
+                                                      dy_get(), ld_dz=ld_g))
                 # parameter gradients live in the stats arena; copy into the grad arena
                 if beta is not None and not red_direct:
                     gb = P.view(bn, "beta", grad=True)
@@ -958,21 +992,27 @@ class Plan:
             raise NotImplementedError("Concatenate of a channel-padded tensor (phys_channels) is not on the hot path")
         N, H, W, _ = ins[0].shape
         Ct = sum(v.C for v in ins)
-        out = Value((N, H, W, Ct), self.dt, self._alloc((N, H, W, Ct), self.dt), n.layer.name)
+        buf = self._concat_buf.get(n.output)
+        if buf is None:
+            buf = self._alloc((N, H, W, Ct), self.dt)
+        out = Value((N, H, W, Ct), self.dt, buf, n.layer.name)
         out.needs_grad = self.training
         self.values[n.output] = out
         M = N * H * W
         off = 0
         for v in ins:
-            self.fwd.append(lambda v=v, off=off: ops.copy2d(v.buf, v.C, out.buf, Ct, M, v.C, y_off=off))
-            self.launches_fwd += 1
+            if not getattr(v, "concat_slice", False):          # (slices written in place by their producer)
+                self.fwd.append(lambda v=v, off=off: ops.copy2d(v.buf, v.C, out.buf, Ct, M, v.C, y_off=off))
+                self.launches_fwd += 1
             off += v.C
         if self.training:
             def sched():
                 g = self._final_grad(out)
                 o = 0
                 for v in ins:
-                    if v.needs_grad:
+                    if v.needs_grad and getattr(v, "concat_slice", False):
+                        v.pending.append(g.view(M, Ct)[:, o:o + v.C])      # read in place (ld_dz = Ct), no copy
+                    elif v.needs_grad:
                         tgt, add2 = self._grad_target(v)
                         self.bwd_seq(lambda v=v, o=o, tgt=tgt, add2=add2: ops.copy2d(
                             g, Ct, tgt, v.C, M, v.C, addend=add2, ld_addend=v.C, x_off=o))

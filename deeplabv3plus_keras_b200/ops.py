@@ -257,11 +257,12 @@ def bn_finalize(sums, gamma, beta, moving_mean, moving_var, Cc, count, eps, mome
 
 
 def bn_train_apply(y, M, Cc, sums, gamma, beta, moving_mean, moving_var, count, eps, momentum, updates, act, out,
-                   scale, shift, mean, invstd, addend=None):
-    """Training-mode BatchNormalization (+activation, +residual add) forward from the batch sums, in one launch."""
+                   scale, shift, mean, invstd, addend=None, ld_out=None):
+    """Training-mode BatchNormalization (+activation, +residual add) forward from the batch sums, in one launch.
+    `ld_out`: row pitch of `out` (a channel slice of a Concatenate buffer)."""
     call("dlv3p_bn_train_apply", _p(y), Cc, _p(sums), _p(gamma), _p(beta), _p(moving_mean), _p(moving_var),
-         float(count), eps, momentum, int(updates), act, _p(addend), Cc, _p(out), Cc, M, Cc, _p(scale), _p(shift),
-         _p(mean), _p(invstd), _dt(y), _stream())
+         float(count), eps, momentum, int(updates), act, _p(addend), Cc, _p(out), Cc if ld_out is None else ld_out, M, Cc,
+         _p(scale), _p(shift), _p(mean), _p(invstd), _dt(y), _stream())
     return out
 
 

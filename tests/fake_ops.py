@@ -36,6 +36,8 @@ def _mask(v, act):
 
 def _rows(t, M, ld, C, off=0):
     """[M,C] view of a buffer with row pitch ld starting `off` elements into it."""
+    if t.dim() == 2 and tuple(t.shape) == (M, C) and t.stride() == (ld, 1) and off == 0:
+        return t                                  # already the strided slice (a channel slice of a concat buffer)
     flat = t.reshape(-1)
     return flat[off:off + (M - 1) * ld + C].as_strided((M, C), (ld, 1))
 
@@ -267,11 +269,11 @@ def bn_finalize(sums, gamma, beta, moving_mean, moving_var, Cc, count, eps, mome
 
 
 def bn_train_apply(y, M, Cc, sums, gamma, beta, moving_mean, moving_var, count, eps, momentum, updates, act, out,
-                   scale, shift, mean, invstd, addend=None):
+                   scale, shift, mean, invstd, addend=None, ld_out=None):
     for u in range(max(updates, 1)):
         bn_finalize(sums, gamma, beta, moving_mean, moving_var, Cc, count, eps, momentum, scale, shift, mean, invstd,
                     update_moving=u < updates)
-    return affine_act(y, M, Cc, out, scale, shift, act, addend=addend)
+    return affine_act(y, M, Cc, out, scale, shift, act, addend=addend, ld_out=ld_out)
 
 
 def weight_prep_table(entries, device):

@@ -123,6 +123,34 @@ def test_channel_pitch_padding_is_invisible_and_skips_concatenated_widths(cpu_en
                                          for n, w in l._weights.items() if l._trainable[n])
 
 
+def test_concat_slices_written_in_place(cpu_engine, monkeypatch):
+    """ASPP branches whose only reader is the Concatenate write their BN+ReLU output straight into the concat buffer
+    (bn_train_apply ld_out) and read their gradient from the concat gradient in place (ld_dz): four of the five slice
+    copies disappear in each direction (the x1 resize of the pooling branch is looked through) (branch 0 also feeds the atrous branches and keeps its copy)."""
+    conf = util.make_conf(width=64, base="xception", output_stride=16, image_size=65)
+    ss = util.build(conf)
+    util.randomize_weights(ss.model)
+    calls = []
+    orig = fake_ops.copy2d
+    monkeypatch.setattr(fake_ops, "copy2d", lambda *a, **k: (calls.append("copy2d"), orig(*a, **k))[1])
+    plans = {}
+    for flag in (True, False):
+        calls.clear()
+        plan = cpu_engine.Plan(ss.model, 2, training=True, concat_in_place=flag)
+        x, y = util.synthetic_batch(conf, 2, plan.out_shape[1:3])
+        plan.set_loss(PW, NW)
+        plan.load_batch(x, y)
+        plan.step_fwd_bwd()
+        plans[flag] = (plan, len(calls))
+    assert plans[False][1] == 10 and plans[True][1] == 2, (plans[True][1], plans[False][1])
+    a, b = plans[True][0], plans[False][0]
+    np.testing.assert_allclose(a.logits.buf.numpy(), b.logits.buf.numpy(), rtol=1e-5, atol=1e-6)
+    ga, gb = a.gradients(), b.gradients()
+    for k in gb:
+        scale = max(np.abs(gb[k]).max(), 1e-3)
+        assert np.abs(ga[k] - gb[k]).max() <= 1e-4 * scale, k
+
+
 def test_implicit_conv_schedule(cpu_engine, monkeypatch):
     """Xception block1_conv2 (3x3 VALID stride 1, 32 -> 64): the implicit-GEMM schedule (no im2col / col2im, prepared
     wk / wd filter matrices) must reproduce the im2col + GEMM schedule."""
