@@ -51,6 +51,8 @@ SIGNATURES = {
     "dlv3p_copy2d": [_p, _l, _p, _l, _l, _i, _p, _l, _i, _p],
     "dlv3p_maxpool3x3s2_fwd": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p],
     "dlv3p_maxpool3x3s2_bwd": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p],
+    "dlv3p_maxpool3x3s2_bn_fwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p],
+    "dlv3p_maxpool3x3s2_bn_bwd": [_p, _p, _p, _p, _p, _p, _p, _d, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "dlv3p_avgpool_fwd": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "dlv3p_avgpool_bwd": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p],
     "dlv3p_bilinear_fwd": [_p, _l, _p, _l, _i, _i, _i, _i, _i, _i, _i, _i, _p],

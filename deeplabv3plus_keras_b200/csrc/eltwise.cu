@@ -1157,10 +1157,18 @@ namespace dlv3p {
 // walk kMpRowsF output rows.  First maximum wins (strict >), padding never wins (it is never visited).
 constexpr int kMpRowsF = 4;
 
+// AFFINE: x is the RAW conv output of a training-mode BatchNormalization layer that feeds the pool directly
+// (Xception block2/3/4 sepconv2_bn -> MaxPooling2D): the pool runs on scale*x+shift without that tensor ever being
+// written.  max(scale*x+shift) = scale*max(x)+shift for scale >= 0 and scale*min(x)+shift otherwise, so the packed bf16
+// compares run on x with the sign bit of the negative-scale channels flipped (x ^ 0x8000 negates a bf16 exactly); the
+// winner's raw value is also stored (ymax): the BatchNormalization backward reductions then only need the POOLED tensors.
+template <bool AFFINE>
 __global__ void __launch_bounds__(256)
 maxpool3x3s2_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                              uint8_t* __restrict__ argmax, int N, int H, int W, int C, int pad_t, int pad_l, int Ho,
-                             int Wo, const __nv_bfloat16* __restrict__ addend, int ncvb) {
+                             int Wo, const __nv_bfloat16* __restrict__ addend, int ncvb,
+                             const float* __restrict__ scale, const float* __restrict__ shift,
+                             __nv_bfloat16* __restrict__ ymax) {
     const int cvb = blockIdx.x % ncvb, wb = blockIdx.x / ncvb;
     const int cv = cvb * 16 + (int)threadIdx.x;
     const int wo = wb * 16 + (int)threadIdx.y;
@@ -1170,6 +1178,15 @@ maxpool3x3s2_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16*
     const int n = blockIdx.y / hblocks;
     const int h0 = (blockIdx.y % hblocks) * kMpRowsF;
     const int wi0 = wo * 2 - pad_l;
+    uint32_t sgn[4] = {0u, 0u, 0u, 0u};
+    float sc[8], sh[8];
+    if (AFFINE) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            sc[k] = __ldg(scale + c0 + k); sh[k] = __ldg(shift + c0 + k);
+            if (sc[k] < 0.f) sgn[k >> 1] |= (k & 1) ? 0x80000000u : 0x00008000u;
+        }
+    }
     for (int ho = h0; ho < min(h0 + kMpRowsF, Ho); ++ho) {
         uint32_t best[4], arg[4];
 #pragma unroll
@@ -1184,7 +1201,7 @@ maxpool3x3s2_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16*
                 const int wi = wi0 + j;
                 if (wi < 0 || wi >= W) continue;
                 const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + rowoff + wi * C));
-                const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+                const uint32_t vv[4] = {v.x ^ sgn[0], v.y ^ sgn[1], v.z ^ sgn[2], v.w ^ sgn[3]};
                 const uint32_t tap2 = (uint32_t)(i * 3 + j) * 0x00010001u;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -1202,7 +1219,24 @@ maxpool3x3s2_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16*
             pk.y = __byte_perm(arg[2], arg[3], 0x6420);
             *reinterpret_cast<uint2*>(argmax + off) = pk;
         }
-        if (addend != nullptr) {
+        if (AFFINE) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) best[k] ^= sgn[k];                 // back to the raw winner
+            *reinterpret_cast<uint4*>(ymax + off) = make_uint4(best[0], best[1], best[2], best[3]);
+            uint32_t av[4] = {0u, 0u, 0u, 0u};
+            if (addend != nullptr) {
+                const uint4 a = __ldg(reinterpret_cast<const uint4*>(addend + off));
+                av[0] = a.x; av[1] = a.y; av[2] = a.z; av[3] = a.w;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 p = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&best[k]));
+                const float2 q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&av[k]));
+                const __nv_bfloat162 r = __floats2bfloat162_rn(fmaf(p.x, sc[2 * k], sh[2 * k]) + q.x,
+                                                               fmaf(p.y, sc[2 * k + 1], sh[2 * k + 1]) + q.y);
+                best[k] = *reinterpret_cast<const uint32_t*>(&r);
+            }
+        } else if (addend != nullptr) {
             const uint4 a = __ldg(reinterpret_cast<const uint4*>(addend + off));
             const uint32_t av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
@@ -1228,9 +1262,9 @@ extern "C" int dlv3p_maxpool3x3s2_fwd(const void* x, void* y, uint8_t* argmax, i
     if (dtype == DLV3P_BF16 && (addend == nullptr || aligned16(addend)) && (argmax == nullptr || aligned16(argmax)) &&
         (long long)N * cdiv(Ho, kMpRowsF) <= 65535 && (long long)N * H * W * C < 0x7fffffffLL) {
         const int ncvb = cdiv(C / 8, 16);
-        maxpool3x3s2_fwd_bf16_kernel<<<dim3(ncvb * cdiv(Wo, 16), N * cdiv(Ho, kMpRowsF)), dim3(16, 16), 0, st>>>(
+        maxpool3x3s2_fwd_bf16_kernel<false><<<dim3(ncvb * cdiv(Wo, 16), N * cdiv(Ho, kMpRowsF)), dim3(16, 16), 0, st>>>(
             (const __nv_bfloat16*)x, (__nv_bfloat16*)y, argmax, N, H, W, C, pad_t, pad_l, Ho, Wo,
-            (const __nv_bfloat16*)addend, ncvb);
+            (const __nv_bfloat16*)addend, ncvb, nullptr, nullptr, nullptr);
         return check_launch("maxpool3x3s2_fwd");
     }
     DLV3P_DISPATCH_DTYPE(dtype, T, {
@@ -1239,6 +1273,23 @@ extern "C" int dlv3p_maxpool3x3s2_fwd(const void* x, void* y, uint8_t* argmax, i
         return check_launch("maxpool_fwd");
     });
     return 0;
+}
+
+extern "C" int dlv3p_maxpool3x3s2_bn_fwd(const void* x, const float* scale, const float* shift, void* y, void* ymax,
+                                         uint8_t* argmax, int N, int H, int W, int C, int pad_t, int pad_l, int Ho,
+                                         int Wo, const void* addend, int dtype, void* stream) {
+    DLV3P_REQUIRE(x && scale && shift && y && ymax && argmax && N > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0, DLV3P_ERR_SHAPE,
+                  "maxpool_bn_fwd: bad arguments");
+    DLV3P_REQUIRE(dtype == DLV3P_BF16, DLV3P_ERR_DTYPE, "maxpool_bn_fwd: bf16 only (use bn_train_apply + maxpool3x3s2_fwd)");
+    DLV3P_REQUIRE(C % 8 == 0 && aligned16(x) && aligned16(y) && aligned16(ymax) && aligned16(argmax) &&
+                  (addend == nullptr || aligned16(addend)), DLV3P_ERR_ALIGN, "maxpool_bn_fwd: C %% 8 and alignment");
+    DLV3P_REQUIRE((long long)N * cdiv(Ho, kMpRowsF) <= 65535 && (long long)N * H * W * C < 0x7fffffffLL, DLV3P_ERR_UNSUPPORTED,
+                  "maxpool_bn_fwd: tensor too large for the 32-bit kernel");
+    const int ncvb = cdiv(C / 8, 16);
+    maxpool3x3s2_fwd_bf16_kernel<true><<<dim3(ncvb * cdiv(Wo, 16), N * cdiv(Ho, kMpRowsF)), dim3(16, 16), 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, argmax, N, H, W, C, pad_t, pad_l, Ho, Wo, (const __nv_bfloat16*)addend, ncvb,
+        scale, shift, (__nv_bfloat16*)ymax);
+    return check_launch("maxpool3x3s2_bn_fwd");
 }
 
 namespace dlv3p {
@@ -1252,10 +1303,17 @@ constexpr int kMpRows = 4;          // 2x2 pixel blocks walked by one thread alo
 // One thread owns 8 channels of a 2x2 block of input pixels {2a, 2a+1} x {2b, 2b+1} (in padded coordinates): the block
 // touches only the windows {a-1, a} x {b-1, b}, so four (argmax, dy) loads serve four output pixels and nine
 // (pixel, window) pairs — the pixel-per-thread version issued up to four loads per pixel.
+// BN: the pooled tensor was max(scale*y+shift) of a training-mode BatchNormalization (maxpool3x3s2_fwd_bf16_kernel
+// <AFFINE>): the routed gradient g is not written; the kernel reads the raw conv output y of the same pixels and writes
+// the BatchNormalization input gradient  scale*(g - red0/M - xhat*red1/M) = scale*g + y*A + B  directly.
+template <bool BN>
 __global__ void __launch_bounds__(256)
 maxpool3x3s2_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ argmax,
                              __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int pad_t, int pad_l, int Ho,
-                             int Wo, const __nv_bfloat16* __restrict__ addend, int ncvb) {
+                             int Wo, const __nv_bfloat16* __restrict__ addend, int ncvb,
+                             const __nv_bfloat16* __restrict__ yraw, const float* __restrict__ scale,
+                             const float* __restrict__ mean, const float* __restrict__ invstd,
+                             const float* __restrict__ red, float inv_count) {
     // block = 16 channel-packs x 16 column pairs; grid.x = (channel-pack block, column block), grid.y = (image, row
     // block).  All index arithmetic is 32-bit and the only divisions are per-block (uniform).
     const int cvb = blockIdx.x % ncvb, wb = blockIdx.x / ncvb;
@@ -1270,6 +1328,16 @@ maxpool3x3s2_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t
     const int a0 = (blockIdx.y % hblocks) * kMpRows;
     const int img = n * Ho;
     const __nv_bfloat162 zero2 = __float2bfloat162_rn(0.f);
+    float bsc[8], bA[8], bB[8];
+    if (BN) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            bsc[k] = __ldg(scale + c0 + k);
+            const float t = bsc[k] * __ldg(invstd + c0 + k) * __ldg(red + C + c0 + k) * inv_count;
+            bA[k] = -t;
+            bB[k] = -bsc[k] * __ldg(red + c0 + k) * inv_count + __ldg(mean + c0 + k) * t;
+        }
+    }
     for (int a2 = a0; a2 < min(a0 + kMpRows, PH); ++a2) {
         // windows (a2-1+u, b2-1+v), u,v in {0,1}
         uint2 pk[2][2]; uint4 g[2][2];
@@ -1310,6 +1378,17 @@ maxpool3x3s2_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t
                     }
                 }
                 const int off = ((n * H + hi) * W + wi) * C + c0;
+                if (BN) {
+                    const uint4 yv = __ldg(reinterpret_cast<const uint4*>(yraw + off));
+                    const uint32_t yy[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 g2 = __bfloat1622float2(acc[k]);
+                        const float2 y2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yy[k]));
+                        acc[k] = __floats2bfloat162_rn(fmaf(bsc[2 * k], g2.x, fmaf(y2.x, bA[2 * k], bB[2 * k])),
+                                                       fmaf(bsc[2 * k + 1], g2.y, fmaf(y2.y, bA[2 * k + 1], bB[2 * k + 1])));
+                    }
+                }
                 if (addend != nullptr) {
                     const uint4 ad = __ldg(reinterpret_cast<const uint4*>(addend + off));
                     const uint32_t av[4] = {ad.x, ad.y, ad.z, ad.w};
@@ -1404,9 +1483,9 @@ extern "C" int dlv3p_maxpool3x3s2_bwd(const void* dy, const uint8_t* argmax, voi
         (long long)N * H * W * C < 0x7fffffffLL) {
         const int ncvb = cdiv(C / 8, 16);
         const int PWp = (W + pad_l + 1) / 2, PHp = (H + pad_t + 1) / 2;
-        maxpool3x3s2_bwd_bf16_kernel<<<dim3(ncvb * cdiv(PWp, 16), N * cdiv(PHp, kMpRows)), dim3(16, 16), 0, st>>>(
+        maxpool3x3s2_bwd_bf16_kernel<false><<<dim3(ncvb * cdiv(PWp, 16), N * cdiv(PHp, kMpRows)), dim3(16, 16), 0, st>>>(
             (const __nv_bfloat16*)dy, argmax, (__nv_bfloat16*)dx, N, H, W, C, pad_t, pad_l, Ho, Wo,
-            (const __nv_bfloat16*)addend, ncvb);
+            (const __nv_bfloat16*)addend, ncvb, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f);
         return check_launch("maxpool3x3s2_bwd");
     }
     DLV3P_DISPATCH_DTYPE(dtype, T, {
@@ -1415,6 +1494,25 @@ extern "C" int dlv3p_maxpool3x3s2_bwd(const void* dy, const uint8_t* argmax, voi
         return check_launch("maxpool_bwd");
     });
     return 0;
+}
+
+extern "C" int dlv3p_maxpool3x3s2_bn_bwd(const void* dy, const uint8_t* argmax, const void* yraw, const float* scale,
+                                         const float* mean, const float* invstd, const float* red, double count,
+                                         void* dx, int N, int H, int W, int C, int pad_t, int pad_l, int Ho, int Wo,
+                                         int dtype, void* stream) {
+    DLV3P_REQUIRE(dy && argmax && yraw && scale && mean && invstd && red && dx && N > 0 && count > 0, DLV3P_ERR_SHAPE,
+                  "maxpool_bn_bwd: bad arguments");
+    DLV3P_REQUIRE(dtype == DLV3P_BF16, DLV3P_ERR_DTYPE, "maxpool_bn_bwd: bf16 only (use maxpool3x3s2_bwd + bn_bwd_*)");
+    DLV3P_REQUIRE(C % 8 == 0 && aligned16(dy) && aligned16(dx) && aligned16(yraw) && aligned16(argmax), DLV3P_ERR_ALIGN,
+                  "maxpool_bn_bwd: C %% 8 and alignment");
+    DLV3P_REQUIRE((long long)N * H <= 65535 && (long long)N * H * W * C < 0x7fffffffLL, DLV3P_ERR_UNSUPPORTED,
+                  "maxpool_bn_bwd: tensor too large for the 32-bit kernel");
+    const int ncvb = cdiv(C / 8, 16);
+    const int PWp = (W + pad_l + 1) / 2, PHp = (H + pad_t + 1) / 2;
+    maxpool3x3s2_bwd_bf16_kernel<true><<<dim3(ncvb * cdiv(PWp, 16), N * cdiv(PHp, kMpRows)), dim3(16, 16), 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dy, argmax, (__nv_bfloat16*)dx, N, H, W, C, pad_t, pad_l, Ho, Wo, nullptr, ncvb,
+        (const __nv_bfloat16*)yraw, scale, mean, invstd, red, (float)(1.0 / count));
+    return check_launch("maxpool3x3s2_bn_bwd");
 }
 
 extern "C" int dlv3p_avgpool_fwd(const void* x, void* y, int N, int H, int W, int C, int k, int Ho, int Wo,

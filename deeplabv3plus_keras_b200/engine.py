@@ -214,7 +214,8 @@ class Plan:
 
     def __init__(self, model: Model, batch_size: int, training: bool = False, dtype: Optional[str] = None,
                  device: Optional[str] = None, dropout_seed: int = 1024, fused_tail: bool = True,
-                 fuse_bn_dw: bool = True, implicit_conv: bool = True, concat_in_place: bool = True):
+                 fuse_bn_dw: bool = True, implicit_conv: bool = True, concat_in_place: bool = True,
+                 fuse_bn_pool: bool = True):
         fake = getattr(ops, "FAKE", False)       # tests/fake_ops.py test double (host-logic tests without a GPU)
         if not torch.cuda.is_available() and not fake:
             raise RuntimeError("engine.Plan needs a CUDA device: there is no CPU execution path")
@@ -227,6 +228,7 @@ class Plan:
         self.bf16 = self.dt == torch.bfloat16
         self.fused_tail = fused_tail
         self.fuse_bn_dw = fuse_bn_dw        # Conv->BN->ReLU->depthwise: BN+ReLU applied on load (False: A/B, materialise it)
+        self.fuse_bn_pool = fuse_bn_pool         # Conv->BN->MaxPooling2D: BN applied inside the pool, fused backward
         self.concat_in_place = concat_in_place   # Conv->BN(->ReLU) read only by a Concatenate writes its slice directly
         self.implicit_conv = implicit_conv  # dense 3x3 VALID stride-1 convs as implicit GEMMs (False: A/B, im2col + GEMM)
         self.dropout_seed = dropout_seed
@@ -384,6 +386,8 @@ class Plan:
                                 and nxt.layer.strides[0] == 1 and tuple(nxt.layer.dilation_rate) == (1, 1)
                                 and nxt.layer.padding == "same"):
                             m["virt"] = True
+                    elif nxt is not None and isinstance(nxt.layer, L.MaxPooling2D):
+                        m["pool_virt"] = True        # Conv -> BN -> MaxPooling2D: BN applied inside the pool (see _BnPoolValue)
                     elif nxt is not None and isinstance(nxt.layer, L.Add) and not nxt.absorbed:
                         other = [i for i in nxt.inputs if i != m["out"]]
                         if len(other) == 1:
@@ -497,11 +501,17 @@ class Plan:
         ld_out = Cout
         virt = (bool(m.get("virt")) and self.fuse_bn_dw and training and bn_node is not None and act != ACT_NONE
                 and other_id is None and m["out"] != out_id and Cout % 8 == 0)
+        gemm_like = not is_dw
         slot_c = self._concat_slot.get(m["out"])
         in_place = (slot_c is not None and not virt and training and bn_node is not None and other_id is None
                     and Cout % 8 == 0 and Cout == Cout_log and y_dtype == self.dt)
+        pool_virt = (bool(m.get("pool_virt")) and self.fuse_bn_pool and (self.bf16 or FORCE_BNRED) and training
+                     and bn_node is not None and act == ACT_NONE and other_id is None and m["out"] != out_id
+                     and Cout % 8 == 0 and gemm_like)
         if virt:
             out = _BnActValue(out_shape, y_dtype, lay.name, act)       # buffers / BN operands attached below
+        elif pool_virt:
+            out = _BnPoolValue(out_shape, y_dtype, lay.name)
         elif in_place:
             cid, c_off, Ct = slot_c
             if cid not in self._concat_buf:
@@ -574,6 +584,8 @@ class Plan:
                 y = self._alloc((N, Ho, Wo, Cout), self.dt)          # raw conv output, saved for backward
                 if virt:
                     out.attach(y, scale, shift, mean, invstd, red_slot)
+                if pool_virt:
+                    out.attach(y, scale, shift, mean, invstd, red_slot, Mo)
             else:
                 self.prep.append(lambda: ops.bn_fold(gamma, beta, mm, mv, C, bn.epsilon, scale, shift))
                 y = None
@@ -655,8 +667,8 @@ class Plan:
                 # (dlv3p_dwconv3x3_bn_fwd): nothing to launch here
                 out.bn_fold = dict(sums=stat, gamma=gamma, beta=beta, mm=mm, mv=mv, count=Mo, eps=bn.epsilon,
                                    momentum=bn.momentum, updates=upd)
-            elif virt:
-                # statistics -> scale/shift (+ moving statistics); the BN+ReLU map itself runs inside the reader
+            elif virt or pool_virt:
+                # statistics -> scale/shift (+ moving statistics); the BN (+ReLU) map itself runs inside the reader
                 for r in range(upd):
                     self.fwd.append(lambda r=r: ops.bn_finalize(stat(), gamma, beta, mm, mv, Cout, Mo, bn.epsilon,
                                                                 bn.momentum, scale, shift, mean, invstd, True))
@@ -683,7 +695,7 @@ class Plan:
 
         # ---- backward (emitted in forward order; the list is reversed at the end, so write steps in REVERSE) --
         def sched():
-            g = self._final_grad(out)
+            g = out.pool_bwd["g"] if pool_virt else self._final_grad(out)
             if g is None:
                 raise RuntimeError(f"no gradient reaches {lay.name}")
             if other is not None:
@@ -698,12 +710,22 @@ class Plan:
                 # virtual BN+ReLU output: g arrives as the gradient w.r.t. the BN output, ReLU mask already applied
                 # by the reader's input-gradient kernel (which may also have produced the two reductions)
                 act_b = ACT_NONE if virt else act
+                if pool_virt:
+                    # the BN output fed a MaxPooling2D directly: reductions over the POOLED tensors (gradient x raw
+                    # winner values), then pool backward + BN input gradient in one pass straight into dy
+                    pb = out.pool_bwd
+                    Mp = g.shape[0] * g.shape[1] * g.shape[2]
+                    self.bwd_seq(lambda: ops.bn_bwd_reduce(g, pb["ymax"], scale, shift, mean, invstd, ACT_NONE, Mp, Cout,
+                                                           red()))
+                    self.bwd_seq(lambda: ops.maxpool3x3s2_bn_bwd(g, pb["argmax"], y, scale, mean, invstd, red(), Mo,
+                                                                 dy_get().view(N, Ho, Wo, Cout)))
                 ld_g = g.stride(0) if g.dim() == 2 else Cout          # 2-D: a channel slice of a concat gradient
-                if not (virt and out.red_done):
+                if not pool_virt and not (virt and out.red_done):
                     self.bwd_seq(lambda: ops.bn_bwd_reduce(g, y, scale, shift, mean, invstd, act_b, Mo, Cout, red(),
                                                            ld_dz=ld_g))
-                self.bwd_seq(lambda: ops.bn_bwd_apply(g, y, scale, shift, mean, invstd, act_b, red(), Mo, Cout,
-                                                      dy_get(), ld_dz=ld_g))
+                if not pool_virt:
+                    self.bwd_seq(lambda: ops.bn_bwd_apply(g, y, scale, shift, mean, invstd, act_b, red(), Mo, Cout,
+                                                          dy_get(), ld_dz=ld_g))
                 # parameter gradients live in the stats arena; copy into the grad arena
                 if beta is not None and not red_direct:
                     gb = P.view(bn, "beta", grad=True)
@@ -879,7 +901,10 @@ class Plan:
     # ---- other ops ---------------------------------------------------------------------------------------
     def _emit_maxpool(self, m: dict):
         n = m["node"]
-        x = self._input_of(n.inputs[0], False)
+        x = self.values[n.inputs[0]]
+        fused_bn = isinstance(x, _BnPoolValue)
+        if not fused_bn:
+            x = self._input_of(n.inputs[0], False)
         N, H, W, C = x.shape
         Ho, Wo = -(-H // 2), -(-W // 2)
         out = Value((N, Ho, Wo, C), self.dt, self._alloc((N, Ho, Wo, C), self.dt), n.layer.name)
@@ -889,7 +914,12 @@ class Plan:
         self.values[m["out"]] = out
         out.needs_grad = self.training
         addend = other.buf if other is not None else None
-        self.fwd.append(lambda: ops.maxpool3x3s2_fwd(x.buf, out=out.buf, argmax=am, addend=addend))
+        if fused_bn:
+            ymax = self._alloc((N, Ho, Wo, C), self.dt)        # raw conv output of every window's winner
+            self.fwd.append(lambda: ops.maxpool3x3s2_bn_fwd(x.buf, x.bn_scale, x.bn_shift, out.buf, ymax, am,
+                                                            addend=addend))
+        else:
+            self.fwd.append(lambda: ops.maxpool3x3s2_fwd(x.buf, out=out.buf, argmax=am, addend=addend))
         self.launches_fwd += 1
         if not self.training:
             return
@@ -898,6 +928,9 @@ class Plan:
             g = self._final_grad(out)
             if other is not None:
                 other.pending.append(g)
+            if fused_bn:
+                x.pool_bwd = dict(g=g, argmax=am, ymax=ymax)   # consumed by the producing conv's backward
+                return
             if x.needs_grad:
                 tgt, add2 = self._grad_target(x)
                 self.bwd_seq(lambda: ops.maxpool3x3s2_bwd(g, am, x.shape, addend=add2, out=tgt))
@@ -1283,6 +1316,22 @@ class _BnActValue(Value):
     def attach(self, y, scale, shift, mean, invstd, red_slot):
         self.buf, self.pre_scale, self.pre_shift = y, scale, shift
         self.bn_mean, self.bn_invstd, self.bn_red = mean, invstd, red_slot
+
+
+class _BnPoolValue(Value):
+    """`scale * y + shift` for the raw conv output y of a training-mode Conv -> BatchNormalization whose only reader is
+    a MaxPooling2D(3, strides 2).  Never written: dlv3p_maxpool3x3s2_bn_fwd pools it on the fly (and keeps the raw
+    winner values), the pool's backward hands its pooled gradient to the producer (`pool_bwd`), whose backward runs
+    the BN reductions on the pooled tensors and dlv3p_maxpool3x3s2_bn_bwd (pool backward + BN input gradient)."""
+
+    def __init__(self, shape, dtype, name):
+        super().__init__(shape, dtype, None, name + "/bn_pool")
+        self.pre_act = -1                   # no consumer but the fused pool may read it
+        self.pool_bwd = None
+
+    def attach(self, y, scale, shift, mean, invstd, red_slot, count):
+        self.buf, self.bn_scale, self.bn_shift = y, scale, shift
+        self.bn_mean, self.bn_invstd, self.bn_red, self.bn_count = mean, invstd, red_slot, count
 
 
 FORCE_IMPLICIT = False  # tests: take the implicit-GEMM 3x3 schedule in fp32 too (through tests/fake_ops.py)

@@ -328,6 +328,28 @@ def maxpool3x3s2_bwd(dy: Tensor, argmax: Tensor, x_shape, addend=None, out: Opti
     return out
 
 
+def maxpool3x3s2_bn_fwd(x: Tensor, scale: Tensor, shift: Tensor, out: Tensor, ymax: Tensor, argmax: Tensor, addend=None):
+    """out = maxpool3x3s2(scale*x + shift) (+ addend) without writing the BN output; ymax = raw x of the winners."""
+    _chk(x, "x")
+    N, H, W, Cc = x.shape
+    ho, pt = same_pad(H, 3, 2)
+    wo, pl = same_pad(W, 3, 2)
+    call("dlv3p_maxpool3x3s2_bn_fwd", _p(x), _p(scale), _p(shift), _p(out), _p(ymax), _p(argmax), N, H, W, Cc, pt, pl, ho,
+         wo, _p(addend), _dt(x), _stream())
+    return out
+
+
+def maxpool3x3s2_bn_bwd(dy: Tensor, argmax: Tensor, x: Tensor, scale, mean, invstd, red, count, out: Tensor):
+    """out = BN input gradient of the layer whose raw output x fed maxpool3x3s2_bn_fwd (pool backward + bn_bwd_apply)."""
+    _chk(dy, "dy")
+    N, H, W, Cc = x.shape
+    ho, pt = same_pad(H, 3, 2)
+    wo, pl = same_pad(W, 3, 2)
+    call("dlv3p_maxpool3x3s2_bn_bwd", _p(dy), _p(argmax), _p(x), _p(scale), _p(mean), _p(invstd), _p(red), float(count),
+         _p(out), N, H, W, Cc, pt, pl, ho, wo, _dt(dy), _stream())
+    return out
+
+
 def avgpool_fwd(x: Tensor, k: int, out: Optional[Tensor] = None):
     N, H, W, Cc = x.shape
     ho, wo = H // k, W // k

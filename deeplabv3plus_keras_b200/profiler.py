@@ -61,6 +61,8 @@ COSTS: Dict[str, Tuple[str, Callable]] = {
     "dlv3p_add": ("hbm", lambda a: (3 * a[3] * _esz(a[4]), a[3])),
     "dlv3p_copy2d": ("hbm", lambda a: ((2 + _opt(a[6])) * a[4] * a[5] * _esz(a[8]), 0)),
     "dlv3p_maxpool3x3s2_fwd": ("hbm", lambda a: ((a[3] * a[4] * a[5] * a[6] + a[3] * a[9] * a[10] * a[6] * (1 + _opt(a[11]))) * _esz(a[12]) + a[3] * a[9] * a[10] * a[6] * _opt(a[2]), 0)),
+    "dlv3p_maxpool3x3s2_bn_fwd": ("hbm", lambda a: ((a[6] * a[7] * a[8] * a[9] + a[6] * a[12] * a[13] * a[9] * (2 + _opt(a[14]))) * _esz(a[15]) + a[6] * a[12] * a[13] * a[9], 0)),
+    "dlv3p_maxpool3x3s2_bn_bwd": ("hbm", lambda a: ((a[9] * a[15] * a[16] * a[12] + 2 * a[9] * a[10] * a[11] * a[12]) * _esz(a[17]) + a[9] * a[15] * a[16] * a[12], 0)),
     "dlv3p_maxpool3x3s2_bwd": ("hbm", lambda a: ((a[3] * a[9] * a[10] * a[6] + a[3] * a[4] * a[5] * a[6] * (1 + _opt(a[11]))) * _esz(a[12]) + a[3] * a[9] * a[10] * a[6], 0)),
     "dlv3p_bilinear_fwd": ("hbm", lambda a: (a[4] * a[5] * a[6] * a[7] * (_esz(a[10]) + a[8] * a[9] * _esz(a[11])), 0)),
     "dlv3p_bilinear_bwd": ("hbm", lambda a: (a[4] * a[5] * a[6] * a[7] * (a[8] * a[9] * _esz(a[11]) + _esz(a[12])), 0)),

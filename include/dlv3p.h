@@ -207,6 +207,20 @@ int dlv3p_maxpool3x3s2_fwd(const void* x, void* y, uint8_t* argmax, int N, int H
                            int pad_l, int Ho, int Wo, const void* addend, int dtype, void* stream);
 int dlv3p_maxpool3x3s2_bwd(const void* dy, const uint8_t* argmax, void* dx, int N, int H, int W, int C, int pad_t,
                            int pad_l, int Ho, int Wo, const void* addend, int dtype, void* stream);
+/* MaxPooling2D(3, strides 2, SAME) fused with the training-mode BatchNormalization that feeds it directly (Xception
+ * block2/3/4: sepconv2_bn -> MaxPooling2D -> Add, keras.applications.xception): the BN output is never written.
+ *   fwd: y = maxpool(scale*x + shift) (+ addend), x = raw conv output; argmax as dlv3p_maxpool3x3s2_fwd; ymax = the raw
+ *        x value of every winner (the BN-backward reductions then run on the POOLED tensors:
+ *        dlv3p_bn_bwd_reduce(dz = dy_pool, y = ymax, act NONE, M = N*Ho*Wo)).
+ *   bwd: dx = scale*(g - red[c]/count - xhat*red[C+c]/count) with g = the pooled gradient dy routed through argmax and
+ *        xhat = (x - mean)*invstd — max-pool backward and dlv3p_bn_bwd_apply in one pass, g is never written.
+ * bf16 only; anything else returns an error and the caller uses the separate entry points. */
+int dlv3p_maxpool3x3s2_bn_fwd(const void* x, const float* scale, const float* shift, void* y, void* ymax,
+                              uint8_t* argmax, int N, int H, int W, int C, int pad_t, int pad_l, int Ho, int Wo,
+                              const void* addend, int dtype, void* stream);
+int dlv3p_maxpool3x3s2_bn_bwd(const void* dy, const uint8_t* argmax, const void* x, const float* scale,
+                              const float* mean, const float* invstd, const float* red, double count, void* dx, int N,
+                              int H, int W, int C, int pad_t, int pad_l, int Ho, int Wo, int dtype, void* stream);
 /* AveragePooling2D(pool_size=k, padding='valid') (stride = k), ss.py:842 */
 int dlv3p_avgpool_fwd(const void* x, void* y, int N, int H, int W, int C, int k, int Ho, int Wo, int dtype,
                       void* stream);

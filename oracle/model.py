@@ -125,7 +125,8 @@ def xception_base(ctx: Ctx, img, output_stride: int):
         if first_relu:
             x = T.relu(x)
         x = _cbn(ctx, _sep(ctx, x, f"block{blk}_sepconv1"), f"block{blk}_sepconv1_bn", M, T.relu, virtual=True)
-        x = _cbn(ctx, _sep(ctx, x, f"block{blk}_sepconv2"), f"block{blk}_sepconv2_bn", M)
+        # (feeds the max-pool directly: in training the product pools scale*y+shift on the fly, no rounding point)
+        x = _cbn(ctx, _sep(ctx, x, f"block{blk}_sepconv2"), f"block{blk}_sepconv2_bn", M, virtual=not tap_here)
         if tap_here:
             nm("conv2d"); nm("batch_normalization")       # block13's shortcut layers exist in Keras, pruned here
             return x

@@ -363,6 +363,28 @@ def maxpool3x3s2_fwd(x, out=None, argmax=None, addend=None):
     return out
 
 
+def maxpool3x3s2_bn_fwd(x, scale, shift, out, ymax, argmax, addend=None):
+    z = x.float() * scale + shift
+    maxpool3x3s2_fwd(z, out=out, argmax=argmax, addend=addend)
+    N, H, W, C = x.shape
+    ho, pt = same_pad(H, 3, 2)
+    wo, pl = same_pad(W, 3, 2)
+    xp = F.pad(x.float(), (0, 0, pl, 2, pt, 2))
+    am = argmax.long()
+    n_i, h_i, w_i, c_i = torch.meshgrid(torch.arange(N), torch.arange(ho), torch.arange(wo), torch.arange(C), indexing="ij")
+    ymax.copy_(xp[n_i, h_i * 2 + am // 3, w_i * 2 + am % 3, c_i])
+    return out
+
+
+def maxpool3x3s2_bn_bwd(dy, argmax, x, scale, mean, invstd, red, count, out):
+    Cc = x.shape[3]
+    g = torch.empty(tuple(x.shape), dtype=torch.float32)
+    maxpool3x3s2_bwd(dy, argmax, tuple(x.shape), out=g)
+    xh = (x.float() - mean) * invstd
+    out.copy_(scale * (g - red[:Cc] / count - xh * red[Cc:2 * Cc] / count))
+    return out
+
+
 def maxpool3x3s2_bwd(dy, argmax, x_shape, addend=None, out=None):
     N, H, W, C = x_shape
     ho, pt = same_pad(H, 3, 2)

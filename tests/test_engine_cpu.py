@@ -151,6 +151,44 @@ def test_concat_slices_written_in_place(cpu_engine, monkeypatch):
         assert np.abs(ga[k] - gb[k]).max() <= 1e-4 * scale, k
 
 
+def test_bn_fused_into_maxpool_schedule(cpu_engine, monkeypatch):
+    """Conv -> BN -> MaxPooling2D (Xception block2/3/4): the BN output is virtual, the pool applies scale/shift on the fly
+    and keeps the raw winners, the producer's backward reduces over the pooled tensors and runs pool backward + BN input
+    gradient in one launch.  Must reproduce the materialised schedule."""
+    monkeypatch.setattr(cpu_engine, "FORCE_BNRED", True)
+    conf = util.make_conf(width=64, base="xception", output_stride=16, image_size=65)
+    ss = util.build(conf)
+    util.randomize_weights(ss.model)
+    calls = []
+    for name in ("maxpool3x3s2_bn_fwd", "maxpool3x3s2_bn_bwd", "maxpool3x3s2_fwd", "maxpool3x3s2_bwd"):
+        orig = getattr(fake_ops, name)
+        monkeypatch.setattr(fake_ops, name, (lambda orig, name: lambda *a, **k: (calls.append(name), orig(*a, **k))[1])(orig, name))
+    plans = {}
+    for flag in (True, False):
+        calls.clear()
+        plan = cpu_engine.Plan(ss.model, 2, training=True, fuse_bn_pool=flag)
+        x, y = util.synthetic_batch(conf, 2, plan.out_shape[1:3])
+        plan.set_loss(PW, NW)
+        plan.load_batch(x, y)
+        plan.step_fwd_bwd()
+        plans[flag] = (plan, list(calls))
+    assert plans[True][1].count("maxpool3x3s2_bn_fwd") == 3 and plans[True][1].count("maxpool3x3s2_bn_bwd") == 3
+    assert "maxpool3x3s2_bn_fwd" not in plans[False][1] and plans[False][1].count("maxpool3x3s2_bwd") == 3
+    a, b = plans[True][0], plans[False][0]
+    np.testing.assert_allclose(a.logits.buf.numpy(), b.logits.buf.numpy(), rtol=1e-4, atol=1e-5)
+    assert abs(a.loss_value() - b.loss_value()) < 1e-5
+    ga, gb = a.gradients(), b.gradients()
+    for k in gb:
+        scale = max(np.abs(gb[k]).max(), 1e-3)
+        assert np.abs(ga[k] - gb[k]).max() <= 2e-3 * scale, k
+    a.params.download()
+    sa = {k: v.copy() for k, v in ss.model.named_weights().items() if "moving" in k}
+    b.params.download()
+    for k, v in ss.model.named_weights().items():
+        if "moving" in k:
+            np.testing.assert_allclose(sa[k], v, rtol=1e-5, atol=1e-6, err_msg=k)
+
+
 def test_implicit_conv_schedule(cpu_engine, monkeypatch):
     """Xception block1_conv2 (3x3 VALID stride 1, 32 -> 64): the implicit-GEMM schedule (no im2col / col2im, prepared
     wk / wd filter matrices) must reproduce the im2col + GEMM schedule."""

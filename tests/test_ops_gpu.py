@@ -243,6 +243,69 @@ def test_dwconv3x3_bn_fwd_equals_finalize_plus_conv(case, updates):
     assert (got.float() != want.float()).float().mean().item() < 1e-2
 
 
+@pytest.mark.parametrize("case", [(2, 30, 31, 64), (1, 64, 64, 736), (2, 127, 127, 256), (1, 7, 9, 8)])
+@pytest.mark.parametrize("with_add", [False, True])
+def test_maxpool_bn_fused_fwd_bwd(case, with_add):
+    """MaxPooling2D(3, s2, SAME) fused with the BatchNormalization that feeds it: forward == maxpool(scale*x+shift)
+    (+addend) with the raw winner values kept; backward == max-pool backward followed by bn_bwd_apply, in one pass.
+    Negative scales exercise the sign-flipped compares."""
+    o = ops()
+    N, H, W, C = case
+    bf = torch.bfloat16
+    x = rnd((N, H, W, C), bf, 1, 1.5)
+    sc = rnd((C,), torch.float32, 3, 0.7) + 0.3                    # a good share of negative scales
+    sh = rnd((C,), torch.float32, 4, 0.3)
+    ho, pt = o.same_pad(H, 3, 2)
+    wo, pl = o.same_pad(W, 3, 2)
+    add = rnd((N, ho, wo, C), bf, 6) if with_add else None
+    z = x.double() * sc.double() + sh.double()                      # fp64 BN output (never rounded in the fused path)
+    zp = torch.nn.functional.pad(z.permute(0, 3, 1, 2), (pl, 2, pt, 2), value=float("-inf"))
+    win = zp.unfold(2, 3, 2).unfold(3, 3, 2)[:, :, :ho, :wo].reshape(N, C, ho, wo, 9)
+    val, idx = win.max(dim=-1)
+    want = val.permute(0, 2, 3, 1) + (add.double() if with_add else 0.0)
+
+    y = torch.empty((N, ho, wo, C), dtype=bf, device=DEV)
+    ymax = torch.empty_like(y)
+    am = torch.empty((N, ho, wo, C), dtype=torch.uint8, device=DEV)
+    o.maxpool3x3s2_bn_fwd(x.to(DEV), sc.to(DEV), sh.to(DEV), y, ymax, am, addend=add.to(DEV) if with_add else None)
+    check("maxpool_bn fwd", y, want, 1e-2, 1e-2)
+    # the stored winner is the raw x under the stored argmax, and BN of it is the pooled value
+    xp = torch.nn.functional.pad(x.float(), (0, 0, pl, 2, pt, 2))
+    n_i, h_i, w_i, c_i = torch.meshgrid(torch.arange(N), torch.arange(ho), torch.arange(wo), torch.arange(C), indexing="ij")
+    amc = am.cpu().long()
+    assert torch.equal(ymax.float().cpu(), xp[n_i, h_i * 2 + amc // 3, w_i * 2 + amc % 3, c_i])
+    check("maxpool_bn ymax->value", ymax.double().cpu() * sc.double() + sh.double(), val.permute(0, 2, 3, 1), 1e-6, 1e-6)
+
+    # backward against the fp64 restatement on the same argmax: the pooled reductions are EXACT sums of the window
+    # gradients (the two-step path first rounds the routed gradient to bf16), then pool backward + BN input gradient
+    gy = rnd((N, ho, wo, C), bf, 5)
+    mean, invstd = rnd((C,), torch.float32, 7, 0.3), rnd((C,), torch.float32, 8, 0.1).abs() + 0.6
+    M = N * H * W
+    ymc = ymax.double().cpu()
+    red_ref = torch.cat([gy.double().sum((0, 1, 2)),
+                         (gy.double() * (ymc - mean.double()) * invstd.double()).sum((0, 1, 2))])
+    red = torch.zeros(2 * C, dtype=torch.float32, device=DEV)
+    o.bn_bwd_reduce(gy.to(DEV), ymax, sc.to(DEV), sh.to(DEV), mean.to(DEV), invstd.to(DEV), o.ACT_NONE, N * ho * wo, C, red)
+    check("pooled reductions", red, red_ref, 2e-3, 2e-3 * math.sqrt(N * ho * wo))
+    g64 = torch.zeros((N, H + 4, W + 4, C), dtype=torch.float64)
+    g64.index_put_((n_i, h_i * 2 - pt + amc // 3 + 2, w_i * 2 - pl + amc % 3 + 2, c_i), gy.double(), accumulate=True)
+    g64 = g64[:, 2:2 + H, 2:2 + W]
+    xh = (x.double() - mean.double()) * invstd.double()
+    r64 = red.double().cpu()
+    dy_ref = sc.double() * (g64 - r64[:C] / M - xh * r64[C:] / M)
+    dy = torch.empty((N, H, W, C), dtype=bf, device=DEV)
+    o.maxpool3x3s2_bn_bwd(gy.to(DEV), am, x.to(DEV), sc.to(DEV), mean.to(DEV), invstd.to(DEV), red, M, dy)
+    # a pixel that wins several windows sums their gradients in packed bf16 before the BN map (as dlv3p_maxpool3x3s2_bwd
+    # does): when terms of opposite sign cancel, the error is a bf16 ulp of the TERMS, not of the small result
+    err = (dy.double().cpu() - dy_ref).abs()
+    bound = 2e-2 + 2e-2 * dy_ref.abs()
+    assert (err > bound).double().mean().item() < 1e-5, float((err > bound).double().mean())
+    assert err.max().item() < 2.0 ** -6 * float(gy.abs().max()) * float(sc.abs().max()) * 4 + 2e-2, float(err.max())
+    with pytest.raises(ValueError):
+        o.maxpool3x3s2_bn_bwd(gy.float().to(DEV), am, x.float().to(DEV), sc.to(DEV), mean.to(DEV), invstd.to(DEV), red, M,
+                              dy.float())                                   # fp32: separate entry points only
+
+
 GEMM_CASES = [
     # M, N, K
     (128, 32, 64),
