@@ -124,9 +124,17 @@ class ParamStore:
     """Flat fp32 arenas: trainable weights (L2-regularised kernels first), their gradients and Adam moments, and
     the non-trainable BatchNormalization moving statistics."""
 
-    def __init__(self, layers_in_order: List[Layer], device, phys=phys_channels):
+    def __init__(self, layers_in_order: List[Layer], device, phys=phys_channels, no_pad=frozenset()):
         self.device = device
         self.phys = phys
+        self.no_pad = frozenset(no_pad)   # channel counts kept at their logical pitch (a property of the graph)
+        # ONE store per (model, device), shared by every Plan of the model (training / inference, any batch size):
+        # `version` counts device-side weight changes so that each plan knows when its derived operands (bf16 copies,
+        # folded BN) are stale; `host_stale` = the device holds newer weights than the layers' host arrays (after an
+        # optimizer step); `dev_stale` = the host arrays are newer (after set_weights / load).
+        self.version = 0
+        self.host_stale = False
+        self.dev_stale = False
         self.entries: Dict[Tuple[int, str], Tuple[str, int, Tuple]] = {}
         reg, plain, frozen = [], [], []
         for l in layers_in_order:
@@ -175,18 +183,43 @@ class ParamStore:
         self.v = torch.zeros_like(self.w)
         self.f = torch.zeros(max(self.n_frozen, 8), dtype=torch.float32, device=device)
         self.num_params = int(sum(w.size for _, n, w in reg + plain))
+        self.step_counter = torch.zeros(1, dtype=torch.int64, device=device)    # dropout stream position
+        for l in layers_in_order:
+            l._stores.append(self)
 
-    def view(self, layer: Layer, name: str, grad=False) -> torch.Tensor:
-        """Contiguous view in the PHYSICAL (channel-padded) shape — what the kernels see."""
+    def view(self, layer: Layer, name: str, grad=False, arena: Optional[str] = None) -> torch.Tensor:
+        """Contiguous view in the PHYSICAL (channel-padded) shape — what the kernels see.  `arena`: "w" weights,
+        "g" gradients, "m" / "v" Adam moments (trainable parameters only)."""
         kind, off, shape = self.entries[(id(layer), name)]
         n = int(np.prod(shape))
-        arena = (self.g if grad else self.w) if kind == "w" else self.f
-        return arena[off:off + n].view(shape)
+        if kind == "w":
+            buf = {"w": self.w, "g": self.g, "m": self.m, "v": self.v}[arena or ("g" if grad else "w")]
+        else:
+            buf = self.f
+        return buf[off:off + n].view(shape)
 
-    def logical(self, layer: Layer, name: str, grad=False) -> torch.Tensor:
+    def logical(self, layer: Layer, name: str, grad=False, arena: Optional[str] = None) -> torch.Tensor:
         """The Keras-shaped part of a parameter (pad channels sliced away)."""
-        v = self.view(layer, name, grad)
+        v = self.view(layer, name, grad, arena)
         return v[tuple(slice(0, d) for d in layer._weights[name].shape)]
+
+    def trainable_items(self):
+        """(layer, weight name) of every trainable parameter, arena order."""
+        return [(l, n) for l, n, _ in self._items if self.entries[(id(l), n)][0] == "w"]
+
+    def mark_updated(self):
+        """The device weights were changed by an optimizer step."""
+        self.version += 1
+        self.host_stale = True
+
+    def sync_host(self):
+        """Bring the layers' host arrays up to date with the device (get_weights / save after training)."""
+        if self.host_stale:
+            self.download()
+
+    def sync_device(self):
+        if self.dev_stale:
+            self.upload()
 
     def has(self, layer: Layer, name: str) -> bool:
         return (id(layer), name) in self.entries
@@ -200,6 +233,8 @@ class ParamStore:
             dst[tuple(slice(0, d) for d in w.shape)] = w        # pad channels stay zero
         self.w.copy_(torch.from_numpy(host_w))
         self.f.copy_(torch.from_numpy(host_f))
+        self.version += 1
+        self.host_stale = self.dev_stale = False
 
     def download(self):
         host_w, host_f = self.w.cpu().numpy(), self.f.cpu().numpy()
@@ -207,6 +242,7 @@ class ParamStore:
             kind, off, pshape = self.entries[(id(l), n)]
             src = (host_w if kind == "w" else host_f)[off:off + int(np.prod(pshape))].reshape(pshape)
             w[...] = src[tuple(slice(0, d) for d in w.shape)]
+        self.host_stale = False
 
 
 class Plan:
@@ -245,7 +281,6 @@ class Plan:
         self._scratch: Dict[str, torch.Tensor] = {}
         self._stat_slices: List[Tuple[int, int]] = []
         self._stats_total = 0
-        self.step_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
 
         self.nodes, in_ids, out_ids = flatten(model)
         if len(in_ids) != 1 or len(out_ids) != 1:
@@ -257,9 +292,21 @@ class Plan:
                   if i in shape_of}
         no_pad |= {n.shape[-1] for n in self.nodes if isinstance(n.layer, L.Concatenate)}
         self.phys = lambda c: c if c in no_pad else phys_channels(c)
-        weight_layers = [l for l in model.flat_layers() if l._weights]
-        self.params = ParamStore(weight_layers, self.device, self.phys)
-        self.params.upload()
+        # ONE parameter store per (model, device): weights, gradients, Adam moments and BN moving statistics are shared
+        # by every plan of the model, so predict / get_weights / a plan for another batch size see the trained state
+        store = model._stores_by_device.get(str(self.device))
+        if store is None:
+            weight_layers = [l for l in model.flat_layers() if l._weights]
+            store = ParamStore(weight_layers, self.device, self.phys, no_pad)
+            store.upload()
+            model._stores_by_device[str(self.device)] = store
+            model._apply_pending_optimizer_state()
+        elif store.no_pad != frozenset(no_pad):
+            raise RuntimeError("internal: channel-pitch rule differs between plans of one model")
+        self.params = store
+        self.params.sync_device()
+        self.step_counter = store.step_counter
+        self._prep_version = -1
 
         self.values: Dict[int, Value] = {}
         H, W, Cin = model.inputs[0].shape[1:]
@@ -267,7 +314,7 @@ class Plan:
         self.values[in_ids[0]] = self.x_in
         self._lower(out_ids[0])
         self.stats = torch.zeros(max(self._stats_total, 8), dtype=torch.float32, device=self.device)
-        self.run_prep()
+        self.ensure_current()
         self.graph = None
         self.finalize()
 
@@ -1104,8 +1151,19 @@ class Plan:
 
     # ---------------------------------------------------------------------------------------------- running
     def upload_weights(self):
+        """Host arrays of the layers -> device (after writing into Model.named_weights() arrays in place)."""
         self.params.upload()
-        self.run_prep()
+        self.ensure_current()
+
+    def ensure_current(self):
+        """Derived operands (bf16 GEMM weights, folded inference BN) follow the shared store: re-derive them when
+        another plan's optimizer step, a set_weights or a checkpoint load changed the weights since this plan last
+        ran.  A pure host-side check when nothing changed (safe inside CUDA-graph capture after the warm-up)."""
+        P = self.params
+        P.sync_device()
+        if self._prep_version != P.version:
+            self.run_prep()
+            self._prep_version = P.version
 
     def run_prep(self):
         if self._wprep:
@@ -1140,6 +1198,7 @@ class Plan:
         self.reg_sum.zero_()
 
     def forward(self):
+        self.ensure_current()
         for fn in self.fwd:
             fn()
 
@@ -1193,7 +1252,9 @@ class Plan:
                      0.0, w_off=P.n_reg)
         opt.iterations += 1
         self.step_counter.add_(1)
+        P.mark_updated()
         self.run_prep()
+        self._prep_version = P.version
 
     def loss_value(self) -> float:
         P = self.N * self.out_shape[1] * self.out_shape[2]

@@ -68,6 +68,7 @@ class Layer:
         self._weights: "OrderedDict[str, np.ndarray]" = OrderedDict()
         self._trainable: Dict[str, bool] = {}
         self._nodes: List[Node] = []
+        self._stores: list = []        # engine.ParamStore objects holding this layer's weights on a device
 
     # -- weights -------------------------------------------------------------------------------------
     def add_weight(self, name: str, shape, initializer, trainable: bool = True) -> np.ndarray:
@@ -76,12 +77,19 @@ class Layer:
         self._trainable[name] = trainable
         return w
 
+    def _sync_host(self) -> None:
+        """Device -> host, when an optimizer step has run since the host arrays were last current."""
+        for s in self._stores:
+            s.sync_host()
+
     @property
     def weights(self) -> List[np.ndarray]:
+        self._sync_host()
         return list(self._weights.values())
 
     def get_weights(self) -> List[np.ndarray]:
         """Keras order: trainable weights first (in creation order), then non-trainable."""
+        self._sync_host()
         tr = [w for n, w in self._weights.items() if self._trainable[n]]
         nt = [w for n, w in self._weights.items() if not self._trainable[n]]
         return [w.copy() for w in tr + nt]
@@ -93,12 +101,14 @@ class Layer:
         names = self.weight_names()
         if len(values) != len(names):
             raise ValueError(f"layer {self.name}: expected {len(names)} weight arrays, got {len(values)}")
+        self._sync_host()              # the other layers' trained values must survive the re-upload
         for n, v in zip(names, values):
             v = np.asarray(v, dtype=np.float32)
             if v.shape != self._weights[n].shape:
                 raise ValueError(f"layer {self.name}/{n}: shape {v.shape} != {self._weights[n].shape}")
             self._weights[n][...] = v
-        self._weights_version = getattr(self, "_weights_version", 0) + 1
+        for s in self._stores:
+            s.dev_stale = True         # uploaded lazily by the next plan that runs (Plan.ensure_current)
 
     def count_params(self) -> int:
         return int(sum(w.size for w in self._weights.values()))

@@ -55,6 +55,8 @@ class Model(Layer):
         self.loss = None
         self.metrics = []
         self._plans: Dict = {}
+        self._stores_by_device: Dict = {}        # device string -> engine.ParamStore shared by all plans
+        self._pending_opt_state: Optional[Dict] = None
 
     # -- Layer protocol: a nested model is one node of the outer graph ------------------------------------
     def compute_output_shape(self, shapes):
@@ -98,7 +100,14 @@ class Model(Layer):
         rec(self)
         return out
 
+    def _sync_host(self):
+        for s in self._stores_by_device.values():
+            s.sync_host()
+        for l in self.flat_layers():
+            l._sync_host()
+
     def get_weights(self):
+        self._sync_host()
         return [w for l in self.flat_layers() for w in l.get_weights()]
 
     def set_weights(self, values):
@@ -113,19 +122,82 @@ class Model(Layer):
         self._invalidate()
 
     def named_weights(self) -> Dict[str, np.ndarray]:
-        """{'layer/weight': array} — the exchange format of utils.save_weights_npz."""
+        """{'layer/weight': array} — the exchange format of utils.save_weights_npz.  The arrays are the layers' host
+        master copies (brought up to date with the device first); after writing into them in place call
+        `_invalidate()`."""
+        self._sync_host()
         return {f"{l.name}/{n}": l._weights[n] for l in self.flat_layers() for n in l.weight_names()}
 
     def count_params(self) -> int:
         return int(sum(l.count_params() for l in self.flat_layers()))
 
     def _invalidate(self):
-        for p in self._plans.values():
-            p.upload_weights()
+        """The host arrays were modified: every device store re-uploads before its next use."""
+        stores = list(self._stores_by_device.values())
+        for l in self.flat_layers():
+            stores += [s for s in l._stores if s not in stores]
+        for s in stores:
+            s.dev_stale = True
+
+    # -- optimizer state (checkpoint / resume, ss.py:482-485: load_model restores the optimizer) ------------
+    def optimizer_state(self) -> Dict[str, np.ndarray]:
+        """{'optimizer/iterations', 'optimizer/lr', 'optimizer/step_counter', 'optimizer/m/<layer>/<weight>',
+        'optimizer/v/...'}: what Adam needs to continue (moments, the iteration count that drives the bias correction
+        and the inverse-time decay) plus the position of the dropout stream."""
+        out: Dict[str, np.ndarray] = {}
+        if self.optimizer is not None:
+            out["optimizer/iterations"] = np.asarray(self.optimizer.iterations, dtype=np.int64)
+            out["optimizer/lr"] = np.asarray(self.optimizer.lr, dtype=np.float64)
+        for store in self._stores_by_device.values():
+            out["optimizer/step_counter"] = store.step_counter.cpu().numpy().astype(np.int64).reshape(())
+            for l, n in store.trainable_items():
+                out[f"optimizer/m/{l.name}/{n}"] = store.logical(l, n, arena="m").cpu().numpy().copy()
+                out[f"optimizer/v/{l.name}/{n}"] = store.logical(l, n, arena="v").cpu().numpy().copy()
+            break
+        return out
+
+    def set_optimizer_state(self, state: Dict[str, np.ndarray]) -> None:
+        """Inverse of optimizer_state(); parts that have no home yet (no optimizer compiled, no device store
+        created) are kept and applied by compile() / the first plan."""
+        self._pending_opt_state = dict(state)
+        self._apply_pending_optimizer_state()
+
+    def _apply_pending_optimizer_state(self):
+        st = self._pending_opt_state
+        if not st:
+            return
+        import torch
+        if self.optimizer is not None:
+            if "optimizer/iterations" in st:
+                self.optimizer.iterations = int(st.pop("optimizer/iterations"))
+            if "optimizer/lr" in st:
+                self.optimizer.lr = float(st.pop("optimizer/lr"))
+        if self._stores_by_device:
+            moments = [k for k in st if k.startswith(("optimizer/m/", "optimizer/v/"))]
+            for store in self._stores_by_device.values():
+                if "optimizer/step_counter" in st:
+                    store.step_counter.fill_(int(st["optimizer/step_counter"]))
+                by_name = {f"{l.name}/{n}": (l, n) for l, n in store.trainable_items()}
+                for k in moments:
+                    arena, name = k.split("/", 2)[1], k.split("/", 2)[2]
+                    if name not in by_name:
+                        raise ValueError(f"optimizer state for unknown weight {name!r}")
+                    l, n = by_name[name]
+                    dst = store.logical(l, n, arena=arena)
+                    v = np.asarray(st[k], dtype=np.float32)
+                    if tuple(v.shape) != tuple(dst.shape):
+                        raise ValueError(f"{k}: shape {tuple(v.shape)}, expected {tuple(dst.shape)}")
+                    dst.copy_(torch.from_numpy(v))
+            st.pop("optimizer/step_counter", None)
+            for k in moments:
+                st.pop(k)
+        if not st:
+            self._pending_opt_state = None
 
     # -- execution -----------------------------------------------------------------------------------------
     def compile(self, optimizer=None, loss=None, metrics=None):
         self.optimizer, self.loss, self.metrics = optimizer, loss, list(metrics or [])
+        self._apply_pending_optimizer_state()
 
     def plan(self, batch_size: int, training: bool = False, **kw):
         from ..engine import Plan

@@ -21,14 +21,22 @@ class Trainer:
     def __init__(self, model, batch_size: int, dtype: Optional[str] = None, use_graph: bool = True,
                  buckets: int = 4, process_group=None, fused_tail: bool = True, overlap_wgrad: bool = True):
         self.model = model
-        self.plan: Plan = model.plan(batch_size, training=True, **({"dtype": dtype} if dtype else {}),
-                                     fused_tail=fused_tail)
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.rank = torch.distributed.get_rank(process_group) if process_group is not None else 0
+        kw = {"dtype": dtype} if dtype else {}
+        if self.world > 1:
+            kw["dropout_seed"] = 1024 + 104729 * self.rank     # independent dropout masks per replica
+        self.plan: Plan = model.plan(batch_size, training=True, fused_tail=fused_tail, **kw)
         p = self.plan
         loss = model.loss
         p.set_loss(loss.pos_weights, loss.neg_weights, loss.epsilon)
         self.opt = model.optimizer
-        self.pg = process_group
-        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        if self.world > 1:
+            # replicas start from rank 0's weights and BN moving statistics whatever each process initialised with
+            torch.distributed.broadcast(p.params.w, 0, group=process_group)
+            torch.distributed.broadcast(p.params.f, 0, group=process_group)
+            p.params.mark_updated()
         self.use_graph = use_graph
         self.buckets = buckets
         self.stream = torch.cuda.Stream()
@@ -144,6 +152,7 @@ class Trainer:
         """One training step on the batch resident in the plan's input buffers."""
         p = self.plan
         with torch.cuda.stream(self.stream):
+            p.ensure_current()                  # another plan of the model stepped, or weights were set / loaded
             for part, ranges in zip(self._parts, self._ranges):
                 part()
                 if self.world > 1 and ranges:
@@ -176,6 +185,8 @@ class Trainer:
                      w_off=P.n_reg)
         opt.iterations += 1
         self.plan.step_counter.add_(1)
+        P.mark_updated()
+        self.plan._prep_version = P.version     # step() re-derives the bf16 operands right after (self._prep)
 
     def read_loss(self) -> float:
         """Device -> host read of the step's loss (data term + L2 term)."""

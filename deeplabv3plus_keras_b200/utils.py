@@ -12,8 +12,14 @@ from typing import Dict
 import numpy as np
 
 
-def save_weights_npz(model, path: str) -> None:
-    np.savez_compressed(path, **{k: np.asarray(v) for k, v in model.named_weights().items()})
+def save_weights_npz(model, path: str, include_optimizer: bool = True) -> None:
+    """Layer weights (read back from the device if an optimizer step ran since) and, like the reference's SavedModel
+    checkpoints (ss.py:983-986), the optimizer state under 'optimizer/': Adam moments, iteration count, learning rate
+    and the dropout stream position."""
+    arrays = {k: np.asarray(v) for k, v in model.named_weights().items()}
+    if include_optimizer:
+        arrays.update(model.optimizer_state())
+    np.savez_compressed(path, **arrays)
 
 
 def load_weights_npz(model, path: str, strict: bool = True) -> Dict[str, str]:
@@ -22,7 +28,8 @@ def load_weights_npz(model, path: str, strict: bool = True) -> Dict[str, str]:
     data = np.load(path if path.endswith(".npz") else path + ".npz")
     named = model.named_weights()
     report = {}
-    extra = set(data.files) - set(named)
+    opt_keys = [k for k in data.files if k.startswith("optimizer/")]
+    extra = set(data.files) - set(named) - set(opt_keys)
     if strict and extra:
         raise ValueError(f"{path}: unexpected weights {sorted(extra)[:5]} ...")
     for k, w in named.items():
@@ -36,6 +43,7 @@ def load_weights_npz(model, path: str, strict: bool = True) -> Dict[str, str]:
             raise ValueError(f"{path}: {k!r} has shape {tuple(v.shape)}, the layer expects {tuple(w.shape)}")
         w[...] = v.astype(w.dtype)
         report[k] = "loaded"
-    for plan in getattr(model, "_plans", {}).values():       # refresh device copies of already-lowered plans
-        plan.upload_weights()
+    model._invalidate()                                      # device copies re-upload before their next use
+    if opt_keys:
+        model.set_optimizer_state({k: data[k] for k in opt_keys})
     return report

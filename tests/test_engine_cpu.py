@@ -85,13 +85,14 @@ def test_bn_relu_fused_into_depthwise_schedule(cpu_engine, monkeypatch, fuse):
         assert calls.count("bn_finalize") >= 20
     else:
         assert n_virtual == 0 and "dwconv3x3_dgrad_bnred" not in calls
+    ga = plan.gradients()               # (the gradient arena is shared by the plans of one model: snapshot first)
     ref = cpu_engine.Plan(ss.model, 2, training=True, fuse_bn_dw=False)
     ref.set_loss(PW, NW)
     ref.load_batch(x, y)
     ref.step_fwd_bwd()
     np.testing.assert_allclose(plan.logits.buf.numpy(), ref.logits.buf.numpy(), rtol=1e-4, atol=1e-5)
     assert abs(plan.loss_value() - ref.loss_value()) < 1e-5
-    ga, gb = plan.gradients(), ref.gradients()
+    gb = ref.gradients()
     for k in gb:
         scale = max(np.abs(gb[k]).max(), 1e-3)
         assert np.abs(ga[k] - gb[k]).max() <= 2e-3 * scale, k
@@ -141,11 +142,11 @@ def test_concat_slices_written_in_place(cpu_engine, monkeypatch):
         plan.set_loss(PW, NW)
         plan.load_batch(x, y)
         plan.step_fwd_bwd()
-        plans[flag] = (plan, len(calls))
+        plans[flag] = (plan, len(calls), plan.gradients())
     assert plans[False][1] == 10 and plans[True][1] == 2, (plans[True][1], plans[False][1])
     a, b = plans[True][0], plans[False][0]
     np.testing.assert_allclose(a.logits.buf.numpy(), b.logits.buf.numpy(), rtol=1e-5, atol=1e-6)
-    ga, gb = a.gradients(), b.gradients()
+    ga, gb = plans[True][2], plans[False][2]
     for k in gb:
         scale = max(np.abs(gb[k]).max(), 1e-3)
         assert np.abs(ga[k] - gb[k]).max() <= 1e-4 * scale, k
@@ -166,27 +167,28 @@ def test_bn_fused_into_maxpool_schedule(cpu_engine, monkeypatch):
     plans = {}
     for flag in (True, False):
         calls.clear()
+        ss.model._invalidate()          # both plans start from the initial moving statistics (shared store)
         plan = cpu_engine.Plan(ss.model, 2, training=True, fuse_bn_pool=flag)
         x, y = util.synthetic_batch(conf, 2, plan.out_shape[1:3])
         plan.set_loss(PW, NW)
         plan.load_batch(x, y)
         plan.step_fwd_bwd()
-        plans[flag] = (plan, list(calls))
+        moving = {k: plan.params.logical(l, n).clone().numpy() for l in ss.model.flat_layers()
+                  for n in l.weight_names() if "moving" in n for k in [f"{l.name}/{n}"]}
+        plans[flag] = (plan, list(calls), plan.gradients(), moving)
     assert plans[True][1].count("maxpool3x3s2_bn_fwd") == 3 and plans[True][1].count("maxpool3x3s2_bn_bwd") == 3
     assert "maxpool3x3s2_bn_fwd" not in plans[False][1] and plans[False][1].count("maxpool3x3s2_bwd") == 3
     a, b = plans[True][0], plans[False][0]
     np.testing.assert_allclose(a.logits.buf.numpy(), b.logits.buf.numpy(), rtol=1e-4, atol=1e-5)
     assert abs(a.loss_value() - b.loss_value()) < 1e-5
-    ga, gb = a.gradients(), b.gradients()
+    ga, gb = plans[True][2], plans[False][2]
     for k in gb:
         scale = max(np.abs(gb[k]).max(), 1e-3)
         assert np.abs(ga[k] - gb[k]).max() <= 2e-3 * scale, k
-    a.params.download()
-    sa = {k: v.copy() for k, v in ss.model.named_weights().items() if "moving" in k}
-    b.params.download()
-    for k, v in ss.model.named_weights().items():
-        if "moving" in k:
-            np.testing.assert_allclose(sa[k], v, rtol=1e-5, atol=1e-6, err_msg=k)
+    sa, sb = plans[True][3], plans[False][3]
+    assert sa and any(np.abs(v - ss.model.named_weights()[k]).max() > 1e-6 for k, v in sa.items())
+    for k, v in sb.items():
+        np.testing.assert_allclose(sa[k], v, rtol=1e-5, atol=1e-6, err_msg=k)
 
 
 def test_implicit_conv_schedule(cpu_engine, monkeypatch):
@@ -209,13 +211,14 @@ def test_implicit_conv_schedule(cpu_engine, monkeypatch):
     assert calls.count("conv3x3_valid_wgrad") == 1
     n_im2col = calls.count("im2col3x3")
     calls.clear()
+    ga = plan.gradients()
     ref = cpu_engine.Plan(ss.model, 2, training=True, implicit_conv=False)
     ref.set_loss(PW, NW)
     ref.load_batch(x, y)
     ref.step_fwd_bwd()
     assert calls.count("im2col3x3") == n_im2col + 1 and "conv3x3_valid_fwd" not in calls
     np.testing.assert_allclose(plan.logits.buf.numpy(), ref.logits.buf.numpy(), rtol=1e-4, atol=1e-5)
-    ga, gb = plan.gradients(), ref.gradients()
+    gb = ref.gradients()
     for k in gb:
         scale = max(np.abs(gb[k]).max(), 1e-3)
         assert np.abs(ga[k] - gb[k]).max() <= 2e-3 * scale, k
@@ -305,3 +308,56 @@ def test_reduce_lr_on_plateau_keras_semantics():
     assert abs(opt.step_size() / t1 - 1e-4 / 3e-5) < 1e-9
     with pytest.raises(ValueError):
         ReduceLROnPlateau(opt, factor=1.0)
+
+
+def test_trained_state_is_shared_by_all_plans_and_checkpointed(cpu_engine, monkeypatch, tmp_path):
+    """One parameter store per model: after train_on_batch the inference plan (predict), get_weights, a training
+    plan for ANOTHER batch size (last partial batch) and a saved checkpoint all see the trained weights, Adam moments,
+    iteration count and BN moving statistics; resuming from the checkpoint continues the optimizer exactly."""
+    from deeplabv3plus_keras_b200.utils import load_weights_npz, save_weights_npz
+    conf = util.make_conf(base="mobilenetv2", image_size=33, width=32, aspp=util.DEFAULT_ASPP, dropout=0.5)
+    conf["hps"]["lr"] = 1e-2
+
+    def fresh():
+        ss = util.build(conf)
+        util.randomize_weights(ss.model, seed=3)
+        return ss
+
+    ss = fresh()
+    m = ss.model
+    p_inf = m.plan(2, training=False)
+    x, y = util.synthetic_batch(conf, 2, p_inf.out_shape[1:3])
+    before = m.predict(x, batch_size=2)
+    w0 = [w.copy() for w in m.get_weights()]
+    losses = [m.train_on_batch(x, y) for _ in range(3)]
+    assert np.isfinite(losses).all()
+    after = m.predict(x, batch_size=2)
+    assert np.abs(after - before).max() > 1e-4, "predict() still sees the initial weights"
+    w1 = m.get_weights()
+    assert sum(float(np.abs(a - b).max()) > 0 for a, b in zip(w0, w1)) > len(w0) // 2, "get_weights() is stale"
+    store = m.plan(2, training=True).params
+    assert m.plan(1, training=True).params is store and p_inf.params is store
+    assert float(store.m.abs().max()) > 0 and m.optimizer.iterations == 3 and int(store.step_counter) == 3
+
+    # checkpoint -> resume in a fresh model -> the 4th step is the same as continuing in place
+    path = str(tmp_path / "ckpt.npz")
+    save_weights_npz(m, path)
+    cont = m.train_on_batch(x[:1], y[:1])                  # partial batch: another plan, same state
+    ss2 = fresh()
+    load_weights_npz(ss2.model, path)
+    assert ss2.model.optimizer.iterations == 3
+    resumed = ss2.model.train_on_batch(x[:1], y[:1])
+    assert abs(resumed - cont) < 1e-5 * max(1.0, abs(cont)), (resumed, cont)
+    st2 = ss2.model.plan(1, training=True).params
+    np.testing.assert_allclose(st2.m.numpy(), store.m.numpy(), rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(st2.w.numpy(), store.w.numpy(), rtol=1e-5, atol=1e-7)
+    assert int(st2.step_counter) == 4
+
+    # set_weights on one layer keeps every other layer's trained values
+    lay = [l for l in m.flat_layers() if l.name == "Conv1"][0]
+    other = [l for l in m.flat_layers() if l.name == "block_3_project"][0]
+    trained_other = other.get_weights()[0].copy()
+    lay.set_weights([np.zeros_like(v) for v in lay.get_weights()])
+    m.predict(x, batch_size=2)
+    assert float(store.logical(lay, "kernel").abs().max()) == 0.0
+    np.testing.assert_array_equal(store.logical(other, "kernel").numpy(), trained_other)
