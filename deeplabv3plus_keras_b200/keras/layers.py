@@ -304,4 +304,7 @@ class Lambda(Layer):
         out = self.function(inputs)
         if not isinstance(out, KTensor):
             raise TypeError("Lambda function must return a symbolic tensor built from backend ops")
+        if out.node.layer is not getattr(inputs, "node", None) and isinstance(out.node.layer, ResizeImages) \
+                and out.node.inputs == [inputs]:
+            out.node.layer.name = self.name       # tf.keras lists the Lambda ("lambda", "lambda_1", ...) in model.layers
         return out

@@ -21,8 +21,39 @@ DEFAULT_ASPP = [   # conf.json:39-45 (asymmetric rates, chained branches)
 ]
 
 
+def global_pool_aspp(feat: int, sub: int = 2):
+    """An ASPP exercising what the shipped JSONs leave identity: a `conv` k=1 branch (ss.py:812-820), a TRUE image-pooling
+    branch (AveragePooling2D over the whole feat x feat map, 1x1 conv, bilinear x feat: ss.py:841-856) and a second
+    pyramid level (pool `sub`, x`sub`) chained behind branch 0."""
+    return [
+        {"kernel": 1, "rate": [1, 1], "op": "conv", "input": -1},
+        {"kernel": 3, "rate": [6, 6], "op": "conv", "input": -1},
+        {"kernel": 3, "rate": [12, 12], "op": "conv", "input": 0},
+        {"kernel": feat, "rate": [1, 1], "op": "pyramid_pooling", "input": -1, "target_size_factor": [feat, feat]},
+        {"kernel": sub, "rate": [1, 1], "op": "pyramid_pooling", "input": 0, "target_size_factor": [sub, sub]},
+    ]
+
+
+def feature_size(base: str, output_stride: int, image_size: int) -> int:
+    """Spatial extent of the backbone tap: Xception's two VALID convs give 513 -> 32 at OS16."""
+    n = image_size
+    if base == "xception":
+        n = (n - 3) // 2 + 1          # block1_conv1 3x3 s2 VALID
+        n = n - 2                     # block1_conv2 3x3 VALID
+        for _ in range({8: 2, 16: 3}[output_stride]):
+            n = -(-n // 2)
+        return n
+    for _ in range({8: 3, 16: 4}[output_stride]):
+        n = -(-n // 2)
+    return n
+
+
 def make_conf(base="xception", output_stride=16, image_size=65, refine=False, dtype="float32", aspp=None,
               num_classes=21, dropout=0.0, rate_mult=1, width=256):
+    if aspp == "default":
+        aspp = DEFAULT_ASPP
+    elif aspp == "global_pool":
+        aspp = global_pool_aspp(feature_size(base, output_stride, image_size))
     return {
         "mode": "train", "resource_path": "", "model_loading": False, "base_model": base, "base_weights": None,
         "hps": {"dtype": dtype, "lr": 1e-4, "beta_1": 0.5, "beta_2": 0.99, "decay": 0.0, "epochs": 1,
