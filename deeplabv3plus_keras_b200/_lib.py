@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdlv3p.so")
+# DLV3P_LIB overrides the library (diagnostic scripts point it at libdlv3p_diag.so, built with DLV3P_DIAG=1)
+LIB_PATH = os.environ.get("DLV3P_LIB") or os.path.join(_HERE, "libdlv3p.so")
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2

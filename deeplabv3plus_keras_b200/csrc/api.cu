@@ -25,9 +25,13 @@ int check_launch(const char* what) {
 }
 
 bool pdl_enabled() {
-    static int on = -1;
+#ifdef DLV3P_DIAG
+    static int on = -1;           // diagnostics build: DLV3P_PDL=0 switches programmatic dependent launch off (A/B)
     if (on < 0) { const char* e = getenv("DLV3P_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
     return on != 0;
+#else
+    return true;
+#endif
 }
 
 }  // namespace dlv3p

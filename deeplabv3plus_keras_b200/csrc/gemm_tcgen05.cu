@@ -76,8 +76,16 @@ struct GemmParams {
     int cv_tpr;                        // fwd/dgrad: 128-pixel M tiles per row; wgrad: 64-pixel reduction blocks per row
     int cv_kbr;                        // fwd/wgrad: 64-element k-blocks per filter row; dgrad: 64-channel blocks per tap
     int cv_run;                        // fwd: 3*Cin, the length of one filter row's run in the [Cout, 9*Cin] filter matrix
-    int dbg;                           // diagnostics only (DLV3P_GEMM_DBG): 1 = no operand loads, 2 = no epilogue work, 4 = no MMAs, 8 = no C stores, 16 = no TMEM reads
+    int dbg;                           // DLV3P_DIAG builds only (libdlv3p_diag.so): 1 = no operand loads, 2 = no epilogue work, 4 = no MMAs, 8 = no C stores, 16 = no TMEM reads
 };
+
+// Bottleneck-decomposition switches exist only in the diagnostics build (csrc/build.sh with DLV3P_DIAG=1 ->
+// libdlv3p_diag.so, used by scripts/gemm_decompose.py); the shipped library has no path that skips work.
+#ifdef DLV3P_DIAG
+#define DLV3P_DBG(p, bit) ((p).dbg & (bit))
+#else
+#define DLV3P_DBG(p, bit) false
+#endif
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -163,7 +171,7 @@ __device__ __forceinline__ void staged_tile_epilogue(const GemmParams& p, const 
 #pragma unroll
         for (int h = 0; h < CW / 32; ++h) {
             uint32_t raw[32];
-            if (p.dbg & 16) {
+            if (DLV3P_DBG(p, 16)) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) raw[j] = 0x3f800000u + (uint32_t)(lane + j);
             } else {
@@ -213,7 +221,7 @@ __device__ __forceinline__ void staged_tile_epilogue(const GemmParams& p, const 
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0 && rbase < row_limit && !(p.dbg & 8)) {
+        if (lane == 0 && rbase < row_limit && !DLV3P_DBG(p, 8)) {
             // c2 >= 0: implicit-convolution tile, rank-3 C map (channel, column in the row, row) clips the ragged row end
             if (WGRAD) { if (c2 >= 0) tma_reduce_add_3d(tmC, stg, n_base, rbase, c2); else tma_reduce_add_2d(tmC, stg, n_base, rbase); }
             else { if (c2 >= 0) tma_store_3d(tmC, stg, n_base, rbase, c2); else tma_store_2d(tmC, stg, n_base, rbase); }
@@ -719,7 +727,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     mbar_wait(empty_bar + 8 * s, ph ^ 1u);
                     const uint32_t a_dst = smem_base + s * STAGE_BYTES;
                     const uint32_t b_dst = a_dst + A_BYTES;
-                    if (p.dbg & 1) { if (leader) mbar_arrive(full_bar + 8 * s); continue; }
+                    if (DLV3P_DBG(p, 1)) { if (leader) mbar_arrive(full_bar + 8 * s); continue; }
                     if (leader) mbar_expect_tx(full_bar + 8 * s, 2 * STAGE_BYTES);     // both CTAs' boxes
                     const uint32_t fb = leader_full + 8 * s;
                     if (WGRAD) {
@@ -764,7 +772,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         // 64-element MN chunk (one 8 KB box), SBO = next 8 K-rows, a K=16 step is 16 rows of 128 B
                         const uint64_t ad = WGRAD ? umma_desc(a_src + k * 2048, 8192, 1024) : umma_desc(a_src + k * 32, 16, 1024);
                         const uint64_t bd = WGRAD ? umma_desc(b_src + k * 2048, 8192, 1024) : umma_desc(b_src + k * 32, 16, 1024);
-                        if (!(p.dbg & 4)) tc_mma_bf16_2sm(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        if (!DLV3P_DBG(p, 4)) tc_mma_bf16_2sm(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
                     tc_commit_2sm(empty_bar + 8 * s);          // slot reusable in BOTH CTAs once these MMAs retire
                 }
@@ -788,7 +796,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t as = t & 1u;
             mbar_wait(tmem_full_bar + 8 * as, (t >> 1) & 1u);
             tc_fence_after();
-            if (p.dbg & 2) {
+            if (DLV3P_DBG(p, 2)) {
                 if (lane == 0) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_tmem_empty + 8 * as) : "memory");
                 continue;
             }
@@ -856,15 +864,24 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
     return check_launch("gemm_bf16 (2-CTA)");
 }
 
-static int g_gemm_2cta = -1;      // DLV3P_GEMM_2CTA=0 disables the 2-CTA path (A/B measurements)
-// DLV3P_GEMM_DBG (re-read on every call once DLV3P_GEMM_DBG_ENABLE is set at first use): bottleneck decomposition of the
-// 2-CTA kernel by switching off operand loads (1), epilogue work (2) and/or MMAs (4); results are garbage by design
+#ifdef DLV3P_DIAG
+// diagnostics build: DLV3P_GEMM_2CTA=0 disables the 2-CTA path (A/B measurements); DLV3P_GEMM_DBG (re-read on every call
+// once DLV3P_GEMM_DBG_ENABLE is set at first use) switches off operand loads (1), epilogue work (2), MMAs (4), C stores
+// (8), TMEM reads (16) of the 2-CTA kernel for the bottleneck decomposition; results are garbage by design
+static int g_gemm_2cta = -1;
 static int gemm_dbg_mode() {
     static const bool enabled = getenv("DLV3P_GEMM_DBG_ENABLE") != nullptr;
     if (!enabled) return 0;
     const char* e = getenv("DLV3P_GEMM_DBG");
     return e ? atoi(e) : 0;
 }
+static bool gemm_2cta_enabled() {
+    return g_gemm_2cta != 0;
+}
+#else
+static int gemm_dbg_mode() { return 0; }
+static bool gemm_2cta_enabled() { return true; }
+#endif
 
 }  // namespace dlv3p
 
@@ -899,9 +916,8 @@ extern "C" int dlv3p_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
         rc = make_tmap(&tmC, C, N, M, ldc, 64, 32);
         if (rc) return rc;
     }
-    if (g_gemm_2cta < 0) { const char* e = getenv("DLV3P_GEMM_2CTA"); g_gemm_2cta = (e && e[0] == '0') ? 0 : 1; }
     // (short reductions are epilogue-bound and gain nothing from pairing: measured 64 vs 51 us at M=258064 N=K=256)
-    if (g_gemm_2cta && bn == 256 && p.tma_store && M >= 2 * kBlockM && K >= 512) {
+    if (gemm_2cta_enabled() && bn == 256 && p.tma_store && M >= 2 * kBlockM && K >= 512) {
         // 2-CTA pairs: every CTA loads half of the B tile (128 rows of the [N,K] operand)
         rc = make_tmap(&tmB, B, K, N, ldb, kBlockK, bn / 2);
         if (rc) return rc;
@@ -950,8 +966,7 @@ extern "C" int dlv3p_gemm_wgrad_bf16(const void* X, int64_t ldx, const void* dY,
         rc = make_tmap(&tmC, dW, N, K, ldw, 32, 32, /*f32=*/true);
         if (rc) return rc;
     }
-    if (g_gemm_2cta < 0) { const char* e = getenv("DLV3P_GEMM_2CTA"); g_gemm_2cta = (e && e[0] == '0') ? 0 : 1; }
-    if (g_gemm_2cta && bn == 256 && p.tma_store && K > kBlockM && M >= 4096) {
+    if (gemm_2cta_enabled() && bn == 256 && p.tma_store && K > kBlockM && M >= 4096) {
         // 2-CTA pairs: 256 input channels x 256 output channels per pair tile, one wave of (split, tile) items
         p.m_tiles = cdiv(K, 2 * kBlockM);
         const int tiles2 = p.n_tiles * p.m_tiles;

@@ -251,7 +251,7 @@ class Plan:
     def __init__(self, model: Model, batch_size: int, training: bool = False, dtype: Optional[str] = None,
                  device: Optional[str] = None, dropout_seed: int = 1024, fused_tail: bool = True,
                  fuse_bn_dw: bool = True, implicit_conv: bool = True, concat_in_place: bool = True,
-                 fuse_bn_pool: bool = True):
+                 fuse_bn_pool: bool = True, keep_scratch: bool = False):
         fake = getattr(ops, "FAKE", False)       # tests/fake_ops.py test double (host-logic tests without a GPU)
         if not torch.cuda.is_available() and not fake:
             raise RuntimeError("engine.Plan needs a CUDA device: there is no CPU execution path")
@@ -268,6 +268,14 @@ class Plan:
         self.concat_in_place = concat_in_place   # Conv->BN(->ReLU) read only by a Concatenate writes its slice directly
         self.implicit_conv = implicit_conv  # dense 3x3 VALID stride-1 convs as implicit GEMMs (False: A/B, im2col + GEMM)
         self.dropout_seed = dropout_seed
+        # introspection for the parity tests (tests/teacher.py): named storage points (value / gradient getters),
+        # activation decision sites and max-pool winners.  `keep_scratch` gives every macro-op its own backward
+        # scratch (dy / dA) instead of two alternating slots, so those gradients can be read after the step.
+        self.keep_scratch = keep_scratch
+        self.trace: Dict[str, dict] = {}
+        self.act_sites: Dict[str, tuple] = {}
+        self.pool_sites: Dict[str, torch.Tensor] = {}
+        self._tname: Dict[int, str] = {}
         self.fwd: List[Callable[[], None]] = []
         self.bwd: List[Tuple[Callable[[], None], bool, Optional[int]]] = []   # (launch, side-stream ok, scratch slot)
         self.side_stream = None            # set by the Trainer: filter-gradient kernels overlap the main backward chain
@@ -378,6 +386,57 @@ class Plan:
             p = v.pending.pop()
             self.bwd_seq(lambda p=p, g=g: ops.add(g, p, g))
         return g
+
+    def _trace_value(self, name: str, getter, clog: int, shape=None):
+        self.trace.setdefault(name, {})["value"] = (getter if callable(getter) else (lambda t=getter: t), clog, shape)
+
+    def _trace_grad(self, name: str, getter, clog: int, shape=None):
+        self.trace.setdefault(name, {})["grad"] = (getter if callable(getter) else (lambda t=getter: t), clog, shape)
+
+    def traced(self, name: str, what: str = "value") -> Optional[torch.Tensor]:
+        """The stored tensor (or its gradient) of a named storage point as a contiguous NHWC tensor with the LOGICAL
+        channel count, or None when the plan does not materialise it."""
+        ent = self.trace.get(name, {}).get(what)
+        if ent is None:
+            return None
+        getter, clog, shape = ent
+        t = getter()
+        if t is None:
+            return None
+        if shape is not None:
+            if t.dim() == 2 and t.shape[1] != shape[3]:
+                t = t[:, :shape[3]]
+            t = t.reshape(shape) if t.is_contiguous() else t.contiguous().view(shape)
+        return t[..., :clog].contiguous()
+
+    def dropout_mask(self, name: str) -> torch.Tensor:
+        """keep / (1 - rate) multiplier the Dropout layer `name` applies at the CURRENT step counter (the counter-based
+        generator is a pure function of seed, counter and element index): what a parity run injects into the oracle."""
+        out, rate, seed = self.dropout_sites[name]
+        ones = torch.ones_like(out.buf)
+        m = torch.empty_like(out.buf)
+        ops.dropout(ones, rate, seed, m, seed_offset=self.step_counter)
+        return m[..., :out.clog].float()
+
+    def decisions(self):
+        """(masks, pool_taps): per activation site an int8 tensor (0 = clamped below, 1 = passed, 2 = clamped above,
+        ReLU6 only) computed the way the backward kernels decide it — from the raw conv output and the BN scale/shift
+        where the activation follows a BatchNormalization, from the stored input otherwise — and per max-pool site the
+        uint8 winning tap (row-major inside the 3x3 window)."""
+        masks = {}
+        for site, ent in self.act_sites.items():
+            if ent[0] == "bn":
+                _, act, y, scale, shift, clog, shape = ent
+                z = (y.float().view(-1, y.shape[-1]) * scale + shift).view(shape)[..., :clog]
+            else:
+                _, act, v = ent
+                z = v.buf.float()[..., :v.clog]
+            m = (z > 0).to(torch.int8)
+            if act == ACT_RELU6:
+                m = m + (z >= 6).to(torch.int8)
+            masks[site] = m
+        taps = {k: (am[..., :c] if c else am) for k, (am, c) in self.pool_sites.items()}
+        return masks, taps
 
     # ---------------------------------------------------------------------------------------------- lowering
     def _lower(self, out_id: int):
@@ -570,6 +629,8 @@ class Plan:
             out = Value(out_shape, y_dtype, self._alloc((N, Ho, Wo, ld_out), y_dtype), lay.name)
         out.clog = Cout_log
         self.values[m["out"]] = out
+        tname = bn_node.layer.name if bn_node is not None else lay.name
+        self._tname[m["out"]] = tname
         other = self.values[other_id] if other_id is not None else None
         needs_in_grad = x.needs_grad
         out.needs_grad = training
@@ -644,6 +705,15 @@ class Plan:
         pad4 = (Ho, Wo, pt, pl)
         xb = x.buf
         launches_f = 0
+        # introspection (parity tests): storage points and the activation decision site of this macro-op
+        if bn_node is not None and training:
+            self._trace_value(f"{tname}/y", y, Cout_log, out_shape)
+            if act != ACT_NONE:
+                self.act_sites[tname] = ("bn", act, y, scale, shift, Cout_log, out_shape)
+        elif bn_node is None:
+            self._trace_value(f"{tname}/y", out.buf, Cout_log, out_shape)
+        if bn_node is not None and not virt and not pool_virt:
+            self._trace_value(f"{tname}/out", lambda: out.buf, Cout_log, out_shape)
 
         # ---- forward ------------------------------------------------------------------------------------
         # A operand of the GEMM
@@ -664,6 +734,8 @@ class Plan:
                                                           in_act=in_act, out=dw_out, pad=pad4))
             launches_f += 1
             A, lda = d, Cin
+            if is_sep:
+                self._trace_value(f"{lay.name}/dw", d, x.clog, (N, Ho, Wo, Cin))
         elif k == 1 and stride == 1:
             A, lda = xb, Cin
         elif k == 1:
@@ -748,11 +820,16 @@ class Plan:
             if other is not None:
                 other.pending.append(g)
             slot = self._bwd_macro & 1                     # scratch copy used by this macro-op (see bwd_seq)
+            skey = self._bwd_macro if self.keep_scratch else slot
             self._bwd_macro += 1
             self.bwd_seq(None, slot=slot)
+            if not virt and not pool_virt:
+                self._trace_grad(f"{tname}/out" if bn_node is not None else f"{tname}/y", g, Cout_log, out_shape)
             # dy: gradient w.r.t. the raw conv output
             if bn_node is not None:
-                dy_get = self._reserve(f"dy{slot}", (Mo, Cout), self.dt)
+                dy_get = self._reserve(f"dy{skey}", (Mo, Cout), self.dt)
+                if self.keep_scratch:
+                    self._trace_grad(f"{tname}/y", dy_get, Cout_log, out_shape)
                 red = red_slot
                 # virtual BN+ReLU output: g arrives as the gradient w.r.t. the BN output, ReLU mask already applied
                 # by the reader's input-gradient kernel (which may also have produced the two reductions)
@@ -798,7 +875,7 @@ class Plan:
                     if addend2 is None:
                         self.bwd_seq(lambda: ops.conv3x3_valid_dgrad(dy_get().view(N, Ho, Wo, Cout), wd, x.shape, Cout, tgt))
                     else:
-                        tmp_get = self._reserve(f"dA{slot}", x.shape, self.dt)
+                        tmp_get = self._reserve(f"dA{skey}", x.shape, self.dt)
                         self.bwd_seq(lambda: ops.conv3x3_valid_dgrad(dy_get().view(N, Ho, Wo, Cout), wd, x.shape, Cout,
                                                                      tmp_get()))
                         self.bwd_seq(lambda: ops.add(tmp_get(), addend2, tgt))
@@ -818,8 +895,10 @@ class Plan:
                         dA_get = lambda: tgt
                     else:
                         shape_dA = (Mo, lda)
-                        dA_get = self._reserve(f"dA{slot}", shape_dA, self.dt)
+                        dA_get = self._reserve(f"dA{skey}", shape_dA, self.dt)
                         addend = None
+                        if is_sep and self.keep_scratch:
+                            self._trace_grad(f"{lay.name}/dw", dA_get, x.clog, (N, Ho, Wo, Cin))
                     if self.bf16:
                         # dA[M,K] = dy[M,N] * W[K,N]^T : B operand = wn (rows = K, contraction over Np, zero padded)
                         self.bwd_seq(lambda: ops.gemm_bf16(dy_get(), wn, Mo, Kdim, ld_dy, dA_get(), lda=ld_dy,
@@ -839,7 +918,9 @@ class Plan:
                                                            addend=addend2, out=tgt))
                 elif is_sep:
                     # depthwise filter gradient still needs d(dw out) even if the input itself needs no gradient
-                    dA_get = self._reserve(f"dA{slot}", (Mo, lda), self.dt)
+                    dA_get = self._reserve(f"dA{skey}", (Mo, lda), self.dt)
+                    if self.keep_scratch:
+                        self._trace_grad(f"{lay.name}/dw", dA_get, x.clog, (N, Ho, Wo, Cin))
                     if self.bf16:
                         self.bwd_seq(lambda: ops.gemm_bf16(dy_get(), wn, Mo, Kdim, ld_dy, dA_get(), lda=ld_dy, ldb=Np,
                                                            ldc=lda))
@@ -959,6 +1040,10 @@ class Plan:
         other = self.values[m["other"]] if m["other"] is not None else None
         am = self._alloc((N, Ho, Wo, C), torch.uint8) if self.training else None
         self.values[m["out"]] = out
+        self._tname[m["out"]] = n.layer.name
+        self._trace_value(f"{n.layer.name}/out", out.buf, out.clog)
+        if am is not None:
+            self.pool_sites[n.layer.name] = (am, out.clog)
         out.needs_grad = self.training
         addend = other.buf if other is not None else None
         if fused_bn:
@@ -973,6 +1058,7 @@ class Plan:
 
         def sched():
             g = self._final_grad(out)
+            self._trace_grad(f"{n.layer.name}/out", g, out.clog)
             if other is not None:
                 other.pending.append(g)
             if fused_bn:
@@ -987,6 +1073,8 @@ class Plan:
         x = self._input_of(n.inputs[0], False)
         cons = consumers.get(n.output, [])
         fusable = cons and all(isinstance(c.layer, (L.SeparableConv2D, L.DepthwiseConv2D)) for c in cons)
+        site = self._tname.get(n.inputs[0], n.layer.name)
+        self.act_sites[site] = ("x", code, x)
         if fusable:
             # virtual pre-activation: consumers apply it on load and mask it in their input gradient
             self.values[n.output] = _AliasValue(x, code)
@@ -1032,9 +1120,11 @@ class Plan:
         self.values[n.output] = out
         self.fwd.append(lambda: ops.avgpool_fwd(x.buf, k, out=out.buf))
         self.launches_fwd += 1
+        self._trace_value(f"{n.layer.name}/out", out.buf, out.clog)
         if self.training and x.needs_grad:
             def sched():
                 g = self._final_grad(out)
+                self._trace_grad(f"{n.layer.name}/out", g, out.clog)
                 tgt, add2 = self._grad_target(x)
                 self.bwd_seq(lambda: ops.avgpool_bwd(g, x.shape, k, addend=add2, out=tgt))
             self._defer_backward(sched)
@@ -1059,9 +1149,11 @@ class Plan:
         self.values[n.output] = out
         self.fwd.append(lambda: ops.bilinear_fwd(x.buf, fh, fw, out=out.buf))
         self.launches_fwd += 1
+        self._trace_value(f"{n.layer.name}/out", out.buf, out.clog)
         if self.training and x.needs_grad:
             def sched():
                 g = self._final_grad(out)
+                self._trace_grad(f"{n.layer.name}/out", g, out.clog)
                 tgt, add2 = self._grad_target(x)
                 self.bwd_seq(lambda: ops.bilinear_bwd(g, x.shape, fh, fw, out=tgt, addend=add2))
             self._defer_backward(sched)
@@ -1078,6 +1170,7 @@ class Plan:
         out = Value((N, H, W, Ct), self.dt, buf, n.layer.name)
         out.needs_grad = self.training
         self.values[n.output] = out
+        self._trace_value(f"{n.layer.name}/out", buf, Ct)
         M = N * H * W
         off = 0
         for v in ins:
@@ -1088,6 +1181,7 @@ class Plan:
         if self.training:
             def sched():
                 g = self._final_grad(out)
+                self._trace_grad(f"{n.layer.name}/out", g, Ct)
                 o = 0
                 for v in ins:
                     if v.needs_grad and getattr(v, "concat_slice", False):
@@ -1113,9 +1207,13 @@ class Plan:
         ctr = self.step_counter
         self.fwd.append(lambda: ops.dropout(x.buf, rate, seed, out.buf, seed_offset=ctr))
         self.launches_fwd += 1
+        self._trace_value(f"{n.layer.name}/out", out.buf, out.clog)
+        self.dropout_sites = getattr(self, "dropout_sites", {})
+        self.dropout_sites[n.layer.name] = (out, rate, seed)
 
         def sched():
             g = self._final_grad(out)
+            self._trace_grad(f"{n.layer.name}/out", g, out.clog)
             tgt, add2 = self._grad_target(x)
             self.bwd_seq(lambda: ops.dropout(g, rate, seed, tgt, addend=add2, seed_offset=ctr))
         self._defer_backward(sched)

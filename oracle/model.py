@@ -47,12 +47,109 @@ class Ctx:
     With it off (default) the oracle is the plain fp64/fp32 restatement."""
 
     def __init__(self, weights: Dict[str, torch.Tensor], training: bool, bn_momentum_new: Dict[str, torch.Tensor],
-                 emulate_bf16: bool = False, momentum_override: Optional[float] = None):
+                 emulate_bf16: bool = False, momentum_override: Optional[float] = None, probe: Optional["Probe"] = None):
         self.w, self.training, self.new_stats = weights, training, bn_momentum_new
         self.names = Names()
         self.l2_terms: List[torch.Tensor] = []
         self.q = _bf16 if emulate_bf16 else (lambda t: t)
         self.momentum_override = momentum_override
+        self.probe = probe
+
+    # ---- named storage points / decision sites (see Probe) ------------------------------------------------
+    def store(self, name: str, t, rounded: bool = True):
+        """A tensor the product writes to HBM under this name.  Rounded like the product's storage; with a Probe the
+        value is recorded and, under teacher forcing, replaced by the product's own stored tensor."""
+        if rounded:
+            t = self.q(t)
+        return t if self.probe is None else self.probe.on_store(name, t)
+
+    def act(self, site: str, z, kind: str):
+        """ReLU / ReLU6 at a named decision site (the Keras layer that produced z)."""
+        if self.probe is not None:
+            return self.probe.on_act(site, z, kind)
+        return T.relu(z) if kind == "relu" else T.relu6(z)
+
+    def max_pool(self, site: str, x):
+        if self.probe is not None:
+            return self.probe.on_pool(site, x)
+        return T.max_pool_3x3_s2_same(x)
+
+
+class Probe:
+    """Test instrumentation of the oracle graph (never used by the plain oracle runs).
+
+    * `values` / `pre` / `pool_arg`: every named storage point, every activation's pre-activation tensor and every
+      max-pool's winning tap (row-major 0..8 inside the 3x3 window, first maximum wins), as the oracle computed them.
+    * teacher forcing (`teacher`, `teacher_grad`): at a storage point the product also has, the oracle's tensor is
+      compared with the product's (`fwd[name] = (oracle, product)`) and then REPLACED by it — value of the product,
+      gradient path of the oracle — so every operation is checked on identical inputs, with no error amplification
+      through the depth of the network.  In backward the gradient arriving at that point is compared with the
+      product's gradient buffer (`bwd[name]`) and replaced by it the same way.
+    * forced decisions (`masks`, `pool_taps`): the oracle runs freely but takes every ReLU/ReLU6 mask and every
+      max-pool winner from the product, so that the two compute the gradient of the SAME piecewise-smooth function;
+      what is left is arithmetic error.  The natural decisions stay recorded so that the test can check that the two
+      only disagree inside the forward-error band around a tie."""
+
+    def __init__(self, teacher=None, teacher_grad=None, masks=None, pool_taps=None, keep_values=True):
+        self.teacher, self.teacher_grad = teacher or {}, teacher_grad or {}
+        self.masks, self.pool_taps = masks or {}, pool_taps or {}
+        self.keep_values = keep_values
+        self.values: Dict[str, torch.Tensor] = {}
+        self.pre: Dict[str, torch.Tensor] = {}
+        self.pool_arg: Dict[str, torch.Tensor] = {}
+        self.pool_margin: Dict[str, torch.Tensor] = {}
+        self.fwd: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self.bwd: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self.order: List[str] = []
+
+    def on_store(self, name, t):
+        self.order.append(name)
+        if self.keep_values:
+            self.values[name] = t.detach()
+        tv = self.teacher.get(name)
+        if tv is None:
+            return t
+        tv = tv.to(t.dtype)
+        if tuple(tv.shape) != tuple(t.shape):
+            raise ValueError(f"teacher tensor {name}: shape {tuple(tv.shape)} vs oracle {tuple(t.shape)}")
+        self.fwd[name] = (t.detach(), tv)
+        out = t + (tv - t).detach()
+        gv = self.teacher_grad.get(name)
+        if gv is not None and out.requires_grad:
+            def hook(g, name=name, gv=gv):
+                self.bwd[name] = (g.detach().clone(), gv)
+                return gv.to(g.dtype)
+            out.register_hook(hook)
+        return out
+
+    def on_act(self, site, z, kind):
+        self.pre[site] = z.detach()
+        m = self.masks.get(site)
+        if m is None:
+            return T.relu(z) if kind == "relu" else T.relu6(z)
+        if tuple(m.shape) != tuple(z.shape):
+            raise ValueError(f"mask {site}: shape {tuple(m.shape)} vs {tuple(z.shape)}")
+        if kind == "relu":
+            return z * (m == 1).to(z.dtype)
+        return torch.where(m == 1, z, torch.where(m == 2, torch.full_like(z, 6.0), torch.zeros_like(z)))
+
+    def on_pool(self, site, x):
+        """3x3 / stride 2 / SAME max-pool with recorded (and optionally forced) winners."""
+        N, H, W, C = x.shape
+        Ho, pt, pb = T.same_pad(H, 3, 2)
+        Wo, pl, pr = T.same_pad(W, 3, 2)
+        xp = torch.nn.functional.pad(x.permute(0, 3, 1, 2), (pl, pr, pt, pb), value=float("-inf"))
+        win = xp.unfold(2, 3, 2).unfold(3, 3, 2).reshape(N, C, Ho, Wo, 9)        # row-major taps
+        best = win.detach().max(dim=-1)
+        # first maximum wins (TF / the kernels use a strict >): argmax of the first occurrence
+        is_max = win.detach() == best.values.unsqueeze(-1)
+        first = torch.argmax(is_max.to(torch.uint8), dim=-1)
+        self.pool_arg[site] = first.permute(0, 2, 3, 1)
+        top2 = torch.topk(win.detach(), 2, dim=-1).values
+        self.pool_margin[site] = (top2[..., 0] - top2[..., 1]).permute(0, 2, 3, 1)
+        forced = self.pool_taps.get(site)
+        idx = first if forced is None else forced.permute(0, 3, 1, 2).long()
+        return torch.gather(win, -1, idx.unsqueeze(-1)).squeeze(-1).permute(0, 2, 3, 1)
 
 
 def _bn(ctx: Ctx, x, name: str, momentum: float, eps: float = 1e-3, scale: bool = True, stats_from=None):
@@ -90,7 +187,7 @@ def _conv(ctx: Ctx, x, name, stride=1, padding="same", l2: float = 0.0):
 
 
 def _sep(ctx: Ctx, x, name, dilation=(1, 1)):
-    d = ctx.q(T.depthwise_conv2d(x, ctx.w[f"{name}/depthwise_kernel"], 1, "same", dilation))
+    d = ctx.store(f"{name}/dw", T.depthwise_conv2d(x, ctx.w[f"{name}/depthwise_kernel"], 1, "same", dilation))
     return T.conv2d(d, ctx.q(ctx.w[f"{name}/pointwise_kernel"]), 1, "same")
 
 
@@ -99,17 +196,24 @@ def _cbn(ctx: Ctx, acc, bn_name, momentum, act=None, add=None, scale=True, stats
     macro-op of the product (engine._emit_conv).  `virtual`: in training the product never stores this BN+ReLU output —
     its only reader, a dense-tap stride-1 depthwise stage, applies the map on load in fp32 (engine._BnActValue) — so
     there is no rounding point; in inference the BN is folded into the GEMM epilogue and the output is stored."""
-    y = ctx.q(acc)
+    y = ctx.store(f"{bn_name}/y", acc)
     if stats_rounded is None:
         # the product's rule (gemm_tcgen05.cu): GEMMs with more than 32 output channels take the staged TMA-store
         # epilogue, whose statistics are those of the stored tile; narrower ones reduce the fp32 accumulators
         stats_rounded = acc.shape[-1] > 32
-    z = _bn(ctx, y, bn_name, momentum, scale=scale, stats_from=(y if stats_rounded else acc))
+    if stats_rounded:
+        src = y
+    elif ctx.probe is not None:
+        src = y + (acc - y).detach()    # values of the accumulators, gradient through the (hooked) storage point
+    else:
+        src = acc
+    z = _bn(ctx, y, bn_name, momentum, scale=scale, stats_from=src)
     if act is not None:
-        z = act(z)
+        z = ctx.act(bn_name, z, "relu6" if act is T.relu6 else "relu")
     if add is not None:
         z = z + add
-    return z if (virtual and ctx.training) else ctx.q(z)
+    # (a virtual tensor is not a rounding point; it is still a named point: the fp32 schedules materialise some of them)
+    return ctx.store(f"{bn_name}/out", z, rounded=not (virtual and ctx.training))
 
 
 # ---- keras.applications.Xception, truncated where the reference taps it (ss.py:517-520) --------------------
@@ -123,23 +227,26 @@ def xception_base(ctx: Ctx, img, output_stride: int):
         # the strided 1x1 shortcut; pruned from the graph when the network is tapped before the pool (OS8)
         res = None if tap_here else _cbn(ctx, _conv(ctx, x, cname, 2, "same"), bname, M)
         if first_relu:
-            x = T.relu(x)
+            x = ctx.act(f"block{blk - 1}_pool", x, "relu")     # block{blk}_sepconv1_act on the previous pool+add output
         x = _cbn(ctx, _sep(ctx, x, f"block{blk}_sepconv1"), f"block{blk}_sepconv1_bn", M, T.relu, virtual=True)
         # (feeds the max-pool directly: in training the product pools scale*y+shift on the fly, no rounding point)
         x = _cbn(ctx, _sep(ctx, x, f"block{blk}_sepconv2"), f"block{blk}_sepconv2_bn", M, virtual=not tap_here)
         if tap_here:
             nm("conv2d"); nm("batch_normalization")       # block13's shortcut layers exist in Keras, pruned here
             return x
-        x = ctx.q(T.max_pool_3x3_s2_same(x) + res)
+        x = ctx.store(f"block{blk}_pool/out", ctx.max_pool(f"block{blk}_pool", x) + res)
+    site = "block4_pool"              # name of the layer whose output x is (decision site of the next ReLU)
     for blk in range(5, 13):
         res = x
         for j in (1, 2, 3):
             # sepconv1/2: BN -> the next iteration's ReLU -> dense-tap depthwise stage: virtual in training
-            x = _cbn(ctx, _sep(ctx, T.relu(x), f"block{blk}_sepconv{j}"), f"block{blk}_sepconv{j}_bn", M,
+            bn = f"block{blk}_sepconv{j}_bn"
+            x = _cbn(ctx, _sep(ctx, ctx.act(site, x, "relu"), f"block{blk}_sepconv{j}"), bn, M,
                      add=res if j == 3 else None, virtual=(j < 3))
+            site = bn
     nm("conv2d"); nm("batch_normalization")               # block13 shortcut: created by Keras, not on the tapped path
-    x = _cbn(ctx, _sep(ctx, T.relu(x), "block13_sepconv1"), "block13_sepconv1_bn", M, virtual=True)
-    x = _cbn(ctx, _sep(ctx, T.relu(x), "block13_sepconv2"), "block13_sepconv2_bn", M)
+    x = _cbn(ctx, _sep(ctx, ctx.act(site, x, "relu"), "block13_sepconv1"), "block13_sepconv1_bn", M, virtual=True)
+    x = _cbn(ctx, _sep(ctx, ctx.act("block13_sepconv1_bn", x, "relu"), "block13_sepconv2"), "block13_sepconv2_bn", M)
     return x
 
 
@@ -173,23 +280,32 @@ def mobilenetv2_base(ctx: Ctx, img, output_stride: int):
 
 def forward(conf: dict, weights: Dict[str, torch.Tensor], image, training: bool = False,
             dropout_mask: Optional[torch.Tensor] = None, emulate_bf16: bool = False,
-            momentum_override: Optional[float] = None):
+            momentum_override: Optional[float] = None, probe: Optional[Probe] = None):
     """Returns dict(logits=[B,h,w,C] low-res, probs=[B,H,W,C], l2=regularisation term, new_stats={...}).
-    `dropout_mask` (keep mask / (1-rate), shape of the concat) is required when training with dropout_rate > 0."""
+    `dropout_mask` (keep mask / (1-rate), shape of the concat) is required when training with dropout_rate > 0.
+    `probe`: test instrumentation (named storage points, teacher forcing, forced decisions), see Probe."""
     arch, hps = conf["nn_arch"], conf["hps"]
-    ctx = Ctx(weights, training, {}, emulate_bf16, momentum_override)
+    ctx = Ctx(weights, training, {}, emulate_bf16, momentum_override, probe)
     q = ctx.q
     osd = arch["output_stride"]
     base_fn = {"xception": xception_base, "mobilenetv2": mobilenetv2_base}[conf["base_model"]]
     names_after_base = None
 
+    base_cache = []
+
     def run_base(x):
         nonlocal names_after_base
+        if probe is not None and base_cache:
+            # instrumented runs evaluate the shared base once (as the product does): the named storage points then
+            # exist once and receive the SUM of both call sites' gradients.  (Moving statistics are then updated once;
+            # the double update is checked by the plain oracle runs.)
+            return base_cache[0]
         saved = ctx.names
         ctx.names = Names()                     # the base's automatic names do not depend on the call site
         y = base_fn(ctx, x, osd)
         names_after_base = ctx.names
         ctx.names = saved
+        base_cache.append(y)
         return y
 
     feats = run_base(image)
@@ -213,38 +329,42 @@ def forward(conf: dict, weights: Dict[str, torch.Tensor], image, training: bool 
             out = _cbn(ctx, _sep(ctx, src, s, rate), b, mom, T.relu, scale=sc)
             out = project(out)
         elif spec["op"] == "pyramid_pooling":
-            out = project(q(T.avg_pool_valid(src, spec["kernel"])))
-            out = q(T.resize_bilinear(out, *spec["target_size_factor"]))
+            out = project(ctx.store(nm("average_pooling2d") + "/out", T.avg_pool_valid(src, spec["kernel"])))
+            out = ctx.store(nm("lambda") + "/out", T.resize_bilinear(out, *spec["target_size_factor"]))
         else:
             raise ValueError("Invalid operation.")
         branches.append(out)
-    x = torch.cat(branches, dim=-1)
+    x = ctx.store(nm("concatenate") + "/out", torch.cat(branches, dim=-1))
+    dname = nm("dropout")
     if training and arch["dropout_rate"] > 0:
         if dropout_mask is None:
             raise ValueError("training with dropout needs an explicit mask for parity")
-        x = q(x * dropout_mask)
+        x = ctx.store(dname + "/out", x * dropout_mask)
     enc = project(x)
 
     if arch["boundary_refinement"]:
         low = run_base(image)                   # shared weights, second pass (ss.py:930)
         low = project(low)
         f = int(osd / 2)
-        x = torch.cat([q(T.resize_bilinear(low, f, f)), q(T.resize_bilinear(enc, f, f))], dim=-1)
+        low_up = ctx.store(nm("lambda") + "/out", T.resize_bilinear(low, f, f))
+        enc_up = ctx.store(nm("lambda") + "/out", T.resize_bilinear(enc, f, f))
+        x = ctx.store(nm("concatenate") + "/out", torch.cat([low_up, enc_up], dim=-1))
         up = int(osd / 8 if osd == 16 else osd / 4)
     else:
         x, up = enc, osd
-    logits = _conv(ctx, x, nm("conv2d"), 1, "same", wd)
+    lname = nm("conv2d")
+    logits = ctx.store(lname + "/y", _conv(ctx, x, lname, 1, "same", wd), rounded=False)
     probs = T.softmax(T.resize_bilinear(logits, up, up))
     l2 = sum(ctx.l2_terms) if ctx.l2_terms else torch.zeros((), dtype=image.dtype)
     return dict(logits=logits, probs=probs, l2=l2, new_stats=ctx.new_stats, encoder=enc, features=feats)
 
 
 def loss_and_grads(conf, weights, image, labels, pos_w, neg_w, eps=1e-7, dropout_mask=None, wrt_logits=False,
-                   emulate_bf16=False):
+                   emulate_bf16=False, probe: Optional[Probe] = None):
     """Training-mode forward + backward through autograd: returns (data_loss, l2, grads dict, forward dict)."""
     ws = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith(("moving_mean", "moving_variance"))
               else v) for k, v in weights.items()}
-    out = forward(conf, ws, image, training=True, dropout_mask=dropout_mask, emulate_bf16=emulate_bf16)
+    out = forward(conf, ws, image, training=True, dropout_mask=dropout_mask, emulate_bf16=emulate_bf16, probe=probe)
     C = out["probs"].shape[-1]
     y = T.one_hot(labels, C, out["probs"].dtype)
     data = T.class_balanced_loss(y, out["probs"], pos_w, neg_w, eps)

@@ -5,6 +5,8 @@ import os
 import sys
 
 os.environ["DLV3P_GEMM_DBG_ENABLE"] = "1"
+os.environ.setdefault("DLV3P_LIB", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                             "deeplabv3plus_keras_b200", "libdlv3p_diag.so"))   # DLV3P_DIAG=1 bash csrc/build.sh
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 

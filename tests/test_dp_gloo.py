@@ -64,13 +64,14 @@ def test_two_rank_gradient_exchange_matches_mean_of_shards():
     util.randomize_weights(ss.model)
     w = util.torch_weights(ss.model)
     lam = conf["hps"]["weight_decay"]
+    regularised = {f"{l.name}/kernel" for l in ss.model.flat_layers() if getattr(l, "kernel_regularizer", None) is not None}
     acc = None
     for lo, hi in ((0, 2), (2, 4)):
         _, _, grads, _ = OM.loss_and_grads(conf, w, torch.from_numpy(x[lo:hi]).double(), torch.from_numpy(y[lo:hi]), PW, NW)
         acc = grads if acc is None else {k: acc[k] + grads[k] for k in grads}
     for k, v in acc.items():
         want = (v / 2).numpy().copy()
-        if k.endswith("/kernel") and k.split("/")[0].startswith("conv2d"):
+        if k in regularised:
             want -= 2 * lam * w[k].numpy()
         scale = max(np.abs(want).max(), 1e-3)
         err = np.abs(named[k] - want) / scale

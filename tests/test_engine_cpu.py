@@ -45,9 +45,10 @@ def test_train_step_matches_oracle(cpu_engine, case):
     got = plan.gradients()
     assert set(got) == set(grads), set(got) ^ set(grads)
     lam = conf["hps"]["weight_decay"]
+    regularised = {f"{l.name}/kernel" for l in ss.model.flat_layers() if getattr(l, "kernel_regularizer", None) is not None}
     for k, g in grads.items():
         g = g.numpy().copy()
-        if k.endswith("/kernel") and k.split("/")[0].startswith("conv2d"):
+        if k in regularised:
             g -= 2 * lam * w[k].numpy()       # the engine applies the L2 term inside Adam
         scale = max(np.abs(g).max(), 1e-3)      # gradients that are analytically zero stay at fp32 noise
         # fp32 test double vs fp64 oracle: a ReLU / max-pool decision that flips at a near-tie moves isolated

@@ -1,23 +1,27 @@
-"""Whole-graph parity on the GPU: the product (engine.Plan over libdlv3p kernels) against the oracle graph on the
-same seeded weights / inputs.
+"""Whole-graph parity on the GPU: the product (engine.Plan over libdlv3p kernels, through the C-ABI) against the
+oracle graph on the same seeded weights / inputs.  Tolerances are BASELINE.json's north star: fp32 1e-3, bf16 2e-2,
+>= 99.9 % identical label pixels, gradients at the same tolerance.
 
-fp32 (north_star: logits rtol 1e-3, >= 99.9 % identical argmax pixels, gradients same tolerance):
-    logits within 1e-3 of max|logit| (measured ~2e-5), loss within 1e-4, labels >= 99.9 %.  Gradients of a ReLU /
-    max-pool network are discontinuous in the forward values: a pre-activation within the forward error of zero flips
-    its mask, which moves the gradient by ~sqrt(flip fraction) — measured 1e-5 (no flips) to 8e-3 rms; asserted
-    per-tensor rms-rel < 5e-2 and median < 1.5e-2.
-bf16 (north_star: 2e-2): bf16 STORAGE of a 40-layer random-init network is chaotic — re-running the oracle itself
-    with bf16 rounding at the product's storage points and weights perturbed by 1e-7 (i.e. a different fp32
-    summation order) moves the logits by 1.5 % (Xception/OS8) to 12 % (MobileNetV2/OS16).  No implementation can be
-    closer to another than that noise floor, so the test measures the floor and asserts the product sits on it:
-    dev(product, exact) <= 1.3 dev(oracle_bf16, exact) + 2e-2 and dev(product, oracle_bf16) <= 1.5 floor + 2e-2.
+Three views of one training step (tests/teacher.py):
+
+* FREE-RUNNING oracle: logits, loss, label map, moving statistics of the whole graph (fp32 at 1e-3).
+* TEACHER-FORCED oracle: every stored tensor and every gradient buffer of the real engine schedule is compared with
+  the oracle's result computed FROM THE PRODUCT'S OWN STORED INPUTS of that operation — depthwise stage, pointwise
+  GEMM + BN statistics, BN(+ReLU)(+residual), BN-on-load readers, fused max-pool+BN, concat slices, resizes, dropout,
+  fused decoder tail, and all their backward kernels (dy / dA scratch kept per macro-op) — so each kernel is held to
+  the tolerance in its engine wiring, in fp32 AND in the benchmarked bf16 tensor-core path, with no amplification
+  through the depth of the network.
+* DECISION-FORCED oracle: the oracle runs freely from the image but takes every ReLU / ReLU6 mask and max-pool winner
+  from the product, so both differentiate the same piecewise-smooth function: the whole-graph parameter gradients are
+  held to 1e-3 in fp32, and the decisions on which product and oracle disagree are counted and must lie inside the
+  forward-error band around a tie (the explicit "flip set").
 """
 import numpy as np
 import pytest
 import torch
 
 from oracle import model as OM
-from tests import util
+from tests import teacher, util
 from tests.test_ops_gpu import NW, PW
 
 pytestmark = pytest.mark.gpu
@@ -27,8 +31,16 @@ CASES = [
     dict(base="xception", output_stride=8, image_size=97, refine=True, rate_mult=2),
     dict(base="mobilenetv2", output_stride=16, image_size=129, aspp=util.DEFAULT_ASPP),
     dict(base="mobilenetv2", output_stride=8, image_size=96, refine=True, aspp=util.DEFAULT_ASPP),
+    # what the shipped JSONs leave identity: conv k=1 branch, TRUE image pooling (global average pool + bilinear x8),
+    # a second pyramid level, and Dropout(0.5) with the product's counter-based mask injected into the oracle
+    dict(base="xception", output_stride=16, image_size=129, aspp="global_pool", dropout=0.5),
+    dict(base="mobilenetv2", output_stride=16, image_size=129, aspp="global_pool", dropout=0.5),
 ]
-IDS = [f"{c['base']}-os{c['output_stride']}-{'br' if c.get('refine') else 'plain'}" for c in CASES]
+IDS = ["xception-os16-plain", "xception-os8-br", "mobilenetv2-os16-plain", "mobilenetv2-os8-br",
+       "xception-os16-globalpool-dropout", "mobilenetv2-os16-globalpool-dropout"]
+
+# north-star tolerances
+FP32_TOL, BF16_TOL = 1e-3, 2e-2
 
 
 def rms_rel(a, b):
@@ -41,49 +53,63 @@ def perturbed(w, eps=1e-7, seed=0):
     return {k: v * (1 + eps * torch.randn(v.shape, generator=g, dtype=v.dtype)) for k, v in w.items()}
 
 
-def grad_devs(got, grads, w, lam):
-    """per-tensor rms-rel deviation of the product's parameter gradients (L2 term removed from the oracle's)."""
-    out = {}
-    for k, g in grads.items():
-        g = g.numpy().copy()
-        if k.endswith("/kernel") and k.split("/")[0].startswith("conv2d"):
-            g -= 2 * lam * w[k].numpy()
-        if np.abs(g).max() < 1e-9:            # analytically zero (beta in front of another batch-normalised conv)
-            assert np.abs(got[k]).max() < 1e-4, k
-            continue
-        out[k] = rms_rel(got[k], g)
-    return out
+def check_teacher_forced(res, tol):
+    """Every storage point / gradient buffer / parameter gradient of the engine schedule within `tol` of the oracle
+    evaluated on the same inputs: rms-relative per tensor, and 99.99 % of the elements within 5 tol of the tensor's
+    max (a localised error — a border, a tile tail — cannot hide in the rms)."""
+    assert not res["unused_teacher"], res["unused_teacher"]          # every traced tensor has its oracle counterpart
+    assert not res["missing_grad_points"], res["missing_grad_points"]
+    assert len(res["fwd"]) >= 40 and len(res["bwd"]) >= 40
+    for part in ("fwd", "bwd", "param_tf"):
+        for name, d in res[part].items():
+            assert d["rms"] <= tol, (part, name, d)
+            assert d["q9999"] <= 5 * tol, (part, name, d)
+    for name, v in res["param_zero"].items():
+        assert v <= 1e-3, ("analytically zero gradient", name, v)
+    a, b = res["loss_tf"]
+    assert abs(a - b) <= (1e-5 if tol == FP32_TOL else 2e-3) * max(1.0, abs(b)), (a, b)
 
 
-def run_product(conf, B=2):
-    from deeplabv3plus_keras_b200.engine import Plan
-    ss = util.build(conf)
-    util.randomize_weights(ss.model)
-    plan = Plan(ss.model, B, training=True)
-    x, y = util.synthetic_batch(conf, B, plan.out_shape[1:3])
-    plan.set_loss(PW, NW)
-    plan.load_batch(x, y)
-    plan.step_fwd_bwd()
-    plan.regularization()
-    torch.cuda.synchronize()
-    return ss, plan, x, y
+def check_decisions(res, band, max_fraction):
+    """The explicit flip set: decisions (ReLU masks, ReLU6 clamps, max-pool winners) on which the product and the
+    free-running oracle disagree must be near-ties — |pre-activation| (or the winner's margin over the runner-up)
+    below `band` x the tensor's mean magnitude — and rare."""
+    assert not res["unused_sites"] and not res["unforced_sites"], (res["unused_sites"], res["unforced_sites"])
+    n = sum(f["count"] for f in res["flips"].values())
+    tot = sum(f["total"] for f in res["flips"].values())
+    assert n <= max_fraction * tot, (n, tot)
+    for site, f in res["flips"].items():
+        assert f["worst_margin"] <= band, (site, f)
 
 
 @pytest.mark.parametrize("case", CASES, ids=IDS)
 def test_train_step_parity_fp32(case):
     conf = util.make_conf(dtype="float32", **case)
-    ss, plan, x, y = run_product(conf)
+    res = teacher.run(conf)
+    print(teacher.summarize(res))
+    ss, plan, x, y = res["ss"], res["plan"], res["x"], res["y"]
+    # free-running oracle: logits / loss / labels / moving statistics
     w = util.torch_weights(ss.model)
-    data, l2, grads, out = OM.loss_and_grads(conf, w, torch.from_numpy(x).double(), torch.from_numpy(y), PW, NW)
+    drop = None
+    if case.get("dropout"):
+        (name,) = plan.dropout_sites
+        drop = plan.dropout_mask(name).cpu().double()
+    data, l2, grads, out = OM.loss_and_grads(conf, w, torch.from_numpy(x).double(), torch.from_numpy(y), PW, NW,
+                                             dropout_mask=drop)
     ref = out["logits"].detach().numpy()
     got = plan.logits.buf.float().cpu().numpy()
-    assert np.abs(got - ref).max() < 1e-3 * np.abs(ref).max()
+    assert np.abs(got - ref).max() < FP32_TOL * np.abs(ref).max()
     assert abs(plan.loss_value() - float(data + l2)) < 1e-4 * max(1.0, abs(float(data)))
-    devs = grad_devs(plan.gradients(), grads, w, conf["hps"]["weight_decay"])
+    zh = plan.logits_highres().cpu().numpy()
+    assert (zh.argmax(-1) == out["probs"].detach().numpy().argmax(-1)).mean() >= 0.999
     assert set(plan.gradients()) == set(grads)
-    worst = max(devs, key=devs.get)
-    assert devs[worst] < 5e-2, (worst, devs[worst])
-    assert np.median(list(devs.values())) < 1.5e-2
+    # every kernel in its engine wiring, forward and backward, on identical inputs
+    check_teacher_forced(res, FP32_TOL)
+    # whole-graph gradients at the north-star tolerance, given the same decisions; the flip set is explicit
+    for name, d in res["param_df"].items():
+        assert d["rms"] <= FP32_TOL, ("decision-forced whole-graph gradient", name, d)
+    assert res["logits_df"]["rms"] <= FP32_TOL
+    check_decisions(res, band=1e-4, max_fraction=1e-4)
     plan.params.download()
     for k, v in out["new_stats"].items():
         np.testing.assert_allclose(ss.model.named_weights()[k], v.numpy(), rtol=2e-3, atol=1e-4, err_msg=k)
@@ -91,30 +117,63 @@ def test_train_step_parity_fp32(case):
 
 @pytest.mark.parametrize("case", CASES, ids=IDS)
 def test_train_step_parity_bf16(case):
+    """The benchmarked path (bf16 storage, tcgen05 GEMMs with TMA-store epilogue statistics, TMA depthwise kernels
+    with BN+ReLU on load, dgrad + BN reductions, fused max-pool + BN, implicit 3x3 conv) at the north-star bf16
+    tolerance, operation by operation in its engine wiring (teacher-forced), against the oracle with bf16 rounding at
+    the product's storage points."""
     conf = util.make_conf(dtype="bfloat16", **case)
-    ss, plan, x, y = run_product(conf)
-    w = util.torch_weights(ss.model)
-    xin = torch.from_numpy(x).to(torch.bfloat16).double()         # the product stores the image in bf16
-    yt = torch.from_numpy(y)
-    lam = conf["hps"]["weight_decay"]
-    d_ex, l2, g_ex, o_ex = OM.loss_and_grads(conf, w, xin, yt, PW, NW)
-    d_em, _, g_em, o_em = OM.loss_and_grads(conf, w, xin, yt, PW, NW, emulate_bf16=True)
-    w2 = perturbed(w)
-    _, _, g_em2, o_em2 = OM.loss_and_grads(conf, w2, xin, yt, PW, NW, emulate_bf16=True)
-    exact, emu, emu2 = (o["logits"].detach().numpy() for o in (o_ex, o_em, o_em2))
-    got = plan.logits.buf.float().cpu().numpy()
-    floor = rms_rel(emu2, emu)                  # bf16 chaos: same algorithm, different fp32 summation order
-    dev_emu_exact = rms_rel(emu, exact)
-    assert rms_rel(got, exact) <= 1.3 * dev_emu_exact + 2e-2, (rms_rel(got, exact), dev_emu_exact)
-    assert rms_rel(got, emu) <= 1.5 * floor + 2e-2, (rms_rel(got, emu), floor)
-    assert abs(plan.loss_value() - float(d_em + l2)) < 2e-2 * max(1.0, abs(float(d_em)))
-    # gradients: the product's deviation from the bf16 oracle vs the bf16 oracle's own chaos floor
-    mine = grad_devs(plan.gradients(), g_em, w, lam)
-    floor_g = grad_devs({k: v.numpy() - (2 * lam * w2[k].numpy() if (k.endswith("/kernel") and
-                                                                    k.split("/")[0].startswith("conv2d")) else 0)
-                         for k, v in g_em2.items()}, g_em, w, lam)
-    m_mine, m_floor = np.median(list(mine.values())), np.median(list(floor_g.values()))
-    assert m_mine <= 1.5 * m_floor + 5e-2, (m_mine, m_floor)
+    res = teacher.run(conf)
+    print(teacher.summarize(res))
+    check_teacher_forced(res, BF16_TOL)
+    check_decisions(res, band=5e-2, max_fraction=2e-2)      # bf16 storage: decisions can differ within a bf16 ulp of a tie
+    # whole graph, same decisions: what is left is bf16 rounding noise accumulated smoothly through the depth
+    assert res["logits_df"]["rms"] <= 5 * BF16_TOL, res["logits_df"]
+    a, b = res["loss_df"]
+    assert abs(a - b) <= BF16_TOL * max(1.0, abs(b)), (a, b)
+
+
+def test_cfg2_full_image_size_vs_oracle():
+    """BASELINE cfg-2 at its real geometry (Xception OS16, 513 x 513 -> 512 x 512 x 21; batch 2 so the fp64 oracle
+    finishes in seconds): the shapes that only exist at full size — M = 129 032 row GEMMs, [2,254,254,128] TMA depthwise
+    tiles, the fused max-pool+BN on the 254^2 / 127^2 / 64^2 maps — in fp32 and in the benchmarked bf16 path."""
+    for dtype, tol in (("bfloat16", BF16_TOL), ("float32", FP32_TOL)):
+        conf = util.make_conf(dtype=dtype, base="xception", output_stride=16, image_size=513, dropout=0.5)
+        res = teacher.run(conf, decision_forced=(dtype == "float32"))
+        print(dtype, teacher.summarize(res))
+        assert res["plan"].out_shape == (2, 512, 512, 21)
+        check_teacher_forced(res, tol)
+        if dtype == "float32":
+            for name, d in res["param_df"].items():
+                assert d["rms"] <= FP32_TOL, (name, d)
+            check_decisions(res, band=1e-4, max_fraction=1e-4)
+            out = res["out_df"]
+            zh = res["plan"].logits_highres().cpu().numpy()
+            assert (zh.argmax(-1) == out["probs"].detach().numpy().argmax(-1)).mean() >= 0.999
+        del res
+        torch.cuda.empty_cache()
+
+
+def test_loss_trajectory_bf16_follows_fp32():
+    """50 optimizer steps on the same batches: the bf16 product's loss curve stays within 2 % of the fp32 product's
+    (same data, same initial weights, dropout off so that both see the same function)."""
+    from deeplabv3plus_keras_b200.trainer import Trainer
+    curves = {}
+    for dtype in ("float32", "bfloat16"):
+        conf = util.make_conf(dtype=dtype, base="xception", output_stride=16, image_size=129)
+        ss = util.build(conf)
+        util.randomize_weights(ss.model)
+        ss.model.optimizer.lr = 3e-4
+        tr = Trainer(ss.model, 4)
+        batches = []
+        for k in range(5):
+            x, y = util.synthetic_batch(conf, 4, tr.plan.out_shape[1:3], seed=100 + k)
+            batches.append((torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()))
+        curves[dtype] = np.array([tr.train_step_e2e(*batches[i % 5]) for i in range(50)])
+    a, b = curves["float32"], curves["bfloat16"]
+    assert np.isfinite(a).all() and np.isfinite(b).all()
+    assert a[-5:].mean() < 0.8 * a[:5].mean(), a                      # it trains
+    rel = np.abs(b - a) / np.abs(a)
+    assert rel.max() <= 0.02, (float(rel.max()), int(rel.argmax()), a[:5], b[:5])
 
 
 def _calibrated(conf, ss, x, dtype):
@@ -293,10 +352,11 @@ def test_golden_fixtures_gpu(name):
     lam = conf["hps"]["weight_decay"]
     mine = plan.gradients()
     named = ss.model.named_weights()
+    regularised = {f"{l.name}/kernel" for l in ss.model.flat_layers() if getattr(l, "kernel_regularizer", None) is not None}
     for k in g["grad_keys"]:
         k = str(k)
         want = g["grad/" + k].copy()
-        if k.endswith("/kernel") and k.split("/")[0].startswith("conv2d"):
+        if k in regularised:
             want -= 2 * lam * named[k]          # the product applies the L2 term inside the Adam kernel
         if np.abs(want).max() < 1e-9:
             continue

@@ -154,6 +154,40 @@ def test_dwconv3x3_dgrad_bnred(case, act):
                                 code, mean.to(DEV), invstd.to(DEV), red, pad=pad)       # fp32: unfused path only
 
 
+@pytest.mark.parametrize("ratio", [5.0, 40.0])
+def test_dwconv3x3_dgrad_bnred_large_mean_over_std(ratio):
+    """The fused kernel finishes sum g*xhat from sum g*y and sum g (it has no second pass over y).  With a channel
+    mean `ratio` standard deviations away from zero the two terms cancel to 1/ratio of their size: the reductions must
+    still hold 1e-2 against fp64 on identical bf16 inputs (review finding: cancellation in the fp32 atomics)."""
+    o = ops()
+    N, H, W, C = 4, 33, 33, 128
+    g = torch.Generator().manual_seed(11)
+    std = 0.5
+    mean = (torch.rand(C, generator=g) * 2 - 1).sign() * ratio * std
+    y = (torch.randn((N, H, W, C), generator=g) * std + mean).to(torch.bfloat16)
+    mean_b = y.double().mean((0, 1, 2))
+    invstd = 1.0 / torch.sqrt(y.double().var((0, 1, 2), unbiased=False) + 1e-3)
+    w = rnd((3, 3, C), torch.float32, 2, 0.3)
+    gamma = rnd((C,), torch.float32, 3, 0.2) + 1.0
+    sc = (gamma.double() * invstd).float()
+    sh = (0.1 - mean_b * sc.double()).float()
+    gy = rnd((N, H, W, C), torch.bfloat16, 5)
+    pad = dw_pad(H, W, 1, (1, 1), "same")
+    zr = torch.zeros((N, H, W, C), dtype=torch.float64, requires_grad=True)
+    O.depthwise_conv2d(zr, w.double().view(3, 3, C, 1), 1, "same", (1, 1)).backward(gy.double())
+    pre = y.double() * sc.double() + sh.double()
+    g_ref = zr.grad * (pre > 0).double()
+    s1 = g_ref.sum((0, 1, 2))
+    s2 = (g_ref * (y.double() - mean_b) * invstd).sum((0, 1, 2))
+    red = torch.zeros(2 * C, dtype=torch.float32, device=DEV)
+    o.dwconv3x3_dgrad_bnred(gy.to(DEV), w.to(DEV), (N, H, W, C), y.to(DEV), sc.to(DEV), sh.to(DEV), o.ACT_RELU,
+                            mean_b.float().to(DEV), invstd.float().to(DEV), red, pad=pad)
+    got = red.double().cpu()
+    scale2 = float(s2.abs().mean())
+    assert float((got[:C] - s1).abs().max()) <= 1e-2 * float(s1.abs().mean())
+    assert float((got[C:] - s2).abs().max()) <= 1e-2 * scale2, (float((got[C:] - s2).abs().max()), scale2)
+
+
 @pytest.mark.parametrize("case", [(2, 20, 37, 32, 64), (1, 9, 131, 32, 64), (2, 12, 260, 40, 128), (1, 5, 3, 32, 64)])
 def test_conv3x3_valid_implicit_gemm(case):
     """Implicit-GEMM 3x3 VALID stride-1 convolution (overlapping-row tensor maps, no im2col matrix): forward with BN
