@@ -1,20 +1,28 @@
 #!/usr/bin/env python
-"""Headline benchmark: img/s of the DeepLabV3+ (reference-truncated Xception, OS16, 513x513, 21 classes) training
-step — forward + loss + backward (+ NCCL gradient all-reduce for N>1) + Adam — on N B200s, one process per GPU.
+"""Benchmarks of the DeepLabV3+ hot path on N B200s, one process per GPU.
 
-  python bench.py --gpus 1 --steps 20 --warmup 5
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+  python bench.py [--config cfg2] --gpus 1 --steps 20 --warmup 5
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \\
          bench.py --gpus N --steps K --warmup W
   python bench.py --impl reference ...     # the CPU restatement of the reference graph on the host cores
+  torchrun ... bench.py --gpus N --check   # data-parallel correctness: N ranks, same batch == 1-GPU run
 
-Prints ONE JSON line (rank 0).  `value` = whole-job img/s with inputs resident in HBM; `e2e` = the same through
-Trainer.train_step_e2e (pinned host batch -> H2D -> step -> D2H loss, next batch's H2D prefetched behind the step); `roofline` = the dominant kernel family
-measured with CUDA events in an instrumented eager pass of the same step; `cpu_baseline` = the oracle
-(PyTorch-CPU restatement of the reference's TF graph; TF 2.4 itself is not installable offline) on a bounded sample.
+Default (`cfg2`, BASELINE.json's headline): img/s of the training step — forward + class-balanced loss + backward
+(+ NCCL gradient all-reduce for N>1) + Adam — of the reference-truncated Xception, OS16, 513x513, 21 classes, batch
+16 per GPU, bf16.  `--config cfg1|cfg3|cfg4|cfg5` run BASELINE.json's other configurations through the same code.
+
+Prints ONE JSON line (rank 0).  `value` = whole-job img/s with inputs resident in HBM; `e2e` = the same through the
+user-facing call (pinned host batch -> H2D -> step -> D2H result); `roofline` / `kernels` = per-kernel durations of the
+REPLAYED CUDA graph (CUPTI activity records, serialised single-stream replay so that the durations add up to the
+step), attributed to the C-ABI calls that launched them, with algorithmic flops / bytes counted on the logical
+(Keras) channel counts; `cpu_baseline` = the oracle (PyTorch-CPU restatement of the reference's TF graph; TF 2.4
+itself is not installable offline) on a bounded sample.
 """
 from __future__ import annotations
 
 import argparse
+import bisect
+import collections
 import copy
 import json
 import os
@@ -37,40 +45,81 @@ ASPP = [
     {"kernel": 3, "rate": [18, 18], "op": "conv", "input": 0},
     {"kernel": 1, "rate": [1, 1], "op": "pyramid_pooling", "input": 0, "target_size_factor": [1, 1]},
 ]
+DEFAULT_ASPP = [   # conf.json:39-45 (asymmetric rates, chained branches)
+    {"kernel": 3, "rate": [1, 1], "op": "conv", "input": -1},
+    {"kernel": 3, "rate": [18, 15], "op": "conv", "input": 0},
+    {"kernel": 3, "rate": [6, 3], "op": "conv", "input": 1},
+    {"kernel": 3, "rate": [1, 1], "op": "conv", "input": 0},
+    {"kernel": 3, "rate": [6, 21], "op": "conv", "input": 0},
+]
 SS_NW = [0.70245001, 0.00893111, 0.00763626, 0.00877043, 0.00649604, 0.00544513, 0.01271576, 0.01909554, 0.03116511,
          0.01246875, 0.00623611, 0.01057388, 0.02777125, 0.00919422, 0.01154691, 0.07393348, 0.00606626, 0.00625678,
          0.01217829, 0.01340344, 0.00766524]
-FLOP_PER_IMG_FWD_BWD = 142.3e9       # SURVEY.md §8(d) ledger, Xception(ref-truncated)/OS16/513^2
-WORKLOAD = ("Xception(ref-truncated, block13_sepconv2_bn tap) OS16 513x513x3 -> 512x512x21, batch {batch}/GPU, "
-            "fwd + class-balanced loss + bwd + Adam, training-mode BN, dropout 0.5, random init")
+
+# BASELINE.json `configs` (same order); GFLOP per image from the SURVEY.md §8(d) ledger / BASELINE.md §3
+CONFIGS = {
+    "cfg1": dict(base="mobilenetv2", os=16, size=513, classes=21, aspp=DEFAULT_ASPP, refine=False, mult=1, batch=1,
+                 dtype="float32", train=False, gflop_img=4.45, scaling="weak",
+                 metric="img/s DeepLabV3+ MobileNetV2 OS16 513^2 inference",
+                 workload="MobileNetV2(block_12_add tap) + default-JSON ASPP + decoder, 513x513x3 -> 528x528 labels, "
+                          "batch {batch}/GPU, inference, random init"),
+    "cfg2": dict(base="xception", os=16, size=513, classes=21, aspp=ASPP, refine=False, mult=1, batch=16,
+                 dtype="bfloat16", train=True, gflop_img=142.3, scaling="weak",
+                 metric="img/s DeepLabV3+ Xception OS16 513^2 fwd+bwd",
+                 workload="Xception(ref-truncated, block13_sepconv2_bn tap) OS16 513x513x3 -> 512x512x21, batch "
+                          "{batch}/GPU, fwd + class-balanced loss + bwd + Adam, training-mode BN, dropout 0.5, random init"),
+    "cfg3": dict(base="xception", os=16, size=513, classes=21, aspp=ASPP, refine=False, mult=1, batch=None,
+                 global_batch=128, dtype="bfloat16", train=True, gflop_img=142.3, scaling="strong",
+                 metric="img/s DeepLabV3+ Xception OS16 513^2 fwd+bwd, global batch 128",
+                 workload="Xception(ref-truncated) OS16 513x513x3 -> 512x512x21, GLOBAL batch 128 ({batch}/GPU), data "
+                          "parallel, fwd + class-balanced loss + bwd + all-reduce + Adam, dropout 0.5, random init"),
+    "cfg4": dict(base="xception", os=8, size=513, classes=21, aspp=ASPP, refine=True, mult=2, batch=16,
+                 dtype="bfloat16", train=True, gflop_img=143.2, scaling="weak",
+                 metric="img/s DeepLabV3+ Xception OS8 (rates x2) + boundary refinement 513^2 fwd+bwd",
+                 workload="Xception(block4_sepconv2_bn tap) OS8, ASPP rates 2/12/24/36, boundary refinement, 513x513x3 -> "
+                          "512x512x21, batch {batch}/GPU, fwd + loss + bwd + Adam, dropout 0.5, random init"),
+    "cfg5": dict(base="mobilenetv2", os=16, size=[1024, 2048], classes=19, aspp=ASPP, refine=False, mult=1, batch=8,
+                 dtype="bfloat16", train=False, gflop_img=32.7, scaling="weak",
+                 metric="img/s DeepLabV3+ MobileNetV2 OS16 1024x2048 19-class inference",
+                 workload="MobileNetV2(block_12_add tap) OS16 1024x2048x3 -> 1024x2048 labels (19 classes), batch "
+                          "{batch}/GPU, inference, random init"),
+}
 
 
-def make_conf(dtype, image_size=513):
-    return {
-        "mode": "train", "resource_path": "", "model_loading": False, "base_model": "xception", "base_weights": None,
+def make_conf(dtype, image_size=513, cfg="cfg2"):
+    c = CONFIGS[cfg]
+    size = c["size"] if cfg != "cfg2" else image_size
+    conf = {
+        "mode": "train", "resource_path": "", "model_loading": False, "base_model": c["base"], "base_weights": None,
         "hps": {"dtype": dtype, "lr": 1e-4, "beta_1": 0.5, "beta_2": 0.99, "decay": 0.0, "epochs": 1,
                 "batch_size": 16, "weight_decay": 4e-5, "bn_momentum": 0.9, "bn_scale": True,
                 "reduce_lr_factor": 0.99},
-        "nn_arch": {"boundary_refinement": False, "output_stride": 16, "image_size": image_size, "num_classes": 21,
-                    "mv2_depth_multiplier": 1, "depth_multiplier": 1, "conv_rate_multiplier": 1,
-                    "reduction_size": 256, "dropout_rate": 0.5, "concat_channels": 256,
-                    "encoder_middle_conf": copy.deepcopy(ASPP)},
+        "nn_arch": {"boundary_refinement": c["refine"], "output_stride": c["os"], "image_size": size,
+                    "num_classes": c["classes"], "mv2_depth_multiplier": 1, "depth_multiplier": 1,
+                    "conv_rate_multiplier": c["mult"], "reduction_size": 256, "dropout_rate": 0.5,
+                    "concat_channels": 256, "encoder_middle_conf": copy.deepcopy(c["aspp"])},
     }
+    if c["classes"] != 21:
+        f = np.random.default_rng(7).dirichlet(np.ones(c["classes"]))
+        conf["class_weights"] = {"pos": list(1.0 - f), "neg": list(f)}
+    return conf
 
 
 def synthetic(conf, batch, out_hw, seed):
     """images U(-1,1) (ss.py:1532); labels: rectangles over background, classes drawn ~ VOC pixel frequencies."""
     rng = np.random.default_rng(seed)
     s = conf["nn_arch"]["image_size"]
-    x = rng.uniform(-1, 1, (batch, s, s, 3)).astype(np.float32)
+    h, w = (s, s) if isinstance(s, int) else s
+    C = conf["nn_arch"]["num_classes"]
+    x = rng.uniform(-1, 1, (batch, h, w, 3)).astype(np.float32)
     y = np.zeros((batch,) + tuple(out_hw), dtype=np.int32)
-    p = np.asarray(SS_NW[1:]) / np.sum(SS_NW[1:])
+    p = np.asarray(SS_NW[1:C]) / np.sum(SS_NW[1:C])
     for b in range(batch):
         for _ in range(rng.integers(4, 13)):
-            c = 1 + int(rng.choice(20, p=p))
-            h, w = rng.integers(16, out_hw[0] // 3), rng.integers(16, out_hw[1] // 3)
-            y0, x0 = rng.integers(0, out_hw[0] - h), rng.integers(0, out_hw[1] - w)
-            y[b, y0:y0 + h, x0:x0 + w] = c
+            c = 1 + int(rng.choice(C - 1, p=p))
+            bh, bw = rng.integers(16, out_hw[0] // 3), rng.integers(16, out_hw[1] // 3)
+            y0, x0 = rng.integers(0, out_hw[0] - bh), rng.integers(0, out_hw[1] - bw)
+            y[b, y0:y0 + bh, x0:x0 + bw] = c
     return x, y
 
 
@@ -92,8 +141,19 @@ def he_init(model, seed=1024):
         l.set_weights(vals)
 
 
+def build_model(conf):
+    from deeplabv3plus_keras_b200 import keras
+    from deeplabv3plus_keras_b200.deeplab import SemanticSegmentation
+    keras.reset_uids()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ss = SemanticSegmentation(conf)
+    he_init(ss.model)
+    return ss
+
+
 class ClockSampler(threading.Thread):
-    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML is polled every 20 ms
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML is polled every 2 ms
     (nvidia-smi takes longer than that per query and would give one sample for a 0.2 s region); nvidia-smi is the
     fallback when pynvml is unavailable."""
 
@@ -152,62 +212,261 @@ class ClockSampler(threading.Thread):
                 "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
-def cpu_baseline(steps=2, warmup=1, batch=2, threads=None):
-    """The reference graph restated on the CPU (oracle, PyTorch-CPU fp32), fwd+bwd, `batch` images per step."""
-    from deeplabv3plus_keras_b200 import keras
-    from deeplabv3plus_keras_b200.deeplab import SemanticSegmentation, ss_nw, ss_pw
+# ---------------------------------------------------------------------------------------------- CPU baseline
+def cpu_baseline(cfg="cfg2", steps=2, warmup=1, threads=None):
+    """The reference graph restated on the CPU (oracle, PyTorch-CPU fp32) on a bounded sample of the config's
+    workload: training configs run fwd+bwd on 2 images, inference configs the forward pass on 1 image."""
+    from deeplabv3plus_keras_b200.deeplab import ss_nw, ss_pw
     from oracle import model as OM
 
+    c = CONFIGS[cfg]
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
-    conf = make_conf("float32")
+    conf = make_conf("float32", cfg=cfg)
     conf["nn_arch"]["dropout_rate"] = 0.0
-    keras.reset_uids()
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        ss = SemanticSegmentation(conf)
-    he_init(ss.model)
+    ss = build_model(conf)
     w = {k: torch.from_numpy(v.copy()) for k, v in ss.model.named_weights().items()}
-    x, y = synthetic(conf, batch, (512, 512), 1024)
+    batch = 2 if c["train"] else 1
+    out_hw = tuple(ss.model.outputs[0].shape[1:3])
+    x, y = synthetic(conf, batch, out_hw, 1024)
     xt, yt = torch.from_numpy(x), torch.from_numpy(y)
+    pw, nw = (ss_pw, ss_nw) if c["classes"] == 21 else (conf["class_weights"]["pos"], conf["class_weights"]["neg"])
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        OM.loss_and_grads(conf, w, xt, yt, ss_pw, ss_nw)
+        if c["train"]:
+            OM.loss_and_grads(conf, w, xt, yt, pw, nw)
+        else:
+            with torch.no_grad():
+                OM.forward(conf, w, xt, training=False)["probs"].argmax(-1)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
-    sec = float(np.mean(times))
+    sec = float(np.median(times))
+    what = "fwd+bwd" if c["train"] else "inference (forward + argmax)"
     return {"value": batch / sec, "unit": "img/s", "cores": threads, "kind": "port",
-            "sample": f"{steps} steps of batch {batch} (of the 16-image workload), Xception OS16 513^2 fwd+bwd fp32, "
-                      f"PyTorch-CPU restatement of the reference TF graph (TF 2.4 not installable offline)",
+            "sample": f"{steps} steps of batch {batch} of the {cfg} workload, {what}, fp32, PyTorch-CPU restatement of "
+                      f"the reference TF graph (TF 2.4 not installable offline)",
             "ms_per_step": sec * 1e3}
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    cb = cpu_baseline(steps=steps, warmup=min(max(args.warmup, 0), 1), batch=2)
-    line = {"impl": "reference", "metric": "img/s DeepLabV3+ Xception OS16 513^2 fwd+bwd", "value": cb["value"],
-            "unit": "img/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
-            "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    c = CONFIGS[args.config]
+    steps = max(1, min(args.steps, 3 if c["train"] else 10))
+    warm = min(max(args.warmup, 0), 1 if c["train"] else 3)
+    cb = cpu_baseline(args.config, steps=steps, warmup=warm)
+    batch = c["batch"] or c["global_batch"] // max(args.gpus, 1)
+    line = {"impl": "reference", "metric": c["metric"], "value": cb["value"],
+            "unit": "img/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": c["scaling"], "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD.format(batch=16), "global_batch": 16, "parallelism": "cpu",
-                       "sample": "each step = 2 images of the 16-image batch on the host cores (bounded sample)"},
+            "config": {"workload": c["workload"].format(batch=batch), "name": args.config,
+                       "global_batch": batch * args.gpus, "parallelism": "cpu",
+                       "sample": "each step = a bounded sample of the batch on the host cores (see cpu_baseline.sample)"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------- graph kernel profile
+def graph_kernel_profile(eager_fn, replay_fn, logical, steps=3):
+    """Per-C-ABI-call durations INSIDE the replayed CUDA graph.
+
+    1. one eager pass under the profiler with every C-ABI call wrapped in a record_function range: CUPTI's kernel
+       records are tied to their launch calls by correlation id, the launch calls lie inside the ranges -> the ordered
+       kernel sequence of the step with the owning C-ABI call (name + arguments) of every kernel;
+    2. `steps` replays of the (serialised, single-stream) graph under the profiler: the same kernel sequence with its
+       in-graph durations.
+    Returns (per-call records [{name, args, us}], other_us per step (kernels of torch ops in the step), n_kernels)."""
+    from torch.profiler import ProfilerActivity, profile, record_function
+
+    from deeplabv3plus_keras_b200 import _lib
+
+    calls = []
+
+    class Hook:
+        def before(self, name, args):
+            calls.append((name, args))
+            rf = record_function(f"dlv3p#{len(calls) - 1}")
+            rf.__enter__()
+            return rf
+
+        def after(self, tok):
+            tok.__exit__(None, None, None)
+
+    _lib.PROFILER = Hook()
+    try:
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            eager_fn()
+            torch.cuda.synchronize()
+    finally:
+        _lib.PROFILER = None
+    evs = prof.profiler.kineto_results.events()
+    ranges, launch_start, kernels = [], {}, []
+    for e in evs:
+        name = e.name()
+        dev = str(e.device_type())
+        if "CUDA" in dev:
+            if not name.startswith(("Memset", "Memcpy")):
+                kernels.append(e)
+        elif name.startswith("dlv3p#"):
+            ranges.append((e.start_ns(), e.start_ns() + e.duration_ns(), int(name[6:])))
+        elif name.startswith(("cudaLaunch", "cuLaunch")):
+            launch_start[e.correlation_id()] = e.start_ns()
+    ranges.sort()
+    starts = [r[0] for r in ranges]
+    kernels.sort(key=lambda e: e.start_ns())
+    seq = []                                            # (kernel name, owning call index or -1)
+    for k in kernels:
+        t = launch_start.get(k.correlation_id(), launch_start.get(k.linked_correlation_id()))
+        owner = -1
+        if t is not None:
+            i = bisect.bisect_right(starts, t) - 1
+            if i >= 0 and ranges[i][0] <= t <= ranges[i][1]:
+                owner = ranges[i][2]
+        seq.append((k.name(), owner))
+
+    with profile(activities=[ProfilerActivity.CUDA]) as prof2:
+        for _ in range(steps):
+            replay_fn()
+        torch.cuda.synchronize()
+    gk = [e for e in prof2.profiler.kineto_results.events()
+          if "CUDA" in str(e.device_type()) and not e.name().startswith(("Memset", "Memcpy"))]
+    gk.sort(key=lambda e: e.start_ns())
+    n = len(seq)
+    info = {"kernels_per_step": n, "graph_kernels": len(gk), "aligned": False}
+    if n == 0 or len(gk) != n * steps or any(gk[i].name() != seq[i % n][0] for i in range(len(gk))):
+        # alignment failed (a torch op chose another kernel under capture, ...): kernel-name level only
+        by_name = collections.defaultdict(lambda: [0, 0.0])
+        for e in gk:
+            by_name[e.name()][0] += 1
+            by_name[e.name()][1] += e.duration_ns() / 1e3
+        info["by_kernel_name"] = {k.split("(")[0][-80:]: {"launches_per_step": v[0] / steps, "us_per_step": v[1] / steps}
+                                  for k, v in sorted(by_name.items(), key=lambda kv: -kv[1][1])[:30]}
+        info["sum_kernel_ms"] = sum(v[1] for v in by_name.values()) / steps / 1e3
+        return None, info
+    info["aligned"] = True
+    per_call = [dict(name=nm, args=[logical.get(a, a) if isinstance(a, int) and not isinstance(a, bool) else a
+                                    for a in args], us=0.0, kernels=[]) for nm, args in calls]
+    other = collections.defaultdict(float)
+    for i, e in enumerate(gk):
+        kname, owner = seq[i % n]
+        us = e.duration_ns() / 1e3 / steps
+        if owner >= 0:
+            per_call[owner]["us"] += us
+            if i < n:
+                per_call[owner]["kernels"].append(kname.split("(")[0].replace("dlv3p::", "").replace("void ", "")[:60])
+        else:
+            other[kname.split("(")[0][-60:]] += us
+    info["other_us"] = dict(other)
+    info["sum_kernel_ms"] = (sum(c["us"] for c in per_call) + sum(other.values())) / 1e3
+    # span of one replay on the device (first kernel start -> last kernel end), averaged
+    spans = [(gk[(s + 1) * n - 1].start_ns() + gk[(s + 1) * n - 1].duration_ns() - gk[s * n].start_ns()) / 1e6
+             for s in range(steps)]
+    info["graph_span_ms"] = float(np.mean(spans))
+    return per_call, info
+
+
+def summarise_calls(per_call, peaks_tc, peak_hbm):
+    from deeplabv3plus_keras_b200 import profiler as PR
+    agg = collections.OrderedDict()
+    shapes = collections.defaultdict(lambda: dict(calls=0, us=0.0, bytes=0, flops=0))
+    for c in per_call:
+        b, f = PR.cost(c["name"], c["args"])
+        a = agg.setdefault(c["name"], dict(calls=0, us=0.0, bytes=0, flops=0, kernels=set()))
+        a["calls"] += 1; a["us"] += c["us"]; a["bytes"] += b; a["flops"] += f
+        a["kernels"].update(c["kernels"])
+        sig = tuple(v for v in c["args"] if isinstance(v, int) and not isinstance(v, bool) and 0 <= v < (1 << 24))
+        s = shapes[(c["name"], sig)]
+        s["calls"] += 1; s["us"] += c["us"]; s["bytes"] += b; s["flops"] += f
+    out = collections.OrderedDict()
+    for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
+        bound = PR.COSTS.get(name, ("hbm",))[0]
+        sec = max(a["us"], 1e-9) / 1e6
+        gbps, tf = a["bytes"] / sec / 1e9, a["flops"] / sec / 1e12
+        out[name] = {"calls_per_step": a["calls"], "ms_per_step": a["us"] / 1e3, "GBps": round(gbps, 1),
+                     "TFLOPs": round(tf, 2), "bound": bound,
+                     "frac": round(tf / peaks_tc if bound == "tensor" else gbps / peak_hbm, 4),
+                     "kernels": sorted(a["kernels"])[:6]}
+    rows = []
+    for (name, sig), s in shapes.items():
+        sec = max(s["us"], 1e-9) / 1e6
+        rows.append(dict(kernel=name, args=list(sig), calls=s["calls"], us_per_step=s["us"],
+                         avg_us=s["us"] / s["calls"], GBps=s["bytes"] / sec / 1e9, TFLOPs=s["flops"] / sec / 1e12))
+    rows.sort(key=lambda r: -r["us_per_step"])
+    return out, rows
+
+
+# ---------------------------------------------------------------------------------------------- DP correctness
+def run_check(args, rank, local_rank, world):
+    """Data-parallel correctness ON HARDWARE: every rank trains on the SAME batch with the product Trainer (prefix
+    all-reduces behind the backward graph segments, 1/world in Adam), so the averaged gradient equals the single-GPU
+    gradient and after k steps every rank's weights and loss must equal a 1-GPU run of the same batch (rank 0 runs
+    that reference in-process with world=1) up to the noise of fp32 atomics / bf16 re-quantisation."""
+    import torch.distributed as dist
+
+    from deeplabv3plus_keras_b200.trainer import Trainer
+    torch.cuda.set_device(local_rank)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    dtype = args.dtype
+    conf = make_conf(dtype, image_size=257)
+    conf["nn_arch"]["dropout_rate"] = 0.0               # replicas draw independent dropout masks by design
+    B, K = 4, 5
+    res = {}
+    for mode in ("dp", "single"):
+        if mode == "single" and rank != 0:
+            continue
+        ss = build_model(conf)
+        ss.model.optimizer.lr = 1e-3
+        tr = Trainer(ss.model, B, process_group=dist.group.WORLD if mode == "dp" else None, buckets=args.buckets)
+        x, y = synthetic(conf, B, tr.plan.out_shape[1:3], 4242)     # the same batch on every rank
+        xs, ys = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
+        losses = [tr.train_step_e2e(xs, ys) for _ in range(K)]
+        torch.cuda.synchronize()
+        res[mode] = (np.array(losses), tr.plan.params.w.clone(), tr.plan.params.f.clone(), tr.plan.params.g.clone())
+    # all ranks hold identical weights after K steps
+    w = res["dp"][1]
+    ref = w.clone()
+    dist.broadcast(ref, 0)
+    same = torch.tensor([float((w - ref).abs().max())], device="cuda")
+    dist.all_reduce(same, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        l_dp, w_dp, f_dp, g_dp = res["dp"]
+        l_1, w_1, f_1, g_1 = res["single"]
+        rel = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-30))
+        out = {"check": "data-parallel == single GPU on the same batch", "n_gpus": world, "steps": K, "dtype": dtype,
+               "buckets": args.buckets, "loss_dp": l_dp.tolist(), "loss_single": l_1.tolist(),
+               "max_rel_loss_diff": float(np.max(np.abs(l_dp - l_1) / np.abs(l_1))),
+               "weights_rms_rel_diff": rel(w_dp, w_1), "moving_stats_rms_rel_diff": rel(f_dp, f_1),
+               "last_gradient_rms_rel_diff": rel(g_dp / world, g_1),
+               "weight_update_rms": float((w_1 - torch.zeros_like(w_1)).norm()),
+               "max_abs_weight_diff_between_ranks": float(same.item())}
+        tol = 2e-2 if dtype == "bfloat16" else 1e-3
+        out["ok"] = bool(out["max_rel_loss_diff"] < tol and out["weights_rms_rel_diff"] < tol
+                         and out["max_abs_weight_diff_between_ranks"] == 0.0)
+        real_stdout.write(json.dumps(out) + "\n")
+        real_stdout.flush()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
-    ap.add_argument("--dtype", default="bfloat16")
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the config's)")
+    ap.add_argument("--dtype", default="", help="override the config's dtype (float32 | bfloat16)")
+    ap.add_argument("--buckets", type=int, default=4, help="gradient all-reduce slices behind backward (N>1)")
+    ap.add_argument("--check", action="store_true", help="data-parallel correctness check (launch under torchrun)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
@@ -218,12 +477,18 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = CONFIGS[args.config]
+    args.dtype = args.dtype or cfg["dtype"]
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.check:
+        run_check(args, rank, local_rank, world)
         return
     if world != args.gpus and not (world == 1 and args.gpus == 1):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
     args.warmup = max(args.warmup, 3)
+    batch = args.batch or cfg["batch"] or cfg["global_batch"] // world
     # the contract is ONE JSON line on stdout: libraries that write to fd 1 (NCCL prints its version there on init) are
     # diverted to stderr; the JSON line goes to the saved descriptor
     real_stdout = os.fdopen(os.dup(1), "w")
@@ -231,10 +496,7 @@ def main():
 
     import torch.distributed as dist
 
-    from deeplabv3plus_keras_b200 import keras
-    from deeplabv3plus_keras_b200.deeplab import SemanticSegmentation
-    from deeplabv3plus_keras_b200.profiler import KernelProfiler
-    from deeplabv3plus_keras_b200.trainer import Trainer
+    from deeplabv3plus_keras_b200.trainer import Predictor, Trainer
 
     torch.cuda.set_device(local_rank)
     pg = None
@@ -243,17 +505,21 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
         pg = dist.group.WORLD
 
-    conf = make_conf(args.dtype)
-    keras.reset_uids()
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        ss = SemanticSegmentation(conf)
-    he_init(ss.model)
-    tr = Trainer(ss.model, args.batch, use_graph=not args.no_graph, process_group=pg, overlap_wgrad=not args.no_overlap)
+    conf = make_conf(args.dtype, cfg=args.config)
+    ss = build_model(conf)
+    train = cfg["train"]
+    if train:
+        tr = Trainer(ss.model, batch, use_graph=not args.no_graph, process_group=pg, overlap_wgrad=not args.no_overlap,
+                     buckets=args.buckets)
+    else:
+        tr = Predictor(ss.model, batch, dtype=args.dtype, use_graph=not args.no_graph)
     plan = tr.plan
-    x, y = synthetic(conf, args.batch, plan.out_shape[1:3], 1024 + rank)
+    x, y = synthetic(conf, batch, plan.out_shape[1:3], 1024 + rank)
     xs, ys = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
-    tr.stage_inputs(xs, ys)
+    if train:
+        tr.stage_inputs(xs, ys)
+    else:
+        tr.stage_inputs(xs)
     torch.cuda.synchronize()
 
     def barrier():
@@ -281,42 +547,49 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_step = ms_total / args.steps
-    value = args.batch * world * args.steps / (ms_total / 1e3)
-    loss = tr.read_loss()
+    value = batch * world * args.steps / (ms_total / 1e3)
+    loss = tr.read_loss() if train else None
 
-    # ---- end to end: pinned host batch -> H2D -> step -> D2H loss ----------------------------------------
-    # every call trains on one batch that comes from pinned host memory and returns that batch's loss from the device;
-    # the H2D copy of the next call's batch is started behind the step launch (Trainer.prefetch, input double
-    # buffering) — one 67 MB H2D copy and one 8-byte D2H read per step, all inside the timed region
+    # ---- end to end through the user-facing call ------------------------------------------------------------
+    # training: Trainer.train_step_e2e — one batch from pinned host memory per call, its loss read back from the device;
+    # the H2D copy of the next call's batch is started behind the step launch (input double buffering).
+    # inference: Predictor.segment_e2e — pinned host images in, int32 label maps out (H2D + graph + D2H), synchronous.
+    if train:
+        e2e_call = lambda: tr.train_step_e2e(xs, ys, prefetch_next=(xs, ys))
+        h2d, d2h = xs.numel() * 4 + ys.numel() * 4, 8
+        pipeline = ("Trainer.train_step_e2e(batch, prefetch_next=next_batch): the H2D copy of the next batch overlaps "
+                    "the current step; the loss of every step is read back synchronously")
+    else:
+        e2e_call = lambda: tr.segment_e2e(xs)
+        h2d, d2h = xs.numel() * 4, tr.host_labels.numel() * 4
+        pipeline = "Predictor.segment_e2e(images): H2D of the batch, graph replay, D2H of the int32 label maps, synchronous"
     for _ in range(2):
-        tr.train_step_e2e(xs, ys, prefetch_next=(xs, ys))
+        e2e_call()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        tr.train_step_e2e(xs, ys, prefetch_next=(xs, ys))
+        e2e_call()
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = args.batch * world * args.steps / float(t.item())
-    h2d = xs.numel() * 4 + ys.numel() * 4
-    d2h = 8
+    e2e_value = batch * world * args.steps / float(t.item())
 
+    flop_img = cfg["gflop_img"] * 1e9
     line = {
-        "metric": "img/s DeepLabV3+ Xception OS16 513^2 fwd+bwd", "value": value, "unit": "img/s",
+        "metric": cfg["metric"], "value": value, "unit": "img/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
         "dtype": "bf16" if args.dtype == "bfloat16" else "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD.format(batch=args.batch), "global_batch": args.batch * world,
-                   "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
-                   "l2_policy": "per-step working set (several GB of activations) far exceeds the 126 MB L2"},
+        "config": {"workload": cfg["workload"].format(batch=batch), "name": args.config,
+                   "global_batch": batch * world, "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
+                   "l2_policy": "per-step working set (GBs of activations) far exceeds the 126 MB L2"},
         "clocks": clocks, "loss": loss,
         "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "pipeline": "Trainer.train_step_e2e(batch, prefetch_next=next_batch): the H2D copy of the next batch "
-                            "overlaps the current step; the loss of every step is read back synchronously"},
+                "pipeline": pipeline},
         "gpu_launches": tr.launches_per_step * args.steps,
-        "model_tflops": FLOP_PER_IMG_FWD_BWD * value / 1e12,
+        "model_tflops": flop_img * value / 1e12,
     }
 
     if rank == 0:
@@ -326,55 +599,88 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
-        peak_src = "measured" if peaks else "fallback"
-        if not args.no_profile:
-            # instrumented eager pass of the same step: CUDA events around every kernel launch
-            side, plan.side_stream = plan.side_stream, None        # serialise: per-kernel times must not overlap
-            with torch.cuda.stream(tr.stream):
-                with KernelProfiler() as kp:
-                    for _ in range(2):
-                        plan.zero_grads(); plan.forward(); plan.loss_forward_backward(); plan.backward()
-                        plan.regularization(); tr._adam(); plan.run_prep()
-                summ = kp.summary()
-            plan.side_stream = side
-            total_ms = sum(a["ms"] for a in summ.values())
-            top_name, top = next(iter(summ.items()))
-            per_launch_ms = top["ms"] / top["calls"]
-            if top["bound"] == "tensor":
-                ach, peak, unit = top["TFLOPs"], tc_peak, "TFLOP/s"
+        # burst vs sustained tensor peak: chosen from the SM clock sampled during the timed region
+        burst = bool(clocks["sm_mhz"] and clocks["sm_max_mhz"] and clocks["sm_mhz"] >= 0.95 * clocks["sm_max_mhz"])
+        tc_peak = peaks.get("bf16_tflops" if burst else "bf16_tflops_sustained", 1629.3 if burst else 1374.9)
+        peak_src = ("measured" if peaks else "fallback") + (", burst (SM clock >= 0.95 max during the timed region)"
+                                                            if burst else ", sustained (SM clock below 0.95 max)")
+        line["step_roofline"] = {"model_TFLOPs": flop_img * batch * world / 1e12 / world / (ms_step / 1e3) / 1e12 * 1e12
+                                 if False else flop_img * batch / (ms_step / 1e3) / 1e12,
+                                 "frac_of_tensor_peak": flop_img * batch / (ms_step / 1e3) / 1e12 / tc_peak,
+                                 "tensor_peak": tc_peak, "peak_source": peak_src}
+        if not args.no_profile and not args.no_graph:
+            # serialised replay (no side stream) so that the kernel durations add up to the step
+            logical = {v.C: v.clog for v in plan.values.values()
+                       if hasattr(v, "clog") and hasattr(v, "shape") and v.C != v.clog}
+            if train:
+                side, plan.side_stream = plan.side_stream, None
+                tr2 = Trainer(ss.model, batch, use_graph=True, process_group=None, overlap_wgrad=False) \
+                    if world == 1 else None
+                if tr2 is not None:
+                    for _ in range(3):
+                        tr2.step()
+                    torch.cuda.synchronize()
+                    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s0.record(tr2.stream)
+                    for _ in range(10):
+                        tr2.step()
+                    s1.record(tr2.stream)
+                    torch.cuda.synchronize()
+                    serial_ms = s0.elapsed_time(s1) / 10
+
+                    def eager():
+                        with torch.cuda.stream(tr2.stream):
+                            plan.zero_grads(); plan.forward(); plan.loss_forward_backward(); plan.backward()
+                            plan.regularization(); tr2._adam(); plan.run_prep()
+                    per_call, info = graph_kernel_profile(eager, tr2.step, logical)
+                else:
+                    per_call, info, serial_ms = None, {"skipped": "profile pass runs at N=1 only"}, None
+                plan.side_stream = side
             else:
-                ach, peak, unit = top["GBps"], hbm_peak, "GB/s"
-            traffic, traffic_src = None, None
-            try:      # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` capture
-                tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-                if top_name in tj:
-                    traffic, traffic_src = tj[top_name]["bytes_per_launch"], tj[top_name]["source"]
-            except Exception:
-                pass
-            line["roofline"] = {"bound": "tensor" if top["bound"] == "tensor" else "hbm", "kernel": top_name,
-                                "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": traffic,
-                                "traffic_source": traffic_src,
-                                "peak_source": peak_src, "share_of_step": top["ms"] / total_ms,
-                                "avg_launch_ms": per_launch_ms, "launches_per_step": top["calls"] // 2}
-            shapes = [r for r in kp.detail(200) if r["kernel"] == top_name]
-            if shapes:       # the single most expensive problem size of the dominant entry point
-                d0 = shapes[0]
-                line["roofline"]["dominant_shape"] = {
-                    "args": d0["args"], "launches_per_step": d0["calls"] // 2, "ms_per_step": d0["ms"] / 2,
-                    "avg_launch_ms": d0["ms"] / d0["calls"], "TFLOPs": round(d0["TFLOPs"], 1),
-                    "GBps": round(d0["GBps"], 1),
-                    "frac": round(d0["TFLOPs"] / tc_peak if top["bound"] == "tensor" else d0["GBps"] / hbm_peak, 4)}
-            line["kernels"] = {k: {"calls_per_step": a["calls"] // 2, "ms_per_step": a["ms"] / 2,
-                                   "GBps": round(a["GBps"], 1), "TFLOPs": round(a["TFLOPs"], 2), "bound": a["bound"],
-                                   "frac": round((a["TFLOPs"] / tc_peak) if a["bound"] == "tensor"
-                                                 else (a["GBps"] / hbm_peak), 4)}
-                               for k, a in list(summ.items())[:14]}
-            if args.profile_json:
-                json.dump({"per_kernel": {k: dict(a) for k, a in summ.items()}, "per_shape": kp.detail(60)},
-                          open(args.profile_json, "w"), indent=1)
-        if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_baseline()
+                serial_ms = ms_step
+
+                def eager():
+                    with torch.cuda.stream(tr.stream):
+                        tr._run()
+                per_call, info = graph_kernel_profile(eager, tr.step, logical)
+            line["profile"] = {k: v for k, v in info.items() if k != "other_us"}
+            line["profile"]["serial_ms_per_step"] = serial_ms
+            line["profile"]["method"] = ("CUPTI kernel durations inside the replayed CUDA graph, single-stream replay; "
+                                         "kernels attributed to C-ABI calls via an eager pass (correlation ids); flops / "
+                                         "bytes on logical channel counts")
+            if per_call is not None:
+                kern, rows = summarise_calls(per_call, tc_peak, hbm_peak)
+                other_ms = sum(info.get("other_us", {}).values()) / 1e3
+                line["profile"]["torch_ops_ms_per_step"] = other_ms
+                top_name, top = next(iter(kern.items()))
+                traffic, traffic_src = None, None
+                try:      # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` capture
+                    tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+                    if top_name in tj:
+                        traffic, traffic_src = tj[top_name]["bytes_per_launch"], tj[top_name]["source"]
+                except Exception:
+                    pass
+                tensor = top["bound"] == "tensor"
+                line["roofline"] = {"bound": "tensor" if tensor else "hbm", "kernel": top_name,
+                                    "achieved": top["TFLOPs"] if tensor else top["GBps"],
+                                    "peak": tc_peak if tensor else hbm_peak, "unit": "TFLOP/s" if tensor else "GB/s",
+                                    "frac": top["frac"], "traffic": traffic, "traffic_source": traffic_src,
+                                    "peak_source": peak_src, "share_of_step": top["ms_per_step"] / info["sum_kernel_ms"],
+                                    "avg_launch_ms": top["ms_per_step"] / top["calls_per_step"],
+                                    "launches_per_step": top["calls_per_step"]}
+                dom = [r for r in rows if r["kernel"] == top_name]
+                if dom:
+                    d0 = dom[0]
+                    line["roofline"]["dominant_shape"] = {
+                        "args": d0["args"], "launches_per_step": d0["calls"], "ms_per_step": d0["us_per_step"] / 1e3,
+                        "avg_launch_ms": d0["avg_us"] / 1e3, "TFLOPs": round(d0["TFLOPs"], 1), "GBps": round(d0["GBps"], 1),
+                        "frac": round(d0["TFLOPs"] / tc_peak if tensor else d0["GBps"] / hbm_peak, 4)}
+                line["kernels"] = collections.OrderedDict(list(kern.items())[:16])
+                if args.profile_json:
+                    json.dump({"per_kernel": kern, "per_shape": rows[:80], "info": info},
+                              open(args.profile_json, "w"), indent=1, default=list)
+        if not args.no_cpu_baseline:
+            cb = cpu_baseline(args.config, steps=2 if train else 5, warmup=1)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()

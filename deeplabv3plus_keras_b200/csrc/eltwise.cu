@@ -97,12 +97,20 @@ bn_bwd_reduce_kernel(const T* __restrict__ dz, long long ld_dz, const T* __restr
     long long r1 = r0 + rows_per_block; if (r1 > M) r1 = M;
     if (cv < CV) {
         const int c0 = cv << 3;
-        float sc[8], sh[8];
+        float sc[8], sh[8], mu[8];
         if (ACT != DLV3P_ACT_NONE) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) { sc[k] = __ldg(scale + c0 + k); sh[k] = __ldg(shift + c0 + k); }
         }
-        // accumulate sum(g) and sum(g*y); sum(g*xhat) = invstd * (sum(g*y) - mean*sum(g)) is formed once at the end
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mu[k] = __ldg(mean + c0 + k);
+        // sum(g) and sum(g*(y-mean)) — the centred form: sum(g*y) - mean*sum(g) cancels to 1/(|mean|/std) of its terms.
+        // The fp32 (parity) instantiation compensates the serial per-thread sums (Kahan): a column of 10^5 pixels of
+        // random-sign gradients otherwise loses 3 digits to the sqrt(N) cancellation of the sum itself.
+        constexpr bool kComp = sizeof(T) == 4;
+        float c1[8], c2[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { c1[k] = 0.f; c2[k] = 0.f; }
         for (long long r = r0 + ty; r < r1; r += U * PL) {
             Vec8<T> a[U], b[U];
 #pragma unroll
@@ -117,14 +125,20 @@ bn_bwd_reduce_kernel(const T* __restrict__ dz, long long ld_dz, const T* __restr
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const float gg = (ACT == DLV3P_ACT_NONE) ? g[k] : g[k] * act_mask_t<ACT>(fmaf(v[k], sc[k], sh[k]));
-                    s1[k] += gg;
-                    s2[k] = fmaf(gg, v[k], s2[k]);
+                    if (kComp) {
+                        const float y1 = gg - c1[k], t1 = s1[k] + y1;
+                        c1[k] = (t1 - s1[k]) - y1; s1[k] = t1;
+                        const float y2 = gg * (v[k] - mu[k]) - c2[k], t2 = s2[k] + y2;
+                        c2[k] = (t2 - s2[k]) - y2; s2[k] = t2;
+                    } else {
+                        s1[k] += gg;
+                        s2[k] = fmaf(gg, v[k] - mu[k], s2[k]);
+                    }
                 }
             }
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-            s2[k] = (s2[k] - __ldg(mean + c0 + k) * s1[k]) * __ldg(invstd + c0 + k);
+        for (int k = 0; k < 8; ++k) s2[k] *= __ldg(invstd + c0 + k);
     }
     block_col_reduce_2x8<CVB>(s1, s2, red, red + C, blockIdx.x * CVB, CV);
 }

@@ -212,3 +212,64 @@ class Trainer:
         if prefetch_next is not None:
             self.prefetch(*prefetch_next)
         return self.read_loss()
+
+
+class Predictor:
+    """Serving-side driver (the reference's `segment()` / `Model.predict` use, ss.py:1207-1227): CUDA-graph replay of the
+    inference plan — forward, bilinear up-sampling of the logits, channel argmax — with pinned host staging.
+
+    `step()` runs on the batch resident in the plan's input buffer; `segment_e2e(images)` is the user-facing call:
+    pinned host fp32 images in, int32 label maps out (H2D + graph + D2H, synchronous)."""
+
+    def __init__(self, model, batch_size: int, dtype: Optional[str] = None, use_graph: bool = True):
+        self.model = model
+        self.plan: Plan = model.plan(batch_size, training=False, **({"dtype": dtype} if dtype else {}))
+        p = self.plan
+        self.stream = torch.cuda.Stream()
+        self.labels = torch.empty(p.out_shape[:3], dtype=torch.int32, device=p.device)
+        self.host_x = torch.empty(p.x_in.shape, dtype=torch.float32).pin_memory()
+        self.host_labels = torch.empty(p.out_shape[:3], dtype=torch.int32).pin_memory()
+        self.dev_x32 = torch.empty(p.x_in.shape, dtype=torch.float32, device=p.device) \
+            if p.x_in.buf.dtype != torch.float32 else None
+        self.use_graph = use_graph
+        self._graph = None
+        with torch.cuda.stream(self.stream):
+            self._run()                                     # warm-up outside capture
+        torch.cuda.synchronize()
+        if use_graph:
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph, stream=self.stream):
+                self._run()
+        self.launches_per_step = p.launches_fwd + 2
+
+    def _run(self):
+        p = self.plan
+        p.forward()
+        zh = p.logits_highres()
+        ops.softmax_argmax(zh, zh.numel() // zh.shape[-1], zh.shape[-1], labels=self.labels)
+
+    def step(self):
+        with torch.cuda.stream(self.stream):
+            self.plan.ensure_current()                      # weights trained / loaded since the last call
+            if self._graph is not None:
+                self._graph.replay()
+            else:
+                self._run()
+
+    def stage_inputs(self, images: torch.Tensor):
+        p = self.plan
+        with torch.cuda.stream(self.stream):
+            if self.dev_x32 is not None:
+                self.dev_x32.copy_(images, non_blocking=True)
+                ops.cast(self.dev_x32, p.x_in.buf)
+            else:
+                p.x_in.buf.copy_(images, non_blocking=True)
+
+    def segment_e2e(self, images: torch.Tensor) -> torch.Tensor:
+        """Pinned host images [B,H,W,3] fp32 -> pinned host label maps [B,Ho,Wo] int32."""
+        self.stage_inputs(images)
+        self.step()
+        with torch.cuda.stream(self.stream):
+            self.host_labels.copy_(self.labels, non_blocking=True)
+        self.stream.synchronize()
+        return self.host_labels

@@ -43,7 +43,8 @@ def dev(a, b) -> Dict[str, float]:
             "ref_rms": float(b.norm() / max(b.numel(), 1) ** 0.5)}
 
 
-def run(conf, B=2, pw=None, nw=None, Plan=None, seed=1024, decision_forced=True, plan_kwargs=None, step_counter=0):
+def run(conf, B=2, pw=None, nw=None, Plan=None, seed=1024, decision_forced=True, plan_kwargs=None, step_counter=0,
+        fp32_floor=False):
     from deeplabv3plus_keras_b200 import engine
     from tests.test_ops_gpu import NW, PW
     pw, nw = pw or PW, nw or NW
@@ -145,6 +146,19 @@ def run(conf, B=2, pw=None, nw=None, Plan=None, seed=1024, decision_forced=True,
     res["logits_df"] = dev(cpu(plan.logits.buf[..., :plan.logits.clog]), out_df["logits"].detach())
     res["loss_df"] = (plan.loss_value(), float(d_df + l2b))
     res["out_df"] = out_df
+    if fp32_floor:
+        # what fp32 ARITHMETIC alone does to this graph: the same oracle, same forced decisions, evaluated in float32
+        # instead of float64 — the conditioning of the network (small BatchNormalization populations, cancelling
+        # reductions), independent of the product
+        probe3 = OM.Probe(masks=masks, pool_taps=taps, keep_values=False)
+        w32 = {k: v.float() for k, v in w.items()}
+        _, _, g32, out32 = OM.loss_and_grads(conf, w32, xin.float(), yt, pw, nw,
+                                             dropout_mask=None if drop is None else drop.float(),
+                                             emulate_bf16=bf16, probe=probe3)
+        g32 = {k: v.double() for k, v in g32.items()}
+        live32, _ = split_zero({k: v - (2 * lam * w[k] if k in regularised else 0) for k, v in g32.items()})
+        res["param_floor"] = {k: dev(live32[k], live[k]) for k in live if k in live32}
+        res["logits_floor"] = dev(out32["logits"].detach().double(), out_df["logits"].detach())
     return res
 
 
@@ -164,6 +178,13 @@ def summarize(res) -> str:
             med = float(np.median([e["rms"] for e in t.values()])) if t else 0.0
             lines.append(f"{part}: {len(t)} tensors, median rms-rel {med:.2e}, worst {v:.2e} at {k}, "
                          f"worst q99.99 {worst(t, 'q9999')[1]:.2e} at {worst(t, 'q9999')[0]}")
+    if "logits_df" in res:
+        lines.append(f"decision-forced whole graph: logits rms-rel {res['logits_df']['rms']:.2e}, loss "
+                     f"{res['loss_df'][0]:.6f} vs {res['loss_df'][1]:.6f}")
+    if "param_floor" in res:
+        t = res["param_floor"]
+        lines.append(f"fp32-arithmetic floor of the oracle itself: median {float(np.median([e['rms'] for e in t.values()])):.2e}, "
+                     f"worst {worst(t)[1]:.2e} at {worst(t)[0]}, logits {res['logits_floor']['rms']:.2e}")
     if "flips" in res:
         n = sum(f["count"] for f in res["flips"].values())
         tot = sum(f["total"] for f in res["flips"].values())

@@ -21,10 +21,11 @@ DEFAULT_ASPP = [   # conf.json:39-45 (asymmetric rates, chained branches)
 ]
 
 
-def global_pool_aspp(feat: int, sub: int = 2):
+def global_pool_aspp(feat: int, sub: int = 0):
     """An ASPP exercising what the shipped JSONs leave identity: a `conv` k=1 branch (ss.py:812-820), a TRUE image-pooling
     branch (AveragePooling2D over the whole feat x feat map, 1x1 conv, bilinear x feat: ss.py:841-856) and a second
     pyramid level (pool `sub`, x`sub`) chained behind branch 0."""
+    sub = sub or next(d for d in range(2, feat + 1) if feat % d == 0)     # AveragePooling2D is VALID: must divide
     return [
         {"kernel": 1, "rate": [1, 1], "op": "conv", "input": -1},
         {"kernel": 3, "rate": [6, 6], "op": "conv", "input": -1},
