@@ -211,8 +211,11 @@ class SemanticSegmentation:
                 f"base_model {name!r}: only 'xception' and 'mobilenetv2' are on the B200 hot path (SURVEY.md §2 #8)")
         if name not in _TAPS:
             raise ValueError("base model is not valid.")          # ss.py:771
+        # the reference lets keras.applications default to weights='imagenet' (ss.py:496-499, 512-515); a resumed model
+        # (model_loading) takes every weight from its checkpoint instead
+        weights = None if self.model_loading else conf.get("base_weights", "imagenet")
         app = (MobileNetV2 if name == BASE_MODEL_MOBILENETV2 else Xception)(
-            input_shape=self._image_shape(), include_top=False, weights=conf.get("base_weights", "imagenet"))
+            input_shape=self._image_shape(), include_top=False, weights=weights)
         tap = app.get_layer(_TAPS[name][self.nn_arch["output_stride"]]).output
         self.base = Model(inputs=app.inputs, outputs=tap)
         self.base.trainable = True

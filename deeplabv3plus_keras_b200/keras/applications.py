@@ -2,24 +2,61 @@
 reference truncates at (ss.py:502-504,518-520).  The Keras-Applications source is NOT part of /root/reference
 (un-vendored dependency); the topologies are restated from the published architecture and pinned by the
 well-known parameter totals (Xception no-top 20,861,480; MobileNetV2 alpha=1 no-top 2,257,984) in
-tests/test_graph.py.  Pretrained ImageNet weights cannot be downloaded here: weights are random-initialised and
-can be injected with Model.set_weights / utils.load_weights_npz.
+tests/test_oracle.py.
+
+`weights`: None = random initialisation; a path to an `.npz` written by scripts/convert_keras_weights.py (arrays keyed
+"layer/weight" in Keras layouts); "imagenet" = that file looked up as `$DLV3P_PRETRAINED_DIR/<name>_imagenet_notop.npz`
+(default `~/.keras/models`).  There is no network here and tf.keras' download cannot run: "imagenet" without a
+converted file RAISES — it never falls back to random weights silently (the reference relies on the pretrained
+backbone, ss.py:496-499 / 512-515).
 """
 from __future__ import annotations
 
-import warnings
+import os
+
+import numpy as np
 
 from . import layers as L
 from .base import Input
 from .models import Model
 
+PRETRAINED_FILES = {"Xception": "xception_imagenet_notop.npz", "MobileNetV2": "mobilenet_v2_1.0_imagenet_notop.npz"}
 
-def _no_pretrained(weights, who):
-    if weights not in (None, "imagenet"):
-        raise ValueError(f"{who}: weights must be None or 'imagenet'")
+
+def _resolve_weights(weights, who):
+    """None, or the path of the converted `.npz` to load after the graph is built."""
+    if weights is None:
+        return None
     if weights == "imagenet":
-        warnings.warn(f"{who}: pretrained ImageNet weights are not bundled (no network); using random "
-                      "initialisation — load weights with utils.load_weights_npz", stacklevel=3)
+        root = os.environ.get("DLV3P_PRETRAINED_DIR") or os.path.join(os.path.expanduser("~"), ".keras", "models")
+        path = os.path.join(root, PRETRAINED_FILES[who])
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{who}(weights='imagenet'): {path} not found.  Pretrained weights cannot be downloaded here; convert the "
+                f"Keras-Applications file on a machine that has it (python scripts/convert_keras_weights.py --model "
+                f"{who.lower()} --out {path}) or pass weights=None (conf['base_weights'] = None) for random initialisation")
+        return path
+    if isinstance(weights, str) and weights.endswith(".npz"):
+        if not os.path.exists(weights):
+            raise FileNotFoundError(f"{who}: weights file {weights} not found")
+        return weights
+    raise ValueError(f"{who}: weights must be None, 'imagenet' or the path of a converted .npz file")
+
+
+def _load_pretrained(model, path, who):
+    """Copy every array of the file into the layer of the same name (layers of the classification top that the
+    no-top graph does not have are ignored; a layer of the graph missing from the file, or a shape mismatch, raises)."""
+    data = np.load(path)
+    have = {}
+    for k in data.files:
+        have.setdefault(k.rsplit("/", 1)[0], {})[k.rsplit("/", 1)[1]] = data[k]
+    for layer in model.flat_layers():
+        names = layer.weight_names()
+        if not names:
+            continue
+        if layer.name not in have:
+            raise ValueError(f"{who}: {path} holds no weights for layer {layer.name!r}")
+        layer.set_weights([have[layer.name][n] for n in names])
 
 
 def _check_no_top(include_top, who):
@@ -29,7 +66,7 @@ def _check_no_top(include_top, who):
 
 def Xception(include_top=False, weights="imagenet", input_tensor=None, input_shape=None, pooling=None, classes=1000):
     _check_no_top(include_top, "Xception")
-    _no_pretrained(weights, "Xception")
+    pretrained = _resolve_weights(weights, "Xception")
     img = input_tensor if input_tensor is not None else Input(shape=input_shape, name="input_1")
 
     def conv_bn_act(x, filters, name, strides=1):
@@ -75,7 +112,10 @@ def Xception(include_top=False, weights="imagenet", input_tensor=None, input_sha
         x = L.SeparableConv2D(filters, (3, 3), padding="same", use_bias=False, name=f"block14_sepconv{j}")(x)
         x = L.BatchNormalization(name=f"block14_sepconv{j}_bn")(x)
         x = L.Activation("relu", name=f"block14_sepconv{j}_act")(x)
-    return Model(img, x, name="xception")
+    model = Model(img, x, name="xception")
+    if pretrained:
+        _load_pretrained(model, pretrained, "Xception")
+    return model
 
 
 def _make_divisible(v, divisor, min_value=None):
@@ -102,7 +142,7 @@ MNV2_BLOCKS = (  # (filters, stride, expansion, block_id)
 def MobileNetV2(input_shape=None, alpha=1.0, include_top=False, weights="imagenet", input_tensor=None, pooling=None,
                 classes=1000):
     _check_no_top(include_top, "MobileNetV2")
-    _no_pretrained(weights, "MobileNetV2")
+    pretrained = _resolve_weights(weights, "MobileNetV2")
     img = input_tensor if input_tensor is not None else Input(shape=input_shape, name="input_1")
     bn = dict(epsilon=1e-3, momentum=0.999)
 
@@ -134,4 +174,7 @@ def MobileNetV2(input_shape=None, alpha=1.0, include_top=False, weights="imagene
     x = L.Conv2D(last, 1, use_bias=False, name="Conv_1")(x)
     x = L.BatchNormalization(name="Conv_1_bn", **bn)(x)
     x = L.ReLU(6.0, name="out_relu")(x)
-    return Model(img, x, name=f"mobilenetv2_{alpha:0.2f}_{input_shape[0] if input_shape else 'None'}")
+    model = Model(img, x, name=f"mobilenetv2_{alpha:0.2f}_{input_shape[0] if input_shape else 'None'}")
+    if pretrained:
+        _load_pretrained(model, pretrained, "MobileNetV2")
+    return model
