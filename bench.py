@@ -309,7 +309,7 @@ def graph_kernel_profile(eager_fn, replay_fn, logical, steps=3):
         name = e.name()
         dev = str(e.device_type())
         if "CUDA" in dev:
-            if not name.startswith(("Memset", "Memcpy")):
+            if not name.startswith(("Memset", "Memcpy", "dlv3p#")):        # (ranges are mirrored on the GPU timeline)
                 kernels.append(e)
         elif name.startswith("dlv3p#"):
             ranges.append((e.start_ns(), e.start_ns() + e.duration_ns(), int(name[6:])))
@@ -333,7 +333,7 @@ def graph_kernel_profile(eager_fn, replay_fn, logical, steps=3):
             replay_fn()
         torch.cuda.synchronize()
     gk = [e for e in prof2.profiler.kineto_results.events()
-          if "CUDA" in str(e.device_type()) and not e.name().startswith(("Memset", "Memcpy"))]
+          if "CUDA" in str(e.device_type()) and not e.name().startswith(("Memset", "Memcpy", "dlv3p#"))]
     gk.sort(key=lambda e: e.start_ns())
     n = len(seq)
     info = {"kernels_per_step": n, "graph_kernels": len(gk), "aligned": False}
@@ -560,9 +560,10 @@ def main():
         pipeline = ("Trainer.train_step_e2e(batch, prefetch_next=next_batch): the H2D copy of the next batch overlaps "
                     "the current step; the loss of every step is read back synchronously")
     else:
-        e2e_call = lambda: tr.segment_e2e(xs)
-        h2d, d2h = xs.numel() * 4, tr.host_labels.numel() * 4
-        pipeline = "Predictor.segment_e2e(images): H2D of the batch, graph replay, D2H of the int32 label maps, synchronous"
+        e2e_call = lambda: tr.segment_e2e(xs, prefetch_next=xs)
+        h2d, d2h = xs.numel() * 4, tr.host_labels.numel() * tr.host_labels.element_size()
+        pipeline = ("Predictor.segment_e2e(images, prefetch_next=next): H2D of the fp32 batch (the next one overlaps this "
+                    "call's compute), graph replay, D2H of the label maps (uint8), synchronous per call")
     for _ in range(2):
         e2e_call()
     barrier()
@@ -612,6 +613,10 @@ def main():
             # serialised replay (no side stream) so that the kernel durations add up to the step
             logical = {v.C: v.clog for v in plan.values.values()
                        if hasattr(v, "clog") and hasattr(v, "shape") and v.C != v.clog}
+            # programmatic dependent launch off for this pass: with it every kernel is made resident while its
+            # predecessor drains and CUPTI would count that wait into its duration (the sum would exceed the step)
+            from deeplabv3plus_keras_b200 import _lib
+            pdl_was = _lib.set_pdl(False)
             if train:
                 side, plan.side_stream = plan.side_stream, None
                 tr2 = Trainer(ss.model, batch, use_graph=True, process_group=None, overlap_wgrad=False) \
@@ -642,12 +647,26 @@ def main():
                 def eager():
                     with torch.cuda.stream(tr.stream):
                         tr._run()
-                per_call, info = graph_kernel_profile(eager, tr.step, logical)
+                tr_np = Predictor(ss.model, batch, dtype=args.dtype, use_graph=True)      # re-captured without PDL
+                tr_np.stage_inputs(xs)
+                for _ in range(3):
+                    tr_np.step()
+                torch.cuda.synchronize()
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record(tr_np.stream)
+                for _ in range(10):
+                    tr_np.step()
+                s1.record(tr_np.stream)
+                torch.cuda.synchronize()
+                serial_ms = s0.elapsed_time(s1) / 10
+                per_call, info = graph_kernel_profile(eager, tr_np.step, logical)
+            _lib.set_pdl(pdl_was)
             line["profile"] = {k: v for k, v in info.items() if k != "other_us"}
             line["profile"]["serial_ms_per_step"] = serial_ms
-            line["profile"]["method"] = ("CUPTI kernel durations inside the replayed CUDA graph, single-stream replay; "
-                                         "kernels attributed to C-ABI calls via an eager pass (correlation ids); flops / "
-                                         "bytes on logical channel counts")
+            line["profile"]["method"] = ("CUPTI kernel durations inside a replayed CUDA graph of the same step captured on "
+                                         "ONE stream without programmatic dependent launch (so durations do not overlap "
+                                         "and add up to serial_ms_per_step); kernels attributed to C-ABI calls via an "
+                                         "eager pass (correlation ids); flops / bytes on logical channel counts")
             if per_call is not None:
                 kern, rows = summarise_calls(per_call, tc_peak, hbm_peak)
                 other_ms = sum(info.get("other_us", {}).values()) / 1e3

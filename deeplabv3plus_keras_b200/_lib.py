@@ -76,7 +76,7 @@ SIGNATURES = {
     "dlv3p_preprocess_label_batch": [_p, _i, _p, _i, _i, _p],
     "dlv3p_cast2d": [_p, _l, _i, _p, _l, _i, _l, _i, _p],
 }
-_PLAIN = {"dlv3p_version": [], "dlv3p_device_arch": []}
+_PLAIN = {"dlv3p_version": [], "dlv3p_device_arch": [], "dlv3p_set_pdl": [_i]}
 
 _lib = None
 PROFILER = None      # set to a profiler.KernelProfiler to bracket every entry-point call with CUDA events
@@ -100,6 +100,12 @@ def load() -> C.CDLL:
     lib.dlv3p_last_error.restype = C.c_char_p
     _lib = lib
     return lib
+
+
+def set_pdl(enabled: bool) -> bool:
+    """Programmatic dependent launch on/off for all subsequent launches (a launch attribute; see include/dlv3p.h).
+    Returns the previous setting."""
+    return bool(load().dlv3p_set_pdl(1 if enabled else 0))
 
 
 def last_error() -> str:

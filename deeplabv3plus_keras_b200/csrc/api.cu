@@ -24,20 +24,14 @@ int check_launch(const char* what) {
     return DLV3P_OK;
 }
 
-bool pdl_enabled() {
-#ifdef DLV3P_DIAG
-    static int on = -1;           // diagnostics build: DLV3P_PDL=0 switches programmatic dependent launch off (A/B)
-    if (on < 0) { const char* e = getenv("DLV3P_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
-    return on != 0;
-#else
-    return true;
-#endif
-}
+static int g_pdl = 1;
+bool pdl_enabled() { return g_pdl != 0; }
 
 }  // namespace dlv3p
 
 extern "C" const char* dlv3p_last_error(void) { return dlv3p::g_err; }
-extern "C" int dlv3p_version(void) { return 100; }
+extern "C" int dlv3p_version(void) { return 200; }
+extern "C" int dlv3p_set_pdl(int enabled) { const int was = dlv3p::g_pdl; dlv3p::g_pdl = enabled ? 1 : 0; return was; }
 extern "C" int dlv3p_device_arch(void) {
     int dev = 0;
     cudaDeviceProp prop;

@@ -107,7 +107,11 @@ bn_bwd_reduce_kernel(const T* __restrict__ dz, long long ld_dz, const T* __restr
         // sum(g) and sum(g*(y-mean)) — the centred form: sum(g*y) - mean*sum(g) cancels to 1/(|mean|/std) of its terms.
         // The fp32 (parity) instantiation compensates the serial per-thread sums (Kahan): a column of 10^5 pixels of
         // random-sign gradients otherwise loses 3 digits to the sqrt(N) cancellation of the sum itself.
+#ifdef DLV3P_NO_KAHAN
+        constexpr bool kComp = false;
+#else
         constexpr bool kComp = sizeof(T) == 4;
+#endif
         float c1[8], c2[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) { c1[k] = 0.f; c2[k] = 0.f; }

@@ -54,3 +54,34 @@ def allreduce_ranges(g: torch.Tensor, ranges, group=None) -> None:
     for lo, hi in ranges:
         if hi > lo:
             dist.all_reduce(g[lo:hi], op=dist.ReduceOp.SUM, group=group)
+
+
+def exchange_schedule(plan, n_buckets: int):
+    """How the Trainer overlaps the gradient exchange with backward: the backward launch list is cut into `n_buckets`
+    contiguous segments; after segment i the arena slices that became FINAL during it (the gradient arena is laid out
+    in backward order, Plan.final_prefixes) are all-reduced while segment i+1 runs.  Returns (cuts, ranges):
+    cuts[i]..cuts[i+1] = launch range of segment i, ranges[i] = [(lo, hi), ...] to exchange after it; the last entry
+    completes both arena regions, so the union of all ranges is exactly [0, n_train)."""
+    P = plan.params
+    n = len(plan.bwd)
+    cuts = [round(i * n / n_buckets) for i in range(n_buckets + 1)]
+    ranges, pa, pb = [], 0, P.n_reg
+    for i, c in enumerate(cuts[1:]):
+        a, b = (P.n_reg, P.n_train) if i == n_buckets - 1 else plan.final_prefixes(c)
+        ranges.append([(pa, a), (pb, b)])
+        pa, pb = a, b
+    return cuts, ranges
+
+
+def run_step_with_exchange(plan, n_buckets: int, group=None) -> None:
+    """Reference (synchronous) execution of the Trainer's data-parallel step on the batch resident in `plan`: head
+    (zero, forward, loss), then per segment: launch it, all-reduce what it finished.  The Trainer does the same with
+    CUDA graphs per segment and the all-reduces on a communication stream."""
+    cuts, ranges = exchange_schedule(plan, n_buckets)
+    plan.finalize()
+    plan.zero_grads()
+    plan.forward()
+    plan.loss_forward_backward()
+    for (a, b), rg in zip(zip(cuts[:-1], cuts[1:]), ranges):
+        plan.run_bwd_range(a, b)
+        allreduce_ranges(plan.params.g, rg, group)

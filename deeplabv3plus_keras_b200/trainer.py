@@ -63,12 +63,10 @@ class Trainer:
     # ------------------------------------------------------------------------------------------------------
     def _build(self, n_buckets: int):
         p = self.plan
-        bwd = p.bwd
-        # split the backward schedule into n_buckets contiguous segments; the all-reduce of the whole arena is cut
-        # into the same number of contiguous slices, slice i being exchanged after segment i has been launched.
-        # (Arena order is not backward order, so every slice is only COMPLETE after the last segment; slices
-        # therefore carry a final pass.  With buckets=1 this degenerates to one all-reduce after backward.)
-        cuts = [round(i * len(bwd) / n_buckets) for i in range(n_buckets + 1)]
+        # the backward launch list in n_buckets contiguous segments; after segment i the gradient-arena slices that
+        # became final during it are exchanged while segment i+1 runs (dp.exchange_schedule; with one bucket this
+        # degenerates to one all-reduce after backward)
+        cuts, ranges = dp.exchange_schedule(p, n_buckets)
 
         def head():
             p.zero_grads()
@@ -76,17 +74,7 @@ class Trainer:
             p.loss_forward_backward()
 
         parts = [head] + [(lambda a=a, b=b: p.run_bwd_range(a, b)) for a, b in zip(cuts[:-1], cuts[1:])]
-        # gradient-arena slices that are final after each backward segment (the arena is laid out in backward order)
-        P = p.params
-        self._ranges: List = [[]]                      # nothing to exchange after the head
-        pa, pb = 0, P.n_reg
-        for i, c in enumerate(cuts[1:]):
-            a, b = (P.n_reg, P.n_train) if i == n_buckets - 1 else p.final_prefixes(c)
-            self._ranges.append([(pa, a), (pb, b)])
-            pa, pb = a, b
-
-        def tail():
-            p.regularization()
+        self._ranges: List = [[]] + ranges             # nothing to exchange after the head
 
         if self.use_graph:
             # warm-up outside capture (lazy module loading, cudaFuncSetAttribute) on the capture stream
@@ -109,6 +97,7 @@ class Trainer:
         else:
             self._parts = parts
             self._prep = p.run_prep
+        # + fused decoder tail, gradient / statistics / loss memsets, L2 sum, two Adam launches, weight re-quantisation
         self.launches_per_step = p.launches_fwd + p.launches_bwd + 8
 
     # ------------------------------------------------------------------------------------------------------
@@ -228,7 +217,10 @@ class Predictor:
         self.stream = torch.cuda.Stream()
         self.labels = torch.empty(p.out_shape[:3], dtype=torch.int32, device=p.device)
         self.host_x = torch.empty(p.x_in.shape, dtype=torch.float32).pin_memory()
-        self.host_labels = torch.empty(p.out_shape[:3], dtype=torch.int32).pin_memory()
+        small = p.out_shape[3] <= 256           # label ids fit a byte: a quarter of the D2H bytes
+        self.host_labels = torch.empty(p.out_shape[:3], dtype=torch.uint8 if small else torch.int32).pin_memory()
+        self._labels_u8 = torch.empty(p.out_shape[:3], dtype=torch.uint8, device=p.device) if small else None
+        self._copy_stream = self._stage_x = self._staged = self._stage_free = None
         self.dev_x32 = torch.empty(p.x_in.shape, dtype=torch.float32, device=p.device) \
             if p.x_in.buf.dtype != torch.float32 else None
         self.use_graph = use_graph
@@ -265,11 +257,46 @@ class Predictor:
             else:
                 p.x_in.buf.copy_(images, non_blocking=True)
 
-    def segment_e2e(self, images: torch.Tensor) -> torch.Tensor:
-        """Pinned host images [B,H,W,3] fp32 -> pinned host label maps [B,Ho,Wo] int32."""
-        self.stage_inputs(images)
+    def prefetch(self, images: torch.Tensor):
+        """Start the H2D copy of the NEXT batch on the copy stream (input double buffering, as Trainer.prefetch)."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._stage_x = torch.empty(self.plan.x_in.shape, dtype=torch.float32, device=self.plan.device)
+        if self._stage_free is not None:
+            self._copy_stream.wait_event(self._stage_free)
+        with torch.cuda.stream(self._copy_stream):
+            self._stage_x.copy_(images, non_blocking=True)
+            self._staged = torch.cuda.Event()
+            self._staged.record(self._copy_stream)
+
+    def _consume_staged(self):
+        p = self.plan
+        self.stream.wait_event(self._staged)
+        with torch.cuda.stream(self.stream):
+            if p.x_in.buf.dtype != torch.float32:
+                ops.cast(self._stage_x, p.x_in.buf)
+            else:
+                p.x_in.buf.copy_(self._stage_x, non_blocking=True)
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record(self.stream)
+        self._staged = None
+
+    def segment_e2e(self, images: Optional[torch.Tensor], prefetch_next: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Pinned host images [B,H,W,3] fp32 -> pinned host label maps [B,Ho,Wo] (uint8 when the class count fits,
+        else int32): H2D + graph + D2H, synchronous.  `prefetch_next`: the NEXT call's batch, copied behind this call's
+        compute; the call that follows uses it (pass None or the same tensor)."""
+        if self._staged is not None:
+            self._consume_staged()
+        else:
+            self.stage_inputs(images)
         self.step()
         with torch.cuda.stream(self.stream):
-            self.host_labels.copy_(self.labels, non_blocking=True)
+            if self.host_labels.dtype == torch.uint8:
+                self._labels_u8.copy_(self.labels)
+                self.host_labels.copy_(self._labels_u8, non_blocking=True)
+            else:
+                self.host_labels.copy_(self.labels, non_blocking=True)
+        if prefetch_next is not None:
+            self.prefetch(prefetch_next)
         self.stream.synchronize()
         return self.host_labels

@@ -46,6 +46,11 @@ const char* dlv3p_last_error(void);
 int dlv3p_version(void);
 /* compute capability major*10+minor of the current device, or a negative error */
 int dlv3p_device_arch(void);
+/* Programmatic dependent launch (the next kernel of the stream is made resident while the current one drains; every
+ * kernel waits on griddepcontrol before touching memory) on (default) / off for all subsequent launches.  A launch
+ * ATTRIBUTE only — results are identical; profilers switch it off so that a kernel's recorded duration does not include
+ * the time it spent resident behind its predecessor.  Returns the previous setting. */
+int dlv3p_set_pdl(int enabled);
 
 /* ------------------------------------------------------------------------------------------------
  * K1 — atrous depthwise 3x3 (TF DepthwiseConv2dNative / ...BackpropInput / ...BackpropFilter; the depthwise

@@ -44,7 +44,7 @@ def dev(a, b) -> Dict[str, float]:
 
 
 def run(conf, B=2, pw=None, nw=None, Plan=None, seed=1024, decision_forced=True, plan_kwargs=None, step_counter=0,
-        fp32_floor=False):
+        fp32_floor=False, bf16_floor=False):
     from deeplabv3plus_keras_b200 import engine
     from tests.test_ops_gpu import NW, PW
     pw, nw = pw or PW, nw or NW
@@ -146,6 +146,15 @@ def run(conf, B=2, pw=None, nw=None, Plan=None, seed=1024, decision_forced=True,
     res["logits_df"] = dev(cpu(plan.logits.buf[..., :plan.logits.clog]), out_df["logits"].detach())
     res["loss_df"] = (plan.loss_value(), float(d_df + l2b))
     res["out_df"] = out_df
+    if bf16_floor:
+        # what bf16 STORAGE alone does to this graph: the same bf16-rounding oracle, same forced decisions, with the
+        # weights perturbed by 1e-7 (i.e. another fp32 summation order): rounding directions flip and the 2^-9 noise of
+        # every stored tensor accumulates through the depth — no implementation can be closer to another than this
+        gen = torch.Generator().manual_seed(0)
+        w2 = {k: v * (1 + 1e-7 * torch.randn(v.shape, generator=gen, dtype=v.dtype)) for k, v in w.items()}
+        probe4 = OM.Probe(masks=masks, pool_taps=taps, keep_values=False)
+        _, _, _, out_p = OM.loss_and_grads(conf, w2, xin, yt, pw, nw, dropout_mask=drop, emulate_bf16=True, probe=probe4)
+        res["logits_bf16_floor"] = dev(out_p["logits"].detach(), out_df["logits"].detach())
     if fp32_floor:
         # what fp32 ARITHMETIC alone does to this graph: the same oracle, same forced decisions, evaluated in float32
         # instead of float64 — the conditioning of the network (small BatchNormalization populations, cancelling
@@ -181,6 +190,9 @@ def summarize(res) -> str:
     if "logits_df" in res:
         lines.append(f"decision-forced whole graph: logits rms-rel {res['logits_df']['rms']:.2e}, loss "
                      f"{res['loss_df'][0]:.6f} vs {res['loss_df'][1]:.6f}")
+    if "logits_bf16_floor" in res:
+        lines.append(f"bf16-storage floor of the oracle itself (weights perturbed by 1e-7): logits rms-rel "
+                     f"{res['logits_bf16_floor']['rms']:.2e}")
     if "param_floor" in res:
         t = res["param_floor"]
         lines.append(f"fp32-arithmetic floor of the oracle itself: median {float(np.median([e['rms'] for e in t.values()])):.2e}, "

@@ -38,7 +38,7 @@ def test_ctypes_table_matches_header():
 
     funcs = header_functions()
     for name, nargs in funcs.items():
-        if name in ("dlv3p_last_error", "dlv3p_version", "dlv3p_device_arch"):
+        if name in ("dlv3p_last_error", "dlv3p_version", "dlv3p_device_arch", "dlv3p_set_pdl"):
             continue
         assert name in _lib.SIGNATURES, f"{name} missing from the ctypes table"
         assert len(_lib.SIGNATURES[name]) == nargs, f"{name}: header has {nargs} args, table {len(_lib.SIGNATURES[name])}"

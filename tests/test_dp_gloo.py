@@ -1,5 +1,5 @@
 """N>1 host logic on CPU: two gloo ranks, each running the engine (through the tests/fake_ops.py test double) on its
-shard of the batch, exchange gradients with dp.allreduce_gradients; the averaged gradient must equal the mean of the
+shard of the batch, exchange gradients with the Trainer's segment-wise prefix schedule (dp.run_step_with_exchange); the averaged gradient must equal the mean of the
 oracle's per-shard gradients (BatchNormalization statistics stay per replica)."""
 import os
 import socket
@@ -36,10 +36,19 @@ def _worker(rank, world, port, q):
     x, y = util.synthetic_batch(conf, G, plan.out_shape[1:3])
     plan.set_loss(PW, NW)
     plan.load_batch(x[lo:hi], y[lo:hi])
-    plan.step_fwd_bwd()
+    # the Trainer's own data-parallel schedule: backward in 3 segments, the arena prefixes each segment finished are
+    # all-reduced right behind it (dp.exchange_schedule / Plan.final_prefixes / dp.allreduce_ranges)
+    dp.run_step_with_exchange(plan, 3, None)
     n = plan.params.n_train
-    dp.allreduce_gradients(plan.params.g, n, None, buckets=3)
     g = (plan.params.g[:n] / world).numpy().copy()
+    # ... and it must equal ONE all-reduce of the complete arena after a plain backward
+    plan.step_fwd_bwd()
+    dp.allreduce_gradients(plan.params.g, n, None, buckets=3)
+    g2 = (plan.params.g[:n] / world).numpy()
+    assert np.allclose(g, g2, rtol=1e-5, atol=1e-7), float(np.abs(g - g2).max())
+    cuts, ranges = dp.exchange_schedule(plan, 3)
+    covered = sorted(r for rg in ranges for r in rg if r[1] > r[0])
+    assert covered[0][0] == 0 and covered[-1][1] == n and sum(hi - lo for lo, hi in covered) == n
     names = {k: v for k, v in plan.gradients().items()}
     if rank == 0:
         q.put((g, {k: v / world for k, v in names.items()}, x, y))
