@@ -32,6 +32,9 @@ SIGNATURES = {
     "dlv3p_conv3x3_valid_fwd_bf16": [_p, _p, _l, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p],
     "dlv3p_conv3x3_valid_dgrad_bf16": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
     "dlv3p_conv3x3_valid_wgrad_bf16": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "dlv3p_conv3x3_same_fwd_bf16": [_p, _p, _l, _p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p],
+    "dlv3p_conv3x3_same_dgrad_bf16": [_p, _l, _p, _p, _i, _i, _i, _i, _i, _p],
+    "dlv3p_conv3x3_same_wgrad_bf16": [_p, _p, _l, _p, _i, _i, _i, _i, _i, _p],
     "dlv3p_gemm_simt": [_p, _l, _l, _p, _l, _l, _p, _l, _i, _i, _i, _i, _i, _p, _p, _i, _p, _l, _i, _p],
     "dlv3p_im2col3x3": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _l, _i, _p],
     "dlv3p_col2im3x3": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _l, _p, _i, _p],
@@ -67,6 +70,7 @@ SIGNATURES = {
     "dlv3p_cbloss_dense_fwd": [_p, _p, _p, _p, _f, _l, _i, _p, _p],
     "dlv3p_cbloss_dense_bwd": [_p, _p, _p, _p, _f, _l, _i, _f, _p, _p],
     "dlv3p_softmax_bwd": [_p, _p, _l, _i, _p, _p],
+    "dlv3p_upsample_argmax": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "dlv3p_confusion_matrix": [_p, _p, _l, _i, _p, _p],
     "dlv3p_dropout": [_p, _p, _l, _f, _u64, _p, _p, _i, _p],
     "dlv3p_adam": [_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _p],

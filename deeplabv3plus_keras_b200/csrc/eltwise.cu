@@ -1592,6 +1592,58 @@ extern "C" int dlv3p_bilinear_fwd(const void* x, int64_t ld_x, void* y, int64_t 
     return 0;
 }
 
+namespace dlv3p {
+// Inference tail (segment(), ss.py:1207-1227): bilinear x(fh, fw) up-sampling of the low-resolution logits fused with
+// the channel argmax — softmax is monotone, so the label map needs neither the [N,Ho,Wo,C] logits (1.27 GB fp32 at
+// BASELINE cfg-5) nor the probabilities.  One thread per output pixel; the four corner logit rows are read through
+// the read-only path (the whole low-resolution tensor is a few MB and stays in L1/L2); the interpolation is the
+// expression of bilinear_fwd_kernel, so the labels equal those of the materialised path bit for bit (first maximum wins).
+template <typename OT>
+__global__ void __launch_bounds__(256)
+upsample_argmax_kernel(const float* __restrict__ z, OT* __restrict__ labels, int N, int H, int W, int C, int fh, int fw,
+                       long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int Wo = W * fw, Ho = H * fh;
+    long long t = idx;
+    const int xo = (int)(t % Wo); t /= Wo;
+    const int yo = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    int y0, y1, x0, x1; float ly, lx;
+    hp_src(yo, 1.f / (float)fh, H, y0, y1, ly);
+    hp_src(xo, 1.f / (float)fw, W, x0, x1, lx);
+    const long long b = (long long)n * H * W;
+    const float* ptl = z + (b + (long long)y0 * W + x0) * C;
+    const float* ptr = z + (b + (long long)y0 * W + x1) * C;
+    const float* pbl = z + (b + (long long)y1 * W + x0) * C;
+    const float* pbr = z + (b + (long long)y1 * W + x1) * C;
+    float best = -INFINITY; int arg = 0;
+    for (int c = 0; c < C; ++c) {
+        const float tl = __ldg(ptl + c), tr = __ldg(ptr + c), bl = __ldg(pbl + c), br = __ldg(pbr + c);
+        const float top = tl + (tr - tl) * lx;
+        const float bot = bl + (br - bl) * lx;
+        const float v = top + (bot - top) * ly;
+        if (v > best) { best = v; arg = c; }
+    }
+    labels[idx] = (OT)arg;
+}
+}  // namespace dlv3p
+
+extern "C" int dlv3p_upsample_argmax(const float* z, void* labels, int label_bytes, int N, int H, int W, int C, int fh,
+                                     int fw, void* stream) {
+    DLV3P_REQUIRE(z && labels && N > 0 && H > 0 && W > 0 && C > 0 && fh >= 1 && fw >= 1, DLV3P_ERR_SHAPE,
+                  "upsample_argmax: bad arguments");
+    DLV3P_REQUIRE(label_bytes == 4 || (label_bytes == 1 && C <= 256), DLV3P_ERR_DTYPE,
+                  "upsample_argmax: labels are int32 (label_bytes 4) or uint8 (label_bytes 1, C <= 256)");
+    const long long total = (long long)N * H * fh * W * fw;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (label_bytes == 4)
+        dlv3p::upsample_argmax_kernel<int32_t><<<dlv3p::cdiv(total, 256), 256, 0, st>>>(z, (int32_t*)labels, N, H, W, C, fh, fw, total);
+    else
+        dlv3p::upsample_argmax_kernel<uint8_t><<<dlv3p::cdiv(total, 256), 256, 0, st>>>(z, (uint8_t*)labels, N, H, W, C, fh, fw, total);
+    return dlv3p::check_launch("upsample_argmax");
+}
+
 extern "C" int dlv3p_bilinear_bwd(const void* dy, int64_t ld_dy, void* dx, int64_t ld_dx, int N, int H, int W,
                                   int C, int fh, int fw, const void* addend, int dy_dtype, int dx_dtype,
                                   void* stream) {

@@ -68,6 +68,9 @@ struct GemmParams {
     int tma_store;                     // epilogue through the smem staging tile + TMA store / reduce-add
     // implicit-GEMM 3x3 VALID stride-1 convolution (no im2col buffer): 0 = plain GEMM, 1 = forward, 2 = input gradient,
     // 3 = filter gradient.  Output/M tiles never cross an image row; A comes straight from the NHWC tensor.
+    // 3x3 SAME stride-1 convolution (the logits / boundary-refinement convolution, ss.py:893-897): 4 = forward, 5 = input
+    // gradient, 6 = filter gradient — every tap is a rank-4 window (channel block, 128 / 64 pixels of one row, row, image)
+    // shifted by the tap; what falls outside the image is zero-filled by TMA, which IS the SAME padding.
     int conv_mode;
     int cv_rows_in;                    // image rows of the A-side tensor per image (fwd/wgrad: H of x; dgrad: Ho of dy)
     int cv_rows_out;                   // rows per image of the M-side index (fwd/wgrad: Ho; dgrad: H)
@@ -328,7 +331,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_expect_tx(fb, STAGE_BYTES);
                     const int kk = kb * kBlockK;
                     if (p.conv_mode != 0) {
-                        if (WGRAD) {
+                        if (WGRAD && p.conv_mode == 6) {
+                            // SAME filter gradient: output rows = (tap, 128 input channels), reduction block kb = 64
+                            // consecutive output pixels of one image row; x window shifted by the tap
+                            const int mt = row0 / kBlockM;
+                            const int tap = mt / p.cv_kbr, ci0 = (mt % p.cv_kbr) * kBlockM;
+                            const int r = kb / p.cv_tpr, qd = kb % p.cv_tpr;
+                            const int n = r / p.cv_rows_out, ho = r % p.cv_rows_out;
+#pragma unroll
+                            for (int h = 0; h < kBlockM / 64; ++h)
+                                tma_load_4d(a_dst + h * 8192, &tmA, fb, ci0 + 64 * h, qd * 64 + tap % 3 - 1, ho + tap / 3 - 1, n);
+#pragma unroll
+                            for (int h = 0; h < BLOCK_N / 64; ++h)
+                                tma_load_2d(b_dst + h * 8192, &tmB, fb, col0 + 64 * h, r * p.cv_width + qd * 64);
+                        } else if (WGRAD) {
                             // filter gradient: output rows = the 128-element padded K-run of filter row i, reduction
                             // block kb = 64 consecutive output pixels of one image row
                             const int i = row0 / kBlockM;
@@ -352,12 +368,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 // filter columns of the same 64 run elements; what the box takes beyond the run belongs
                                 // to the next filter row (or is zero-filled) and meets the zero-filled A elements
                                 tma_load_2d(b_dst, &tmB, fb, i * p.cv_run + part * 64, col0);
-                            } else {
+                            } else if (p.conv_mode == 2) {
                                 // input gradient: k-block = 64 output channels of dy under tap (i, j), window shifted by
                                 // (-i, -j); positions outside dy are zero-filled (full correlation)
                                 const int tap = kb / p.cv_kbr, part = kb % p.cv_kbr;
                                 tma_load_4d(a_dst, &tmA, fb, part * 64, w0 - tap % 3, hh - tap / 3, n);
                                 tma_load_2d(b_dst, &tmB, fb, kk, col0);
+                            } else {
+                                // SAME forward (4) / input gradient (5): k-block = 64 channels of the operand image under
+                                // tap (i, j), window shifted by +-(i-1, j-1); outside the image = zero = the SAME padding.
+                                // B: the tap's slice of the filter matrix (cv_run K-elements per tap); a channel block
+                                // that runs past the tap's channels meets zero-filled A columns
+                                const int tap = kb / p.cv_kbr, part = kb % p.cv_kbr;
+                                const int sg = p.conv_mode == 4 ? 1 : -1;
+                                tma_load_4d(a_dst, &tmA, fb, part * 64, w0 + sg * (tap % 3 - 1), hh + sg * (tap / 3 - 1), n);
+                                tma_load_2d(b_dst, &tmB, fb, tap * p.cv_run + part * 64, col0);
                             }
                         }
                     } else if (WGRAD) {
@@ -435,7 +460,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 int rb = row0 + q * 32, rl = row_limit, c2 = -1;
                 if (p.conv_mode != 0) {
                     const int mt = row0 / kBlockM;
-                    if (WGRAD) { rb = q * 32; rl = p.cv_rlimit; c2 = mt; }               // (cout, element of the run, filter row)
+                    if (WGRAD && p.conv_mode == 6) { rb = (mt % p.cv_kbr) * kBlockM + q * 32; rl = p.cv_rlimit; c2 = mt / p.cv_kbr; }   // (cout, cin, tap)
+                    else if (WGRAD) { rb = q * 32; rl = p.cv_rlimit; c2 = mt; }          // (cout, element of the run, filter row)
                     else { rb = (mt % p.cv_tpr) * kBlockM + q * 32; rl = p.cv_rlimit; c2 = mt / p.cv_tpr; }   // (ch, column, row)
                 }
                 staged_tile_epilogue<BLOCK_N, WGRAD, false>(p, &tmC, tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N,
@@ -455,9 +481,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (lane == 0) mbar_arrive(tmem_empty_bar + 8 * as);
                 continue;
             }
-            const int rbase = row0 + q * 32;                   // first output row of this warp
+            int rbase = row0 + q * 32;                         // first output row of this warp
+            int rlim = row_limit;
+            if (p.conv_mode != 0) {
+                // implicit-convolution tiles: the tile index is (image row, 128-pixel block) / (tap, 128-channel block);
+                // rows past the end of the image row / of the tap's channels are padding of the tile
+                const int mt = row0 / kBlockM;
+                if (WGRAD) {
+                    const int tap = mt / p.cv_kbr;
+                    rbase = tap * p.cv_rlimit + (mt % p.cv_kbr) * kBlockM + q * 32;
+                    rlim = (tap + 1) * p.cv_rlimit;
+                } else {
+                    const int line = mt / p.cv_tpr;
+                    rbase = line * p.cv_width + (mt % p.cv_tpr) * kBlockM + q * 32;
+                    rlim = line * p.cv_width + p.cv_rlimit;
+                }
+            }
             const int r = rbase + lane;                        // output row owned by this lane (row-per-lane layout)
-            const bool row_ok = r < row_limit;
+            const bool row_ok = r < rlim;
 #pragma unroll 1
             for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
                 const int n_base = col0 + ch * 32;
@@ -486,7 +527,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             float* dst = reinterpret_cast<float*>(p.C) + (long long)rbase * p.ldc + col;
 #pragma unroll 8
                             for (int rr = 0; rr < 32; ++rr)
-                                if (rbase + rr < row_limit) atomicAdd(dst + (long long)rr * p.ldc, stage[rr * 33 + lane]);
+                                if (rbase + rr < rlim) atomicAdd(dst + (long long)rr * p.ldc, stage[rr * 33 + lane]);
                         }
                     } else {
                         float s1 = 0.f, s2 = 0.f;          // rows beyond M were zero-filled by TMA: they add nothing
@@ -1434,6 +1475,164 @@ extern "C" int dlv3p_conv3x3_valid_wgrad_bf16(const void* x, const void* dy, flo
     p.kb_per_split = cdiv(total_kb, splits);
     p.splits = cdiv(total_kb, p.kb_per_split);
     p.conv_mode = 3; p.cv_rows_in = H; p.cv_rows_out = Ho; p.cv_width = Wo; p.cv_rlimit = 3 * Cin; p.cv_kbr = 2;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (bn) {
+        case 64: return launch_gemm<64, true>(tmA, tmB, tmC, p, st);
+        case 128: return launch_gemm<128, true>(tmA, tmB, tmC, p, st);
+        default: return launch_gemm<256, true>(tmA, tmB, tmC, p, st);
+    }
+}
+
+
+// =====================================================================================================================
+// 3x3 SAME stride-1 convolution as implicit GEMMs (conv modes 4 / 5 / 6 of gemm_tc_kernel): the logits convolution of
+// the decoder (ss.py:893-897; after boundary refinement its input is the 304-channel concat at 256 x 256, ss.py:915-954)
+// without the [pixels, 9*Cin] column matrix (5.7 GB per step at BASELINE cfg-4) that im2col + GEMM + col2im move.
+// =====================================================================================================================
+static int same_check(const char* who, const void* a, const void* b, const void* c, int N, int H, int W, int Cin, int Cout) {
+    DLV3P_REQUIRE(a && b && c && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, DLV3P_ERR_SHAPE,
+                  "%s: bad arguments N=%d H=%d W=%d Cin=%d Cout=%d", who, N, H, W, Cin, Cout);
+    DLV3P_REQUIRE((Cin % 8) == 0 && aligned16(a) && aligned16(b), DLV3P_ERR_ALIGN,
+                  "%s: Cin must be a multiple of 8 and the operand pointers 16-byte aligned (Cin=%d)", who, Cin);
+    DLV3P_REQUIRE((long long)N * H * cdiv(W, kBlockM) < (1LL << 23), DLV3P_ERR_UNSUPPORTED, "%s: too many tiles", who);
+    return 0;
+}
+
+extern "C" int dlv3p_conv3x3_same_fwd_bf16(const void* x, const void* wt, int64_t ldw, void* y, int c_dtype, int N, int H,
+                                           int W, int Cin, int Cout, const float* col_scale, const float* col_shift,
+                                           int act, float* col_stats, void* stream) {
+    int rc = same_check("conv3x3_same_fwd", x, wt, y, N, H, W, Cin, Cout);
+    if (rc) return rc;
+    DLV3P_REQUIRE(Cout <= 256, DLV3P_ERR_UNSUPPORTED, "conv3x3_same_fwd: Cout <= 256 (got %d)", Cout);
+    DLV3P_REQUIRE(ldw >= 9LL * Cin && (ldw % 8) == 0, DLV3P_ERR_ALIGN, "conv3x3_same_fwd: ldw >= 9*Cin and a multiple of 8");
+    DLV3P_REQUIRE((col_scale == nullptr) == (col_shift == nullptr), DLV3P_ERR_SHAPE, "conv3x3_same_fwd: scale/shift mismatch");
+    DLV3P_REQUIRE(c_dtype == DLV3P_BF16 || c_dtype == DLV3P_F32, DLV3P_ERR_DTYPE, "conv3x3_same_fwd: bad c_dtype %d", c_dtype);
+    const int bn = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256));
+    const int kbr = cdiv(Cin, kBlockK);
+    CUtensorMap tmA, tmB, tmC;
+    {
+        const long long dims[4] = {Cin, W, H, N};
+        const long long str[3] = {2LL * Cin, 2LL * W * Cin, 2LL * H * W * Cin};
+        const int box[4] = {kBlockK, kBlockM, 1, 1};
+        rc = make_tmap_nd(&tmA, x, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    rc = make_tmap(&tmB, wt, 9LL * Cin, Cout, ldw, kBlockK, bn);
+    if (rc) return rc;
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.tma_store = (c_dtype == DLV3P_BF16 && (Cout % 8) == 0 && aligned16(y) && bn >= 64) ? 1 : 0;
+    tmC = tmA;
+    if (p.tma_store) {
+        const long long dims[3] = {Cout, W, (long long)N * H};
+        const long long str[2] = {2LL * Cout, 2LL * W * Cout};
+        const int box[3] = {64, 32, 1};
+        rc = make_tmap_nd(&tmC, y, 3, dims, str, box);
+        if (rc) return rc;
+    }
+    p.cv_tpr = cdiv(W, kBlockM);
+    p.m_tiles = N * H * p.cv_tpr; p.n_tiles = cdiv(Cout, bn);
+    p.M = p.m_tiles * kBlockM; p.N = Cout; p.K = 9 * kbr * kBlockK;
+    p.C = y; p.ldc = Cout; p.c_dtype = c_dtype; p.col_scale = col_scale; p.col_shift = col_shift; p.act = act;
+    p.col_stats = col_stats; p.splits = 1;
+    p.conv_mode = 4; p.cv_rows_in = H; p.cv_rows_out = H; p.cv_width = W; p.cv_rlimit = W; p.cv_kbr = kbr; p.cv_run = Cin;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (bn) {
+        case 32: return launch_gemm<32, false>(tmA, tmB, tmC, p, st);
+        case 64: return launch_gemm<64, false>(tmA, tmB, tmC, p, st);
+        case 128: return launch_gemm<128, false>(tmA, tmB, tmC, p, st);
+        default: return launch_gemm<256, false>(tmA, tmB, tmC, p, st);
+    }
+}
+
+// dx[n,h,w,ci] = sum_{i,j,co} dy[n, h-i+1, w-j+1, co] * W[i,j,ci,co].  dy: bf16 [N,H,W,ld_dy] (ld_dy >= Cout, the engine's
+// 8-element padded cast of the fp32 logits gradient); wd: bf16 [Cin, 9*kp] K-major with kp = 64*ceil(Cout/64) columns per
+// tap, wd[ci, tap*kp + co] = W[tap, ci, co], zero beyond Cout.
+extern "C" int dlv3p_conv3x3_same_dgrad_bf16(const void* dy, int64_t ld_dy, const void* wd, void* dx, int N, int H, int W,
+                                             int Cin, int Cout, void* stream) {
+    int rc = same_check("conv3x3_same_dgrad", dy, wd, dx, N, H, W, Cin, Cout);
+    if (rc) return rc;
+    DLV3P_REQUIRE(ld_dy >= Cout && (ld_dy % 8) == 0 && aligned16(dx), DLV3P_ERR_ALIGN,
+                  "conv3x3_same_dgrad: ld_dy >= Cout, a multiple of 8, dx 16-byte aligned (ld_dy=%lld)", (long long)ld_dy);
+    const int kbr = cdiv(Cout, kBlockK), kp = kbr * kBlockK;
+    // fewest padded output columns: 304 input channels = 3 x 128 rather than 2 x 256
+    int bn = 256;
+    if (Cin <= 32) bn = 32; else if (Cin <= 64) bn = 64; else if (Cin <= 128) bn = 128;
+    else if (cdiv(Cin, 128) * 128 < cdiv(Cin, 256) * 256) bn = 128;
+    CUtensorMap tmA, tmB, tmC;
+    {
+        const long long dims[4] = {Cout, W, H, N};
+        const long long str[3] = {2LL * ld_dy, 2LL * W * ld_dy, 2LL * H * W * ld_dy};
+        const int box[4] = {kBlockK, kBlockM, 1, 1};
+        rc = make_tmap_nd(&tmA, dy, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    rc = make_tmap(&tmB, wd, 9LL * kp, Cin, 9LL * kp, kBlockK, bn);
+    if (rc) return rc;
+    {
+        const long long dims[3] = {Cin, W, (long long)N * H};
+        const long long str[2] = {2LL * Cin, 2LL * W * Cin};
+        const int box[3] = {64, 32, 1};
+        rc = make_tmap_nd(&tmC, dx, 3, dims, str, box);
+        if (rc) return rc;
+    }
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.cv_tpr = cdiv(W, kBlockM);
+    p.m_tiles = N * H * p.cv_tpr; p.n_tiles = cdiv(Cin, bn);
+    p.M = p.m_tiles * kBlockM; p.N = Cin; p.K = 9 * kp;
+    p.C = dx; p.ldc = Cin; p.c_dtype = DLV3P_BF16; p.splits = 1;
+    p.tma_store = bn >= 64 ? 1 : 0;
+    p.conv_mode = 5; p.cv_rows_in = H; p.cv_rows_out = H; p.cv_width = W; p.cv_rlimit = W; p.cv_kbr = kbr; p.cv_run = kp;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (bn) {
+        case 32: return launch_gemm<32, false>(tmA, tmB, tmC, p, st);
+        case 64: return launch_gemm<64, false>(tmA, tmB, tmC, p, st);
+        case 128: return launch_gemm<128, false>(tmA, tmB, tmC, p, st);
+        default: return launch_gemm<256, false>(tmA, tmB, tmC, p, st);
+    }
+}
+
+// dw[tap, ci, co] += sum_{n,h,w} x[n, h+i-1, w+j-1, ci] * dy[n,h,w,co]   (fp32 HWIO [3,3,Cin,Cout], accumulated)
+extern "C" int dlv3p_conv3x3_same_wgrad_bf16(const void* x, const void* dy, int64_t ld_dy, float* dw, int N, int H, int W,
+                                             int Cin, int Cout, void* stream) {
+    int rc = same_check("conv3x3_same_wgrad", x, dy, dw, N, H, W, Cin, Cout);
+    if (rc) return rc;
+    DLV3P_REQUIRE(ld_dy >= Cout && (ld_dy % 8) == 0 && Cout <= 256, DLV3P_ERR_ALIGN,
+                  "conv3x3_same_wgrad: ld_dy >= Cout, a multiple of 8, Cout <= 256 (ld_dy=%lld Cout=%d)", (long long)ld_dy, Cout);
+    const int bn = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
+    const int cit = cdiv(Cin, kBlockM);                   // 128-channel row tiles per tap
+    CUtensorMap tmA, tmB, tmC;
+    {
+        const long long dims[4] = {Cin, W, H, N};
+        const long long str[3] = {2LL * Cin, 2LL * W * Cin, 2LL * H * W * Cin};
+        const int box[4] = {64, kBlockK, 1, 1};
+        rc = make_tmap_nd(&tmA, x, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    rc = make_tmap(&tmB, dy, Cout, (long long)N * H * W, ld_dy, 64, kBlockK);
+    if (rc) return rc;
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.tma_store = ((Cout % 4) == 0 && aligned16(dw)) ? 1 : 0;      // TMA strides are multiples of 16 bytes
+    tmC = tmA;
+    if (p.tma_store) {
+        const long long dims[3] = {Cout, Cin, 9};
+        const long long str[2] = {4LL * Cout, 4LL * Cin * Cout};
+        const int box[3] = {32, 32, 1};
+        rc = make_tmap_nd(&tmC, dw, 3, dims, str, box, /*f32=*/true);
+        if (rc) return rc;
+    }
+    p.cv_tpr = cdiv(W, kBlockK);                          // 64-pixel reduction blocks per image row
+    const int total_kb = N * H * p.cv_tpr;
+    p.m_tiles = 9 * cit; p.n_tiles = cdiv(Cout, bn);
+    p.M = total_kb * kBlockK; p.N = Cout; p.K = p.m_tiles * kBlockM;
+    p.C = dw; p.ldc = Cout; p.c_dtype = DLV3P_F32;
+    const int tiles = p.m_tiles * p.n_tiles;
+    int splits = (2 * kNumSMs) / tiles; if (splits < 1) splits = 1; if (splits > total_kb) splits = total_kb;
+    p.kb_per_split = cdiv(total_kb, splits);
+    p.splits = cdiv(total_kb, p.kb_per_split);
+    p.conv_mode = 6; p.cv_rows_in = H; p.cv_rows_out = H; p.cv_width = W; p.cv_rlimit = Cin; p.cv_kbr = cit;
     cudaStream_t st = (cudaStream_t)stream;
     switch (bn) {
         case 64: return launch_gemm<64, true>(tmA, tmB, tmC, p, st);

@@ -639,7 +639,7 @@ class Plan:
         dw_w = P.view(lay, "depthwise_kernel").view(3, 3, Cin) if (is_sep or is_dw) else None
         dw_g = P.view(lay, "depthwise_kernel", grad=True).view(3, 3, Cin) if (is_sep or is_dw) else None
         gemm = not is_dw
-        implicit = False
+        implicit = implicit_same = False
         if gemm:
             wname = "pointwise_kernel" if is_sep else "kernel"
             Kdim = Cin if (is_sep or k == 1) else 9 * Cin
@@ -652,7 +652,24 @@ class Plan:
                         and tuple(dil) == (1, 1) and lay.padding == "valid"
                         and getattr(node, "explicit_pad", None) is None and not is_logits and other_id is None
                         and ops.conv3x3_valid_supported(Cin, Cout))
-            if implicit:
+            # dense 3x3 SAME stride-1 conv (the logits convolution, 304 channels at 256^2 after boundary refinement):
+            # implicit GEMMs over tap-shifted TMA windows, no [pixels, 9*Cin] column matrix
+            implicit_same = (self.implicit_conv and (self.bf16 or FORCE_IMPLICIT) and k == 3 and not is_sep
+                             and stride == 1 and tuple(dil) == (1, 1) and lay.padding == "same"
+                             and getattr(node, "explicit_pad", None) is None and other_id is None
+                             and (bn_node is None or Cout % 8 == 0) and ops.conv3x3_same_supported(Cin, Cout))
+            if implicit_same:
+                wdt = torch.bfloat16 if self.bf16 else torch.float32          # (fp32 only under FORCE_IMPLICIT, CPU tests)
+                kp_tap = (Cout + 63) // 64 * 64
+                wt = self._alloc((Cout, Kp), wdt, zero=True)
+                wd = self._alloc((Cin, 9 * kp_tap), wdt, zero=True) if training else None
+                self._wprep.append((w32, Kdim, Cout, wt, Kp, None, Np))
+
+                def prep_same():
+                    if wd is not None:       # wd[c, tap*kp + o] = W[tap, c, o]
+                        wd.view(Cin, 9, kp_tap)[:, :, :Cout].copy_(w32.view(9, Cin, Cout).permute(1, 0, 2))
+                self.prep.append(prep_same)
+            elif implicit:
                 wdt = torch.bfloat16 if self.bf16 else torch.float32          # (fp32 only under FORCE_IMPLICIT, CPU tests)
                 wt = self._alloc((Cout, Kp), wdt, zero=True)                  # forward B operand = the im2col GEMM's
                 wd = self._alloc((Cin, 9 * Cout), wdt) if training else None  # input-gradient B operand
@@ -743,7 +760,7 @@ class Plan:
             self.fwd.append(lambda: ops.subsample_fwd(xb, stride, out=xs))
             launches_f += 1
             A, lda = xs, Cin
-        elif implicit:
+        elif implicit or implicit_same:
             A, lda = None, Kp
         else:
             col = self._alloc((Mo, Kp), self.dt)
@@ -755,7 +772,13 @@ class Plan:
         addend_f = other.buf if other is not None else None
         if gemm:
             Kg = lda if (k == 3 and not is_sep) else Kdim
-            if implicit:
+            if implicit_same:
+                tgt = out.buf if (fuse_epi or bn_node is None) else y
+                stats_fn = stat if (bn_node is not None and training) else None
+                self.fwd.append(lambda: ops.conv3x3_same_fwd(
+                    xb, wt, tgt, Cout, ldw=Kp, col_scale=scale if fuse_epi else None, col_shift=shift if fuse_epi else None,
+                    act=act if fuse_epi else ACT_NONE, col_stats=stats_fn() if stats_fn else None))
+            elif implicit:
                 tgt = out.buf if (fuse_epi or bn_node is None) else y
                 stats_fn = stat if (bn_node is not None and training) else None
                 self.fwd.append(lambda: ops.conv3x3_valid_fwd(
@@ -777,7 +800,7 @@ class Plan:
                     act=act if fuse_epi else ACT_NONE, addend=addend_f if fuse_epi else None, ld_addend=Cout))
             launches_f += 1
         if bn_node is not None and training:
-            if not (gemm and (self.bf16 or implicit)):
+            if not (gemm and (self.bf16 or implicit or implicit_same)):
                 self.fwd.append(lambda: ops.bn_stats(y, Mo, Cout, stat()))
                 launches_f += 1
             upd = bn_node.calls
@@ -867,7 +890,17 @@ class Plan:
                     dy_get = lambda: g
             ld_dy = Np if (bn_node is None and y_dtype == torch.float32 and self.bf16) else Cout
 
-            if gemm and implicit:
+            if gemm and implicit_same:
+                self.bwd_seq(lambda: ops.conv3x3_same_wgrad(xb, dy_get(), ld_dy, g32, Cout), side=True, slot=slot)
+                if needs_in_grad:
+                    tgt, addend2 = self._grad_target(x)
+                    if addend2 is None:
+                        self.bwd_seq(lambda: ops.conv3x3_same_dgrad(dy_get(), ld_dy, wd, x.shape, Cout, tgt))
+                    else:
+                        tmp_get = self._reserve(f"dA{skey}", x.shape, self.dt)
+                        self.bwd_seq(lambda: ops.conv3x3_same_dgrad(dy_get(), ld_dy, wd, x.shape, Cout, tmp_get()))
+                        self.bwd_seq(lambda: ops.add(tmp_get(), addend2, tgt))
+            elif gemm and implicit:
                 self.bwd_seq(lambda: ops.conv3x3_valid_wgrad(xb, dy_get().view(N, Ho, Wo, Cout), g32, Cout), side=True,
                              slot=slot)
                 if needs_in_grad:
@@ -1402,13 +1435,20 @@ class Plan:
         self.load_batch(images)
         return self.predict_device().cpu().numpy()
 
+    def segment_device(self, labels: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Label maps [N,Ho,Wo] (int32, or the uint8 / int32 tensor passed in) of the batch resident in the input
+        buffer: forward, then bilinear up-sampling fused with the channel argmax on the low-resolution logits
+        (dlv3p_upsample_argmax) — the high-resolution logits / probabilities are never written."""
+        self.forward()
+        if labels is None:
+            labels = self.tail_buf("lab", self.out_shape[:3], torch.int32)
+        f = self.tail_factor
+        ops.upsample_argmax(self.logits.buf, f, f, labels)
+        return labels
+
     def segment(self, images) -> np.ndarray:
         self.load_batch(images)
-        self.forward()
-        zh = self.logits_highres()
-        lab = self.tail_buf("lab", self.out_shape[:3], torch.int32)
-        ops.softmax_argmax(zh, zh.numel() // zh.shape[-1], zh.shape[-1], labels=lab)
-        return lab.cpu().numpy().astype(np.int64)
+        return self.segment_device().cpu().numpy().astype(np.int64)
 
     def gradients(self) -> Dict[str, np.ndarray]:
         """{'layer/weight': gradient} after step_fwd_bwd (parity tests)."""

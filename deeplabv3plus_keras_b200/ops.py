@@ -182,6 +182,48 @@ def conv3x3_valid_wgrad(x: Tensor, dy: Tensor, dw: Tensor, Cout: int):
     return dw
 
 
+def upsample_argmax(z: Tensor, fh: int, fw: int, labels: Tensor):
+    """labels[N,H*fh,W*fw] (int32 or uint8) = argmax_c bilinear_upsample(z[N,H,W,C] fp32): the inference tail without the
+    high-resolution logits / probabilities."""
+    _chk(z, "z")
+    if z.dtype != torch.float32 or labels.dtype not in (torch.int32, torch.uint8):
+        raise ValueError("upsample_argmax: fp32 logits, int32 or uint8 labels")
+    N, H, W, Cc = z.shape
+    call("dlv3p_upsample_argmax", _p(z), _p(labels), labels.element_size(), N, H, W, Cc, fh, fw, _stream())
+    return labels
+
+
+def conv3x3_same_supported(Cin: int, Cout: int) -> bool:
+    """Shapes the implicit-GEMM SAME convolution entry points accept (see include/dlv3p.h)."""
+    return Cin % 8 == 0 and Cin >= 16 and Cout <= 256
+
+
+def conv3x3_same_fwd(x: Tensor, wt: Tensor, out: Tensor, Cout: int, ldw=None, col_scale=None, col_shift=None,
+                     act=ACT_NONE, col_stats=None):
+    """out[N,H,W,Cout] (bf16 or fp32) = epi(conv3x3_same(x[N,H,W,Cin])); wt bf16 [Cout, 9*Cin] K-major (pitch ldw)."""
+    _chk(x, "x")
+    N, H, W, Cin = x.shape
+    call("dlv3p_conv3x3_same_fwd_bf16", _p(x), _p(wt), 9 * Cin if ldw is None else ldw, _p(out), _dt(out), N, H, W, Cin,
+         Cout, _p(col_scale), _p(col_shift), act, _p(col_stats), _stream())
+    return out
+
+
+def conv3x3_same_dgrad(dy: Tensor, ld_dy: int, wd: Tensor, x_shape, Cout: int, out: Tensor):
+    """out[N,H,W,Cin] (bf16) = SAME conv_transpose(dy[N,H,W,:Cout] with channel pitch ld_dy); wd bf16 [Cin, 9*kp]."""
+    _chk(dy, "dy")
+    N, H, W, Cin = x_shape
+    call("dlv3p_conv3x3_same_dgrad_bf16", _p(dy), ld_dy, _p(wd), _p(out), N, H, W, Cin, Cout, _stream())
+    return out
+
+
+def conv3x3_same_wgrad(x: Tensor, dy: Tensor, ld_dy: int, dw: Tensor, Cout: int):
+    """dw (fp32 HWIO [3,3,Cin,Cout], accumulated) += shifted x windows^T dy."""
+    _chk(x, "x"); _chk(dy, "dy")
+    N, H, W, Cin = x.shape
+    call("dlv3p_conv3x3_same_wgrad_bf16", _p(x), _p(dy), ld_dy, _p(dw), N, H, W, Cin, Cout, _stream())
+    return dw
+
+
 def gemm_simt(a: Tensor, sam: int, sak: int, b: Tensor, sbk: int, sbn: int, out: Tensor, ldc: int, M: int, N: int,
               K: int, col_scale=None, col_shift=None, act=ACT_NONE, addend=None, ld_addend=0, accumulate=False):
     call("dlv3p_gemm_simt", _p(a), sam, sak, _p(b), sbk, sbn, _p(out), ldc, M, N, K, _dt(a), _dt(out),

@@ -44,6 +44,15 @@ COSTS: Dict[str, Tuple[str, Callable]] = {
                                                            18 * a[3] * (a[4] - 2) * (a[5] - 2) * a[6] * a[7])),
     "dlv3p_conv3x3_valid_wgrad_bf16": ("tensor", lambda a: ((a[3] * a[4] * a[5] * a[6] + a[3] * (a[4] - 2) * (a[5] - 2) * a[7]) * 2 + 36 * a[6] * a[7],
                                                            18 * a[3] * (a[4] - 2) * (a[5] - 2) * a[6] * a[7])),
+    # SAME 3x3: x once + y once (+ filter); args (x, wt, ldw, y, c_dtype, N, H, W, Cin, Cout, ...)
+    "dlv3p_conv3x3_same_fwd_bf16": ("tensor", lambda a: (a[5] * a[6] * a[7] * (a[8] * 2 + a[9] * _esz(a[4])) + 18 * a[8] * a[9],
+                                                        18 * a[5] * a[6] * a[7] * a[8] * a[9])),
+    # (dy, ld_dy, wd, dx, N, H, W, Cin, Cout)
+    "dlv3p_conv3x3_same_dgrad_bf16": ("tensor", lambda a: (a[4] * a[5] * a[6] * (a[7] + a[8]) * 2 + 18 * a[7] * a[8],
+                                                          18 * a[4] * a[5] * a[6] * a[7] * a[8])),
+    # (x, dy, ld_dy, dw, N, H, W, Cin, Cout)
+    "dlv3p_conv3x3_same_wgrad_bf16": ("tensor", lambda a: (a[4] * a[5] * a[6] * (a[7] + a[8]) * 2 + 36 * a[7] * a[8],
+                                                          18 * a[4] * a[5] * a[6] * a[7] * a[8])),
     "dlv3p_gemm_simt": ("fp32", lambda a: ((a[8] * a[10] + a[10] * a[9]) * _esz(a[11]) + a[8] * a[9] * _esz(a[12]),
                                           2 * a[8] * a[9] * a[10])),
     "dlv3p_im2col3x3": ("hbm", lambda a: ((a[2] * a[3] * a[4] * a[5] + a[2] * a[10] * a[11] * a[12]) * _esz(a[13]), 0)),

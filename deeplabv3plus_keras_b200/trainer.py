@@ -215,11 +215,10 @@ class Predictor:
         self.plan: Plan = model.plan(batch_size, training=False, **({"dtype": dtype} if dtype else {}))
         p = self.plan
         self.stream = torch.cuda.Stream()
-        self.labels = torch.empty(p.out_shape[:3], dtype=torch.int32, device=p.device)
+        small = p.out_shape[3] <= 256           # label ids fit a byte: a quarter of the label-map bytes (HBM and D2H)
+        self.labels = torch.empty(p.out_shape[:3], dtype=torch.uint8 if small else torch.int32, device=p.device)
         self.host_x = torch.empty(p.x_in.shape, dtype=torch.float32).pin_memory()
-        small = p.out_shape[3] <= 256           # label ids fit a byte: a quarter of the D2H bytes
-        self.host_labels = torch.empty(p.out_shape[:3], dtype=torch.uint8 if small else torch.int32).pin_memory()
-        self._labels_u8 = torch.empty(p.out_shape[:3], dtype=torch.uint8, device=p.device) if small else None
+        self.host_labels = torch.empty(p.out_shape[:3], dtype=self.labels.dtype).pin_memory()
         self._copy_stream = self._stage_x = self._staged = self._stage_free = None
         self.dev_x32 = torch.empty(p.x_in.shape, dtype=torch.float32, device=p.device) \
             if p.x_in.buf.dtype != torch.float32 else None
@@ -232,13 +231,10 @@ class Predictor:
             self._graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph, stream=self.stream):
                 self._run()
-        self.launches_per_step = p.launches_fwd + 2
+        self.launches_per_step = p.launches_fwd + 1
 
     def _run(self):
-        p = self.plan
-        p.forward()
-        zh = p.logits_highres()
-        ops.softmax_argmax(zh, zh.numel() // zh.shape[-1], zh.shape[-1], labels=self.labels)
+        self.plan.segment_device(self.labels)
 
     def step(self):
         with torch.cuda.stream(self.stream):
@@ -291,11 +287,7 @@ class Predictor:
             self.stage_inputs(images)
         self.step()
         with torch.cuda.stream(self.stream):
-            if self.host_labels.dtype == torch.uint8:
-                self._labels_u8.copy_(self.labels)
-                self.host_labels.copy_(self._labels_u8, non_blocking=True)
-            else:
-                self.host_labels.copy_(self.labels, non_blocking=True)
+            self.host_labels.copy_(self.labels, non_blocking=True)
         if prefetch_next is not None:
             self.prefetch(prefetch_next)
         self.stream.synchronize()

@@ -132,6 +132,24 @@ int dlv3p_conv3x3_valid_dgrad_bf16(const void* dy, const void* wd, void* dx, int
                                    void* stream);
 int dlv3p_conv3x3_valid_wgrad_bf16(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout,
                                    void* stream);
+/* 3x3 SAME stride-1 convolution (Conv2D(num_classes, kernel_size=3, padding='same', use_bias=False), the logits layer of
+ * the decoder, ss.py:893-897; after _refine_boundary its input is the 304-channel concat at 256 x 256, ss.py:915-954) as
+ * implicit GEMMs: every tap is a rank-4 TMA window (64 channels, 128 pixels of one image row, row, image) shifted by the
+ * tap, what falls outside the image is zero-filled by TMA — that IS the SAME padding; no [pixels, 9*Cin] column matrix.
+ *   fwd:   y[N,H,W,Cout] (c_dtype bf16 or fp32; Cout <= 256, any count: 21 classes run as one 32-column tile) =
+ *          epilogue(conv(x, W)); wt = bf16 [Cout, 9*Cin] K-major, pitch ldw, as for the VALID convolution.
+ *   dgrad: dx[N,H,W,Cin] (bf16) = sum_taps dy(shifted) * W^T.  dy = bf16 [N,H,W,ld_dy] (ld_dy >= Cout, multiple of 8);
+ *          wd = bf16 [Cin, 9*kp], kp = 64*ceil(Cout/64): wd[c, tap*kp + o] = W[tap,c,o], zero for o >= Cout.
+ *   wgrad: dw (fp32 HWIO [3,3,Cin,Cout]) += sum_pixels x(shifted) * dy; split over the pixel axis, partial tiles combined
+ *          with TMA reduce-adds (Cout % 4 == 0) or fp32 atomics.
+ * Cin a multiple of 8; other shapes / strides / dilations: dlv3p_im2col3x3 + dlv3p_gemm_bf16. */
+int dlv3p_conv3x3_same_fwd_bf16(const void* x, const void* wt, int64_t ldw, void* y, int c_dtype, int N, int H, int W,
+                                int Cin, int Cout, const float* col_scale, const float* col_shift, int act,
+                                float* col_stats, void* stream);
+int dlv3p_conv3x3_same_dgrad_bf16(const void* dy, int64_t ld_dy, const void* wd, void* dx, int N, int H, int W, int Cin,
+                                  int Cout, void* stream);
+int dlv3p_conv3x3_same_wgrad_bf16(const void* x, const void* dy, int64_t ld_dy, float* dw, int N, int H, int W, int Cin,
+                                  int Cout, void* stream);
 /* generic fp32-accumulate SIMT GEMM for the fp32 parity mode and shapes the TMA path cannot take:
  *   C[m,n] = sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] (+ C if accumulate), same epilogue as above.
  *   ab_dtype: storage of A and B; c_dtype: storage of C. */
@@ -238,6 +256,12 @@ int dlv3p_bilinear_fwd(const void* x, int64_t ld_x, void* y, int64_t ld_y, int N
 /* dx[N,H,W,C] = resize^T(dy) (+ addend) */
 int dlv3p_bilinear_bwd(const void* dy, int64_t ld_dy, void* dx, int64_t ld_dx, int N, int H, int W, int C, int fh,
                        int fw, const void* addend, int dy_dtype, int dx_dtype, void* stream);
+/* Inference tail (segment(), ss.py:1207-1227: K.resize_images of the logits, softmax, argmax): bilinear x(fh, fw)
+ * up-sampling of the LOW-RESOLUTION fp32 logits z[N,H,W,C] fused with the channel argmax (softmax is monotone) — the
+ * [N,H*fh,W*fw,C] logits / probabilities are never written.  labels[N,H*fh,W*fw]: int32 (label_bytes 4) or uint8
+ * (label_bytes 1, C <= 256); first maximum wins; bit-identical to dlv3p_bilinear_fwd + dlv3p_softmax_argmax. */
+int dlv3p_upsample_argmax(const float* z, void* labels, int label_bytes, int N, int H, int W, int C, int fh, int fw,
+                          void* stream);
 
 /* Activation('softmax') + ClassBalancedLoss (ss.py:909, 438-447) on an integer label map:
  *   p = softmax(z[pix,:]);  L_pix = -sum_i [ pw_i*y_i*log(p_i+eps) + nw_i*(1-y_i)*log(1-p_i+eps) ], y = onehot(label)

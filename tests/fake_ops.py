@@ -180,6 +180,46 @@ def conv3x3_valid_wgrad(x, dy, dw, Cout):
     return dw
 
 
+def upsample_argmax(z, fh, fw, labels):
+    labels.copy_(_resize(z.float(), fh, fw).argmax(-1).to(labels.dtype))
+    return labels
+
+
+def conv3x3_same_supported(Cin, Cout):
+    return Cin % 8 == 0 and Cin >= 16 and Cout <= 256
+
+
+def conv3x3_same_fwd(x, wt, out, Cout, ldw=None, col_scale=None, col_shift=None, act=ACT_NONE, col_stats=None):
+    N, H, W, Cin = x.shape
+    ldw = ldw or 9 * Cin
+    w = _rows(wt, Cout, ldw, 9 * Cin).float().reshape(Cout, 3, 3, Cin)                 # [o, i, j, c]
+    acc = F.conv2d(x.float().permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
+    if col_stats is not None:
+        col_stats[:Cout] += acc.sum(0)
+        col_stats[Cout:2 * Cout] += (acc * acc).sum(0)
+    out.view(-1, Cout).copy_(_epi(acc, col_scale, col_shift, act, None))
+    return out
+
+
+def conv3x3_same_dgrad(dy, ld_dy, wd, x_shape, Cout, out):
+    N, H, W, Cin = x_shape
+    kp = wd.shape[1] // 9
+    w = wd.float().view(Cin, 9, kp)[:, :, :Cout].reshape(Cin, 3, 3, Cout)          # [c, i, j, o]
+    g = dy.float().reshape(N, H, W, ld_dy)[..., :Cout]
+    dx = F.conv_transpose2d(g.permute(0, 3, 1, 2), w.permute(3, 0, 1, 2), padding=1).permute(0, 2, 3, 1)
+    out.copy_(dx)
+    return out
+
+
+def conv3x3_same_wgrad(x, dy, ld_dy, dw, Cout):
+    N, H, W, Cin = x.shape
+    g = dy.float().reshape(N, H, W, ld_dy)[..., :Cout]
+    wz = torch.zeros((Cout, Cin, 3, 3), dtype=torch.float32, requires_grad=True)
+    F.conv2d(x.float().permute(0, 3, 1, 2), wz, padding=1).backward(g.permute(0, 3, 1, 2))
+    dw.view(3, 3, Cin, Cout).add_(wz.grad.permute(2, 3, 1, 0))
+    return dw
+
+
 def gemm_simt(a, sam, sak, b, sbk, sbn, out, ldc, M, N, K, col_scale=None, col_shift=None, act=ACT_NONE, addend=None,
               ld_addend=0, accumulate=False):
     A = a.reshape(-1).as_strided((M, K), (sam, sak)).float()

@@ -97,8 +97,13 @@ def run(conf, B=2, pw=None, nw=None, Plan=None, seed=1024, decision_forced=True,
         return live, dead
 
     res = dict(ss=ss, plan=plan, x=x, y=y, teacher=teacher, teacher_grad=teacher_grad, grads=got_grads)
-    # ---- 1. teacher-forced
-    probe = OM.Probe(teacher=teacher, teacher_grad=teacher_grad, keep_values=False)
+    masks, taps = plan.decisions()
+    masks = {k: v.cpu() for k, v in masks.items()}
+    taps = {k: v.cpu() for k, v in taps.items()}
+    # ---- 1. teacher-forced (on the product's decisions too: a BN -> ReLU mask is decided from batch statistics that the
+    # product accumulates in fp32 atomics and the oracle in fp64, so an element within one ulp of zero can flip even on
+    # identical stored inputs — one such element moves a 10^5-term random-sign sum like dbeta by 1/sqrt(N))
+    probe = OM.Probe(teacher=teacher, teacher_grad=teacher_grad, masks=masks, pool_taps=taps, keep_values=False)
     d_tf, l2, g_tf, out_tf = OM.loss_and_grads(conf, w, xin, yt, pw, nw, dropout_mask=drop, emulate_bf16=bf16, probe=probe)
     res["unused_teacher"] = sorted(set(teacher) - set(probe.fwd))
     res["fwd"] = {k: dev(o, t) for k, (o, t) in probe.fwd.items()}
@@ -111,9 +116,6 @@ def run(conf, B=2, pw=None, nw=None, Plan=None, seed=1024, decision_forced=True,
     if not decision_forced:
         return res
     # ---- 2. decision-forced, free running
-    masks, taps = plan.decisions()
-    masks = {k: v.cpu() for k, v in masks.items()}
-    taps = {k: v.cpu() for k, v in taps.items()}
     probe2 = OM.Probe(masks=masks, pool_taps=taps, keep_values=False)
     d_df, l2b, g_df, out_df = OM.loss_and_grads(conf, w, xin, yt, pw, nw, dropout_mask=drop, emulate_bf16=bf16, probe=probe2)
     res["unused_sites"] = sorted((set(masks) - set(probe2.pre)) | (set(taps) - set(probe2.pool_arg)))

@@ -217,7 +217,44 @@ def test_implicit_conv_schedule(cpu_engine, monkeypatch):
     ref.set_loss(PW, NW)
     ref.load_batch(x, y)
     ref.step_fwd_bwd()
-    assert calls.count("im2col3x3") == n_im2col + 1 and "conv3x3_valid_fwd" not in calls
+    assert calls.count("im2col3x3") == n_im2col + 2 and "conv3x3_valid_fwd" not in calls      # block1_conv2 + logits conv
+    np.testing.assert_allclose(plan.logits.buf.numpy(), ref.logits.buf.numpy(), rtol=1e-4, atol=1e-5)
+    gb = ref.gradients()
+    for k in gb:
+        scale = max(np.abs(gb[k]).max(), 1e-3)
+        assert np.abs(ga[k] - gb[k]).max() <= 2e-3 * scale, k
+
+
+@pytest.mark.parametrize("case", [dict(base="xception", output_stride=16, image_size=65),
+                                  dict(base="xception", output_stride=8, image_size=49, refine=True, rate_mult=2)],
+                         ids=["logits-256ch", "logits-304ch-after-refinement"])
+def test_implicit_same_conv_schedule(cpu_engine, monkeypatch, case):
+    """The logits convolution (3x3 SAME, ss.py:893-897; 304 input channels after boundary refinement): the implicit-GEMM
+    schedule (conv3x3_same_fwd / _dgrad / _wgrad, prepared wt / wd filter matrices, no im2col / col2im) must reproduce
+    the im2col + GEMM schedule."""
+    monkeypatch.setattr(cpu_engine, "FORCE_IMPLICIT", True)
+    conf = util.make_conf(width=64, **case)
+    ss = util.build(conf)
+    util.randomize_weights(ss.model)
+    calls = []
+    for name in ("im2col3x3", "col2im3x3", "conv3x3_same_fwd", "conv3x3_same_dgrad", "conv3x3_same_wgrad"):
+        orig = getattr(fake_ops, name)
+        monkeypatch.setattr(fake_ops, name, (lambda orig, name: lambda *a, **k: (calls.append(name), orig(*a, **k))[1])(orig, name))
+    plan = cpu_engine.Plan(ss.model, 2, training=True)
+    x, y = util.synthetic_batch(conf, 2, plan.out_shape[1:3])
+    plan.set_loss(PW, NW)
+    plan.load_batch(x, y)
+    plan.step_fwd_bwd()
+    assert calls.count("conv3x3_same_fwd") == 1 and calls.count("conv3x3_same_dgrad") == 1
+    assert calls.count("conv3x3_same_wgrad") == 1 and "col2im3x3" not in calls
+    assert calls.count("im2col3x3") == 1                     # only the 3-channel stride-2 first convolution is left
+    ga = plan.gradients()
+    calls.clear()
+    ref = cpu_engine.Plan(ss.model, 2, training=True, implicit_conv=False)
+    ref.set_loss(PW, NW)
+    ref.load_batch(x, y)
+    ref.step_fwd_bwd()
+    assert "conv3x3_same_fwd" not in calls and calls.count("col2im3x3") >= 1
     np.testing.assert_allclose(plan.logits.buf.numpy(), ref.logits.buf.numpy(), rtol=1e-4, atol=1e-5)
     gb = ref.gradients()
     for k in gb:

@@ -188,6 +188,60 @@ def test_dwconv3x3_dgrad_bnred_large_mean_over_std(ratio):
     assert float((got[C:] - s2).abs().max()) <= 1e-2 * scale2, (float((got[C:] - s2).abs().max()), scale2)
 
 
+@pytest.mark.parametrize("case", [(2, 16, 32, 256, 21), (1, 9, 131, 304, 21), (2, 12, 260, 48, 19), (1, 5, 3, 64, 21),
+                                  (2, 7, 70, 96, 64), (1, 33, 33, 256, 32), (1, 4, 200, 136, 128)])
+def test_conv3x3_same_implicit_gemm(case):
+    """Implicit-GEMM 3x3 SAME stride-1 convolution (tap-shifted rank-4 TMA windows; outside the image = zero = the SAME
+    padding; no im2col matrix) — the logits layer (21 / 19 classes, fp32 output, Cin = 256 or 304 after boundary
+    refinement) and BatchNormalization-carrying shapes (bf16 output + column statistics): forward, input gradient and
+    filter gradient against the fp64 convolution on the same bf16 operands.  Widths straddle the 128-pixel M tile and the
+    64-pixel reduction block; channel counts straddle the 64-channel k-block (304 = 4.75 blocks) and the 128-row tile."""
+    o = ops()
+    N, H, W, Cin, Cout = case
+    bf = torch.bfloat16
+    x = rnd((N, H, W, Cin), bf, 1)
+    w = rnd((3, 3, Cin, Cout), torch.float32, 2, 0.1).to(bf)             # HWIO, bf16-representable
+    Kp = (9 * Cin + 7) // 8 * 8
+    wt = torch.zeros((Cout, Kp), dtype=bf)
+    wt[:, :9 * Cin] = w.reshape(9 * Cin, Cout).t()                       # [Cout, 9*Cin] K-major, as the im2col GEMM's B
+    kp = (Cout + 63) // 64 * 64
+    wd = torch.zeros((Cin, 9, kp), dtype=bf)
+    wd[:, :, :Cout] = w.reshape(9, Cin, Cout).permute(1, 0, 2)
+    wd = wd.reshape(Cin, 9 * kp).contiguous()
+
+    xr = x.double().requires_grad_(True)
+    wr = w.double().requires_grad_(True)
+    y_ref = torch.nn.functional.conv2d(xr.permute(0, 3, 1, 2), wr.permute(3, 2, 0, 1), padding=1).permute(0, 2, 3, 1)
+    ld = (Cout + 7) // 8 * 8
+    gy = rnd((N, H, W, Cout), bf, 5)
+    y_ref.backward(gy.double())
+    gy_pad = torch.zeros((N, H, W, ld), dtype=bf)
+    gy_pad[..., :Cout] = gy
+
+    # forward, fp32 output (logits) ...
+    y32 = torch.full((N, H, W, Cout), float("nan"), dtype=torch.float32, device=DEV)
+    o.conv3x3_same_fwd(x.to(DEV), wt.to(DEV), y32, Cout, ldw=Kp)
+    check("same fwd f32", y32, y_ref.detach(), 2e-3, 2e-3 * math.sqrt(9 * Cin) * 0.1)
+    # ... and bf16 output with column statistics and an epilogue (a convolution followed by BatchNormalization)
+    if Cout % 8 == 0:
+        yb = torch.full((N, H, W, Cout), float("nan"), dtype=bf, device=DEV)
+        stats = torch.zeros(2 * Cout, dtype=torch.float32, device=DEV)
+        o.conv3x3_same_fwd(x.to(DEV), wt.to(DEV), yb, Cout, ldw=Kp, col_stats=stats)
+        check("same fwd bf16", yb, y_ref.detach(), 1e-2, 1e-2 * math.sqrt(9 * Cin) * 0.1)
+        ys = yb.double().cpu().reshape(-1, Cout) if Cout > 32 else y_ref.detach().reshape(-1, Cout)
+        check("same fwd stats", stats, torch.cat([ys.sum(0), (ys * ys).sum(0)]), 5e-3, 5e-3 * math.sqrt(N * H * W) * 2)
+
+    dx = torch.full((N, H, W, Cin), float("nan"), dtype=bf, device=DEV)
+    o.conv3x3_same_dgrad(gy_pad.to(DEV), ld, wd.to(DEV), (N, H, W, Cin), Cout, dx)
+    check("same dgrad", dx, xr.grad, 1e-2, 1e-2 * math.sqrt(9 * Cout) * 0.1)
+
+    dw = torch.zeros((3, 3, Cin, Cout), dtype=torch.float32, device=DEV)
+    o.conv3x3_same_wgrad(x.to(DEV), gy_pad.to(DEV), ld, dw, Cout)
+    check("same wgrad", dw, wr.grad, 2e-3, 2e-3 * math.sqrt(N * H * W))
+    o.conv3x3_same_wgrad(x.to(DEV), gy_pad.to(DEV), ld, dw, Cout)          # accumulates
+    check("same wgrad x2", dw, 2 * wr.grad, 2e-3, 4e-3 * math.sqrt(N * H * W))
+
+
 @pytest.mark.parametrize("case", [(2, 20, 37, 32, 64), (1, 9, 131, 32, 64), (2, 12, 260, 40, 128), (1, 5, 3, 32, 64)])
 def test_conv3x3_valid_implicit_gemm(case):
     """Implicit-GEMM 3x3 VALID stride-1 convolution (overlapping-row tensor maps, no im2col matrix): forward with BN
@@ -707,6 +761,27 @@ def test_softmax_cbloss():
     cm = torch.zeros((C, C), dtype=torch.float64, device=DEV)
     o.confusion_matrix(lab.to(DEV), labels, P, C, cm)
     check("confusion", cm, O.confusion_matrix(lab, labels.cpu(), C), 0, 0)
+
+
+def test_fused_upsample_argmax_equals_materialised_path():
+    """dlv3p_upsample_argmax (inference tail: no high-resolution logits) gives the label map of bilinear_fwd +
+    softmax_argmax bit for bit — including exact ties (first maximum wins) — for int32 and uint8 labels, anisotropic
+    factors, and matches the oracle's resize + argmax."""
+    o = ops()
+    for (N, H, W, C, fh, fw) in ((2, 9, 11, 21, 16, 16), (1, 33, 33, 21, 16, 16), (1, 5, 7, 19, 8, 4), (2, 4, 4, 3, 1, 1)):
+        z = rnd((N, H, W, C), torch.float32, 3 + H, 2.0)
+        z[..., 1] = z[..., 0]                              # ties everywhere between classes 0 and 1
+        zd = z.to(DEV)
+        zh = o.bilinear_fwd(zd, fh, fw)
+        P = zh.numel() // C
+        want = torch.empty(P, dtype=torch.int32, device=DEV)
+        o.softmax_argmax(zh.view(P, C), P, C, labels=want)
+        for dt in (torch.int32, torch.uint8):
+            lab = torch.full((N, H * fh, W * fw), 77, dtype=dt, device=DEV)
+            o.upsample_argmax(zd, fh, fw, lab)
+            assert torch.equal(lab.view(-1).to(torch.int32), want), (N, H, W, C, fh, fw, dt)
+        ref = O.argmax_labels(O.resize_bilinear(z.double(), fh, fw))
+        assert (want.view(N, H * fh, W * fw).cpu().long() == ref).float().mean() > 0.999
 
 
 @pytest.mark.parametrize("case", [(2, 6, 7, 21, 16), (1, 5, 5, 21, 2), (1, 4, 6, 19, 8), (2, 3, 3, 21, 4),
