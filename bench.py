@@ -423,7 +423,8 @@ def run_check(args, rank, local_rank, world):
             continue
         ss = build_model(conf)
         ss.model.optimizer.lr = 1e-3
-        tr = Trainer(ss.model, B, process_group=dist.group.WORLD if mode == "dp" else None, buckets=args.buckets)
+        tr = Trainer(ss.model, B, process_group=dist.group.WORLD if mode == "dp" else None, buckets=args.buckets,
+                     exchange=args.exchange, grad_dtype=args.grad_dtype if mode == "dp" else "float32")
         x, y = synthetic(conf, B, tr.plan.out_shape[1:3], 4242)     # the same batch on every rank
         xs, ys = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
         losses = [tr.train_step_e2e(xs, ys) for _ in range(K)]
@@ -440,7 +441,7 @@ def run_check(args, rank, local_rank, world):
         l_1, w_1, f_1, g_1 = res["single"]
         rel = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-30))
         out = {"check": "data-parallel == single GPU on the same batch", "n_gpus": world, "steps": K, "dtype": dtype,
-               "buckets": args.buckets, "loss_dp": l_dp.tolist(), "loss_single": l_1.tolist(),
+               "buckets": args.buckets, "exchange": f"{args.exchange}/{args.grad_dtype}", "loss_dp": l_dp.tolist(), "loss_single": l_1.tolist(),
                "max_rel_loss_diff": float(np.max(np.abs(l_dp - l_1) / np.abs(l_1))),
                "weights_rms_rel_diff": rel(w_dp, w_1), "moving_stats_rms_rel_diff": rel(f_dp, f_1),
                "last_gradient_rms_rel_diff": rel(g_dp / world, g_1),
@@ -466,6 +467,10 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the config's)")
     ap.add_argument("--dtype", default="", help="override the config's dtype (float32 | bfloat16)")
     ap.add_argument("--buckets", type=int, default=4, help="gradient all-reduce slices behind backward (N>1)")
+    ap.add_argument("--exchange", default="overlap", choices=["overlap", "tail"],
+                    help="N>1: all-reduce prefix slices behind backward segments | one all-reduce after backward")
+    ap.add_argument("--grad-dtype", default="float32", choices=["float32", "bfloat16"],
+                    help="N>1, --exchange tail: dtype of the exchanged gradient copy")
     ap.add_argument("--check", action="store_true", help="data-parallel correctness check (launch under torchrun)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -510,7 +515,7 @@ def main():
     train = cfg["train"]
     if train:
         tr = Trainer(ss.model, batch, use_graph=not args.no_graph, process_group=pg, overlap_wgrad=not args.no_overlap,
-                     buckets=args.buckets)
+                     buckets=args.buckets, exchange=args.exchange, grad_dtype=args.grad_dtype)
     else:
         tr = Predictor(ss.model, batch, dtype=args.dtype, use_graph=not args.no_graph)
     plan = tr.plan
@@ -585,6 +590,8 @@ def main():
         "dtype": "bf16" if args.dtype == "bfloat16" else "f32", "data": "synthetic",
         "config": {"workload": cfg["workload"].format(batch=batch), "name": args.config,
                    "global_batch": batch * world, "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
+                   "exchange": (f"{args.exchange}/{args.grad_dtype}" + (f"/{args.buckets} buckets" if args.exchange == "overlap" else ""))
+                   if world > 1 else None,
                    "l2_policy": "per-step working set (GBs of activations) far exceeds the 126 MB L2"},
         "clocks": clocks, "loss": loss,
         "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

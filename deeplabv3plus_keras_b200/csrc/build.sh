@@ -20,5 +20,5 @@ done
 rc=0
 for p in "${pids[@]}"; do wait "$p" || rc=1; done
 if [ $rc -ne 0 ]; then cat "${BUILD}"/*.log | grep -v "^ptxas info" | head -80; exit 1; fi
-"${NVCC}" -shared -o "${OUT}" "${BUILD}"/*.o -lcudart
+"${NVCC}" -gencode arch=compute_100a,code=sm_100a -shared -o "${OUT}" "${BUILD}"/*.o -lcudart
 echo "built ${OUT}"

@@ -341,9 +341,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                             for (int h = 0; h < kBlockM / 64; ++h)
                                 tma_load_4d(a_dst + h * 8192, &tmA, fb, ci0 + 64 * h, qd * 64 + tap % 3 - 1, ho + tap / 3 - 1, n);
+                            // dy through a rank-3 map (channel, pixel of the row, row): pixels past the end of the row are
+                            // zero-filled — the shifted x window is NOT zero there (it still covers real pixels)
 #pragma unroll
                             for (int h = 0; h < BLOCK_N / 64; ++h)
-                                tma_load_2d(b_dst + h * 8192, &tmB, fb, col0 + 64 * h, r * p.cv_width + qd * 64);
+                                tma_load_3d(b_dst + h * 8192, &tmB, fb, col0 + 64 * h, qd * 64, r);
                         } else if (WGRAD) {
                             // filter gradient: output rows = the 128-element padded K-run of filter row i, reduction
                             // block kb = 64 consecutive output pixels of one image row
@@ -530,10 +532,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 if (rbase + rr < rlim) atomicAdd(dst + (long long)rr * p.ldc, stage[rr * 33 + lane]);
                         }
                     } else {
-                        float s1 = 0.f, s2 = 0.f;          // rows beyond M were zero-filled by TMA: they add nothing
+                        // rows beyond M were zero-filled by TMA and add nothing; the ghost pixels past the end of an image
+                        // row of a SAME-convolution tile are NOT zero (their shifted windows cover real pixels): skipped
+                        float s1 = 0.f, s2 = 0.f;
 #pragma unroll 8
                         for (int rr = 0; rr < 32; ++rr) {
-                            const float u = stage[rr * 33 + lane];
+                            const float u = (rbase + rr < rlim) ? stage[rr * 33 + lane] : 0.f;
                             s1 += u; s2 = fmaf(u, u, s2);
                         }
                         if (col < p.N) {
@@ -1610,8 +1614,13 @@ extern "C" int dlv3p_conv3x3_same_wgrad_bf16(const void* x, const void* dy, int6
         rc = make_tmap_nd(&tmA, x, 4, dims, str, box);
         if (rc) return rc;
     }
-    rc = make_tmap(&tmB, dy, Cout, (long long)N * H * W, ld_dy, 64, kBlockK);
-    if (rc) return rc;
+    {
+        const long long dims[3] = {Cout, W, (long long)N * H};
+        const long long str[2] = {2LL * ld_dy, 2LL * W * ld_dy};
+        const int box[3] = {64, kBlockK, 1};
+        rc = make_tmap_nd(&tmB, dy, 3, dims, str, box);
+        if (rc) return rc;
+    }
     GemmParams p;
     memset(&p, 0, sizeof(p));
     p.tma_store = ((Cout % 4) == 0 && aligned16(dw)) ? 1 : 0;      // TMA strides are multiples of 16 bytes

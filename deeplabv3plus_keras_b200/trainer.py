@@ -19,7 +19,19 @@ from .engine import Plan
 
 class Trainer:
     def __init__(self, model, batch_size: int, dtype: Optional[str] = None, use_graph: bool = True,
-                 buckets: int = 4, process_group=None, fused_tail: bool = True, overlap_wgrad: bool = True):
+                 buckets: int = 4, process_group=None, fused_tail: bool = True, overlap_wgrad: bool = True,
+                 exchange: str = "overlap", grad_dtype: str = "float32"):
+        """`exchange` (world > 1): "overlap" = the arena prefixes each backward segment finished are all-reduced on a
+        communication stream while the next segment runs (`buckets` segments); "tail" = ONE all-reduce of the whole arena
+        after backward on the training stream.  Every hot kernel here is a persistent one-CTA-per-SM launch, so NCCL's
+        CTAs displace CTAs of whatever runs beside them and that kernel's tail doubles: overlapping hides nothing
+        beyond what it costs, and the tail exchange of a bf16 copy of the gradients (`grad_dtype="bfloat16"`, half
+        the bytes, summed in fp32 per pair by NCCL's bf16 reduction) is the cheaper one (profiles/r2_scaling.md)."""
+        if exchange not in ("overlap", "tail") or grad_dtype not in ("float32", "bfloat16"):
+            raise ValueError("exchange: 'overlap' | 'tail'; grad_dtype: 'float32' | 'bfloat16'")
+        if grad_dtype == "bfloat16" and exchange != "tail":
+            raise ValueError("grad_dtype='bfloat16' needs exchange='tail'")
+        self.exchange, self.grad_dtype = exchange, grad_dtype
         self.model = model
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
@@ -42,7 +54,9 @@ class Trainer:
         self.stream = torch.cuda.Stream()
         if overlap_wgrad:
             p.side_stream = torch.cuda.Stream()
-        self.comm_stream = torch.cuda.Stream() if self.world > 1 else None
+        self.comm_stream = torch.cuda.Stream() if (self.world > 1 and exchange == "overlap") else None
+        self._g16 = torch.empty(p.params.n_train, dtype=torch.bfloat16, device=p.device) \
+            if (self.world > 1 and grad_dtype == "bfloat16") else None
         self._segments: List = []          # (graph or callable, grad-arena range completed by it)
         self._prep_graph = None
         # pinned host staging for the end-to-end path
@@ -58,7 +72,7 @@ class Trainer:
         self.stage_y = torch.empty(tuple(p.labels.shape), dtype=torch.int32, device=p.device)
         self._staged = None                # event: staging buffers hold a complete batch
         self._stage_free = None            # event: the training stream has consumed the staging buffers
-        self._build(buckets if self.world > 1 else 1)
+        self._build(buckets if (self.world > 1 and exchange == "overlap") else 1)
 
     # ------------------------------------------------------------------------------------------------------
     def _build(self, n_buckets: int):
@@ -144,10 +158,12 @@ class Trainer:
             p.ensure_current()                  # another plan of the model stepped, or weights were set / loaded
             for part, ranges in zip(self._parts, self._ranges):
                 part()
-                if self.world > 1 and ranges:
+                if self.world > 1 and ranges and self.exchange == "overlap":
                     self._exchange(ranges)      # all-reduce what this segment finished while the next one runs
-            if self.world > 1:
+            if self.world > 1 and self.exchange == "overlap":
                 self.stream.wait_event(self._comm_done)
+            elif self.world > 1:
+                self._exchange_tail()
             if optimizer_step:
                 p.regularization()
                 self._adam()
@@ -162,6 +178,17 @@ class Trainer:
             dp.allreduce_ranges(g, ranges, self.pg)
             self._comm_done = torch.cuda.Event()
             self._comm_done.record(self.comm_stream)
+
+    def _exchange_tail(self):
+        """One all-reduce of the complete gradient arena behind backward, on the training stream."""
+        P = self.plan.params
+        g = P.g[:P.n_train]
+        if self._g16 is not None:
+            ops.cast(g, self._g16)
+            torch.distributed.all_reduce(self._g16, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+            ops.cast(self._g16, g)
+        else:
+            torch.distributed.all_reduce(g, op=torch.distributed.ReduceOp.SUM, group=self.pg)
 
     def _adam(self):
         P, opt = self.plan.params, self.opt
