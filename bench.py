@@ -401,10 +401,11 @@ def summarise_calls(per_call, peaks_tc, peak_hbm):
 
 # ---------------------------------------------------------------------------------------------- DP correctness
 def run_check(args, rank, local_rank, world):
-    """Data-parallel correctness ON HARDWARE: every rank trains on the SAME batch with the product Trainer (prefix
-    all-reduces behind the backward graph segments, 1/world in Adam), so the averaged gradient equals the single-GPU
-    gradient and after k steps every rank's weights and loss must equal a 1-GPU run of the same batch (rank 0 runs
-    that reference in-process with world=1) up to the noise of fp32 atomics / bf16 re-quantisation."""
+    """Data-parallel correctness ON HARDWARE: every rank trains on the SAME batch with the product Trainer (graph
+    segments, prefix / tail all-reduce, 1/world in Adam), so the averaged gradient equals the single-GPU gradient and
+    after k steps every rank's weights and loss must equal a 1-GPU run of the same batch (rank 0 runs that reference
+    in-process with world=1).  Run in float32 (default here): the bf16 step is not reproducible run to run beyond ~1e-2
+    even on one GPU (fp32 atomics order -> bf16 rounding flips), which would mask an exchange bug."""
     import torch.distributed as dist
 
     from deeplabv3plus_keras_b200.trainer import Trainer
@@ -413,7 +414,7 @@ def run_check(args, rank, local_rank, world):
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     real_stdout = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
-    dtype = args.dtype
+    dtype = args.check_dtype
     conf = make_conf(dtype, image_size=257)
     conf["nn_arch"]["dropout_rate"] = 0.0               # replicas draw independent dropout masks by design
     B, K = 4, 5
@@ -427,28 +428,35 @@ def run_check(args, rank, local_rank, world):
                      exchange=args.exchange, grad_dtype=args.grad_dtype if mode == "dp" else "float32")
         x, y = synthetic(conf, B, tr.plan.out_shape[1:3], 4242)     # the same batch on every rank
         xs, ys = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
+        P = tr.plan.params
+        tr.stage_inputs(xs, ys)
+        tr.step(optimizer_step=False)                   # gradient of the initial weights, exchanged, not applied
+        torch.cuda.synchronize()
+        g0, w0 = P.g[:P.n_train].clone(), P.w.clone()
         losses = [tr.train_step_e2e(xs, ys) for _ in range(K)]
         torch.cuda.synchronize()
-        res[mode] = (np.array(losses), tr.plan.params.w.clone(), tr.plan.params.f.clone(), tr.plan.params.g.clone())
-    # all ranks hold identical weights after K steps
+        res[mode] = (np.array(losses), P.w.clone(), P.f.clone(), g0, w0)
     w = res["dp"][1]
     ref = w.clone()
     dist.broadcast(ref, 0)
     same = torch.tensor([float((w - ref).abs().max())], device="cuda")
     dist.all_reduce(same, op=dist.ReduceOp.MAX)
     if rank == 0:
-        l_dp, w_dp, f_dp, g_dp = res["dp"]
-        l_1, w_1, f_1, g_1 = res["single"]
+        l_dp, w_dp, f_dp, g_dp, w0 = res["dp"]
+        l_1, w_1, f_1, g_1, _ = res["single"]
         rel = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-30))
         out = {"check": "data-parallel == single GPU on the same batch", "n_gpus": world, "steps": K, "dtype": dtype,
-               "buckets": args.buckets, "exchange": f"{args.exchange}/{args.grad_dtype}", "loss_dp": l_dp.tolist(), "loss_single": l_1.tolist(),
+               "exchange": f"{args.exchange}/{args.grad_dtype}" + (f"/{args.buckets} buckets" if args.exchange == "overlap" else ""),
+               "loss_dp": l_dp.tolist(), "loss_single": l_1.tolist(),
+               "first_gradient_rms_rel_diff": rel(g_dp / world, g_1),
                "max_rel_loss_diff": float(np.max(np.abs(l_dp - l_1) / np.abs(l_1))),
-               "weights_rms_rel_diff": rel(w_dp, w_1), "moving_stats_rms_rel_diff": rel(f_dp, f_1),
-               "last_gradient_rms_rel_diff": rel(g_dp / world, g_1),
-               "weight_update_rms": float((w_1 - torch.zeros_like(w_1)).norm()),
+               "weight_update_rms_rel_diff": float((w_dp - w_1).norm() / (w_1 - w0).norm().clamp_min(1e-30)),
+               "moving_stats_rms_rel_diff": rel(f_dp, f_1),
                "max_abs_weight_diff_between_ranks": float(same.item())}
-        tol = 2e-2 if dtype == "bfloat16" else 1e-3
-        out["ok"] = bool(out["max_rel_loss_diff"] < tol and out["weights_rms_rel_diff"] < tol
+        tol_g = 3e-1 if dtype != "float32" else (1e-3 if args.grad_dtype == "float32" else 1e-2)
+        tol_l = 1e-3 if dtype == "float32" else 5e-2
+        out["ok"] = bool(out["first_gradient_rms_rel_diff"] < tol_g and out["max_rel_loss_diff"] < tol_l
+                         and out["weight_update_rms_rel_diff"] < (5e-2 if dtype == "float32" else 1.0)
                          and out["max_abs_weight_diff_between_ranks"] == 0.0)
         real_stdout.write(json.dumps(out) + "\n")
         real_stdout.flush()
@@ -471,6 +479,7 @@ def main():
                     help="N>1: all-reduce prefix slices behind backward segments | one all-reduce after backward")
     ap.add_argument("--grad-dtype", default="float32", choices=["float32", "bfloat16"],
                     help="N>1, --exchange tail: dtype of the exchanged gradient copy")
+    ap.add_argument("--check-dtype", default="float32", help="--check: float32 (reproducible) | bfloat16")
     ap.add_argument("--check", action="store_true", help="data-parallel correctness check (launch under torchrun)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

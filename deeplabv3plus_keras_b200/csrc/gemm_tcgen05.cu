@@ -274,7 +274,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int B_BYTES = BLOCK_N * kBlockK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr int kStages = GemmCfg<BLOCK_N>::kStages;
-    constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;            // two accumulator stages (64 .. 512, power of two)
+    // accumulator stages in TMEM: two 256 / 128-column tiles, four 64-column or eight 32-column ones (256 columns): the
+    // narrow-N GEMMs (MobileNetV2's 16..96-channel projections, the 21-class logits convolution) have ONE k-block per tile,
+    // so a tile lives ~3 us of pure latency (TMA -> MMA -> TMEM read -> store); with two stages the issuer stalls on the
+    // epilogue every other tile, with eight the chain is pipelined and the kernel becomes bandwidth-bound
+    constexpr uint32_t kAcc = BLOCK_N >= 128 ? 2u : (BLOCK_N == 64 ? 4u : 8u);
+    constexpr uint32_t TMEM_COLS = kAcc * BLOCK_N;         // 256 .. 512, power of two
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* epi_bytes = smem + kStages * STAGE_BYTES;                       // 1024-aligned (stage sizes are)
@@ -284,9 +289,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t full_bar = smem_u32(bars);                      // kStages
     const uint32_t empty_bar = smem_u32(bars + kStages);           // kStages
-    const uint32_t tmem_full_bar = smem_u32(bars + 2 * kStages);   // 2
-    const uint32_t tmem_empty_bar = smem_u32(bars + 2 * kStages + 2);  // 2
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    const uint32_t tmem_full_bar = smem_u32(bars + 2 * kStages);          // kAcc
+    const uint32_t tmem_empty_bar = smem_u32(bars + 2 * kStages + kAcc);  // kAcc
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kAcc);
+    static_assert((2 * kStages + 2 * kAcc + 1) * 8 <= 256, "barrier area");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     pdl_launch_dependents();
@@ -298,7 +304,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
         if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
         for (int s = 0; s < kStages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + 8 * s, 1); mbar_init(tmem_empty_bar + 8 * s, kEpiWarps); }
+        for (int s = 0; s < (int)kAcc; ++s) { mbar_init(tmem_full_bar + 8 * s, 1); mbar_init(tmem_empty_bar + 8 * s, kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -410,8 +416,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++t) {
                 int row0, col0, kb_begin, kb_end;
                 decode_work<BLOCK_N, WGRAD>(p, w, row0, col0, kb_begin, kb_end);
-                const uint32_t as = t & 1u;                    // accumulator stage
-                mbar_wait(tmem_empty_bar + 8 * as, ((t >> 1) & 1u) ^ 1u);   // epilogue has drained this stage
+                const uint32_t as = t % kAcc;                  // accumulator stage
+                mbar_wait(tmem_empty_bar + 8 * as, ((t / kAcc) & 1u) ^ 1u);   // epilogue has drained this stage
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BLOCK_N;
                 for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
@@ -456,8 +462,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++t) {
                 int row0, col0, kb_begin, kb_end;
                 decode_work<BLOCK_N, WGRAD>(p, w, row0, col0, kb_begin, kb_end);
-                const uint32_t as = t & 1u;
-                mbar_wait(tmem_full_bar + 8 * as, (t >> 1) & 1u);
+                const uint32_t as = t % kAcc;
+                mbar_wait(tmem_full_bar + 8 * as, (t / kAcc) & 1u);
                 tc_fence_after();
                 int rb = row0 + q * 32, rl = row_limit, c2 = -1;
                 if (p.conv_mode != 0) {
@@ -476,8 +482,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++t) {
             int row0, col0, kb_begin, kb_end;
             decode_work<BLOCK_N, WGRAD>(p, w, row0, col0, kb_begin, kb_end);
-            const uint32_t as = t & 1u;
-            mbar_wait(tmem_full_bar + 8 * as, (t >> 1) & 1u);
+            const uint32_t as = t % kAcc;
+            mbar_wait(tmem_full_bar + 8 * as, (t / kAcc) & 1u);
             tc_fence_after();
             if (half == 1) {                                   // the direct-store fallback uses one warp per quadrant
                 if (lane == 0) mbar_arrive(tmem_empty_bar + 8 * as);
