@@ -419,8 +419,8 @@ def run_check(args, rank, local_rank, world):
     conf["nn_arch"]["dropout_rate"] = 0.0               # replicas draw independent dropout masks by design
     B, K = 4, 5
     res = {}
-    for mode in ("dp", "single"):
-        if mode == "single" and rank != 0:
+    for mode in ("dp", "single", "single2"):
+        if mode != "dp" and rank != 0:
             continue
         ss = build_model(conf)
         ss.model.optimizer.lr = 1e-3
@@ -441,10 +441,19 @@ def run_check(args, rank, local_rank, world):
     dist.broadcast(ref, 0)
     same = torch.tensor([float((w - ref).abs().max())], device="cuda")
     dist.all_reduce(same, op=dist.ReduceOp.MAX)
+    # the exchanged gradient arena is bit-identical on every rank (an all-reduce result is), i.e. every slice of the
+    # arena went through the exchange: the local gradients differ in their last bits (fp32 atomics order)
+    gref = res["dp"][3].clone()
+    dist.broadcast(gref, 0)
+    gsame = torch.tensor([float((res["dp"][3] - gref).abs().max())], device="cuda")
+    dist.all_reduce(gsame, op=dist.ReduceOp.MAX)
     if rank == 0:
         l_dp, w_dp, f_dp, g_dp, w0 = res["dp"]
         l_1, w_1, f_1, g_1, _ = res["single"]
+        l_2, w_2, f_2, g_2, _ = res["single2"]           # a second, independent 1-GPU run: the run-to-run noise floor
         rel = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-30))
+        floor_g, floor_l = rel(g_2, g_1), float(np.max(np.abs(l_2 - l_1) / np.abs(l_1)))
+        floor_u = float((w_2 - w_1).norm() / (w_1 - w0).norm().clamp_min(1e-30))
         out = {"check": "data-parallel == single GPU on the same batch", "n_gpus": world, "steps": K, "dtype": dtype,
                "exchange": f"{args.exchange}/{args.grad_dtype}" + (f"/{args.buckets} buckets" if args.exchange == "overlap" else ""),
                "loss_dp": l_dp.tolist(), "loss_single": l_1.tolist(),
@@ -452,11 +461,16 @@ def run_check(args, rank, local_rank, world):
                "max_rel_loss_diff": float(np.max(np.abs(l_dp - l_1) / np.abs(l_1))),
                "weight_update_rms_rel_diff": float((w_dp - w_1).norm() / (w_1 - w0).norm().clamp_min(1e-30)),
                "moving_stats_rms_rel_diff": rel(f_dp, f_1),
+               "single_vs_single_floor": {"first_gradient": floor_g, "max_rel_loss": floor_l, "weight_update": floor_u},
+               "max_abs_exchanged_gradient_diff_between_ranks": float(gsame.item()),
                "max_abs_weight_diff_between_ranks": float(same.item())}
-        tol_g = 3e-1 if dtype != "float32" else (1e-3 if args.grad_dtype == "float32" else 1e-2)
-        tol_l = 1e-3 if dtype == "float32" else 5e-2
-        out["ok"] = bool(out["first_gradient_rms_rel_diff"] < tol_g and out["max_rel_loss_diff"] < tol_l
-                         and out["weight_update_rms_rel_diff"] < (5e-2 if dtype == "float32" else 1.0)
+        # the step is not bit-reproducible (fp32 atomics order -> a few ReLU / max-pool decisions at near-ties, and Adam's
+        # first steps are sign-like): the data-parallel run must be as close to a 1-GPU run as two 1-GPU runs are
+        extra = 0.0 if args.grad_dtype == "float32" else 5e-3          # bf16 rounding of the exchanged copy
+        out["ok"] = bool(out["first_gradient_rms_rel_diff"] <= 3 * floor_g + 1e-4 + extra
+                         and out["max_rel_loss_diff"] <= 3 * floor_l + 1e-4 + extra
+                         and out["weight_update_rms_rel_diff"] <= 3 * floor_u + 1e-3 + 10 * extra
+                         and out["max_abs_exchanged_gradient_diff_between_ranks"] == 0.0
                          and out["max_abs_weight_diff_between_ranks"] == 0.0)
         real_stdout.write(json.dumps(out) + "\n")
         real_stdout.flush()
