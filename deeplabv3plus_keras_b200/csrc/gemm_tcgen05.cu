@@ -566,11 +566,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
                 if (row_ok) {
                     if (p.col_scale != nullptr) {
+                        const int jmax = p.N - n_base;             // columns of this chunk that exist (predicated loads)
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int n = min(n_base + j, p.N - 1);
-                            v[j] = fmaf(v[j], __ldg(p.col_scale + n), __ldg(p.col_shift + n));
-                        }
+                        for (int j = 0; j < 32; ++j)
+                            if (j < jmax) v[j] = fmaf(v[j], __ldg(p.col_scale + n_base + j), __ldg(p.col_shift + n_base + j));
                     }
                     if (p.act != DLV3P_ACT_NONE) {
 #pragma unroll
@@ -581,11 +580,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)r * p.ldc + n_base;
                         const __nv_bfloat16* add =
                             p.addend ? reinterpret_cast<const __nv_bfloat16*>(p.addend) + (long long)r * p.ld_add + n_base : nullptr;
-                        const bool vec = full && ((p.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                        // 16-byte stores per group of 8 columns; a narrow output (MobileNetV2's 16 / 24 / 32-channel projections)
+                        // stores its 2 / 3 / 4 whole groups instead of 16 / 24 / 32 two-byte elements per lane
+                        const bool vec = (full || (p.N & 7) == 0) && ((p.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                                          (add == nullptr || (((p.ld_add & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.addend) & 15) == 0)));
                         if (vec) {
 #pragma unroll
                             for (int g = 0; g < 4; ++g) {
+                                if (n_base + g * 8 >= p.N) break;
                                 float f[8];
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) f[j] = v[g * 8 + j];
