@@ -10,6 +10,7 @@ The backward schedule is written by hand per macro-op (there is no autograd anyw
 from __future__ import annotations
 
 import math
+from types import SimpleNamespace
 from typing import Callable, Dict, List, Optional, Tuple
 
 import numpy as np
@@ -45,6 +46,13 @@ _CHANNEL_AXES = {"depthwise_kernel": (2,), "pointwise_kernel": (2, 3), "kernel":
 def _phys_shape(name: str, shape, phys=phys_channels) -> Tuple[int, ...]:
     axes = _CHANNEL_AXES.get(name, ())
     return tuple(phys(d) if i in axes else d for i, d in enumerate(shape))
+
+
+class _MacroScope(SimpleNamespace):
+    """Names set up by Plan._emit_conv for its forward / backward halves; a name a branch did not define reads as None."""
+
+    def __getattr__(self, name):
+        return None
 
 
 class Value:
@@ -577,6 +585,9 @@ class Plan:
 
     # ---- conv macro-op ---------------------------------------------------------------------------------
     def _emit_conv(self, m: dict, out_id: int):
+        """Conv / SeparableConv / Depthwise (+ BatchNormalization)(+ ReLU/ReLU6)(+ residual Add) macro-op: geometry, output
+        value, parameters and BN state here; launches in _emit_conv_forward / _emit_conv_backward (they share the
+        namespace `cx` of this set-up)."""
         P, N = self.params, self.N
         node: FlatNode = m["conv"]
         lay = node.layer
@@ -732,6 +743,24 @@ class Plan:
         if bn_node is not None and not virt and not pool_virt:
             self._trace_value(f"{tname}/out", lambda: out.buf, Cout_log, out_shape)
 
+        cx = _MacroScope(**{k: v for k, v in locals().items() if k not in ("self", "cx")})
+        self._emit_conv_forward(cx)
+        if training:
+            self._emit_conv_backward(cx)
+
+    def _emit_conv_forward(self, cx):
+        """Forward launches of a conv macro-op (A operand: depthwise stage / subsample / im2col / implicit; GEMM with
+        epilogue; training BN statistics + apply, or the BN finished inside the reader)."""
+        Cin, Cout, Ho, Kdim, Kp, Mo, N, Wo = cx.Cin, cx.Cout, cx.Ho, cx.Kdim, cx.Kp, cx.Mo, cx.N, cx.Wo
+        act, beta, bn, bn_node = cx.act, cx.beta, cx.bn, cx.bn_node
+        dil, dw_w, gamma, gemm = cx.dil, cx.dw_w, cx.gamma, cx.gemm
+        implicit, implicit_same, in_act, in_sc = cx.implicit, cx.implicit_same, cx.in_act, cx.in_sc
+        in_sh, invstd, is_dw, is_sep = cx.in_sh, cx.invstd, cx.is_dw, cx.is_sep
+        k, launches_f, lay, ld_out = cx.k, cx.launches_f, cx.lay, cx.ld_out
+        mean, mm, mv, other = cx.mean, cx.mm, cx.mv, cx.other
+        out, pad4, pl, pool_virt = cx.out, cx.pad4, cx.pl, cx.pool_virt
+        pt, scale, shift, stat = cx.pt, cx.scale, cx.shift, cx.stat
+        stride, training, virt, w32, wt, x, xb, y = cx.stride, cx.training, cx.virt, cx.w32, cx.wt, cx.x, cx.xb, cx.y
         # ---- forward ------------------------------------------------------------------------------------
         # A operand of the GEMM
         if is_sep or is_dw:
@@ -832,9 +861,24 @@ class Plan:
             self.fwd.append(lambda: ops.affine_act(out.buf, Mo, Cout, out.buf, scale, shift, act, addend=addend_f))
             launches_f += 1
         self.launches_fwd += launches_f
-        if not training:
-            return
 
+        cx.A = A
+        cx.lda = lda
+
+    def _emit_conv_backward(self, cx):
+        """Backward schedule of a conv macro-op (deferred: finalize() runs the thunks in reverse topological order):
+        BN backward -> dy; filter gradient (side stream); input gradient GEMM / implicit conv; depthwise backward."""
+        A, Cin, Cout, Cout_log, Ho, Kdim, Kp, Mo = cx.A, cx.Cin, cx.Cout, cx.Cout_log, cx.Ho, cx.Kdim, cx.Kp, cx.Mo
+        N, Np, P, Wo, act, beta, bn, bn_node = cx.N, cx.Np, cx.P, cx.Wo, cx.act, cx.beta, cx.bn, cx.bn_node
+        dil, dw_g, dw_w, g32 = cx.dil, cx.dw_g, cx.dw_w, cx.g32
+        gamma, gemm, implicit, implicit_same = cx.gamma, cx.gemm, cx.implicit, cx.implicit_same
+        in_act, invstd, is_sep, k = cx.in_act, cx.invstd, cx.is_sep, cx.k
+        lay, lda, mean, needs_in_grad = cx.lay, cx.lda, cx.mean, cx.needs_in_grad
+        other, out, out_shape, pad4 = cx.other, cx.out, cx.out_shape, cx.pad4
+        pl, pool_virt, pt, red_direct = cx.pl, cx.pool_virt, cx.pt, cx.red_direct
+        red_slot, scale, shift, stride = cx.red_slot, cx.scale, cx.shift, cx.stride
+        tname, virt, w32, wd = cx.tname, cx.virt, cx.w32, cx.wd
+        wn, x, xb, y, y_dtype = cx.wn, cx.x, cx.xb, cx.y, cx.y_dtype
         # ---- backward (emitted in forward order; the list is reversed at the end, so write steps in REVERSE) --
         def sched():
             g = out.pool_bwd["g"] if pool_virt else self._final_grad(out)

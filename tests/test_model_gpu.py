@@ -430,3 +430,34 @@ def test_other_baseline_configs_full_geometry():
     assert bool(torch.isfinite(probs).all()) and float((probs.sum(-1) - 1).abs().max()) < 1e-5
     lab = plan.segment(x)
     assert lab.shape == (1, 1024, 2048) and 0 <= lab.min() and lab.max() <= 18
+
+
+def test_predictor_graph_replay_matches_plan_and_sees_training():
+    """trainer.Predictor (CUDA-graph inference: forward + fused up-sampling/argmax, pinned staging, input prefetch) gives
+    the label maps of Model.segment; after optimizer steps on the SAME model (shared parameter store) both change, and
+    the prefetch pipeline returns the same maps as plain calls."""
+    from deeplabv3plus_keras_b200.trainer import Predictor
+    conf = util.make_conf(dtype="bfloat16", base="mobilenetv2", output_stride=16, image_size=129, aspp=util.DEFAULT_ASPP)
+    ss = util.build(conf)
+    util.randomize_weights(ss.model)
+    ss.model.optimizer.lr = 1e-2
+    B = 2
+    pr = Predictor(ss.model, B)
+    x, y = util.synthetic_batch(conf, B, pr.plan.out_shape[1:3])
+    x2 = np.ascontiguousarray(np.roll(x, 5, axis=2))
+    xs, xs2 = torch.from_numpy(x).pin_memory(), torch.from_numpy(x2).pin_memory()
+    lab = pr.segment_e2e(xs).clone()
+    assert lab.dtype == torch.uint8 and tuple(lab.shape) == tuple(pr.plan.out_shape[:3])
+    assert np.array_equal(lab.numpy().astype(np.int64), ss.segment(x))
+    # materialised path (bilinear_fwd + softmax + argmax) gives the same labels as the fused tail
+    assert np.array_equal(ss.model.predict(x, batch_size=B).argmax(-1), lab.numpy().astype(np.int64))
+    # prefetch pipeline over two different batches == plain calls
+    a = pr.segment_e2e(xs, prefetch_next=xs2).clone()
+    b = pr.segment_e2e(None).clone()
+    assert torch.equal(a, lab) and torch.equal(b, pr.segment_e2e(xs2))
+    # training on the same model moves what the predictor sees
+    for _ in range(3):
+        ss.model.train_on_batch(x, y)
+    after = pr.segment_e2e(xs)
+    assert not torch.equal(after, lab), "the inference plan still sees the initial weights"
+    assert np.array_equal(after.numpy().astype(np.int64), ss.segment(x))
