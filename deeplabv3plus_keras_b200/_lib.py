@@ -22,6 +22,7 @@ _p, _i, _l, _f, _d, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
 # name -> argtypes, mirrors include/dlv3p.h one to one (tests/test_abi.py checks the header against this table)
 SIGNATURES = {
     "dlv3p_dwconv3x3_fwd": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p],
+    "dlv3p_dwconv3x3_fwd_epi": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p],
     "dlv3p_dwconv3x3_dgrad": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p],
     "dlv3p_dwconv3x3_bn_fwd": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _d, _f, _f, _i, _i, _p, _p,
                                _p, _p, _i, _p],

@@ -21,7 +21,8 @@ int launch_dw_conv_tma(const __nv_bfloat16* in, const float* w, __nv_bfloat16* o
                        const float* m_scale, const float* m_shift, int m_act, const __nv_bfloat16* addend,
                        cudaStream_t st, const float* in_scale = nullptr, const float* in_shift = nullptr,
                        const float* bn_mean = nullptr, const float* bn_invstd = nullptr, float* bn_red = nullptr,
-                       const DwBnFold* fold = nullptr);
+                       const DwBnFold* fold = nullptr, const float* out_scale = nullptr,
+                       const float* out_shift = nullptr, int out_act = 0);
 
 int launch_dw_wgrad_tma(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int N, int H, int W, int C, int Ho,
                         int Wo, int pad_t, int pad_l, int in_act, cudaStream_t st, const float* in_scale = nullptr,
@@ -128,6 +129,12 @@ dw_conv_kernel(const T* __restrict__ in, const float* __restrict__ w, T* __restr
         if (wo >= Wout) break;
         const long long off = obase + (long long)wo * C;
         if (HAS_EPI) {
+            if (mask_src == nullptr && m_shift != nullptr) {
+                // output epilogue (inference DepthwiseConv2D -> BatchNormalization -> ReLU/ReLU6): act(scale*acc + shift)
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    acc[o][k] = apply_act(fmaf(acc[o][k], __ldg(m_scale + c0 + k), __ldg(m_shift + c0 + k)), m_act);
+            }
             if (mask_src != nullptr && m_act != DLV3P_ACT_NONE) {
                 Vec8<T> mv; mv.load(mask_src + off);
                 float mf[8]; mv.to_float(mf);
@@ -468,6 +475,29 @@ extern "C" int dlv3p_dwconv3x3_fwd(const void* x, const float* w, void* y, int N
         return launch_dw_conv<T, false, false>((const T*)x, w, (T*)y, N, H, W, C, Ho, Wo, stride, dil_h, dil_w,
                                                pad_t, pad_l, 0, nullptr, nullptr, in_act, nullptr, nullptr,
                                                nullptr, 0, nullptr, st);
+    });
+    return 0;
+}
+
+extern "C" int dlv3p_dwconv3x3_fwd_epi(const void* x, const float* w, void* y, int N, int H, int W, int C, int stride,
+                                       int dil_h, int dil_w, int pad_t, int pad_l, int Ho, int Wo,
+                                       const float* out_scale, const float* out_shift, int out_act, int dtype,
+                                       void* stream) {
+    int rc = check_dw_args(x, w, y, N, H, W, C, stride, dil_h, dil_w, Ho, Wo);
+    if (rc) return rc;
+    DLV3P_REQUIRE(out_scale != nullptr && out_shift != nullptr, DLV3P_ERR_SHAPE,
+                  "dwconv3x3_fwd_epi: out_scale and out_shift are required (use dwconv3x3_fwd otherwise)");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == DLV3P_BF16 && stride == 1 && dil_h == 1 && dil_w == 1) {
+        rc = launch_dw_conv_tma((const __nv_bfloat16*)x, w, (__nv_bfloat16*)y, N, H, W, C, Ho, Wo, pad_t, pad_l, 0,
+                                DLV3P_ACT_NONE, nullptr, nullptr, nullptr, 0, nullptr, st, nullptr, nullptr, nullptr,
+                                nullptr, nullptr, nullptr, out_scale, out_shift, out_act);
+        if (rc != 0) return rc < 0 ? rc : 0;
+    }
+    DLV3P_DISPATCH_DTYPE(dtype, T, {
+        return launch_dw_conv<T, false, true>((const T*)x, w, (T*)y, N, H, W, C, Ho, Wo, stride, dil_h, dil_w, pad_t,
+                                              pad_l, 0, nullptr, nullptr, DLV3P_ACT_NONE, nullptr, out_scale, out_shift,
+                                              out_act, nullptr, st);
     });
     return 0;
 }

@@ -35,6 +35,8 @@ struct DwTmaParams {
     const float* f_sums; const float* f_gamma; const float* f_beta; float* f_mm; float* f_mv;
     float* f_scale; float* f_shift; float* f_mean; float* f_invstd;
     double f_count, f_inv_count; float f_eps, f_momentum; int f_updates;
+    const float* out_scale; const float* out_shift;           // OUT_EPI: y := act(out_scale*conv + out_shift), out_act
+    int out_act;
     int tiles_h, tiles_w, tiles_c;
     int spatial_tiles, ctas_per_cb;
 };
@@ -105,7 +107,8 @@ struct DwStageCfg {
     static constexpr int kAddOff = kDwStageBytes + (M_ACT != DLV3P_ACT_NONE ? kEpiBytes : 0);
 };
 
-template <int IN_ACT, int M_ACT, bool M_AFFINE, bool HAS_ADD, bool IN_AFFINE, bool STATS, bool IN_BN = false>
+template <int IN_ACT, int M_ACT, bool M_AFFINE, bool HAS_ADD, bool IN_AFFINE, bool STATS, bool IN_BN = false,
+          bool OUT_EPI = false>
 __global__ void __launch_bounds__(kDwThreads, 1)
 dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_mask,
                    const __grid_constant__ CUtensorMap tm_add, const DwTmaParams p) {
@@ -173,6 +176,7 @@ dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
     }
 
     float msc[4] = {1.f, 1.f, 1.f, 1.f}, msh[4] = {0.f, 0.f, 0.f, 0.f};
+    float osc[4] = {1.f, 1.f, 1.f, 1.f}, osh[4] = {0.f, 0.f, 0.f, 0.f};
     float2 isc[2], ish[2];
     float bs1[4] = {0.f, 0.f, 0.f, 0.f}, bs2[4] = {0.f, 0.f, 0.f, 0.f};
     if (ch_ok) {
@@ -217,6 +221,10 @@ dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
         if (M_ACT != DLV3P_ACT_NONE && M_AFFINE) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) { msc[k] = __ldg(p.m_scale + c0 + k); msh[k] = __ldg(p.m_shift + c0 + k); }
+        }
+        if (OUT_EPI) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { osc[k] = __ldg(p.out_scale + c0 + k); osh[k] = __ldg(p.out_shift + c0 + k); }
         }
     }
     const long long row_stride = (long long)p.Wout * p.C;
@@ -300,6 +308,10 @@ dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
                         widen4_t<DLV3P_ACT_NONE>(araw, af);
                         f[0] += af[0].x; f[1] += af[0].y; f[2] += af[1].x; f[3] += af[1].y;
                     }
+                    if (OUT_EPI) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) f[k] = apply_act(fmaf(f[k], osc[k], osh[k]), p.out_act);
+                    }
                     uint2 o;
                     __nv_bfloat162 lo = __floats2bfloat162_rn(f[0], f[1]), hi = __floats2bfloat162_rn(f[2], f[3]);
                     o.x = *reinterpret_cast<uint32_t*>(&lo);
@@ -347,19 +359,20 @@ dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
     }
 }
 
-template <int IN_ACT, int M_ACT, bool M_AFFINE, bool HAS_ADD, bool IN_AFFINE = false, bool STATS = false, bool IN_BN = false>
+template <int IN_ACT, int M_ACT, bool M_AFFINE, bool HAS_ADD, bool IN_AFFINE = false, bool STATS = false, bool IN_BN = false,
+          bool OUT_EPI = false>
 static int launch_dw_tma_inst(const CUtensorMap& tm, const CUtensorMap& tmm, const CUtensorMap& tma,
                               const DwTmaParams& p, int grid, cudaStream_t st) {
     using Cfg = DwStageCfg<M_ACT, HAS_ADD>;
     constexpr int smem = Cfg::kStages * Cfg::kStageBytes + 128 + 64;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(dw_conv_tma_kernel<IN_ACT, M_ACT, M_AFFINE, HAS_ADD, IN_AFFINE, STATS, IN_BN>,
+        cudaError_t e = cudaFuncSetAttribute(dw_conv_tma_kernel<IN_ACT, M_ACT, M_AFFINE, HAS_ADD, IN_AFFINE, STATS, IN_BN, OUT_EPI>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         DLV3P_REQUIRE(e == cudaSuccess, DLV3P_ERR_CUDA, "cudaFuncSetAttribute(dw tma smem=%d): %s", smem, cudaGetErrorString(e));
         configured = true;
     }
-    launch_pdl(dw_conv_tma_kernel<IN_ACT, M_ACT, M_AFFINE, HAS_ADD, IN_AFFINE, STATS, IN_BN>, dim3(grid), dim3(kDwThreads), smem, st, tm, tmm, tma, p);
+    launch_pdl(dw_conv_tma_kernel<IN_ACT, M_ACT, M_AFFINE, HAS_ADD, IN_AFFINE, STATS, IN_BN, OUT_EPI>, dim3(grid), dim3(kDwThreads), smem, st, tm, tmm, tma, p);
     return check_launch("dwconv3x3 (tma)");
 }
 
@@ -368,9 +381,14 @@ int launch_dw_conv_tma(const __nv_bfloat16* in, const float* w, __nv_bfloat16* o
                        int Hout, int Wout, int pad_t, int pad_l, int flip, int in_act, const __nv_bfloat16* mask_src,
                        const float* m_scale, const float* m_shift, int m_act, const __nv_bfloat16* addend,
                        cudaStream_t st, const float* in_scale, const float* in_shift, const float* bn_mean,
-                       const float* bn_invstd, float* bn_red, const DwBnFold* fold) {
+                       const float* bn_invstd, float* bn_red, const DwBnFold* fold, const float* out_scale,
+                       const float* out_shift, int out_act) {
     if (get_encode_fn() == nullptr) return 0;
     if (mask_src == nullptr) m_act = DLV3P_ACT_NONE;
+    const bool out_epi = (out_scale != nullptr);
+    if (out_epi && (in_act != DLV3P_ACT_NONE || m_act != DLV3P_ACT_NONE || addend != nullptr || in_scale != nullptr ||
+                    fold != nullptr || bn_red != nullptr || (C & 3)))
+        return 0;                       // the output epilogue exists for the plain forward only
     if (in_act != DLV3P_ACT_NONE && (m_act != DLV3P_ACT_NONE || addend != nullptr)) return 0;   // not a used combination
     const bool in_aff = (in_scale != nullptr) || (fold != nullptr);
     if (in_aff && (in_act == DLV3P_ACT_NONE || (C & 3))) return 0;          // NaN padding needs a clamping activation
@@ -394,6 +412,7 @@ int launch_dw_conv_tma(const __nv_bfloat16* in, const float* w, __nv_bfloat16* o
     p.m_shift = m_shift; p.m_act = m_act; p.addend = addend;
     p.in_scale = in_scale; p.in_shift = in_shift; p.bn_mean = bn_mean; p.bn_invstd = bn_invstd; p.bn_red = bn_red;
     p.f_sums = nullptr;
+    p.out_scale = out_scale; p.out_shift = out_shift; p.out_act = out_act;
     if (fold != nullptr) {
         p.f_sums = fold->sums; p.f_gamma = fold->gamma; p.f_beta = fold->beta; p.f_mm = fold->moving_mean;
         p.f_mv = fold->moving_var; p.f_scale = fold->scale; p.f_shift = fold->shift; p.f_mean = fold->mean;
@@ -411,7 +430,9 @@ int launch_dw_conv_tma(const __nv_bfloat16* in, const float* w, __nv_bfloat16* o
     const bool aff = (m_scale != nullptr);
     const bool add = (addend != nullptr);
 #define DLV3P_DW(IA, MA, AF, AD) rc = launch_dw_tma_inst<IA, MA, AF, AD>(tm, tmm, tma, p, grid, st)
-    if (in_aff && fold != nullptr) {
+    if (out_epi) {
+        rc = launch_dw_tma_inst<0, 0, false, false, false, false, false, true>(tm, tmm, tma, p, grid, st);
+    } else if (in_aff && fold != nullptr) {
         if (in_act == DLV3P_ACT_RELU) rc = launch_dw_tma_inst<1, 0, false, false, true, false, true>(tm, tmm, tma, p, grid, st);
         else rc = launch_dw_tma_inst<2, 0, false, false, true, false, true>(tm, tmm, tma, p, grid, st);
     } else if (in_aff) {

@@ -770,7 +770,14 @@ class Plan:
                 # inference depthwise+BN: conv into `out`, then fold BN in place
                 dw_out = out.buf
             fold = getattr(x, "bn_fold", None)
-            if fold is not None:
+            # inference DepthwiseConv2D -> BN (-> ReLU/ReLU6) (MobileNetV2): the folded BN runs in the convolution's epilogue
+            dw_epi = (is_dw and bn_node is not None and not training and other is None and in_act == ACT_NONE
+                      and in_sc is None and fold is None)
+            cx.dw_epi = dw_epi
+            if dw_epi:
+                self.fwd.append(lambda: ops.dwconv3x3_fwd_epi(xb, dw_w, scale, shift, act, stride, dil, out=out.buf,
+                                                              pad=pad4))
+            elif fold is not None:
                 self.fwd.append(lambda: ops.dwconv3x3_bn_fwd(
                     xb, dw_w, fold["sums"](), fold["gamma"], fold["beta"], fold["mm"], fold["mv"], fold["count"],
                     fold["eps"], fold["momentum"], fold["updates"], in_act, in_sc, in_sh, x.bn_mean, x.bn_invstd,
@@ -857,7 +864,7 @@ class Plan:
                     launches_f += 1
                 self.fwd.append(lambda: ops.affine_act(y, Mo, Cout, out.buf, scale, shift, act, addend=addend_f))
                 launches_f += 1
-        elif bn_node is not None and is_dw:
+        elif bn_node is not None and is_dw and not cx.dw_epi:
             self.fwd.append(lambda: ops.affine_act(out.buf, Mo, Cout, out.buf, scale, shift, act, addend=addend_f))
             launches_f += 1
         self.launches_fwd += launches_f

@@ -80,6 +80,19 @@ def dwconv3x3_fwd(x: Tensor, w: Tensor, stride=1, dil=(1, 1), padding="same", in
     return out
 
 
+def dwconv3x3_fwd_epi(x: Tensor, w: Tensor, out_scale: Tensor, out_shift: Tensor, out_act: int, stride=1, dil=(1, 1),
+                      padding="same", out: Optional[Tensor] = None, pad: Optional[Tuple[int, int, int, int]] = None):
+    """Inference DepthwiseConv2D -> BatchNormalization -> ReLU/ReLU6: act(out_scale * conv(x) + out_shift) in one launch."""
+    _chk(x, "x")
+    N, H, W, Cc = x.shape
+    ho, wo, pt, pl = pad if pad is not None else conv_geometry(H, W, 3, stride, dil, padding)
+    if out is None:
+        out = torch.empty((N, ho, wo, Cc), dtype=x.dtype, device=x.device)
+    call("dlv3p_dwconv3x3_fwd_epi", _p(x), _p(w), _p(out), N, H, W, Cc, stride, dil[0], dil[1], pt, pl, ho, wo,
+         _p(out_scale), _p(out_shift), out_act, _dt(x), _stream())
+    return out
+
+
 def dwconv3x3_dgrad(dy: Tensor, w: Tensor, x_shape, stride=1, dil=(1, 1), padding="same", x_pre=None, in_scale=None,
                     in_shift=None, in_act=ACT_NONE, addend=None, out: Optional[Tensor] = None, pad=None):
     _chk(dy, "dy")

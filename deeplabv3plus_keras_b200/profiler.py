@@ -27,6 +27,8 @@ def _opt(p) -> int:
 COSTS: Dict[str, Tuple[str, Callable]] = {
     "dlv3p_dwconv3x3_fwd": ("hbm", lambda a: ((a[3] * a[4] * a[5] * a[6] + a[3] * a[12] * a[13] * a[6]) * _esz(a[17]) + 36 * a[6],
                                              18 * a[3] * a[12] * a[13] * a[6])),
+    "dlv3p_dwconv3x3_fwd_epi": ("hbm", lambda a: ((a[3] * a[4] * a[5] * a[6] + a[3] * a[12] * a[13] * a[6]) * _esz(a[17]) + 44 * a[6],
+                                                 20 * a[3] * a[12] * a[13] * a[6])),
     "dlv3p_dwconv3x3_dgrad": ("hbm", lambda a: ((a[3] * a[4] * a[5] * a[6] * (1 + _opt(a[14]) + _opt(a[18])) + a[3] * a[12] * a[13] * a[6]) * _esz(a[19]) + 36 * a[6],
                                                18 * a[3] * a[4] * a[5] * a[6])),
     "dlv3p_dwconv3x3_bn_fwd": ("hbm", lambda a: ((a[3] * a[4] * a[5] * a[6] + a[3] * a[9] * a[10] * a[6]) * _esz(a[25]) + 36 * a[6],

@@ -65,6 +65,13 @@ int dlv3p_dwconv3x3_fwd(const void* x, const float* w, void* y, int N, int H, in
                         const float* in_shift, int in_act, int dtype, void* stream);
 /* dx = mask * conv_transpose(dy) (+ addend), mask = act'(in_scale*x_pre+in_shift) when in_act != NONE.
  * The result is the gradient w.r.t. the activation INPUT z = in_scale*x_pre+in_shift (not w.r.t. x_pre). */
+/* Inference form of DepthwiseConv2D -> BatchNormalization -> ReLU/ReLU6 (every MobileNetV2 block, keras.applications
+ * mobilenet_v2 `*_depthwise`, `*_depthwise_BN`, `*_depthwise_relu`): y = act(out_scale[c] * conv(x)[c] + out_shift[c]) with
+ * the folded BN applied in the convolution's epilogue (TF runs DepthwiseConv2dNative, FusedBatchNormV3 and Relu6 as three
+ * kernels over the tensor).  No input prologue; other arguments as dlv3p_dwconv3x3_fwd. */
+int dlv3p_dwconv3x3_fwd_epi(const void* x, const float* w, void* y, int N, int H, int W, int C, int stride, int dil_h,
+                            int dil_w, int pad_t, int pad_l, int Ho, int Wo, const float* out_scale,
+                            const float* out_shift, int out_act, int dtype, void* stream);
 int dlv3p_dwconv3x3_dgrad(const void* dy, const float* w, void* dx, int N, int H, int W, int C, int stride,
                           int dil_h, int dil_w, int pad_t, int pad_l, int Ho, int Wo, const void* x_pre,
                           const float* in_scale, const float* in_shift, int in_act, const void* addend, int dtype,

@@ -69,6 +69,16 @@ def dwconv3x3_fwd(x, w, stride=1, dil=(1, 1), padding="same", in_scale=None, in_
     return out
 
 
+def dwconv3x3_fwd_epi(x, w, out_scale, out_shift, out_act, stride=1, dil=(1, 1), padding="same", out=None, pad=None):
+    N, H, W, C = x.shape
+    Ho, Wo, pt, pl = pad if pad is not None else conv_geometry(H, W, 3, stride, dil, padding)
+    y = _act(_dw(x.float(), w, stride, dil, Ho, Wo, pt, pl) * out_scale + out_shift, out_act)
+    if out is None:
+        return y.to(x.dtype).contiguous()
+    out.copy_(y)
+    return out
+
+
 def dwconv3x3_dgrad(dy, w, x_shape, stride=1, dil=(1, 1), padding="same", x_pre=None, in_scale=None, in_shift=None,
                     in_act=ACT_NONE, addend=None, out=None, pad=None):
     N, H, W, C = x_shape

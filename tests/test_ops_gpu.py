@@ -114,6 +114,37 @@ def test_dwconv3x3_fwd_dgrad_wgrad(case, dtype, prologue):
     check("dw wgrad", dw, wr.grad, 2e-3, 2e-3 * math.sqrt(N * ho * wo))
 
 
+@pytest.mark.parametrize("case", [c for c in DW_CASES if c[5] == (1, 1)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_dwconv3x3_fwd_output_epilogue(case, dtype):
+    """Inference DepthwiseConv2D -> BatchNormalization -> ReLU6 in one launch (dlv3p_dwconv3x3_fwd_epi: folded BN + clamp
+    in the convolution's epilogue; TMA kernel for the dense stride-1 bf16 case, direct kernel for stride 2 / fp32) against
+    the fp64 restatement and against the two-launch form (dwconv3x3_fwd + affine_act)."""
+    o = ops()
+    N, H, W, C, stride, dil, padding = case
+    x = rnd((N, H, W, C), dtype, 1)
+    w = rnd((3, 3, C), torch.float32, 2, 0.3)
+    sc = rnd((C,), torch.float32, 3, 0.3) + 1.0
+    sh = rnd((C,), torch.float32, 4, 0.5) + 1.0
+    pad = dw_pad(H, W, stride, dil, padding)
+    for act, code in (("relu6", o.ACT_RELU6), ("relu", o.ACT_RELU), ("none", o.ACT_NONE)):
+        got = o.dwconv3x3_fwd_epi(x.to(DEV), w.to(DEV), sc.to(DEV), sh.to(DEV), code, stride, dil, pad=pad)
+        xx = x.double()
+        if padding == "mnv2":
+            xx = O.zero_pad2d(xx, ((1 - (1 - H % 2), 1), (1 - (1 - W % 2), 1)))
+            conv = O.depthwise_conv2d(xx, w.double().view(3, 3, C, 1), stride, "valid", dil)
+        else:
+            conv = O.depthwise_conv2d(xx, w.double().view(3, 3, C, 1), stride, padding, dil)
+        z = conv * sc.double() + sh.double()
+        ref = torch.clamp(z, 0, 6) if act == "relu6" else (torch.clamp_min(z, 0) if act == "relu" else z)
+        rt, at = tol(dtype)
+        check(f"dw fwd epi {act}", got, ref, rt, at * 4)
+        two = o.dwconv3x3_fwd(x.to(DEV), w.to(DEV), stride, dil, pad=pad)
+        M = two.numel() // C
+        o.affine_act(two, M, C, two, sc.to(DEV), sh.to(DEV), code)
+        check(f"dw fwd epi vs two launches {act}", got, two, 2e-2 if dtype == torch.bfloat16 else 1e-5, at * 4)
+
+
 @pytest.mark.parametrize("case", [(2, 17, 19, 64), (2, 30, 31, 728), (1, 32, 32, 736), (3, 40, 70, 128)])
 @pytest.mark.parametrize("act", ["relu", "relu6"])
 def test_dwconv3x3_dgrad_bnred(case, act):
