@@ -51,7 +51,10 @@ __host__ __device__ constexpr int stat_capacity(int region_floats, int slots) { 
 static_assert(kEpiBytes >= 4 * kEpiStageFloats * 4, "staging area must hold the fallback transposes");
 template <int BLOCK_N> struct GemmCfg {
     static constexpr int kStageBytes = kBlockM * kBlockK * 2 + BLOCK_N * kBlockK * 2;
-    static constexpr int kStages = BLOCK_N == 256 ? 3 : 4;          // 3 x 48 KB / 4 x <=32 KB operand ring
+    // operand ring: 3 x 48 KB (N tile 256), 4 x 32 KB (128), 6 x 24 KB (64), 7 x 20 KB (32).  The narrow tiles are the
+    // K-deep, latency-bound ones (the 21-class logits convolution: 45 k-blocks of 20 KB per 128-pixel tile, tensor pipe
+    // 8 % active, nothing saturated in the ncu capture profiles/r2_new_kernels_ncu.md): more k-blocks in flight
+    static constexpr int kStages = BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 4 : (BLOCK_N == 64 ? 6 : 7));
     static constexpr int kSmem = kStages * kStageBytes + kEpiBytes + 2 * kMaxStatCols * 4 + 1024 /*align*/ + 256 /*barriers*/;
     static_assert(kSmem <= 232448, "shared memory budget");
 };
