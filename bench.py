@@ -309,7 +309,8 @@ def graph_kernel_profile(eager_fn, replay_fn, logical, steps=3):
         name = e.name()
         dev = str(e.device_type())
         if "CUDA" in dev:
-            if not name.startswith(("Memset", "Memcpy", "dlv3p#")):        # (ranges are mirrored on the GPU timeline)
+            if not name.lower().startswith(("memset", "memcpy", "dlv3p#")):   # (ranges are mirrored on the GPU timeline;
+                # memset / memcpy nodes of a graph replay show up as kernels named memset32 / memcpy...)
                 kernels.append(e)
         elif name.startswith("dlv3p#"):
             ranges.append((e.start_ns(), e.start_ns() + e.duration_ns(), int(name[6:])))
@@ -333,7 +334,7 @@ def graph_kernel_profile(eager_fn, replay_fn, logical, steps=3):
             replay_fn()
         torch.cuda.synchronize()
     gk = [e for e in prof2.profiler.kineto_results.events()
-          if "CUDA" in str(e.device_type()) and not e.name().startswith(("Memset", "Memcpy", "dlv3p#"))]
+          if "CUDA" in str(e.device_type()) and not e.name().lower().startswith(("memset", "memcpy", "dlv3p#"))]
     gk.sort(key=lambda e: e.start_ns())
     n = len(seq)
     info = {"kernels_per_step": n, "graph_kernels": len(gk), "aligned": False}
