@@ -29,6 +29,10 @@ int launch_dw_wgrad_tma(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* 
                         const float* in_shift = nullptr);
 
 // dwconv_tma.cu: whole-image smem staging for atrous taps on small feature maps; returns 1 if it took the launch
+int launch_dw_bwd_tma(const __nv_bfloat16* dy, const __nv_bfloat16* x_src, const float* w, __nv_bfloat16* dx, float* dwg,
+                      int N, int H, int W, int C, int x_act, const float* x_scale, const float* x_shift,
+                      const __nv_bfloat16* addend, const float* bn_mean, const float* bn_invstd, float* bn_red,
+                      cudaStream_t st);
 int launch_dw_image(int mode, const __nv_bfloat16* in, const float* w, __nv_bfloat16* out, const __nv_bfloat16* dy,
                     float* dwg, int N, int H, int W, int C, int dil_h, int dil_w, int flip, int in_act,
                     const __nv_bfloat16* addend, cudaStream_t st);
@@ -632,4 +636,36 @@ extern "C" int dlv3p_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, i
         return check_launch("dwconv3x3_wgrad");
     });
     return 0;
+}
+
+extern "C" int dlv3p_dwconv3x3_bwd(const void* dy, const void* x, const float* w, void* dx, float* dw, int N, int H,
+                                   int W, int C, const float* in_scale, const float* in_shift, int in_act,
+                                   const void* addend, const float* bn_mean, const float* bn_invstd, float* bn_red,
+                                   int dtype, void* stream) {
+    int rc = check_dw_args(dy, w, dx, N, H, W, C, 1, 1, 1, H, W);
+    if (rc) return rc;
+    DLV3P_REQUIRE(x != nullptr && dw != nullptr, DLV3P_ERR_SHAPE, "dwconv3x3_bwd: x and dw are required");
+    DLV3P_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), DLV3P_ERR_SHAPE,
+                  "dwconv3x3_bwd: in_scale and in_shift must both be given or both be NULL");
+    DLV3P_REQUIRE(in_scale == nullptr || in_act != DLV3P_ACT_NONE, DLV3P_ERR_SHAPE,
+                  "dwconv3x3_bwd: an affine input map needs an activation");
+    DLV3P_REQUIRE(bn_red == nullptr || (in_scale && bn_mean && bn_invstd && addend == nullptr), DLV3P_ERR_SHAPE,
+                  "dwconv3x3_bwd: the BN reductions need in_scale/in_shift, bn_mean, bn_invstd and no addend");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == DLV3P_BF16) {
+        rc = launch_dw_bwd_tma((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, w, (__nv_bfloat16*)dx, dw, N, H, W, C,
+                               in_act, in_scale, in_shift, (const __nv_bfloat16*)addend, bn_mean, bn_invstd, bn_red, st);
+        if (rc != 0) return rc < 0 ? rc : 0;
+    }
+    // fp32 (parity mode) or no TMA: the same result from the separate entry points
+    if (bn_red != nullptr) {
+        DLV3P_REQUIRE(dtype == DLV3P_BF16, DLV3P_ERR_DTYPE, "dwconv3x3_bwd: BN reductions are bf16 only");
+        rc = dlv3p_dwconv3x3_dgrad_bnred(dy, w, dx, N, H, W, C, 1, 1, H, W, x, in_scale, in_shift, in_act, bn_mean,
+                                         bn_invstd, bn_red, dtype, stream);
+    } else {
+        rc = dlv3p_dwconv3x3_dgrad(dy, w, dx, N, H, W, C, 1, 1, 1, 1, 1, H, W, in_act != DLV3P_ACT_NONE ? x : nullptr,
+                                   in_scale, in_shift, in_act, addend, dtype, stream);
+    }
+    if (rc) return rc;
+    return dlv3p_dwconv3x3_wgrad(x, dy, dw, N, H, W, C, 1, 1, 1, 1, 1, H, W, in_scale, in_shift, in_act, dtype, stream);
 }

@@ -647,6 +647,368 @@ int launch_dw_wgrad_tma(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* 
 
 
 // =====================================================================================================================
+// Fused depthwise backward (stride 1, dilation 1, SAME, bf16): input gradient + filter gradient (+ the BN-backward
+// reductions of the producing layer) in ONE pass over dy.
+//
+// dlv3p_dwconv3x3_dgrad and dlv3p_dwconv3x3_wgrad both stream the gradient dy of the depthwise output and the tensor the
+// convolution read (as the activation mask in one, as the convolved operand in the other).  Written around the INPUT
+// pixel (h, w) both need the same 3x3 window of dy:
+//     dx[h,w]    = mask(x) * sum_{i,j} w[i][j] * dy[h+1-i, w+1-j]        (conv-transpose = flipped taps)
+//     dwg[i][j] += x_act[h,w] * dy[h+1-i, w+1-j]                          (filter gradient, re-indexed from output to
+//                                                                          input pixels; dy outside the image is zero)
+// so one kernel slides the dy window (TMA halo box, zero fill) once, reads x from a halo-free box of the same stage,
+// and keeps the 9 x 4 filter-gradient partial sums in registers next to the 9 x 4 taps.  That is 36 registers more than
+// the input-gradient kernel: at 4 channels x 1 column per thread the kernel needs ~150 registers, so a CTA is
+// 12 channel quads x 32 columns = 384 threads on 48-channel blocks (<= 168 registers, 12 resident warps) instead of
+// 16 x 32 = 512 threads on 64-channel blocks.  Per middle-flow layer ([16,32,32,728]) this replaces a 17.5 us and a
+// 15.3 us launch, each mostly launch ramp and tail on a 24 MB L2-resident tensor.
+// =====================================================================================================================
+template <int CQ, int TW, bool HAS_ADD>
+struct DwBwdCfg {
+    static constexpr int kCB = CQ * 4;                                        // channels per block
+    static constexpr int kThreads = CQ * TW;
+    static constexpr int kHaloBytes = (kDwTH + 2) * (TW + 2) * kCB * 2;
+    static constexpr int kCtrBytes = kDwTH * TW * kCB * 2;
+    static constexpr int kStageBytes = kHaloBytes + (HAS_ADD ? 2 : 1) * kCtrBytes;
+    static constexpr int kBudget = 226 * 1024;
+    static constexpr int kStages = kBudget / kStageBytes >= 4 ? 4 : (kBudget / kStageBytes >= 3 ? 3 : 2);
+    static constexpr int kXOff = kHaloBytes;
+    static constexpr int kAddOff = kHaloBytes + kCtrBytes;
+    static constexpr int kRedWg = 9 * TW * kCB * 4;                        // filter-gradient reduction buffer
+    static constexpr int kRedBn = 2 * TW * kCB * 4;
+    static constexpr int kSmem = kStages * kStageBytes + 128 + 64;
+    static_assert(kRedWg + kRedBn <= kStages * kStageBytes, "reduction buffers reuse the stage ring");
+    static_assert(kHaloBytes % 128 == 0 && kCtrBytes % 128 == 0, "TMA destinations stay 128-byte aligned");
+};
+
+struct DwBwdParams {
+    int N, H, W, C;
+    const float* w;                         // [3,3,C] fp32
+    float* dwg;                             // [3,3,C] fp32, accumulated
+    __nv_bfloat16* dx;
+    const float* x_scale; const float* x_shift;                    // X_AFFINE: x := act(x_scale*x_src + x_shift)
+    const float* bn_mean; const float* bn_invstd; float* bn_red;   // STATS
+    int tiles_h, tiles_w, spatial_tiles, ctas_per_cb;
+};
+
+// X_ACT: activation between x_src and the convolution (its derivative masks dx), X_AFFINE: per-channel affine map in
+// front of it (the producing layer's training-mode BatchNormalization), HAS_ADD: gradient addend, STATS: BN reductions.
+template <int X_ACT, bool X_AFFINE, bool HAS_ADD, bool STATS, int CQ, int TW>
+__global__ void __launch_bounds__(CQ * TW, 1)
+dw_bwd_tma_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_x,
+                  const __grid_constant__ CUtensorMap tm_add, const DwBwdParams p) {
+    using Cfg = DwBwdCfg<CQ, TW, HAS_ADD>;
+    constexpr int kCB = Cfg::kCB, kStages = Cfg::kStages, kStageBytes = Cfg::kStageBytes;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    const uint32_t bar0 = smem_u32(bars);
+    const uint32_t stage0 = smem_u32(smem);
+
+    const int tid = threadIdx.x;
+    const int cq = tid % CQ;                // channel quad inside the block
+    const int col = tid / CQ;               // column inside the tile, 0..TW-1
+    const int cb = blockIdx.x / p.ctas_per_cb;
+    const int gstride = p.ctas_per_cb;
+    const int c0 = cb * kCB + cq * 4;
+    pdl_launch_dependents();
+
+    if (tid == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_dy)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_x)) : "memory");
+        if (HAS_ADD) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_add)) : "memory");
+        for (int s = 0; s < kStages; ++s) mbar_init(bar0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // taps in window order: window position a = (i', j') meets tap 8 - a.  Master weights / BN vectors only change in
+    // kernels that do not trigger dependent launches, so these loads run ahead of the dependency wait
+    float2 wgt[9][2];
+    const bool ch_ok = c0 < p.C;
+    float msc[4] = {1.f, 1.f, 1.f, 1.f}, msh[4] = {0.f, 0.f, 0.f, 0.f}, mu[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ch_ok) {
+#pragma unroll
+        for (int a = 0; a < 9; ++a) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p.w + (8 - a) * p.C + c0));
+            wgt[a][0] = make_float2(v.x, v.y); wgt[a][1] = make_float2(v.z, v.w);
+        }
+    }
+    pdl_wait();
+    if (ch_ok) {
+        if (X_AFFINE) {
+            const float4 a = __ldcg(reinterpret_cast<const float4*>(p.x_scale + c0));
+            const float4 b = __ldcg(reinterpret_cast<const float4*>(p.x_shift + c0));
+            msc[0] = a.x; msc[1] = a.y; msc[2] = a.z; msc[3] = a.w;
+            msh[0] = b.x; msh[1] = b.y; msh[2] = b.z; msh[3] = b.w;
+        }
+        if (STATS) {
+            const float4 m = __ldcg(reinterpret_cast<const float4*>(p.bn_mean + c0));
+            mu[0] = m.x; mu[1] = m.y; mu[2] = m.z; mu[3] = m.w;
+        }
+    }
+
+    auto decode = [&](int tile, int& n, int& th, int& tw) {
+        tw = tile % p.tiles_w; const int t = tile / p.tiles_w;
+        th = t % p.tiles_h; n = t / p.tiles_h;
+    };
+    auto issue = [&](int tile, int s) {
+        int n, th, tw;
+        decode(tile, n, th, tw);
+        mbar_expect_tx(bar0 + 8 * s, kStageBytes);
+        const uint32_t dst = stage0 + s * kStageBytes;
+        tma_load_4d(dst, &tm_dy, bar0 + 8 * s, cb * kCB, tw * TW - 1, th * kDwTH - 1, n);
+        tma_load_4d(dst + Cfg::kXOff, &tm_x, bar0 + 8 * s, cb * kCB, tw * TW, th * kDwTH, n);
+        if (HAS_ADD) tma_load_4d(dst + Cfg::kAddOff, &tm_add, bar0 + 8 * s, cb * kCB, tw * TW, th * kDwTH, n);
+    };
+
+    int tile = blockIdx.x % p.ctas_per_cb;
+    if (tid == 0) {
+        for (int a = 0; a < kStages - 1; ++a)
+            if (tile + a * gstride < p.spatial_tiles) issue(tile + a * gstride, a);
+    }
+
+    float2 acc9[9][2];
+#pragma unroll
+    for (int a = 0; a < 9; ++a) { acc9[a][0] = make_float2(0.f, 0.f); acc9[a][1] = make_float2(0.f, 0.f); }
+    float bs1[4] = {0.f, 0.f, 0.f, 0.f}, bs2[4] = {0.f, 0.f, 0.f, 0.f};
+    const long long row_stride = (long long)p.W * p.C;
+
+    uint32_t it = 0;
+    for (; tile < p.spatial_tiles; tile += gstride, ++it) {
+        const int s = it % kStages;
+        const int ahead = tile + (kStages - 1) * gstride;
+        if (ahead < p.spatial_tiles && tid == 0) issue(ahead, (it + kStages - 1) % kStages);
+
+        int n, th, tw;
+        decode(tile, n, th, tw);
+        const int wo = tw * TW + col;
+        const bool lane_ok = ch_ok && (wo < p.W);
+
+        mbar_wait(bar0 + 8 * s, (it / kStages) & 1u);
+
+        if (lane_ok) {
+            // stage layout: dy [TH+2][TW+2][CB], then x_src [TH][TW][CB] (, addend [TH][TW][CB])
+            const uint32_t base = stage0 + s * kStageBytes + (col * kCB + cq * 4) * 2;
+            auto load_row = [&](int row, float2 (&dst)[3][2]) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    uint2 raw;
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];"
+                                 : "=r"(raw.x), "=r"(raw.y)
+                                 : "r"(base + (uint32_t)((row * (TW + 2) + j) * (kCB * 2))));
+                    widen4_t<DLV3P_ACT_NONE>(raw, dst[j]);
+                }
+            };
+            auto lds_ctr = [&](int byte_off, int r) {
+                uint2 raw;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];"
+                             : "=r"(raw.x), "=r"(raw.y)
+                             : "r"(base + (uint32_t)(byte_off + r * TW * kCB * 2)));
+                return raw;
+            };
+            long long off = (((long long)n * p.H + th * kDwTH) * p.W + wo) * p.C + c0;
+            const int rows_valid = p.H - th * kDwTH;
+            auto emit = [&](int r, const float2 (&ra)[3][2], const float2 (&rb)[3][2], const float2 (&rc)[3][2]) {
+                if (r < rows_valid) {                    // uniform across the CTA
+                    // one accumulation chain per channel pair: this kernel is bound by the FP32 pipe (a packed FMA with three
+                    // distinct register pairs occupies it for 3 cycles, scripts/ubench/fma_rate.cu), so the two extra
+                    // packed adds of a three-chain sum cost more than the chain latency the 18 independent filter-gradient
+                    // FMAs below hide anyway
+                    float2 acc[2];
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        float2 a0 = __fmul2_rn(ra[0][k], wgt[0][k]);
+                        a0 = __ffma2_rn(ra[1][k], wgt[1][k], a0);
+                        a0 = __ffma2_rn(ra[2][k], wgt[2][k], a0);
+                        a0 = __ffma2_rn(rb[0][k], wgt[3][k], a0);
+                        a0 = __ffma2_rn(rb[1][k], wgt[4][k], a0);
+                        a0 = __ffma2_rn(rb[2][k], wgt[5][k], a0);
+                        a0 = __ffma2_rn(rc[0][k], wgt[6][k], a0);
+                        a0 = __ffma2_rn(rc[1][k], wgt[7][k], a0);
+                        acc[k] = __ffma2_rn(rc[2][k], wgt[8][k], a0);
+                    }
+                    float f[4] = {acc[0].x, acc[0].y, acc[1].x, acc[1].y};
+                    const uint2 xraw = lds_ctr(Cfg::kXOff, r);
+                    float2 xf[2];
+                    widen4_t<DLV3P_ACT_NONE>(xraw, xf);
+                    const float u[4] = {xf[0].x, xf[0].y, xf[1].x, xf[1].y};
+                    float xv[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float v = X_AFFINE ? fmaf(u[k], msc[k], msh[k]) : u[k];
+                        if (X_ACT == DLV3P_ACT_RELU) {
+                            f[k] = v > 0.f ? f[k] : 0.f;
+                            xv[k] = fmaxf(v, 0.f);
+                        } else if (X_ACT == DLV3P_ACT_RELU6) {
+                            f[k] = (v > 0.f && v < 6.f) ? f[k] : 0.f;
+                            xv[k] = fminf(fmaxf(v, 0.f), 6.f);
+                        } else {
+                            xv[k] = v;
+                        }
+                        // centred second sum: sum g*(y - mean) (the form dlv3p_bn_bwd_reduce uses; sum g*y - mean*sum g
+                        // cancels to 1/(|mean|/std) of its terms)
+                        if (STATS) { bs1[k] += f[k]; bs2[k] = fmaf(f[k], u[k] - mu[k], bs2[k]); }
+                    }
+                    const float2 x2[2] = {make_float2(xv[0], xv[1]), make_float2(xv[2], xv[3])};
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            acc9[0 * 3 + j][k] = __ffma2_rn(ra[j][k], x2[k], acc9[0 * 3 + j][k]);
+                            acc9[1 * 3 + j][k] = __ffma2_rn(rb[j][k], x2[k], acc9[1 * 3 + j][k]);
+                            acc9[2 * 3 + j][k] = __ffma2_rn(rc[j][k], x2[k], acc9[2 * 3 + j][k]);
+                        }
+                    }
+                    if (HAS_ADD) {
+                        const uint2 araw = lds_ctr(Cfg::kAddOff, r);
+                        float2 af[2];
+                        widen4_t<DLV3P_ACT_NONE>(araw, af);
+                        f[0] += af[0].x; f[1] += af[0].y; f[2] += af[1].x; f[3] += af[1].y;
+                    }
+                    uint2 o;
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(f[0], f[1]), hi = __floats2bfloat162_rn(f[2], f[3]);
+                    o.x = *reinterpret_cast<uint32_t*>(&lo);
+                    o.y = *reinterpret_cast<uint32_t*>(&hi);
+                    *reinterpret_cast<uint2*>(p.dx + off) = o;
+                }
+                off += row_stride;
+            };
+            float2 r0[3][2], r1[3][2], r2[3][2];
+            load_row(0, r0);
+            load_row(1, r1);
+            static_assert(kDwTH == 8, "row loop below is unrolled for TH = 8");
+            load_row(2, r2); emit(0, r0, r1, r2);
+            load_row(3, r0); emit(1, r1, r2, r0);
+            load_row(4, r1); emit(2, r2, r0, r1);
+            load_row(5, r2); emit(3, r0, r1, r2);
+            load_row(6, r0); emit(4, r1, r2, r0);
+            load_row(7, r1); emit(5, r2, r0, r1);
+            load_row(8, r2); emit(6, r0, r1, r2);
+            load_row(9, r0); emit(7, r1, r2, r0);
+        }
+        __syncthreads();
+    }
+    // every TMA box this CTA issued has been consumed: the ring becomes [9][TW cols][CB] (+ [2][TW][CB]) fp32
+    float* red = reinterpret_cast<float*>(smem);
+    float* redbn = reinterpret_cast<float*>(smem + Cfg::kRedWg);
+#pragma unroll
+    for (int a = 0; a < 9; ++a)
+        *reinterpret_cast<float4*>(red + (a * TW + col) * kCB + cq * 4) =
+            make_float4(acc9[a][0].x, acc9[a][0].y, acc9[a][1].x, acc9[a][1].y);
+    if (STATS) {
+        *reinterpret_cast<float4*>(redbn + col * kCB + cq * 4) = make_float4(bs1[0], bs1[1], bs1[2], bs1[3]);
+        *reinterpret_cast<float4*>(redbn + (TW + col) * kCB + cq * 4) = make_float4(bs2[0], bs2[1], bs2[2], bs2[3]);
+    }
+    __syncthreads();
+    for (int o = tid; o < 9 * kCB; o += Cfg::kThreads) {
+        const int a = o / kCB, c = o % kCB;
+        const int ch = cb * kCB + c;
+        if (ch < p.C) {
+            float sum = 0.f;
+#pragma unroll 8
+            for (int q = 0; q < TW; ++q) sum += red[(a * TW + q) * kCB + c];
+            atomicAdd(p.dwg + (8 - a) * p.C + ch, sum);
+        }
+    }
+    if (STATS) {
+        // red[0..C) += sum g, red[C..2C) += sum g*xhat, g = the masked gradient written above (dlv3p_bn_bwd_reduce)
+        for (int o = tid; o < 2 * kCB; o += Cfg::kThreads) {
+            const int q2 = o / kCB, c = o % kCB;
+            const int ch = cb * kCB + c;
+            if (ch < p.C) {
+                float sum = 0.f;
+#pragma unroll 8
+                for (int q = 0; q < TW; ++q) sum += redbn[(q2 * TW + q) * kCB + c];
+                if (q2 == 1) sum *= __ldg(p.bn_invstd + ch);
+                atomicAdd(p.bn_red + q2 * p.C + ch, sum);
+            }
+        }
+    }
+}
+
+template <int X_ACT, bool X_AFFINE, bool HAS_ADD, bool STATS, int CQ, int TW>
+static int launch_dw_bwd_inst(const CUtensorMap& tmd, const CUtensorMap& tmx, const CUtensorMap& tma,
+                              const DwBwdParams& p, int grid, cudaStream_t st) {
+    using Cfg = DwBwdCfg<CQ, TW, HAS_ADD>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(dw_bwd_tma_kernel<X_ACT, X_AFFINE, HAS_ADD, STATS, CQ, TW>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+        DLV3P_REQUIRE(e == cudaSuccess, DLV3P_ERR_CUDA, "cudaFuncSetAttribute(dw bwd smem=%d): %s", Cfg::kSmem, cudaGetErrorString(e));
+        configured = true;
+    }
+    launch_pdl(dw_bwd_tma_kernel<X_ACT, X_AFFINE, HAS_ADD, STATS, CQ, TW>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmem, st,
+               tmd, tmx, tma, p);
+    return check_launch("dwconv3x3_bwd (tma)");
+}
+
+// Two CTA geometries, both 384 threads: 12 channel quads x 32 columns (48-channel blocks) and 16 x 24 (64-channel blocks).
+// The launcher takes the one that wastes fewer lanes on the ragged channel / width tails: 728 channels on 32-wide maps
+// fill 48 x 32 tiles to 95 %, 64 / 128 channels on 254-wide maps fill 64 x 24 tiles to 96 % (48 x 32: 67 % / 89 %).
+template <int CQ, int TW>
+static int launch_dw_bwd_geom(const __nv_bfloat16* dy, const __nv_bfloat16* x_src, const float* w, __nv_bfloat16* dx,
+                              float* dwg, int N, int H, int W, int C, int x_act, const float* x_scale,
+                              const float* x_shift, const __nv_bfloat16* addend, const float* bn_mean,
+                              const float* bn_invstd, float* bn_red, cudaStream_t st) {
+    const bool aff = (x_scale != nullptr), add = (addend != nullptr), stats = (bn_red != nullptr);
+    constexpr int kCB = CQ * 4;
+    CUtensorMap tmd, tmx, tma;
+    int rc = make_tmap_nhwc(&tmd, dy, N, H, W, C, kCB, TW + 2, kDwTH + 2);
+    if (rc) return rc;
+    rc = make_tmap_nhwc(&tmx, x_src, N, H, W, C, kCB, TW, kDwTH);
+    if (rc) return rc;
+    tma = tmx;
+    if (add) {
+        rc = make_tmap_nhwc(&tma, addend, N, H, W, C, kCB, TW, kDwTH);
+        if (rc) return rc;
+    }
+    DwBwdParams p;
+    p.N = N; p.H = H; p.W = W; p.C = C; p.w = w; p.dwg = dwg; p.dx = dx; p.x_scale = x_scale; p.x_shift = x_shift;
+    p.bn_mean = bn_mean; p.bn_invstd = bn_invstd; p.bn_red = bn_red;
+    p.tiles_h = cdiv(H, kDwTH); p.tiles_w = cdiv(W, TW);
+    const int tiles_c = cdiv(C, kCB);
+    const long long nt = (long long)N * p.tiles_h * p.tiles_w;
+    if (nt > 0x7fffffffLL) return 0;
+    p.spatial_tiles = (int)nt;
+    int per = kNumSMs / tiles_c; if (per < 1) per = 1;
+    if (per > p.spatial_tiles) per = p.spatial_tiles;
+    p.ctas_per_cb = per;
+    const int grid = tiles_c * per;
+#define DLV3P_DWB(XA, AF, AD, ST) rc = launch_dw_bwd_inst<XA, AF, AD, ST, CQ, TW>(tmd, tmx, tma, p, grid, st)
+    if (x_act == DLV3P_ACT_NONE) { if (add) DLV3P_DWB(0, false, true, false); else DLV3P_DWB(0, false, false, false); }
+    else if (x_act == DLV3P_ACT_RELU) {
+        if (stats) DLV3P_DWB(1, true, false, true);
+        else if (aff) { if (add) DLV3P_DWB(1, true, true, false); else DLV3P_DWB(1, true, false, false); }
+        else { if (add) DLV3P_DWB(1, false, true, false); else DLV3P_DWB(1, false, false, false); }
+    } else {
+        if (stats) DLV3P_DWB(2, true, false, true);
+        else if (aff) { if (add) DLV3P_DWB(2, true, true, false); else DLV3P_DWB(2, true, false, false); }
+        else { if (add) DLV3P_DWB(2, false, true, false); else DLV3P_DWB(2, false, false, false); }
+    }
+#undef DLV3P_DWB
+    return rc ? rc : 1;
+}
+
+// Returns 1 if the fused kernel took the launch, 0 if the combination is not served (caller reports), < 0 on error.
+int launch_dw_bwd_tma(const __nv_bfloat16* dy, const __nv_bfloat16* x_src, const float* w, __nv_bfloat16* dx, float* dwg,
+                      int N, int H, int W, int C, int x_act, const float* x_scale, const float* x_shift,
+                      const __nv_bfloat16* addend, const float* bn_mean, const float* bn_invstd, float* bn_red,
+                      cudaStream_t st) {
+    if (get_encode_fn() == nullptr || (C & 3)) return 0;
+    const bool aff = (x_scale != nullptr), add = (addend != nullptr), stats = (bn_red != nullptr);
+    if (x_act == DLV3P_ACT_NONE && (aff || stats)) return 0;
+    if (stats && (!aff || add)) return 0;
+    auto fill = [&](int cb, int tw) {
+        return ((double)C / (cdiv(C, cb) * cb)) * ((double)W / (cdiv(W, tw) * tw));
+    };
+    if (fill(64, 24) > fill(48, 32) + 1e-9)
+        return launch_dw_bwd_geom<16, 24>(dy, x_src, w, dx, dwg, N, H, W, C, x_act, x_scale, x_shift, addend, bn_mean,
+                                          bn_invstd, bn_red, st);
+    return launch_dw_bwd_geom<12, 32>(dy, x_src, w, dx, dwg, N, H, W, C, x_act, x_scale, x_shift, addend, bn_mean,
+                                      bn_invstd, bn_red, st);
+}
+
+// =====================================================================================================================
 // Atrous depthwise 3x3 on small feature maps (the ASPP branches: rates 6 / 12 / 18 on [N,32,32,256], ss.py:823-830).
 // With dilation d a tile of outputs needs inputs from a (TH+2d) x (TW+2d) window — for d >= 6 on a 32 x 32 map that
 // is the whole image — so ONE TMA box {64 ch, W, H} stages the complete image of one (n, channel block) in shared memory

@@ -10,6 +10,7 @@ The backward schedule is written by hand per macro-op (there is no autograd anyw
 from __future__ import annotations
 
 import math
+import os
 from types import SimpleNamespace
 from typing import Callable, Dict, List, Optional, Tuple
 
@@ -1028,6 +1029,20 @@ class Plan:
         Cin = x.C
         xb = x.buf
         in_sc, in_sh = getattr(x, "pre_scale", None), getattr(x, "pre_shift", None)
+        if (need_dx and (self.bf16 or FORCE_BNRED) and FUSE_DW_BWD and stride == 1 and tuple(dil) == (1, 1)
+                and (Ho, Wo, pad4[2], pad4[3]) == (x.shape[1], x.shape[2], 1, 1) and Cin % 4 == 0
+                and (in_act != ACT_NONE or in_sc is None)):
+            # input gradient + filter gradient (+ the BN-backward reductions of the layer that produced x) in ONE pass
+            # over d(dw out): both need the same 3x3 window of it around every input pixel
+            tgt, addend = self._grad_target(x)
+            bnred = isinstance(x, _BnActValue) and addend is None
+            if bnred:
+                x.red_done = True
+            self.bwd_seq(lambda: ops.dwconv3x3_bwd(
+                dd_get().view(N, Ho, Wo, Cin), xb, dw_w, dw_g, in_scale=in_sc, in_shift=in_sh, in_act=in_act,
+                addend=addend, bn_mean=x.bn_mean if bnred else None, bn_invstd=x.bn_invstd if bnred else None,
+                bn_red=x.bn_red() if bnred else None, out=tgt))
+            return
         self.bwd_seq(lambda: ops.dwconv3x3_wgrad(xb, dd_get().view(N, Ho, Wo, Cin), dw_g, stride, dil, in_scale=in_sc,
                                                  in_shift=in_sh, in_act=in_act, pad=pad4), side=True, slot=slot)
         if need_dx:
@@ -1586,6 +1601,7 @@ class _BnPoolValue(Value):
 
 FORCE_IMPLICIT = False  # tests: take the implicit-GEMM 3x3 schedule in fp32 too (through tests/fake_ops.py)
 FORCE_BNRED = False     # tests: take the fused dgrad+reduction schedule in fp32 too (through tests/fake_ops.py)
+FUSE_DW_BWD = os.environ.get("DLV3P_FUSE_DW_BWD", "1") != "0"   # A/B switch of the schedule (host side only)
 
 
 class _TailResize:

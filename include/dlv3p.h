@@ -101,6 +101,19 @@ int dlv3p_dwconv3x3_dgrad_bnred(const void* dy, const float* w, void* dx, int N,
 int dlv3p_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int C, int stride,
                           int dil_h, int dil_w, int pad_t, int pad_l, int Ho, int Wo, const float* in_scale,
                           const float* in_shift, int in_act, int dtype, void* stream);
+/* Whole backward of a stride-1, dilation-1, SAME depthwise convolution in ONE pass over dy (the depthwise half of every
+ * Xception SeparableConv2D, keras.applications.xception / ss.py:823-830; TF runs DepthwiseConv2dNativeBackpropInput,
+ * DepthwiseConv2dNativeBackpropFilter, ReluGrad and — for the producing layer — FusedBatchNormGradV3's reductions as
+ * separate kernels): equivalent to dlv3p_dwconv3x3_dgrad (or _dgrad_bnred when bn_red != NULL) followed by
+ * dlv3p_dwconv3x3_wgrad on the same operands.
+ *   x: what the forward convolution read BEFORE its fused prologue, i.e. conv input = act(in_scale*x + in_shift);
+ *   dx = act'(in_scale*x + in_shift) * conv_transpose(dy) (+ addend);  dw[3,3,C] (fp32) += sum act(..)[tap] * dy;
+ *   bn_red (optional, needs in_scale/in_shift, no addend): [0..C) += sum dx, [C..2C) += sum dx*(x-bn_mean)*bn_invstd.
+ * Written around the input pixel both gradients need the same 3x3 window of dy, so the bf16 kernel stages dy once
+ * (TMA halo box) and keeps the filter-gradient partial sums in registers next to the taps. */
+int dlv3p_dwconv3x3_bwd(const void* dy, const void* x, const float* w, void* dx, float* dw, int N, int H, int W, int C,
+                        const float* in_scale, const float* in_shift, int in_act, const void* addend,
+                        const float* bn_mean, const float* bn_invstd, float* bn_red, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K2 — pointwise / projection convolutions as bf16 tcgen05 tensor-core GEMMs (TF Conv2D 1x1, the pointwise

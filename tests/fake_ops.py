@@ -130,6 +130,19 @@ def dwconv3x3_wgrad(x, dy, dw, stride=1, dil=(1, 1), padding="same", in_scale=No
     return dw
 
 
+def dwconv3x3_bwd(dy, x, w, dw, in_scale=None, in_shift=None, in_act=ACT_NONE, addend=None, bn_mean=None,
+                  bn_invstd=None, bn_red=None, out=None):
+    pad = conv_geometry(x.shape[1], x.shape[2], 3, 1, (1, 1), "same")
+    if bn_red is not None:
+        out = dwconv3x3_dgrad_bnred(dy, w, tuple(x.shape), x, in_scale, in_shift, in_act, bn_mean, bn_invstd, bn_red,
+                                    out=out, pad=pad)
+    else:
+        out = dwconv3x3_dgrad(dy, w, tuple(x.shape), 1, (1, 1), x_pre=x if in_act != ACT_NONE else None,
+                              in_scale=in_scale, in_shift=in_shift, in_act=in_act, addend=addend, out=out, pad=pad)
+    dwconv3x3_wgrad(x, dy, dw, 1, (1, 1), in_scale=in_scale, in_shift=in_shift, in_act=in_act, pad=pad)
+    return out
+
+
 def _epi(acc, col_scale, col_shift, act, addend):
     if col_scale is not None:
         acc = acc * col_scale + col_shift

@@ -185,6 +185,88 @@ def test_dwconv3x3_dgrad_bnred(case, act):
                                 code, mean.to(DEV), invstd.to(DEV), red, pad=pad)       # fp32: unfused path only
 
 
+@pytest.mark.parametrize("case", [(2, 17, 19, 64), (2, 30, 31, 728), (1, 32, 32, 736), (3, 40, 70, 128), (1, 9, 33, 48),
+                                  (2, 8, 32, 104)])
+@pytest.mark.parametrize("mode", ["bnred_relu", "bnred_relu6", "affine_add", "preact", "preact_add", "plain", "plain_add"])
+def test_dwconv3x3_bwd_fused(case, mode):
+    """dlv3p_dwconv3x3_bwd: input gradient + filter gradient (+ BN-backward reductions) of a stride-1 SAME depthwise
+    conv in one launch, against the fp64 restatement on the same bf16 operands, for every operand combination the
+    engine emits: BN+ReLU(6) on load with reductions, BN+ReLU on load with a gradient addend, pre-activation ReLU
+    with / without addend, no activation.  Shapes straddle the 8 x 32 tile and the 48-channel block."""
+    o = ops()
+    N, H, W, C = case
+    bf = torch.bfloat16
+    xs = rnd((N, H, W, C), bf, 1, 2.0)                      # what the forward read before its prologue
+    w = rnd((3, 3, C), torch.float32, 2, 0.3)
+    gy = rnd((N, H, W, C), bf, 5)
+    affine = mode.startswith("bnred") or mode == "affine_add"
+    act = {"bnred_relu": o.ACT_RELU, "bnred_relu6": o.ACT_RELU6, "affine_add": o.ACT_RELU, "preact": o.ACT_RELU,
+           "preact_add": o.ACT_RELU, "plain": o.ACT_NONE, "plain_add": o.ACT_NONE}[mode]
+    sc = (rnd((C,), torch.float32, 3, 0.2) + 1.0) if affine else None
+    sh = (rnd((C,), torch.float32, 4, 0.5) + (2.0 if act == o.ACT_RELU6 else 0.0)) if affine else None
+    add = rnd((N, H, W, C), bf, 6) if mode.endswith("add") else None
+    stats = mode.startswith("bnred")
+    mean = rnd((C,), torch.float32, 7, 0.3)
+    invstd = rnd((C,), torch.float32, 8, 0.1).abs() + 0.6
+
+    pre = xs.double() * sc.double() + sh.double() if affine else xs.double()
+    if act == o.ACT_RELU:
+        xa, mask = pre.clamp(min=0), (pre > 0).double()
+    elif act == o.ACT_RELU6:
+        xa, mask = pre.clamp(0, 6), ((pre > 0) & (pre < 6)).double()
+    else:
+        xa, mask = pre, torch.ones_like(pre)
+    xr = xa.clone().requires_grad_(True)
+    wr = w.double().view(3, 3, C, 1).clone().requires_grad_(True)
+    O.depthwise_conv2d(xr, wr, 1, "same", (1, 1)).backward(gy.double())
+    g_ref = xr.grad * mask
+    dx_ref = g_ref + (add.double() if add is not None else 0.0)
+    dw_ref = wr.grad.view(3, 3, C)
+    red_ref = torch.cat([g_ref.sum((0, 1, 2)), (g_ref * (xs.double() - mean.double()) * invstd.double()).sum((0, 1, 2))])
+
+    dw = torch.zeros((3, 3, C), dtype=torch.float32, device=DEV)
+    red = torch.zeros(2 * C, dtype=torch.float32, device=DEV) if stats else None
+    d = lambda t: None if t is None else t.to(DEV)
+    run = lambda: o.dwconv3x3_bwd(gy.to(DEV), xs.to(DEV), w.to(DEV), dw, in_scale=d(sc), in_shift=d(sh), in_act=act,
+                                  addend=d(add), bn_mean=d(mean) if stats else None,
+                                  bn_invstd=d(invstd) if stats else None, bn_red=red)
+    dx = run()
+    rt, at = tol(bf)
+    check(f"dw bwd dx {mode}", dx, dx_ref, rt, at * 4)
+    n_sum = N * H * W
+    check(f"dw bwd dw {mode}", dw, dw_ref, 2e-3, 2e-3 * math.sqrt(n_sum) * 2.0)
+    if stats:
+        check(f"dw bwd red {mode}", red, red_ref, 2e-3, 2e-3 * math.sqrt(n_sum))
+    run()                                                    # dw and bn_red accumulate
+    check(f"dw bwd dw x2 {mode}", dw, 2 * dw_ref, 2e-3, 4e-3 * math.sqrt(n_sum) * 2.0)
+    if stats:
+        check(f"dw bwd red x2 {mode}", red, 2 * red_ref, 2e-3, 4e-3 * math.sqrt(n_sum))
+    # the fused launch equals the two separate entry points on the same operands
+    dw2 = torch.zeros_like(dw)
+    pad = dw_pad(H, W, 1, (1, 1), "same")
+    dx2 = o.dwconv3x3_dgrad(gy.to(DEV), w.to(DEV), (N, H, W, C), 1, (1, 1), x_pre=xs.to(DEV) if act != o.ACT_NONE else None,
+                            in_scale=d(sc), in_shift=d(sh), in_act=act, addend=d(add), pad=pad)
+    o.dwconv3x3_wgrad(xs.to(DEV), gy.to(DEV), dw2, 1, (1, 1), in_scale=d(sc), in_shift=d(sh), in_act=act, pad=pad)
+    check(f"dw bwd dx vs dgrad {mode}", dx, dx2.double().cpu(), 8e-3, 1e-3)      # one bf16 ulp: different summation order
+    check(f"dw bwd dw vs wgrad {mode}", dw, 2 * dw2.double().cpu(), 1e-4, 1e-3 * math.sqrt(n_sum))
+
+
+def test_dwconv3x3_bwd_fused_fp32_route():
+    """fp32 (parity mode) takes the separate kernels behind the same entry point."""
+    o = ops()
+    N, H, W, C = 2, 11, 13, 32
+    xs = rnd((N, H, W, C), torch.float32, 1, 2.0)
+    w = rnd((3, 3, C), torch.float32, 2, 0.3)
+    gy = rnd((N, H, W, C), torch.float32, 5)
+    xr = xs.double().clamp(min=0).requires_grad_(True)
+    wr = w.double().view(3, 3, C, 1).clone().requires_grad_(True)
+    O.depthwise_conv2d(xr, wr, 1, "same", (1, 1)).backward(gy.double())
+    dw = torch.zeros((3, 3, C), dtype=torch.float32, device=DEV)
+    dx = o.dwconv3x3_bwd(gy.to(DEV), xs.to(DEV), w.to(DEV), dw, in_act=o.ACT_RELU)
+    check("dw bwd fp32 dx", dx, xr.grad * (xs.double() > 0), 1e-5, 1e-5)
+    check("dw bwd fp32 dw", dw, wr.grad.view(3, 3, C), 1e-4, 1e-4)
+
+
 @pytest.mark.parametrize("ratio", [5.0, 40.0])
 def test_dwconv3x3_dgrad_bnred_large_mean_over_std(ratio):
     """The fused kernel finishes sum g*xhat from sum g*y and sum g (it has no second pass over y).  With a channel

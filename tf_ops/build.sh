@@ -11,7 +11,7 @@ CFLAGS=$(python -c 'import tensorflow as tf; print(" ".join(tf.sysconfig.get_com
 LFLAGS=$(python -c 'import tensorflow as tf; print(" ".join(tf.sysconfig.get_link_flags()))')
 LIBDIR="${HERE}/../deeplabv3plus_keras_b200"
 [ -f "${LIBDIR}/libdlv3p.so" ] || bash "${LIBDIR}/csrc/build.sh"
-g++ -std=c++17 -shared -fPIC -O2 -DGOOGLE_CUDA=1 "${HERE}/dlv3p_tf_ops.cc" -o "${HERE}/libdlv3p_tf_ops.so" \
+g++ -std=c++17 -shared -fPIC -O2 -DGOOGLE_CUDA=1 "${HERE}/dlv3p_tf_ops.cc" "${HERE}/dlv3p_tf_raw_ops.cc" -o "${HERE}/libdlv3p_tf_ops.so" \
     ${CFLAGS} -I/usr/local/cuda/include ${LFLAGS} -L"${LIBDIR}" -ldlv3p -L/usr/local/cuda/lib64 -lcudart \
     -Wl,-rpath,"${LIBDIR}"
 echo "built ${HERE}/libdlv3p_tf_ops.so"
