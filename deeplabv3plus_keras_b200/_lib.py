@@ -28,7 +28,7 @@ SIGNATURES = {
                                _p, _p, _i, _p],
     "dlv3p_dwconv3x3_dgrad_bnred": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p, _p, _p, _i, _p],
     "dlv3p_dwconv3x3_wgrad": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p],
-    "dlv3p_dwconv3x3_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _p, _i, _p],
+    "dlv3p_dwconv3x3_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _p, _p, _i, _p],
     "dlv3p_gemm_bf16": [_p, _l, _p, _l, _p, _l, _i, _i, _i, _i, _p, _p, _i, _p, _l, _p, _p],
     "dlv3p_gemm_wgrad_bf16": [_p, _l, _p, _l, _p, _l, _i, _i, _i, _p],
     "dlv3p_conv3x3_valid_fwd_bf16": [_p, _p, _l, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p],

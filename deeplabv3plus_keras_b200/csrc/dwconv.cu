@@ -32,7 +32,7 @@ int launch_dw_wgrad_tma(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* 
 int launch_dw_bwd_tma(const __nv_bfloat16* dy, const __nv_bfloat16* x_src, const float* w, __nv_bfloat16* dx, float* dwg,
                       int N, int H, int W, int C, int x_act, const float* x_scale, const float* x_shift,
                       const __nv_bfloat16* addend, const float* bn_mean, const float* bn_invstd, float* bn_red,
-                      cudaStream_t st);
+                      const __nv_bfloat16* bn_y, cudaStream_t st);
 int launch_dw_image(int mode, const __nv_bfloat16* in, const float* w, __nv_bfloat16* out, const __nv_bfloat16* dy,
                     float* dwg, int N, int H, int W, int C, int dil_h, int dil_w, int flip, int in_act,
                     const __nv_bfloat16* addend, cudaStream_t st);
@@ -641,7 +641,7 @@ extern "C" int dlv3p_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, i
 extern "C" int dlv3p_dwconv3x3_bwd(const void* dy, const void* x, const float* w, void* dx, float* dw, int N, int H,
                                    int W, int C, const float* in_scale, const float* in_shift, int in_act,
                                    const void* addend, const float* bn_mean, const float* bn_invstd, float* bn_red,
-                                   int dtype, void* stream) {
+                                   const void* bn_y, int dtype, void* stream) {
     int rc = check_dw_args(dy, w, dx, N, H, W, C, 1, 1, 1, H, W);
     if (rc) return rc;
     DLV3P_REQUIRE(x != nullptr && dw != nullptr, DLV3P_ERR_SHAPE, "dwconv3x3_bwd: x and dw are required");
@@ -649,17 +649,22 @@ extern "C" int dlv3p_dwconv3x3_bwd(const void* dy, const void* x, const float* w
                   "dwconv3x3_bwd: in_scale and in_shift must both be given or both be NULL");
     DLV3P_REQUIRE(in_scale == nullptr || in_act != DLV3P_ACT_NONE, DLV3P_ERR_SHAPE,
                   "dwconv3x3_bwd: an affine input map needs an activation");
-    DLV3P_REQUIRE(bn_red == nullptr || (in_scale && bn_mean && bn_invstd && addend == nullptr), DLV3P_ERR_SHAPE,
-                  "dwconv3x3_bwd: the BN reductions need in_scale/in_shift, bn_mean, bn_invstd and no addend");
+    DLV3P_REQUIRE(bn_red == nullptr || (bn_mean && bn_invstd), DLV3P_ERR_SHAPE,
+                  "dwconv3x3_bwd: the BN reductions need bn_mean and bn_invstd");
+    DLV3P_REQUIRE(bn_red == nullptr || bn_y != nullptr || (in_scale && addend == nullptr), DLV3P_ERR_SHAPE,
+                  "dwconv3x3_bwd: reductions against x need in_scale/in_shift and no addend (pass bn_y otherwise)");
+    DLV3P_REQUIRE(bn_y == nullptr || (bn_red != nullptr && aligned16(bn_y)), DLV3P_ERR_SHAPE,
+                  "dwconv3x3_bwd: bn_y needs bn_red (and 16-byte alignment)");
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == DLV3P_BF16) {
         rc = launch_dw_bwd_tma((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, w, (__nv_bfloat16*)dx, dw, N, H, W, C,
-                               in_act, in_scale, in_shift, (const __nv_bfloat16*)addend, bn_mean, bn_invstd, bn_red, st);
+                               in_act, in_scale, in_shift, (const __nv_bfloat16*)addend, bn_mean, bn_invstd, bn_red,
+                               (const __nv_bfloat16*)bn_y, st);
         if (rc != 0) return rc < 0 ? rc : 0;
     }
-    // fp32 (parity mode) or no TMA: the same result from the separate entry points
-    if (bn_red != nullptr) {
-        DLV3P_REQUIRE(dtype == DLV3P_BF16, DLV3P_ERR_DTYPE, "dwconv3x3_bwd: BN reductions are bf16 only");
+    // fp32 (parity mode), no TMA, or an operand combination the fused kernel does not serve: separate entry points
+    if (bn_red != nullptr && bn_y == nullptr) {
+        DLV3P_REQUIRE(dtype == DLV3P_BF16, DLV3P_ERR_DTYPE, "dwconv3x3_bwd: reductions against x are bf16 only");
         rc = dlv3p_dwconv3x3_dgrad_bnred(dy, w, dx, N, H, W, C, 1, 1, H, W, x, in_scale, in_shift, in_act, bn_mean,
                                          bn_invstd, bn_red, dtype, stream);
     } else {
@@ -667,5 +672,10 @@ extern "C" int dlv3p_dwconv3x3_bwd(const void* dy, const void* x, const float* w
                                    in_scale, in_shift, in_act, addend, dtype, stream);
     }
     if (rc) return rc;
+    if (bn_y != nullptr) {
+        rc = dlv3p_bn_bwd_reduce(dx, C, bn_y, C, nullptr, nullptr, bn_mean, bn_invstd, DLV3P_ACT_NONE, (int64_t)N * H * W, C,
+                                 bn_red, dtype, stream);
+        if (rc) return rc;
+    }
     return dlv3p_dwconv3x3_wgrad(x, dy, dw, N, H, W, C, 1, 1, 1, 1, 1, H, W, in_scale, in_shift, in_act, dtype, stream);
 }

@@ -663,17 +663,18 @@ int launch_dw_wgrad_tma(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* 
 // 16 x 32 = 512 threads on 64-channel blocks.  Per middle-flow layer ([16,32,32,728]) this replaces a 17.5 us and a
 // 15.3 us launch, each mostly launch ramp and tail on a 24 MB L2-resident tensor.
 // =====================================================================================================================
-template <int CQ, int TW, bool HAS_ADD>
+template <int CQ, int TW, bool HAS_ADD, bool YBOX>
 struct DwBwdCfg {
     static constexpr int kCB = CQ * 4;                                        // channels per block
     static constexpr int kThreads = CQ * TW;
     static constexpr int kHaloBytes = (kDwTH + 2) * (TW + 2) * kCB * 2;
     static constexpr int kCtrBytes = kDwTH * TW * kCB * 2;
-    static constexpr int kStageBytes = kHaloBytes + (HAS_ADD ? 2 : 1) * kCtrBytes;
+    static constexpr int kStageBytes = kHaloBytes + (1 + (HAS_ADD ? 1 : 0) + (YBOX ? 1 : 0)) * kCtrBytes;
     static constexpr int kBudget = 226 * 1024;
     static constexpr int kStages = kBudget / kStageBytes >= 4 ? 4 : (kBudget / kStageBytes >= 3 ? 3 : 2);
     static constexpr int kXOff = kHaloBytes;
     static constexpr int kAddOff = kHaloBytes + kCtrBytes;
+    static constexpr int kYOff = kHaloBytes + (HAS_ADD ? 2 : 1) * kCtrBytes;
     static constexpr int kRedWg = 9 * TW * kCB * 4;                        // filter-gradient reduction buffer
     static constexpr int kRedBn = 2 * TW * kCB * 4;
     static constexpr int kSmem = kStages * kStageBytes + 128 + 64;
@@ -692,12 +693,17 @@ struct DwBwdParams {
 };
 
 // X_ACT: activation between x_src and the convolution (its derivative masks dx), X_AFFINE: per-channel affine map in
-// front of it (the producing layer's training-mode BatchNormalization), HAS_ADD: gradient addend, STATS: BN reductions.
-template <int X_ACT, bool X_AFFINE, bool HAS_ADD, bool STATS, int CQ, int TW>
+// front of it (the producing layer's training-mode BatchNormalization), HAS_ADD: gradient addend, STATS: BN reductions
+// of the masked gradient against x_src (x_src = raw output of the BN's layer), YSTATS: BN reductions of the FINAL
+// gradient (addend included) against a separate tensor bn_y — the layer whose BatchNormalization output (+ residual) was
+// materialised and is read here through a pre-activation (the block-closing sepconv of an Xception block).
+template <int X_ACT, bool X_AFFINE, bool HAS_ADD, bool STATS, bool YSTATS, int CQ, int TW>
 __global__ void __launch_bounds__(CQ * TW, 1)
 dw_bwd_tma_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_x,
-                  const __grid_constant__ CUtensorMap tm_add, const DwBwdParams p) {
-    using Cfg = DwBwdCfg<CQ, TW, HAS_ADD>;
+                  const __grid_constant__ CUtensorMap tm_add, const __grid_constant__ CUtensorMap tm_y,
+                  const DwBwdParams p) {
+    static_assert(!(STATS && YSTATS), "one set of reductions per launch");
+    using Cfg = DwBwdCfg<CQ, TW, HAS_ADD, YSTATS>;
     constexpr int kCB = Cfg::kCB, kStages = Cfg::kStages, kStageBytes = Cfg::kStageBytes;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
@@ -717,6 +723,7 @@ dw_bwd_tma_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_dy)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_x)) : "memory");
         if (HAS_ADD) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_add)) : "memory");
+        if (YSTATS) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_y)) : "memory");
         for (int s = 0; s < kStages; ++s) mbar_init(bar0 + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -741,7 +748,7 @@ dw_bwd_tma_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
             msc[0] = a.x; msc[1] = a.y; msc[2] = a.z; msc[3] = a.w;
             msh[0] = b.x; msh[1] = b.y; msh[2] = b.z; msh[3] = b.w;
         }
-        if (STATS) {
+        if (STATS || YSTATS) {
             const float4 m = __ldcg(reinterpret_cast<const float4*>(p.bn_mean + c0));
             mu[0] = m.x; mu[1] = m.y; mu[2] = m.z; mu[3] = m.w;
         }
@@ -759,6 +766,7 @@ dw_bwd_tma_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
         tma_load_4d(dst, &tm_dy, bar0 + 8 * s, cb * kCB, tw * TW - 1, th * kDwTH - 1, n);
         tma_load_4d(dst + Cfg::kXOff, &tm_x, bar0 + 8 * s, cb * kCB, tw * TW, th * kDwTH, n);
         if (HAS_ADD) tma_load_4d(dst + Cfg::kAddOff, &tm_add, bar0 + 8 * s, cb * kCB, tw * TW, th * kDwTH, n);
+        if (YSTATS) tma_load_4d(dst + Cfg::kYOff, &tm_y, bar0 + 8 * s, cb * kCB, tw * TW, th * kDwTH, n);
     };
 
     int tile = blockIdx.x % p.ctas_per_cb;
@@ -787,7 +795,7 @@ dw_bwd_tma_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
         mbar_wait(bar0 + 8 * s, (it / kStages) & 1u);
 
         if (lane_ok) {
-            // stage layout: dy [TH+2][TW+2][CB], then x_src [TH][TW][CB] (, addend [TH][TW][CB])
+            // stage layout: dy [TH+2][TW+2][CB], then x_src [TH][TW][CB] (, addend [TH][TW][CB]) (, bn_y [TH][TW][CB])
             const uint32_t base = stage0 + s * kStageBytes + (col * kCB + cq * 4) * 2;
             auto load_row = [&](int row, float2 (&dst)[3][2]) {
 #pragma unroll
@@ -865,6 +873,14 @@ dw_bwd_tma_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
                         widen4_t<DLV3P_ACT_NONE>(araw, af);
                         f[0] += af[0].x; f[1] += af[0].y; f[2] += af[1].x; f[3] += af[1].y;
                     }
+                    if (YSTATS) {
+                        const uint2 yraw = lds_ctr(Cfg::kYOff, r);
+                        float2 yf[2];
+                        widen4_t<DLV3P_ACT_NONE>(yraw, yf);
+                        const float yv[4] = {yf[0].x, yf[0].y, yf[1].x, yf[1].y};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { bs1[k] += f[k]; bs2[k] = fmaf(f[k], yv[k] - mu[k], bs2[k]); }
+                    }
                     uint2 o;
                     __nv_bfloat162 lo = __floats2bfloat162_rn(f[0], f[1]), hi = __floats2bfloat162_rn(f[2], f[3]);
                     o.x = *reinterpret_cast<uint32_t*>(&lo);
@@ -895,7 +911,7 @@ dw_bwd_tma_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
     for (int a = 0; a < 9; ++a)
         *reinterpret_cast<float4*>(red + (a * TW + col) * kCB + cq * 4) =
             make_float4(acc9[a][0].x, acc9[a][0].y, acc9[a][1].x, acc9[a][1].y);
-    if (STATS) {
+    if (STATS || YSTATS) {
         *reinterpret_cast<float4*>(redbn + col * kCB + cq * 4) = make_float4(bs1[0], bs1[1], bs1[2], bs1[3]);
         *reinterpret_cast<float4*>(redbn + (TW + col) * kCB + cq * 4) = make_float4(bs2[0], bs2[1], bs2[2], bs2[3]);
     }
@@ -910,8 +926,8 @@ dw_bwd_tma_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
             atomicAdd(p.dwg + (8 - a) * p.C + ch, sum);
         }
     }
-    if (STATS) {
-        // red[0..C) += sum g, red[C..2C) += sum g*xhat, g = the masked gradient written above (dlv3p_bn_bwd_reduce)
+    if (STATS || YSTATS) {
+        // red[0..C) += sum g, red[C..2C) += sum g*xhat, g = the gradient written above (dlv3p_bn_bwd_reduce)
         for (int o = tid; o < 2 * kCB; o += Cfg::kThreads) {
             const int q2 = o / kCB, c = o % kCB;
             const int ch = cb * kCB + c;
@@ -926,19 +942,19 @@ dw_bwd_tma_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
     }
 }
 
-template <int X_ACT, bool X_AFFINE, bool HAS_ADD, bool STATS, int CQ, int TW>
-static int launch_dw_bwd_inst(const CUtensorMap& tmd, const CUtensorMap& tmx, const CUtensorMap& tma,
+template <int X_ACT, bool X_AFFINE, bool HAS_ADD, bool STATS, bool YSTATS, int CQ, int TW>
+static int launch_dw_bwd_inst(const CUtensorMap& tmd, const CUtensorMap& tmx, const CUtensorMap& tma, const CUtensorMap& tmy,
                               const DwBwdParams& p, int grid, cudaStream_t st) {
-    using Cfg = DwBwdCfg<CQ, TW, HAS_ADD>;
+    using Cfg = DwBwdCfg<CQ, TW, HAS_ADD, YSTATS>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(dw_bwd_tma_kernel<X_ACT, X_AFFINE, HAS_ADD, STATS, CQ, TW>,
+        cudaError_t e = cudaFuncSetAttribute(dw_bwd_tma_kernel<X_ACT, X_AFFINE, HAS_ADD, STATS, YSTATS, CQ, TW>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
         DLV3P_REQUIRE(e == cudaSuccess, DLV3P_ERR_CUDA, "cudaFuncSetAttribute(dw bwd smem=%d): %s", Cfg::kSmem, cudaGetErrorString(e));
         configured = true;
     }
-    launch_pdl(dw_bwd_tma_kernel<X_ACT, X_AFFINE, HAS_ADD, STATS, CQ, TW>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmem, st,
-               tmd, tmx, tma, p);
+    launch_pdl(dw_bwd_tma_kernel<X_ACT, X_AFFINE, HAS_ADD, STATS, YSTATS, CQ, TW>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmem, st,
+               tmd, tmx, tma, tmy, p);
     return check_launch("dwconv3x3_bwd (tma)");
 }
 
@@ -949,17 +965,22 @@ template <int CQ, int TW>
 static int launch_dw_bwd_geom(const __nv_bfloat16* dy, const __nv_bfloat16* x_src, const float* w, __nv_bfloat16* dx,
                               float* dwg, int N, int H, int W, int C, int x_act, const float* x_scale,
                               const float* x_shift, const __nv_bfloat16* addend, const float* bn_mean,
-                              const float* bn_invstd, float* bn_red, cudaStream_t st) {
-    const bool aff = (x_scale != nullptr), add = (addend != nullptr), stats = (bn_red != nullptr);
+                              const float* bn_invstd, float* bn_red, const __nv_bfloat16* bn_y, cudaStream_t st) {
+    const bool aff = (x_scale != nullptr), add = (addend != nullptr), ystats = (bn_y != nullptr);
+    const bool stats = (bn_red != nullptr) && !ystats;
     constexpr int kCB = CQ * 4;
-    CUtensorMap tmd, tmx, tma;
+    CUtensorMap tmd, tmx, tma, tmy;
     int rc = make_tmap_nhwc(&tmd, dy, N, H, W, C, kCB, TW + 2, kDwTH + 2);
     if (rc) return rc;
     rc = make_tmap_nhwc(&tmx, x_src, N, H, W, C, kCB, TW, kDwTH);
     if (rc) return rc;
-    tma = tmx;
+    tma = tmx; tmy = tmx;
     if (add) {
         rc = make_tmap_nhwc(&tma, addend, N, H, W, C, kCB, TW, kDwTH);
+        if (rc) return rc;
+    }
+    if (ystats) {
+        rc = make_tmap_nhwc(&tmy, bn_y, N, H, W, C, kCB, TW, kDwTH);
         if (rc) return rc;
     }
     DwBwdParams p;
@@ -974,7 +995,11 @@ static int launch_dw_bwd_geom(const __nv_bfloat16* dy, const __nv_bfloat16* x_sr
     if (per > p.spatial_tiles) per = p.spatial_tiles;
     p.ctas_per_cb = per;
     const int grid = tiles_c * per;
-#define DLV3P_DWB(XA, AF, AD, ST) rc = launch_dw_bwd_inst<XA, AF, AD, ST, CQ, TW>(tmd, tmx, tma, p, grid, st)
+#define DLV3P_DWB(XA, AF, AD, ST) rc = launch_dw_bwd_inst<XA, AF, AD, ST, false, CQ, TW>(tmd, tmx, tma, tmy, p, grid, st)
+    if (ystats) {
+        if (add) rc = launch_dw_bwd_inst<1, false, true, false, true, CQ, TW>(tmd, tmx, tma, tmy, p, grid, st);
+        else rc = launch_dw_bwd_inst<1, false, false, false, true, CQ, TW>(tmd, tmx, tma, tmy, p, grid, st);
+    } else
     if (x_act == DLV3P_ACT_NONE) { if (add) DLV3P_DWB(0, false, true, false); else DLV3P_DWB(0, false, false, false); }
     else if (x_act == DLV3P_ACT_RELU) {
         if (stats) DLV3P_DWB(1, true, false, true);
@@ -993,19 +1018,20 @@ static int launch_dw_bwd_geom(const __nv_bfloat16* dy, const __nv_bfloat16* x_sr
 int launch_dw_bwd_tma(const __nv_bfloat16* dy, const __nv_bfloat16* x_src, const float* w, __nv_bfloat16* dx, float* dwg,
                       int N, int H, int W, int C, int x_act, const float* x_scale, const float* x_shift,
                       const __nv_bfloat16* addend, const float* bn_mean, const float* bn_invstd, float* bn_red,
-                      cudaStream_t st) {
+                      const __nv_bfloat16* bn_y, cudaStream_t st) {
     if (get_encode_fn() == nullptr || (C & 3)) return 0;
     const bool aff = (x_scale != nullptr), add = (addend != nullptr), stats = (bn_red != nullptr);
     if (x_act == DLV3P_ACT_NONE && (aff || stats)) return 0;
-    if (stats && (!aff || add)) return 0;
+    if (bn_y != nullptr && (!stats || aff || x_act != DLV3P_ACT_RELU)) return 0;      // pre-activation ReLU readers only
+    if (stats && bn_y == nullptr && (!aff || add)) return 0;
     auto fill = [&](int cb, int tw) {
         return ((double)C / (cdiv(C, cb) * cb)) * ((double)W / (cdiv(W, tw) * tw));
     };
     if (fill(64, 24) > fill(48, 32) + 1e-9)
         return launch_dw_bwd_geom<16, 24>(dy, x_src, w, dx, dwg, N, H, W, C, x_act, x_scale, x_shift, addend, bn_mean,
-                                          bn_invstd, bn_red, st);
+                                          bn_invstd, bn_red, bn_y, st);
     return launch_dw_bwd_geom<12, 32>(dy, x_src, w, dx, dwg, N, H, W, C, x_act, x_scale, x_shift, addend, bn_mean,
-                                      bn_invstd, bn_red, st);
+                                      bn_invstd, bn_red, bn_y, st);
 }
 
 // =====================================================================================================================

@@ -337,6 +337,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t a_dst = smem_base + s * STAGE_BYTES;
                     const uint32_t b_dst = a_dst + A_BYTES;
                     const uint32_t fb = full_bar + 8 * s;
+                    if (DLV3P_DBG(p, 1)) { mbar_arrive(fb); continue; }
                     mbar_expect_tx(fb, STAGE_BYTES);
                     const int kk = kb * kBlockK;
                     if (p.conv_mode != 0) {
@@ -443,7 +444,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             ad = umma_desc(a_src + k * 32, 16, 1024);
                             bd = umma_desc(b_src + k * 32, 16, 1024);
                         }
-                        tc_mma_bf16(d_tmem, ad, bd, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+                        if (!DLV3P_DBG(p, 4)) tc_mma_bf16(d_tmem, ad, bd, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
                     }
                     tc_commit(empty_bar + 8 * s);              // smem slot reusable once these MMAs retire
                 }
@@ -468,6 +469,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t as = t % kAcc;
                 mbar_wait(tmem_full_bar + 8 * as, (t / kAcc) & 1u);
                 tc_fence_after();
+                if (DLV3P_DBG(p, 2)) { if (lane == 0) mbar_arrive(tmem_empty_bar + 8 * as); continue; }
                 int rb = row0 + q * 32, rl = row_limit, c2 = -1;
                 if (p.conv_mode != 0) {
                     const int mt = row0 / kBlockM;
@@ -488,6 +490,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t as = t % kAcc;
             mbar_wait(tmem_full_bar + 8 * as, (t / kAcc) & 1u);
             tc_fence_after();
+            if (DLV3P_DBG(p, 2)) { if (lane == 0) mbar_arrive(tmem_empty_bar + 8 * as); continue; }
             if (half == 1) {                                   // the direct-store fallback uses one warp per quadrant
                 if (lane == 0) mbar_arrive(tmem_empty_bar + 8 * as);
                 continue;

@@ -59,6 +59,10 @@ class _MacroScope(SimpleNamespace):
 class Value:
     """A materialised NHWC activation, its gradient buffer and pending (zero-copy) gradient contributions."""
 
+    # plan-time: set by the fused depthwise-backward launch that wrote this tensor's gradient LAST, so that the producer
+    # (a Conv -> BN (+ residual) macro-op) can ask that launch for its BatchNormalization reductions as well
+    fold_hook: Optional[dict] = None
+
     def __init__(self, shape, dtype, buf=None, name=""):
         self.shape = tuple(shape)
         self.dtype = dtype
@@ -372,6 +376,7 @@ class Plan:
     def _grad_target(self, v: Value) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
         """(buffer to write, addend) for a real gradient writer, given what the schedule has emitted so far."""
         g = self._grad_of(v)
+        v.fold_hook = None                                   # a new writer: any earlier one is no longer the last
         if v.grad_written:
             return g, g
         v.grad_written = True
@@ -393,6 +398,7 @@ class Plan:
         g = self._grad_of(v)
         while v.pending:
             p = v.pending.pop()
+            v.fold_hook = None                               # the gradient is completed by this add, not by the hook's launch
             self.bwd_seq(lambda p=p, g=g: ops.add(g, p, g))
         return g
 
@@ -919,7 +925,13 @@ class Plan:
                     self.bwd_seq(lambda: ops.maxpool3x3s2_bn_bwd(g, pb["argmax"], y, scale, mean, invstd, red(), Mo,
                                                                  dy_get().view(N, Ho, Wo, Cout)))
                 ld_g = g.stride(0) if g.dim() == 2 else Cout          # 2-D: a channel slice of a concat gradient
-                if not pool_virt and not (virt and out.red_done):
+                hook = out.fold_hook
+                folded = (hook is not None and not virt and not pool_virt and act_b == ACT_NONE and g is out.grad
+                          and ld_g == Cout and y.dtype == g.dtype)
+                if folded:
+                    # the launch that wrote g last (a fused depthwise backward of the reader) reduces it against y as well
+                    hook.update(bn_y=y, bn_mean=mean, bn_invstd=invstd, bn_red=red)
+                if not pool_virt and not folded and not (virt and out.red_done):
                     self.bwd_seq(lambda: ops.bn_bwd_reduce(g, y, scale, shift, mean, invstd, act_b, Mo, Cout, red(),
                                                            ld_dz=ld_g))
                 if not pool_virt:
@@ -1035,13 +1047,25 @@ class Plan:
             # input gradient + filter gradient (+ the BN-backward reductions of the layer that produced x) in ONE pass
             # over d(dw out): both need the same 3x3 window of it around every input pixel
             tgt, addend = self._grad_target(x)
-            bnred = isinstance(x, _BnActValue) and addend is None
-            if bnred:
+            red = {}
+            if isinstance(x, _BnActValue) and addend is None:
+                # x = relu(BN(y)) never written: the masked gradient and the reductions of that BN come out together
                 x.red_done = True
-            self.bwd_seq(lambda: ops.dwconv3x3_bwd(
-                dd_get().view(N, Ho, Wo, Cin), xb, dw_w, dw_g, in_scale=in_sc, in_shift=in_sh, in_act=in_act,
-                addend=addend, bn_mean=x.bn_mean if bnred else None, bn_invstd=x.bn_invstd if bnred else None,
-                bn_red=x.bn_red() if bnred else None, out=tgt))
+                red = dict(bn_mean=x.bn_mean, bn_invstd=x.bn_invstd, bn_red=x.bn_red)
+            elif in_act == ACT_RELU and in_sc is None and FOLD_BLOCK_RED:
+                # x = a materialised BN output (+ residual) read through a pre-activation (the next block's first
+                # SeparableConv2D): if this launch turns out to write the FINAL gradient of x, the producer's backward
+                # (_emit_conv_backward) fills `red` with its raw output y / mean / invstd / slot and skips its own
+                # dlv3p_bn_bwd_reduce pass over the two tensors
+                x.fold_hook = red
+
+            def launch():
+                slot = red.get("bn_red")
+                ops.dwconv3x3_bwd(dd_get().view(N, Ho, Wo, Cin), xb, dw_w, dw_g, in_scale=in_sc, in_shift=in_sh,
+                                  in_act=in_act, addend=addend, bn_mean=red.get("bn_mean"),
+                                  bn_invstd=red.get("bn_invstd"), bn_red=slot() if slot is not None else None,
+                                  bn_y=red.get("bn_y"), out=tgt)
+            self.bwd_seq(launch)
             return
         self.bwd_seq(lambda: ops.dwconv3x3_wgrad(xb, dd_get().view(N, Ho, Wo, Cin), dw_g, stride, dil, in_scale=in_sc,
                                                  in_shift=in_sh, in_act=in_act, pad=pad4), side=True, slot=slot)
@@ -1564,6 +1588,14 @@ class _AliasValue(Value):
     def pending(self):
         return self._x.pending
 
+    @property
+    def fold_hook(self):
+        return self._x.fold_hook
+
+    @fold_hook.setter
+    def fold_hook(self, v):
+        self._x.fold_hook = v
+
 
 class _BnActValue(Value):
     """`act(scale * y + shift)` for the raw conv output y of a training-mode Conv -> BatchNormalization -> ReLU/ReLU6
@@ -1602,6 +1634,7 @@ class _BnPoolValue(Value):
 FORCE_IMPLICIT = False  # tests: take the implicit-GEMM 3x3 schedule in fp32 too (through tests/fake_ops.py)
 FORCE_BNRED = False     # tests: take the fused dgrad+reduction schedule in fp32 too (through tests/fake_ops.py)
 FUSE_DW_BWD = os.environ.get("DLV3P_FUSE_DW_BWD", "1") != "0"   # A/B switch of the schedule (host side only)
+FOLD_BLOCK_RED = os.environ.get("DLV3P_FOLD_BLOCK_RED", "1") != "0"
 
 
 class _TailResize:

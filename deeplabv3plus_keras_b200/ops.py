@@ -146,16 +146,17 @@ def dwconv3x3_wgrad(x: Tensor, dy: Tensor, dw: Tensor, stride=1, dil=(1, 1), pad
 
 
 def dwconv3x3_bwd(dy: Tensor, x: Tensor, w: Tensor, dw: Tensor, in_scale=None, in_shift=None, in_act=ACT_NONE,
-                  addend=None, bn_mean=None, bn_invstd=None, bn_red=None, out: Optional[Tensor] = None):
-    """Input gradient + filter gradient (+ BN-backward reductions of x's layer) of a stride-1 dilation-1 SAME depthwise
-    conv in one launch; dw [3,3,C] fp32 and bn_red [2C] are ACCUMULATED into.  Returns dx."""
+                  addend=None, bn_mean=None, bn_invstd=None, bn_red=None, bn_y=None, out: Optional[Tensor] = None):
+    """Input gradient + filter gradient (+ BN-backward reductions: of x's layer, or with bn_y of the layer whose raw
+    output is bn_y, taken on the final gradient) of a stride-1 dilation-1 SAME depthwise conv in one launch; dw [3,3,C]
+    fp32 and bn_red [2C] are ACCUMULATED into.  Returns dx."""
     _chk(dy, "dy"); _chk(x, "x")
     N, H, W, Cc = x.shape
     assert tuple(dy.shape) == (N, H, W, Cc), (dy.shape, x.shape)
     if out is None:
         out = torch.empty((N, H, W, Cc), dtype=dy.dtype, device=dy.device)
     call("dlv3p_dwconv3x3_bwd", _p(dy), _p(x), _p(w), _p(out), _p(dw), N, H, W, Cc, _p(in_scale), _p(in_shift), in_act,
-         _p(addend), _p(bn_mean), _p(bn_invstd), _p(bn_red), _dt(dy), _stream())
+         _p(addend), _p(bn_mean), _p(bn_invstd), _p(bn_red), _p(bn_y), _dt(dy), _stream())
     return out
 
 

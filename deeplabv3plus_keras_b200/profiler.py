@@ -35,7 +35,7 @@ COSTS: Dict[str, Tuple[str, Callable]] = {
                                                 20 * a[3] * a[9] * a[10] * a[6])),
     "dlv3p_dwconv3x3_dgrad_bnred": ("hbm", lambda a: ((2 * a[3] * a[4] * a[5] * a[6] + a[3] * a[9] * a[10] * a[6]) * _esz(a[18]) + 36 * a[6],
                                                      22 * a[3] * a[4] * a[5] * a[6])),
-    "dlv3p_dwconv3x3_bwd": ("hbm", lambda a: (a[5] * a[6] * a[7] * a[8] * (3 + _opt(a[12])) * _esz(a[16]) + 72 * a[8],
+    "dlv3p_dwconv3x3_bwd": ("hbm", lambda a: (a[5] * a[6] * a[7] * a[8] * (3 + _opt(a[12]) + _opt(a[16])) * _esz(a[17]) + 72 * a[8],
                                              (36 + 4 * _opt(a[15])) * a[5] * a[6] * a[7] * a[8])),
     "dlv3p_dwconv3x3_wgrad": ("hbm", lambda a: ((a[3] * a[4] * a[5] * a[6] + a[3] * a[12] * a[13] * a[6]) * _esz(a[17]) + 36 * a[6],
                                                18 * a[3] * a[12] * a[13] * a[6])),

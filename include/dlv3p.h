@@ -108,12 +108,18 @@ int dlv3p_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, int N, int H
  * dlv3p_dwconv3x3_wgrad on the same operands.
  *   x: what the forward convolution read BEFORE its fused prologue, i.e. conv input = act(in_scale*x + in_shift);
  *   dx = act'(in_scale*x + in_shift) * conv_transpose(dy) (+ addend);  dw[3,3,C] (fp32) += sum act(..)[tap] * dy;
- *   bn_red (optional, needs in_scale/in_shift, no addend): [0..C) += sum dx, [C..2C) += sum dx*(x-bn_mean)*bn_invstd.
+ *   bn_red (optional): BatchNormalization-backward reductions (dlv3p_bn_bwd_reduce's contract, accumulated):
+ *     bn_y == NULL (needs in_scale/in_shift, no addend): of the layer whose raw output is x —
+ *       [0..C) += sum g, [C..2C) += sum g*(x-bn_mean)*bn_invstd with g = the masked gradient (dx before any addend);
+ *     bn_y != NULL (in_act = RELU, no in_scale): of the layer whose raw output is bn_y and whose BN output (+ residual)
+ *       is x (the block-closing SeparableConv2D of an Xception block read through the next block's pre-activation) —
+ *       [0..C) += sum dx, [C..2C) += sum dx*(bn_y-bn_mean)*bn_invstd with dx the FINAL gradient (addend included).
  * Written around the input pixel both gradients need the same 3x3 window of dy, so the bf16 kernel stages dy once
  * (TMA halo box) and keeps the filter-gradient partial sums in registers next to the taps. */
 int dlv3p_dwconv3x3_bwd(const void* dy, const void* x, const float* w, void* dx, float* dw, int N, int H, int W, int C,
                         const float* in_scale, const float* in_shift, int in_act, const void* addend,
-                        const float* bn_mean, const float* bn_invstd, float* bn_red, int dtype, void* stream);
+                        const float* bn_mean, const float* bn_invstd, float* bn_red, const void* bn_y, int dtype,
+                        void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K2 — pointwise / projection convolutions as bf16 tcgen05 tensor-core GEMMs (TF Conv2D 1x1, the pointwise

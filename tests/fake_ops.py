@@ -131,14 +131,19 @@ def dwconv3x3_wgrad(x, dy, dw, stride=1, dil=(1, 1), padding="same", in_scale=No
 
 
 def dwconv3x3_bwd(dy, x, w, dw, in_scale=None, in_shift=None, in_act=ACT_NONE, addend=None, bn_mean=None,
-                  bn_invstd=None, bn_red=None, out=None):
+                  bn_invstd=None, bn_red=None, bn_y=None, out=None):
     pad = conv_geometry(x.shape[1], x.shape[2], 3, 1, (1, 1), "same")
-    if bn_red is not None:
+    if bn_red is not None and bn_y is None:
         out = dwconv3x3_dgrad_bnred(dy, w, tuple(x.shape), x, in_scale, in_shift, in_act, bn_mean, bn_invstd, bn_red,
                                     out=out, pad=pad)
     else:
         out = dwconv3x3_dgrad(dy, w, tuple(x.shape), 1, (1, 1), x_pre=x if in_act != ACT_NONE else None,
                               in_scale=in_scale, in_shift=in_shift, in_act=in_act, addend=addend, out=out, pad=pad)
+    if bn_y is not None:
+        Cc = x.shape[3]
+        g = out.float().reshape(-1, Cc)
+        bn_red[:Cc] += g.sum(0)
+        bn_red[Cc:2 * Cc] += (g * (bn_y.float().reshape(-1, Cc) - bn_mean) * bn_invstd).sum(0)
     dwconv3x3_wgrad(x, dy, dw, 1, (1, 1), in_scale=in_scale, in_shift=in_shift, in_act=in_act, pad=pad)
     return out
 

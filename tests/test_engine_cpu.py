@@ -99,6 +99,42 @@ def test_bn_relu_fused_into_depthwise_schedule(cpu_engine, monkeypatch, fuse):
         assert np.abs(ga[k] - gb[k]).max() <= 2e-3 * scale, k
 
 
+def test_block_closing_bn_reductions_fold_into_the_readers_backward(cpu_engine, monkeypatch):
+    """Xception block output = BN(sepconv3) + residual, read by the next block's first SeparableConv2D through a
+    pre-activation ReLU.  When that reader's fused depthwise backward (dlv3p_dwconv3x3_bwd) writes the FINAL gradient of
+    the block output, it also produces the BN-backward reductions of sepconv3 (bn_y) and the producer's own
+    bn_bwd_reduce pass disappears; every gradient must equal the unfolded schedule."""
+    monkeypatch.setattr(cpu_engine, "FORCE_BNRED", True)
+    conf = util.make_conf(width=64, base="xception", output_stride=16, image_size=65)
+    ss = util.build(conf)
+    util.randomize_weights(ss.model)
+    x = y = None
+    res = {}
+    for fold in (True, False):
+        monkeypatch.setattr(cpu_engine, "FOLD_BLOCK_RED", fold)
+        calls = []
+        with monkeypatch.context() as mp:
+            for name in ("bn_bwd_reduce", "dwconv3x3_bwd"):
+                orig = getattr(fake_ops, name)
+                mp.setattr(fake_ops, name, (lambda orig, name: lambda *a, **k: (calls.append((name, k.get("bn_y") is not None)),
+                                                                                orig(*a, **k))[1])(orig, name))
+            plan = cpu_engine.Plan(ss.model, 2, training=True)
+            if x is None:
+                x, y = util.synthetic_batch(conf, 2, plan.out_shape[1:3])
+            plan.set_loss(PW, NW)
+            plan.load_batch(x, y)
+            plan.step_fwd_bwd()
+            res[fold] = (plan.gradients(), plan.loss_value(), calls.count(("dwconv3x3_bwd", True)),
+                         sum(1 for c in calls if c[0] == "bn_bwd_reduce"))
+    (ga, la, n_y, n_red), (gb, lb, n_y0, n_red0) = res[True], res[False]
+    # middle flow: the outputs of blocks 4..11 are read by blocks 5..12 (8 folds); entry flow: whatever closes last
+    assert n_y0 == 0 and n_y >= 8 and n_red0 - n_red == n_y, (n_y, n_red, n_red0)
+    assert abs(la - lb) < 1e-6
+    for k in gb:
+        scale = max(np.abs(gb[k]).max(), 1e-3)
+        assert np.abs(ga[k] - gb[k]).max() <= 2e-3 * scale, k
+
+
 def test_channel_pitch_padding_is_invisible_and_skips_concatenated_widths(cpu_engine):
     """728-channel tensors live on a 736-channel pitch (pad parameters zero, Keras-shaped views outside); a width that
     reaches a Concatenate (ASPP reduction_size = 72 here) keeps its logical pitch."""

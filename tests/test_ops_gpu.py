@@ -251,6 +251,39 @@ def test_dwconv3x3_bwd_fused(case, mode):
     check(f"dw bwd dw vs wgrad {mode}", dw, 2 * dw2.double().cpu(), 1e-4, 1e-3 * math.sqrt(n_sum))
 
 
+@pytest.mark.parametrize("case", [(2, 30, 31, 728), (3, 40, 70, 128), (1, 32, 32, 736)])
+@pytest.mark.parametrize("with_add", [False, True])
+def test_dwconv3x3_bwd_fused_bn_y(case, with_add):
+    """dlv3p_dwconv3x3_bwd with bn_y: besides dx and dw, the BatchNormalization-backward reductions of the layer whose
+    raw output is bn_y, taken on the FINAL gradient (addend included) — what the engine asks of the reader of an
+    Xception block output."""
+    o = ops()
+    N, H, W, C = case
+    bf = torch.bfloat16
+    xs = rnd((N, H, W, C), bf, 1, 2.0)
+    by = rnd((N, H, W, C), bf, 9, 1.5) + 0.7
+    w = rnd((3, 3, C), torch.float32, 2, 0.3)
+    gy = rnd((N, H, W, C), bf, 5)
+    add = rnd((N, H, W, C), bf, 6) if with_add else None
+    mean = rnd((C,), torch.float32, 7, 0.3) + 0.7
+    invstd = rnd((C,), torch.float32, 8, 0.1).abs() + 0.6
+    xr = xs.double().clamp(min=0).requires_grad_(True)
+    wr = w.double().view(3, 3, C, 1).clone().requires_grad_(True)
+    O.depthwise_conv2d(xr, wr, 1, "same", (1, 1)).backward(gy.double())
+    dx_ref = xr.grad * (xs.double() > 0) + (add.double() if with_add else 0.0)
+    dw = torch.zeros((3, 3, C), dtype=torch.float32, device=DEV)
+    red = torch.zeros(2 * C, dtype=torch.float32, device=DEV)
+    dx = o.dwconv3x3_bwd(gy.to(DEV), xs.to(DEV), w.to(DEV), dw, in_act=o.ACT_RELU, addend=None if add is None else add.to(DEV),
+                         bn_mean=mean.to(DEV), bn_invstd=invstd.to(DEV), bn_red=red, bn_y=by.to(DEV))
+    rt, at = tol(bf)
+    check("dw bwd bn_y dx", dx, dx_ref, rt, at * 4)
+    check("dw bwd bn_y dw", dw, wr.grad.view(3, 3, C), 2e-3, 4e-3 * math.sqrt(N * H * W))
+    # the reductions are those of the STORED (bf16-rounded) gradient, as dlv3p_bn_bwd_reduce would compute them from dx
+    g = dx.double().cpu()
+    red_ref = torch.cat([g.sum((0, 1, 2)), (g * (by.double() - mean.double()) * invstd.double()).sum((0, 1, 2))])
+    check("dw bwd bn_y red", red, red_ref, 4e-3, 4e-3 * math.sqrt(N * H * W) * 2)
+
+
 def test_dwconv3x3_bwd_fused_fp32_route():
     """fp32 (parity mode) takes the separate kernels behind the same entry point."""
     o = ops()
