@@ -64,6 +64,14 @@ template <> struct Vec8<__nv_bfloat16> {
         asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                      : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "l"(p));
     }
+    // Coherent load (L2, no non-coherent / L1 copy) for operands that may ALIAS the kernel's output: the engine
+    // accumulates gradients in place (addend == out).  A non-coherent load (__ldg / ld.global.nc) of memory the same
+    // kernel writes is undefined by PTX and leaves stale lines in the SM's read-only cache that a dependent kernel's
+    // non-coherent loads can still hit (seen as a few stale 8-element vectors in a BN backward, 1 run in 6).
+    __device__ __forceinline__ void load_rw(const __nv_bfloat16* p) {
+        asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "l"(p) : "memory");
+    }
     __device__ __forceinline__ void store(__nv_bfloat16* p) const { *reinterpret_cast<uint4*>(p) = raw; }
     __device__ __forceinline__ void zero() { raw = make_uint4(0, 0, 0, 0); }
     __device__ __forceinline__ void to_float(float (&f)[8]) const {
@@ -88,6 +96,10 @@ template <> struct Vec8<float> {
         b = __ldg(reinterpret_cast<const float4*>(p) + 1);
     }
     __device__ __forceinline__ void load_stream(const float* p) { load(p); }
+    __device__ __forceinline__ void load_rw(const float* p) {
+        asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(p) : "memory");
+        asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p + 4) : "memory");
+    }
     __device__ __forceinline__ void store(float* p) const {
         reinterpret_cast<float4*>(p)[0] = a;
         reinterpret_cast<float4*>(p)[1] = b;
@@ -104,6 +116,8 @@ template <> struct Vec8<float> {
 template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+// scalar coherent load (see Vec8::load_rw)
+template <typename T> __device__ __forceinline__ float ld_rw_f(const T* p) { return to_f<T>(__ldcg(p)); }
 template <typename T> __device__ __forceinline__ T from_f(float v);
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
@@ -143,6 +157,7 @@ template <typename T, int V> struct Pack;
 template <typename T> struct Pack<T, 8> {
     Vec8<T> v;
     __device__ __forceinline__ void load(const T* p) { v.load(p); }
+    __device__ __forceinline__ void load_rw(const T* p) { v.load_rw(p); }
     __device__ __forceinline__ void store(T* p) const { v.store(p); }
     __device__ __forceinline__ void to_float(float (&f)[8]) const { v.to_float(f); }
     __device__ __forceinline__ void from_float(const float (&f)[8]) { v.from_float(f); }
@@ -150,6 +165,7 @@ template <typename T> struct Pack<T, 8> {
 template <typename T> struct Pack<T, 1> {
     T v;
     __device__ __forceinline__ void load(const T* p) { v = *p; }
+    __device__ __forceinline__ void load_rw(const T* p) { v = __ldcg(p); }
     __device__ __forceinline__ void store(T* p) const { *p = v; }
     __device__ __forceinline__ void to_float(float (&f)[1]) const { f[0] = to_f<T>(v); }
     __device__ __forceinline__ void from_float(const float (&f)[1]) { v = from_f<T>(f[0]); }

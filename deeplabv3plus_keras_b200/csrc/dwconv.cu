@@ -150,7 +150,7 @@ dw_conv_kernel(const T* __restrict__ in, const float* __restrict__ w, T* __restr
                 }
             }
             if (addend != nullptr) {
-                Vec8<T> av; av.load(addend + off);
+                Vec8<T> av; av.load_rw(addend + off);
                 float af[8]; av.to_float(af);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) acc[o][k] += af[k];
@@ -212,7 +212,7 @@ dw_dgrad_strided_kernel(const T* __restrict__ dy, const float* __restrict__ w, T
         }
     }
     if (addend != nullptr) {
-        Vec8<T> av; av.load(addend + off);
+        Vec8<T> av; av.load_rw(addend + off);
         float af[8]; av.to_float(af);
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] += af[k];

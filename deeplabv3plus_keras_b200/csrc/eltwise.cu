@@ -205,7 +205,7 @@ affine_act_kernel(const T* __restrict__ y, long long ld_y, const float* __restri
         f[k] = apply_act(u, act);
     }
     if (addend != nullptr) {
-        Pack<T, V> b; b.load(addend + r * ld_a + c0);
+        Pack<T, V> b; b.load_rw(addend + r * ld_a + c0);
         float g[V]; b.to_float(g);
 #pragma unroll
         for (int k = 0; k < V; ++k) f[k] += g[k];
@@ -421,7 +421,7 @@ act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict_
 #pragma unroll
     for (int k = 0; k < V; ++k) g[k] *= act_mask(v[k], act);
     if (addend != nullptr) {
-        Pack<T, V> c; c.load(addend + i);
+        Pack<T, V> c; c.load_rw(addend + i);
         float h[V]; c.to_float(h);
 #pragma unroll
         for (int k = 0; k < V; ++k) g[k] += h[k];
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(256)
 add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long long n) {
     const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V;
     if (i >= n) return;
-    Pack<T, V> pa, pb; pa.load(a + i); pb.load(b + i);
+    Pack<T, V> pa, pb; pa.load_rw(a + i); pb.load_rw(b + i);      // out may alias a or b
     float fa[V], fb[V]; pa.to_float(fa); pb.to_float(fb);
 #pragma unroll
     for (int k = 0; k < V; ++k) fa[k] += fb[k];
@@ -486,7 +486,7 @@ maxpool3x3s2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __r
         *reinterpret_cast<uint2*>(argmax + off) = pk;
     }
     if (addend != nullptr) {
-        Vec8<T> a; a.load(addend + off);
+        Vec8<T> a; a.load_rw(addend + off);
         float g[8]; a.to_float(g);
 #pragma unroll
         for (int k = 0; k < 8; ++k) best[k] += g[k];
@@ -537,7 +537,7 @@ maxpool3x3s2_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ ar
     }
     const long long off = (((long long)n * H + hi) * W + wi) * C + c0;
     if (addend != nullptr) {
-        Vec8<T> a; a.load(addend + off);
+        Vec8<T> a; a.load_rw(addend + off);
         float g[8]; a.to_float(g);
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] += g[k];
@@ -600,7 +600,7 @@ avgpool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int N, int H, i
     }
     const long long off = (((long long)n * H + hi) * W + wi) * C + c0;
     if (addend != nullptr) {
-        Vec8<T> a; a.load(addend + off);
+        Vec8<T> a; a.load_rw(addend + off);
         float g[8]; a.to_float(g);
 #pragma unroll
         for (int q = 0; q < 8; ++q) acc[q] += g[q];
@@ -694,7 +694,7 @@ bilinear_bwd_kernel(const TI* __restrict__ dy, long long ld_dy, TO* __restrict__
     }
     const long long off = (((long long)n * H + hi) * W + wi) * ld_dx + c0;
     if (addend != nullptr) {
-        Pack<TO, V> a; a.load(addend + off);
+        Pack<TO, V> a; a.load_rw(addend + off);
         float g[V]; a.to_float(g);
 #pragma unroll
         for (int k = 0; k < V; ++k) acc[k] += g[k];
@@ -766,7 +766,7 @@ col2im3x3_kernel(const T* __restrict__ col, T* __restrict__ dx, int N, int H, in
     }
     const I off = (((I)n * H + hi) * W + wi) * C + c0;
     if (addend != nullptr) {
-        Pack<T, V> a; a.load(addend + off);
+        Pack<T, V> a; a.load_rw(addend + off);
         float g[V]; a.to_float(g);
 #pragma unroll
         for (int k = 0; k < V; ++k) acc[k] += g[k];
@@ -812,7 +812,7 @@ subsample_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int N, int H,
     }
     const I off = (((I)n * H + hi) * W + wi) * C + c0;
     if (addend != nullptr) {
-        Vec8<T> a; a.load(addend + off);
+        Vec8<T> a; a.load_rw(addend + off);
         float g[8]; a.to_float(g);
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] += g[k];
@@ -913,7 +913,7 @@ dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, float ra
     const uint64_t h = splitmix64(seed * 0xD1342543DE82EF95ull + (uint64_t)i);
     const float u = (float)(h >> 40) * (1.0f / 16777216.0f);   // [0,1)
     float v = (u >= rate) ? to_f<T>(x[i]) / (1.f - rate) : 0.f;
-    if (addend != nullptr) v += to_f<T>(addend[i]);
+    if (addend != nullptr) v += ld_rw_f<T>(addend + i);
     y[i] = from_f<T>(v);
 }
 
@@ -1408,7 +1408,7 @@ maxpool3x3s2_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t
                     }
                 }
                 if (addend != nullptr) {
-                    const uint4 ad = __ldg(reinterpret_cast<const uint4*>(addend + off));
+                    const uint4 ad = __ldcg(reinterpret_cast<const uint4*>(addend + off));      // may alias dx
                     const uint32_t av[4] = {ad.x, ad.y, ad.z, ad.w};
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -1480,7 +1480,7 @@ dropout8_kernel(const T* __restrict__ x, T* __restrict__ y, long long n8, float 
         f[2 * q + 1] = (u1 >= rate) ? f[2 * q + 1] * keep : 0.f;
     }
     if (addend != nullptr) {
-        Vec8<T> d; d.load_stream(addend + i * 8);
+        Vec8<T> d; d.load_rw(addend + i * 8);          // may alias y (gradient accumulated in place)
         float e[8]; d.to_float(e);
 #pragma unroll
         for (int k = 0; k < 8; ++k) f[k] += e[k];

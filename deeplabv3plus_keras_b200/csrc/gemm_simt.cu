@@ -76,7 +76,7 @@ gemm_simt_kernel(const TA* __restrict__ A, long long sam, long long sak, const T
             }
             if (col_scale != nullptr) v = fmaf(v, col_scale[n], col_shift[n]);
             v = apply_act(v, act);
-            if (addend != nullptr) v += to_f<TC>(addend[m * ld_add + n]);
+            if (addend != nullptr) v += ld_rw_f<TC>(addend + m * ld_add + n);    // may alias C
             if (accumulate) v += to_f<TC>(C[m * ldc + n]);
             C[m * ldc + n] = from_f<TC>(v);
         }

@@ -154,7 +154,7 @@ template <int BLOCK_N, bool WGRAD, bool REMOTE>
 __device__ __forceinline__ void staged_tile_epilogue(const GemmParams& p, const CUtensorMap* tmC, uint32_t acc_tmem,
                                                      int rbase, int col0, int lane, int half, uint32_t stg0, uint32_t& buf,
                                                      uint32_t empty_bar, float* stat_smem, int stat_mode, int stat_slot,
-                                                     int stat_cap, int row_limit, int c2) {
+                                                     int stat_cap, int row_limit, int c2, const float* sc_tab = nullptr) {
     constexpr int CW = WGRAD ? 32 : 64;                 // columns per staging tile (128-byte rows)
     const uint32_t lane_row = (uint32_t)lane * 128u;
     const uint32_t sw = (uint32_t)(lane & 7);
@@ -201,7 +201,19 @@ __device__ __forceinline__ void staged_tile_epilogue(const GemmParams& p, const 
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-                if (p.col_scale != nullptr) {
+                if (sc_tab != nullptr) {
+                    // per-column scale / shift (folded BatchNormalization) from the CTA's shared-memory table: 16 broadcast
+                    // LDS.128 per 32 columns instead of 64 global loads per lane (the ncu source page of the MobileNetV2
+                    // projections showed the epilogue warps serialised on them, profiles/r2_skinny_gemm.md)
+                    const float4* sc4 = reinterpret_cast<const float4*>(sc_tab + n_base + h * 32);
+                    const float4* sh4 = reinterpret_cast<const float4*>(sc_tab + kMaxStatCols + n_base + h * 32);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 a = sc4[j], b = sh4[j];
+                        v[4 * j] = fmaf(v[4 * j], a.x, b.x); v[4 * j + 1] = fmaf(v[4 * j + 1], a.y, b.y);
+                        v[4 * j + 2] = fmaf(v[4 * j + 2], a.z, b.z); v[4 * j + 3] = fmaf(v[4 * j + 3], a.w, b.w);
+                    }
+                } else if (p.col_scale != nullptr) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int n = min(n_base + h * 32 + j, p.N - 1);
@@ -269,6 +281,22 @@ __device__ __forceinline__ void staged_tile_epilogue(const GemmParams& p, const 
     }
 }
 
+// Per-column epilogue operands (col_scale / col_shift = the folded BatchNormalization of an inference GEMM) staged once
+// per CTA in the statistics region ([kMaxStatCols] scale, then [kMaxStatCols] shift; the region is free because a GEMM
+// either folds a BN or collects its batch statistics, never both).  Columns past N read as scale 0 / shift 0.  Called by
+// ALL threads right after the programmatic-dependency wait (the vectors may come from the preceding dlv3p_bn_fold).
+template <bool WGRAD>
+__device__ __forceinline__ const float* fill_scale_table(const GemmParams& p, float* stat_smem, int nthreads) {
+    if (WGRAD || p.col_scale == nullptr || p.col_stats != nullptr || p.N > kMaxStatCols) return nullptr;
+    const int n_pad = min((p.N + 255) & ~255, kMaxStatCols);        // whole 256-column tiles are read unpredicated
+    for (int i = threadIdx.x; i < n_pad; i += nthreads) {
+        stat_smem[i] = i < p.N ? __ldg(p.col_scale + i) : 0.f;
+        stat_smem[kMaxStatCols + i] = i < p.N ? __ldg(p.col_shift + i) : 0.f;
+    }
+    __syncthreads();
+    return stat_smem;
+}
+
 template <int BLOCK_N, bool WGRAD>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -320,6 +348,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     pdl_wait();                              // prologue done; the operands may still be in flight from the previous kernel
+    const float* sc_tab = fill_scale_table<WGRAD>(p, stat_smem, kThreads);
 
     const int num_work = p.n_tiles * p.m_tiles * (WGRAD ? p.splits : 1);
 
@@ -479,7 +508,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 staged_tile_epilogue<BLOCK_N, WGRAD, false>(p, &tmC, tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N,
                                                             rb, col0, lane, half, stg0, buf,
-                                                            tmem_empty_bar + 8 * as, stat_smem, stat_mode, q, kCap1, rl, c2);
+                                                            tmem_empty_bar + 8 * as, stat_smem, stat_mode, q, kCap1, rl, c2,
+                                                            sc_tab);
             }
             if (lane == 0) tma_wait_group_read<0>();      // smem may be released; the writes drain before the grid completes
         } else {
@@ -571,7 +601,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
 
                 if (row_ok) {
-                    if (p.col_scale != nullptr) {
+                    if (sc_tab != nullptr) {
+                        const float4* sc4 = reinterpret_cast<const float4*>(sc_tab + n_base);
+                        const float4* sh4 = reinterpret_cast<const float4*>(sc_tab + kMaxStatCols + n_base);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 a = sc4[j], b = sh4[j];
+                            v[4 * j] = fmaf(v[4 * j], a.x, b.x); v[4 * j + 1] = fmaf(v[4 * j + 1], a.y, b.y);
+                            v[4 * j + 2] = fmaf(v[4 * j + 2], a.z, b.z); v[4 * j + 3] = fmaf(v[4 * j + 3], a.w, b.w);
+                        }
+                    } else if (p.col_scale != nullptr) {
                         const int jmax = p.N - n_base;             // columns of this chunk that exist (predicated loads)
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
@@ -598,7 +637,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) f[j] = v[g * 8 + j];
                                 if (add != nullptr) {
-                                    Vec8<__nv_bfloat16> a8; a8.load(add + g * 8);
+                                    Vec8<__nv_bfloat16> a8; a8.load_rw(add + g * 8);      // may alias C
                                     float af[8]; a8.to_float(af);
 #pragma unroll
                                     for (int j = 0; j < 8; ++j) f[j] += af[j];
@@ -611,7 +650,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             for (int j = 0; j < 32; ++j) {
                                 if (n_base + j < p.N) {
                                     float f = v[j];
-                                    if (add != nullptr) f += __bfloat162float(add[j]);
+                                    if (add != nullptr) f += __bfloat162float(__ldcg(add + j));
                                     dst[j] = __float2bfloat16_rn(f);
                                 }
                             }
@@ -622,7 +661,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const bool vec = full && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (add != nullptr && n_base + j < p.N) v[j] += add[j];
+                            if (add != nullptr && n_base + j < p.N) v[j] += __ldcg(add + j);
                         if (vec) {
 #pragma unroll
                             for (int g = 0; g < 8; ++g)
@@ -758,6 +797,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     pdl_wait();
+    const float* sc_tab = fill_scale_table<WGRAD>(p, stat_smem, kThreads);
 
     // forward: 256 x BLOCK_N pair tiles, n fastest.  filter gradient: (pixel-range split) x (tile), split-major; rows =
     // input channels (p.K), columns = output channels (p.N), reduction over the p.M pixels
@@ -862,7 +902,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             staged_tile_epilogue<BLOCK_N, WGRAD, true>(p, &tmC, tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N,
                                                        row0 + q * 32, col0, lane, half, stg0, buf,
                                                        leader_tmem_empty + 8 * as, stat_smem, stat_mode, q, kCap2,
-                                                       WGRAD ? p.K : p.M, -1);
+                                                       WGRAD ? p.K : p.M, -1, sc_tab);
         }
         if (lane == 0) tma_wait_group_read<0>();      // smem may be released; the writes drain before the grid completes
         if (use_smem_stats) {
