@@ -521,7 +521,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(tmem_full_bar + 8 * as, (t / kAcc) & 1u);
             tc_fence_after();
             if (DLV3P_DBG(p, 2)) { if (lane == 0) mbar_arrive(tmem_empty_bar + 8 * as); continue; }
-            if (half == 1) {                                   // the direct-store fallback uses one warp per quadrant
+            // (the statistics / filter-gradient variants share per-quadrant tables and a staging buffer: one warp only)
+            const int owner = (WGRAD || p.col_stats != nullptr) ? 0 : (int)(t & 1u);
+            if (half != owner) {
+                // direct-store fallback: ONE warp per lane quadrant per tile, the two warps of a quadrant take alternate
+                // tiles (the narrow-N GEMMs that come here are epilogue-paced: scripts/skinny_decompose.py)
                 if (lane == 0) mbar_arrive(tmem_empty_bar + 8 * as);
                 continue;
             }

@@ -442,7 +442,11 @@ class Plan:
         for site, ent in self.act_sites.items():
             if ent[0] == "bn":
                 _, act, y, scale, shift, clog, shape = ent
-                z = (y.float().view(-1, y.shape[-1]) * scale + shift).view(shape)[..., :clog]
+                # the kernels decide on fmaf(y, scale, shift) (ONE rounding): y*scale is exact in fp64 and the sum rounds
+                # once, so this reproduces their sign / clamp decision bit for bit.  A separate fp32 multiply and add rounds
+                # twice and flips the decision of an element within an ulp of the threshold — about one parity run in
+                # eight had such an element (the BN statistics differ in the last bit from run to run: fp32 atomics)
+                z = (y.double().view(-1, y.shape[-1]) * scale.double() + shift.double()).float().view(shape)[..., :clog]
             else:
                 _, act, v = ent
                 z = v.buf.float()[..., :v.clog]
