@@ -273,19 +273,22 @@ dw_conv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
             // one output row from the three window rows (ra above, rb centre, rc below); three independent
             // accumulation chains per channel pair (one per window row) keep the FMA pipe fed at 4 warps/scheduler
             auto emit = [&](int r, const float2 (&ra)[3][2], const float2 (&rb)[3][2], const float2 (&rc)[3][2]) {
+                // two accumulation chains per channel pair (taps 0..4 / 5..8) and one packed add: the kernel is bound by the
+                // FP32 pipe (a packed FMA on three distinct register pairs holds it for 3 cycles, scripts/ubench/fma_rate.cu),
+                // a three-chain sum spends two packed adds per pair where one is enough to cover the FMA latency
                 float2 acc[2];
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     float2 a0 = __fmul2_rn(ra[0][k], wgt[0][k]);
-                    float2 a1 = __fmul2_rn(rb[0][k], wgt[3][k]);
-                    float2 a2 = __fmul2_rn(rc[0][k], wgt[6][k]);
+                    float2 a1 = __fmul2_rn(rb[2][k], wgt[5][k]);
                     a0 = __ffma2_rn(ra[1][k], wgt[1][k], a0);
-                    a1 = __ffma2_rn(rb[1][k], wgt[4][k], a1);
-                    a2 = __ffma2_rn(rc[1][k], wgt[7][k], a2);
+                    a1 = __ffma2_rn(rc[0][k], wgt[6][k], a1);
                     a0 = __ffma2_rn(ra[2][k], wgt[2][k], a0);
-                    a1 = __ffma2_rn(rb[2][k], wgt[5][k], a1);
-                    a2 = __ffma2_rn(rc[2][k], wgt[8][k], a2);
-                    acc[k] = __fadd2_rn(__fadd2_rn(a0, a1), a2);
+                    a1 = __ffma2_rn(rc[1][k], wgt[7][k], a1);
+                    a0 = __ffma2_rn(rb[0][k], wgt[3][k], a0);
+                    a1 = __ffma2_rn(rc[2][k], wgt[8][k], a1);
+                    a0 = __ffma2_rn(rb[1][k], wgt[4][k], a0);
+                    acc[k] = __fadd2_rn(a0, a1);
                 }
                 if (r < rows_valid) {
                     float f[4] = {acc[0].x, acc[0].y, acc[1].x, acc[1].y};

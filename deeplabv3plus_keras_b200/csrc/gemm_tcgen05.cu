@@ -150,7 +150,9 @@ __device__ __forceinline__ void decode_work(const GemmParams& p, int w, int& row
 // `acc_tmem` = TMEM address of this warp's lane quadrant at the accumulator stage; `rbase` = first output row of the
 // warp; `empty_bar` is arrived on once every TMEM read of the tile has completed (REMOTE: it is a shared::cluster
 // address in the leader CTA of a 2-CTA pair).
-template <int BLOCK_N, bool WGRAD, bool REMOTE>
+// SC: 0 = per-column scale / shift (if any) fetched with global loads (the implicit-convolution kernels), 1 = from the
+// CTA's shared-memory table `sc_tab`, 2 = the launch has none (compiled out: the training GEMMs)
+template <int BLOCK_N, bool WGRAD, bool REMOTE, int SC = 0>
 __device__ __forceinline__ void staged_tile_epilogue(const GemmParams& p, const CUtensorMap* tmC, uint32_t acc_tmem,
                                                      int rbase, int col0, int lane, int half, uint32_t stg0, uint32_t& buf,
                                                      uint32_t empty_bar, float* stat_smem, int stat_mode, int stat_slot,
@@ -201,7 +203,7 @@ __device__ __forceinline__ void staged_tile_epilogue(const GemmParams& p, const 
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-                if (sc_tab != nullptr) {
+                if (SC == 1) {
                     // per-column scale / shift (folded BatchNormalization) from the CTA's shared-memory table: 16 broadcast
                     // LDS.128 per 32 columns instead of 64 global loads per lane (the ncu source page of the MobileNetV2
                     // projections showed the epilogue warps serialised on them, profiles/r2_skinny_gemm.md)
@@ -213,7 +215,7 @@ __device__ __forceinline__ void staged_tile_epilogue(const GemmParams& p, const 
                         v[4 * j] = fmaf(v[4 * j], a.x, b.x); v[4 * j + 1] = fmaf(v[4 * j + 1], a.y, b.y);
                         v[4 * j + 2] = fmaf(v[4 * j + 2], a.z, b.z); v[4 * j + 3] = fmaf(v[4 * j + 3], a.w, b.w);
                     }
-                } else if (p.col_scale != nullptr) {
+                } else if (SC == 0 && p.col_scale != nullptr) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int n = min(n_base + h * 32 + j, p.N - 1);
@@ -285,9 +287,7 @@ __device__ __forceinline__ void staged_tile_epilogue(const GemmParams& p, const 
 // per CTA in the statistics region ([kMaxStatCols] scale, then [kMaxStatCols] shift; the region is free because a GEMM
 // either folds a BN or collects its batch statistics, never both).  Columns past N read as scale 0 / shift 0.  Called by
 // ALL threads right after the programmatic-dependency wait (the vectors may come from the preceding dlv3p_bn_fold).
-template <bool WGRAD>
 __device__ __forceinline__ const float* fill_scale_table(const GemmParams& p, float* stat_smem, int nthreads) {
-    if (WGRAD || p.col_scale == nullptr || p.col_stats != nullptr || p.N > kMaxStatCols) return nullptr;
     const int n_pad = min((p.N + 255) & ~255, kMaxStatCols);        // whole 256-column tiles are read unpredicated
     for (int i = threadIdx.x; i < n_pad; i += nthreads) {
         stat_smem[i] = i < p.N ? __ldg(p.col_scale + i) : 0.f;
@@ -297,7 +297,10 @@ __device__ __forceinline__ const float* fill_scale_table(const GemmParams& p, fl
     return stat_smem;
 }
 
-template <int BLOCK_N, bool WGRAD>
+// SC (see staged_tile_epilogue): 2 = no col_scale / col_shift (the training GEMMs: compiled out), 1 = from the
+// shared-memory table (inference GEMM with a folded BatchNormalization), 0 = global loads (scale together with col_stats,
+// or N > kMaxStatCols: the table lives in the statistics region)
+template <int BLOCK_N, bool WGRAD, int SC>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
@@ -348,7 +351,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     pdl_wait();                              // prologue done; the operands may still be in flight from the previous kernel
-    const float* sc_tab = fill_scale_table<WGRAD>(p, stat_smem, kThreads);
+    const float* sc_tab = SC == 1 ? fill_scale_table(p, stat_smem, kThreads) : nullptr;
 
     const int num_work = p.n_tiles * p.m_tiles * (WGRAD ? p.splits : 1);
 
@@ -506,7 +509,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     else if (WGRAD) { rb = q * 32; rl = p.cv_rlimit; c2 = mt; }          // (cout, element of the run, filter row)
                     else { rb = (mt % p.cv_tpr) * kBlockM + q * 32; rl = p.cv_rlimit; c2 = mt / p.cv_tpr; }   // (ch, column, row)
                 }
-                staged_tile_epilogue<BLOCK_N, WGRAD, false>(p, &tmC, tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N,
+                staged_tile_epilogue<BLOCK_N, WGRAD, false, SC>(p, &tmC, tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N,
                                                             rb, col0, lane, half, stg0, buf,
                                                             tmem_empty_bar + 8 * as, stat_smem, stat_mode, q, kCap1, rl, c2,
                                                             sc_tab);
@@ -605,7 +608,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
 
                 if (row_ok) {
-                    if (sc_tab != nullptr) {
+                    if (SC == 1) {
                         const float4* sc4 = reinterpret_cast<const float4*>(sc_tab + n_base);
                         const float4* sh4 = reinterpret_cast<const float4*>(sc_tab + kMaxStatCols + n_base);
 #pragma unroll
@@ -614,7 +617,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             v[4 * j] = fmaf(v[4 * j], a.x, b.x); v[4 * j + 1] = fmaf(v[4 * j + 1], a.y, b.y);
                             v[4 * j + 2] = fmaf(v[4 * j + 2], a.z, b.z); v[4 * j + 3] = fmaf(v[4 * j + 3], a.w, b.w);
                         }
-                    } else if (p.col_scale != nullptr) {
+                    } else if (SC == 0 && p.col_scale != nullptr) {
                         const int jmax = p.N - n_base;             // columns of this chunk that exist (predicated loads)
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
@@ -754,7 +757,7 @@ __device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t tmem_d, uint64_t adesc,
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-template <int BLOCK_N, bool WGRAD>
+template <int BLOCK_N, bool WGRAD, int SC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
@@ -801,7 +804,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     pdl_wait();
-    const float* sc_tab = fill_scale_table<WGRAD>(p, stat_smem, kThreads);
+    const float* sc_tab = SC == 1 ? fill_scale_table(p, stat_smem, kThreads) : nullptr;
 
     // forward: 256 x BLOCK_N pair tiles, n fastest.  filter gradient: (pixel-range split) x (tile), split-major; rows =
     // input channels (p.K), columns = output channels (p.N), reduction over the p.M pixels
@@ -903,7 +906,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (lane == 0) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_tmem_empty + 8 * as) : "memory");
                 continue;
             }
-            staged_tile_epilogue<BLOCK_N, WGRAD, true>(p, &tmC, tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N,
+            staged_tile_epilogue<BLOCK_N, WGRAD, true, SC>(p, &tmC, tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N,
                                                        row0 + q * 32, col0, lane, half, stg0, buf,
                                                        leader_tmem_empty + 8 * as, stat_smem, stat_mode, q, kCap2,
                                                        WGRAD ? p.K : p.M, -1, sc_tab);
@@ -933,38 +936,63 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // ---- host side --------------------------------------------------------------------------------------------------
-template <int BLOCK_N, bool WGRAD>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
-                       cudaStream_t st) {
+template <int BLOCK_N, bool WGRAD, int SC>
+static int launch_gemm_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
+                            cudaStream_t st) {
     constexpr int smem = GemmCfg<BLOCK_N>::kSmem;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, WGRAD, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         DLV3P_REQUIRE(e == cudaSuccess, DLV3P_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
         configured = true;
     }
     const int work = p.n_tiles * p.m_tiles * (WGRAD ? p.splits : 1);
     const int grid = work < kNumSMs ? work : kNumSMs;         // persistent: one CTA per SM
-    launch_pdl(gemm_tc_kernel<BLOCK_N, WGRAD>, dim3(grid), dim3(kThreads), smem, st, tmA, tmB, tmC, p);
+    launch_pdl(gemm_tc_kernel<BLOCK_N, WGRAD, SC>, dim3(grid), dim3(kThreads), smem, st, tmA, tmB, tmC, p);
     return check_launch(WGRAD ? "gemm_wgrad_bf16" : "gemm_bf16");
 }
 
+// the shared-memory scale / shift table lives in the statistics region: usable when the launch collects no statistics
+static inline bool scale_table_ok(const GemmParams& p) { return p.col_stats == nullptr && p.N <= kMaxStatCols; }
+
 template <int BLOCK_N, bool WGRAD>
-static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, GemmParams p,
-                        cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
+                       cudaStream_t st) {
+    if constexpr (!WGRAD) {
+        if (p.col_scale != nullptr)
+            return scale_table_ok(p) ? launch_gemm_inst<BLOCK_N, false, 1>(tmA, tmB, tmC, p, st)
+                                     : launch_gemm_inst<BLOCK_N, false, 0>(tmA, tmB, tmC, p, st);
+    }
+    return launch_gemm_inst<BLOCK_N, WGRAD, 2>(tmA, tmB, tmC, p, st);
+}
+
+template <int BLOCK_N, bool WGRAD, int SC>
+static int launch_gemm2_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, GemmParams p,
+                             cudaStream_t st) {
     constexpr int smem = kStages2 * (kBlockM * kBlockK * 2 + (BLOCK_N / 2) * kBlockK * 2) + kEpiBytes +
                          kStatFloats2 * 4 + 1024 + 256;
     static_assert(smem <= 232448, "shared memory budget");
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BLOCK_N, WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BLOCK_N, WGRAD, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         DLV3P_REQUIRE(e == cudaSuccess, DLV3P_ERR_CUDA, "cudaFuncSetAttribute(2-CTA smem=%d): %s", smem, cudaGetErrorString(e));
         configured = true;
     }
     const int work = p.n_tiles * p.m_tiles * (WGRAD ? p.splits : 1);
     const int pairs = work < kNumSMs / 2 ? work : kNumSMs / 2;
-    launch_pdl(gemm_tc2_kernel<BLOCK_N, WGRAD>, dim3(2 * pairs), dim3(kThreads), smem, st, tmA, tmB, tmC, p);
+    launch_pdl(gemm_tc2_kernel<BLOCK_N, WGRAD, SC>, dim3(2 * pairs), dim3(kThreads), smem, st, tmA, tmB, tmC, p);
     return check_launch("gemm_bf16 (2-CTA)");
+}
+
+template <int BLOCK_N, bool WGRAD>
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
+                        cudaStream_t st) {
+    if constexpr (!WGRAD) {
+        if (p.col_scale != nullptr)
+            return scale_table_ok(p) ? launch_gemm2_inst<BLOCK_N, false, 1>(tmA, tmB, tmC, p, st)
+                                     : launch_gemm2_inst<BLOCK_N, false, 0>(tmA, tmB, tmC, p, st);
+    }
+    return launch_gemm2_inst<BLOCK_N, WGRAD, 2>(tmA, tmB, tmC, p, st);
 }
 
 #ifdef DLV3P_DIAG
