@@ -1270,7 +1270,34 @@ class Plan:
             # decoder tail: handled by _emit_softmax_tail (fused with the loss in training)
             self.values[n.output] = _TailResize(x, fh, fw)
             return
-        out = Value((N, H * fh, W * fw, C), x.dtype, self._alloc((N, H * fh, W * fw, C), x.dtype), n.layer.name)
+        oshape = (N, H * fh, W * fw, C)
+        slot_c = self._concat_slot.get(n.output) if (x.clog == C and x.dtype == self.dt and C % 8 == 0) else None
+        if slot_c is not None and slot_c[1] % 8 == 0:
+            # the resize's only reader is a Concatenate (boundary refinement, ss.py:941-950: the x(OS/2) encoder output and
+            # low-level features, 304 channels at 256^2): written straight into its channel slice (ld_y), gradient read
+            # from the same slice of the concat gradient (ld_dy) — no slice copies of the largest tensors of the model
+            cid, c_off, Ct = slot_c
+            if cid not in self._concat_buf:
+                self._concat_buf[cid] = self._alloc((N, H * fh, W * fw, Ct), self.dt)
+            cbuf = self._concat_buf[cid]
+            out = Value(oshape, x.dtype, cbuf.view(N * H * fh * W * fw, Ct)[:, c_off:c_off + C], n.layer.name)
+            out.concat_slice = True
+            out.clog = x.clog
+            out.needs_grad = self.training
+            self.values[n.output] = out
+            self.fwd.append(lambda: ops.bilinear_fwd(x.buf, fh, fw, out=cbuf, ld_y=Ct, C=C, y_off=c_off))
+            self.launches_fwd += 1
+            self._trace_value(f"{n.layer.name}/out", out.buf, out.clog, oshape)
+            if self.training and x.needs_grad:
+                def sched():
+                    g = self._final_grad(out)                # the [M, C] slice view of the concat gradient
+                    self._trace_grad(f"{n.layer.name}/out", g, out.clog, oshape)
+                    ld_g = g.stride(0) if g.dim() == 2 else C
+                    tgt, add2 = self._grad_target(x)
+                    self.bwd_seq(lambda: ops.bilinear_bwd(g, x.shape, fh, fw, out=tgt, addend=add2, ld_dy=ld_g))
+                self._defer_backward(sched)
+            return
+        out = Value(oshape, x.dtype, self._alloc(oshape, x.dtype), n.layer.name)
         out.clog = x.clog
         out.needs_grad = self.training
         self.values[n.output] = out

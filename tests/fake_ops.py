@@ -497,12 +497,18 @@ def bilinear_fwd(x, fh, fw, out=None, ld_x=None, ld_y=None, C=None, y_off=0, out
     y = _resize(x.float(), fh, fw)
     if out is None:
         return y.to(out_dtype or x.dtype).contiguous()
+    if ld_y is not None and ld_y != y.shape[3]:
+        # channel-slice write into a wider (concat) buffer: rows of ld_y elements, slice starts y_off elements in
+        out.view(-1, ld_y)[:, y_off:y_off + y.shape[3]].copy_(y.reshape(-1, y.shape[3]))
+        return out
     out.copy_(y)
     return out
 
 
 def bilinear_bwd(dy, x_shape, fh, fw, out=None, addend=None, ld_dy=None, ld_dx=None, dy_off=0, out_dtype=None):
     z = torch.zeros(x_shape, dtype=torch.float32, requires_grad=True)
+    if dy.dim() == 2:                                   # [M, C] slice view of a concat gradient (ld_dy = its row pitch)
+        dy = dy.reshape(x_shape[0], x_shape[1] * fh, x_shape[2] * fw, x_shape[3])
     _resize(z, fh, fw).backward(dy.float())
     g = z.grad + (addend.float() if addend is not None else 0)
     out.copy_(g)

@@ -189,6 +189,35 @@ def test_concat_slices_written_in_place(cpu_engine, monkeypatch):
         assert np.abs(ga[k] - gb[k]).max() <= 1e-4 * scale, k
 
 
+def test_boundary_refinement_resizes_write_concat_slices(cpu_engine, monkeypatch):
+    """Boundary refinement (ss.py:915-954): the x(OS/2) resizes of the encoder output and of the low-level features are
+    read only by the Concatenate, so they write their channel slice of the concat buffer directly (bilinear_fwd ld_y)
+    and read their gradient slice in place (bilinear_bwd ld_dy): the four slice copies of the 304-channel tensor go."""
+    conf = util.make_conf(width=64, base="xception", output_stride=8, image_size=49, refine=True, rate_mult=2)
+    ss = util.build(conf)
+    util.randomize_weights(ss.model)
+    calls = []
+    orig = fake_ops.copy2d
+    monkeypatch.setattr(fake_ops, "copy2d", lambda *a, **k: (calls.append((a[1], a[3])), orig(*a, **k))[1])
+    plans = {}
+    for flag in (True, False):
+        calls.clear()
+        plan = cpu_engine.Plan(ss.model, 2, training=True, concat_in_place=flag)
+        x, y = util.synthetic_batch(conf, 2, plan.out_shape[1:3])
+        plan.set_loss(PW, NW)
+        plan.load_batch(x, y)
+        plan.step_fwd_bwd()
+        wide = [c for c in calls if 64 + 48 in c]              # copies into / out of the refinement concat (64 + 48 channels)
+        plans[flag] = (plan, len(wide), plan.gradients())
+    assert plans[False][1] == 4 and plans[True][1] == 0, (plans[True][1], plans[False][1])
+    a, b = plans[True][0], plans[False][0]
+    np.testing.assert_allclose(a.logits.buf.numpy(), b.logits.buf.numpy(), rtol=1e-5, atol=1e-6)
+    ga, gb = plans[True][2], plans[False][2]
+    for k in gb:
+        scale = max(np.abs(gb[k]).max(), 1e-3)
+        assert np.abs(ga[k] - gb[k]).max() <= 1e-4 * scale, k
+
+
 def test_bn_fused_into_maxpool_schedule(cpu_engine, monkeypatch):
     """Conv -> BN -> MaxPooling2D (Xception block2/3/4): the BN output is virtual, the pool applies scale/shift on the fly
     and keeps the raw winners, the producer's backward reduces over the pooled tensors and runs pool backward + BN input
