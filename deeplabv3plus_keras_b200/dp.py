@@ -85,3 +85,74 @@ def run_step_with_exchange(plan, n_buckets: int, group=None) -> None:
     for (a, b), rg in zip(zip(cuts[:-1], cuts[1:]), ranges):
         plan.run_bwd_range(a, b)
         allreduce_ranges(plan.params.g, rg, group)
+
+
+class PeerExchange:
+    """SUM all-reduce of slices of the flat gradient arena WITHOUT SM-resident collective kernels: a reduce-scatter
+    by peer-to-peer pushes into NVLink-mapped (symmetric-memory) staging rows, a local reduction of this rank's slice,
+    and an all-gather by peer-to-peer pulls — the transfers are `cudaMemcpyAsync` between peer-mapped buffers (copy
+    engines over NVLink / NVSwitch), the only kernels are three one-CTA signal barriers and one small row sum.
+
+    Why: every hot kernel of the training step is a persistent one-CTA-per-SM launch with a static tile stride.  An NCCL
+    all-reduce running beside backward puts its CTAs on SMs, the displaced CTAs of the compute kernel run after the
+    others and that kernel's tail doubles: overlapping hid a quarter of the exchange (profiles/r2_scaling.md).  Copy
+    engines take no SM; what is left beside backward is ~120 MB of extra HBM traffic per step.
+
+    Every slice is reduced by exactly ONE rank in a fixed order (rank 0 .. world-1) and then copied to all the others, so
+    the exchanged gradient is bit-identical on every rank, as after an NCCL all-reduce.
+
+    Layout of the symmetric buffer (fp32, per rank): `world` staging rows of `cap` elements (row r = what rank r pushed
+    for MY slices), then one row of `cap` elements with my reduced slices (what the peers pull)."""
+
+    def __init__(self, n: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.cap = -(-n // self.world) + 64                      # two ranges per exchange, each chunk rounded up to 8
+        self.buf = symm.empty((self.world + 1) * self.cap, dtype=torch.float32, device=device)
+        self.hdl = symm.rendezvous(self.buf, self.group.group_name)
+        self.rows = self.buf[:self.world * self.cap].view(self.world, self.cap)
+        self.red = self.buf[self.world * self.cap:]
+
+    def _slices(self, ranges):
+        out, off = [], 0
+        for lo, hi in ranges:
+            L = hi - lo
+            if L <= 0:
+                continue
+            ch = (-(-L // self.world) + 7) // 8 * 8
+            out.append((lo, lo + L, ch, off))
+            off += ch
+        assert off <= self.cap, (off, self.cap)
+        return out
+
+    def all_reduce_(self, g: torch.Tensor, ranges) -> None:
+        """In place on the current stream: g[lo:hi] <- sum over ranks, for every (lo, hi) of `ranges`."""
+        segs = self._slices(ranges)
+        if not segs:
+            return
+        W, me, cap, hdl = self.world, self.rank, self.cap, self.hdl
+        # (no barrier in front: a peer pushes into my rows only after it has passed the closing barrier of the previous
+        # exchange, which I entered after my reduction had read them)
+        for step in range(W):                            # reduce-scatter, push: my contribution to rank r's slices
+            r = (me + step) % W
+            dst = hdl.get_buffer(r, (cap,), torch.float32, me * cap)
+            for lo, end, ch, o in segs:
+                a, b = lo + r * ch, min(lo + (r + 1) * ch, end)
+                if b > a:
+                    dst[o:o + b - a].copy_(g[a:b])
+        hdl.barrier()                                    # every push into my rows has landed
+        for lo, end, ch, o in segs:
+            a, b = lo + me * ch, min(lo + (me + 1) * ch, end)
+            if b > a:
+                torch.sum(self.rows[:, o:o + b - a], dim=0, out=self.red[o:o + b - a])
+                g[a:b].copy_(self.red[o:o + b - a])
+        hdl.barrier()                                    # every rank's reduced slices are in its `red` row
+        for step in range(1, W):                         # all-gather, pull
+            r = (me + step) % W
+            src = hdl.get_buffer(r, (cap,), torch.float32, W * cap)
+            for lo, end, ch, o in segs:
+                a, b = lo + r * ch, min(lo + (r + 1) * ch, end)
+                if b > a:
+                    g[a:b].copy_(src[o:o + b - a])
+        hdl.barrier()                                    # nobody still reads my `red` row when the next exchange starts

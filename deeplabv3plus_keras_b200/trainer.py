@@ -26,9 +26,11 @@ class Trainer:
         after backward on the training stream.  Every hot kernel here is a persistent one-CTA-per-SM launch, so NCCL's
         CTAs displace CTAs of whatever runs beside them and that kernel's tail doubles: overlapping hides nothing
         beyond what it costs, and the tail exchange of a bf16 copy of the gradients (`grad_dtype="bfloat16"`, half
-        the bytes, summed in fp32 per pair by NCCL's bf16 reduction) is the cheaper one (profiles/r2_scaling.md)."""
-        if exchange not in ("overlap", "tail") or grad_dtype not in ("float32", "bfloat16"):
-            raise ValueError("exchange: 'overlap' | 'tail'; grad_dtype: 'float32' | 'bfloat16'")
+        the bytes, summed in fp32 per pair by NCCL's bf16 reduction) is the cheaper one (profiles/r2_scaling.md).
+        "peer" = the overlap schedule with dp.PeerExchange instead of NCCL: peer-to-peer copies over NVLink-mapped
+        symmetric memory on the copy engines (no collective CTAs beside the persistent compute kernels)."""
+        if exchange not in ("overlap", "tail", "peer") or grad_dtype not in ("float32", "bfloat16"):
+            raise ValueError("exchange: 'overlap' | 'tail' | 'peer'; grad_dtype: 'float32' | 'bfloat16'")
         if grad_dtype == "bfloat16" and exchange != "tail":
             raise ValueError("grad_dtype='bfloat16' needs exchange='tail'")
         self.exchange, self.grad_dtype = exchange, grad_dtype
@@ -54,7 +56,9 @@ class Trainer:
         self.stream = torch.cuda.Stream()
         if overlap_wgrad:
             p.side_stream = torch.cuda.Stream()
-        self.comm_stream = torch.cuda.Stream() if (self.world > 1 and exchange == "overlap") else None
+        self.comm_stream = torch.cuda.Stream(priority=-1) if (self.world > 1 and exchange in ("overlap", "peer")) else None
+        self.peer = dp.PeerExchange(p.params.n_train, p.device, process_group) \
+            if (self.world > 1 and exchange == "peer") else None
         self._g16 = torch.empty(p.params.n_train, dtype=torch.bfloat16, device=p.device) \
             if (self.world > 1 and grad_dtype == "bfloat16") else None
         self._segments: List = []          # (graph or callable, grad-arena range completed by it)
@@ -72,7 +76,7 @@ class Trainer:
         self.stage_y = torch.empty(tuple(p.labels.shape), dtype=torch.int32, device=p.device)
         self._staged = None                # event: staging buffers hold a complete batch
         self._stage_free = None            # event: the training stream has consumed the staging buffers
-        self._build(buckets if (self.world > 1 and exchange == "overlap") else 1)
+        self._build(buckets if (self.world > 1 and exchange in ("overlap", "peer")) else 1)
 
     # ------------------------------------------------------------------------------------------------------
     def _build(self, n_buckets: int):
@@ -158,9 +162,9 @@ class Trainer:
             p.ensure_current()                  # another plan of the model stepped, or weights were set / loaded
             for part, ranges in zip(self._parts, self._ranges):
                 part()
-                if self.world > 1 and ranges and self.exchange == "overlap":
+                if self.world > 1 and ranges and self.exchange in ("overlap", "peer"):
                     self._exchange(ranges)      # all-reduce what this segment finished while the next one runs
-            if self.world > 1 and self.exchange == "overlap":
+            if self.world > 1 and self.exchange in ("overlap", "peer"):
                 self.stream.wait_event(self._comm_done)
             elif self.world > 1:
                 self._exchange_tail()
@@ -175,7 +179,10 @@ class Trainer:
         ev.record(self.stream)
         self.comm_stream.wait_event(ev)
         with torch.cuda.stream(self.comm_stream):
-            dp.allreduce_ranges(g, ranges, self.pg)
+            if self.peer is not None:
+                self.peer.all_reduce_(g, ranges)
+            else:
+                dp.allreduce_ranges(g, ranges, self.pg)
             self._comm_done = torch.cuda.Event()
             self._comm_done.record(self.comm_stream)
 
