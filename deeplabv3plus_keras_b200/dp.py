@@ -131,28 +131,42 @@ class PeerExchange:
         segs = self._slices(ranges)
         if not segs:
             return
-        W, me, cap, hdl = self.world, self.rank, self.cap, self.hdl
         # (no barrier in front: a peer pushes into my rows only after it has passed the closing barrier of the previous
         # exchange, which I entered after my reduction had read them)
-        for step in range(W):                            # reduce-scatter, push: my contribution to rank r's slices
+        self._push(g, segs)
+        self.hdl.barrier()                               # every push into my rows has landed
+        self._reduce(g, segs)
+        self.hdl.barrier()                               # every rank's reduced slices are in its `red` row
+        self._pull(g, segs)
+        self.hdl.barrier()                               # nobody still reads my `red` row when the next exchange starts
+
+    def _push(self, g, segs):
+        """reduce-scatter, push: my contribution to rank r's slices into row `me` of rank r's staging rows"""
+        W, me, cap = self.world, self.rank, self.cap
+        for step in range(W):
             r = (me + step) % W
-            dst = hdl.get_buffer(r, (cap,), torch.float32, me * cap)
+            dst = self.hdl.get_buffer(r, (cap,), torch.float32, me * cap)
             for lo, end, ch, o in segs:
                 a, b = lo + r * ch, min(lo + (r + 1) * ch, end)
                 if b > a:
                     dst[o:o + b - a].copy_(g[a:b])
-        hdl.barrier()                                    # every push into my rows has landed
+
+    def _reduce(self, g, segs):
+        """my slices: sum of the staging rows in rank order -> `red` row and my own arena"""
+        me = self.rank
         for lo, end, ch, o in segs:
             a, b = lo + me * ch, min(lo + (me + 1) * ch, end)
             if b > a:
                 torch.sum(self.rows[:, o:o + b - a], dim=0, out=self.red[o:o + b - a])
                 g[a:b].copy_(self.red[o:o + b - a])
-        hdl.barrier()                                    # every rank's reduced slices are in its `red` row
-        for step in range(1, W):                         # all-gather, pull
+
+    def _pull(self, g, segs):
+        """all-gather, pull: every other rank's reduced slices out of its `red` row"""
+        W, me, cap = self.world, self.rank, self.cap
+        for step in range(1, W):
             r = (me + step) % W
-            src = hdl.get_buffer(r, (cap,), torch.float32, W * cap)
+            src = self.hdl.get_buffer(r, (cap,), torch.float32, W * cap)
             for lo, end, ch, o in segs:
                 a, b = lo + r * ch, min(lo + (r + 1) * ch, end)
                 if b > a:
                     g[a:b].copy_(src[o:o + b - a])
-        hdl.barrier()                                    # nobody still reads my `red` row when the next exchange starts

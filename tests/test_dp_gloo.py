@@ -96,3 +96,51 @@ def test_bucket_ranges_cover_and_align():
             assert all(lo % 8 == 0 for lo, _ in r)
     with pytest.raises(ValueError):
         dp.shard_bounds(10, 0, 4)
+
+
+def test_peer_exchange_schedule_in_lockstep():
+    """dp.PeerExchange (copy-engine all-reduce over symmetric memory): its push / reduce / pull phases executed in
+    lockstep for W simulated ranks over plain tensors — every element of every range ends up as the sum over ranks on
+    every rank (bit-identical across ranks: one rank reduces each slice), elements outside the ranges are untouched,
+    ragged ranges (length not a multiple of W or 8, shorter than W) included."""
+    import torch
+    from deeplabv3plus_keras_b200 import dp
+
+    for W in (2, 3, 8):
+        n = 1000
+        cap = -(-n // W) + 64
+        bufs = [torch.full(((W + 1) * cap,), float("nan")) for _ in range(W)]
+
+        class Hdl:
+            def get_buffer(self, r, sizes, dtype, off):
+                return bufs[r][off:off + sizes[0]]
+
+            def barrier(self):
+                pass
+
+        xs = []
+        for r in range(W):
+            x = object.__new__(dp.PeerExchange)
+            x.world, x.rank, x.cap, x.hdl, x.buf = W, r, cap, Hdl(), bufs[r]
+            x.rows, x.red = bufs[r][:W * cap].view(W, cap), bufs[r][W * cap:]
+            xs.append(x)
+        gen = torch.Generator().manual_seed(W)
+        gs = [torch.randn(n, generator=gen) for _ in range(W)]
+        ref = torch.stack(gs).sum(0)
+        for ranges in ([(0, 13), (500, 777)], [(13, 500), (777, 1000)], [(3, 5), (0, 0)], [(0, 0), (990, 997)]):
+            before = [g.clone() for g in gs]
+            segs = [x._slices(ranges) for x in xs]
+            for x, g, sg in zip(xs, gs, segs):
+                x._push(g, sg)
+            for x, g, sg in zip(xs, gs, segs):
+                x._reduce(g, sg)
+            for x, g, sg in zip(xs, gs, segs):
+                x._pull(g, sg)
+            inside = torch.zeros(n, dtype=torch.bool)
+            for lo, hi in ranges:
+                inside[lo:hi] = True
+            want = torch.stack(before).sum(0)
+            for r in range(W):
+                assert torch.equal(gs[r][~inside], before[r][~inside])
+                assert torch.equal(gs[r][inside], gs[0][inside])                       # identical on every rank
+                assert torch.allclose(gs[r][inside], want[inside], rtol=1e-6, atol=1e-6)
