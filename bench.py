@@ -426,7 +426,8 @@ def run_check(args, rank, local_rank, world):
         ss = build_model(conf)
         ss.model.optimizer.lr = 1e-3
         tr = Trainer(ss.model, B, process_group=dist.group.WORLD if mode == "dp" else None, buckets=args.buckets,
-                     exchange=args.exchange, grad_dtype=args.grad_dtype if mode == "dp" else "float32")
+                     exchange=args.exchange, grad_dtype=args.grad_dtype if mode == "dp" else "float32",
+                     cut_events=args.cut_events)
         x, y = synthetic(conf, B, tr.plan.out_shape[1:3], 4242)     # the same batch on every rank
         xs, ys = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
         P = tr.plan.params
@@ -490,13 +491,16 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the config's)")
     ap.add_argument("--dtype", default="", help="override the config's dtype (float32 | bfloat16)")
     ap.add_argument("--buckets", type=int, default=4, help="gradient all-reduce slices behind backward (N>1)")
-    ap.add_argument("--exchange", default="overlap", choices=["overlap", "tail", "peer"],
+    ap.add_argument("--exchange", default="overlap", choices=["overlap", "tail", "peer", "none"],
                     help="N>1: all-reduce prefix slices behind backward segments | one all-reduce after backward")
     ap.add_argument("--grad-dtype", default="float32", choices=["float32", "bfloat16"],
                     help="N>1, --exchange tail: dtype of the exchanged gradient copy")
     ap.add_argument("--check-dtype", default="float32", help="--check: float32 (reproducible) | bfloat16")
     ap.add_argument("--check", action="store_true", help="data-parallel correctness check (launch under torchrun)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--cut-events", action="store_true",
+                    help="N>1: one CUDA graph for the whole step, segment cuts marked by external events (A/B; default: "
+                         "one graph per backward segment)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--profile-json", default="")
@@ -539,7 +543,8 @@ def main():
     train = cfg["train"]
     if train:
         tr = Trainer(ss.model, batch, use_graph=not args.no_graph, process_group=pg, overlap_wgrad=not args.no_overlap,
-                     buckets=args.buckets, exchange=args.exchange, grad_dtype=args.grad_dtype)
+                     buckets=args.buckets, exchange=args.exchange, grad_dtype=args.grad_dtype,
+                     cut_events=args.cut_events)
     else:
         tr = Predictor(ss.model, batch, dtype=args.dtype, use_graph=not args.no_graph)
     plan = tr.plan

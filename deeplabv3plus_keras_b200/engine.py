@@ -1124,7 +1124,10 @@ class Plan:
                     b = off + size
         return a, b
 
-    def run_bwd_range(self, a: int, b: int):
+    def run_bwd_range(self, a: int, b: int, join: bool = True, pending=None):
+        """Launch backward[a:b].  `join=False` leaves the side stream un-joined at the end and returns its open events
+        (pass them back as `pending` to the call that continues the range): the data-parallel step captures all its
+        segments in ONE graph and only marks the cuts with external events (Trainer)."""
         side = self.side_stream
         if side is None:
             for fn, _, _ in self.bwd[a:b]:
@@ -1132,7 +1135,7 @@ class Plan:
                     fn()
             return
         main = torch.cuda.current_stream()
-        pending: Dict[int, torch.cuda.Event] = {}
+        pending = {} if pending is None else pending
         for fn, on_side, slot in self.bwd[a:b]:
             if fn is None:                                   # macro-op boundary: it is about to overwrite scratch `slot`
                 ev = pending.pop(slot, None)
@@ -1150,8 +1153,11 @@ class Plan:
                 pending[slot if slot is not None else -1] = done
             else:
                 fn()
+        if not join:
+            return pending
         for ev in pending.values():                          # join: the gradient arena is complete after this range
             main.wait_event(ev)
+        return {}
 
     # ---- other ops ---------------------------------------------------------------------------------------
     def _emit_maxpool(self, m: dict):

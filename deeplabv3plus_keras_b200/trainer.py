@@ -20,7 +20,7 @@ from .engine import Plan
 class Trainer:
     def __init__(self, model, batch_size: int, dtype: Optional[str] = None, use_graph: bool = True,
                  buckets: int = 4, process_group=None, fused_tail: bool = True, overlap_wgrad: bool = True,
-                 exchange: str = "overlap", grad_dtype: str = "float32"):
+                 exchange: str = "overlap", grad_dtype: str = "float32", cut_events: bool = False):
         """`exchange` (world > 1): "overlap" = the arena prefixes each backward segment finished are all-reduced on a
         communication stream while the next segment runs (`buckets` segments); "tail" = ONE all-reduce of the whole arena
         after backward on the training stream.  Every hot kernel here is a persistent one-CTA-per-SM launch, so NCCL's
@@ -29,11 +29,21 @@ class Trainer:
         the bytes, summed in fp32 per pair by NCCL's bf16 reduction) is the cheaper one (profiles/r2_scaling.md).
         "peer" = the overlap schedule with dp.PeerExchange instead of NCCL: peer-to-peer copies over NVLink-mapped
         symmetric memory on the copy engines (no collective CTAs beside the persistent compute kernels)."""
-        if exchange not in ("overlap", "tail", "peer") or grad_dtype not in ("float32", "bfloat16"):
-            raise ValueError("exchange: 'overlap' | 'tail' | 'peer'; grad_dtype: 'float32' | 'bfloat16'")
+        if exchange not in ("overlap", "tail", "peer", "none") or grad_dtype not in ("float32", "bfloat16"):
+            raise ValueError("exchange: 'overlap' | 'tail' | 'peer' | 'none'; grad_dtype: 'float32' | 'bfloat16'")
+        # ("none": independent replicas, NO gradient exchange — a measurement aid only: what N ranks stepping side by side
+        # cost by themselves, i.e. the slowest GPU of the box and the max-over-ranks of the timing, before any collective)
         if grad_dtype == "bfloat16" and exchange != "tail":
             raise ValueError("grad_dtype='bfloat16' needs exchange='tail'")
         self.exchange, self.grad_dtype = exchange, grad_dtype
+        # cut_events (world > 1, overlap / peer, CUDA graphs; off by default): ONE graph for the whole step as on one GPU —
+        # no per-segment graph launches, no side-stream join at the cuts; the segment ends are marked inside it by EXTERNAL
+        # events (event-record nodes) on the training and the filter-gradient streams, and the communication stream, outside
+        # the graph, waits for them before it exchanges the slices that segment completed.  Correct (`bench.py --check
+        # --cut-events`) but no faster than one graph per segment (8.34 vs 8.29-8.32 ms at N=2; 8.13 on one GPU or with
+        # two replicas that never exchange): the cost of the data-parallel step is neither the graph cuts nor — the peer
+        # exchange runs on copy engines and costs the same — NCCL's CTAs; it was not located this round (DESIGN §10)
+        self.cut_events = cut_events
         # (measured at N=2: NCCL kernels and copy engines cost the same 0.18 ms per step — 8.32 / 8.31 ms against 8.13 on one
         # GPU — so what the data-parallel step pays is the segmentation itself: a graph launch and a side-stream join per
         # segment.  Capturing the whole step with the exchanges forked inside ONE graph was tried and dropped: slower
@@ -97,6 +107,26 @@ class Trainer:
 
         parts = [head] + [(lambda a=a, b=b: p.run_bwd_range(a, b)) for a, b in zip(cuts[:-1], cuts[1:])]
         self._ranges: List = [[]] + ranges             # nothing to exchange after the head
+        self._cuts = None
+        if self.use_graph and n_buckets > 1 and self.cut_events:
+            segs = list(zip(cuts[:-1], cuts[1:]))
+            marks = [(torch.cuda.Event(external=True),
+                      torch.cuda.Event(external=True) if p.side_stream is not None else None) for _ in segs[:-1]]
+
+            def whole():
+                head()
+                pend = None
+                for i, (a, b) in enumerate(segs):
+                    last = i == len(segs) - 1
+                    pend = p.run_bwd_range(a, b, join=last, pending=pend)
+                    if not last:
+                        em, es = marks[i]
+                        em.record(self.stream)                       # everything the training stream launched so far
+                        if es is not None:
+                            es.record(p.side_stream)                 # ... and the filter-gradient kernels launched so far
+            parts = [whole]
+            self._cuts = (marks, ranges)
+            self._ranges = [[]]
 
         if self.use_graph:
             # warm-up outside capture (lazy module loading, cudaFuncSetAttribute) on the capture stream
@@ -168,20 +198,30 @@ class Trainer:
                 part()
                 if self.world > 1 and ranges and self.exchange in ("overlap", "peer"):
                     self._exchange(ranges)      # all-reduce what this segment finished while the next one runs
+            if self._cuts is not None:
+                marks, ranges = self._cuts
+                for (em, es), rg in zip(marks, ranges[:-1]):
+                    self._exchange(rg, after=(em, es))      # waits for the cut marks recorded inside the running graph
+                self._exchange(ranges[-1])                  # the rest, once the graph has completed
             if self.world > 1 and self.exchange in ("overlap", "peer"):
                 self.stream.wait_event(self._comm_done)
-            elif self.world > 1:
+            elif self.world > 1 and self.exchange == "tail":
                 self._exchange_tail()
             if optimizer_step:
                 p.regularization()
                 self._adam()
                 self._prep()
 
-    def _exchange(self, ranges):
+    def _exchange(self, ranges, after=None):
         g = self.plan.params.g
-        ev = torch.cuda.Event()
-        ev.record(self.stream)
-        self.comm_stream.wait_event(ev)
+        if after is None:
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+            self.comm_stream.wait_event(ev)
+        else:
+            for ev in after:
+                if ev is not None:
+                    self.comm_stream.wait_event(ev)
         with torch.cuda.stream(self.comm_stream):
             if self.peer is not None:
                 self.peer.all_reduce_(g, ranges)
