@@ -457,7 +457,7 @@ def run_check(args, rank, local_rank, world):
         floor_g, floor_l = rel(g_2, g_1), float(np.max(np.abs(l_2 - l_1) / np.abs(l_1)))
         floor_u = float((w_2 - w_1).norm() / (w_1 - w0).norm().clamp_min(1e-30))
         out = {"check": "data-parallel == single GPU on the same batch", "n_gpus": world, "steps": K, "dtype": dtype,
-               "exchange": f"{args.exchange}/{args.grad_dtype}" + (f"/{args.buckets} buckets" if args.exchange in ("overlap", "peer") else ""),
+               "exchange": f"{args.exchange}/{args.grad_dtype}" + (f"/{args.buckets} buckets" if args.exchange in ("overlap", "peer", "gather") else ""),
                "loss_dp": l_dp.tolist(), "loss_single": l_1.tolist(),
                "first_gradient_rms_rel_diff": rel(g_dp / world, g_1),
                "max_rel_loss_diff": float(np.max(np.abs(l_dp - l_1) / np.abs(l_1))),
@@ -491,7 +491,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the config's)")
     ap.add_argument("--dtype", default="", help="override the config's dtype (float32 | bfloat16)")
     ap.add_argument("--buckets", type=int, default=4, help="gradient all-reduce slices behind backward (N>1)")
-    ap.add_argument("--exchange", default="overlap", choices=["overlap", "tail", "peer", "none"],
+    ap.add_argument("--exchange", default="overlap", choices=["overlap", "tail", "peer", "gather", "none"],
                     help="N>1: all-reduce prefix slices behind backward segments | one all-reduce after backward")
     ap.add_argument("--grad-dtype", default="float32", choices=["float32", "bfloat16"],
                     help="N>1, --exchange tail: dtype of the exchanged gradient copy")
@@ -619,7 +619,7 @@ def main():
         "dtype": "bf16" if args.dtype == "bfloat16" else "f32", "data": "synthetic",
         "config": {"workload": cfg["workload"].format(batch=batch), "name": args.config,
                    "global_batch": batch * world, "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
-                   "exchange": (f"{args.exchange}/{args.grad_dtype}" + (f"/{args.buckets} buckets" if args.exchange in ("overlap", "peer") else ""))
+                   "exchange": (f"{args.exchange}/{args.grad_dtype}" + (f"/{args.buckets} buckets" if args.exchange in ("overlap", "peer", "gather") else ""))
                    if world > 1 else None,
                    "l2_policy": "per-step working set (GBs of activations) far exceeds the 126 MB L2"},
         "clocks": clocks, "loss": loss,

@@ -29,8 +29,10 @@ class Trainer:
         the bytes, summed in fp32 per pair by NCCL's bf16 reduction) is the cheaper one (profiles/r2_scaling.md).
         "peer" = the overlap schedule with dp.PeerExchange instead of NCCL: peer-to-peer copies over NVLink-mapped
         symmetric memory on the copy engines (no collective CTAs beside the persistent compute kernels)."""
-        if exchange not in ("overlap", "tail", "peer", "none") or grad_dtype not in ("float32", "bfloat16"):
-            raise ValueError("exchange: 'overlap' | 'tail' | 'peer' | 'none'; grad_dtype: 'float32' | 'bfloat16'")
+        if exchange not in ("overlap", "tail", "peer", "gather", "none") or grad_dtype not in ("float32", "bfloat16"):
+            raise ValueError("exchange: 'overlap' | 'tail' | 'peer' | 'gather' | 'none'; grad_dtype: 'float32' | 'bfloat16'")
+        # "gather" = dp.GatherExchange: copy-engine pushes of every finished slice to all peers behind backward, one barrier
+        # and one row sum after it — nothing SM-resident beside the persistent compute kernels
         # ("none": independent replicas, NO gradient exchange — a measurement aid only: what N ranks stepping side by side
         # cost by themselves, i.e. the slowest GPU of the box and the max-over-ranks of the timing, before any collective)
         if grad_dtype == "bfloat16" and exchange != "tail":
@@ -70,7 +72,9 @@ class Trainer:
         self.stream = torch.cuda.Stream()
         if overlap_wgrad:
             p.side_stream = torch.cuda.Stream()
-        self.comm_stream = torch.cuda.Stream(priority=-1) if (self.world > 1 and exchange in ("overlap", "peer")) else None
+        self.comm_stream = torch.cuda.Stream(priority=-1) if (self.world > 1 and exchange in ("overlap", "peer", "gather")) else None
+        self.gather = dp.GatherExchange(p.params.n_train, p.device, process_group) \
+            if (self.world > 1 and exchange == "gather") else None
         self.peer = dp.PeerExchange(p.params.n_train, p.device, process_group) \
             if (self.world > 1 and exchange == "peer") else None
         self._g16 = torch.empty(p.params.n_train, dtype=torch.bfloat16, device=p.device) \
@@ -90,7 +94,7 @@ class Trainer:
         self.stage_y = torch.empty(tuple(p.labels.shape), dtype=torch.int32, device=p.device)
         self._staged = None                # event: staging buffers hold a complete batch
         self._stage_free = None            # event: the training stream has consumed the staging buffers
-        self._build(buckets if (self.world > 1 and exchange in ("overlap", "peer")) else 1)
+        self._build(buckets if (self.world > 1 and exchange in ("overlap", "peer", "gather")) else 1)
 
     # ------------------------------------------------------------------------------------------------------
     def _build(self, n_buckets: int):
@@ -196,14 +200,19 @@ class Trainer:
             p.ensure_current()                  # another plan of the model stepped, or weights were set / loaded
             for part, ranges in zip(self._parts, self._ranges):
                 part()
-                if self.world > 1 and ranges and self.exchange in ("overlap", "peer"):
+                if self.world > 1 and ranges and self.exchange in ("overlap", "peer", "gather"):
                     self._exchange(ranges)      # all-reduce what this segment finished while the next one runs
             if self._cuts is not None:
                 marks, ranges = self._cuts
                 for (em, es), rg in zip(marks, ranges[:-1]):
                     self._exchange(rg, after=(em, es))      # waits for the cut marks recorded inside the running graph
                 self._exchange(ranges[-1])                  # the rest, once the graph has completed
-            if self.world > 1 and self.exchange in ("overlap", "peer"):
+            if self.world > 1 and self.exchange == "gather":
+                with torch.cuda.stream(self.comm_stream):
+                    self.gather.finish_(self.plan.params.g)
+                    self._comm_done = torch.cuda.Event()
+                    self._comm_done.record(self.comm_stream)
+            if self.world > 1 and self.exchange in ("overlap", "peer", "gather"):
                 self.stream.wait_event(self._comm_done)
             elif self.world > 1 and self.exchange == "tail":
                 self._exchange_tail()
@@ -225,6 +234,8 @@ class Trainer:
         with torch.cuda.stream(self.comm_stream):
             if self.peer is not None:
                 self.peer.all_reduce_(g, ranges)
+            elif self.gather is not None:
+                self.gather.push_(g, ranges)
             else:
                 dp.allreduce_ranges(g, ranges, self.pg)
             self._comm_done = torch.cuda.Event()

@@ -144,3 +144,40 @@ def test_peer_exchange_schedule_in_lockstep():
                 assert torch.equal(gs[r][~inside], before[r][~inside])
                 assert torch.equal(gs[r][inside], gs[0][inside])                       # identical on every rank
                 assert torch.allclose(gs[r][inside], want[inside], rtol=1e-6, atol=1e-6)
+
+
+def test_gather_exchange_schedule_in_lockstep():
+    """dp.GatherExchange: every rank pushes its slices into row `rank` of every rank's staging buffer, then each sums the
+    rows in rank order — simulated for W ranks over plain tensors: the arena ends up as the sum over ranks, bit-identical
+    on every rank, whatever the slicing of the pushes."""
+    import torch
+    from deeplabv3plus_keras_b200 import dp
+
+    for W in (2, 5):
+        n = 777
+        bufs = [torch.full((W * n,), float("nan")) for _ in range(W)]
+
+        class Hdl:
+            def barrier(self):
+                pass
+
+        xs = []
+        for r in range(W):
+            x = object.__new__(dp.GatherExchange)
+            x.world, x.rank, x.n, x.hdl, x.buf = W, r, n, Hdl(), bufs[r]
+            x.rows = bufs[r].view(W, n)
+            x._mine = [bufs[q][r * n:(r + 1) * n] for q in range(W)]
+            xs.append(x)
+        gen = torch.Generator().manual_seed(W)
+        gs = [torch.randn(n + 5, generator=gen) for _ in range(W)]           # 5 trailing elements outside the arena
+        want = torch.stack([g[:n] for g in gs]).sum(0)
+        tails = [g[n:].clone() for g in gs]
+        for ranges in ([(0, 100), (400, 500)], [(100, 400), (500, 700)], [(0, 0), (700, 777)]):
+            for x, g in zip(xs, gs):
+                x.push_(g, ranges)
+        for x, g in zip(xs, gs):
+            x.finish_(g)
+        for r in range(W):
+            assert torch.equal(gs[r][:n], gs[0][:n])
+            assert torch.allclose(gs[r][:n], want, rtol=1e-6, atol=1e-6)
+            assert torch.equal(gs[r][n:], tails[r])
