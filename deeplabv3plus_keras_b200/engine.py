@@ -1387,11 +1387,11 @@ class Plan:
         else:
             logits, f = src, 1
         if logits.dtype != torch.float32:
-            raise NotImplementedError("decoder tail expects fp32 logits (num_classes not a multiple of 8)")
+            raise NotImplementedError("decoder tail expects fp32 logits: the class-score convolution must not be followed by BatchNormalization (ss.py:893-897)")
         self.logits, self.tail_factor = logits, f
         N, H, W, C = logits.shape
         if C > 32:
-            raise NotImplementedError("softmax tail supports up to 32 classes")
+            raise NotImplementedError("softmax tail supports up to 32 classes (one warp lane per class; VOC 21 / Cityscapes 19)")
         self.out_shape = (N, H * f, W * f, C)
         self.labels = self._alloc((N, H * f, W * f), torch.int32, zero=True)
         self.loss_sum = torch.zeros(1, dtype=torch.float32, device=self.device)
