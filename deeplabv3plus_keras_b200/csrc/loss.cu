@@ -269,19 +269,31 @@ __device__ __forceinline__ float fast_log(float x) {
     return y * 0.6931471805599453f;
 }
 
-// EXACT: C == CMAX, the class loops carry no `c < C` predicates
-template <int CMAX, bool FWD, bool BWD, bool EXACT>
-__global__ void __launch_bounds__(256)
-tail_pixel_kernel(const float* __restrict__ zl, const int32_t* __restrict__ labels, const float* __restrict__ pw,
-                  const float* __restrict__ nw, float eps, int N, int H, int W, int C, int f, float gscale,
-                  float* __restrict__ loss_sum, float* __restrict__ dzl, int nby, int nbx) {
+__device__ __forceinline__ float fast_lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// One 16x16 tile of output pixels.  EXACT: C == CMAX, the class loops carry no `c < C` predicates.  F: the resize factor as
+// a compile-time constant (2 / 4 / 8 / 16) — S = 16/F sub-tiles per side, (S+1)^2 corners; with F a runtime value the two
+// reduction loops below (trip count f) and the divisions by S+1 were 45 % of the kernel's instructions at x2 and the ALU
+// pipe its busiest unit (profiles/r2_tail_ncu.md).
+template <int CMAX, bool FWD, bool BWD, bool EXACT, int F>
+__device__ __forceinline__ void
+tail_pixel_tile(float* __restrict__ sm, const float* __restrict__ zl, const int32_t* __restrict__ labels,
+                const float* __restrict__ pw, const float* __restrict__ nw, float eps, int H, int W, int C, float gscale,
+                float* __restrict__ loss_sum, float* __restrict__ dzl, int nby, int nbx) {
     constexpr int CS = CMAX | 1;                    // odd class stride: conflict-free per-pixel rows in smem
-    extern __shared__ float sm[];
-    const int S = 16 / f;
-    const int PS = S + 1;
+    constexpr int S = 16 / F, PS = S + 1;
+    constexpr int LF = (F == 2) ? 1 : (F == 4) ? 2 : (F == 8) ? 3 : 4, LS = 4 - LF;
     float* patch = sm;                              // [PS][PS][CS]   corner logits
-    float* G = patch + PS * PS * CS;                // [PS][PS][CS]   corner gradient accumulators
-    float* spw = G + PS * PS * CS;                  // [32]
+    float* spw = patch + PS * PS * CS;              // [32]
     float* snw = spw + 32;                          // [32]
     float* wtab = snw + 32;                         // [2][16]        lerp weights of the gradient reduction: 1-l, l
     float* D = wtab + 32;                           // [256][CS]      per-pixel logit gradients
@@ -292,31 +304,30 @@ tail_pixel_kernel(const float* __restrict__ zl, const int32_t* __restrict__ labe
     const int bx = b % nbx; b /= nbx;
     const int by = b % nby;
     const int n = b / nby;
-    const int Ho = H * f, Wo = W * f;
+    const int Ho = H * F, Wo = W * F;
     const int ly0 = S * by - 1, lx0 = S * bx - 1;   // low-res coordinates of patch row/col 0 (before clamping)
 
     for (int i = tid; i < PS * PS * CS; i += 256) {
         const int c = i % CS;
         const int r = i / CS;
-        const int pr = r / PS, pc = r % PS;
+        const int pr = r / PS, pc = r - pr * PS;
         const int yy = min(max(ly0 + pr, 0), H - 1), xx = min(max(lx0 + pc, 0), W - 1);
         patch[i] = (c < C) ? __ldg(zl + (((long long)n * H + yy) * W + xx) * C + c) : 0.f;
-        if (BWD) G[i] = 0.f;
     }
     if (tid < 32) {
         spw[tid] = tid < C ? __ldg(pw + tid) : 0.f; snw[tid] = tid < C ? __ldg(nw + tid) : 0.f;
-        const float l = ((float)(tid & 15) + 0.5f) / (float)f;
+        const float l = ((float)(tid & 15) + 0.5f) * (1.f / (float)F);
         wtab[tid] = (tid & 16) ? l : 1.f - l;
     }
     __syncthreads();
 
     const int py = tid >> 4, px = tid & 15;
-    const int yo = 16 * by + py - f / 2, xo = 16 * bx + px - f / 2;
+    const int yo = 16 * by + py - F / 2, xo = 16 * bx + px - F / 2;
     const bool valid = (yo >= 0 && yo < Ho && xo >= 0 && xo < Wo);
-    const int sy = py / f, sx = px / f;
-    const float inv_f = 1.f / (float)f;
-    const float ly = ((float)(py - sy * f) + 0.5f) * inv_f;     // TF half-pixel lerp: frac((o+0.5)/f - 0.5)
-    const float lx = ((float)(px - sx * f) + 0.5f) * inv_f;
+    const int sy = py >> LF, sx = px >> LF;
+    constexpr float inv_f = 1.f / (float)F;
+    const float ly = ((float)(py & (F - 1)) + 0.5f) * inv_f;     // TF half-pixel lerp: frac((o+0.5)/f - 0.5)
+    const float lx = ((float)(px & (F - 1)) + 0.5f) * inv_f;
     float loss_acc = 0.f;
     float d[CMAX];
     if (valid) {
@@ -341,27 +352,29 @@ tail_pixel_kernel(const float* __restrict__ zl, const int32_t* __restrict__ labe
             z[c] = (EXACT || c < C) ? fast_exp2((z[c] - m) * 1.4426950408889634f) : 0.f;
             s += z[c];
         }
-        const float inv = __fdividef(1.f, s);
+        const float inv = fast_rcp(s);              // s in [1, C]
         const int lab = __ldg(labels + ((long long)n * Ho + yo) * Wo + xo);
-        float dot = 0.f;
+        float dot = 0.f, lg_acc = 0.f;
 #pragma unroll
         for (int c = 0; c < CMAX; ++c) {
             if (EXACT || c < C) {
+                // -(pw*y*log(p+eps) + nw*(1-y)*log(1-p+eps)), y one-hot: one weight, one log argument per class; the
+                // gradient w.r.t. p is -+w / arg — ONE reciprocal of the selected argument (arg in [eps, 1+eps]; the two
+                // __fdividef of both branches were 21 % of the x16 kernel's instructions)
                 const float p = z[c] * inv;
                 const bool hit = (c == lab);
-                if (FWD) {
-                    // -(pw*y*log(p+eps) + nw*(1-y)*log(1-p+eps)), y one-hot
-                    const float arg = hit ? (p + eps) : (1.f - p + eps);
-                    loss_acc -= (hit ? spw[c] : snw[c]) * fast_log(arg);
-                }
+                const float w = hit ? spw[c] : snw[c];
+                const float arg = (hit ? p : 1.f - p) + eps;
+                if (FWD) lg_acc = fmaf(w, fast_lg2(arg), lg_acc);
                 if (BWD) {
-                    const float g = hit ? -__fdividef(spw[c], p + eps) : __fdividef(snw[c], 1.f - p + eps);
+                    const float g = (hit ? -w : w) * fast_rcp(arg);
                     dot = fmaf(g, p, dot);
                     d[c] = g;
                     z[c] = p;
                 }
             }
         }
+        if (FWD) loss_acc = -0.6931471805599453f * lg_acc;
         if (BWD) {
 #pragma unroll
             for (int c = 0; c < CMAX; ++c) d[c] = (EXACT || c < C) ? gscale * z[c] * (d[c] - dot) : 0.f;
@@ -377,8 +390,6 @@ tail_pixel_kernel(const float* __restrict__ zl, const int32_t* __restrict__ labe
     for (int c = 0; c < CMAX; ++c) D[tid * CS + c] = d[c];
     __syncthreads();
     // phase A: reduce over x inside each sub-tile: R[py][sx][kx][c] = sum_px D[py][px][c] * (kx ? lx : 1-lx)
-    // (f and S = 16/f are powers of two: shifts; the class count is a compile-time constant in the EXACT instantiation)
-    const int lf = __ffs(f) - 1, lS = 4 - lf;
     const int Cc = EXACT ? CMAX : C;
     const int itemsA = 16 * S * 2 * Cc;
     for (int i = tid; i < itemsA; i += 256) {
@@ -386,11 +397,12 @@ tail_pixel_kernel(const float* __restrict__ zl, const int32_t* __restrict__ labe
         int r = i / Cc;
         const int kx = r & 1; r >>= 1;
         const int ssx = r & (S - 1);
-        const int ppy = r >> lS;
+        const int ppy = r >> LS;
         float acc = 0.f;
-        const float* dp = D + (ppy * 16 + (ssx << lf)) * CS + c;
+        const float* dp = D + (ppy * 16 + (ssx << LF)) * CS + c;
         const float* wp = wtab + kx * 16;
-        for (int j = 0; j < f; ++j) acc = fmaf(dp[j * CS], wp[j], acc);
+#pragma unroll
+        for (int j = 0; j < F; ++j) acc = fmaf(dp[j * CS], wp[j], acc);
         R[((ppy * S + ssx) * 2 + kx) * CS + c] = acc;
     }
     __syncthreads();
@@ -413,9 +425,10 @@ tail_pixel_kernel(const float* __restrict__ zl, const int32_t* __restrict__ labe
             for (int kx = 0; kx < 2; ++kx) {
                 const int ssx = cx - kx;
                 if (ssx < 0 || ssx >= S) continue;
-                const float* rp = R + ((((ssy << lf) * S) + ssx) * 2 + kx) * CS + c;
+                const float* rp = R + ((((ssy << LF) * S) + ssx) * 2 + kx) * CS + c;
                 float acc = 0.f;
-                for (int j = 0; j < f; ++j) acc = fmaf(rp[j * S * 2 * CS], wp[j], acc);
+#pragma unroll
+                for (int j = 0; j < F; ++j) acc = fmaf(rp[j * S * 2 * CS], wp[j], acc);
                 v += acc;
             }
         }
@@ -424,6 +437,23 @@ tail_pixel_kernel(const float* __restrict__ zl, const int32_t* __restrict__ labe
             atomicAdd(dzl + (((long long)n * H + yy) * W + xx) * C + c, v);
         }
     }
+}
+
+template <int CMAX, bool FWD, bool BWD, bool EXACT>
+__global__ void __launch_bounds__(256)
+tail_pixel_kernel(const float* __restrict__ zl, const int32_t* __restrict__ labels, const float* __restrict__ pw,
+                  const float* __restrict__ nw, float eps, int N, int H, int W, int C, int f, float gscale,
+                  float* __restrict__ loss_sum, float* __restrict__ dzl, int nby, int nbx) {
+    extern __shared__ float sm[];
+#define DLV3P_TILE(F_)                                                                                              \
+    tail_pixel_tile<CMAX, FWD, BWD, EXACT, F_>(sm, zl, labels, pw, nw, eps, H, W, C, gscale, loss_sum, dzl, nby, nbx)
+    switch (f) {                                    // block-uniform; launch_tail_pixel admits 2 / 4 / 8 / 16 only
+    case 16: DLV3P_TILE(16); break;
+    case 8: DLV3P_TILE(8); break;
+    case 4: DLV3P_TILE(4); break;
+    default: DLV3P_TILE(2); break;
+    }
+#undef DLV3P_TILE
 }
 
 template <bool FWD, bool BWD>
@@ -436,7 +466,7 @@ static int launch_tail_pixel(const float* zl, const int32_t* labels, const float
 #define DLV3P_TAIL(CM)                                                                                             \
     do {                                                                                                           \
         constexpr int CS = (CM) | 1;                                                                               \
-        const int smem = (2 * PS * PS * CS + 96 + (BWD ? 256 * CS + 16 * S * 2 * CS : 0)) * 4;                     \
+        const int smem = (PS * PS * CS + 96 + (BWD ? 256 * CS + 16 * S * 2 * CS : 0)) * 4;                     \
         static int configured = 0;                                                                                 \
         if (smem > configured) {                                                                                   \
             cudaError_t e = cudaFuncSetAttribute(tail_pixel_kernel<CM, FWD, BWD, false>,                           \
