@@ -252,8 +252,8 @@ upsample_softmax_cbloss_kernel(const float* __restrict__ zl, const int32_t* __re
 // of 256 threads owns a 16x16 patch of output pixels aligned to the half-factor-shifted grid, i.e. S x S (S = 16/f)
 // sub-tiles whose pixels interpolate between the same 2x2 low-resolution logits.  The (S+1)^2 x C corner logits are
 // staged in shared memory; each thread keeps its pixel's C logits / probabilities in registers (softmax without any
-// shuffle), and the transposed-resize gradient is reduced separably through shared memory (over x, then over y) into
-// an (S+1)^2 x C accumulator that is flushed with one global RED per (corner, class).  Forward and backward share one
+// shuffle), and the transposed-resize gradient is reduced separably through shared memory (over x per sub-tile, then
+// over y by the corner that gathers its up-to-four sub-tiles) and leaves with one global RED per (corner, class).  Forward and backward share one
 // pass (`fwd_bwd`), so the softmax is evaluated once per pixel per step.
 // ex2 / lg2 without the denormal fix-up sequences of __expf / __logf (16 % of the kernel's issue slots were ISETP/BRA and
 // @p FMUL range handling, profiles/r1_tail_ncu.md); flushing denormal probabilities to zero is far below the loss's
