@@ -84,7 +84,7 @@ def scaling():
     if not sessions:
         return
     md = ["# Round 2 — data-parallel scaling and exchange variants\n",
-          "`torchrun --nproc-per-node N bench.py --gpus N [--exchange overlap|tail|peer] [--grad-dtype ...]`, 16 images per GPU "
+          "`torchrun --nproc-per-node N bench.py --gpus N [--exchange overlap|tail|peer|gather|none] [--grad-dtype ...]`, 16 images per GPU "
           "(weak scaling; BASELINE cfg-3's global batch 128 is exactly the N=8 line), CUDA events on the training stream, max "
           "over ranks.  Efficiency = img/s / (N x the 1-GPU img/s of the same session).\n",
           "| GPUs | config | exchange | img/s | ms/step | e2e img/s | efficiency | clocks / reasons |", "|---:|---|---|---:|---:|---:|---:|---|"]
