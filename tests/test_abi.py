@@ -53,3 +53,46 @@ def test_missing_library_is_loud(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError):
         _lib.load()
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: no module of the package may import / execute anything under oracle/ except
+    smoke.py (the checker of __graft_entry__.smoke()), and nothing in the package may read /root/reference."""
+    import ast
+
+    pkg = os.path.join(ROOT, "deeplabv3plus_keras_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith(".py"):
+                continue
+            path = os.path.join(dirpath, f)
+            src = open(path).read()
+            tree = ast.parse(src)
+            docs = {id(n.value) for n in ast.walk(tree) if isinstance(n, ast.Expr) and isinstance(n.value, ast.Constant)}
+            for node in ast.walk(tree):          # a path string in code (docstrings may cite the reference)
+                if isinstance(node, ast.Constant) and isinstance(node.value, str) and id(node) not in docs \
+                        and "/root/reference" in node.value:
+                    offenders.append((os.path.relpath(path, ROOT), "/root/reference"))
+            if f == "smoke.py":
+                continue
+            for node in ast.walk(tree):
+                mods = []
+                if isinstance(node, ast.Import):
+                    mods = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom) and node.level == 0:
+                    mods = [node.module or ""]
+                for m in mods:
+                    if m == "oracle" or m.startswith("oracle.") or m == "tests" or m.startswith("tests."):
+                        offenders.append((os.path.relpath(path, ROOT), m))
+    assert not offenders, offenders
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No CPU fallback: a missing libdlv3p.so is a RuntimeError at load time, not a silent eager path."""
+    from deeplabv3plus_keras_b200 import _lib
+
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "absent.so"))
+    monkeypatch.setattr(_lib, "_lib", None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()
